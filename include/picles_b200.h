@@ -1,0 +1,230 @@
+/*
+ * picles_b200.h — C ABI of the B200-native PiCLES per-timestep particle-in-cell path.
+ *
+ * The reference (mochell/PiCLES, pure Julia) has no FFI; the seam this library cuts
+ * is "everything `init_particles!` and `time_step!` do" (SURVEY.md §8b):
+ *
+ *   picles_seed   replaces  init_particles!          src/Simulations/run.jl:199-247
+ *                           SeedParticle             src/Operators/core_2D.jl:434-488
+ *   picles_step   replaces  State .= 0               src/Simulations/run.jl:75-79
+ *                           time_step!               src/Operators/TimeSteppers.jl:109-166
+ *                             advance!               src/Operators/mapping_2D.jl:118-243
+ *                             ParticleToNode!        src/Operators/mapping_2D.jl:59-73
+ *                             remesh!/NodeToParticle! src/Operators/mapping_2D.jl:250-356
+ *   picles_set_grid         grid.data / grid.stats   src/Grids/CartesianGrid.jl:26-136,
+ *                                                    src/Grids/TripolarGridMOM6.jl:288-459
+ *   picles_set_params       ODESettings/ODEParameters src/ParticleSystems/particle_waves_v5.jl:34-75,184-196
+ *                           WaveGrowth2D kwargs      src/Models/WaveGrowthModels2D.jl:194-345
+ *
+ * Conventions
+ *   - all entry points return 0 on success, a negative picles_status_t on failure;
+ *     picles_last_error() returns a message for the most recent failure on a handle.
+ *   - array arguments are caller-owned HOST pointers (column-major, i fastest,
+ *     Float64 / Int32 / UInt8) unless the name ends in `_dev`; they are copied during
+ *     the call.  Device memory is owned by the opaque handle.
+ *   - one handle = one GPU = one y-strip of the global grid (a single strip for 1 GPU).
+ *   - calls are synchronous unless stated, and a handle must be driven by one host
+ *     thread at a time.  No callbacks into the host language.
+ *   - per-particle integration failures are status codes (picles_get_particles),
+ *     not call failures — mirroring the reference's "push to FailedCollection and
+ *     carry on" (mapping_2D.jl:151-170).
+ *   - there is NO CPU fallback: every entry point that computes fails with
+ *     PICLES_ERR_CUDA when no sm_100-class device is usable.
+ */
+#ifndef PICLES_B200_H
+#define PICLES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PICLES_ABI_VERSION 1
+
+typedef struct picles_handle picles_t;
+
+typedef enum {
+    PICLES_OK = 0,
+    PICLES_ERR_ARG = -1,      /* bad argument / call order */
+    PICLES_ERR_CUDA = -2,     /* CUDA runtime error or no usable device */
+    PICLES_ERR_ALLOC = -3,    /* device allocation failed */
+    PICLES_ERR_HALO = -4,     /* particle reach exceeded the halo width */
+    PICLES_ERR_STATE = -5     /* grid/params/seed missing */
+} picles_status_t;
+
+/* axis boundary types: custom_structures.jl:51-61 */
+enum { PICLES_BND_NONPERIODIC = 0, PICLES_BND_PERIODIC = 1, PICLES_BND_TRIPOLAR_NORTH = 2 };
+/* total mask values: mask_utils.jl:26-30 */
+enum { PICLES_MASK_LAND = 0, PICLES_MASK_OCEAN = 1, PICLES_MASK_LAND_BOUNDARY = 2, PICLES_MASK_GRID_BOUNDARY = 3 };
+/* solver ids: ODESettings.solver (particle_waves_v5.jl:47) */
+enum { PICLES_SOLVER_TSIT5 = 0, PICLES_SOLVER_DP5 = 1 };
+
+/* per-particle status bits (picles_get_particles) */
+enum {
+    PICLES_PST_OK = 0,
+    PICLES_PST_MAXITERS = 1,      /* iter > maxiters: integrator stopped */
+    PICLES_PST_DTMIN = 2,         /* dt <= dtmin without force_dtmin */
+    PICLES_PST_UNSTABLE = 4,      /* NaN in u during integration */
+    PICLES_PST_NAN_RESET = 8,     /* advance!: NaN  -> reseed (mapping_2D.jl:196-209) */
+    PICLES_PST_INF_RESET = 16,    /* advance!: Inf  -> reseed (mapping_2D.jl:211-220) */
+    PICLES_PST_EMAX_CLAMP = 32    /* advance!: lne > log_energy_maximum (mapping_2D.jl:222-233) */
+};
+
+/* particle flag bits (picles_get_particles `flags`) */
+enum {
+    PICLES_PF_ON = 1,             /* ParticleInstance2D.on */
+    PICLES_PF_BOUNDARY = 2,       /* ParticleInstance2D.boundary */
+    PICLES_PF_DT_RESET = 4,       /* auto_dt_reset! pending (evaluated lazily at the next advance) */
+    PICLES_PF_ACTIVE = 8          /* member of ocean_points (iterated by time_step!) */
+};
+
+/*
+ * Flattened ODESettings + ODEParameters + WaveGrowth2D keyword arguments.
+ * The host language computes the derived constants exactly as the reference does
+ * (IDConstants / magic_fractions / e_T_func, particle_waves_v5.jl:87-128,271) and
+ * FetchRelations.MinimalState (FetchRelations.jl:412-415); the library never
+ * re-derives them, so oracle and device see identical inputs.
+ */
+typedef struct {
+    /* ODEParameters (particle_waves_v5.jl:184-196) */
+    double r_g;
+    double C_alpha;
+    double C_varphi;
+    double C_e;
+    double g;            /* carried for API parity; the RHS uses the 9.81 default of
+                            c_g_conversions_vector (particle_waves_v5.jl:281,504) */
+    /* particle_equations constants (particle_waves_v5.jl:393-394) */
+    double p;            /* magic_fractions(q)[1] */
+    double q;
+    double n;            /* magic_fractions(q)[3] */
+    double e_T;          /* e_T_func(γ,p,q,n; c_β,c_D,c_e,c_α) */
+    /* term switches of particle_equations (particle_waves_v5.jl:382-390) */
+    int32_t propagation;
+    int32_t input;
+    int32_t dissipation;
+    int32_t peak_shift;
+    int32_t direction;
+    /* ODESettings (particle_waves_v5.jl:34-75) */
+    int32_t solver;
+    double abstol;
+    double reltol;
+    double dt;           /* initial substep after seeding */
+    double dtmin;
+    double dtmax;        /* OrdinaryDiffEq default: tspan length = total_time */
+    int32_t force_dtmin;
+    int32_t adaptive;    /* must be 1 */
+    int64_t maxiters;
+    double log_energy_minimum;  /* carried; unused by the 2-D path (SURVEY B-7) */
+    double log_energy_maximum;
+    double wind_min_squared;
+    double seed_timescale;      /* ODESettings.timestep: fetch-law time scale at seeding (run.jl:223) */
+    /* WaveGrowth2D */
+    double minimal_state[2];    /* [E_min, |m|^2_min]  (WaveGrowthModels2D.jl:241-246) */
+    int32_t has_defaults;       /* 0: ODEinit_type == "wind_sea" (ODEdefaults === nothing) */
+    double defaults[5];         /* ParticleDefaults lne, c̄_x, c̄_y, x, y */
+    int32_t periodic_boundary;  /* the MODEL kwarg: selects ocean_points (WaveGrowthModels2D.jl:256-270) */
+    /* quirk switches */
+    int32_t on_persist;         /* 0: `on` frozen at seed (as the reference runs, B-1); 1: as intended */
+    int32_t reserved;
+} picles_params_t;
+
+/* per-step device counters (summed over this handle's strip) */
+typedef struct {
+    int64_t n_active;        /* particles iterated (|ocean_points| of this strip) */
+    int64_t n_integrated;    /* particles that took the step! branch */
+    int64_t n_substeps;      /* accepted RK substeps */
+    int64_t n_rejects;       /* rejected RK substeps */
+    int64_t n_rhs;           /* RHS evaluations (incl. fsal resets and dt resets) */
+    int64_t n_reseed_advance;/* off->on reseeds in advance! */
+    int64_t n_fixups;        /* NaN/Inf/e_max fix-ups in advance! */
+    int64_t n_failed;        /* maxiters / dtmin / unstable stops */
+    int64_t n_deposited;     /* particles projected onto the grid */
+    int64_t n_remesh_A;      /* node -> particle (enough energy) */
+    int64_t n_remesh_B;      /* wind-sea reseed (interior) */
+    int64_t n_remesh_C;      /* wind-sea reseed (boundary) */
+    int64_t n_remesh_D;      /* switched off */
+    int32_t reach;           /* max |node offset| of any deposit corner, in cells */
+    int32_t max_attempts;    /* max RK attempts of any particle this step */
+    double ms_advance;       /* CUDA-event times of the three kernels of the last step */
+    double ms_project;
+    double ms_remesh;
+} picles_counters_t;
+
+/* ---- lifecycle --------------------------------------------------------- */
+int picles_abi_version(void);
+/* device_id: CUDA ordinal.  Fails with PICLES_ERR_CUDA when no device is usable. */
+int picles_create(picles_t** h, int device_id);
+int picles_destroy(picles_t* h);
+const char* picles_last_error(picles_t* h);
+
+/* ---- setup ------------------------------------------------------------- */
+/*
+ * Global grid shape and boundary types plus this handle's y-strip.
+ *   Nx, Ny        global node counts            (grid.stats.Nx.N, grid.stats.Ny.N)
+ *   bx, by        PICLES_BND_*                  (typeof(grid.stats.Nx / Ny))
+ *   j0, ny_local  first global row (0-based) and row count owned by this handle
+ *   halo          rows of neighbour particle records kept on each side (0 for 1 strip)
+ *   mask          uint8 total mask of rows [j0-halo, j0+ny_local+halo) clipped/wrapped
+ *                 by the caller: (ny_local + 2*halo) * Nx values; halo rows outside a
+ *                 non-periodic domain are ignored
+ *   M             per-node projection kernel, 4 planes (M11,M12,M21,M22) of ny_local*Nx,
+ *                 or NULL with M_const != NULL for a uniform kernel (Cartesian)
+ *   pc_coef       great-circle coefficient per node (ny_local*Nx) or NULL (=0)
+ */
+int picles_set_grid(picles_t* h, int Nx, int Ny, int bx, int by,
+                    int j0, int ny_local, int halo,
+                    const uint8_t* mask, const double* M, const double* M_const,
+                    const double* pc_coef);
+int picles_set_params(picles_t* h, const picles_params_t* p);
+
+/* ---- the path ---------------------------------------------------------- */
+/* init_particles!: wind at t = 0 on this strip's nodes (ny_local*Nx each). */
+int picles_seed(picles_t* h, const double* u0, const double* v0);
+
+/*
+ * One model step on this strip:  State .= 0 ; advance! ; ParticleToNode! ; remesh!.
+ * u_t/v_t: wind at the pre-step clock time t, u_t1/v_t1 at t+dt_model (ny_local*Nx
+ * each, host).  Any of them may be NULL to reuse what is already on the device
+ * (u_t NULL: the previous step's t1 level becomes this step's t level).
+ * Single-strip handles run the whole step; multi-strip handles must use the
+ * phase-split calls below so the host can exchange halos in between.
+ */
+int picles_step(picles_t* h, double t, double dt_model,
+                const double* u_t, const double* v_t,
+                const double* u_t1, const double* v_t1);
+
+/* Phase-split form of picles_step (same arithmetic):                          */
+int picles_upload_winds(picles_t* h, const double* u_t, const double* v_t,
+                        const double* u_t1, const double* v_t1);
+int picles_step_advance(picles_t* h, double t, double dt_model);   /* async on the handle's stream */
+/* device pointers + byte count of the packed halo rows to send to / receive from the
+   lower (j0-1) and upper (j0+ny_local) neighbour; valid after picles_step_advance */
+int picles_halo_buffers(picles_t* h, void** send_lo_dev, void** send_hi_dev,
+                        void** recv_lo_dev, void** recv_hi_dev, int64_t* nbytes);
+int picles_halo_pack(picles_t* h);     /* records -> send buffers (async) */
+int picles_halo_unpack(picles_t* h);   /* recv buffers -> halo rows (async) */
+int picles_step_project_remesh(picles_t* h, double t, double dt_model);
+int picles_synchronize(picles_t* h);
+/* reach (cells) of the last advance on this strip; the caller all-reduces(max) it */
+int picles_get_reach(picles_t* h, int32_t* reach);
+
+/* ---- state access ------------------------------------------------------ */
+int picles_get_state(picles_t* h, double* S /* ny_local*Nx*3: planes e, m_x, m_y */);
+int picles_set_state(picles_t* h, const double* S);
+int picles_get_particles(picles_t* h, double* z /* 5 planes of ny_local*Nx */,
+                         double* t, double* dt, uint8_t* flags, int32_t* status);
+int picles_get_counters(picles_t* h, picles_counters_t* c);
+/* sum over this strip of State[:,:,0] (mean_of_state, run.jl:23-25, times n) — a cheap
+   per-step scalar read-back */
+int picles_state_energy_sum(picles_t* h, double* sum_e);
+
+/* device pointers for zero-copy consumers (torch / CUDA.jl): planes as above */
+int picles_state_dev(picles_t* h, double** S_dev);
+int picles_wind_dev(picles_t* h, double** u_t_dev, double** v_t_dev,
+                    double** u_t1_dev, double** v_t1_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PICLES_B200_H */
