@@ -220,9 +220,33 @@ int picles_get_counters(picles_t* h, picles_counters_t* c);
 int picles_state_energy_sum(picles_t* h, double* sum_e);
 
 /* device pointers for zero-copy consumers (torch / CUDA.jl): planes as above */
-int picles_state_dev(picles_t* h, double** S_dev);
+int picles_state_dev(picles_t* h, double** S_dev /* out: 3 plane pointers e, m_x, m_y */);
 int picles_wind_dev(picles_t* h, double** u_t_dev, double** v_t_dev,
                     double** u_t1_dev, double** v_t1_dev);
+
+/* ---- options -------------------------------------------------------------- */
+enum {
+    /* 0 (default): the step starts from State == 0, as run! does (run.jl:75-79).
+       1: a bare time_step! on whatever State holds — deposits are added to the current
+          node values in the reference's order (ParticleInCell.jl:372), as the scripts
+          that call time_step! directly do (tests/T03_PIC_tripolar_aqua.jl:216-225). */
+    PICLES_OPT_ACCUMULATE_STATE = 1
+};
+int picles_set_option(picles_t* h, int option, int value);
+/* State .= 0 */
+int picles_zero_state(picles_t* h);
+
+/* ---- utilities for hosts without their own CUDA binding ------------------ */
+/* async device-to-device copy on the handle's stream (same GPU or a peer) */
+int picles_copy_dev(picles_t* h, void* dst_dev, const void* src_dev, int64_t nbytes);
+/* CUDA-event stopwatch on the handle's stream: start; ...calls...; stop -> milliseconds */
+int picles_timer_start(picles_t* h);
+int picles_timer_stop(picles_t* h, double* ms);
+/* measured FP64 FMA throughput of this device (register-resident DFMA chains), the
+   roofline denominator of the advance kernel; ~50 ms */
+int picles_measure_fp64_peak(picles_t* h, double* tflops);
+/* measured HBM copy bandwidth (read+write bytes / s) over a buffer of `mib` MiB */
+int picles_measure_hbm_copy(picles_t* h, int mib, double* gbs);
 
 #ifdef __cplusplus
 }

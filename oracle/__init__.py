@@ -50,6 +50,7 @@ def load(variant: str = "default"):
     lib.oracle_create.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(PiclesParams)]
     lib.oracle_destroy.argtypes = [vp]
     lib.oracle_set_threads.argtypes = [vp, i32]
+    lib.oracle_set_accumulate.argtypes = [vp, i32]
     lib.oracle_seed.argtypes = [vp, vp, vp]
     lib.oracle_step.argtypes = [vp, d, d, vp, vp, vp, vp]
     lib.oracle_get_state.argtypes = [vp, vp]
@@ -119,6 +120,9 @@ class Oracle:
                 self.h = None
         except Exception:
             pass
+
+    def set_accumulate(self, on):
+        self.lib.oracle_set_accumulate(self.h, int(bool(on)))
 
     def seed(self, u0, v0):
         u0 = _f64(np.broadcast_to(u0, (self.Ny, self.Nx)))

@@ -96,6 +96,7 @@ typedef struct oracle {
     picles_counters_t C;
     int64_t stiff_triggers; /* times AutoTsit5 would have switched */
     int nthreads;
+    int accumulate; /* 0: State .= 0 before the step (run!); 1: bare time_step! */
 } oracle_t;
 
 /* ------------------------------------------------------------------------ */
@@ -589,6 +590,7 @@ void oracle_destroy(oracle_t* o) {
 }
 
 void oracle_set_threads(oracle_t* o, int n) { o->nthreads = n < 1 ? 1 : n; }
+void oracle_set_accumulate(oracle_t* o, int on) { o->accumulate = on ? 1 : 0; }
 
 /* init_particles! / SeedParticle, run.jl:199-247, core_2D.jl:434-488 */
 void oracle_seed(oracle_t* o, const double* u0, const double* v0) {
@@ -713,7 +715,7 @@ void oracle_step(oracle_t* o, double t, double DT, const double* u_t, const doub
                  const double* u_t1, const double* v_t1) {
     (void)t;
     int64_t n = (int64_t)o->Nx * o->Ny;
-    memset(o->S, 0, 3 * n * sizeof(double));
+    if (!o->accumulate) memset(o->S, 0, 3 * n * sizeof(double)); /* run.jl:75-79 */
     picles_counters_t C;
     memset(&C, 0, sizeof C);
     C.n_active = o->n_ocean;

@@ -22,6 +22,8 @@ PST_OK, PST_MAXITERS, PST_DTMIN, PST_UNSTABLE = 0, 1, 2, 4
 PST_NAN_RESET, PST_INF_RESET, PST_EMAX_CLAMP = 8, 16, 32
 PF_ON, PF_BOUNDARY, PF_DT_RESET, PF_ACTIVE = 1, 2, 4, 8
 
+OPT_ACCUMULATE_STATE = 1
+
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_ALLOC", -4: "ERR_HALO", -5: "ERR_STATE"}
 
 
@@ -124,6 +126,13 @@ SYMBOLS = {
     "picles_state_energy_sum": (C.c_int, [_vp, _dp]),
     "picles_state_dev": (C.c_int, [_vp, C.POINTER(_vp)]),
     "picles_wind_dev": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "picles_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "picles_zero_state": (C.c_int, [_vp]),
+    "picles_copy_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
+    "picles_timer_start": (C.c_int, [_vp]),
+    "picles_timer_stop": (C.c_int, [_vp, _dp]),
+    "picles_measure_fp64_peak": (C.c_int, [_vp, _dp]),
+    "picles_measure_hbm_copy": (C.c_int, [_vp, C.c_int, _dp]),
 }
 
 _lib = None

@@ -1,0 +1,752 @@
+/*
+ * physics.h — per-particle arithmetic of the PiCLES particle-in-cell step, written for
+ * the sm_100a kernels (registers only, no arrays of stage derivatives for the
+ * propagation components, explicit fused multiply-adds).
+ *
+ * Every function is `__host__ __device__` so that tests/ can compile this header with
+ * g++ and compare it bit-for-bit with the CPU oracle before any GPU time is spent;
+ * the product itself only ever calls these from kernels (there is no CPU path).
+ *
+ * Build rules: device code with --fmad=false, host code with -ffp-contract=off.  All
+ * contractions are written out with fma(), all transcendentals come from pmath.h, so
+ * host and device agree bit-for-bit and accept/reject decisions of the adaptive
+ * controller cannot flip.
+ *
+ * Reference call sites (paths relative to /root/reference/src):
+ *   rhs3 / prop      ParticleSystems/particle_waves_v5.jl:479-556
+ *   integrate        Operators/mapping_2D.jl:152  step!(integ, DT, true)  [OrdinaryDiffEq Tsit5/DP5]
+ *   initdt           Operators/mapping_2D.jl:95,103,110 auto_dt_reset!     [OrdinaryDiffEq initdt]
+ *   windsea          FetchRelations.jl:314-359
+ *   charge / vertex  Operators/core_2D.jl:69-78, 121-128
+ *   weights_1d       ParticleInCell.jl:58-71
+ *   corner_target    ParticleInCell.jl:341-376, 409-428, 444-466
+ *   advance_particle Operators/mapping_2D.jl:118-243
+ *   remesh_particle  Operators/mapping_2D.jl:250-356
+ */
+#ifndef PICLES_PHYSICS_H
+#define PICLES_PHYSICS_H
+
+#include "../../include/picles_b200.h"
+#include "pmath.h"
+
+#define PH_QOLDINIT 1e-4
+#define PH_CELL_INVALID ((int32_t)-1)
+#define PH_CELL_BIAS 8192
+#define PH_REACH_MAX 15
+
+namespace picles {
+
+/* ---- tableaus (OrdinaryDiffEq Tsit5ConstantCache / DP5ConstantCache) ----- */
+struct Tsit5Tab {
+    static constexpr double c1 = 0.161, c2 = 0.327, c3 = 0.9, c4 = 0.9800255409045097;
+    static constexpr double a21 = 0.161;
+    static constexpr double a31 = -0.008480655492356989, a32 = 0.335480655492357;
+    static constexpr double a41 = 2.8971530571054935, a42 = -6.359448489975075, a43 = 4.3622954328695815;
+    static constexpr double a51 = 5.325864828439257, a52 = -11.748883564062828, a53 = 7.4955393428898365,
+                            a54 = -0.09249506636175525;
+    static constexpr double a61 = 5.86145544294642, a62 = -12.92096931784711, a63 = 8.159367898576159,
+                            a64 = -0.071584973281401, a65 = -0.028269050394068383;
+    static constexpr double a71 = 0.09646076681806523, a72 = 0.01, a73 = 0.4798896504144996,
+                            a74 = 1.379008574103742, a75 = -3.290069515436081, a76 = 2.324710524099774;
+    static constexpr double bt1 = -0.00178001105222577714, bt2 = -0.0008164344596567469,
+                            bt3 = 0.007880878010261995, bt4 = -0.1447110071732629, bt5 = 0.5823571654525552,
+                            bt6 = -0.45808210592918697, bt7 = 0.015151515151515152;
+    static constexpr double beta1 = 0.14, beta2 = 0.08;
+};
+struct DP5Tab {
+    static constexpr double c1 = 0.2, c2 = 0.3, c3 = 0.8, c4 = 8.0 / 9.0;
+    static constexpr double a21 = 0.2;
+    static constexpr double a31 = 3.0 / 40.0, a32 = 9.0 / 40.0;
+    static constexpr double a41 = 44.0 / 45.0, a42 = -56.0 / 15.0, a43 = 32.0 / 9.0;
+    static constexpr double a51 = 19372.0 / 6561.0, a52 = -25360.0 / 2187.0, a53 = 64448.0 / 6561.0,
+                            a54 = -212.0 / 729.0;
+    static constexpr double a61 = 9017.0 / 3168.0, a62 = -355.0 / 33.0, a63 = 46732.0 / 5247.0,
+                            a64 = 49.0 / 176.0, a65 = -5103.0 / 18656.0;
+    static constexpr double a71 = 35.0 / 384.0, a72 = 0.0, a73 = 500.0 / 1113.0, a74 = 125.0 / 192.0,
+                            a75 = -2187.0 / 6784.0, a76 = 11.0 / 84.0;
+    static constexpr double bt1 = -71.0 / 57600.0, bt2 = 0.0, bt3 = 71.0 / 16695.0, bt4 = -71.0 / 1920.0,
+                            bt5 = 17253.0 / 339200.0, bt6 = -22.0 / 525.0, bt7 = 1.0 / 40.0;
+    static constexpr double beta1 = 0.17, beta2 = 0.04;
+};
+
+/* per-thread view of one particle (ODEIntegrator fields that survive between steps) */
+struct Particle {
+    double u0, u1, u2, u3, u4; /* lne, c̄_x, c̄_y, x, y */
+    double t, dt, qold;
+    int32_t iter;
+    uint8_t flags;  /* PICLES_PF_* */
+    uint8_t status; /* PICLES_PST_* */
+};
+
+/* wind at the home node: level t and the increment to level t+DT */
+struct Wind {
+    double u0, v0, du, dv;
+    double t_start, inv_DT;
+};
+
+/* per-thread counter deltas */
+struct Tally {
+    int32_t integrated, substeps, rejects, rhs, reseed, fixups, failed, deposited, A, B, C, D;
+    int32_t reach, max_attempts;
+};
+PM_HD void tally_zero(Tally& c) {
+    c.integrated = c.substeps = c.rejects = c.rhs = c.reseed = c.fixups = c.failed = c.deposited = 0;
+    c.A = c.B = c.C = c.D = 0;
+    c.reach = 0;
+    c.max_attempts = 0;
+}
+
+/* deposit record written by the advance kernel and read by the projection gather */
+struct Record {
+    double e, mx, my; /* GetParticleEnergyMomentum */
+    double wxc, wyc;  /* ceil-side weights; floor-side = 1 - w */
+    int32_t cell;     /* packed floor offsets + class, or PH_CELL_INVALID */
+};
+
+/* ---- FetchRelations.get_initial_windsea(...; particle_state=true) ---------- */
+PM_HD void windsea(double U10, double V10, double time_scale, double& lne, double& cgx, double& cgy) {
+    double U_amp = sqrt(U10 * U10 + V10 * V10);
+    U_amp = (U_amp < 0.1) ? 0.1 : U_amp;
+    time_scale = fabs(time_scale);
+    double tau = 9.81 * time_scale / fabs(U_amp);
+    double X_tilde = pm_pow(tau / (22.8013 * 2.4097), 1.0 / (1.0 - 0.2748));
+    double f_m = 3.5 * (9.81 / U_amp) * pm_pow(X_tilde, -0.33);
+    double a_j = 0.033 * pm_pow(f_m * U_amp / 9.81, 0.67);
+    double w = f_m * 2.0 * 3.141592653589793;
+    double iw = 1.0 / w;
+    double iw2 = iw * iw;
+    double E = 0.31 * (9.81 * 9.81) * a_j * (iw2 * iw2);
+    double f_peak = f_m * 9.81 / U_amp;
+    double T_bar = 0.9 * (1.0 / f_peak);
+    double cg_amp = 9.81 * T_bar / (4.0 * 3.141592653589793);
+    cgx = cg_amp * U10 / U_amp;
+    cgy = cg_amp * V10 / U_amp;
+    lne = pm_log(E);
+}
+
+/* MinimalParticle(U,V,T): fetch law at unit wind speed, rand_sign() fixed to +1 */
+PM_HD void minimal_particle(double U10, double V10, double T, double& lne, double& cgx, double& cgy) {
+    if (U10 == 0.0) U10 = 1.0;
+    if (V10 == 0.0) V10 = 1.0;
+    double Uamp = sqrt(U10 * U10 + V10 * V10);
+    double a = 1.0 * U10 / Uamp, b = 1.0 * V10 / Uamp;
+    windsea(a, b, T, lne, cgx, cgy);
+}
+
+/* ResetParticleValues(defaults, (0,0), wind, DT) */
+PM_HD void reset_particle_values(const picles_params_t& P, double wu, double wv, double DT, Particle& p) {
+    if (!P.has_defaults) {
+        windsea(wu, wv, DT, p.u0, p.u1, p.u2);
+    } else {
+        p.u0 = P.defaults[0];
+        p.u1 = P.defaults[1];
+        p.u2 = P.defaults[2];
+    }
+    p.u3 = 0.0;
+    p.u4 = 0.0;
+}
+
+/* GetParticleEnergyMomentum */
+PM_HD void charge(double lne, double cx, double cy, double& e, double& mx, double& my) {
+    e = pm_exp(lne);
+    double cs = sqrt(cx * cx + cy * cy);
+    mx = cx * e / (cs * cs) / 2.0;
+    my = cy * e / (cs * cs) / 2.0;
+}
+
+/* GetVariablesAtVertex(state, 0, 0) */
+PM_HD void vertex(double e, double mx, double my, Particle& p) {
+    double m_amp = sqrt(mx * mx + my * my);
+    p.u0 = pm_log(e);
+    p.u1 = mx * e / (2.0 * (m_amp * m_amp));
+    p.u2 = my * e / (2.0 * (m_amp * m_amp));
+    p.u3 = 0.0;
+    p.u4 = 0.0;
+}
+
+/* ---- right-hand side: components lne, c̄_x, c̄_y --------------------------- */
+PM_HD double alpha_func(double us, double cgp) {
+    double a = us / (2.0 * cgp);
+    return (a > 500.0) ? 500.0 : a;
+}
+
+PM_HD void rhs3(const picles_params_t& P, double lne, double cx, double cy, double u, double v, double pc,
+                double& d0, double& d1, double& d2) {
+    double r_g = P.r_g;
+    double cbar = sqrt(cx * cx + cy * cy);
+    double us = sqrt(u * u + v * v);
+    double c_gp = fabs(cbar) / r_g;
+    double kp = 9.81 / (4.0 * pm_max(c_gp * c_gp, 1e-2));
+    double wp = 9.81 / (2.0 * pm_max(fabs(c_gp), 0.1));
+    double gx = cx / r_g, gy = cy / r_g;
+    double alpha = alpha_func(us, c_gp);
+    double sg = sqrt(gx * gx + gy * gy);
+    double msg = pm_max(sg, 1e-4);
+    double alpha_p = (u * gx + v * gy) / (2.0 * (msg * msg));
+    double Hp = 0.5 * (1.0 + pm_tanh(P.p * (alpha_p - 0.85)));
+    double sch = pm_sech(10.0 * (alpha_p - 0.85));
+    double Dp = 1.0 - 1.25 * (sch * sch);
+    double It = 0.0, Dt = 0.0, Scg = 0.0, Sdir = 0.0;
+    if (P.input) It = P.C_e * Hp * (alpha * alpha);
+    if (P.dissipation) {
+        double r = kp / P.e_T, pw;
+        double twon = 2.0 * P.n;
+        if (twon == 4.0) {
+            double r2 = r * r;
+            pw = r2 * r2;
+        } else if (twon == 2.0) {
+            pw = r * r;
+        } else {
+            pw = pm_pow(r, twon);
+        }
+        Dt = pm_exp(P.n * lne) * pw;
+    }
+    if (P.peak_shift) {
+        double k2 = kp * kp;
+        Scg = P.C_alpha * Dp * (k2 * k2) * pm_exp(2.0 * lne);
+    }
+    if (P.direction) {
+        double a2 = alpha_func(us, sg);
+        double prod = us * sg;
+        double s2 = 0.0;
+        if (!(prod == 0.0)) {
+            s2 = (2.0 / (prod * prod)) *
+                 (u * v * (2.0 * (gy * gy) - sg * sg) - gx * gy * (2.0 * (v * v) - us * us));
+        }
+        Sdir = a2 * a2 * P.C_varphi * Hp * s2;
+    }
+    double Ssph = cx * pc;
+    d0 = wp * r_g * Scg + wp * (It - Dt);
+    d1 = -cx * wp * r_g * Scg + cy * Sdir + cy * Ssph;
+    d2 = -cy * wp * r_g * Scg - cx * Sdir - cx * Ssph;
+}
+
+/* propagation components: [dz4, dz5] = M * [c̄_x, c̄_y] */
+PM_HD void prop(const picles_params_t& P, const double* M, double cx, double cy, double& d3, double& d4) {
+    if (P.propagation) {
+        d3 = M[0] * cx + M[1] * cy;
+        d4 = M[2] * cx + M[3] * cy;
+    } else {
+        d3 = 0.0;
+        d4 = 0.0;
+    }
+}
+
+/* wind at stage time ts (linear between the two staged levels) + rhs3 */
+PM_HD void f3(const picles_params_t& P, const Wind& w, double pc, double lne, double cx, double cy, double ts,
+              double& d0, double& d1, double& d2) {
+    double s = (ts - w.t_start) * w.inv_DT;
+    double u = fma(w.du, s, w.u0);
+    double v = fma(w.dv, s, w.v0);
+    rhs3(P, lne, cx, cy, u, v, pc, d0, d1, d2);
+}
+
+PM_HD double rms5(double a, double b, double c, double d, double e) {
+    double s = 0.0;
+    s += a * a;
+    s += b * b;
+    s += c * c;
+    s += d * d;
+    s += e * e;
+    return sqrt(s / 5.0);
+}
+
+/* ode_determine_initdt (Hairer); f0 = f(u,t) supplied as (k0..k4) */
+PM_HD double initdt(const picles_params_t& P, const Wind& w, const double* M, double pc, const Particle& p,
+                    double k0, double k1, double k2, double k3, double k4, int32_t& nrhs) {
+    double dtmin = pm_nextfloat_pos(P.dtmin);
+    const double smalldt = 1e-6;
+    double s0 = fma(fabs(p.u0), P.reltol, P.abstol);
+    double s1 = fma(fabs(p.u1), P.reltol, P.abstol);
+    double s2 = fma(fabs(p.u2), P.reltol, P.abstol);
+    double s3 = fma(fabs(p.u3), P.reltol, P.abstol);
+    double s4 = fma(fabs(p.u4), P.reltol, P.abstol);
+    double d0 = rms5(p.u0 / s0, p.u1 / s1, p.u2 / s2, p.u3 / s3, p.u4 / s4);
+    double d1 = rms5(k0 / s0, k1 / s1, k2 / s2, k3 / s3, k4 / s4);
+    if (d1 != d1) return dtmin;
+    double dt0 = ((d0 < 1e-5) | (d1 < 1e-5)) ? smalldt : (d0 / d1) / 100.0;
+    dt0 = pm_min(dt0, P.dtmax);
+    if (dt0 < 10.0 * 2.220446049250313e-16) return pm_max(smalldt, dtmin);
+    double a0 = fma(dt0, k0, p.u0);
+    double a1 = fma(dt0, k1, p.u1);
+    double a2 = fma(dt0, k2, p.u2);
+    double f0, f1, f2, f3x, f4x;
+    f3(P, w, pc, a0, a1, a2, p.t + dt0, f0, f1, f2);
+    prop(P, M, a1, a2, f3x, f4x);
+    nrhs++;
+    int same = (k0 == f0) & (k1 == f1) & (k2 == f2) & (k3 == f3x) & (k4 == f4x);
+    if (same) return pm_max(dtmin, 100.0 * dt0);
+    double d2 = rms5((f0 - k0) / s0, (f1 - k1) / s1, (f2 - k2) / s2, (f3x - k3) / s3, (f4x - k4) / s4) / dt0;
+    double mx = pm_max(d1, d2);
+    double dt1;
+    if (mx <= 1e-15) dt1 = pm_max(1e-6, dt0 * 1e-3);
+    else dt1 = pm_exp10(-(2.0 + pm_log10(mx)) / 5.0);
+    return pm_max(dtmin, pm_min(pm_min(100.0 * dt0, dt1), P.dtmax));
+}
+
+/* one 3-component stage argument: uprev + dt*(sum a_j k_j) with the fma chain of the spec */
+#define PH_STAGE3(out, U, expr_inner) out = fma(dt, (expr_inner), U)
+
+/* step!(integrator, DT, true): advance particle p from p.t to p.t + DT */
+template <class T>
+PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, double pc, double DT, Particle& p,
+                     Tally& c) {
+    if (p.status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE)) return;
+    double t = p.t;
+    const double tstop = t + DT;
+    double u0 = p.u0, u1 = p.u1, u2 = p.u2, u3 = p.u3, u4 = p.u4;
+    int32_t nrhs = 0;
+    /* u_modified -> reset_fsal!: k1 = f(u, t) */
+    double k10, k11, k12;
+    f3(P, w, pc, u0, u1, u2, t, k10, k11, k12);
+    nrhs++;
+    double dt = p.dt;
+    if (p.flags & PICLES_PF_DT_RESET) {
+        double k13, k14;
+        prop(P, M, u1, u2, k13, k14);
+        dt = initdt(P, w, M, pc, p, k10, k11, k12, k13, k14, nrhs);
+        p.flags &= (uint8_t)~PICLES_PF_DT_RESET;
+    }
+    double qold = p.qold;
+    int32_t iter = p.iter;
+    int32_t attempts = 0;
+    const double qmin = 0.2, qmax = 10.0, gamma = 0.9;
+    while (t < tstop) {
+        /* loopheader!: fix_dt_at_bounds!, modify_dt_for_tstops! */
+        iter++;
+        double dtmin_t = pm_max(pm_eps(t), P.dtmin);
+        dt = pm_min(P.dtmax, dt);
+        dt = pm_max(dt, dtmin_t);
+        dt = pm_min(dt, tstop - t);
+        /* check_error! */
+        if (dt != dt) { p.status |= PICLES_PST_UNSTABLE; c.failed++; break; }
+        if ((int64_t)iter > P.maxiters) { p.status |= PICLES_PST_MAXITERS; c.failed++; break; }
+        if (!P.force_dtmin && dt <= P.dtmin && (t + dt < tstop)) { p.status |= PICLES_PST_DTMIN; c.failed++; break; }
+        attempts++;
+
+        /* perform_step!; propagation derivatives k_j[3:4] = M*c̄_j are folded into the
+           running sums of stage 7 (x7,y7) and of the error estimate (xe,ye) as each k_j
+           appears — the same fma chain as storing them, without the registers */
+        double kx, ky;
+        prop(P, M, u1, u2, kx, ky);
+        double x7 = T::a71 * kx, y7 = T::a71 * ky;
+        double xe = T::bt1 * kx, ye = T::bt1 * ky;
+        double a0, a1, a2; /* stage argument */
+        double k20, k21, k22, k30, k31, k32, k40, k41, k42, k50, k51, k52, k60, k61, k62, k70, k71, k72;
+        {
+            double a = dt * T::a21;
+            a0 = fma(a, k10, u0); a1 = fma(a, k11, u1); a2 = fma(a, k12, u2);
+            f3(P, w, pc, a0, a1, a2, fma(T::c1, dt, t), k20, k21, k22);
+            prop(P, M, a1, a2, kx, ky);
+            if (T::a72 != 0.0) { x7 = fma(T::a72, kx, x7); y7 = fma(T::a72, ky, y7); }
+            if (T::bt2 != 0.0) { xe = fma(T::bt2, kx, xe); ye = fma(T::bt2, ky, ye); }
+        }
+        {
+            PH_STAGE3(a0, u0, fma(T::a32, k20, T::a31 * k10));
+            PH_STAGE3(a1, u1, fma(T::a32, k21, T::a31 * k11));
+            PH_STAGE3(a2, u2, fma(T::a32, k22, T::a31 * k12));
+            f3(P, w, pc, a0, a1, a2, fma(T::c2, dt, t), k30, k31, k32);
+            prop(P, M, a1, a2, kx, ky);
+            x7 = fma(T::a73, kx, x7); y7 = fma(T::a73, ky, y7);
+            xe = fma(T::bt3, kx, xe); ye = fma(T::bt3, ky, ye);
+        }
+        {
+            PH_STAGE3(a0, u0, fma(T::a43, k30, fma(T::a42, k20, T::a41 * k10)));
+            PH_STAGE3(a1, u1, fma(T::a43, k31, fma(T::a42, k21, T::a41 * k11)));
+            PH_STAGE3(a2, u2, fma(T::a43, k32, fma(T::a42, k22, T::a41 * k12)));
+            f3(P, w, pc, a0, a1, a2, fma(T::c3, dt, t), k40, k41, k42);
+            prop(P, M, a1, a2, kx, ky);
+            x7 = fma(T::a74, kx, x7); y7 = fma(T::a74, ky, y7);
+            xe = fma(T::bt4, kx, xe); ye = fma(T::bt4, ky, ye);
+        }
+        {
+            PH_STAGE3(a0, u0, fma(T::a54, k40, fma(T::a53, k30, fma(T::a52, k20, T::a51 * k10))));
+            PH_STAGE3(a1, u1, fma(T::a54, k41, fma(T::a53, k31, fma(T::a52, k21, T::a51 * k11))));
+            PH_STAGE3(a2, u2, fma(T::a54, k42, fma(T::a53, k32, fma(T::a52, k22, T::a51 * k12))));
+            f3(P, w, pc, a0, a1, a2, fma(T::c4, dt, t), k50, k51, k52);
+            prop(P, M, a1, a2, kx, ky);
+            x7 = fma(T::a75, kx, x7); y7 = fma(T::a75, ky, y7);
+            xe = fma(T::bt5, kx, xe); ye = fma(T::bt5, ky, ye);
+        }
+        {
+            PH_STAGE3(a0, u0, fma(T::a65, k50, fma(T::a64, k40, fma(T::a63, k30, fma(T::a62, k20, T::a61 * k10)))));
+            PH_STAGE3(a1, u1, fma(T::a65, k51, fma(T::a64, k41, fma(T::a63, k31, fma(T::a62, k21, T::a61 * k11)))));
+            PH_STAGE3(a2, u2, fma(T::a65, k52, fma(T::a64, k42, fma(T::a63, k32, fma(T::a62, k22, T::a61 * k12)))));
+            f3(P, w, pc, a0, a1, a2, t + dt, k60, k61, k62);
+            prop(P, M, a1, a2, kx, ky);
+            x7 = fma(T::a76, kx, x7); y7 = fma(T::a76, ky, y7);
+            xe = fma(T::bt6, kx, xe); ye = fma(T::bt6, ky, ye);
+        }
+        double n0, n1, n2, n3, n4; /* u_new */
+        {
+            double i0 = T::a71 * k10, i1 = T::a71 * k11, i2 = T::a71 * k12;
+            if (T::a72 != 0.0) { i0 = fma(T::a72, k20, i0); i1 = fma(T::a72, k21, i1); i2 = fma(T::a72, k22, i2); }
+            i0 = fma(T::a73, k30, i0); i1 = fma(T::a73, k31, i1); i2 = fma(T::a73, k32, i2);
+            i0 = fma(T::a74, k40, i0); i1 = fma(T::a74, k41, i1); i2 = fma(T::a74, k42, i2);
+            i0 = fma(T::a75, k50, i0); i1 = fma(T::a75, k51, i1); i2 = fma(T::a75, k52, i2);
+            i0 = fma(T::a76, k60, i0); i1 = fma(T::a76, k61, i1); i2 = fma(T::a76, k62, i2);
+            n0 = fma(dt, i0, u0); n1 = fma(dt, i1, u1); n2 = fma(dt, i2, u2);
+            n3 = fma(dt, x7, u3); n4 = fma(dt, y7, u4);
+            f3(P, w, pc, n0, n1, n2, t + dt, k70, k71, k72);
+            prop(P, M, n1, n2, kx, ky);
+            xe = fma(T::bt7, kx, xe); ye = fma(T::bt7, ky, ye);
+        }
+        nrhs += 6;
+        /* error estimate: utilde = dt*sum(btilde_j k_j); calculate_residuals; RMS norm */
+        double EEst;
+        {
+            double e0 = T::bt1 * k10, e1 = T::bt1 * k11, e2 = T::bt1 * k12;
+            if (T::bt2 != 0.0) { e0 = fma(T::bt2, k20, e0); e1 = fma(T::bt2, k21, e1); e2 = fma(T::bt2, k22, e2); }
+            e0 = fma(T::bt3, k30, e0); e1 = fma(T::bt3, k31, e1); e2 = fma(T::bt3, k32, e2);
+            e0 = fma(T::bt4, k40, e0); e1 = fma(T::bt4, k41, e1); e2 = fma(T::bt4, k42, e2);
+            e0 = fma(T::bt5, k50, e0); e1 = fma(T::bt5, k51, e1); e2 = fma(T::bt5, k52, e2);
+            e0 = fma(T::bt6, k60, e0); e1 = fma(T::bt6, k61, e1); e2 = fma(T::bt6, k62, e2);
+            e0 = fma(T::bt7, k70, e0); e1 = fma(T::bt7, k71, e1); e2 = fma(T::bt7, k72, e2);
+            double r0 = (dt * e0) / fma(pm_max(fabs(u0), fabs(n0)), P.reltol, P.abstol);
+            double r1 = (dt * e1) / fma(pm_max(fabs(u1), fabs(n1)), P.reltol, P.abstol);
+            double r2 = (dt * e2) / fma(pm_max(fabs(u2), fabs(n2)), P.reltol, P.abstol);
+            double r3 = (dt * xe) / fma(pm_max(fabs(u3), fabs(n3)), P.reltol, P.abstol);
+            double r4 = (dt * ye) / fma(pm_max(fabs(u4), fabs(n4)), P.reltol, P.abstol);
+            EEst = rms5(r0, r1, r2, r3, r4);
+        }
+        /* stepsize_controller! (PIController) */
+        double q, q11 = 1.0;
+        if (EEst == 0.0) {
+            q = 1.0 / qmax;
+        } else {
+            q11 = pm_pow(EEst, T::beta1);
+            q = q11 / pm_pow(qold, T::beta2);
+            q = pm_max(1.0 / qmax, pm_min(1.0 / qmin, q / gamma));
+        }
+        bool accept = (EEst <= 1.0) || (P.force_dtmin && fabs(dt) <= dtmin_t);
+        if (accept) {
+            qold = pm_max(EEst, PH_QOLDINIT);
+            double dtnew = dt / q;
+            double ttmp = t + dt;
+            t = (fabs(ttmp - tstop) < 100.0 * pm_eps(tstop)) ? tstop : ttmp;
+            double dtp = pm_min(P.dtmax, dtnew);
+            dtp = pm_max(dtp, pm_max(pm_eps(t), P.dtmin));
+            dt = dtp;
+            u0 = n0; u1 = n1; u2 = n2; u3 = n3; u4 = n4;
+            k10 = k70; k11 = k71; k12 = k72; /* FSAL */
+            c.substeps++;
+            if ((u0 != u0) | (u1 != u1) | (u2 != u2) | (u3 != u3) | (u4 != u4)) {
+                p.status |= PICLES_PST_UNSTABLE; c.failed++; break;
+            }
+        } else {
+            dt = dt / pm_min(1.0 / qmin, q11 / gamma);
+            c.rejects++;
+        }
+    }
+    p.u0 = u0; p.u1 = u1; p.u2 = u2; p.u3 = u3; p.u4 = u4;
+    p.t = t; p.dt = dt; p.qold = qold; p.iter = iter;
+    c.rhs += nrhs;
+    c.integrated++;
+    if (attempts > c.max_attempts) c.max_attempts = attempts;
+}
+
+/* ---- ParticleInCell ------------------------------------------------------- */
+/* get_absolute_i_and_w(zp, i_node): floor offset and ceil-side weight */
+PM_HD bool weights_1d(double zp, int32_t& f, double& wc) {
+    if (!(fabs(zp) < 1.0e9)) return false;
+    double base = floor(zp);
+    f = (int32_t)base;
+    wc = rint((zp - base) * 1e6) / 1e6;
+    return true;
+}
+
+PM_HD int64_t wrap_index(int64_t pos, int64_t N) {
+    pos = pos % N;
+    if (pos < 0) pos += N;
+    else if (pos == 0) pos += N;
+    return pos;
+}
+
+/* push_to_grid! boundary rules for one corner (1-based global i,j):
+   returns false if the corner is dropped, else the 1-based target (ii,jj) */
+PM_HD bool corner_target(int Nx, int Ny, int bx, int by, int64_t i, int64_t j, int64_t& ii, int64_t& jj) {
+    if (((bx == PICLES_BND_NONPERIODIC) && !(i > 0 && i <= Nx)) ||
+        ((by == PICLES_BND_NONPERIODIC) && !(j > 0 && j <= Ny)) || ((by == PICLES_BND_TRIPOLAR_NORTH) && (j < 1)))
+        return false;
+    if ((by == PICLES_BND_TRIPOLAR_NORTH) && (j > Ny)) {
+        if (bx != PICLES_BND_PERIODIC) return false;
+        if (i < 0) ii = Nx - (Nx + i % Nx);
+        else ii = Nx - i % Nx;
+        jj = 2 * (int64_t)Ny - j + 1;
+        if (ii < 1 || ii > Nx || jj < 1 || jj > Ny) return false;
+    } else {
+        ii = wrap_index(i, Nx);
+        jj = wrap_index(j, Ny);
+    }
+    return true;
+}
+
+PM_HD int32_t pack_cell(int32_t fx, int32_t fy, int cls) {
+    return (int32_t)(((uint32_t)(fx + PH_CELL_BIAS) & 0x3fffu) | (((uint32_t)(fy + PH_CELL_BIAS) & 0x3fffu) << 14) |
+                     ((uint32_t)(cls & 1) << 28));
+}
+PM_HD void unpack_cell(int32_t cell, int32_t& fx, int32_t& fy, int& cls) {
+    fx = (int32_t)((uint32_t)cell & 0x3fffu) - PH_CELL_BIAS;
+    fy = (int32_t)(((uint32_t)cell >> 14) & 0x3fffu) - PH_CELL_BIAS;
+    cls = (int)(((uint32_t)cell >> 28) & 1u);
+}
+
+
+/* ---- ParticleToNode! as a gather --------------------------------------------- */
+/* read-only view of the deposit records of one strip (+ halo rows) */
+struct RecView {
+    int Nx, Ny, bx, by; /* global shape and boundary types */
+    int j0, ny, halo;   /* strip: first owned global row (0-based), rows owned, halo rows */
+    const double *e, *mx, *my, *wx, *wy;
+    const int32_t* cell;
+};
+
+/* local extended row of global 1-based row j, or -1 */
+PM_HD int ext_row(const RecView& V, int64_t j) {
+    int64_t r = j - 1 - V.j0 + V.halo;
+    if (r >= 0 && r < V.ny + 2 * V.halo) return (int)r;
+    if (V.by == PICLES_BND_PERIODIC) { /* wrapped neighbour rows live in the halo */
+        r = j + V.Ny - 1 - V.j0 + V.halo;
+        if (r >= 0 && r < V.ny + 2 * V.halo) return (int)r;
+        r = j - V.Ny - 1 - V.j0 + V.halo;
+        if (r >= 0 && r < V.ny + 2 * V.halo) return (int)r;
+    }
+    return -1;
+}
+
+/* insert v into a sorted list without duplicates */
+PM_HD void list_insert(int* lst, int& n, int v) {
+    int k = 0;
+    while (k < n && lst[k] < v) k++;
+    if (k < n && lst[k] == v) return;
+    for (int m = n; m > k; m--) lst[m] = lst[m - 1];
+    lst[k] = v;
+    n++;
+}
+
+#define PH_GEN_LIST_MAX (2 * (2 * PH_REACH_MAX + 1) + 2)
+
+/* candidate source indices (1-based, in-domain, ascending) along one axis whose corners
+   can reach target T directly (|src - T| <= R, wrapped or clipped) or through the
+   tripolar fold (rows: corner row 2N+1-T; columns: corner column ≡ N-T mod N) */
+PM_HD void axis_candidates(int* lst, int& n, int64_t T, int R, int N, int bnd, bool fold_x, bool fold_y) {
+    n = 0;
+    for (int d = -R; d <= R; d++) {
+        int64_t s = T + d;
+        if (bnd == PICLES_BND_PERIODIC) s = wrap_index(s, N);
+        else if (s < 1 || s > N) continue;
+        list_insert(lst, n, (int)s);
+    }
+    if (fold_y) {
+        int64_t cj = 2 * (int64_t)N + 1 - T;
+        for (int d = -R; d <= R; d++) {
+            int64_t s = cj + d;
+            if (s < 1 || s > N) continue;
+            list_insert(lst, n, (int)s);
+        }
+    }
+    if (fold_x) {
+        int64_t ci = (int64_t)N - T;
+        for (int d = -R; d <= R; d++) list_insert(lst, n, (int)wrap_index(ci + d, N));
+    }
+}
+
+/*
+ * Sum of all deposits landing on global node (I,J) (1-based), accumulated in the
+ * reference's single-thread order: ocean_points order (class 0 = mask 1 nodes, then
+ * class 1 = mask 3 nodes when the model is periodic; within a class column-major, i
+ * fastest), corners (x0,y0),(x1,y0),(x0,y1),(x1,y1) within a particle.  R = reach of
+ * this step (max |corner - home| over all deposits).  s0,s1,s2 are in/out: the caller
+ * initialises them with 0 (run!: State .= 0 before the step) or with the node's current
+ * State (a bare time_step! on a non-zero State accumulates, ParticleInCell.jl:372).
+ */
+PM_HD void gather_node(const RecView& V, int I, int J, int R, int n_classes, double& s0, double& s1, double& s2) {
+    const int Nx = V.Nx, Ny = V.Ny;
+    bool fast_x = (V.bx == PICLES_BND_NONPERIODIC) || (I > R && I <= Nx - R);
+    bool fast_y = (V.by == PICLES_BND_NONPERIODIC) || (V.by == PICLES_BND_PERIODIC && J > R && J <= Ny - R) ||
+                  (V.by == PICLES_BND_TRIPOLAR_NORTH && J <= Ny - R);
+    if (fast_x && fast_y) {
+        /* no wrap, no fold: a source (i,j) reaches (I,J) through exactly one corner,
+           dx = I-i-fx in {0,1}, dy = J-j-fy in {0,1} */
+        int jlo = (J - R > 1) ? J - R : 1, jhi = (J + R < Ny) ? J + R : Ny;
+        int ilo = (I - R > 1) ? I - R : 1, ihi = (I + R < Nx) ? I + R : Nx;
+        for (int cls = 0; cls < n_classes; cls++) {
+            for (int j = jlo; j <= jhi; j++) {
+                int64_t row = (int64_t)(j - 1 - V.j0 + V.halo) * Nx;
+                for (int i = ilo; i <= ihi; i++) {
+                    int64_t le = row + (i - 1);
+                    int32_t cell = V.cell[le];
+                    if (cell == PH_CELL_INVALID) continue;
+                    int32_t fx, fy;
+                    int k;
+                    unpack_cell(cell, fx, fy, k);
+                    int dx = I - i - fx, dy = J - j - fy;
+                    if (k != cls || (unsigned)dx > 1u || (unsigned)dy > 1u) continue;
+                    double wxc = V.wx[le], wyc = V.wy[le];
+                    double wx = dx ? wxc : 1.0 - wxc;
+                    double wy = dy ? wyc : 1.0 - wyc;
+                    double w = wx * wy;
+                    s0 += w * V.e[le];
+                    s1 += w * V.mx[le];
+                    s2 += w * V.my[le];
+                }
+            }
+        }
+        return;
+    }
+    /* generic path (wrap / fold zones): enumerate candidate sources in canonical order
+       and push all four corners through the reference's boundary rules */
+    int rows[PH_GEN_LIST_MAX], cols[PH_GEN_LIST_MAX];
+    int nr, nc;
+    bool tri = (V.by == PICLES_BND_TRIPOLAR_NORTH);
+    axis_candidates(rows, nr, J, R, Ny, tri ? PICLES_BND_NONPERIODIC : V.by, false, tri);
+    axis_candidates(cols, nc, I, R, Nx, V.bx, tri && V.bx == PICLES_BND_PERIODIC, false);
+    const int64_t tgt = (int64_t)(I - 1) + (int64_t)(J - 1) * Nx;
+    for (int cls = 0; cls < n_classes; cls++) {
+        for (int a = 0; a < nr; a++) {
+            int j = rows[a];
+            int er = ext_row(V, j);
+            if (er < 0) continue;
+            for (int b = 0; b < nc; b++) {
+                int i = cols[b];
+                int64_t le = (int64_t)er * Nx + (i - 1);
+                int32_t cell = V.cell[le];
+                if (cell == PH_CELL_INVALID) continue;
+                int32_t fx, fy;
+                int k;
+                unpack_cell(cell, fx, fy, k);
+                if (k != cls) continue;
+                double wxc = V.wx[le], wyc = V.wy[le];
+                double ce = V.e[le], cmx = V.mx[le], cmy = V.my[le];
+                for (int q = 0; q < 4; q++) { /* (x0,y0),(x1,y0),(x0,y1),(x1,y1) */
+                    int dx = q & 1, dy = q >> 1;
+                    int64_t ii, jj;
+                    if (!corner_target(Nx, Ny, V.bx, V.by, (int64_t)i + fx + dx, (int64_t)j + fy + dy, ii, jj)) continue;
+                    if ((ii - 1) + (jj - 1) * Nx != tgt) continue;
+                    double wx = dx ? wxc : 1.0 - wxc;
+                    double wy = dy ? wyc : 1.0 - wyc;
+                    double w = wx * wy;
+                    s0 += w * ce;
+                    s1 += w * cmx;
+                    s2 += w * cmy;
+                }
+            }
+        }
+    }
+}
+
+/* ---- advance! (everything except the scatter, which the gather replaces) ----- */
+template <class T>
+PM_HD void advance_particle(const picles_params_t& P, Particle& p, int mask, double DT, double wu0, double wv0,
+                            double wu1, double wv1, const double* M, double pc, Record& rec, Tally& c) {
+    double t_start = p.t;
+    bool on = (p.flags & PICLES_PF_ON) != 0;
+    if (on) {
+        Wind w;
+        w.u0 = wu0; w.v0 = wv0; w.du = wu1 - wu0; w.dv = wv1 - wv0;
+        w.t_start = t_start; w.inv_DT = 1.0 / DT;
+        integrate<T>(P, w, M, pc, DT, p, c);
+    } else {
+        if (wu1 * wu1 + wv1 * wv1 >= P.wind_min_squared) {
+            reset_particle_values(P, wu1, wv1, DT, p);
+            p.flags |= PICLES_PF_DT_RESET;
+            on = true;
+            c.reseed++;
+        }
+    }
+    bool anynan = (p.u0 != p.u0) | (p.u1 != p.u1) | (p.u2 != p.u2);
+    bool anyinf = pm_isinf(p.u0) | pm_isinf(p.u1) | pm_isinf(p.u2);
+    if (anynan) {
+        reset_particle_values(P, wu1, wv1, DT, p);
+        p.flags |= PICLES_PF_DT_RESET; p.status |= PICLES_PST_NAN_RESET; c.fixups++;
+    } else if (anyinf) {
+        reset_particle_values(P, wu0, wv0, DT, p);
+        p.flags |= PICLES_PF_DT_RESET; p.status |= PICLES_PST_INF_RESET; c.fixups++;
+    } else if (p.u0 > P.log_energy_maximum) {
+        p.u0 = P.log_energy_maximum;
+        p.flags |= PICLES_PF_DT_RESET; p.status |= PICLES_PST_EMAX_CLAMP; c.fixups++;
+    }
+    if (P.on_persist) p.flags = (uint8_t)(on ? (p.flags | PICLES_PF_ON) : (p.flags & ~PICLES_PF_ON));
+    /* ParticleToNode!: weights + charge -> record */
+    rec.cell = PH_CELL_INVALID;
+    rec.e = rec.mx = rec.my = rec.wxc = rec.wyc = 0.0;
+    if (on) {
+        int32_t fx, fy;
+        double wxc, wyc;
+        if (weights_1d(p.u3, fx, wxc) && weights_1d(p.u4, fy, wyc)) {
+            int32_t r = 0, d;
+            d = fx < 0 ? -fx : fx; if (d > r) r = d;
+            d = fx + 1 < 0 ? -(fx + 1) : fx + 1; if (d > r) r = d;
+            d = fy < 0 ? -fy : fy; if (d > r) r = d;
+            d = fy + 1 < 0 ? -(fy + 1) : fy + 1; if (d > r) r = d;
+            if (r > c.reach) c.reach = r;
+            if (r < PH_CELL_BIAS - 2) {
+                charge(p.u0, p.u1, p.u2, rec.e, rec.mx, rec.my);
+                rec.wxc = wxc; rec.wyc = wyc;
+                rec.cell = pack_cell(fx, fy, mask == PICLES_MASK_GRID_BOUNDARY);
+            }
+            c.deposited++;
+        }
+    }
+}
+
+/* ---- remesh! / NodeToParticle! ---------------------------------------------- */
+PM_HD void remesh_particle(const picles_params_t& P, Particle& p, double e, double mx, double my, double wu,
+                           double wv, double DT, Tally& c) {
+    bool boundary = (p.flags & PICLES_PF_BOUNDARY) != 0;
+    bool on;
+    if (!boundary && (e >= P.minimal_state[0]) && (mx * mx + my * my >= P.minimal_state[1])) {
+        vertex(e, mx, my, p);
+        p.flags |= PICLES_PF_DT_RESET;
+        on = true;
+        c.A++;
+    } else if (!boundary && (wu * wu + wv * wv >= P.wind_min_squared)) {
+        reset_particle_values(P, wu, wv, DT, p);
+        p.qold = PH_QOLDINIT; p.iter = 0; p.status = 0;
+        p.flags |= PICLES_PF_DT_RESET;
+        on = true;
+        c.B++;
+    } else if (boundary && (wu * wu + wv * wv >= P.wind_min_squared)) {
+        reset_particle_values(P, wu, wv, DT, p);
+        p.qold = PH_QOLDINIT; p.iter = 0; p.status = 0;
+        p.flags |= PICLES_PF_DT_RESET;
+        on = true;
+        c.C++;
+    } else {
+        on = false;
+        c.D++;
+    }
+    if (P.on_persist) p.flags = (uint8_t)(on ? (p.flags | PICLES_PF_ON) : (p.flags & ~PICLES_PF_ON));
+}
+
+/* ---- SeedParticle -------------------------------------------------------- */
+/* returns false for land (mask 0: dummy instance); fills p and the initial node state */
+PM_HD bool seed_particle(const picles_params_t& P, int mask, double wu, double wv, Particle& p, double& e,
+                         double& mx, double& my) {
+    p.u0 = p.u1 = p.u2 = p.u3 = p.u4 = 0.0;
+    p.t = 0.0; p.dt = 0.0; p.qold = 0.0; p.iter = 0; p.flags = 0; p.status = 0;
+    e = mx = my = 0.0;
+    if (mask == PICLES_MASK_LAND) return false;
+    bool on;
+    if (!P.has_defaults) {
+        if (sqrt(wu * wu + wv * wv) > sqrt(2.0)) {
+            windsea(wu, wv, P.seed_timescale, p.u0, p.u1, p.u2);
+            on = true;
+        } else {
+            minimal_particle(wu, wv, P.seed_timescale, p.u0, p.u1, p.u2);
+            on = false;
+        }
+    } else {
+        p.u0 = P.defaults[0]; p.u1 = P.defaults[1]; p.u2 = P.defaults[2];
+        on = true;
+    }
+    bool boundary = P.periodic_boundary ? (mask == PICLES_MASK_LAND_BOUNDARY) : (mask >= 2);
+    bool active = (mask == PICLES_MASK_OCEAN) || (P.periodic_boundary && mask == PICLES_MASK_GRID_BOUNDARY);
+    if (on) charge(p.u0, p.u1, p.u2, e, mx, my);
+    p.dt = P.dt; p.qold = PH_QOLDINIT;
+    p.flags = (uint8_t)((on ? PICLES_PF_ON : 0) | (boundary ? PICLES_PF_BOUNDARY : 0) | (active ? PICLES_PF_ACTIVE : 0));
+    return true;
+}
+
+} /* namespace picles */
+#endif /* PICLES_PHYSICS_H */

@@ -1,0 +1,557 @@
+/*
+ * picles_capi.cu — the C ABI of include/picles_b200.h: handle, device memory, streams,
+ * host<->device staging and kernel orchestration of one model step on one y-strip.
+ * No torch types, no CPU fallback.
+ */
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/picles_b200.h"
+#include "picles_device.h"
+
+using namespace picles;
+
+#define ENERGY_BLOCKS 1024
+
+struct picles_handle {
+    int device = -1;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; /* adv0, adv1, prj0, prj1=rms0, rms1 */
+    cudaEvent_t tev[2] = {nullptr, nullptr};                           /* user stopwatch */
+    bool have_grid = false, have_params = false, seeded = false, winds_loaded = false;
+    DeviceArrays A;
+    picles_params_t P;
+    DeviceCounters* d_counters = nullptr;
+    DeviceCounters* h_counters = nullptr; /* pinned */
+    double* d_partial = nullptr;
+    double* h_partial = nullptr;          /* pinned */
+    char *send_lo = nullptr, *send_hi = nullptr, *recv_lo = nullptr, *recv_hi = nullptr;
+    int64_t halo_bytes = 0;
+    std::vector<void*> allocs;
+    picles_counters_t last;
+    int64_t n_active = 0;
+    bool timing_valid = false;
+    int accumulate = 0; /* PICLES_OPT_ACCUMULATE_STATE */
+    char err[512];
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(picles_t* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) snprintf(h->err, sizeof h->err, "%s", buf);
+    snprintf(g_err, sizeof g_err, "%s", buf);
+    return code;
+}
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(h, PICLES_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,        \
+                        cudaGetErrorString(e_));                                                        \
+    } while (0)
+
+template <class T>
+static int dalloc(picles_t* h, T** p, int64_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (size_t)(count > 0 ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(h, PICLES_ERR_ALLOC, "cudaMalloc(%lld bytes): %s", (long long)(count * sizeof(T)), cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+#define DALLOC(ptr, count)                      \
+    do {                                        \
+        int rc_ = dalloc(h, &(ptr), (count));   \
+        if (rc_) return rc_;                    \
+    } while (0)
+
+static void free_grid(picles_t* h) {
+    for (void* p : h->allocs) cudaFree(p);
+    h->allocs.clear();
+    memset(&h->A, 0, sizeof h->A);
+    h->send_lo = h->send_hi = h->recv_lo = h->recv_hi = nullptr;
+    h->have_grid = h->seeded = h->winds_loaded = false;
+}
+
+extern "C" {
+
+int picles_abi_version(void) { return PICLES_ABI_VERSION; }
+
+const char* picles_last_error(picles_t* h) { return h ? h->err : g_err; }
+
+int picles_create(picles_t** out, int device_id) {
+    picles_t* h = nullptr;
+    if (!out) return fail(nullptr, PICLES_ERR_ARG, "picles_create: null handle pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, PICLES_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device_id < 0 || device_id >= ndev) return fail(nullptr, PICLES_ERR_ARG, "device %d out of range [0,%d)", device_id, ndev);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device_id);
+    if (e != cudaSuccess) return fail(nullptr, PICLES_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, PICLES_ERR_CUDA, "device %d is sm_%d%d; this library ships sm_100a code only", device_id,
+                    prop.major, prop.minor);
+    h = new picles_handle();
+    h->err[0] = 0;
+    h->device = device_id;
+    h->sms = prop.multiProcessorCount;
+    memset(&h->A, 0, sizeof h->A);
+    memset(&h->last, 0, sizeof h->last);
+    CK(cudaSetDevice(device_id));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 5; k++) CK(cudaEventCreate(&h->ev[k]));
+    for (int k = 0; k < 2; k++) CK(cudaEventCreate(&h->tev[k]));
+    CK(cudaMalloc((void**)&h->d_counters, sizeof(DeviceCounters)));
+    CK(cudaMallocHost((void**)&h->h_counters, sizeof(DeviceCounters)));
+    CK(cudaMalloc((void**)&h->d_partial, ENERGY_BLOCKS * sizeof(double)));
+    CK(cudaMallocHost((void**)&h->h_partial, ENERGY_BLOCKS * sizeof(double)));
+    *out = h;
+    return PICLES_OK;
+}
+
+int picles_destroy(picles_t* h) {
+    if (!h) return PICLES_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_grid(h);
+    if (h->d_counters) cudaFree(h->d_counters);
+    if (h->h_counters) cudaFreeHost(h->h_counters);
+    if (h->d_partial) cudaFree(h->d_partial);
+    if (h->h_partial) cudaFreeHost(h->h_partial);
+    for (int k = 0; k < 5; k++)
+        if (h->ev[k]) cudaEventDestroy(h->ev[k]);
+    for (int k = 0; k < 2; k++)
+        if (h->tev[k]) cudaEventDestroy(h->tev[k]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return PICLES_OK;
+}
+
+int picles_set_grid(picles_t* h, int Nx, int Ny, int bx, int by, int j0, int ny_local, int halo,
+                    const uint8_t* mask, const double* M, const double* M_const, const double* pc_coef) {
+    if (!h) return fail(nullptr, PICLES_ERR_ARG, "null handle");
+    if (Nx < 1 || Ny < 1 || ny_local < 1 || j0 < 0 || j0 + ny_local > Ny || halo < 0)
+        return fail(h, PICLES_ERR_ARG, "bad grid shape Nx=%d Ny=%d j0=%d ny=%d halo=%d", Nx, Ny, j0, ny_local, halo);
+    if (bx < 0 || bx > 1 || by < 0 || by > 2) return fail(h, PICLES_ERR_ARG, "bad boundary types bx=%d by=%d", bx, by);
+    if (!mask) return fail(h, PICLES_ERR_ARG, "mask is required");
+    if (!M && !M_const) return fail(h, PICLES_ERR_ARG, "one of M / M_const is required");
+    if (halo > PH_REACH_MAX_ABI) return fail(h, PICLES_ERR_ARG, "halo %d exceeds the supported reach %d", halo, PH_REACH_MAX_ABI);
+    if (ny_local != Ny && halo > ny_local) return fail(h, PICLES_ERR_ARG, "halo %d wider than the strip (%d rows)", halo, ny_local);
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    free_grid(h);
+    DeviceArrays& A = h->A;
+    A.Nx = Nx; A.Ny = Ny; A.bx = bx; A.by = by; A.j0 = j0; A.ny = ny_local; A.halo = halo;
+    int64_t n = (int64_t)Nx * ny_local;
+    int64_t ne = (int64_t)Nx * (ny_local + 2 * halo);
+    for (int k = 0; k < 5; k++) DALLOC(A.z[k], n);
+    DALLOC(A.t, n); DALLOC(A.dt, n); DALLOC(A.qold, n);
+    DALLOC(A.iter, n);
+    DALLOC(A.flags, n); DALLOC(A.status, n); DALLOC(A.mask, n);
+    DALLOC(A.u_t, n); DALLOC(A.v_t, n); DALLOC(A.u_t1, n); DALLOC(A.v_t1, n);
+    for (int k = 0; k < 5; k++) DALLOC(A.rec[k], ne);
+    DALLOC(A.cell, ne);
+    for (int k = 0; k < 3; k++) DALLOC(A.S[k], n);
+    CK(cudaMemcpyAsync(A.mask, mask, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    if (M) {
+        for (int k = 0; k < 4; k++) {
+            DALLOC(A.M[k], n);
+            CK(cudaMemcpyAsync(A.M[k], M + k * n, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+        }
+    } else {
+        for (int k = 0; k < 4; k++) { A.M[k] = nullptr; A.Mc[k] = M_const[k]; }
+    }
+    if (pc_coef) {
+        DALLOC(A.pc, n);
+        CK(cudaMemcpyAsync(A.pc, pc_coef, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    for (int k = 0; k < 5; k++) CK(cudaMemsetAsync(A.rec[k], 0, (size_t)ne * 8, h->stream));
+    launch_fill_i32(A.cell, ne, -1, h->sms, h->stream);
+    for (int k = 0; k < 3; k++) CK(cudaMemsetAsync(A.S[k], 0, (size_t)n * 8, h->stream));
+    CK(cudaMemsetAsync(A.flags, 0, (size_t)n, h->stream));
+    h->halo_bytes = (int64_t)halo * Nx * (5 * 8 + 4);
+    if (halo > 0) {
+        DALLOC(h->send_lo, h->halo_bytes); DALLOC(h->send_hi, h->halo_bytes);
+        DALLOC(h->recv_lo, h->halo_bytes); DALLOC(h->recv_hi, h->halo_bytes);
+        /* until a neighbour delivers rows, received halos are "no deposit" */
+        CK(cudaMemsetAsync(h->recv_lo, 0xff, (size_t)h->halo_bytes, h->stream));
+        CK(cudaMemsetAsync(h->recv_hi, 0xff, (size_t)h->halo_bytes, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    /* |ocean_points| of this strip */
+    h->n_active = -1; /* resolved at seed (depends on the model's periodic_boundary) */
+    h->have_grid = true;
+    return PICLES_OK;
+}
+
+int picles_set_params(picles_t* h, const picles_params_t* p) {
+    if (!h || !p) return fail(h, PICLES_ERR_ARG, "null argument");
+    if (p->solver != PICLES_SOLVER_TSIT5 && p->solver != PICLES_SOLVER_DP5) return fail(h, PICLES_ERR_ARG, "unknown solver id %d", p->solver);
+    if (!p->adaptive) return fail(h, PICLES_ERR_ARG, "adaptive=false is not supported");
+    if (!(p->abstol > 0) || !(p->reltol > 0) || !(p->dtmin >= 0) || !(p->dt > 0) || !(p->dtmax > 0) || !(p->r_g > 0) || !(p->e_T > 0))
+        return fail(h, PICLES_ERR_ARG, "non-positive tolerance / step / constant in params");
+    if (p->maxiters < 1 || p->maxiters > 2000000000LL) return fail(h, PICLES_ERR_ARG, "maxiters out of range");
+    h->P = *p;
+    h->have_params = true;
+    return PICLES_OK;
+}
+
+static int need_ready(picles_t* h, bool seeded) {
+    if (!h) return fail(nullptr, PICLES_ERR_ARG, "null handle");
+    if (!h->have_grid || !h->have_params) return fail(h, PICLES_ERR_STATE, "picles_set_grid and picles_set_params must be called first");
+    if (seeded && !h->seeded) return fail(h, PICLES_ERR_STATE, "picles_seed must be called first");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return fail(h, PICLES_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int picles_seed(picles_t* h, const double* u0, const double* v0) {
+    int rc = need_ready(h, false);
+    if (rc) return rc;
+    if (!u0 || !v0) return fail(h, PICLES_ERR_ARG, "picles_seed: wind arrays are required");
+    DeviceArrays& A = h->A;
+    int64_t n = (int64_t)A.Nx * A.ny;
+    /* stage the t=0 wind in the t1 slots: the first step's t level (see picles_step) */
+    CK(cudaMemcpyAsync(A.u_t1, u0, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(A.v_t1, v0, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    launch_seed(A, h->P, A.u_t1, A.v_t1, h->sms, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(A.u_t, A.u_t1, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(A.v_t, A.v_t1, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->seeded = true;
+    h->winds_loaded = true;
+    memset(&h->last, 0, sizeof h->last);
+    return PICLES_OK;
+}
+
+int picles_upload_winds(picles_t* h, const double* u_t, const double* v_t, const double* u_t1, const double* v_t1) {
+    int rc = need_ready(h, true);
+    if (rc) return rc;
+    DeviceArrays& A = h->A;
+    size_t bytes = (size_t)A.Nx * A.ny * 8;
+    if ((u_t == nullptr) != (v_t == nullptr) || (u_t1 == nullptr) != (v_t1 == nullptr))
+        return fail(h, PICLES_ERR_ARG, "wind components must be given in pairs");
+    if (u_t) {
+        CK(cudaMemcpyAsync(A.u_t, u_t, bytes, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(A.v_t, v_t, bytes, cudaMemcpyHostToDevice, h->stream));
+    } else if (u_t1) {
+        /* the previous step's t+DT level is this step's t level: swap, no copy */
+        double* tu = A.u_t; A.u_t = A.u_t1; A.u_t1 = tu;
+        double* tv = A.v_t; A.v_t = A.v_t1; A.v_t1 = tv;
+    }
+    if (u_t1) {
+        CK(cudaMemcpyAsync(A.u_t1, u_t1, bytes, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(A.v_t1, v_t1, bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    return PICLES_OK;
+}
+
+int picles_step_advance(picles_t* h, double t, double dt_model) {
+    int rc = need_ready(h, true);
+    if (rc) return rc;
+    (void)t;
+    if (!(dt_model > 0)) return fail(h, PICLES_ERR_ARG, "dt_model must be positive");
+    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(DeviceCounters), h->stream));
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    launch_advance(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream);
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaGetLastError());
+    h->timing_valid = false;
+    return PICLES_OK;
+}
+
+int picles_get_reach(picles_t* h, int32_t* reach) {
+    int rc = need_ready(h, true);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(&h->h_counters->reach, &h->d_counters->reach, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *reach = h->h_counters->reach;
+    return PICLES_OK;
+}
+
+int picles_halo_buffers(picles_t* h, void** send_lo, void** send_hi, void** recv_lo, void** recv_hi, int64_t* nbytes) {
+    if (!h || !h->have_grid) return fail(h, PICLES_ERR_STATE, "grid not set");
+    if (send_lo) *send_lo = h->send_lo;
+    if (send_hi) *send_hi = h->send_hi;
+    if (recv_lo) *recv_lo = h->recv_lo;
+    if (recv_hi) *recv_hi = h->recv_hi;
+    if (nbytes) *nbytes = h->halo_bytes;
+    return PICLES_OK;
+}
+
+int picles_halo_pack(picles_t* h) {
+    int rc = need_ready(h, true);
+    if (rc) return rc;
+    launch_halo_pack(h->A, h->send_lo, h->send_hi, h->sms, h->stream);
+    CK(cudaGetLastError());
+    return PICLES_OK;
+}
+
+int picles_halo_unpack(picles_t* h) {
+    int rc = need_ready(h, true);
+    if (rc) return rc;
+    launch_halo_unpack(h->A, h->recv_lo, h->recv_hi, h->sms, h->stream);
+    CK(cudaGetLastError());
+    return PICLES_OK;
+}
+
+static int finish_counters(picles_t* h) {
+    CK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const DeviceCounters& d = *h->h_counters;
+    picles_counters_t& c = h->last;
+    c.n_integrated = (int64_t)d.sums[0]; c.n_substeps = (int64_t)d.sums[1]; c.n_rejects = (int64_t)d.sums[2];
+    c.n_rhs = (int64_t)d.sums[3]; c.n_reseed_advance = (int64_t)d.sums[4]; c.n_fixups = (int64_t)d.sums[5];
+    c.n_failed = (int64_t)d.sums[6]; c.n_deposited = (int64_t)d.sums[7];
+    c.n_remesh_A = (int64_t)d.sums[8]; c.n_remesh_B = (int64_t)d.sums[9]; c.n_remesh_C = (int64_t)d.sums[10];
+    c.n_remesh_D = (int64_t)d.sums[11];
+    c.n_active = c.n_remesh_A + c.n_remesh_B + c.n_remesh_C + c.n_remesh_D;
+    c.reach = d.reach; c.max_attempts = d.max_attempts;
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); c.ms_advance = ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); c.ms_project = ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4])); c.ms_remesh = ms;
+    h->timing_valid = true;
+    return PICLES_OK;
+}
+
+int picles_step_project_remesh(picles_t* h, double t, double dt_model) {
+    int rc = need_ready(h, true);
+    if (rc) return rc;
+    (void)t;
+    /* a halo exchange may have run since the advance: ms_project brackets the gather alone */
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    launch_project(h->A, h->P.periodic_boundary ? 2 : 1, h->accumulate, &h->d_counters->reach, h->sms, h->stream);
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    launch_remesh(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream);
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    CK(cudaGetLastError());
+    rc = finish_counters(h);
+    if (rc) return rc;
+    int limit = (h->A.ny != h->A.Ny) ? h->A.halo : PH_REACH_MAX_ABI;
+    if (h->last.reach > limit)
+        return fail(h, PICLES_ERR_HALO, "particle reach %d cells exceeds %s %d", h->last.reach,
+                    (h->A.ny != h->A.Ny) ? "the halo width" : "the supported reach", limit);
+    return PICLES_OK;
+}
+
+int picles_step(picles_t* h, double t, double dt_model, const double* u_t, const double* v_t, const double* u_t1,
+                const double* v_t1) {
+    int rc = need_ready(h, true);
+    if (rc) return rc;
+    if (h->A.ny != h->A.Ny)
+        return fail(h, PICLES_ERR_STATE, "picles_step needs a single-strip handle; use the phase-split calls for strips");
+    rc = picles_upload_winds(h, u_t, v_t, u_t1, v_t1);
+    if (rc) return rc;
+    /* advance timing must not include the H2D copies queued above */
+    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(DeviceCounters), h->stream));
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    launch_advance(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream);
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    launch_project(h->A, h->P.periodic_boundary ? 2 : 1, h->accumulate, &h->d_counters->reach, h->sms, h->stream);
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    launch_remesh(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream);
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    CK(cudaGetLastError());
+    rc = finish_counters(h);
+    if (rc) return rc;
+    if (h->last.reach > PH_REACH_MAX_ABI)
+        return fail(h, PICLES_ERR_HALO, "particle reach %d cells exceeds the supported reach %d", h->last.reach, PH_REACH_MAX_ABI);
+    return PICLES_OK;
+}
+
+int picles_synchronize(picles_t* h) {
+    if (!h) return fail(nullptr, PICLES_ERR_ARG, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return PICLES_OK;
+}
+
+int picles_get_state(picles_t* h, double* S) {
+    int rc = need_ready(h, false);
+    if (rc) return rc;
+    if (!S) return fail(h, PICLES_ERR_ARG, "null output");
+    int64_t n = (int64_t)h->A.Nx * h->A.ny;
+    for (int k = 0; k < 3; k++) CK(cudaMemcpyAsync(S + k * n, h->A.S[k], (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PICLES_OK;
+}
+
+int picles_set_state(picles_t* h, const double* S) {
+    int rc = need_ready(h, false);
+    if (rc) return rc;
+    if (!S) return fail(h, PICLES_ERR_ARG, "null input");
+    int64_t n = (int64_t)h->A.Nx * h->A.ny;
+    for (int k = 0; k < 3; k++) CK(cudaMemcpyAsync(h->A.S[k], S + k * n, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PICLES_OK;
+}
+
+int picles_get_particles(picles_t* h, double* z, double* t, double* dt, uint8_t* flags, int32_t* status) {
+    int rc = need_ready(h, true);
+    if (rc) return rc;
+    const DeviceArrays& A = h->A;
+    int64_t n = (int64_t)A.Nx * A.ny;
+    if (z) for (int k = 0; k < 5; k++) CK(cudaMemcpyAsync(z + k * n, A.z[k], (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (t) CK(cudaMemcpyAsync(t, A.t, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (dt) CK(cudaMemcpyAsync(dt, A.dt, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (flags) CK(cudaMemcpyAsync(flags, A.flags, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<uint8_t> st8;
+    if (status) {
+        st8.resize((size_t)n);
+        CK(cudaMemcpyAsync(st8.data(), A.status, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    if (status) for (int64_t l = 0; l < n; l++) status[l] = st8[(size_t)l];
+    return PICLES_OK;
+}
+
+int picles_get_counters(picles_t* h, picles_counters_t* c) {
+    if (!h || !c) return fail(h, PICLES_ERR_ARG, "null argument");
+    *c = h->last;
+    return PICLES_OK;
+}
+
+int picles_state_energy_sum(picles_t* h, double* sum_e) {
+    int rc = need_ready(h, false);
+    if (rc) return rc;
+    if (!sum_e) return fail(h, PICLES_ERR_ARG, "null output");
+    int64_t n = (int64_t)h->A.Nx * h->A.ny;
+    launch_energy(h->A.S[0], n, h->d_partial, ENERGY_BLOCKS, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_partial, h->d_partial, ENERGY_BLOCKS * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    double s = 0.0;
+    for (int k = 0; k < ENERGY_BLOCKS; k++) s += h->h_partial[k];
+    *sum_e = s;
+    return PICLES_OK;
+}
+
+int picles_state_dev(picles_t* h, double** S_dev) {
+    if (!h || !h->have_grid || !S_dev) return fail(h, PICLES_ERR_STATE, "grid not set");
+    /* the three State planes are separate allocations: return them as 3 pointers */
+    S_dev[0] = h->A.S[0]; S_dev[1] = h->A.S[1]; S_dev[2] = h->A.S[2];
+    return PICLES_OK;
+}
+
+int picles_wind_dev(picles_t* h, double** u_t, double** v_t, double** u_t1, double** v_t1) {
+    if (!h || !h->have_grid) return fail(h, PICLES_ERR_STATE, "grid not set");
+    if (u_t) *u_t = h->A.u_t;
+    if (v_t) *v_t = h->A.v_t;
+    if (u_t1) *u_t1 = h->A.u_t1;
+    if (v_t1) *v_t1 = h->A.v_t1;
+    return PICLES_OK;
+}
+
+int picles_set_option(picles_t* h, int option, int value) {
+    if (!h) return fail(nullptr, PICLES_ERR_ARG, "null handle");
+    switch (option) {
+        case PICLES_OPT_ACCUMULATE_STATE: h->accumulate = value ? 1 : 0; return PICLES_OK;
+        default: return fail(h, PICLES_ERR_ARG, "unknown option %d", option);
+    }
+}
+
+int picles_zero_state(picles_t* h) {
+    int rc = need_ready(h, false);
+    if (rc) return rc;
+    int64_t n = (int64_t)h->A.Nx * h->A.ny;
+    for (int k = 0; k < 3; k++) CK(cudaMemsetAsync(h->A.S[k], 0, (size_t)n * 8, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PICLES_OK;
+}
+
+int picles_copy_dev(picles_t* h, void* dst, const void* src, int64_t nbytes) {
+    if (!h || !dst || !src || nbytes < 0) return fail(h, PICLES_ERR_ARG, "picles_copy_dev: bad argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDefault, h->stream));
+    return PICLES_OK;
+}
+
+int picles_timer_start(picles_t* h) {
+    if (!h) return fail(nullptr, PICLES_ERR_ARG, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->tev[0], h->stream));
+    return PICLES_OK;
+}
+
+int picles_timer_stop(picles_t* h, double* ms) {
+    if (!h || !ms) return fail(h, PICLES_ERR_ARG, "null argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->tev[1], h->stream));
+    CK(cudaEventSynchronize(h->tev[1]));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, h->tev[0], h->tev[1]));
+    *ms = f;
+    return PICLES_OK;
+}
+
+int picles_measure_fp64_peak(picles_t* h, double* tflops) {
+    if (!h || !tflops) return fail(h, PICLES_ERR_ARG, "null argument");
+    CK(cudaSetDevice(h->device));
+    int64_t fmas = 0;
+    double best = 0.0;
+    launch_fp64_peak(h->d_partial, 256, h->sms, h->stream, &fmas); /* warm-up */
+    CK(cudaStreamSynchronize(h->stream));
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(h->tev[0], h->stream));
+        launch_fp64_peak(h->d_partial, 4096, h->sms, h->stream, &fmas);
+        CK(cudaEventRecord(h->tev[1], h->stream));
+        CK(cudaEventSynchronize(h->tev[1]));
+        CK(cudaGetLastError());
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->tev[0], h->tev[1]));
+        double tf = 2.0 * (double)fmas / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    *tflops = best;
+    return PICLES_OK;
+}
+
+int picles_measure_hbm_copy(picles_t* h, int mib, double* gbs) {
+    if (!h || !gbs || mib < 1) return fail(h, PICLES_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(h->device));
+    int64_t n = (int64_t)mib * 1024 * 1024 / 8;
+    double *a = nullptr, *b = nullptr;
+    if (cudaMalloc((void**)&a, (size_t)n * 8) != cudaSuccess || cudaMalloc((void**)&b, (size_t)n * 8) != cudaSuccess) {
+        if (a) cudaFree(a);
+        return fail(h, PICLES_ERR_ALLOC, "cannot allocate 2 x %d MiB", mib);
+    }
+    cudaMemsetAsync(a, 0, (size_t)n * 8, h->stream);
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(h->tev[0], h->stream);
+        launch_copy_f64(b, a, n, h->sms, h->stream);
+        cudaEventRecord(h->tev[1], h->stream);
+        cudaEventSynchronize(h->tev[1]);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->tev[0], h->tev[1]);
+        double g = 2.0 * (double)n * 8 / (ms * 1e-3) / 1e9;
+        if (rep > 0 && g > best) best = g;
+    }
+    cudaFree(a);
+    cudaFree(b);
+    CK(cudaGetLastError());
+    *gbs = best;
+    return PICLES_OK;
+}
+
+} /* extern "C" */

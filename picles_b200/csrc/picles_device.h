@@ -1,0 +1,63 @@
+/* picles_device.h — device-side data layout shared by the kernels and the C ABI layer. */
+#ifndef PICLES_DEVICE_H
+#define PICLES_DEVICE_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/picles_b200.h"
+
+/* launch shapes: grids are capped at (SM count x resident blocks) and grid-stride */
+#define ADV_THREADS 128
+#define ADV_MIN_BLOCKS 4
+#define PRJ_THREADS 256
+#define RMS_THREADS 256
+/* largest particle reach (cells) the projection gather supports; == PH_REACH_MAX */
+#define PH_REACH_MAX_ABI 15
+
+namespace picles {
+
+/*
+ * All planes are ny*Nx doubles, x fastest, for the rows this strip owns; `rec`/`cell`
+ * have (ny + 2*halo)*Nx entries (neighbour rows below and above).
+ */
+struct DeviceArrays {
+    int Nx, Ny;       /* global shape */
+    int bx, by;       /* PICLES_BND_* */
+    int j0, ny, halo; /* strip: first global row (0-based), rows owned, halo rows */
+    double* z[5];     /* lne, c̄_x, c̄_y, x, y */
+    double *t, *dt, *qold;
+    int32_t* iter;
+    uint8_t *flags, *status, *mask;
+    double *u_t, *v_t, *u_t1, *v_t1; /* staged winds at t and t+DT */
+    double* M[4];                    /* per-node projection kernel planes, or nullptr */
+    double Mc[4];                    /* uniform projection kernel */
+    double* pc;                      /* great-circle coefficient plane, or nullptr */
+    double* rec[5];                  /* deposit records: e, m_x, m_y, w_x(ceil), w_y(ceil) */
+    int32_t* cell;                   /* packed floor offsets + class, PH_CELL_INVALID if none */
+    double* S[3];                    /* State planes e, m_x, m_y */
+};
+
+struct DeviceCounters {
+    /* integrated, substeps, rejects, rhs, reseed, fixups, failed, deposited, A, B, C, D */
+    unsigned long long sums[12];
+    int32_t reach;
+    int32_t max_attempts;
+};
+
+void launch_seed(const DeviceArrays& A, const picles_params_t& P, const double* u0, const double* v0, int sms,
+                 cudaStream_t st);
+void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
+                    cudaStream_t st);
+void launch_project(const DeviceArrays& A, int n_classes, int accumulate, const int32_t* reach, int sms, cudaStream_t st);
+void launch_remesh(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
+                   cudaStream_t st);
+void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cudaStream_t st);
+void launch_halo_pack(const DeviceArrays& A, char* lo, char* hi, int sms, cudaStream_t st);
+void launch_halo_unpack(const DeviceArrays& A, const char* lo, const char* hi, int sms, cudaStream_t st);
+void launch_fill_i32(int32_t* p, int64_t n, int32_t v, int sms, cudaStream_t st);
+void launch_fp64_peak(double* out, int iters, int sms, cudaStream_t st, int64_t* fmas);
+void launch_copy_f64(double* dst, const double* src, int64_t n, int sms, cudaStream_t st);
+
+} /* namespace picles */
+#endif

@@ -1,0 +1,167 @@
+"""B200Engine — thin object wrapper over the C ABI of libpicles_b200.so.
+
+One engine = one `picles_t` handle = one GPU = one y-strip of the global grid.  All
+arrays cross the boundary as host numpy buffers (row-major (ny, Nx) == the reference's
+column-major (Nx, ny), i fastest); nothing here computes — every method is one or two
+C-ABI calls, and every failure of the library raises PiclesError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._abi import ERR_NAMES, PiclesCounters, PiclesError, PiclesParams, load_library
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class B200Engine:
+    def __init__(self, Nx, Ny, bx, by, mask, params: PiclesParams, M=None, M_const=None, pc=None, device=0,
+                 j0=0, ny_local=None, halo=0):
+        """mask/M/pc cover the rows this strip owns: (ny_local, Nx), (4, ny_local, Nx), (ny_local, Nx)."""
+        self.lib = load_library()
+        self.Nx, self.Ny = int(Nx), int(Ny)
+        self.j0 = int(j0)
+        self.ny = int(Ny if ny_local is None else ny_local)
+        self.halo = int(halo)
+        self.h = C.c_void_p()
+        self._check(self.lib.picles_create(C.byref(self.h), int(device)), None)
+        mask = np.ascontiguousarray(np.asarray(mask, np.uint8).reshape(self.ny, self.Nx))
+        Mp = np.ascontiguousarray(np.asarray(M, np.float64).reshape(4, self.ny, self.Nx)) if M is not None else None
+        Mc = np.ascontiguousarray(np.asarray(M_const, np.float64).reshape(4)) if M_const is not None else None
+        pcp = np.ascontiguousarray(np.asarray(pc, np.float64).reshape(self.ny, self.Nx)) if pc is not None else None
+        self._check(self.lib.picles_set_grid(self.h, self.Nx, self.Ny, int(bx), int(by), self.j0, self.ny, self.halo,
+                                             _ptr(mask), _ptr(Mp), _ptr(Mc), _ptr(pcp)))
+        self.params = params
+        self._check(self.lib.picles_set_params(self.h, C.byref(params)))
+
+    # -- plumbing ------------------------------------------------------------------
+    def _check(self, rc, h="self"):
+        if rc != 0:
+            hh = self.h if h == "self" else None
+            msg = self.lib.picles_last_error(hh)
+            raise PiclesError(f"{ERR_NAMES.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.picles_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _wind(self, a):
+        if a is None:
+            return None
+        a = np.asarray(a, np.float64)
+        if a.shape != (self.ny, self.Nx):
+            a = np.broadcast_to(a, (self.ny, self.Nx))
+        return np.ascontiguousarray(a)
+
+    # -- the path ------------------------------------------------------------------
+    def seed(self, u0, v0):
+        a, b = self._wind(u0), self._wind(v0)
+        self._check(self.lib.picles_seed(self.h, _ptr(a), _ptr(b)))
+
+    def step(self, t, DT, u_t=None, v_t=None, u_t1=None, v_t1=None):
+        """State .= 0; time_step!  —  None reuses the winds already on the device."""
+        a = [self._wind(x) for x in (u_t, v_t, u_t1, v_t1)]
+        self._check(self.lib.picles_step(self.h, float(t), float(DT), *[_ptr(x) for x in a]))
+
+    def step_raw(self, t, DT, pu_t=None, pv_t=None, pu_t1=None, pv_t1=None):
+        """Same as step() with raw host pointers (ints), e.g. of pinned torch tensors."""
+        self._check(self.lib.picles_step(self.h, float(t), float(DT), pu_t, pv_t, pu_t1, pv_t1))
+
+    # phase-split form (multi-strip)
+    def upload_winds(self, u_t=None, v_t=None, u_t1=None, v_t1=None):
+        a = [self._wind(x) for x in (u_t, v_t, u_t1, v_t1)]
+        self._check(self.lib.picles_upload_winds(self.h, *[_ptr(x) for x in a]))
+
+    def step_advance(self, t, DT):
+        self._check(self.lib.picles_step_advance(self.h, float(t), float(DT)))
+
+    def halo_buffers(self):
+        p = [C.c_void_p() for _ in range(4)]
+        nb = C.c_int64()
+        self._check(self.lib.picles_halo_buffers(self.h, *[C.byref(x) for x in p], C.byref(nb)))
+        return [x.value for x in p], nb.value
+
+    def halo_pack(self):
+        self._check(self.lib.picles_halo_pack(self.h))
+
+    def halo_unpack(self):
+        self._check(self.lib.picles_halo_unpack(self.h))
+
+    def step_project_remesh(self, t, DT):
+        self._check(self.lib.picles_step_project_remesh(self.h, float(t), float(DT)))
+
+    def synchronize(self):
+        self._check(self.lib.picles_synchronize(self.h))
+
+    def reach(self):
+        r = C.c_int32()
+        self._check(self.lib.picles_get_reach(self.h, C.byref(r)))
+        return r.value
+
+    # -- accessors -----------------------------------------------------------------
+    def state(self):
+        S = np.empty((3, self.ny, self.Nx))
+        self._check(self.lib.picles_get_state(self.h, _ptr(S)))
+        return S
+
+    def set_state(self, S):
+        S = np.ascontiguousarray(np.asarray(S, np.float64).reshape(3, self.ny, self.Nx))
+        self._check(self.lib.picles_set_state(self.h, _ptr(S)))
+
+    def particles(self):
+        sh = (self.ny, self.Nx)
+        z = np.empty((5,) + sh)
+        t, dt = np.empty(sh), np.empty(sh)
+        flags = np.empty(sh, np.uint8)
+        status = np.empty(sh, np.int32)
+        self._check(self.lib.picles_get_particles(self.h, _ptr(z), _ptr(t), _ptr(dt), _ptr(flags), _ptr(status)))
+        return dict(z=z, t=t, dt=dt, flags=flags, status=status)
+
+    def counters(self):
+        c = PiclesCounters()
+        self._check(self.lib.picles_get_counters(self.h, C.byref(c)))
+        return c.as_dict()
+
+    def set_accumulate(self, on: bool):
+        """False: run! semantics (State zeroed before the step); True: bare time_step!."""
+        self._check(self.lib.picles_set_option(self.h, 1, int(bool(on))))
+
+    def zero_state(self):
+        self._check(self.lib.picles_zero_state(self.h))
+
+    def copy_dev(self, dst, src, nbytes):
+        self._check(self.lib.picles_copy_dev(self.h, dst, src, int(nbytes)))
+
+    def timer_start(self):
+        self._check(self.lib.picles_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(self.lib.picles_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        self._check(self.lib.picles_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
+
+    def measure_hbm_copy(self, mib=2048):
+        v = C.c_double()
+        self._check(self.lib.picles_measure_hbm_copy(self.h, int(mib), C.byref(v)))
+        return v.value
+
+    def energy_sum(self):
+        s = C.c_double()
+        self._check(self.lib.picles_state_energy_sum(self.h, C.byref(s)))
+        return s.value

@@ -1,0 +1,208 @@
+"""Shared builders for the tests: synthetic configurations, the oracle,
+the CPU host build of the device physics (tests/host_shim.cpp) and comparison helpers."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+
+import oracle
+from picles_b200 import FetchRelations as FR
+from picles_b200._abi import (BND_NONPERIODIC, BND_PERIODIC, BND_TRIPOLAR_NORTH, PiclesCounters,  # noqa: F401
+                              PiclesParams)
+from picles_b200.ParticleSystems import particle_waves_v5 as PW
+from picles_b200.params import make_params
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SHIM_SRC = os.path.join(HERE, "host_shim.cpp")
+SHIM_SO = os.path.join(HERE, "_build", "libhost_shim.so")
+
+
+def default_params(DT=600.0, solver="Tsit5", dt=1e-3, dtmin=1e-4, force_dtmin=True, periodic_boundary=False,
+                   on_persist=False, wind_min_squared=4.0, log_energy_maximum=math.log(17), defaults=None,
+                   timestep=None, minimal_state=None, C_phi=None, **switches):
+    """example_00_minimal.jl:17-67 settings unless overridden."""
+    pars, cid, _ = PW.ODEParameters(r_g=0.85)
+    if C_phi is not None:
+        pars["C_φ"] = C_phi
+    ps = PW.particle_equations(None, None, γ=cid.γ, q=cid.q, **switches)
+    ts = DT if timestep is None else timestep
+    sets = PW.ODESettings(Parameters=pars, log_energy_minimum=FR.MinimalWindsea(10, 10, DT)["lne"], saving_step=DT,
+                          timestep=ts, total_time=6 * 86400.0, dt=dt, dtmin=dtmin, force_dtmin=force_dtmin,
+                          solver=solver, wind_min_squared=wind_min_squared, log_energy_maximum=log_energy_maximum)
+    ms = FR.MinimalState(2, 2, ts) if minimal_state is None else minimal_state
+    return make_params(sets, ps, ms, defaults=defaults, periodic_boundary=periodic_boundary, on_persist=on_persist)
+
+
+def cartesian_grid(Nx, Ny, dx=2000.0, dy=2000.0, bx=BND_NONPERIODIC, by=BND_NONPERIODIC, ocean=None):
+    """TwoDCartesianGridMesh: x[i]=i*dx, y[j]=j*dy, total mask, uniform kernel diag(1/dx,1/dy)."""
+    ocean = np.ones((Ny, Nx), np.uint8) if ocean is None else np.asarray(ocean, np.uint8)
+    mask = oracle.make_boundaries(ocean, bx, by)
+    x = np.broadcast_to(np.arange(Nx) * dx, (Ny, Nx)).copy()
+    y = np.broadcast_to((np.arange(Ny) * dy)[:, None], (Ny, Nx)).copy()
+    return dict(Nx=Nx, Ny=Ny, bx=bx, by=by, mask=mask, x=x, y=y, M_const=np.array([1 / dx, 0.0, 0.0, 1 / dy]), M=None,
+                pc=None)
+
+
+def tripolar_grid(Nx, Ny, ocean=None, lat_min=-70.0, lat_max=89.0, R_earth=6.371e6, seed=0):
+    """Synthetic tripolar-like mesh: periodic x, tripolar-north y, per-node rotated kernel
+    [cos/dx sin/dy; -sin/dx cos/dy] (TripolarGridMOM6.jl:448-459) and great-circle coefficient
+    sign(φ)·min(sign(φ)·tand(φ),60)/R (spherical_grid_corrections.jl:13)."""
+    lon = -280.0 + (np.arange(Nx) + 0.5) * 360.0 / Nx
+    lat = lat_min + (np.arange(Ny) + 0.5) * (lat_max - lat_min) / Ny
+    LON, LAT = np.meshgrid(lon, lat)
+    cap = np.clip((LAT - 60.0) / 30.0, 0.0, 1.0)
+    angle = 40.0 * cap * np.sin(np.deg2rad(2 * (LON + 280.0)))
+    dlon, dlat = 360.0 / Nx, (lat_max - lat_min) / Ny
+    dx = np.maximum(R_earth * np.cos(np.deg2rad(LAT)) * np.deg2rad(dlon), 2000.0)
+    dy = np.full_like(dx, R_earth * np.deg2rad(dlat))
+    ca, sa = np.cos(angle * np.pi / 180), np.sin(angle * np.pi / 180)
+    M = np.stack([ca / dx, sa / dy, -sa / dx, ca / dy])
+    sgn = np.sign(LAT)
+    pc = (sgn * np.minimum(sgn * np.tan(np.deg2rad(LAT)), 60.0)) / 6.3710e6
+    ocean = np.ones((Ny, Nx), np.uint8) if ocean is None else np.asarray(ocean, np.uint8)
+    mask = oracle.make_boundaries(ocean, BND_PERIODIC, BND_TRIPOLAR_NORTH)
+    return dict(Nx=Nx, Ny=Ny, bx=BND_PERIODIC, by=BND_TRIPOLAR_NORTH, mask=mask, x=LON, y=LAT, M=M, M_const=None, pc=pc)
+
+
+def make_oracle(grid, P, variant="default", threads=1):
+    return oracle.Oracle(grid["Nx"], grid["Ny"], grid["bx"], grid["by"], grid["mask"], P, M=grid["M"],
+                         M_const=grid["M_const"], pc=grid["pc"], variant=variant, threads=threads)
+
+
+# ---- host build of the device physics ------------------------------------------------
+
+def _build_shim():
+    deps = [SHIM_SRC, os.path.join(ROOT, "picles_b200", "csrc", "physics.h"),
+            os.path.join(ROOT, "picles_b200", "csrc", "pmath.h"), os.path.join(ROOT, "include", "picles_b200.h")]
+    if os.path.exists(SHIM_SO) and all(os.path.getmtime(SHIM_SO) >= os.path.getmtime(d) for d in deps):
+        return
+    os.makedirs(os.path.dirname(SHIM_SO), exist_ok=True)
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-mfma", "-shared", "-o",
+           SHIM_SO, SHIM_SRC]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host shim build failed:\n" + r.stderr)
+
+
+_shim = None
+
+
+def shim_lib():
+    global _shim
+    if _shim is None:
+        _build_shim()
+        lib = C.CDLL(SHIM_SO)
+        vp, d, i32, i64 = C.c_void_p, C.c_double, C.c_int, C.c_int64
+        lib.shim_create.restype = vp
+        lib.shim_create.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(PiclesParams)]
+        lib.shim_destroy.argtypes = [vp]
+        lib.shim_set_accumulate.argtypes = [vp, i32]
+        lib.shim_seed.argtypes = [vp, vp, vp]
+        lib.shim_step.argtypes = [vp, d, d, vp, vp, vp, vp]
+        lib.shim_get_state.argtypes = [vp, vp]
+        lib.shim_get_particles.argtypes = [vp] + [vp] * 7
+        lib.shim_get_tally.argtypes = [vp, vp]
+        lib.shim_corner_target.restype = i64
+        lib.shim_corner_target.argtypes = [i32, i32, i32, i32, i64, i64]
+        lib.shim_rhs.argtypes = [C.POINTER(PiclesParams), vp, d, d, vp, d, vp]
+        lib.shim_pack_roundtrip.argtypes = [i32, i32, i32, vp]
+        _shim = lib
+    return _shim
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+TALLY_NAMES = ["n_integrated", "n_substeps", "n_rejects", "n_rhs", "n_reseed_advance", "n_fixups", "n_failed",
+               "n_deposited", "n_remesh_A", "n_remesh_B", "n_remesh_C", "n_remesh_D", "reach", "max_attempts"]
+
+
+class HostShim:
+    """The device code path (physics.h) executed on the CPU, optionally split in y-strips."""
+
+    def __init__(self, grid, P, nstrips=1, halo=0):
+        self.lib = shim_lib()
+        self.Nx, self.Ny = grid["Nx"], grid["Ny"]
+        m = np.ascontiguousarray(grid["mask"], dtype=np.uint8)
+        M = np.ascontiguousarray(grid["M"], dtype=np.float64) if grid["M"] is not None else None
+        Mc = np.ascontiguousarray(grid["M_const"], dtype=np.float64) if grid["M_const"] is not None else None
+        pc = np.ascontiguousarray(grid["pc"], dtype=np.float64) if grid["pc"] is not None else None
+        self._keep = (m, M, Mc, pc)
+        self.h = self.lib.shim_create(self.Nx, self.Ny, grid["bx"], grid["by"], nstrips, halo, _p(m), _p(M), _p(Mc),
+                                      _p(pc), C.byref(P))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.shim_destroy(self.h)
+            self.h = None
+
+    def _full(self, a):
+        return np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.float64), (self.Ny, self.Nx)))
+
+    def set_accumulate(self, on):
+        self.lib.shim_set_accumulate(self.h, int(bool(on)))
+
+    def seed(self, u0, v0):
+        a, b = self._full(u0), self._full(v0)
+        self.lib.shim_seed(self.h, _p(a), _p(b))
+
+    def step(self, t, DT, u_t, v_t, u_t1, v_t1):
+        a = [self._full(x) for x in (u_t, v_t, u_t1, v_t1)]
+        self.lib.shim_step(self.h, float(t), float(DT), *[_p(x) for x in a])
+
+    def state(self):
+        S = np.empty((3, self.Ny, self.Nx))
+        self.lib.shim_get_state(self.h, _p(S))
+        return S
+
+    def particles(self):
+        sh = (self.Ny, self.Nx)
+        z = np.empty((5,) + sh)
+        t, dt, qold = np.empty(sh), np.empty(sh), np.empty(sh)
+        it = np.empty(sh, np.int32)
+        fl = np.empty(sh, np.uint8)
+        st = np.empty(sh, np.int32)
+        self.lib.shim_get_particles(self.h, _p(z), _p(t), _p(dt), _p(qold), _p(it), _p(fl), _p(st))
+        return dict(z=z, t=t, dt=dt, qold=qold, iter=it, flags=fl, status=st)
+
+    def counters(self):
+        out = np.empty(14, np.int32)
+        self.lib.shim_get_tally(self.h, _p(out))
+        return dict(zip(TALLY_NAMES, [int(v) for v in out]))
+
+
+def bits_equal(a, b):
+    """bit-for-bit equality of two float64 arrays (NaN payloads included)."""
+    a = np.ascontiguousarray(a, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def compare_models(ref, dut, check_aux=True):
+    """Assert that `dut` (HostShim or the B200 engine adaptor) reproduces `ref` (Oracle) exactly."""
+    Sr, Sd = ref.state(), dut.state()
+    assert bits_equal(Sr, Sd), f"State differs: max abs diff {np.nanmax(np.abs(Sr - Sd))}"
+    pr, pd = ref.particles(), dut.particles()
+    exists = (pr["flags"] & 8) != 0  # PF_ACTIVE: only iterated particles are meaningful
+    for k in range(5):
+        assert bits_equal(pr["z"][k][exists], pd["z"][k][exists]), f"particle component {k} differs"
+    assert bits_equal(pr["t"][exists], pd["t"][exists])
+    assert np.array_equal(pr["flags"][exists], pd["flags"][exists])
+    assert np.array_equal(pr["status"][exists], pd["status"][exists])
+    # dt is only meaningful while no auto_dt_reset! is pending
+    live = exists & ((pr["flags"] & 4) == 0)
+    assert bits_equal(pr["dt"][live], pd["dt"][live])
+    if check_aux and "qold" in pd:
+        ar = ref.aux()
+        assert bits_equal(ar["qold"][exists], pd["qold"][exists])
+        assert np.array_equal(ar["iter"][exists], pd["iter"][exists].astype(np.int64))
+    cr, cd = ref.counters(), dut.counters()
+    for name in TALLY_NAMES:
+        assert cr[name] == cd[name], f"counter {name}: oracle {cr[name]} vs device path {cd[name]}"

@@ -1,0 +1,219 @@
+/*
+ * host_shim.cpp — TEST-ONLY host build of picles_b200/csrc/physics.h.
+ *
+ * Runs the product's per-particle / per-node device functions (advance_particle,
+ * gather_node, remesh_particle, seed_particle) on the CPU with the same data layout and
+ * strip/halo decomposition the CUDA kernels use, so the bit-exact comparison with the
+ * oracle and the multi-strip logic can be checked without a GPU.  This file is not part
+ * of the product and is never loaded by it.
+ */
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../picles_b200/csrc/physics.h"
+
+using namespace picles;
+
+struct Strip {
+    int j0, ny, halo;
+    std::vector<double> z[5], t, dt, qold, ut, vt, ut1, vt1, rec[5], S[3], M[4], pc;
+    std::vector<int32_t> iter, cell;
+    std::vector<uint8_t> flags, status, mask;
+};
+
+struct Shim {
+    int Nx, Ny, bx, by, nstrips, halo;
+    picles_params_t P;
+    double Mc[4];
+    bool perM, hasPc;
+    std::vector<Strip> s;
+    Tally tally;
+    int accumulate = 0;
+};
+
+static void load(const Strip& s, int64_t l, Particle& p) {
+    p.u0 = s.z[0][l]; p.u1 = s.z[1][l]; p.u2 = s.z[2][l]; p.u3 = s.z[3][l]; p.u4 = s.z[4][l];
+    p.t = s.t[l]; p.dt = s.dt[l]; p.qold = s.qold[l]; p.iter = s.iter[l]; p.flags = s.flags[l]; p.status = s.status[l];
+}
+static void store(Strip& s, int64_t l, const Particle& p) {
+    s.z[0][l] = p.u0; s.z[1][l] = p.u1; s.z[2][l] = p.u2; s.z[3][l] = p.u3; s.z[4][l] = p.u4;
+    s.t[l] = p.t; s.dt[l] = p.dt; s.qold[l] = p.qold; s.iter[l] = p.iter; s.flags[l] = p.flags; s.status[l] = p.status;
+}
+static void tally_add(Tally& a, const Tally& b) {
+    a.integrated += b.integrated; a.substeps += b.substeps; a.rejects += b.rejects; a.rhs += b.rhs;
+    a.reseed += b.reseed; a.fixups += b.fixups; a.failed += b.failed; a.deposited += b.deposited;
+    a.A += b.A; a.B += b.B; a.C += b.C; a.D += b.D;
+    if (b.reach > a.reach) a.reach = b.reach;
+    if (b.max_attempts > a.max_attempts) a.max_attempts = b.max_attempts;
+}
+
+extern "C" {
+
+Shim* shim_create(int Nx, int Ny, int bx, int by, int nstrips, int halo, const uint8_t* mask, const double* M,
+                  const double* M_const, const double* pc, const picles_params_t* P) {
+    Shim* h = new Shim();
+    h->Nx = Nx; h->Ny = Ny; h->bx = bx; h->by = by; h->nstrips = nstrips; h->halo = (nstrips > 1) ? halo : 0;
+    h->P = *P;
+    h->perM = (M != nullptr);
+    h->hasPc = (pc != nullptr);
+    if (M_const) memcpy(h->Mc, M_const, sizeof h->Mc);
+    h->s.resize(nstrips);
+    int64_t plane = (int64_t)Nx * Ny;
+    for (int r = 0; r < nstrips; r++) {
+        Strip& s = h->s[r];
+        s.j0 = (int)((int64_t)Ny * r / nstrips);
+        int j1 = (int)((int64_t)Ny * (r + 1) / nstrips);
+        s.ny = j1 - s.j0; s.halo = h->halo;
+        int64_t n = (int64_t)Nx * s.ny, ne = (int64_t)Nx * (s.ny + 2 * s.halo);
+        for (int k = 0; k < 5; k++) { s.z[k].assign(n, 0.0); s.rec[k].assign(ne, 0.0); }
+        s.t.assign(n, 0.0); s.dt.assign(n, 0.0); s.qold.assign(n, 0.0);
+        s.ut.assign(n, 0.0); s.vt.assign(n, 0.0); s.ut1.assign(n, 0.0); s.vt1.assign(n, 0.0);
+        for (int k = 0; k < 3; k++) s.S[k].assign(n, 0.0);
+        s.iter.assign(n, 0); s.cell.assign(ne, PH_CELL_INVALID);
+        s.flags.assign(n, 0); s.status.assign(n, 0);
+        s.mask.assign(mask + (int64_t)s.j0 * Nx, mask + (int64_t)s.j0 * Nx + n);
+        if (M) for (int k = 0; k < 4; k++) s.M[k].assign(M + k * plane + (int64_t)s.j0 * Nx, M + k * plane + (int64_t)s.j0 * Nx + n);
+        if (pc) s.pc.assign(pc + (int64_t)s.j0 * Nx, pc + (int64_t)s.j0 * Nx + n);
+    }
+    tally_zero(h->tally);
+    return h;
+}
+void shim_destroy(Shim* h) { delete h; }
+void shim_set_accumulate(Shim* h, int on) { h->accumulate = on ? 1 : 0; }
+
+void shim_seed(Shim* h, const double* u0, const double* v0) {
+    for (auto& s : h->s) {
+        int64_t n = (int64_t)h->Nx * s.ny, off = (int64_t)s.j0 * h->Nx;
+        for (int64_t l = 0; l < n; l++) {
+            Particle p;
+            double e, mx, my;
+            seed_particle(h->P, s.mask[l], u0[off + l], v0[off + l], p, e, mx, my);
+            store(s, l, p);
+            s.S[0][l] = e; s.S[1][l] = mx; s.S[2][l] = my;
+        }
+        std::fill(s.cell.begin(), s.cell.end(), PH_CELL_INVALID);
+    }
+}
+
+void shim_step(Shim* h, double t, double DT, const double* u_t, const double* v_t, const double* u_t1, const double* v_t1) {
+    (void)t;
+    const int Nx = h->Nx;
+    Tally T;
+    tally_zero(T);
+    /* advance */
+    for (auto& s : h->s) {
+        int64_t n = (int64_t)Nx * s.ny, off = (int64_t)s.j0 * Nx;
+        for (int64_t l = 0; l < n; l++) {
+            if (!(s.flags[l] & PICLES_PF_ACTIVE)) continue;
+            Particle p;
+            load(s, l, p);
+            double M[4];
+            if (h->perM) { M[0] = s.M[0][l]; M[1] = s.M[1][l]; M[2] = s.M[2][l]; M[3] = s.M[3][l]; }
+            else memcpy(M, h->Mc, sizeof M);
+            double pc = h->hasPc ? s.pc[l] : 0.0;
+            Record r;
+            Tally c;
+            tally_zero(c);
+            if (h->P.solver == PICLES_SOLVER_DP5)
+                advance_particle<DP5Tab>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l], v_t1[off + l], M, pc, r, c);
+            else
+                advance_particle<Tsit5Tab>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l], v_t1[off + l], M, pc, r, c);
+            tally_add(T, c);
+            store(s, l, p);
+            int64_t le = l + (int64_t)s.halo * Nx;
+            s.rec[0][le] = r.e; s.rec[1][le] = r.mx; s.rec[2][le] = r.my; s.rec[3][le] = r.wxc; s.rec[4][le] = r.wyc;
+            s.cell[le] = r.cell;
+        }
+    }
+    /* halo exchange: my first/last H owned rows -> neighbour's upper/lower halo rows */
+    int H = h->halo, ns = h->nstrips;
+    if (ns > 1 && H > 0) {
+        for (int r = 0; r < ns; r++) {
+            Strip& s = h->s[r];
+            int64_t m = (int64_t)H * Nx;
+            int lo = r - 1, hi = r + 1;
+            if (h->by == PICLES_BND_PERIODIC) { lo = (lo + ns) % ns; hi = hi % ns; }
+            if (lo >= 0) { /* my first H owned rows -> upper halo of the lower neighbour */
+                Strip& d = h->s[lo];
+                int64_t src = (int64_t)H * Nx, dst = (int64_t)(d.ny + H) * Nx;
+                for (int k = 0; k < 5; k++) memcpy(&d.rec[k][dst], &s.rec[k][src], m * 8);
+                memcpy(&d.cell[dst], &s.cell[src], m * 4);
+            }
+            if (hi < ns) { /* my last H owned rows -> lower halo of the upper neighbour */
+                Strip& d = h->s[hi];
+                int64_t src = (int64_t)s.ny * Nx, dst = 0;
+                for (int k = 0; k < 5; k++) memcpy(&d.rec[k][dst], &s.rec[k][src], m * 8);
+                memcpy(&d.cell[dst], &s.cell[src], m * 4);
+            }
+        }
+    }
+    int R = T.reach < PH_REACH_MAX ? T.reach : PH_REACH_MAX;
+    if (ns > 1 && R > H) R = H;
+    /* projection gather + remesh */
+    for (auto& s : h->s) {
+        RecView V;
+        V.Nx = Nx; V.Ny = h->Ny; V.bx = h->bx; V.by = h->by; V.j0 = s.j0; V.ny = s.ny; V.halo = s.halo;
+        V.e = s.rec[0].data(); V.mx = s.rec[1].data(); V.my = s.rec[2].data(); V.wx = s.rec[3].data(); V.wy = s.rec[4].data();
+        V.cell = s.cell.data();
+        int64_t n = (int64_t)Nx * s.ny, off = (int64_t)s.j0 * Nx;
+        for (int64_t l = 0; l < n; l++) {
+            int I = (int)(l % Nx) + 1, J = (int)(l / Nx) + 1 + s.j0;
+            if (!h->accumulate) { s.S[0][l] = 0.0; s.S[1][l] = 0.0; s.S[2][l] = 0.0; }
+            gather_node(V, I, J, R, h->P.periodic_boundary ? 2 : 1, s.S[0][l], s.S[1][l], s.S[2][l]);
+        }
+        for (int64_t l = 0; l < n; l++) {
+            if (!(s.flags[l] & PICLES_PF_ACTIVE)) continue;
+            Particle p;
+            load(s, l, p);
+            Tally c;
+            tally_zero(c);
+            remesh_particle(h->P, p, s.S[0][l], s.S[1][l], s.S[2][l], u_t[off + l], v_t[off + l], DT, c);
+            tally_add(T, c);
+            store(s, l, p);
+        }
+    }
+    h->tally = T;
+}
+
+void shim_get_state(const Shim* h, double* S) {
+    int64_t plane = (int64_t)h->Nx * h->Ny;
+    for (auto& s : h->s) {
+        int64_t n = (int64_t)h->Nx * s.ny, off = (int64_t)s.j0 * h->Nx;
+        for (int k = 0; k < 3; k++) memcpy(S + k * plane + off, s.S[k].data(), n * 8);
+    }
+}
+void shim_get_particles(const Shim* h, double* z, double* t, double* dt, double* qold, int32_t* iter, uint8_t* flags,
+                        int32_t* status) {
+    int64_t plane = (int64_t)h->Nx * h->Ny;
+    for (auto& s : h->s) {
+        int64_t n = (int64_t)h->Nx * s.ny, off = (int64_t)s.j0 * h->Nx;
+        for (int k = 0; k < 5; k++) memcpy(z + k * plane + off, s.z[k].data(), n * 8);
+        memcpy(t + off, s.t.data(), n * 8);
+        memcpy(dt + off, s.dt.data(), n * 8);
+        memcpy(qold + off, s.qold.data(), n * 8);
+        memcpy(iter + off, s.iter.data(), n * 4);
+        memcpy(flags + off, s.flags.data(), n);
+        for (int64_t l = 0; l < n; l++) status[off + l] = s.status[l];
+    }
+}
+/* integrated, substeps, rejects, rhs, reseed, fixups, failed, deposited, A, B, C, D, reach, max_attempts */
+void shim_get_tally(const Shim* h, int32_t* out14) { memcpy(out14, &h->tally, 14 * sizeof(int32_t)); }
+
+int64_t shim_corner_target(int Nx, int Ny, int bx, int by, int64_t i, int64_t j) {
+    int64_t ii, jj;
+    if (!corner_target(Nx, Ny, bx, by, i, j, ii, jj)) return -1;
+    return (ii - 1) + (jj - 1) * (int64_t)Nx;
+}
+void shim_rhs(const picles_params_t* P, const double* z, double u, double v, const double* M, double pc, double* dz) {
+    rhs3(*P, z[0], z[1], z[2], u, v, pc, dz[0], dz[1], dz[2]);
+    prop(*P, M, z[1], z[2], dz[3], dz[4]);
+}
+void shim_pack_roundtrip(int32_t fx, int32_t fy, int cls, int32_t* out3) {
+    int32_t c = pack_cell(fx, fy, cls);
+    int k;
+    unpack_cell(c, out3[0], out3[1], k);
+    out3[2] = k;
+}
+}
