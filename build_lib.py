@@ -27,11 +27,11 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, extra=()) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra=(), out: str | None = None) -> str:
+    if out is None and not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", out or OUT] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         print(" ".join(cmd))
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose or r.stderr.strip():
         sys.stderr.write(r.stderr)
-    return OUT
+    return out or OUT
 
 
 if __name__ == "__main__":

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpicles_b200.so")
+LIB_PATH = os.environ.get("PICLES_B200_LIB", os.path.join(HERE, "libpicles_b200.so"))
 
 ABI_VERSION = 1
 

@@ -29,6 +29,18 @@
 #include "../../include/picles_b200.h"
 #include "pmath.h"
 
+#if defined(__CUDACC__)
+#define PM_HD_NOINLINE_DECL __host__ __device__ __noinline__
+#else
+#define PM_HD_NOINLINE_DECL static inline
+#endif
+
+#if defined(__CUDACC__)
+#define PM_HDM __host__ __device__ __forceinline__
+#else
+#define PM_HDM inline
+#endif
+
 #define PH_QOLDINIT 1e-4
 #define PH_CELL_INVALID ((int32_t)-1)
 #define PH_CELL_BIAS 8192
@@ -37,36 +49,68 @@
 namespace picles {
 
 /* ---- tableaus (OrdinaryDiffEq Tsit5ConstantCache / DP5ConstantCache) ----- */
-struct Tsit5Tab {
-    static constexpr double c1 = 0.161, c2 = 0.327, c3 = 0.9, c4 = 0.9800255409045097;
-    static constexpr double a21 = 0.161;
-    static constexpr double a31 = -0.008480655492356989, a32 = 0.335480655492357;
-    static constexpr double a41 = 2.8971530571054935, a42 = -6.359448489975075, a43 = 4.3622954328695815;
-    static constexpr double a51 = 5.325864828439257, a52 = -11.748883564062828, a53 = 7.4955393428898365,
-                            a54 = -0.09249506636175525;
-    static constexpr double a61 = 5.86145544294642, a62 = -12.92096931784711, a63 = 8.159367898576159,
-                            a64 = -0.071584973281401, a65 = -0.028269050394068383;
-    static constexpr double a71 = 0.09646076681806523, a72 = 0.01, a73 = 0.4798896504144996,
-                            a74 = 1.379008574103742, a75 = -3.290069515436081, a76 = 2.324710524099774;
-    static constexpr double bt1 = -0.00178001105222577714, bt2 = -0.0008164344596567469,
-                            bt3 = 0.007880878010261995, bt4 = -0.1447110071732629, bt5 = 0.5823571654525552,
-                            bt6 = -0.45808210592918697, bt7 = 0.015151515151515152;
-    static constexpr double beta1 = 0.14, beta2 = 0.08;
+/* a[s][j]: weight of k_j in the argument of stage s (s = 2..7, j = 1..s-1; row 7 = b);
+   c[s-1]: time fraction of stage s; bt[j]: error weights (btilde). */
+struct Tableau {
+    double c[8];
+    double a[8][8];
+    double bt[8];
+    double beta1, beta2;
 };
-struct DP5Tab {
-    static constexpr double c1 = 0.2, c2 = 0.3, c3 = 0.8, c4 = 8.0 / 9.0;
-    static constexpr double a21 = 0.2;
-    static constexpr double a31 = 3.0 / 40.0, a32 = 9.0 / 40.0;
-    static constexpr double a41 = 44.0 / 45.0, a42 = -56.0 / 15.0, a43 = 32.0 / 9.0;
-    static constexpr double a51 = 19372.0 / 6561.0, a52 = -25360.0 / 2187.0, a53 = 64448.0 / 6561.0,
-                            a54 = -212.0 / 729.0;
-    static constexpr double a61 = 9017.0 / 3168.0, a62 = -355.0 / 33.0, a63 = 46732.0 / 5247.0,
-                            a64 = 49.0 / 176.0, a65 = -5103.0 / 18656.0;
-    static constexpr double a71 = 35.0 / 384.0, a72 = 0.0, a73 = 500.0 / 1113.0, a74 = 125.0 / 192.0,
-                            a75 = -2187.0 / 6784.0, a76 = 11.0 / 84.0;
-    static constexpr double bt1 = -71.0 / 57600.0, bt2 = 0.0, bt3 = 71.0 / 16695.0, bt4 = -71.0 / 1920.0,
-                            bt5 = 17253.0 / 339200.0, bt6 = -22.0 / 525.0, bt7 = 1.0 / 40.0;
-    static constexpr double beta1 = 0.17, beta2 = 0.04;
+#define PH_TABLEAU_INIT                                                                                          \
+    {                                                                                                            \
+        /* Tsit5 */                                                                                              \
+        {{0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0, 0},                                                \
+         {{0}, {0},                                                                                              \
+          {0, 0.161},                                                                                            \
+          {0, -0.008480655492356989, 0.335480655492357},                                                         \
+          {0, 2.8971530571054935, -6.359448489975075, 4.3622954328695815},                                       \
+          {0, 5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525},                 \
+          {0, 5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383}, \
+          {0, 0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081,              \
+           2.324710524099774}},                                                                                  \
+         {0, -0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,         \
+          0.5823571654525552, -0.45808210592918697, 0.015151515151515152},                                       \
+         0.14, 0.08},                                                                                            \
+        /* DP5 */                                                                                                \
+        {{0, 0.2, 0.3, 0.8, 8.0 / 9.0, 1.0, 1.0, 0},                                                             \
+         {{0}, {0},                                                                                              \
+          {0, 0.2},                                                                                              \
+          {0, 3.0 / 40.0, 9.0 / 40.0},                                                                           \
+          {0, 44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0},                                                            \
+          {0, 19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0},                            \
+          {0, 9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0},                \
+          {0, 35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}},                 \
+         {0, -71.0 / 57600.0, 0.0, 71.0 / 16695.0, -71.0 / 1920.0, 17253.0 / 339200.0, -22.0 / 525.0,            \
+          1.0 / 40.0},                                                                                           \
+         0.17, 0.04}                                                                                             \
+    }
+#if defined(__CUDACC__)
+__constant__ Tableau d_tableaus[2] = PH_TABLEAU_INIT;
+#endif
+static const Tableau h_tableaus[2] = PH_TABLEAU_INIT;
+
+PM_HD const Tableau& tableau(int solver) {
+    int k = (solver == PICLES_SOLVER_DP5) ? 1 : 0;
+#if defined(__CUDA_ARCH__)
+    return d_tableaus[k];
+#else
+    return h_tableaus[k];
+#endif
+}
+
+/* stage-derivative store k_j[c], j = 1..7, c = 0..2: shared memory on the device (one
+   column per thread), a local array on the host */
+struct KLocal {
+    double k[7][3];
+    PM_HDM double get(int j, int c) const { return k[j - 1][c]; }
+    PM_HDM void set(int j, int c, double v) { k[j - 1][c] = v; }
+};
+struct KStrided {
+    double* base; /* &smem[threadIdx.x] */
+    int stride;   /* blockDim.x */
+    PM_HDM double get(int j, int c) const { return base[((j - 1) * 3 + c) * stride]; }
+    PM_HDM void set(int j, int c, double v) { base[((j - 1) * 3 + c) * stride] = v; }
 };
 
 /* per-thread view of one particle (ODEIntegrator fields that survive between steps) */
@@ -104,7 +148,8 @@ struct Record {
 };
 
 /* ---- FetchRelations.get_initial_windsea(...; particle_state=true) ---------- */
-PM_HD void windsea(double U10, double V10, double time_scale, double& lne, double& cgx, double& cgy) {
+/* cold: reseeds only — kept out of line so the advance kernel's hot loop stays small */
+PM_HD_NOINLINE_DECL void windsea(double U10, double V10, double time_scale, double& lne, double& cgx, double& cgy) {
     double U_amp = sqrt(U10 * U10 + V10 * V10);
     U_amp = (U_amp < 0.1) ? 0.1 : U_amp;
     time_scale = fabs(time_scale);
@@ -241,6 +286,13 @@ PM_HD void f3(const picles_params_t& P, const Wind& w, double pc, double lne, do
     rhs3(P, lne, cx, cy, u, v, pc, d0, d1, d2);
 }
 
+/* cold (out-of-loop) right-hand side: one shared non-inlined copy for the FSAL reset and
+   the initial-step heuristic, so the hot stage loop is the only inlined copy */
+PM_HD_NOINLINE_DECL void f3_cold(const picles_params_t& P, const Wind& w, double pc, double lne, double cx, double cy,
+                                 double ts, double& d0, double& d1, double& d2) {
+    f3(P, w, pc, lne, cx, cy, ts, d0, d1, d2);
+}
+
 PM_HD double rms5(double a, double b, double c, double d, double e) {
     double s = 0.0;
     s += a * a;
@@ -252,7 +304,7 @@ PM_HD double rms5(double a, double b, double c, double d, double e) {
 }
 
 /* ode_determine_initdt (Hairer); f0 = f(u,t) supplied as (k0..k4) */
-PM_HD double initdt(const picles_params_t& P, const Wind& w, const double* M, double pc, const Particle& p,
+PM_HD_NOINLINE_DECL double initdt(const picles_params_t& P, const Wind& w, const double* M, double pc, const Particle& p,
                     double k0, double k1, double k2, double k3, double k4, int32_t& nrhs) {
     double dtmin = pm_nextfloat_pos(P.dtmin);
     const double smalldt = 1e-6;
@@ -271,7 +323,7 @@ PM_HD double initdt(const picles_params_t& P, const Wind& w, const double* M, do
     double a1 = fma(dt0, k1, p.u1);
     double a2 = fma(dt0, k2, p.u2);
     double f0, f1, f2, f3x, f4x;
-    f3(P, w, pc, a0, a1, a2, p.t + dt0, f0, f1, f2);
+    f3_cold(P, w, pc, a0, a1, a2, p.t + dt0, f0, f1, f2);
     prop(P, M, a1, a2, f3x, f4x);
     nrhs++;
     int same = (k0 == f0) & (k1 == f1) & (k2 == f2) & (k3 == f3x) & (k4 == f4x);
@@ -284,27 +336,32 @@ PM_HD double initdt(const picles_params_t& P, const Wind& w, const double* M, do
     return pm_max(dtmin, pm_min(pm_min(100.0 * dt0, dt1), P.dtmax));
 }
 
-/* one 3-component stage argument: uprev + dt*(sum a_j k_j) with the fma chain of the spec */
-#define PH_STAGE3(out, U, expr_inner) out = fma(dt, (expr_inner), U)
-
-/* step!(integrator, DT, true): advance particle p from p.t to p.t + DT */
-template <class T>
+/* step!(integrator, DT, true): advance particle p from p.t to p.t + DT.
+   One runtime loop over the 6 new stages per attempt (FSAL), stage derivatives of
+   (lne, c̄_x, c̄_y) in K; the propagation derivatives k_j[3:4] = M*c̄_j are folded into
+   the running sums of stage 7 (x7,y7) and of the error estimate (xe,ye) as each k_j
+   appears — the same fma chain as storing them, without the storage. */
+template <class KS>
 PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, double pc, double DT, Particle& p,
-                     Tally& c) {
+                     Tally& c, KS& K) {
     if (p.status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE)) return;
+    const Tableau& T = tableau(P.solver);
     double t = p.t;
     const double tstop = t + DT;
     double u0 = p.u0, u1 = p.u1, u2 = p.u2, u3 = p.u3, u4 = p.u4;
     int32_t nrhs = 0;
     /* u_modified -> reset_fsal!: k1 = f(u, t) */
-    double k10, k11, k12;
-    f3(P, w, pc, u0, u1, u2, t, k10, k11, k12);
-    nrhs++;
+    {
+        double k10, k11, k12;
+        f3_cold(P, w, pc, u0, u1, u2, t, k10, k11, k12);
+        nrhs++;
+        K.set(1, 0, k10); K.set(1, 1, k11); K.set(1, 2, k12);
+    }
     double dt = p.dt;
     if (p.flags & PICLES_PF_DT_RESET) {
         double k13, k14;
         prop(P, M, u1, u2, k13, k14);
-        dt = initdt(P, w, M, pc, p, k10, k11, k12, k13, k14, nrhs);
+        dt = initdt(P, w, M, pc, p, K.get(1, 0), K.get(1, 1), K.get(1, 2), k13, k14, nrhs);
         p.flags &= (uint8_t)~PICLES_PF_DT_RESET;
     }
     double qold = p.qold;
@@ -324,84 +381,53 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
         if (!P.force_dtmin && dt <= P.dtmin && (t + dt < tstop)) { p.status |= PICLES_PST_DTMIN; c.failed++; break; }
         attempts++;
 
-        /* perform_step!; propagation derivatives k_j[3:4] = M*c̄_j are folded into the
-           running sums of stage 7 (x7,y7) and of the error estimate (xe,ye) as each k_j
-           appears — the same fma chain as storing them, without the registers */
+        /* perform_step! */
         double kx, ky;
         prop(P, M, u1, u2, kx, ky);
-        double x7 = T::a71 * kx, y7 = T::a71 * ky;
-        double xe = T::bt1 * kx, ye = T::bt1 * ky;
-        double a0, a1, a2; /* stage argument */
-        double k20, k21, k22, k30, k31, k32, k40, k41, k42, k50, k51, k52, k60, k61, k62, k70, k71, k72;
-        {
-            double a = dt * T::a21;
-            a0 = fma(a, k10, u0); a1 = fma(a, k11, u1); a2 = fma(a, k12, u2);
-            f3(P, w, pc, a0, a1, a2, fma(T::c1, dt, t), k20, k21, k22);
-            prop(P, M, a1, a2, kx, ky);
-            if (T::a72 != 0.0) { x7 = fma(T::a72, kx, x7); y7 = fma(T::a72, ky, y7); }
-            if (T::bt2 != 0.0) { xe = fma(T::bt2, kx, xe); ye = fma(T::bt2, ky, ye); }
-        }
-        {
-            PH_STAGE3(a0, u0, fma(T::a32, k20, T::a31 * k10));
-            PH_STAGE3(a1, u1, fma(T::a32, k21, T::a31 * k11));
-            PH_STAGE3(a2, u2, fma(T::a32, k22, T::a31 * k12));
-            f3(P, w, pc, a0, a1, a2, fma(T::c2, dt, t), k30, k31, k32);
-            prop(P, M, a1, a2, kx, ky);
-            x7 = fma(T::a73, kx, x7); y7 = fma(T::a73, ky, y7);
-            xe = fma(T::bt3, kx, xe); ye = fma(T::bt3, ky, ye);
-        }
-        {
-            PH_STAGE3(a0, u0, fma(T::a43, k30, fma(T::a42, k20, T::a41 * k10)));
-            PH_STAGE3(a1, u1, fma(T::a43, k31, fma(T::a42, k21, T::a41 * k11)));
-            PH_STAGE3(a2, u2, fma(T::a43, k32, fma(T::a42, k22, T::a41 * k12)));
-            f3(P, w, pc, a0, a1, a2, fma(T::c3, dt, t), k40, k41, k42);
-            prop(P, M, a1, a2, kx, ky);
-            x7 = fma(T::a74, kx, x7); y7 = fma(T::a74, ky, y7);
-            xe = fma(T::bt4, kx, xe); ye = fma(T::bt4, ky, ye);
-        }
-        {
-            PH_STAGE3(a0, u0, fma(T::a54, k40, fma(T::a53, k30, fma(T::a52, k20, T::a51 * k10))));
-            PH_STAGE3(a1, u1, fma(T::a54, k41, fma(T::a53, k31, fma(T::a52, k21, T::a51 * k11))));
-            PH_STAGE3(a2, u2, fma(T::a54, k42, fma(T::a53, k32, fma(T::a52, k22, T::a51 * k12))));
-            f3(P, w, pc, a0, a1, a2, fma(T::c4, dt, t), k50, k51, k52);
-            prop(P, M, a1, a2, kx, ky);
-            x7 = fma(T::a75, kx, x7); y7 = fma(T::a75, ky, y7);
-            xe = fma(T::bt5, kx, xe); ye = fma(T::bt5, ky, ye);
-        }
-        {
-            PH_STAGE3(a0, u0, fma(T::a65, k50, fma(T::a64, k40, fma(T::a63, k30, fma(T::a62, k20, T::a61 * k10)))));
-            PH_STAGE3(a1, u1, fma(T::a65, k51, fma(T::a64, k41, fma(T::a63, k31, fma(T::a62, k21, T::a61 * k11)))));
-            PH_STAGE3(a2, u2, fma(T::a65, k52, fma(T::a64, k42, fma(T::a63, k32, fma(T::a62, k22, T::a61 * k12)))));
-            f3(P, w, pc, a0, a1, a2, t + dt, k60, k61, k62);
-            prop(P, M, a1, a2, kx, ky);
-            x7 = fma(T::a76, kx, x7); y7 = fma(T::a76, ky, y7);
-            xe = fma(T::bt6, kx, xe); ye = fma(T::bt6, ky, ye);
-        }
-        double n0, n1, n2, n3, n4; /* u_new */
-        {
-            double i0 = T::a71 * k10, i1 = T::a71 * k11, i2 = T::a71 * k12;
-            if (T::a72 != 0.0) { i0 = fma(T::a72, k20, i0); i1 = fma(T::a72, k21, i1); i2 = fma(T::a72, k22, i2); }
-            i0 = fma(T::a73, k30, i0); i1 = fma(T::a73, k31, i1); i2 = fma(T::a73, k32, i2);
-            i0 = fma(T::a74, k40, i0); i1 = fma(T::a74, k41, i1); i2 = fma(T::a74, k42, i2);
-            i0 = fma(T::a75, k50, i0); i1 = fma(T::a75, k51, i1); i2 = fma(T::a75, k52, i2);
-            i0 = fma(T::a76, k60, i0); i1 = fma(T::a76, k61, i1); i2 = fma(T::a76, k62, i2);
-            n0 = fma(dt, i0, u0); n1 = fma(dt, i1, u1); n2 = fma(dt, i2, u2);
-            n3 = fma(dt, x7, u3); n4 = fma(dt, y7, u4);
-            f3(P, w, pc, n0, n1, n2, t + dt, k70, k71, k72);
+        double x7 = T.a[7][1] * kx, y7 = T.a[7][1] * ky;
+        double xe = T.bt[1] * kx, ye = T.bt[1] * ky;
+        double n0 = u0, n1 = u1, n2 = u2; /* argument of the current stage; u_new after stage 7 */
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int s = 2; s <= 7; s++) {
+            if (s == 2) {
+                double a = dt * T.a[2][1];
+                n0 = fma(a, K.get(1, 0), u0); n1 = fma(a, K.get(1, 1), u1); n2 = fma(a, K.get(1, 2), u2);
+            } else {
+                double a1 = T.a[s][1];
+                double i0 = a1 * K.get(1, 0), i1 = a1 * K.get(1, 1), i2 = a1 * K.get(1, 2);
+                for (int j = 2; j < s; j++) {
+                    double aj = T.a[s][j];
+                    if (aj != 0.0) {
+                        i0 = fma(aj, K.get(j, 0), i0); i1 = fma(aj, K.get(j, 1), i1); i2 = fma(aj, K.get(j, 2), i2);
+                    }
+                }
+                n0 = fma(dt, i0, u0); n1 = fma(dt, i1, u1); n2 = fma(dt, i2, u2);
+            }
+            double ts = (s >= 6) ? (t + dt) : fma(T.c[s - 1], dt, t);
+            double d0, d1, d2;
+            f3(P, w, pc, n0, n1, n2, ts, d0, d1, d2);
+            K.set(s, 0, d0); K.set(s, 1, d1); K.set(s, 2, d2);
             prop(P, M, n1, n2, kx, ky);
-            xe = fma(T::bt7, kx, xe); ye = fma(T::bt7, ky, ye);
+            if (s < 7) {
+                double a7 = T.a[7][s];
+                if (a7 != 0.0) { x7 = fma(a7, kx, x7); y7 = fma(a7, ky, y7); }
+            }
+            double bs = T.bt[s];
+            if (bs != 0.0) { xe = fma(bs, kx, xe); ye = fma(bs, ky, ye); }
         }
+        double n3 = fma(dt, x7, u3), n4 = fma(dt, y7, u4);
         nrhs += 6;
         /* error estimate: utilde = dt*sum(btilde_j k_j); calculate_residuals; RMS norm */
         double EEst;
         {
-            double e0 = T::bt1 * k10, e1 = T::bt1 * k11, e2 = T::bt1 * k12;
-            if (T::bt2 != 0.0) { e0 = fma(T::bt2, k20, e0); e1 = fma(T::bt2, k21, e1); e2 = fma(T::bt2, k22, e2); }
-            e0 = fma(T::bt3, k30, e0); e1 = fma(T::bt3, k31, e1); e2 = fma(T::bt3, k32, e2);
-            e0 = fma(T::bt4, k40, e0); e1 = fma(T::bt4, k41, e1); e2 = fma(T::bt4, k42, e2);
-            e0 = fma(T::bt5, k50, e0); e1 = fma(T::bt5, k51, e1); e2 = fma(T::bt5, k52, e2);
-            e0 = fma(T::bt6, k60, e0); e1 = fma(T::bt6, k61, e1); e2 = fma(T::bt6, k62, e2);
-            e0 = fma(T::bt7, k70, e0); e1 = fma(T::bt7, k71, e1); e2 = fma(T::bt7, k72, e2);
+            double b1 = T.bt[1];
+            double e0 = b1 * K.get(1, 0), e1 = b1 * K.get(1, 1), e2 = b1 * K.get(1, 2);
+            for (int j = 2; j <= 7; j++) {
+                double bj = T.bt[j];
+                if (bj != 0.0) { e0 = fma(bj, K.get(j, 0), e0); e1 = fma(bj, K.get(j, 1), e1); e2 = fma(bj, K.get(j, 2), e2); }
+            }
             double r0 = (dt * e0) / fma(pm_max(fabs(u0), fabs(n0)), P.reltol, P.abstol);
             double r1 = (dt * e1) / fma(pm_max(fabs(u1), fabs(n1)), P.reltol, P.abstol);
             double r2 = (dt * e2) / fma(pm_max(fabs(u2), fabs(n2)), P.reltol, P.abstol);
@@ -414,8 +440,8 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
         if (EEst == 0.0) {
             q = 1.0 / qmax;
         } else {
-            q11 = pm_pow(EEst, T::beta1);
-            q = q11 / pm_pow(qold, T::beta2);
+            q11 = pm_pow(EEst, T.beta1);
+            q = q11 / pm_pow(qold, T.beta2);
             q = pm_max(1.0 / qmax, pm_min(1.0 / qmin, q / gamma));
         }
         bool accept = (EEst <= 1.0) || (P.force_dtmin && fabs(dt) <= dtmin_t);
@@ -428,7 +454,7 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
             dtp = pm_max(dtp, pm_max(pm_eps(t), P.dtmin));
             dt = dtp;
             u0 = n0; u1 = n1; u2 = n2; u3 = n3; u4 = n4;
-            k10 = k70; k11 = k71; k12 = k72; /* FSAL */
+            K.set(1, 0, K.get(7, 0)); K.set(1, 1, K.get(7, 1)); K.set(1, 2, K.get(7, 2)); /* FSAL */
             c.substeps++;
             if ((u0 != u0) | (u1 != u1) | (u2 != u2) | (u3 != u3) | (u4 != u4)) {
                 p.status |= PICLES_PST_UNSTABLE; c.failed++; break;
@@ -636,16 +662,16 @@ PM_HD void gather_node(const RecView& V, int I, int J, int R, int n_classes, dou
 }
 
 /* ---- advance! (everything except the scatter, which the gather replaces) ----- */
-template <class T>
+template <class KS>
 PM_HD void advance_particle(const picles_params_t& P, Particle& p, int mask, double DT, double wu0, double wv0,
-                            double wu1, double wv1, const double* M, double pc, Record& rec, Tally& c) {
+                            double wu1, double wv1, const double* M, double pc, Record& rec, Tally& c, KS& K) {
     double t_start = p.t;
     bool on = (p.flags & PICLES_PF_ON) != 0;
     if (on) {
         Wind w;
         w.u0 = wu0; w.v0 = wv0; w.du = wu1 - wu0; w.dv = wv1 - wv0;
         w.t_start = t_start; w.inv_DT = 1.0 / DT;
-        integrate<T>(P, w, M, pc, DT, p, c);
+        integrate(P, w, M, pc, DT, p, c, K);
     } else {
         if (wu1 * wu1 + wv1 * wv1 >= P.wind_min_squared) {
             reset_particle_values(P, wu1, wv1, DT, p);

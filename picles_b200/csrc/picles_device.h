@@ -8,8 +8,12 @@
 #include "../../include/picles_b200.h"
 
 /* launch shapes: grids are capped at (SM count x resident blocks) and grid-stride */
+#ifndef ADV_THREADS
 #define ADV_THREADS 128
+#endif
+#ifndef ADV_MIN_BLOCKS
 #define ADV_MIN_BLOCKS 4
+#endif
 #define PRJ_THREADS 256
 #define RMS_THREADS 256
 /* largest particle reach (cells) the projection gather supports; == PH_REACH_MAX */

@@ -110,9 +110,15 @@ __global__ void __launch_bounds__(256) k_seed(DeviceArrays A, picles_params_t P,
  * whose particle reached t+DT wait at the loop exit for the slowest lane of the warp
  * (neighbouring nodes carry near-identical states, so attempt counts are close).
  */
-template <class T, bool PER_NODE_M>
+template <bool PER_NODE_M>
 __global__ void __launch_bounds__(ADV_THREADS, ADV_MIN_BLOCKS)
 k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc) {
+    /* stage derivatives k_j[0:3], j = 1..7: 21 doubles per thread, one column per thread
+       (consecutive threads -> consecutive 8-byte words: conflict-free) */
+    __shared__ double s_k[21 * ADV_THREADS];
+    KStrided K;
+    K.base = &s_k[threadIdx.x];
+    K.stride = ADV_THREADS;
     Tally c;
     tally_zero(c);
     int64_t n = (int64_t)A.Nx * A.ny;
@@ -127,7 +133,7 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc) {
         else { M[0] = A.Mc[0]; M[1] = A.Mc[1]; M[2] = A.Mc[2]; M[3] = A.Mc[3]; }
         double pc = A.pc ? A.pc[l] : 0.0;
         Record r;
-        advance_particle<T>(P, p, A.mask[l], DT, A.u_t[l], A.v_t[l], A.u_t1[l], A.v_t1[l], M, pc, r, c);
+        advance_particle(P, p, A.mask[l], DT, A.u_t[l], A.v_t[l], A.u_t1[l], A.v_t1[l], M, pc, r, c, K);
         store_particle(A, l, p);
         store_record(A, le, r);
     }
@@ -279,13 +285,8 @@ void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, 
     int64_t n = (int64_t)A.Nx * A.ny;
     int g = grid_for(n, ADV_THREADS, sms, ADV_MIN_BLOCKS);
     bool pn = (A.M[0] != nullptr);
-    if (P.solver == PICLES_SOLVER_DP5) {
-        if (pn) k_advance<DP5Tab, true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc);
-        else k_advance<DP5Tab, false><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc);
-    } else {
-        if (pn) k_advance<Tsit5Tab, true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc);
-        else k_advance<Tsit5Tab, false><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc);
-    }
+    if (pn) k_advance<true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc);
+    else k_advance<false><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc);
 }
 
 void launch_project(const DeviceArrays& A, int n_classes, int accumulate, const int32_t* reach, int sms, cudaStream_t st) {

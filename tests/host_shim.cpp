@@ -116,10 +116,8 @@ void shim_step(Shim* h, double t, double DT, const double* u_t, const double* v_
             Record r;
             Tally c;
             tally_zero(c);
-            if (h->P.solver == PICLES_SOLVER_DP5)
-                advance_particle<DP5Tab>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l], v_t1[off + l], M, pc, r, c);
-            else
-                advance_particle<Tsit5Tab>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l], v_t1[off + l], M, pc, r, c);
+            KLocal K;
+            advance_particle(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l], v_t1[off + l], M, pc, r, c, K);
             tally_add(T, c);
             store(s, l, p);
             int64_t le = l + (int64_t)s.halo * Nx;
