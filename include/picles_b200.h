@@ -245,6 +245,11 @@ int picles_timer_stop(picles_t* h, double* ms);
 /* measured FP64 FMA throughput of this device (register-resident DFMA chains), the
    roofline denominator of the advance kernel; ~50 ms */
 int picles_measure_fp64_peak(picles_t* h, double* tflops);
+/* self-test of the device fast-path division / sqrt (pmath.h) against the IEEE operators
+   on random operands (raw bit patterns, physics-range magnitudes, special values).
+   out6 = {n_div, flagged_div, mismatch_div, n_sqrt, flagged_sqrt, mismatch_sqrt};
+   a mismatch is an unflagged result that differs from a/b or sqrt(x): must be 0. */
+int picles_selftest_math(picles_t* h, uint64_t seed, int iters, int64_t* out6);
 /* measured HBM copy bandwidth (read+write bytes / s) over a buffer of `mib` MiB */
 int picles_measure_hbm_copy(picles_t* h, int mib, double* gbs);
 

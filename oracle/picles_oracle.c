@@ -399,13 +399,16 @@ static void integrate(oracle_t* o, particle_t* p, const rhs_ctx_t* c, double DT,
             r[i] = ut / sc;
         }
         double EEst = rms5(r);
-        /* stepsize_controller! (PIController) */
+        /* stepsize_controller! (PIController): q = EEst^beta1 / qold^beta2, evaluated as
+           exp(beta1*log(EEst) - beta2*log(qold)); OrdinaryDiffEq evaluates the two powers
+           with an approximate `fastpow`, so the last bits are not pinned by the reference */
         double q, q11 = 1.0;
         if (EEst == 0.0) {
             q = 1.0 / qmax;
         } else {
-            q11 = O_POW(EEst, T->beta1);
-            q = q11 / O_POW(qold, T->beta2);
+            double t1 = T->beta1 * O_LOG(EEst);
+            q11 = O_EXP(t1);
+            q = O_EXP(t1 - T->beta2 * O_LOG(qold));
             q = pm_max(1.0 / qmax, pm_min(1.0 / qmin, q / gamma));
         }
         int accept = (EEst <= 1.0) || (P->force_dtmin && fabs(dt) <= dtmin_t);

@@ -131,6 +131,7 @@ SYMBOLS = {
     "picles_copy_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
     "picles_timer_start": (C.c_int, [_vp]),
     "picles_timer_stop": (C.c_int, [_vp, _dp]),
+    "picles_selftest_math": (C.c_int, [_vp, C.c_uint64, C.c_int, C.POINTER(C.c_int64)]),
     "picles_measure_fp64_peak": (C.c_int, [_vp, _dp]),
     "picles_measure_hbm_copy": (C.c_int, [_vp, C.c_int, _dp]),
 }

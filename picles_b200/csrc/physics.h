@@ -42,6 +42,7 @@
 #endif
 
 #define PH_QOLDINIT 1e-4
+#define PH_LOG_QOLDINIT (-0x1.26bb1bbb55515p+3) /* = pm_log(PH_QOLDINIT) */
 #define PH_CELL_INVALID ((int32_t)-1)
 #define PH_CELL_BIAS 8192
 #define PH_REACH_MAX 15
@@ -128,6 +129,13 @@ struct Wind {
     double t_start, inv_DT;
 };
 
+/* loop invariants of one particle's integration, hoisted out of the stage loop */
+struct Hoist {
+    double y_rg, y_eT; /* Newton reciprocals of r_g and e_T (fast path only) */
+    double us0;        /* sqrt(u0^2+v0^2): the wind speed when the wind does not change over DT */
+    bool steady;       /* du == 0 && dv == 0 */
+};
+
 /* per-thread counter deltas */
 struct Tally {
     int32_t integrated, substeps, rejects, rhs, reseed, fixups, failed, deposited, A, B, C, D;
@@ -209,56 +217,87 @@ PM_HD void vertex(double e, double mx, double my, Particle& p) {
     p.u4 = 0.0;
 }
 
-/* ---- right-hand side: components lne, c̄_x, c̄_y --------------------------- */
-PM_HD double alpha_func(double us, double cgp) {
-    double a = us / (2.0 * cgp);
-    return (a > 500.0) ? 500.0 : a;
-}
+/* ---- arithmetic policies ----------------------------------------------------- */
+/* IEEE operators (host, oracle parity, device fallback and cold paths) */
+struct OpsSafe {
+    static PM_HDM double div(double a, double b, unsigned*) { return a / b; }
+    static PM_HDM double divz(double a, double b, unsigned*) { return a / b; }
+    static PM_HDM double prep(double) { return 0.0; }
+    static PM_HDM double div_pre(double a, double b, double, unsigned*) { return a / b; }
+    static PM_HDM double divz_pre(double a, double b, double, unsigned*) { return a / b; }
+    static PM_HDM double sqrt_(double x, unsigned*) { return sqrt(x); }
+    static PM_HDM double sqrtz(double x, unsigned*) { return sqrt(x); }
+    static PM_HDM double tanh_(double x, unsigned*) { return pm_tanh_safe(x); }
+    static PM_HDM double sech(double x, unsigned*) { return pm_sech_safe(x); }
+    static PM_HDM double pow_(double x, double y, unsigned*) { return pm_pow_safe(x, y); }
+    static PM_HDM double log_(double x, unsigned*) { return pm_log_safe(x); }
+    static PM_HDM double log10_(double x, unsigned*) { return pm_log10_safe(x); }
+};
+#if defined(__CUDA_ARCH__)
+/* device fast paths with a deferred validity flag (pmath.h) */
+struct OpsFast {
+    static __device__ __forceinline__ double div(double a, double b, unsigned* bad) { return pm_div_fast(a, b, bad); }
+    static __device__ __forceinline__ double divz(double a, double b, unsigned* bad) { return pm_divz_fast(a, b, bad); }
+    static __device__ __forceinline__ double prep(double b) { return pm_rcp_newton(b); }
+    static __device__ __forceinline__ double div_pre(double a, double b, double y, unsigned* bad) { return pm_div_pre_fast(a, b, y, bad); }
+    static __device__ __forceinline__ double divz_pre(double a, double b, double y, unsigned* bad) { return pm_divz_pre_fast(a, b, y, bad); }
+    static __device__ __forceinline__ double sqrt_(double x, unsigned* bad) { return pm_sqrt_fast(x, bad); }
+    static __device__ __forceinline__ double sqrtz(double x, unsigned* bad) { return pm_sqrtz_fast(x, bad); }
+    static __device__ __forceinline__ double tanh_(double x, unsigned* bad) { return pm_tanh_fast(x, bad); }
+    static __device__ __forceinline__ double sech(double x, unsigned* bad) { return pm_sech_fast(x, bad); }
+    static __device__ __forceinline__ double pow_(double x, double y, unsigned* bad) { return pm_pow_fast(x, y, bad); }
+    static __device__ __forceinline__ double log_(double x, unsigned* bad) { return pm_log_fast(x, bad); }
+    static __device__ __forceinline__ double log10_(double x, unsigned* bad) { return pm_log10_fast(x, bad); }
+};
+#endif
 
-PM_HD void rhs3(const picles_params_t& P, double lne, double cx, double cy, double u, double v, double pc,
-                double& d0, double& d1, double& d2) {
+/* ---- right-hand side: components lne, c̄_x, c̄_y --------------------------- */
+/* Straight-line: the term switches and guards are selects, so with O = OpsFast the whole
+   evaluation is one basic block and its independent chains (tanh, sech, the two exps,
+   the k_p / ω_p divisions) overlap in the FP64 pipe. */
+template <class O>
+PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx, double cy, double u, double v,
+                double us, double pc, double& d0, double& d1, double& d2, unsigned* bad) {
     double r_g = P.r_g;
-    double cbar = sqrt(cx * cx + cy * cy);
-    double us = sqrt(u * u + v * v);
-    double c_gp = fabs(cbar) / r_g;
-    double kp = 9.81 / (4.0 * pm_max(c_gp * c_gp, 1e-2));
-    double wp = 9.81 / (2.0 * pm_max(fabs(c_gp), 0.1));
-    double gx = cx / r_g, gy = cy / r_g;
-    double alpha = alpha_func(us, c_gp);
-    double sg = sqrt(gx * gx + gy * gy);
+    double cbar = O::sqrt_(cx * cx + cy * cy, bad);
+    double c_gp = O::div_pre(fabs(cbar), r_g, H.y_rg, bad);
+    double kp = O::div(9.81, 4.0 * pm_max(c_gp * c_gp, 1e-2), bad);
+    double wp = O::div(9.81, 2.0 * pm_max(fabs(c_gp), 0.1), bad);
+    double gx = O::divz_pre(cx, r_g, H.y_rg, bad), gy = O::divz_pre(cy, r_g, H.y_rg, bad);
+    double a1 = O::div(us, 2.0 * c_gp, bad); /* α_func(us, c_gp) */
+    double alpha = (a1 > 500.0) ? 500.0 : a1;
+    double sg = O::sqrt_(gx * gx + gy * gy, bad);
     double msg = pm_max(sg, 1e-4);
-    double alpha_p = (u * gx + v * gy) / (2.0 * (msg * msg));
-    double Hp = 0.5 * (1.0 + pm_tanh(P.p * (alpha_p - 0.85)));
-    double sch = pm_sech(10.0 * (alpha_p - 0.85));
+    double alpha_p = O::div(u * gx + v * gy, 2.0 * (msg * msg), bad);
+    double Hp = 0.5 * (1.0 + O::tanh_(P.p * (alpha_p - 0.85), bad));
+    double sch = O::sech(10.0 * (alpha_p - 0.85), bad);
     double Dp = 1.0 - 1.25 * (sch * sch);
-    double It = 0.0, Dt = 0.0, Scg = 0.0, Sdir = 0.0;
-    if (P.input) It = P.C_e * Hp * (alpha * alpha);
-    if (P.dissipation) {
-        double r = kp / P.e_T, pw;
+    double It = P.input ? P.C_e * Hp * (alpha * alpha) : 0.0;
+    double Dt, Scg;
+    {
+        double r = O::div_pre(kp, P.e_T, H.y_eT, bad), pw;
         double twon = 2.0 * P.n;
-        if (twon == 4.0) {
-            double r2 = r * r;
-            pw = r2 * r2;
-        } else if (twon == 2.0) {
-            pw = r * r;
-        } else {
-            pw = pm_pow(r, twon);
-        }
-        Dt = pm_exp(P.n * lne) * pw;
-    }
-    if (P.peak_shift) {
+        double r2 = r * r;
+        pw = (twon == 4.0) ? r2 * r2 : r2;
+        if (twon != 4.0 && twon != 2.0) pw = O::pow_(r, twon, bad); /* general q: uniform, cold */
+        /* n == 2 (q = -1/4): exp(n*lne) and exp(2*lne) are the same evaluation */
+        double e2 = pm_exp(2.0 * lne);
+        double en = (P.n == 2.0) ? e2 : pm_exp(P.n * lne);
+        Dt = P.dissipation ? en * pw : 0.0;
         double k2 = kp * kp;
-        Scg = P.C_alpha * Dp * (k2 * k2) * pm_exp(2.0 * lne);
+        Scg = P.peak_shift ? P.C_alpha * Dp * (k2 * k2) * e2 : 0.0;
     }
-    if (P.direction) {
-        double a2 = alpha_func(us, sg);
+    double Sdir;
+    {
+        double a2r = O::div(us, 2.0 * sg, bad); /* α_func(us, sg) */
+        double a2 = (a2r > 500.0) ? 500.0 : a2r;
         double prod = us * sg;
-        double s2 = 0.0;
-        if (!(prod == 0.0)) {
-            s2 = (2.0 / (prod * prod)) *
-                 (u * v * (2.0 * (gy * gy) - sg * sg) - gx * gy * (2.0 * (v * v) - us * us));
-        }
-        Sdir = a2 * a2 * P.C_varphi * Hp * s2;
+        bool zero = (prod == 0.0);
+        double den = zero ? 1.0 : prod * prod;
+        double s2 = O::div(2.0, den, bad) *
+                    (u * v * (2.0 * (gy * gy) - sg * sg) - gx * gy * (2.0 * (v * v) - us * us));
+        s2 = zero ? 0.0 : s2;
+        Sdir = P.direction ? a2 * a2 * P.C_varphi * Hp * s2 : 0.0;
     }
     double Ssph = cx * pc;
     d0 = wp * r_g * Scg + wp * (It - Dt);
@@ -277,124 +316,224 @@ PM_HD void prop(const picles_params_t& P, const double* M, double cx, double cy,
     }
 }
 
-/* wind at stage time ts (linear between the two staged levels) + rhs3 */
-PM_HD void f3(const picles_params_t& P, const Wind& w, double pc, double lne, double cx, double cy, double ts,
-              double& d0, double& d1, double& d2) {
-    double s = (ts - w.t_start) * w.inv_DT;
-    double u = fma(w.du, s, w.u0);
-    double v = fma(w.dv, s, w.v0);
-    rhs3(P, lne, cx, cy, u, v, pc, d0, d1, d2);
+/* wind at stage time ts (linear between the two staged levels) and its speed.  A wind
+   that does not change over DT (du = dv = 0) gives u0, v0 and the hoisted us0 exactly. */
+template <class O>
+PM_HD void stage_wind(const Wind& w, const Hoist& H, double ts, double& u, double& v, double& us, unsigned* bad) {
+    if (H.steady) {
+        u = w.u0; v = w.v0; us = H.us0;
+    } else {
+        double s = (ts - w.t_start) * w.inv_DT;
+        u = fma(w.du, s, w.u0);
+        v = fma(w.dv, s, w.v0);
+        us = O::sqrtz(u * u + v * v, bad);
+    }
 }
 
-/* cold (out-of-loop) right-hand side: one shared non-inlined copy for the FSAL reset and
-   the initial-step heuristic, so the hot stage loop is the only inlined copy */
+/* IEEE right-hand side, one shared out-of-line copy: the FSAL reset, the initial-step
+   heuristic, and the fallback of the fast path */
 PM_HD_NOINLINE_DECL void f3_cold(const picles_params_t& P, const Wind& w, double pc, double lne, double cx, double cy,
                                  double ts, double& d0, double& d1, double& d2) {
-    f3(P, w, pc, lne, cx, cy, ts, d0, d1, d2);
+    Hoist H;
+    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false;
+    double u, v, us;
+    stage_wind<OpsSafe>(w, H, ts, u, v, us, (unsigned*)0);
+    rhs3<OpsSafe>(P, H, lne, cx, cy, u, v, us, pc, d0, d1, d2, (unsigned*)0);
 }
 
-PM_HD double rms5(double a, double b, double c, double d, double e) {
+/* loop invariants of the hot right-hand side */
+PM_HD void make_hoist(const picles_params_t& P, const Wind& w, Hoist& H) {
+#if defined(__CUDA_ARCH__)
+    H.y_rg = pm_rcp_newton(P.r_g);
+    H.y_eT = pm_rcp_newton(P.e_T);
+#else
+    H.y_rg = 0.0; H.y_eT = 0.0;
+#endif
+    H.steady = (w.du == 0.0) && (w.dv == 0.0);
+    H.us0 = sqrt(w.u0 * w.u0 + w.v0 * w.v0);
+}
+
+/* hot right-hand side of the stage loop */
+PM_HD void f3(const picles_params_t& P, const Wind& w, const Hoist& H, double pc, double lne, double cx, double cy,
+              double ts, double& d0, double& d1, double& d2) {
+#if defined(__CUDA_ARCH__)
+    double u, v, us;
+    unsigned bad = 0;
+    stage_wind<OpsFast>(w, H, ts, u, v, us, &bad);
+    rhs3<OpsFast>(P, H, lne, cx, cy, u, v, us, pc, d0, d1, d2, &bad);
+    if (bad) f3_cold(P, w, pc, lne, cx, cy, ts, d0, d1, d2); /* rare: denormal/huge/non-finite operands */
+#else
+    (void)H;
+    f3_cold(P, w, pc, lne, cx, cy, ts, d0, d1, d2);
+#endif
+}
+
+template <class O>
+PM_HD double rms5(double a, double b, double c, double d, double e, unsigned* bad) {
     double s = 0.0;
     s += a * a;
     s += b * b;
     s += c * c;
     s += d * d;
     s += e * e;
-    return sqrt(s / 5.0);
+    return O::sqrtz(O::divz(s, 5.0, bad), bad);
 }
 
-/* ode_determine_initdt (Hairer); f0 = f(u,t) supplied as (k0..k4) */
-PM_HD_NOINLINE_DECL double initdt(const picles_params_t& P, const Wind& w, const double* M, double pc, const Particle& p,
-                    double k0, double k1, double k2, double k3, double k4, int32_t& nrhs) {
+/* ---- ode_determine_initdt (Hairer), split around its one right-hand side ---------- */
+/* part A: from u and f0 = f(u,t) to either a final dt (returns true) or the trial step
+   dt0 of the second evaluation f1 = f(u + dt0*f0, t + dt0) (returns false) */
+template <class O>
+PM_HD bool initdt_a(const picles_params_t& P, double u0, double u1, double u2, double u3, double u4, double k0,
+                    double k1, double k2, double k3, double k4, double& dt_out, double& dt0_out, double& d1_out,
+                    unsigned* bad) {
     double dtmin = pm_nextfloat_pos(P.dtmin);
     const double smalldt = 1e-6;
-    double s0 = fma(fabs(p.u0), P.reltol, P.abstol);
-    double s1 = fma(fabs(p.u1), P.reltol, P.abstol);
-    double s2 = fma(fabs(p.u2), P.reltol, P.abstol);
-    double s3 = fma(fabs(p.u3), P.reltol, P.abstol);
-    double s4 = fma(fabs(p.u4), P.reltol, P.abstol);
-    double d0 = rms5(p.u0 / s0, p.u1 / s1, p.u2 / s2, p.u3 / s3, p.u4 / s4);
-    double d1 = rms5(k0 / s0, k1 / s1, k2 / s2, k3 / s3, k4 / s4);
-    if (d1 != d1) return dtmin;
-    double dt0 = ((d0 < 1e-5) | (d1 < 1e-5)) ? smalldt : (d0 / d1) / 100.0;
+    double s0 = fma(fabs(u0), P.reltol, P.abstol);
+    double s1 = fma(fabs(u1), P.reltol, P.abstol);
+    double s2 = fma(fabs(u2), P.reltol, P.abstol);
+    double s3 = fma(fabs(u3), P.reltol, P.abstol);
+    double s4 = fma(fabs(u4), P.reltol, P.abstol);
+    double d0 = rms5<O>(O::divz(u0, s0, bad), O::divz(u1, s1, bad), O::divz(u2, s2, bad), O::divz(u3, s3, bad),
+                        O::divz(u4, s4, bad), bad);
+    double d1 = rms5<O>(O::divz(k0, s0, bad), O::divz(k1, s1, bad), O::divz(k2, s2, bad), O::divz(k3, s3, bad),
+                        O::divz(k4, s4, bad), bad);
+    bool tiny = (d0 < 1e-5) | (d1 < 1e-5);
+    double dt0 = tiny ? smalldt : O::div(O::div(d0, tiny ? 1.0 : d1, bad), 100.0, bad);
     dt0 = pm_min(dt0, P.dtmax);
-    if (dt0 < 10.0 * 2.220446049250313e-16) return pm_max(smalldt, dtmin);
-    double a0 = fma(dt0, k0, p.u0);
-    double a1 = fma(dt0, k1, p.u1);
-    double a2 = fma(dt0, k2, p.u2);
-    double f0, f1, f2, f3x, f4x;
-    f3_cold(P, w, pc, a0, a1, a2, p.t + dt0, f0, f1, f2);
-    prop(P, M, a1, a2, f3x, f4x);
-    nrhs++;
-    int same = (k0 == f0) & (k1 == f1) & (k2 == f2) & (k3 == f3x) & (k4 == f4x);
-    if (same) return pm_max(dtmin, 100.0 * dt0);
-    double d2 = rms5((f0 - k0) / s0, (f1 - k1) / s1, (f2 - k2) / s2, (f3x - k3) / s3, (f4x - k4) / s4) / dt0;
+    d1_out = d1;
+    dt0_out = dt0;
+    if (d1 != d1) { dt_out = dtmin; return true; }
+    if (dt0 < 10.0 * 2.220446049250313e-16) { dt_out = pm_max(smalldt, dtmin); return true; }
+    return false;
+}
+/* part B: with f1 in hand */
+template <class O>
+PM_HD double initdt_b(const picles_params_t& P, double u0, double u1, double u2, double u3, double u4, double k0,
+                      double k1, double k2, double k3, double k4, double f0, double f1, double f2, double f3x,
+                      double f4x, double dt0, double d1, unsigned* bad) {
+    double dtmin = pm_nextfloat_pos(P.dtmin);
+    bool same = (k0 == f0) & (k1 == f1) & (k2 == f2) & (k3 == f3x) & (k4 == f4x);
+    double s0 = fma(fabs(u0), P.reltol, P.abstol);
+    double s1 = fma(fabs(u1), P.reltol, P.abstol);
+    double s2 = fma(fabs(u2), P.reltol, P.abstol);
+    double s3 = fma(fabs(u3), P.reltol, P.abstol);
+    double s4 = fma(fabs(u4), P.reltol, P.abstol);
+    double d2 = O::div(rms5<O>(O::divz(f0 - k0, s0, bad), O::divz(f1 - k1, s1, bad), O::divz(f2 - k2, s2, bad),
+                               O::divz(f3x - k3, s3, bad), O::divz(f4x - k4, s4, bad), bad),
+                       dt0, bad);
     double mx = pm_max(d1, d2);
-    double dt1;
-    if (mx <= 1e-15) dt1 = pm_max(1e-6, dt0 * 1e-3);
-    else dt1 = pm_exp10(-(2.0 + pm_log10(mx)) / 5.0);
-    return pm_max(dtmin, pm_min(pm_min(100.0 * dt0, dt1), P.dtmax));
+    bool flat = (mx <= 1e-15);
+    double lg = O::log10_(flat ? 1.0 : mx, bad);
+    double dt1 = flat ? pm_max(1e-6, dt0 * 1e-3) : pm_exp10(O::div(-(2.0 + lg), 5.0, bad));
+    double dt = pm_max(dtmin, pm_min(pm_min(100.0 * dt0, dt1), P.dtmax));
+    return same ? pm_max(dtmin, 100.0 * dt0) : dt;
+}
+/* IEEE fallbacks, out of line */
+PM_HD_NOINLINE_DECL bool initdt_a_cold(const picles_params_t& P, double u0, double u1, double u2, double u3, double u4,
+                                       double k0, double k1, double k2, double k3, double k4, double& dt_out,
+                                       double& dt0_out, double& d1_out) {
+    return initdt_a<OpsSafe>(P, u0, u1, u2, u3, u4, k0, k1, k2, k3, k4, dt_out, dt0_out, d1_out, (unsigned*)0);
+}
+PM_HD_NOINLINE_DECL double initdt_b_cold(const picles_params_t& P, double u0, double u1, double u2, double u3,
+                                         double u4, double k0, double k1, double k2, double k3, double k4, double f0,
+                                         double f1, double f2, double f3x, double f4x, double dt0, double d1) {
+    return initdt_b<OpsSafe>(P, u0, u1, u2, u3, u4, k0, k1, k2, k3, k4, f0, f1, f2, f3x, f4x, dt0, d1, (unsigned*)0);
 }
 
-/* step!(integrator, DT, true): advance particle p from p.t to p.t + DT.
-   One runtime loop over the 6 new stages per attempt (FSAL), stage derivatives of
-   (lne, c̄_x, c̄_y) in K; the propagation derivatives k_j[3:4] = M*c̄_j are folded into
-   the running sums of stage 7 (x7,y7) and of the error estimate (xe,ye) as each k_j
-   appears — the same fma chain as storing them, without the storage. */
+/* ---- error estimate + PI controller of one attempt -------------------------------- */
+/* utilde = dt*sum(btilde_j k_j); calculate_residuals; RMS norm; stepsize_controller!:
+   q = EEst^beta1 / qold^beta2 evaluated as exp(beta1*log(EEst) - beta2*log(qold)) (the
+   reference's OrdinaryDiffEq uses an approximate fastpow here).  lq is
+   log(qold), carried between attempts; t1 = beta1*log(EEst) feeds the reject branch. */
+struct StepCtl {
+    double EEst, q, t1, lE;
+};
+template <class O>
+PM_HD void step_control(const picles_params_t& P, const Tableau& T, double dt, double e0, double e1, double e2,
+                        double xe, double ye, double u0, double u1, double u2, double u3, double u4, double n0,
+                        double n1, double n2, double n3, double n4, double lq, StepCtl& sc, unsigned* bad) {
+    const double qmin = 0.2, qmax = 10.0, gamma = 0.9;
+    double r0 = O::divz(dt * e0, fma(pm_max(fabs(u0), fabs(n0)), P.reltol, P.abstol), bad);
+    double r1 = O::divz(dt * e1, fma(pm_max(fabs(u1), fabs(n1)), P.reltol, P.abstol), bad);
+    double r2 = O::divz(dt * e2, fma(pm_max(fabs(u2), fabs(n2)), P.reltol, P.abstol), bad);
+    double r3 = O::divz(dt * xe, fma(pm_max(fabs(u3), fabs(n3)), P.reltol, P.abstol), bad);
+    double r4 = O::divz(dt * ye, fma(pm_max(fabs(u4), fabs(n4)), P.reltol, P.abstol), bad);
+    double EEst = rms5<O>(r0, r1, r2, r3, r4, bad);
+    bool zero = (EEst == 0.0);
+    double lE = O::log_(zero ? 1.0 : EEst, bad);
+    double t1 = T.beta1 * lE;
+    double q = pm_exp(t1 - T.beta2 * lq);
+    q = pm_max(1.0 / qmax, pm_min(1.0 / qmin, O::div(q, gamma, bad)));
+    sc.EEst = EEst;
+    sc.q = zero ? 1.0 / qmax : q;
+    sc.t1 = t1;
+    sc.lE = lE;
+}
+PM_HD_NOINLINE_DECL void step_control_cold(const picles_params_t& P, const Tableau& T, double dt, double e0, double e1,
+                                           double e2, double xe, double ye, double u0, double u1, double u2, double u3,
+                                           double u4, double n0, double n1, double n2, double n3, double n4, double lq,
+                                           StepCtl& sc) {
+    step_control<OpsSafe>(P, T, dt, e0, e1, e2, xe, ye, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, lq, sc, (unsigned*)0);
+}
+
+/* ---- step!(integrator, DT, true): advance particle p from p.t to p.t + DT ------------ */
+/*
+ * Every right-hand side of the integration — the FSAL reset k1 = f(u,t), the second
+ * evaluation of the initial-step heuristic, and the six new stages of each attempt —
+ * goes through ONE inlined call site, driven by a small phase machine, so the kernel's
+ * instruction footprint stays inside the SM's instruction cache:
+ *   ph = 1  k1 = f(u, t)                       (then initdt part A when a reset is pending)
+ *   ph = 0  f1 = f(u + dt0*k1, t + dt0)         (then initdt part B)
+ *   ph = 2..7 stage ph of the current attempt   (after 7: error estimate, controller,
+ *                                               accept/reject, header of the next attempt)
+ * Stage derivatives of (lne, c̄_x, c̄_y) live in K; the propagation derivatives
+ * k_j[3:4] = M*c̄_j are folded into the running sums of stage 7 (x7,y7) and of the error
+ * estimate (xe,ye) as each k_j appears — the same fma chain as storing them.
+ */
 template <class KS>
 PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, double pc, double DT, Particle& p,
                      Tally& c, KS& K) {
     if (p.status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE)) return;
     const Tableau& T = tableau(P.solver);
+    Hoist H;
+    make_hoist(P, w, H);
     double t = p.t;
     const double tstop = t + DT;
     double u0 = p.u0, u1 = p.u1, u2 = p.u2, u3 = p.u3, u4 = p.u4;
-    int32_t nrhs = 0;
-    /* u_modified -> reset_fsal!: k1 = f(u, t) */
-    {
-        double k10, k11, k12;
-        f3_cold(P, w, pc, u0, u1, u2, t, k10, k11, k12);
-        nrhs++;
-        K.set(1, 0, k10); K.set(1, 1, k11); K.set(1, 2, k12);
-    }
     double dt = p.dt;
-    if (p.flags & PICLES_PF_DT_RESET) {
-        double k13, k14;
-        prop(P, M, u1, u2, k13, k14);
-        dt = initdt(P, w, M, pc, p, K.get(1, 0), K.get(1, 1), K.get(1, 2), k13, k14, nrhs);
-        p.flags &= (uint8_t)~PICLES_PF_DT_RESET;
-    }
     double qold = p.qold;
+    double lq = pm_log(qold);
+    const double LQ0 = PH_LOG_QOLDINIT; /* pm_log(1e-4), pinned by tests/test_pmath.py */
     int32_t iter = p.iter;
-    int32_t attempts = 0;
-    const double qmin = 0.2, qmax = 10.0, gamma = 0.9;
-    while (t < tstop) {
-        /* loopheader!: fix_dt_at_bounds!, modify_dt_for_tstops! */
-        iter++;
-        double dtmin_t = pm_max(pm_eps(t), P.dtmin);
-        dt = pm_min(P.dtmax, dt);
-        dt = pm_max(dt, dtmin_t);
-        dt = pm_min(dt, tstop - t);
-        /* check_error! */
-        if (dt != dt) { p.status |= PICLES_PST_UNSTABLE; c.failed++; break; }
-        if ((int64_t)iter > P.maxiters) { p.status |= PICLES_PST_MAXITERS; c.failed++; break; }
-        if (!P.force_dtmin && dt <= P.dtmin && (t + dt < tstop)) { p.status |= PICLES_PST_DTMIN; c.failed++; break; }
-        attempts++;
+    int32_t nrhs = 0, attempts = 0;
+    const double qmin = 0.2, gamma = 0.9;
+    bool need_reset = (p.flags & PICLES_PF_DT_RESET) != 0;
+    p.flags &= (uint8_t)~PICLES_PF_DT_RESET;
 
-        /* perform_step! */
-        double kx, ky;
-        prop(P, M, u1, u2, kx, ky);
-        double x7 = T.a[7][1] * kx, y7 = T.a[7][1] * ky;
-        double xe = T.bt[1] * kx, ye = T.bt[1] * ky;
-        double n0 = u0, n1 = u1, n2 = u2; /* argument of the current stage; u_new after stage 7 */
+    int ph = 1;
+    double n0 = u0, n1 = u1, n2 = u2, ts = t; /* argument of the next right-hand side */
+    double x7 = 0.0, y7 = 0.0, xe = 0.0, ye = 0.0, dt0 = 0.0, d1n = 0.0;
+    double dtmin_t = P.dtmin;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-        for (int s = 2; s <= 7; s++) {
-            if (s == 2) {
-                double a = dt * T.a[2][1];
-                n0 = fma(a, K.get(1, 0), u0); n1 = fma(a, K.get(1, 1), u1); n2 = fma(a, K.get(1, 2), u2);
-            } else {
+    for (;;) {
+        double d0, d1, d2;
+        f3(P, w, H, pc, n0, n1, n2, ts, d0, d1, d2);
+        nrhs++;
+        if (ph >= 2) {
+            K.set(ph, 0, d0); K.set(ph, 1, d1); K.set(ph, 2, d2);
+            double kx, ky;
+            prop(P, M, n1, n2, kx, ky);
+            if (ph < 7) {
+                double a7 = T.a[7][ph];
+                if (a7 != 0.0) { x7 = fma(a7, kx, x7); y7 = fma(a7, ky, y7); }
+            }
+            double bs = T.bt[ph];
+            if (bs != 0.0) { xe = fma(bs, kx, xe); ye = fma(bs, ky, ye); }
+            if (ph < 7) {
+                /* argument of stage s = ph+1 >= 3 */
+                int s = ++ph;
                 double a1 = T.a[s][1];
                 double i0 = a1 * K.get(1, 0), i1 = a1 * K.get(1, 1), i2 = a1 * K.get(1, 2);
                 for (int j = 2; j < s; j++) {
@@ -404,64 +543,106 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
                     }
                 }
                 n0 = fma(dt, i0, u0); n1 = fma(dt, i1, u1); n2 = fma(dt, i2, u2);
+                ts = (s >= 6) ? (t + dt) : fma(T.c[s - 1], dt, t);
+                continue;
             }
-            double ts = (s >= 6) ? (t + dt) : fma(T.c[s - 1], dt, t);
-            double d0, d1, d2;
-            f3(P, w, pc, n0, n1, n2, ts, d0, d1, d2);
-            K.set(s, 0, d0); K.set(s, 1, d1); K.set(s, 2, d2);
-            prop(P, M, n1, n2, kx, ky);
-            if (s < 7) {
-                double a7 = T.a[7][s];
-                if (a7 != 0.0) { x7 = fma(a7, kx, x7); y7 = fma(a7, ky, y7); }
-            }
-            double bs = T.bt[s];
-            if (bs != 0.0) { xe = fma(bs, kx, xe); ye = fma(bs, ky, ye); }
-        }
-        double n3 = fma(dt, x7, u3), n4 = fma(dt, y7, u4);
-        nrhs += 6;
-        /* error estimate: utilde = dt*sum(btilde_j k_j); calculate_residuals; RMS norm */
-        double EEst;
-        {
+            /* all seven stages done: (n0,n1,n2) is u_new */
+            double n3 = fma(dt, x7, u3), n4 = fma(dt, y7, u4);
             double b1 = T.bt[1];
             double e0 = b1 * K.get(1, 0), e1 = b1 * K.get(1, 1), e2 = b1 * K.get(1, 2);
             for (int j = 2; j <= 7; j++) {
                 double bj = T.bt[j];
                 if (bj != 0.0) { e0 = fma(bj, K.get(j, 0), e0); e1 = fma(bj, K.get(j, 1), e1); e2 = fma(bj, K.get(j, 2), e2); }
             }
-            double r0 = (dt * e0) / fma(pm_max(fabs(u0), fabs(n0)), P.reltol, P.abstol);
-            double r1 = (dt * e1) / fma(pm_max(fabs(u1), fabs(n1)), P.reltol, P.abstol);
-            double r2 = (dt * e2) / fma(pm_max(fabs(u2), fabs(n2)), P.reltol, P.abstol);
-            double r3 = (dt * xe) / fma(pm_max(fabs(u3), fabs(n3)), P.reltol, P.abstol);
-            double r4 = (dt * ye) / fma(pm_max(fabs(u4), fabs(n4)), P.reltol, P.abstol);
-            EEst = rms5(r0, r1, r2, r3, r4);
-        }
-        /* stepsize_controller! (PIController) */
-        double q, q11 = 1.0;
-        if (EEst == 0.0) {
-            q = 1.0 / qmax;
-        } else {
-            q11 = pm_pow(EEst, T.beta1);
-            q = q11 / pm_pow(qold, T.beta2);
-            q = pm_max(1.0 / qmax, pm_min(1.0 / qmin, q / gamma));
-        }
-        bool accept = (EEst <= 1.0) || (P.force_dtmin && fabs(dt) <= dtmin_t);
-        if (accept) {
-            qold = pm_max(EEst, PH_QOLDINIT);
-            double dtnew = dt / q;
-            double ttmp = t + dt;
-            t = (fabs(ttmp - tstop) < 100.0 * pm_eps(tstop)) ? tstop : ttmp;
-            double dtp = pm_min(P.dtmax, dtnew);
-            dtp = pm_max(dtp, pm_max(pm_eps(t), P.dtmin));
-            dt = dtp;
-            u0 = n0; u1 = n1; u2 = n2; u3 = n3; u4 = n4;
-            K.set(1, 0, K.get(7, 0)); K.set(1, 1, K.get(7, 1)); K.set(1, 2, K.get(7, 2)); /* FSAL */
-            c.substeps++;
-            if ((u0 != u0) | (u1 != u1) | (u2 != u2) | (u3 != u3) | (u4 != u4)) {
-                p.status |= PICLES_PST_UNSTABLE; c.failed++; break;
+            StepCtl sc;
+#if defined(__CUDA_ARCH__)
+            unsigned bad = 0;
+            step_control<OpsFast>(P, T, dt, e0, e1, e2, xe, ye, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, lq, sc, &bad);
+            if (bad) step_control_cold(P, T, dt, e0, e1, e2, xe, ye, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, lq, sc);
+#else
+            step_control_cold(P, T, dt, e0, e1, e2, xe, ye, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, lq, sc);
+#endif
+            double EEst = sc.EEst;
+            bool accept = (EEst <= 1.0) || (P.force_dtmin && fabs(dt) <= dtmin_t);
+            if (accept) {
+                /* step_accept_controller!, fixed_t_for_floatingpoint_error!, calc_dt_propose! */
+                bool big = (EEst > PH_QOLDINIT) || (EEst != EEst);
+                qold = big ? EEst : PH_QOLDINIT; /* max(EEst, qoldinit) */
+                lq = big ? sc.lE : LQ0;
+                double dtnew = dt / sc.q;
+                double ttmp = t + dt;
+                t = (fabs(ttmp - tstop) < 100.0 * pm_eps(tstop)) ? tstop : ttmp;
+                double dtp = pm_min(P.dtmax, dtnew);
+                dtp = pm_max(dtp, pm_max(pm_eps(t), P.dtmin));
+                dt = dtp;
+                u0 = n0; u1 = n1; u2 = n2; u3 = n3; u4 = n4;
+                K.set(1, 0, K.get(7, 0)); K.set(1, 1, K.get(7, 1)); K.set(1, 2, K.get(7, 2)); /* FSAL */
+                c.substeps++;
+                if ((u0 != u0) | (u1 != u1) | (u2 != u2) | (u3 != u3) | (u4 != u4)) {
+                    p.status |= PICLES_PST_UNSTABLE; c.failed++; break;
+                }
+            } else {
+                /* step_reject_controller!: dt /= min(1/qmin, q11/gamma), q11 = EEst^beta1 */
+                double q11 = (EEst == 0.0) ? 1.0 : pm_exp(sc.t1);
+                dt = dt / pm_min(1.0 / qmin, q11 / gamma);
+                c.rejects++;
             }
-        } else {
-            dt = dt / pm_min(1.0 / qmin, q11 / gamma);
-            c.rejects++;
+        } else if (ph == 1) {
+            K.set(1, 0, d0); K.set(1, 1, d1); K.set(1, 2, d2);
+            if (need_reset) {
+                need_reset = false;
+                double k3, k4, dtr;
+                prop(P, M, u1, u2, k3, k4);
+                bool final_;
+#if defined(__CUDA_ARCH__)
+                unsigned bad = 0;
+                final_ = initdt_a<OpsFast>(P, u0, u1, u2, u3, u4, d0, d1, d2, k3, k4, dtr, dt0, d1n, &bad);
+                if (bad) final_ = initdt_a_cold(P, u0, u1, u2, u3, u4, d0, d1, d2, k3, k4, dtr, dt0, d1n);
+#else
+                final_ = initdt_a_cold(P, u0, u1, u2, u3, u4, d0, d1, d2, k3, k4, dtr, dt0, d1n);
+#endif
+                if (final_) {
+                    dt = dtr;
+                } else {
+                    n0 = fma(dt0, d0, u0); n1 = fma(dt0, d1, u1); n2 = fma(dt0, d2, u2);
+                    ts = t + dt0;
+                    ph = 0;
+                    continue;
+                }
+            }
+        } else { /* ph == 0: (d0,d1,d2) = f1 of the initial-step heuristic */
+            double k3, k4, f3x, f4x;
+            prop(P, M, u1, u2, k3, k4);
+            prop(P, M, n1, n2, f3x, f4x);
+            double k0 = K.get(1, 0), k1 = K.get(1, 1), k2 = K.get(1, 2);
+#if defined(__CUDA_ARCH__)
+            unsigned bad = 0;
+            dt = initdt_b<OpsFast>(P, u0, u1, u2, u3, u4, k0, k1, k2, k3, k4, d0, d1, d2, f3x, f4x, dt0, d1n, &bad);
+            if (bad) dt = initdt_b_cold(P, u0, u1, u2, u3, u4, k0, k1, k2, k3, k4, d0, d1, d2, f3x, f4x, dt0, d1n);
+#else
+            dt = initdt_b_cold(P, u0, u1, u2, u3, u4, k0, k1, k2, k3, k4, d0, d1, d2, f3x, f4x, dt0, d1n);
+#endif
+        }
+        /* ---- header of the next attempt: loopheader!, check_error! ---- */
+        if (!(t < tstop)) break;
+        iter++;
+        dtmin_t = pm_max(pm_eps(t), P.dtmin);
+        dt = pm_min(P.dtmax, dt);
+        dt = pm_max(dt, dtmin_t);
+        dt = pm_min(dt, tstop - t);
+        if (dt != dt) { p.status |= PICLES_PST_UNSTABLE; c.failed++; break; }
+        if ((int64_t)iter > P.maxiters) { p.status |= PICLES_PST_MAXITERS; c.failed++; break; }
+        if (!P.force_dtmin && dt <= P.dtmin && (t + dt < tstop)) { p.status |= PICLES_PST_DTMIN; c.failed++; break; }
+        attempts++;
+        {
+            double kx, ky;
+            prop(P, M, u1, u2, kx, ky);
+            x7 = T.a[7][1] * kx; y7 = T.a[7][1] * ky;
+            xe = T.bt[1] * kx; ye = T.bt[1] * ky;
+            double a = dt * T.a[2][1];
+            n0 = fma(a, K.get(1, 0), u0); n1 = fma(a, K.get(1, 1), u1); n2 = fma(a, K.get(1, 2), u2);
+            ts = fma(T.c[1], dt, t);
+            ph = 2;
         }
     }
     p.u0 = u0; p.u1 = u1; p.u2 = u2; p.u3 = u3; p.u4 = u4;

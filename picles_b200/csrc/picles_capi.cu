@@ -504,6 +504,22 @@ int picles_timer_stop(picles_t* h, double* ms) {
     return PICLES_OK;
 }
 
+int picles_selftest_math(picles_t* h, uint64_t seed, int iters, int64_t* out6) {
+    if (!h || !out6 || iters < 1) return fail(h, PICLES_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(h->device));
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc((void**)&d, 6 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d, 0, 6 * sizeof(unsigned long long), h->stream));
+    launch_selftest_math(seed, iters, d, h->sms, h->stream);
+    unsigned long long hbuf[6];
+    cudaError_t e = cudaMemcpyAsync(hbuf, d, sizeof hbuf, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(h, PICLES_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
+    for (int k = 0; k < 6; k++) out6[k] = (int64_t)hbuf[k];
+    return PICLES_OK;
+}
+
 int picles_measure_fp64_peak(picles_t* h, double* tflops) {
     if (!h || !tflops) return fail(h, PICLES_ERR_ARG, "null argument");
     CK(cudaSetDevice(h->device));

@@ -60,6 +60,7 @@ void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cud
 void launch_halo_pack(const DeviceArrays& A, char* lo, char* hi, int sms, cudaStream_t st);
 void launch_halo_unpack(const DeviceArrays& A, const char* lo, const char* hi, int sms, cudaStream_t st);
 void launch_fill_i32(int32_t* p, int64_t n, int32_t v, int sms, cudaStream_t st);
+void launch_selftest_math(uint64_t seed, int iters, unsigned long long* out, int sms, cudaStream_t st);
 void launch_fp64_peak(double* out, int iters, int sms, cudaStream_t st, int64_t* fmas);
 void launch_copy_f64(double* dst, const double* src, int64_t n, int sms, cudaStream_t st);
 

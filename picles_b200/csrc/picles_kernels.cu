@@ -266,6 +266,54 @@ __global__ void __launch_bounds__(256) k_copy_f64(double2* __restrict__ dst, con
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n2; q += (int64_t)gridDim.x * blockDim.x) dst[q] = src[q];
 }
 
+/* ---- self-test of the fast-path arithmetic (pmath.h) against the IEEE operators ---- */
+__device__ __forceinline__ uint64_t st_next(uint64_t& s) {
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    return s;
+}
+/* operand classes: 0 raw bit patterns (every exponent, NaN/Inf/denormals included),
+   1 moderate magnitudes 2^[-40,40] (the physics range), 2 one operand from a table of
+   special values */
+__device__ double st_operand(uint64_t& s, int cls) {
+    uint64_t r = st_next(s);
+    if (cls == 0) return __longlong_as_double((long long)r);
+    if (cls == 1) {
+        uint64_t mant = r & 0x000fffffffffffffull;
+        uint64_t e = 1023 - 40 + ((r >> 52) % 81);
+        uint64_t sign = (r >> 63) << 63;
+        return __longlong_as_double((long long)(sign | (e << 52) | mant));
+    }
+    const double tab[12] = {0.0, -0.0, 1.0, -1.0, 4.9406564584124654e-324, 2.2250738585072014e-308,
+                            1.7976931348623157e308, __longlong_as_double(0x7ff0000000000000ll),
+                            __longlong_as_double(0x7ff8000000000000ll), 1.9999999999999998, 0.85, 1e-300};
+    return tab[(r >> 32) % 12];
+}
+__global__ void k_selftest_math(uint64_t seed, int iters, unsigned long long* out /* [6] */) {
+    uint64_t s = seed ^ (0x9E3779B97F4A7C15ull * (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x + 1));
+    unsigned long long n_div = 0, bad_div = 0, mis_div = 0, n_sqrt = 0, bad_sqrt = 0, mis_sqrt = 0;
+    for (int it = 0; it < iters; it++) {
+        int cls = it % 3;
+        double a = st_operand(s, cls == 2 ? (it & 1 ? 2 : 1) : cls);
+        double b = st_operand(s, cls == 2 ? (it & 1 ? 1 : 2) : cls);
+        unsigned bad = 0;
+        double q = (it & 4) ? pm_divz_fast(a, b, &bad) : pm_div_fast(a, b, &bad);
+        double qi = a / b;
+        n_div++;
+        if (bad) bad_div++;
+        else if (__double_as_longlong(q) != __double_as_longlong(qi) && !(q != q && qi != qi)) mis_div++;
+        double x = fabs(a);
+        if (cls == 2 && (it & 2)) x = a;
+        bad = 0;
+        double r = (it & 4) ? pm_sqrtz_fast(x, &bad) : pm_sqrt_fast(x, &bad);
+        double ri = sqrt(x);
+        n_sqrt++;
+        if (bad) bad_sqrt++;
+        else if (__double_as_longlong(r) != __double_as_longlong(ri) && !(r != r && ri != ri)) mis_sqrt++;
+    }
+    atomicAdd(&out[0], n_div); atomicAdd(&out[1], bad_div); atomicAdd(&out[2], mis_div);
+    atomicAdd(&out[3], n_sqrt); atomicAdd(&out[4], bad_sqrt); atomicAdd(&out[5], mis_sqrt);
+}
+
 /* ---- launchers ------------------------------------------------------------------ */
 static int grid_for(int64_t n, int threads, int sms, int blocks_per_sm) {
     int64_t need = (n + threads - 1) / threads;
@@ -316,6 +364,9 @@ void launch_fill_i32(int32_t* p, int64_t n, int32_t v, int sms, cudaStream_t st)
     if (n > 0) k_fill_i32<<<grid_for(n, 256, sms, 4), 256, 0, st>>>(p, n, v);
 }
 
+void launch_selftest_math(uint64_t seed, int iters, unsigned long long* out, int sms, cudaStream_t st) {
+    k_selftest_math<<<sms * 8, 256, 0, st>>>(seed, iters, out);
+}
 void launch_fp64_peak(double* out, int iters, int sms, cudaStream_t st, int64_t* fmas) {
     int blocks = sms * 8;
     k_fp64_peak<<<blocks, 256, 0, st>>>(out, iters);

@@ -1,0 +1,79 @@
+/*
+ * pmath_body.h — bodies of the pmath functions that divide or take square roots.
+ * Included (twice) by pmath.h with PMV / PM_DIV / PM_DIVZ / PM_SQRT / PM_BADP / PM_BADA
+ * set for the IEEE ("_safe") or the device fast-path ("_fast") instantiation; see pmath.h.
+ * No include guard on purpose.  Straight-line code only (selects, no early returns).
+ */
+
+/* log(x), fdlibm/musl kernel.  x <= 0, inf, NaN handled by the trailing selects. */
+PM_FN double PMV(pm_log)(double x PM_BADP) {
+    uint64_t ub = (uint64_t)pm_d2i(x);
+    int sub = ((ub >> 52) == 0); /* +0 or positive subnormal: scale up by 2^54 */
+    double xs = sub ? x * 18014398509481984.0 : x;
+    int k = sub ? -54 : 0;
+    int64_t b = pm_d2i(xs);
+    /* normalise the mantissa to [sqrt(2)/2, sqrt(2)) */
+    uint32_t hx = (uint32_t)((uint64_t)b >> 32);
+    hx += 0x3ff00000u - 0x3fe6a09eu;
+    k += (int)(hx >> 20) - 0x3ff;
+    hx = (hx & 0x000fffffu) + 0x3fe6a09eu;
+    b = (int64_t)(((uint64_t)hx << 32) | ((uint64_t)b & 0xffffffffu));
+    double m = pm_i2d(b);
+
+    double f = m - 1.0;
+    double hfsq = 0.5 * f * f;
+    double s = PM_DIVZ(f, 2.0 + f);
+    double z = s * s;
+    double w = z * z;
+    double t1 = w * (PMK.Lg[2] + w * (PMK.Lg[4] + w * PMK.Lg[6]));
+    double t2 = z * (PMK.Lg[1] + w * (PMK.Lg[3] + w * (PMK.Lg[5] + w * PMK.Lg[7])));
+    double R = t2 + t1;
+    double dk = (double)k;
+    double res = s * (hfsq + R) + dk * PMK.LN2_LO - hfsq + f + dk * PMK.LN2_HI;
+    res = pm_isinf(x) ? x : res;
+    res = (x == 0.0) ? -pm_inf() : res;
+    res = (x < 0.0) ? pm_nan() : res;
+    return (x != x) ? x : res;
+}
+
+PM_FN double PMV(pm_log10)(double x PM_BADP) {
+    /* a plain quotient is enough for the initial-step heuristic this feeds */
+    return PM_DIVZ(PMV(pm_log)(x PM_BADA), PMK.LN10);
+}
+
+/* x^y for x >= 0 (naive exp(y*log x): controller and fetch-law exponents) */
+PM_FN double PMV(pm_pow)(double x, double y PM_BADP) {
+    double l = PMV(pm_log)(x PM_BADA);
+    double r = pm_exp(y * l);
+    r = (x == 0.0) ? ((y > 0.0) ? 0.0 : pm_inf()) : r;
+    r = (x < 0.0) ? pm_nan() : r;
+    r = (x != x || y != y) ? pm_nan() : r;
+    return (y == 0.0) ? 1.0 : r;
+}
+
+/* tanh(x) = em1/(em1+2), em1 = expm1(2|x|) = 2^k*expm1(r) + (2^k - 1) */
+PM_FN double PMV(pm_tanh)(double x PM_BADP) {
+    double ax = fabs(x);
+    double y = (ax > 25.0) ? 50.0 : 2.0 * ax;
+    y = (x != x) ? 0.0 : y;
+    double p, r;
+    int k = pm_exp_reduce(y, &p, &r); /* 0 <= k <= 73 */
+    double em = r * p;
+    double s = pm_pow2i(k);
+    double em1 = fma(s, em, s - 1.0);
+    double t = PM_DIVZ(em1, em1 + 2.0);
+    t = (ax > 22.0) ? 1.0 : t;
+    t = (x < 0.0) ? -t : t;
+    return (x != x) ? x : t;
+}
+
+/* sech(x) = 2e/(e^2+1), e = exp(min(|x|,350)); only ever used squared inside
+   1 - 1.25*sech^2, where anything below 1e-9 vanishes */
+PM_FN double PMV(pm_sech)(double x PM_BADP) {
+    double ax = fabs(x);
+    ax = (ax > 350.0) ? 350.0 : ax;
+    ax = (x != x) ? 0.0 : ax;
+    double e = pm_exp_core(ax);
+    double t = PM_DIV(2.0 * e, fma(e, e, 1.0));
+    return (x != x) ? x : t;
+}

@@ -151,6 +151,12 @@ class B200Engine:
         self._check(self.lib.picles_timer_stop(self.h, C.byref(ms)))
         return ms.value
 
+    def selftest_math(self, seed=1, iters=4096):
+        out = (C.c_int64 * 6)()
+        self._check(self.lib.picles_selftest_math(self.h, int(seed), int(iters), out))
+        names = ("n_div", "flagged_div", "mismatch_div", "n_sqrt", "flagged_sqrt", "mismatch_sqrt")
+        return dict(zip(names, [int(v) for v in out]))
+
     def measure_fp64_peak(self):
         v = C.c_double()
         self._check(self.lib.picles_measure_fp64_peak(self.h, C.byref(v)))
