@@ -207,16 +207,6 @@ PM_HD void charge(double lne, double cx, double cy, double& e, double& mx, doubl
     my = cy * e / (cs * cs) / 2.0;
 }
 
-/* GetVariablesAtVertex(state, 0, 0) */
-PM_HD void vertex(double e, double mx, double my, Particle& p) {
-    double m_amp = sqrt(mx * mx + my * my);
-    p.u0 = pm_log(e);
-    p.u1 = mx * e / (2.0 * (m_amp * m_amp));
-    p.u2 = my * e / (2.0 * (m_amp * m_amp));
-    p.u3 = 0.0;
-    p.u4 = 0.0;
-}
-
 /* ---- arithmetic policies ----------------------------------------------------- */
 /* IEEE operators (host, oracle parity, device fallback and cold paths) */
 struct OpsSafe {
@@ -250,6 +240,30 @@ struct OpsFast {
     static __device__ __forceinline__ double log10_(double x, unsigned* bad) { return pm_log10_fast(x, bad); }
 };
 #endif
+
+/* GetVariablesAtVertex(state, 0, 0) */
+template <class O>
+PM_HD void vertex_t(double e, double mx, double my, Particle& p, unsigned* bad) {
+    double m_amp = O::sqrtz(mx * mx + my * my, bad);
+    double den = 2.0 * (m_amp * m_amp);
+    p.u0 = O::log_(e, bad);
+    p.u1 = O::divz(mx * e, den, bad);
+    p.u2 = O::divz(my * e, den, bad);
+    p.u3 = 0.0;
+    p.u4 = 0.0;
+}
+PM_HD_NOINLINE_DECL void vertex_cold(double e, double mx, double my, Particle& p) {
+    vertex_t<OpsSafe>(e, mx, my, p, (unsigned*)0);
+}
+PM_HD void vertex(double e, double mx, double my, Particle& p) {
+#if defined(__CUDA_ARCH__)
+    unsigned bad = 0;
+    vertex_t<OpsFast>(e, mx, my, p, &bad);
+    if (bad) vertex_cold(e, mx, my, p);
+#else
+    vertex_cold(e, mx, my, p);
+#endif
+}
 
 /* ---- right-hand side: components lne, c̄_x, c̄_y --------------------------- */
 /* Straight-line: the term switches and guards are selects, so with O = OpsFast the whole
@@ -758,6 +772,37 @@ PM_HD void axis_candidates(int* lst, int& n, int64_t T, int R, int N, int bnd, b
     }
 }
 
+/* interior fast path with a compile-time reach R (fully unrolled (2R+1)^2 window, one
+   class): every candidate row/column is inside the domain and the strip's storage.
+   `base` = extended linear index of (I,J) itself. */
+template <int R>
+PM_HD void gather_interior(const RecView& V, int64_t base, double& s0, double& s1, double& s2) {
+    const int Nx = V.Nx;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int dj = -R; dj <= R; dj++) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int di = -R; di <= R; di++) {
+            int64_t le = base + (int64_t)dj * Nx + di;
+            int32_t cell = V.cell[le];
+            /* source (I+di, J+dj) reaches (I,J) iff fx in {-di-1,-di} and fy in {-dj-1,-dj} */
+            int dx = -di - ((int32_t)((uint32_t)cell & 0x3fffu) - PH_CELL_BIAS);
+            int dy = -dj - ((int32_t)(((uint32_t)cell >> 14) & 0x3fffu) - PH_CELL_BIAS);
+            if (cell == PH_CELL_INVALID || (unsigned)dx > 1u || (unsigned)dy > 1u) continue;
+            double wxc = V.wx[le], wyc = V.wy[le];
+            double wx = dx ? wxc : 1.0 - wxc;
+            double wy = dy ? wyc : 1.0 - wyc;
+            double w = wx * wy;
+            s0 += w * V.e[le];
+            s1 += w * V.mx[le];
+            s2 += w * V.my[le];
+        }
+    }
+}
+
 /*
  * Sum of all deposits landing on global node (I,J) (1-based), accumulated in the
  * reference's single-thread order: ocean_points order (class 0 = mask 1 nodes, then
@@ -772,6 +817,13 @@ PM_HD void gather_node(const RecView& V, int I, int J, int R, int n_classes, dou
     bool fast_x = (V.bx == PICLES_BND_NONPERIODIC) || (I > R && I <= Nx - R);
     bool fast_y = (V.by == PICLES_BND_NONPERIODIC) || (V.by == PICLES_BND_PERIODIC && J > R && J <= Ny - R) ||
                   (V.by == PICLES_BND_TRIPOLAR_NORTH && J <= Ny - R);
+    /* deep interior, single class, small reach: unrolled window (same order: j, then i) */
+    if (n_classes == 1 && R <= 2 && I > R && I <= Nx - R && J > R && J <= Ny - R && fast_x && fast_y) {
+        int64_t base = (int64_t)(J - 1 - V.j0 + V.halo) * Nx + (I - 1);
+        if (R <= 1) gather_interior<1>(V, base, s0, s1, s2);
+        else gather_interior<2>(V, base, s0, s1, s2);
+        return;
+    }
     if (fast_x && fast_y) {
         /* no wrap, no fold: a source (i,j) reaches (I,J) through exactly one corner,
            dx = I-i-fx in {0,1}, dy = J-j-fy in {0,1} */

@@ -12,7 +12,7 @@
 #define ADV_THREADS 128
 #endif
 #ifndef ADV_MIN_BLOCKS
-#define ADV_MIN_BLOCKS 4
+#define ADV_MIN_BLOCKS 3
 #endif
 #define PRJ_THREADS 256
 #define RMS_THREADS 256

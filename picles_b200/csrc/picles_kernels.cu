@@ -154,16 +154,19 @@ __global__ void __launch_bounds__(PRJ_THREADS) k_project(DeviceArrays A, int n_c
     V.cell = A.cell;
     int R = min(*reach_ptr, PH_REACH_MAX);
     if (A.ny != A.Ny) R = min(R, A.halo); /* strips: the host rejects reach > halo (PICLES_ERR_HALO) */
-    const int64_t n = (int64_t)A.Nx * A.ny;
-    for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x) {
-        const int I = (int)(l % A.Nx) + 1; /* global 1-based target */
-        const int J = (int)(l / A.Nx) + 1 + A.j0;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        if (accumulate) { s0 = A.S[0][l]; s1 = A.S[1][l]; s2 = A.S[2][l]; }
-        gather_node(V, I, J, R, n_classes, s0, s1, s2);
-        A.S[0][l] = s0;
-        A.S[1][l] = s1;
-        A.S[2][l] = s2;
+    /* 2-D launch: blockIdx.y strides rows, threads run along x (no integer division) */
+    for (int jr = blockIdx.y; jr < A.ny; jr += gridDim.y) {
+        const int J = jr + 1 + A.j0; /* global 1-based target row */
+        for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < A.Nx; i0 += gridDim.x * blockDim.x) {
+            const int I = i0 + 1;
+            const int64_t l = (int64_t)jr * A.Nx + i0;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            if (accumulate) { s0 = A.S[0][l]; s1 = A.S[1][l]; s2 = A.S[2][l]; }
+            gather_node(V, I, J, R, n_classes, s0, s1, s2);
+            A.S[0][l] = s0;
+            A.S[1][l] = s1;
+            A.S[2][l] = s2;
+        }
     }
 }
 
@@ -338,8 +341,10 @@ void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, 
 }
 
 void launch_project(const DeviceArrays& A, int n_classes, int accumulate, const int32_t* reach, int sms, cudaStream_t st) {
-    int64_t n = (int64_t)A.Nx * A.ny;
-    k_project<<<grid_for(n, PRJ_THREADS, sms, 16), PRJ_THREADS, 0, st>>>(A, n_classes, accumulate, reach);
+    int gx = (A.Nx + PRJ_THREADS - 1) / PRJ_THREADS;
+    int gy = A.ny < 65535 ? A.ny : 65535;
+    (void)sms;
+    k_project<<<dim3(gx, gy), PRJ_THREADS, 0, st>>>(A, n_classes, accumulate, reach);
 }
 
 void launch_remesh(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
