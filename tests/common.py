@@ -106,6 +106,7 @@ def shim_lib():
         lib.shim_seed.argtypes = [vp, vp, vp]
         lib.shim_step.argtypes = [vp, d, d, vp, vp, vp, vp]
         lib.shim_get_state.argtypes = [vp, vp]
+        lib.shim_set_state.argtypes = [vp, vp]
         lib.shim_get_particles.argtypes = [vp] + [vp] * 7
         lib.shim_get_tally.argtypes = [vp, vp]
         lib.shim_corner_target.restype = i64
@@ -162,6 +163,13 @@ class HostShim:
         self.lib.shim_get_state(self.h, _p(S))
         return S
 
+    def set_state(self, S):
+        S = np.ascontiguousarray(np.asarray(S, np.float64).reshape(3, self.Ny, self.Nx))
+        self.lib.shim_set_state(self.h, _p(S))
+
+    def zero_state(self):
+        self.set_state(np.zeros((3, self.Ny, self.Nx)))
+
     def particles(self):
         sh = (self.Ny, self.Nx)
         z = np.empty((5,) + sh)
@@ -206,3 +214,43 @@ def compare_models(ref, dut, check_aux=True):
     cr, cd = ref.counters(), dut.counters()
     for name in TALLY_NAMES:
         assert cr[name] == cd[name], f"counter {name}: oracle {cr[name]} vs device path {cd[name]}"
+
+
+class ShimEngine(HostShim):
+    """HostShim behind the B200Engine interface (wind levels kept between steps, `None`
+    reuses them) so the host API (WaveGrowth2D / Simulation / run) can be exercised on CPU."""
+
+    def __init__(self, grid, P, **kw):
+        super().__init__(grid, P, **kw)
+        self.ny = self.Ny
+        self._t = None
+        self._t1 = None
+
+    def seed(self, u0, v0):
+        super().seed(u0, v0)
+        self._t = (self._full(u0).copy(), self._full(v0).copy())
+        self._t1 = self._t
+
+    def step(self, t, DT, u_t=None, v_t=None, u_t1=None, v_t1=None):
+        if u_t is not None:
+            self._t = (self._full(u_t).copy(), self._full(v_t).copy())
+        elif u_t1 is not None:
+            self._t = self._t1
+        if u_t1 is not None:
+            self._t1 = (self._full(u_t1).copy(), self._full(v_t1).copy())
+        super().step(t, DT, self._t[0], self._t[1], self._t1[0], self._t1[1])
+
+    def counters(self):
+        c = super().counters()
+        c["n_active"] = c["n_remesh_A"] + c["n_remesh_B"] + c["n_remesh_C"] + c["n_remesh_D"]
+        return c
+
+
+def grid_dict_from_mesh(grid):
+    """tests-side view of a picles_b200 grid object as the dict the oracle builders use."""
+    met = grid.device_metric()
+    T = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a).T)
+    M = None if met["M"] is None else np.stack([T(met["M"][k]) for k in range(4)])
+    return dict(Nx=grid.stats.Nx.N, Ny=grid.stats.Ny.N, bx=grid.stats.Nx.code, by=grid.stats.Ny.code,
+                mask=T(grid.data.mask).astype(np.uint8), x=T(grid.data.x), y=T(grid.data.y), M=M,
+                M_const=met["M_const"], pc=T(met["pc"]))

@@ -97,14 +97,11 @@ void shim_seed(Shim* h, const double* u0, const double* v0) {
     }
 }
 
-void shim_step(Shim* h, double t, double DT, const double* u_t, const double* v_t, const double* u_t1, const double* v_t1) {
-    (void)t;
+static void shim_advance_all(Shim* h, double DT, const double* u_t, const double* v_t, const double* u_t1,
+                             const double* v_t1, Tally& T, bool local_winds) {
     const int Nx = h->Nx;
-    Tally T;
-    tally_zero(T);
-    /* advance */
     for (auto& s : h->s) {
-        int64_t n = (int64_t)Nx * s.ny, off = (int64_t)s.j0 * Nx;
+        int64_t n = (int64_t)Nx * s.ny, off = local_winds ? 0 : (int64_t)s.j0 * Nx;
         for (int64_t l = 0; l < n; l++) {
             if (!(s.flags[l] & PICLES_PF_ACTIVE)) continue;
             Particle p;
@@ -125,6 +122,41 @@ void shim_step(Shim* h, double t, double DT, const double* u_t, const double* v_
             s.cell[le] = r.cell;
         }
     }
+}
+
+static void shim_project_remesh_all(Shim* h, double DT, int R, const double* u_t, const double* v_t, Tally& T,
+                                    bool local_winds) {
+    const int Nx = h->Nx;
+    for (auto& s : h->s) {
+        RecView V;
+        V.Nx = Nx; V.Ny = h->Ny; V.bx = h->bx; V.by = h->by; V.j0 = s.j0; V.ny = s.ny; V.halo = s.halo;
+        V.e = s.rec[0].data(); V.mx = s.rec[1].data(); V.my = s.rec[2].data(); V.wx = s.rec[3].data(); V.wy = s.rec[4].data();
+        V.cell = s.cell.data();
+        int64_t n = (int64_t)Nx * s.ny, off = local_winds ? 0 : (int64_t)s.j0 * Nx;
+        for (int64_t l = 0; l < n; l++) {
+            int I = (int)(l % Nx) + 1, J = (int)(l / Nx) + 1 + s.j0;
+            if (!h->accumulate) { s.S[0][l] = 0.0; s.S[1][l] = 0.0; s.S[2][l] = 0.0; }
+            gather_node(V, I, J, R, h->P.periodic_boundary ? 2 : 1, s.S[0][l], s.S[1][l], s.S[2][l]);
+        }
+        for (int64_t l = 0; l < n; l++) {
+            if (!(s.flags[l] & PICLES_PF_ACTIVE)) continue;
+            Particle p;
+            load(s, l, p);
+            Tally c;
+            tally_zero(c);
+            remesh_particle(h->P, p, s.S[0][l], s.S[1][l], s.S[2][l], u_t[off + l], v_t[off + l], DT, c);
+            tally_add(T, c);
+            store(s, l, p);
+        }
+    }
+}
+
+void shim_step(Shim* h, double t, double DT, const double* u_t, const double* v_t, const double* u_t1, const double* v_t1) {
+    (void)t;
+    const int Nx = h->Nx;
+    Tally T;
+    tally_zero(T);
+    shim_advance_all(h, DT, u_t, v_t, u_t1, v_t1, T, false);
     /* halo exchange: my first/last H owned rows -> neighbour's upper/lower halo rows */
     int H = h->halo, ns = h->nstrips;
     if (ns > 1 && H > 0) {
@@ -149,29 +181,80 @@ void shim_step(Shim* h, double t, double DT, const double* u_t, const double* v_
     }
     int R = T.reach < PH_REACH_MAX ? T.reach : PH_REACH_MAX;
     if (ns > 1 && R > H) R = H;
-    /* projection gather + remesh */
-    for (auto& s : h->s) {
-        RecView V;
-        V.Nx = Nx; V.Ny = h->Ny; V.bx = h->bx; V.by = h->by; V.j0 = s.j0; V.ny = s.ny; V.halo = s.halo;
-        V.e = s.rec[0].data(); V.mx = s.rec[1].data(); V.my = s.rec[2].data(); V.wx = s.rec[3].data(); V.wy = s.rec[4].data();
-        V.cell = s.cell.data();
-        int64_t n = (int64_t)Nx * s.ny, off = (int64_t)s.j0 * Nx;
-        for (int64_t l = 0; l < n; l++) {
-            int I = (int)(l % Nx) + 1, J = (int)(l / Nx) + 1 + s.j0;
-            if (!h->accumulate) { s.S[0][l] = 0.0; s.S[1][l] = 0.0; s.S[2][l] = 0.0; }
-            gather_node(V, I, J, R, h->P.periodic_boundary ? 2 : 1, s.S[0][l], s.S[1][l], s.S[2][l]);
-        }
-        for (int64_t l = 0; l < n; l++) {
-            if (!(s.flags[l] & PICLES_PF_ACTIVE)) continue;
-            Particle p;
-            load(s, l, p);
-            Tally c;
-            tally_zero(c);
-            remesh_particle(h->P, p, s.S[0][l], s.S[1][l], s.S[2][l], u_t[off + l], v_t[off + l], DT, c);
-            tally_add(T, c);
-            store(s, l, p);
-        }
+    shim_project_remesh_all(h, DT, R, u_t, v_t, T, false);
+    h->tally = T;
+}
+
+/* ---- one strip per process: the phase-split interface of the C ABI ---------------- */
+Shim* shim_create_strip(int Nx, int Ny, int bx, int by, int j0, int ny, int halo, const uint8_t* mask /* ny*Nx */,
+                        const double* M /* 4 planes ny*Nx */, const double* M_const, const double* pc,
+                        const picles_params_t* P) {
+    Shim* h = new Shim();
+    h->Nx = Nx; h->Ny = Ny; h->bx = bx; h->by = by; h->nstrips = (ny == Ny) ? 1 : 2; h->halo = halo;
+    h->P = *P;
+    h->perM = (M != nullptr);
+    h->hasPc = (pc != nullptr);
+    if (M_const) memcpy(h->Mc, M_const, sizeof h->Mc);
+    h->s.resize(1);
+    Strip& s = h->s[0];
+    s.j0 = j0; s.ny = ny; s.halo = halo;
+    int64_t n = (int64_t)Nx * ny, ne = (int64_t)Nx * (ny + 2 * halo);
+    for (int k = 0; k < 5; k++) { s.z[k].assign(n, 0.0); s.rec[k].assign(ne, 0.0); }
+    s.t.assign(n, 0.0); s.dt.assign(n, 0.0); s.qold.assign(n, 0.0);
+    for (int k = 0; k < 3; k++) s.S[k].assign(n, 0.0);
+    s.iter.assign(n, 0); s.cell.assign(ne, PH_CELL_INVALID);
+    s.flags.assign(n, 0); s.status.assign(n, 0);
+    s.mask.assign(mask, mask + n);
+    if (M) for (int k = 0; k < 4; k++) s.M[k].assign(M + k * n, M + (k + 1) * n);
+    if (pc) s.pc.assign(pc, pc + n);
+    tally_zero(h->tally);
+    return h;
+}
+void shim_strip_seed(Shim* h, const double* u0, const double* v0) {
+    Strip& s = h->s[0];
+    int64_t n = (int64_t)h->Nx * s.ny;
+    for (int64_t l = 0; l < n; l++) {
+        Particle p;
+        double e, mx, my;
+        seed_particle(h->P, s.mask[l], u0[l], v0[l], p, e, mx, my);
+        store(s, l, p);
+        s.S[0][l] = e; s.S[1][l] = mx; s.S[2][l] = my;
     }
+    std::fill(s.cell.begin(), s.cell.end(), PH_CELL_INVALID);
+}
+void shim_strip_advance(Shim* h, double DT, const double* u_t, const double* v_t, const double* u_t1, const double* v_t1) {
+    Tally T;
+    tally_zero(T);
+    shim_advance_all(h, DT, u_t, v_t, u_t1, v_t1, T, true);
+    h->tally = T;
+}
+int64_t shim_strip_halo_bytes(const Shim* h) { return (int64_t)h->halo * h->Nx * 44; }
+/* same packing as k_halo_pack / k_halo_unpack: 5 planes of doubles then the cell plane */
+void shim_strip_pack(const Shim* h, char* lo, char* hi) {
+    const Strip& s = h->s[0];
+    int64_t m = (int64_t)h->halo * h->Nx;
+    for (int k = 0; k < 5; k++) {
+        memcpy(lo + k * m * 8, &s.rec[k][(int64_t)s.halo * h->Nx], m * 8);
+        memcpy(hi + k * m * 8, &s.rec[k][(int64_t)s.ny * h->Nx], m * 8);
+    }
+    memcpy(lo + 5 * m * 8, &s.cell[(int64_t)s.halo * h->Nx], m * 4);
+    memcpy(hi + 5 * m * 8, &s.cell[(int64_t)s.ny * h->Nx], m * 4);
+}
+void shim_strip_unpack(Shim* h, const char* lo, const char* hi) {
+    Strip& s = h->s[0];
+    int64_t m = (int64_t)h->halo * h->Nx;
+    for (int k = 0; k < 5; k++) {
+        memcpy(&s.rec[k][0], lo + k * m * 8, m * 8);
+        memcpy(&s.rec[k][(int64_t)(s.ny + s.halo) * h->Nx], hi + k * m * 8, m * 8);
+    }
+    memcpy(&s.cell[0], lo + 5 * m * 8, m * 4);
+    memcpy(&s.cell[(int64_t)(s.ny + s.halo) * h->Nx], hi + 5 * m * 8, m * 4);
+}
+void shim_strip_project_remesh(Shim* h, double DT, int R, const double* u_t, const double* v_t) {
+    Tally T = h->tally;
+    if (R > PH_REACH_MAX) R = PH_REACH_MAX;
+    if (h->s[0].ny != h->Ny && R > h->halo) R = h->halo;
+    shim_project_remesh_all(h, DT, R, u_t, v_t, T, true);
     h->tally = T;
 }
 
@@ -180,6 +263,13 @@ void shim_get_state(const Shim* h, double* S) {
     for (auto& s : h->s) {
         int64_t n = (int64_t)h->Nx * s.ny, off = (int64_t)s.j0 * h->Nx;
         for (int k = 0; k < 3; k++) memcpy(S + k * plane + off, s.S[k].data(), n * 8);
+    }
+}
+void shim_set_state(Shim* h, const double* S) {
+    int64_t plane = (int64_t)h->Nx * h->Ny;
+    for (auto& s : h->s) {
+        int64_t n = (int64_t)h->Nx * s.ny, off = (int64_t)s.j0 * h->Nx;
+        for (int k = 0; k < 3; k++) memcpy(s.S[k].data(), S + k * plane + off, n * 8);
     }
 }
 void shim_get_particles(const Shim* h, double* z, double* t, double* dt, double* qold, int32_t* iter, uint8_t* flags,
