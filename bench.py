@@ -346,7 +346,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "roofline": roofline, "roofline_hbm": roofline_hbm,
             "measured_here": {"fp64_dfma_tflops": fp64_peak, "hbm_copy_gbs": hbm_meas},
-            "clocks": clocks, "gpu_launches": 3 * args.steps,
+            "clocks": clocks, "gpu_launches": (3 if world == 1 else 5) * args.steps,
             "substeps_per_particle_step": float(np.mean([c["n_substeps"] / max(c["n_integrated"], 1) for c in per_step])),
             "max_attempts": int(max(c["max_attempts"] for c in per_step)),
             "rejects": int(sum(c["n_rejects"] for c in per_step)),

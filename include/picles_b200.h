@@ -50,7 +50,8 @@ typedef enum {
     PICLES_ERR_CUDA = -2,     /* CUDA runtime error or no usable device */
     PICLES_ERR_ALLOC = -3,    /* device allocation failed */
     PICLES_ERR_HALO = -4,     /* particle reach exceeded the halo width */
-    PICLES_ERR_STATE = -5     /* grid/params/seed missing */
+    PICLES_ERR_STATE = -5,    /* grid/params/seed missing */
+    PICLES_ERR_COMM = -6      /* NCCL unavailable or a collective failed */
 } picles_status_t;
 
 /* axis boundary types: custom_structures.jl:51-61 */
@@ -208,6 +209,31 @@ int picles_step_project_remesh(picles_t* h, double t, double dt_model);
 int picles_synchronize(picles_t* h);
 /* reach (cells) of the last advance on this strip; the caller all-reduces(max) it */
 int picles_get_reach(picles_t* h, int32_t* reach);
+
+/* ---- multi-GPU: y-strips, one handle per GPU/process ------------------------- */
+/*
+ * The reference has no domain decomposition; strips are this library's
+ * own.  Between the advance and the gather each strip sends the deposit records of its
+ * first / last `halo` rows to its y-neighbours, so every GPU sums its own nodes in the
+ * reference's canonical order and the result does not depend on the GPU count.
+ *   picles_comm_unique_id   rank 0 creates the NCCL id (128 bytes); the host broadcasts it
+ *                           with whatever it has (MPI.jl, Distributed.jl, torch.distributed)
+ *   picles_comm_init        every rank joins; nccl_path = libnccl.so.2 to dlopen, NULL =
+ *                           the copy already in the process, else the default soname
+ *   picles_halo_exchange    pack -> ncclSend/ncclRecv (one group) -> unpack, asynchronous on
+ *                           the handle's stream; lo_rank / hi_rank = ranks owning the rows
+ *                           below / above this strip, -1 for none (domain edge)
+ *   picles_step_strip       picles_step for a strip, exchange included
+ */
+#define PICLES_COMM_ID_BYTES 128
+int picles_comm_unique_id(char* id128, const char* nccl_path);
+int picles_comm_init(picles_t* h, const char* id128, int rank, int nranks, const char* nccl_path);
+int picles_comm_destroy(picles_t* h);
+int picles_halo_exchange(picles_t* h, int lo_rank, int hi_rank);
+int picles_step_strip(picles_t* h, double t, double dt_model,
+                      const double* u_t, const double* v_t,
+                      const double* u_t1, const double* v_t1,
+                      int lo_rank, int hi_rank);
 
 /* ---- state access ------------------------------------------------------ */
 int picles_get_state(picles_t* h, double* S /* ny_local*Nx*3: planes e, m_x, m_y */);

@@ -24,7 +24,7 @@ PF_ON, PF_BOUNDARY, PF_DT_RESET, PF_ACTIVE = 1, 2, 4, 8
 
 OPT_ACCUMULATE_STATE = 1
 
-ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_ALLOC", -4: "ERR_HALO", -5: "ERR_STATE"}
+ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_ALLOC", -4: "ERR_HALO", -5: "ERR_STATE", -6: "ERR_COMM"}
 
 
 class PiclesParams(C.Structure):
@@ -119,6 +119,11 @@ SYMBOLS = {
     "picles_step_project_remesh": (C.c_int, [_vp, C.c_double, C.c_double]),
     "picles_synchronize": (C.c_int, [_vp]),
     "picles_get_reach": (C.c_int, [_vp, _i32p]),
+    "picles_comm_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "picles_comm_init": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
+    "picles_comm_destroy": (C.c_int, [_vp]),
+    "picles_halo_exchange": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "picles_step_strip": (C.c_int, [_vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
     "picles_get_state": (C.c_int, [_vp, _vp]),
     "picles_set_state": (C.c_int, [_vp, _vp]),
     "picles_get_particles": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),

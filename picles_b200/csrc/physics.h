@@ -711,6 +711,18 @@ PM_HD void unpack_cell(int32_t cell, int32_t& fx, int32_t& fy, int& cls) {
     fy = (int32_t)(((uint32_t)cell >> 14) & 0x3fffu) - PH_CELL_BIAS;
     cls = (int)(((uint32_t)cell >> 28) & 1u);
 }
+/* reach of one deposit record: max |corner - home| over its four corners (0 if none) */
+PM_HD int32_t cell_reach(int32_t cell) {
+    if (cell == PH_CELL_INVALID) return 0;
+    int32_t fx, fy, d, r = 0;
+    int cls;
+    unpack_cell(cell, fx, fy, cls);
+    d = fx < 0 ? -fx : fx; if (d > r) r = d;
+    d = fx + 1 < 0 ? -(fx + 1) : fx + 1; if (d > r) r = d;
+    d = fy < 0 ? -fy : fy; if (d > r) r = d;
+    d = fy + 1 < 0 ? -(fy + 1) : fy + 1; if (d > r) r = d;
+    return r;
+}
 
 
 /* ---- ParticleToNode! as a gather --------------------------------------------- */

@@ -4,6 +4,7 @@
  * No torch types, no CPU fallback.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -38,6 +39,8 @@ struct picles_handle {
     int64_t n_active = 0;
     bool timing_valid = false;
     int accumulate = 0; /* PICLES_OPT_ACCUMULATE_STATE */
+    void* comm = nullptr; /* ncclComm_t of the strip communicator */
+    int comm_rank = -1, comm_size = 0;
     char err[512];
 };
 
@@ -85,6 +88,59 @@ static void free_grid(picles_t* h) {
     h->have_grid = h->seeded = h->winds_loaded = false;
 }
 
+/* ---- NCCL, bound at run time --------------------------------------------------------
+ * The strip communicator is the only place the library talks to another GPU.  NCCL is
+ * resolved with dlopen so a single-GPU host (or one that exchanges halos itself through
+ * picles_halo_buffers) needs no NCCL at all; a host process that already loaded NCCL
+ * (torch, NCCL.jl) shares that copy.  Only the types the six entry points need are
+ * declared here (nccl.h: ncclUniqueId is 128 opaque bytes, ncclInt8 = 0). */
+typedef struct { char internal[128]; } pk_nccl_id_t;
+typedef int (*pk_nccl_get_id_fn)(pk_nccl_id_t*);
+typedef int (*pk_nccl_init_rank_fn)(void**, int, pk_nccl_id_t, int);
+typedef int (*pk_nccl_destroy_fn)(void*);
+typedef int (*pk_nccl_sendrecv_fn)(void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*pk_nccl_group_fn)(void);
+typedef const char* (*pk_nccl_errstr_fn)(int);
+static struct {
+    void* dl = nullptr;
+    pk_nccl_get_id_fn get_id = nullptr;
+    pk_nccl_init_rank_fn init_rank = nullptr;
+    pk_nccl_destroy_fn destroy = nullptr;
+    pk_nccl_sendrecv_fn send = nullptr, recv = nullptr;
+    pk_nccl_group_fn group_start = nullptr, group_end = nullptr;
+    pk_nccl_errstr_fn errstr = nullptr;
+} g_nccl;
+
+static int nccl_load(picles_t* h, const char* path) {
+    if (g_nccl.dl) return 0;
+    void* dl = nullptr;
+    if (path && *path) dl = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!dl) dl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL); /* the host's copy */
+    if (!dl) dl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!dl) dl = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!dl) return fail(h, PICLES_ERR_COMM, "cannot load NCCL (%s); pass the path of libnccl.so.2", dlerror());
+#define PK_SYM(field, type, name)                                                                \
+    g_nccl.field = (type)dlsym(dl, name);                                                        \
+    if (!g_nccl.field) return fail(h, PICLES_ERR_COMM, "NCCL symbol %s not found", name);
+    PK_SYM(get_id, pk_nccl_get_id_fn, "ncclGetUniqueId")
+    PK_SYM(init_rank, pk_nccl_init_rank_fn, "ncclCommInitRank")
+    PK_SYM(destroy, pk_nccl_destroy_fn, "ncclCommDestroy")
+    PK_SYM(send, pk_nccl_sendrecv_fn, "ncclSend")
+    PK_SYM(recv, pk_nccl_sendrecv_fn, "ncclRecv")
+    PK_SYM(group_start, pk_nccl_group_fn, "ncclGroupStart")
+    PK_SYM(group_end, pk_nccl_group_fn, "ncclGroupEnd")
+    PK_SYM(errstr, pk_nccl_errstr_fn, "ncclGetErrorString")
+#undef PK_SYM
+    g_nccl.dl = dl;
+    return 0;
+}
+#define NCK(call)                                                                                   \
+    do {                                                                                            \
+        int r_ = (call);                                                                            \
+        if (r_ != 0) return fail(h, PICLES_ERR_COMM, "%s failed: %s", #call, g_nccl.errstr(r_));    \
+    } while (0)
+
+
 extern "C" {
 
 int picles_abi_version(void) { return PICLES_ABI_VERSION; }
@@ -129,6 +185,7 @@ int picles_destroy(picles_t* h) {
     if (!h) return PICLES_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.destroy) { g_nccl.destroy(h->comm); h->comm = nullptr; }
     free_grid(h);
     if (h->d_counters) cudaFree(h->d_counters);
     if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -308,7 +365,7 @@ int picles_halo_pack(picles_t* h) {
 int picles_halo_unpack(picles_t* h) {
     int rc = need_ready(h, true);
     if (rc) return rc;
-    launch_halo_unpack(h->A, h->recv_lo, h->recv_hi, h->sms, h->stream);
+    launch_halo_unpack(h->A, h->recv_lo, h->recv_hi, h->d_counters, h->sms, h->stream);
     CK(cudaGetLastError());
     return PICLES_OK;
 }
@@ -339,7 +396,7 @@ int picles_step_project_remesh(picles_t* h, double t, double dt_model) {
     (void)t;
     /* a halo exchange may have run since the advance: ms_project brackets the gather alone */
     CK(cudaEventRecord(h->ev[2], h->stream));
-    launch_project(h->A, h->P.periodic_boundary ? 2 : 1, h->accumulate, &h->d_counters->reach, h->sms, h->stream);
+    launch_project(h->A, h->P.periodic_boundary ? 2 : 1, h->accumulate, h->d_counters, h->sms, h->stream);
     CK(cudaEventRecord(h->ev[3], h->stream));
     launch_remesh(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream);
     CK(cudaEventRecord(h->ev[4], h->stream));
@@ -367,7 +424,7 @@ int picles_step(picles_t* h, double t, double dt_model, const double* u_t, const
     launch_advance(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream);
     CK(cudaEventRecord(h->ev[1], h->stream));
     CK(cudaEventRecord(h->ev[2], h->stream));
-    launch_project(h->A, h->P.periodic_boundary ? 2 : 1, h->accumulate, &h->d_counters->reach, h->sms, h->stream);
+    launch_project(h->A, h->P.periodic_boundary ? 2 : 1, h->accumulate, h->d_counters, h->sms, h->stream);
     CK(cudaEventRecord(h->ev[3], h->stream));
     launch_remesh(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream);
     CK(cudaEventRecord(h->ev[4], h->stream));
@@ -568,6 +625,91 @@ int picles_measure_hbm_copy(picles_t* h, int mib, double* gbs) {
     CK(cudaGetLastError());
     *gbs = best;
     return PICLES_OK;
+}
+
+/* ---- strip communicator: halo exchange over NVLink inside the library ----------------- */
+int picles_comm_unique_id(char* id128, const char* nccl_path) {
+    picles_t* h = nullptr;
+    if (!id128) return fail(nullptr, PICLES_ERR_ARG, "null id buffer");
+    int rc = nccl_load(nullptr, nccl_path);
+    if (rc) return rc;
+    pk_nccl_id_t id;
+    NCK(g_nccl.get_id(&id));
+    memcpy(id128, id.internal, sizeof id.internal);
+    return PICLES_OK;
+}
+
+int picles_comm_init(picles_t* h, const char* id128, int rank, int nranks, const char* nccl_path) {
+    if (!h || !id128) return fail(h, PICLES_ERR_ARG, "null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, PICLES_ERR_ARG, "bad rank %d of %d", rank, nranks);
+    if (h->comm) return fail(h, PICLES_ERR_STATE, "communicator already initialised");
+    int rc = nccl_load(h, nccl_path);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    pk_nccl_id_t id;
+    memcpy(id.internal, id128, sizeof id.internal);
+    NCK(g_nccl.init_rank(&h->comm, nranks, id, rank));
+    h->comm_rank = rank;
+    h->comm_size = nranks;
+    return PICLES_OK;
+}
+
+int picles_comm_destroy(picles_t* h) {
+    if (!h) return fail(nullptr, PICLES_ERR_ARG, "null handle");
+    if (h->comm) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+        NCK(g_nccl.destroy(h->comm));
+        h->comm = nullptr;
+        h->comm_rank = -1;
+        h->comm_size = 0;
+    }
+    return PICLES_OK;
+}
+
+/* pack -> grouped ncclSend/ncclRecv with the two y-neighbours -> unpack, all enqueued on the
+   handle's stream: no host synchronisation between the advance and the gather */
+int picles_halo_exchange(picles_t* h, int lo_rank, int hi_rank) {
+    int rc = need_ready(h, true);
+    if (rc) return rc;
+    if (h->A.halo == 0) return PICLES_OK;
+    if ((lo_rank >= 0 || hi_rank >= 0) && !h->comm)
+        return fail(h, PICLES_ERR_STATE, "picles_comm_init must be called before picles_halo_exchange");
+    if (lo_rank >= h->comm_size || hi_rank >= h->comm_size || lo_rank == h->comm_rank || hi_rank == h->comm_rank) {
+        /* a periodic ring of one strip would be its own neighbour: not a strip decomposition */
+        return fail(h, PICLES_ERR_ARG, "bad neighbour ranks lo=%d hi=%d (rank %d of %d)", lo_rank, hi_rank, h->comm_rank, h->comm_size);
+    }
+    launch_halo_pack(h->A, h->send_lo, h->send_hi, h->sms, h->stream);
+    CK(cudaGetLastError());
+    if (lo_rank >= 0 || hi_rank >= 0) {
+        size_t nb = (size_t)h->halo_bytes;
+        NCK(g_nccl.group_start());
+        /* my first rows -> the lower neighbour's upper halo, my last rows -> the upper
+           neighbour's lower halo.  Sends are issued lo,hi and receives hi,lo so that a
+           periodic ring of two strips (lo_rank == hi_rank) pairs them up correctly:
+           NCCL matches the operations between two ranks in issue order. */
+        if (lo_rank >= 0) NCK(g_nccl.send(h->send_lo, nb, 0 /* ncclInt8 */, lo_rank, h->comm, h->stream));
+        if (hi_rank >= 0) NCK(g_nccl.send(h->send_hi, nb, 0, hi_rank, h->comm, h->stream));
+        if (hi_rank >= 0) NCK(g_nccl.recv(h->recv_hi, nb, 0, hi_rank, h->comm, h->stream));
+        if (lo_rank >= 0) NCK(g_nccl.recv(h->recv_lo, nb, 0, lo_rank, h->comm, h->stream));
+        NCK(g_nccl.group_end());
+    }
+    launch_halo_unpack(h->A, h->recv_lo, h->recv_hi, h->d_counters, h->sms, h->stream);
+    CK(cudaGetLastError());
+    return PICLES_OK;
+}
+
+/* one model step of a strip, exchange included: upload winds, advance, halo exchange,
+   gather, remesh; one host synchronisation at the end (the counters) */
+int picles_step_strip(picles_t* h, double t, double dt_model, const double* u_t, const double* v_t, const double* u_t1,
+                      const double* v_t1, int lo_rank, int hi_rank) {
+    int rc = picles_upload_winds(h, u_t, v_t, u_t1, v_t1);
+    if (rc) return rc;
+    rc = picles_step_advance(h, t, dt_model);
+    if (rc) return rc;
+    rc = picles_halo_exchange(h, lo_rank, hi_rank);
+    if (rc) return rc;
+    return picles_step_project_remesh(h, t, dt_model);
 }
 
 } /* extern "C" */

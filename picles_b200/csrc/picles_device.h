@@ -45,20 +45,22 @@ struct DeviceArrays {
 struct DeviceCounters {
     /* integrated, substeps, rejects, rhs, reseed, fixups, failed, deposited, A, B, C, D */
     unsigned long long sums[12];
-    int32_t reach;
+    int32_t reach;        /* max reach of this strip's own deposits */
     int32_t max_attempts;
+    int32_t reach_halo;   /* max reach of the records received into the halo rows */
+    int32_t pad_;
 };
 
 void launch_seed(const DeviceArrays& A, const picles_params_t& P, const double* u0, const double* v0, int sms,
                  cudaStream_t st);
 void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
                     cudaStream_t st);
-void launch_project(const DeviceArrays& A, int n_classes, int accumulate, const int32_t* reach, int sms, cudaStream_t st);
+void launch_project(const DeviceArrays& A, int n_classes, int accumulate, const DeviceCounters* dc, int sms, cudaStream_t st);
 void launch_remesh(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
                    cudaStream_t st);
 void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cudaStream_t st);
 void launch_halo_pack(const DeviceArrays& A, char* lo, char* hi, int sms, cudaStream_t st);
-void launch_halo_unpack(const DeviceArrays& A, const char* lo, const char* hi, int sms, cudaStream_t st);
+void launch_halo_unpack(const DeviceArrays& A, const char* lo, const char* hi, DeviceCounters* dc, int sms, cudaStream_t st);
 void launch_fill_i32(int32_t* p, int64_t n, int32_t v, int sms, cudaStream_t st);
 void launch_selftest_math(uint64_t seed, int iters, unsigned long long* out, int sms, cudaStream_t st);
 void launch_fp64_peak(double* out, int iters, int sms, cudaStream_t st, int64_t* fmas);

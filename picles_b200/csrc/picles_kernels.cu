@@ -147,12 +147,14 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc) {
  * very same code.  Neighbouring threads read overlapping record windows, which L1/L2
  * serve; HBM sees each record once.
  */
-__global__ void __launch_bounds__(PRJ_THREADS) k_project(DeviceArrays A, int n_classes, int accumulate, const int32_t* __restrict__ reach_ptr) {
+__global__ void __launch_bounds__(PRJ_THREADS) k_project(DeviceArrays A, int n_classes, int accumulate, const DeviceCounters* __restrict__ dc) {
     RecView V;
     V.Nx = A.Nx; V.Ny = A.Ny; V.bx = A.bx; V.by = A.by; V.j0 = A.j0; V.ny = A.ny; V.halo = A.halo;
     V.e = A.rec[0]; V.mx = A.rec[1]; V.my = A.rec[2]; V.wx = A.rec[3]; V.wy = A.rec[4];
     V.cell = A.cell;
-    int R = min(*reach_ptr, PH_REACH_MAX);
+    /* deposits landing on this strip come from its own particles (reach) and from the
+       neighbours' rows received into the halo (reach_halo) */
+    int R = min(max(dc->reach, dc->reach_halo), PH_REACH_MAX);
     if (A.ny != A.Ny) R = min(R, A.halo); /* strips: the host rejects reach > halo (PICLES_ERR_HALO) */
     /* 2-D launch: blockIdx.y strides rows, threads run along x (no integer division) */
     for (int jr = blockIdx.y; jr < A.ny; jr += gridDim.y) {
@@ -232,8 +234,10 @@ __global__ void k_halo_pack(DeviceArrays A, char* __restrict__ send_lo, char* __
         ((int32_t*)(send_hi + 5 * m * 8))[q] = A.cell[hi];
     }
 }
-__global__ void k_halo_unpack(DeviceArrays A, const char* __restrict__ recv_lo, const char* __restrict__ recv_hi) {
+__global__ void k_halo_unpack(DeviceArrays A, const char* __restrict__ recv_lo, const char* __restrict__ recv_hi,
+                              DeviceCounters* dc) {
     int64_t m = (int64_t)A.halo * A.Nx;
+    int32_t reach = 0;
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < m; q += (int64_t)gridDim.x * blockDim.x) {
         int64_t lo = q;                                           /* lower halo rows */
         int64_t hi = (int64_t)(A.ny + A.halo) * A.Nx + q;         /* upper halo rows */
@@ -242,9 +246,13 @@ __global__ void k_halo_unpack(DeviceArrays A, const char* __restrict__ recv_lo, 
             A.rec[k][lo] = ((const double*)recv_lo)[k * m + q];
             A.rec[k][hi] = ((const double*)recv_hi)[k * m + q];
         }
-        A.cell[lo] = ((const int32_t*)(recv_lo + 5 * m * 8))[q];
-        A.cell[hi] = ((const int32_t*)(recv_hi + 5 * m * 8))[q];
+        int32_t clo = ((const int32_t*)(recv_lo + 5 * m * 8))[q], chi = ((const int32_t*)(recv_hi + 5 * m * 8))[q];
+        A.cell[lo] = clo;
+        A.cell[hi] = chi;
+        reach = max(reach, max(cell_reach(clo), cell_reach(chi)));
     }
+    reach = warp_max(reach);
+    if ((threadIdx.x & 31) == 0 && reach) atomicMax(&dc->reach_halo, reach);
 }
 __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) p[q] = v;
@@ -340,11 +348,11 @@ void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, 
     else k_advance<false><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc);
 }
 
-void launch_project(const DeviceArrays& A, int n_classes, int accumulate, const int32_t* reach, int sms, cudaStream_t st) {
+void launch_project(const DeviceArrays& A, int n_classes, int accumulate, const DeviceCounters* dc, int sms, cudaStream_t st) {
     int gx = (A.Nx + PRJ_THREADS - 1) / PRJ_THREADS;
     int gy = A.ny < 65535 ? A.ny : 65535;
     (void)sms;
-    k_project<<<dim3(gx, gy), PRJ_THREADS, 0, st>>>(A, n_classes, accumulate, reach);
+    k_project<<<dim3(gx, gy), PRJ_THREADS, 0, st>>>(A, n_classes, accumulate, dc);
 }
 
 void launch_remesh(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
@@ -361,9 +369,9 @@ void launch_halo_pack(const DeviceArrays& A, char* lo, char* hi, int sms, cudaSt
     int64_t m = (int64_t)A.halo * A.Nx;
     if (m > 0) k_halo_pack<<<grid_for(m, 256, sms, 4), 256, 0, st>>>(A, lo, hi);
 }
-void launch_halo_unpack(const DeviceArrays& A, const char* lo, const char* hi, int sms, cudaStream_t st) {
+void launch_halo_unpack(const DeviceArrays& A, const char* lo, const char* hi, DeviceCounters* dc, int sms, cudaStream_t st) {
     int64_t m = (int64_t)A.halo * A.Nx;
-    if (m > 0) k_halo_unpack<<<grid_for(m, 256, sms, 4), 256, 0, st>>>(A, lo, hi);
+    if (m > 0) k_halo_unpack<<<grid_for(m, 256, sms, 4), 256, 0, st>>>(A, lo, hi, dc);
 }
 void launch_fill_i32(int32_t* p, int64_t n, int32_t v, int sms, cudaStream_t st) {
     if (n > 0) k_fill_i32<<<grid_for(n, 256, sms, 4), 256, 0, st>>>(p, n, v);

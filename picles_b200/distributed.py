@@ -1,0 +1,157 @@
+"""y-strip decomposition of the particle-in-cell step: one process per GPU, one strip per process.
+
+The reference has no domain decomposition: particles are independent
+during the ODE phase and couple only through the bilinear deposit, whose reach is a few
+rows.  Each rank owns a contiguous block of rows of every per-node plane; between the
+advance and the projection gather it ships the deposit records (5 f64 + packed cell) of
+its first / last `halo` rows to the two y-neighbours.  Every rank then sums its own
+nodes in the reference's canonical order, so the fields are bit-identical for any rank
+count.  There is no other data-path collective.
+
+Two transports for the exchange:
+
+  "nccl-lib"   picles_halo_exchange: pack, ncclSend/ncclRecv (one group) and unpack are all
+               enqueued on the handle's stream inside libpicles_b200.so.  torch.distributed
+               is used once, to broadcast the 128-byte NCCL id.  This is the GPU path.
+  "torch-p2p"  torch.distributed.batch_isend_irecv on tensors that alias the engine's halo
+               buffers.  With the gloo backend and a host build of the device code this is
+               what the CPU tests run (world_size 2); with NCCL it is an alternative for
+               hosts that want every collective to stay in torch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+
+def strip_bounds(Ny: int, world: int):
+    """[(j0, j1)) rows of every rank: contiguous, balanced to one row."""
+    return [(Ny * r // world, Ny * (r + 1) // world) for r in range(world)]
+
+
+def neighbours(rank: int, world: int, periodic_y: bool):
+    """(lo, hi): ranks owning the rows below / above this strip, -1 at a domain edge."""
+    if world == 1:
+        return -1, -1
+    lo, hi = rank - 1, rank + 1
+    if periodic_y:
+        return lo % world, hi % world
+    return (lo if lo >= 0 else -1), (hi if hi < world else -1)
+
+
+def slab(a, j0, j1, lead=0):
+    """rows [j0, j1) of a global (…, Ny, Nx) array (None passes through)."""
+    if a is None:
+        return None
+    a = np.asarray(a)
+    return a[(slice(None),) * lead + (slice(j0, j1),)]
+
+
+class _DeviceBytes:
+    """zero-copy view of `nbytes` of device memory for torch.as_tensor"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class NcclLibTransport:
+    """halo exchange inside the library (picles_comm_init / picles_halo_exchange)"""
+
+    name = "nccl-lib"
+
+    def __init__(self, eng, rank, world, nccl_path=None, bcast=None):
+        lib = eng.lib
+        path = nccl_path.encode() if nccl_path else None
+        idbuf = C.create_string_buffer(128)
+        if rank == 0:
+            eng._check(lib.picles_comm_unique_id(idbuf, path), None)
+        payload = [idbuf.raw if rank == 0 else None]
+        if bcast is None:
+            import torch.distributed as dist
+            dist.broadcast_object_list(payload, src=0)
+        else:
+            payload[0] = bcast(payload[0])
+        eng._check(lib.picles_comm_init(eng.h, payload[0], int(rank), int(world), path))
+        self.eng = eng
+
+    def exchange(self, lo, hi):
+        e = self.eng
+        e._check(e.lib.picles_halo_exchange(e.h, int(lo), int(hi)))
+
+
+class TorchP2PTransport:
+    """halo exchange through torch.distributed point-to-point operations"""
+
+    name = "torch-p2p"
+
+    def __init__(self, eng, rank, world):
+        import torch
+        self.torch = torch
+        self.eng = eng
+        bufs, nb = eng.halo_buffers()
+        self.on_device = not isinstance(bufs[0], np.ndarray)
+        if self.on_device:
+            dev = torch.device("cuda", eng.device)
+            self.t = [torch.as_tensor(_DeviceBytes(p, nb), device=dev) for p in bufs]
+        else:
+            self.t = [torch.from_numpy(b) for b in bufs]
+
+    def exchange(self, lo, hi):
+        import torch.distributed as dist
+        e = self.eng
+        e.halo_pack()
+        send_lo, send_hi, recv_lo, recv_hi = self.t
+        ops = []
+        # tag 1: rows travelling down (my first rows -> lower neighbour's upper halo),
+        # tag 0: rows travelling up.  Issue order sends lo,hi / receives hi,lo so a two-strip
+        # ring (lo == hi) pairs correctly on backends that ignore tags (NCCL).
+        if lo >= 0:
+            ops.append(dist.P2POp(dist.isend, send_lo, lo, tag=1))
+        if hi >= 0:
+            ops.append(dist.P2POp(dist.isend, send_hi, hi, tag=0))
+        if hi >= 0:
+            ops.append(dist.P2POp(dist.irecv, recv_hi, hi, tag=1))
+        if lo >= 0:
+            ops.append(dist.P2POp(dist.irecv, recv_lo, lo, tag=0))
+        if ops:
+            if self.on_device:
+                e.synchronize()  # pack ran on the handle's stream; NCCL runs on torch's
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            if self.on_device:
+                self.torch.cuda.current_stream().synchronize()
+        e.halo_unpack()
+
+
+class StripStepper:
+    """time_step! of one y-strip: upload winds, advance, halo exchange, gather, remesh."""
+
+    def __init__(self, eng, rank, world, periodic_y=False, transport="nccl-lib", **kw):
+        if world > 1 and eng.halo < 1:
+            raise ValueError("a strip decomposition needs halo >= 1")
+        self.eng, self.rank, self.world = eng, int(rank), int(world)
+        self.lo, self.hi = neighbours(self.rank, self.world, periodic_y)
+        if world == 1:
+            self.transport = None
+        elif transport == "nccl-lib":
+            self.transport = NcclLibTransport(eng, rank, world, **kw)
+        elif transport == "torch-p2p":
+            self.transport = TorchP2PTransport(eng, rank, world)
+        else:
+            raise ValueError(f"unknown transport {transport!r}")
+
+    def step(self, t, DT, host_ptrs=None, winds=None):
+        """host_ptrs = (u_t1, v_t1) raw host pointers of this strip's wind at t+DT (the
+        previous t+DT level becomes the t level); winds = (u_t, v_t, u_t1, v_t1) arrays;
+        neither: reuse what is on the device."""
+        e = self.eng
+        if host_ptrs is not None:
+            e.upload_winds_raw(None, None, host_ptrs[0], host_ptrs[1])
+        elif winds is not None:
+            e.upload_winds(*winds)
+        e.step_advance(t, DT)
+        if self.transport is not None:
+            self.transport.exchange(self.lo, self.hi)
+        e.step_project_remesh(t, DT)

@@ -27,6 +27,7 @@ class B200Engine:
         self.j0 = int(j0)
         self.ny = int(Ny if ny_local is None else ny_local)
         self.halo = int(halo)
+        self.device = int(device)
         self.h = C.c_void_p()
         self._check(self.lib.picles_create(C.byref(self.h), int(device)), None)
         mask = np.ascontiguousarray(np.asarray(mask, np.uint8).reshape(self.ny, self.Nx))
@@ -83,6 +84,9 @@ class B200Engine:
         a = [self._wind(x) for x in (u_t, v_t, u_t1, v_t1)]
         self._check(self.lib.picles_upload_winds(self.h, *[_ptr(x) for x in a]))
 
+    def upload_winds_raw(self, pu_t=None, pv_t=None, pu_t1=None, pv_t1=None):
+        self._check(self.lib.picles_upload_winds(self.h, pu_t, pv_t, pu_t1, pv_t1))
+
     def step_advance(self, t, DT):
         self._check(self.lib.picles_step_advance(self.h, float(t), float(DT)))
 
@@ -100,6 +104,14 @@ class B200Engine:
 
     def step_project_remesh(self, t, DT):
         self._check(self.lib.picles_step_project_remesh(self.h, float(t), float(DT)))
+
+    def halo_exchange(self, lo=-1, hi=-1):
+        """pack -> ncclSend/ncclRecv with the ranks owning the rows below/above -> unpack"""
+        self._check(self.lib.picles_halo_exchange(self.h, int(lo), int(hi)))
+
+    def step_strip(self, t, DT, u_t=None, v_t=None, u_t1=None, v_t1=None, lo=-1, hi=-1):
+        a = [self._wind(x) for x in (u_t, v_t, u_t1, v_t1)]
+        self._check(self.lib.picles_step_strip(self.h, float(t), float(DT), *[_ptr(x) for x in a], int(lo), int(hi)))
 
     def synchronize(self):
         self._check(self.lib.picles_synchronize(self.h))

@@ -113,6 +113,17 @@ def shim_lib():
         lib.shim_corner_target.argtypes = [i32, i32, i32, i32, i64, i64]
         lib.shim_rhs.argtypes = [C.POINTER(PiclesParams), vp, d, d, vp, d, vp]
         lib.shim_pack_roundtrip.argtypes = [i32, i32, i32, vp]
+        lib.shim_create_strip.restype = vp
+        lib.shim_create_strip.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(PiclesParams)]
+        lib.shim_strip_seed.argtypes = [vp, vp, vp]
+        lib.shim_strip_advance.argtypes = [vp, d, vp, vp, vp, vp]
+        lib.shim_strip_halo_bytes.restype = i64
+        lib.shim_strip_halo_bytes.argtypes = [vp]
+        lib.shim_strip_pack.argtypes = [vp, vp, vp]
+        lib.shim_strip_unpack.argtypes = [vp, vp, vp]
+        lib.shim_strip_project_remesh.argtypes = [vp, d, vp, vp]
+        lib.shim_get_state_local.argtypes = [vp, vp]
+        lib.shim_get_particles_local.argtypes = [vp] + [vp] * 7
         _shim = lib
     return _shim
 
@@ -244,6 +255,87 @@ class ShimEngine(HostShim):
         c = super().counters()
         c["n_active"] = c["n_remesh_A"] + c["n_remesh_B"] + c["n_remesh_C"] + c["n_remesh_D"]
         return c
+
+
+class ShimStripEngine:
+    """One y-strip of the host build of the device code behind the phase-split interface of
+    B200Engine (upload_winds / step_advance / halo_pack / halo_buffers / halo_unpack /
+    step_project_remesh), with host numpy halo buffers: what one rank of the world_size-2
+    gloo tests drives through picles_b200.distributed.StripStepper."""
+
+    def __init__(self, grid, P, j0, j1, halo):
+        self.lib = shim_lib()
+        self.Nx, self.Ny, self.j0, self.ny, self.halo = grid["Nx"], grid["Ny"], j0, j1 - j0, halo
+        self.device = -1
+        m = np.ascontiguousarray(grid["mask"][j0:j1], dtype=np.uint8)
+        M = np.ascontiguousarray(grid["M"][:, j0:j1], dtype=np.float64) if grid["M"] is not None else None
+        Mc = np.ascontiguousarray(grid["M_const"], dtype=np.float64) if grid["M_const"] is not None else None
+        pc = np.ascontiguousarray(grid["pc"][j0:j1], dtype=np.float64) if grid["pc"] is not None else None
+        self.h = self.lib.shim_create_strip(self.Nx, self.Ny, grid["bx"], grid["by"], j0, self.ny, halo, _p(m), _p(M),
+                                            _p(Mc), _p(pc), C.byref(P))
+        nb = int(self.lib.shim_strip_halo_bytes(self.h))
+        self._bufs = [np.zeros(nb, np.uint8), np.zeros(nb, np.uint8), np.full(nb, 0xFF, np.uint8),
+                      np.full(nb, 0xFF, np.uint8)]  # send_lo, send_hi, recv_lo, recv_hi
+        self._w = [None] * 4
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.shim_destroy(self.h)
+            self.h = None
+
+    def _loc(self, a):
+        return np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.float64), (self.ny, self.Nx)))
+
+    def seed(self, u0, v0):
+        a, b = self._loc(u0), self._loc(v0)
+        self.lib.shim_strip_seed(self.h, _p(a), _p(b))
+        self._w = [a, b, a, b]
+
+    def upload_winds(self, u_t=None, v_t=None, u_t1=None, v_t1=None):
+        if u_t is not None:
+            self._w[0], self._w[1] = self._loc(u_t), self._loc(v_t)
+        elif u_t1 is not None:
+            self._w[0], self._w[1] = self._w[2], self._w[3]
+        if u_t1 is not None:
+            self._w[2], self._w[3] = self._loc(u_t1), self._loc(v_t1)
+
+    def step_advance(self, t, DT):
+        self.lib.shim_strip_advance(self.h, float(DT), *[_p(x) for x in self._w])
+
+    def halo_buffers(self):
+        return self._bufs, self._bufs[0].nbytes
+
+    def halo_pack(self):
+        self.lib.shim_strip_pack(self.h, _p(self._bufs[0]), _p(self._bufs[1]))
+
+    def halo_unpack(self):
+        self.lib.shim_strip_unpack(self.h, _p(self._bufs[2]), _p(self._bufs[3]))
+
+    def step_project_remesh(self, t, DT):
+        self.lib.shim_strip_project_remesh(self.h, float(DT), _p(self._w[0]), _p(self._w[1]))
+
+    def synchronize(self):
+        pass
+
+    def state(self):
+        S = np.empty((3, self.ny, self.Nx))
+        self.lib.shim_get_state_local(self.h, _p(S))
+        return S
+
+    def particles(self):
+        sh = (self.ny, self.Nx)
+        z = np.empty((5,) + sh)
+        t, dt, qold = np.empty(sh), np.empty(sh), np.empty(sh)
+        it = np.empty(sh, np.int32)
+        fl = np.empty(sh, np.uint8)
+        st = np.empty(sh, np.int32)
+        self.lib.shim_get_particles_local(self.h, _p(z), _p(t), _p(dt), _p(qold), _p(it), _p(fl), _p(st))
+        return dict(z=z, t=t, dt=dt, qold=qold, iter=it, flags=fl, status=st)
+
+    def counters(self):
+        out = np.empty(14, np.int32)
+        self.lib.shim_get_tally(self.h, _p(out))
+        return dict(zip(TALLY_NAMES, [int(v) for v in out]))
 
 
 def grid_dict_from_mesh(grid):

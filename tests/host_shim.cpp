@@ -31,6 +31,7 @@ struct Shim {
     std::vector<Strip> s;
     Tally tally;
     int accumulate = 0;
+    int reach_halo = 0; /* per-process strips: max reach of the received halo records */
 };
 
 static void load(const Strip& s, int64_t l, Particle& p) {
@@ -227,6 +228,7 @@ void shim_strip_advance(Shim* h, double DT, const double* u_t, const double* v_t
     tally_zero(T);
     shim_advance_all(h, DT, u_t, v_t, u_t1, v_t1, T, true);
     h->tally = T;
+    h->reach_halo = 0;
 }
 int64_t shim_strip_halo_bytes(const Shim* h) { return (int64_t)h->halo * h->Nx * 44; }
 /* same packing as k_halo_pack / k_halo_unpack: 5 planes of doubles then the cell plane */
@@ -249,9 +251,17 @@ void shim_strip_unpack(Shim* h, const char* lo, const char* hi) {
     }
     memcpy(&s.cell[0], lo + 5 * m * 8, m * 4);
     memcpy(&s.cell[(int64_t)(s.ny + s.halo) * h->Nx], hi + 5 * m * 8, m * 4);
+    /* as k_halo_unpack: the gather's window must cover the neighbours' deposits too */
+    for (int64_t q = 0; q < m; q++) {
+        int r = cell_reach(s.cell[q]);
+        if (r > h->reach_halo) h->reach_halo = r;
+        r = cell_reach(s.cell[(int64_t)(s.ny + s.halo) * h->Nx + q]);
+        if (r > h->reach_halo) h->reach_halo = r;
+    }
 }
-void shim_strip_project_remesh(Shim* h, double DT, int R, const double* u_t, const double* v_t) {
+void shim_strip_project_remesh(Shim* h, double DT, const double* u_t, const double* v_t) {
     Tally T = h->tally;
+    int R = T.reach > h->reach_halo ? T.reach : h->reach_halo;
     if (R > PH_REACH_MAX) R = PH_REACH_MAX;
     if (h->s[0].ny != h->Ny && R > h->halo) R = h->halo;
     shim_project_remesh_all(h, DT, R, u_t, v_t, T, true);
@@ -285,6 +295,24 @@ void shim_get_particles(const Shim* h, double* z, double* t, double* dt, double*
         memcpy(flags + off, s.flags.data(), n);
         for (int64_t l = 0; l < n; l++) status[off + l] = s.status[l];
     }
+}
+/* strip-local accessors (shim_create_strip handles: one strip, local plane size) */
+void shim_get_state_local(const Shim* h, double* S) {
+    const Strip& s = h->s[0];
+    int64_t n = (int64_t)h->Nx * s.ny;
+    for (int k = 0; k < 3; k++) memcpy(S + k * n, s.S[k].data(), n * 8);
+}
+void shim_get_particles_local(const Shim* h, double* z, double* t, double* dt, double* qold, int32_t* iter,
+                              uint8_t* flags, int32_t* status) {
+    const Strip& s = h->s[0];
+    int64_t n = (int64_t)h->Nx * s.ny;
+    for (int k = 0; k < 5; k++) memcpy(z + k * n, s.z[k].data(), n * 8);
+    memcpy(t, s.t.data(), n * 8);
+    memcpy(dt, s.dt.data(), n * 8);
+    memcpy(qold, s.qold.data(), n * 8);
+    memcpy(iter, s.iter.data(), n * 4);
+    memcpy(flags, s.flags.data(), n);
+    for (int64_t l = 0; l < n; l++) status[l] = s.status[l];
 }
 /* integrated, substeps, rejects, rhs, reseed, fixups, failed, deposited, A, B, C, D, reach, max_attempts */
 void shim_get_tally(const Shim* h, int32_t* out14) { memcpy(out14, &h->tally, 14 * sizeof(int32_t)); }
