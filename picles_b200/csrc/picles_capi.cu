@@ -675,7 +675,8 @@ int picles_halo_exchange(picles_t* h, int lo_rank, int hi_rank) {
     if (h->A.halo == 0) return PICLES_OK;
     if ((lo_rank >= 0 || hi_rank >= 0) && !h->comm)
         return fail(h, PICLES_ERR_STATE, "picles_comm_init must be called before picles_halo_exchange");
-    if (lo_rank >= h->comm_size || hi_rank >= h->comm_size || lo_rank == h->comm_rank || hi_rank == h->comm_rank) {
+    if (lo_rank >= h->comm_size || hi_rank >= h->comm_size || (lo_rank >= 0 && lo_rank == h->comm_rank) ||
+        (hi_rank >= 0 && hi_rank == h->comm_rank)) {
         /* a periodic ring of one strip would be its own neighbour: not a strip decomposition */
         return fail(h, PICLES_ERR_ARG, "bad neighbour ranks lo=%d hi=%d (rank %d of %d)", lo_rank, hi_rank, h->comm_rank, h->comm_size);
     }
