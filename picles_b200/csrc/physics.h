@@ -730,6 +730,7 @@ PM_HD int32_t cell_reach(int32_t cell) {
 struct RecView {
     int Nx, Ny, bx, by; /* global shape and boundary types */
     int j0, ny, halo;   /* strip: first owned global row (0-based), rows owned, halo rows */
+    int pitch;          /* elements between consecutive rows of the record planes (>= Nx) */
     const double *e, *mx, *my, *wx, *wy;
     const int32_t* cell;
 };
@@ -784,33 +785,47 @@ PM_HD void axis_candidates(int* lst, int& n, int64_t T, int R, int N, int bnd, b
     }
 }
 
-/* interior fast path with a compile-time reach R (fully unrolled (2R+1)^2 window, one
-   class): every candidate row/column is inside the domain and the strip's storage.
-   `base` = extended linear index of (I,J) itself. */
-template <int R>
-PM_HD void gather_interior(const RecView& V, int64_t base, double& s0, double& s1, double& s2) {
-    const int Nx = V.Nx;
+/* window fast path with a compile-time reach R (fully unrolled (2R+1)^2 window): every
+   candidate row/column is addressable relative to `base`, the element of (I,J) itself, in
+   planes of row pitch `pitch` — the record planes in HBM, or a tile of them staged in shared
+   memory (PITCH > 0: compile-time pitch, so every offset is an immediate).  Elements that
+   hold no deposit (PH_CELL_INVALID, or the zero fill of a TMA box outside the planes)
+   never match.  Order: class, then j, then i — the reference's ocean_points order. */
+template <int R, int PITCH, int NCLS>
+PM_HD void gather_window(const double* __restrict__ pe, const double* __restrict__ pmx, const double* __restrict__ pmy,
+                         const double* __restrict__ pwx, const double* __restrict__ pwy,
+                         const int32_t* __restrict__ pcell, int pitch_rt, int64_t base, double& s0, double& s1,
+                         double& s2) {
+    const int pitch = PITCH > 0 ? PITCH : pitch_rt;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int dj = -R; dj <= R; dj++) {
+    for (int cls = 0; cls < NCLS; cls++) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int di = -R; di <= R; di++) {
-            int64_t le = base + (int64_t)dj * Nx + di;
-            int32_t cell = V.cell[le];
-            /* source (I+di, J+dj) reaches (I,J) iff fx in {-di-1,-di} and fy in {-dj-1,-dj} */
-            int dx = -di - ((int32_t)((uint32_t)cell & 0x3fffu) - PH_CELL_BIAS);
-            int dy = -dj - ((int32_t)(((uint32_t)cell >> 14) & 0x3fffu) - PH_CELL_BIAS);
-            if (cell == PH_CELL_INVALID || (unsigned)dx > 1u || (unsigned)dy > 1u) continue;
-            double wxc = V.wx[le], wyc = V.wy[le];
-            double wx = dx ? wxc : 1.0 - wxc;
-            double wy = dy ? wyc : 1.0 - wyc;
-            double w = wx * wy;
-            s0 += w * V.e[le];
-            s1 += w * V.mx[le];
-            s2 += w * V.my[le];
+        for (int dj = -R; dj <= R; dj++) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int di = -R; di <= R; di++) {
+                int64_t le = base + (int64_t)dj * pitch + di;
+                uint32_t cell = (uint32_t)pcell[le];
+                /* source (I+di, J+dj) reaches (I,J) iff fx in {-di-1,-di} and fy in {-dj-1,-dj};
+                   PH_CELL_INVALID (all ones) and a zero-filled cell decode to |offsets| ~ 8191
+                   and never match.  With one class every record is class 0. */
+                unsigned dx = (unsigned)(PH_CELL_BIAS - di) - (cell & 0x3fffu);
+                unsigned dy = (unsigned)(PH_CELL_BIAS - dj) - ((cell >> 14) & 0x3fffu);
+                if (dx > 1u || dy > 1u) continue;
+                if (NCLS > 1 && (int)((cell >> 28) & 1u) != cls) continue;
+                double wxc = pwx[le], wyc = pwy[le];
+                double wx = dx ? wxc : 1.0 - wxc;
+                double wy = dy ? wyc : 1.0 - wyc;
+                double w = wx * wy;
+                s0 += w * pe[le];
+                s1 += w * pmx[le];
+                s2 += w * pmy[le];
+            }
         }
     }
 }
@@ -829,11 +844,16 @@ PM_HD void gather_node(const RecView& V, int I, int J, int R, int n_classes, dou
     bool fast_x = (V.bx == PICLES_BND_NONPERIODIC) || (I > R && I <= Nx - R);
     bool fast_y = (V.by == PICLES_BND_NONPERIODIC) || (V.by == PICLES_BND_PERIODIC && J > R && J <= Ny - R) ||
                   (V.by == PICLES_BND_TRIPOLAR_NORTH && J <= Ny - R);
-    /* deep interior, single class, small reach: unrolled window (same order: j, then i) */
-    if (n_classes == 1 && R <= 2 && I > R && I <= Nx - R && J > R && J <= Ny - R && fast_x && fast_y) {
-        int64_t base = (int64_t)(J - 1 - V.j0 + V.halo) * Nx + (I - 1);
-        if (R <= 1) gather_interior<1>(V, base, s0, s1, s2);
-        else gather_interior<2>(V, base, s0, s1, s2);
+    /* deep interior, small reach: unrolled window (same order: class, j, then i) */
+    if (R <= 2 && I > R && I <= Nx - R && J > R && J <= Ny - R && fast_x && fast_y) {
+        int64_t base = (int64_t)(J - 1 - V.j0 + V.halo) * V.pitch + (I - 1);
+        if (n_classes == 1) {
+            if (R <= 1) gather_window<1, 0, 1>(V.e, V.mx, V.my, V.wx, V.wy, V.cell, V.pitch, base, s0, s1, s2);
+            else gather_window<2, 0, 1>(V.e, V.mx, V.my, V.wx, V.wy, V.cell, V.pitch, base, s0, s1, s2);
+        } else {
+            if (R <= 1) gather_window<1, 0, 2>(V.e, V.mx, V.my, V.wx, V.wy, V.cell, V.pitch, base, s0, s1, s2);
+            else gather_window<2, 0, 2>(V.e, V.mx, V.my, V.wx, V.wy, V.cell, V.pitch, base, s0, s1, s2);
+        }
         return;
     }
     if (fast_x && fast_y) {
@@ -843,7 +863,7 @@ PM_HD void gather_node(const RecView& V, int I, int J, int R, int n_classes, dou
         int ilo = (I - R > 1) ? I - R : 1, ihi = (I + R < Nx) ? I + R : Nx;
         for (int cls = 0; cls < n_classes; cls++) {
             for (int j = jlo; j <= jhi; j++) {
-                int64_t row = (int64_t)(j - 1 - V.j0 + V.halo) * Nx;
+                int64_t row = (int64_t)(j - 1 - V.j0 + V.halo) * V.pitch;
                 for (int i = ilo; i <= ihi; i++) {
                     int64_t le = row + (i - 1);
                     int32_t cell = V.cell[le];
@@ -880,7 +900,7 @@ PM_HD void gather_node(const RecView& V, int I, int J, int R, int n_classes, dou
             if (er < 0) continue;
             for (int b = 0; b < nc; b++) {
                 int i = cols[b];
-                int64_t le = (int64_t)er * Nx + (i - 1);
+                int64_t le = (int64_t)er * V.pitch + (i - 1);
                 int32_t cell = V.cell[le];
                 if (cell == PH_CELL_INVALID) continue;
                 int32_t fx, fy;

@@ -27,6 +27,7 @@ struct picles_handle {
     cudaEvent_t tev[2] = {nullptr, nullptr};                           /* user stopwatch */
     bool have_grid = false, have_params = false, seeded = false, winds_loaded = false;
     DeviceArrays A;
+    ProjectMaps maps; /* TMA tensor maps of the record planes */
     picles_params_t P;
     DeviceCounters* d_counters = nullptr;
     DeviceCounters* h_counters = nullptr; /* pinned */
@@ -79,6 +80,38 @@ static int dalloc(picles_t* h, T** p, int64_t count) {
         int rc_ = dalloc(h, &(ptr), (count));   \
         if (rc_) return rc_;                    \
     } while (0)
+
+/* ---- TMA tensor maps of the record planes --------------------------------------------
+ * cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime so the
+ * library does not link libcuda.  Planes are 2-D (Nx, ny + 2*halo) with row pitch rp; the box
+ * is the projection tile (PR_BW x PR_BH); out-of-bounds elements are zero-filled. */
+typedef CUresult (*pk_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_project_maps(picles_t* h) {
+    static pk_encode_tiled_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(h, PICLES_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = (pk_encode_tiled_fn)fn;
+    }
+    const DeviceArrays& A = h->A;
+    cuuint64_t dims[2] = {(cuuint64_t)A.Nx, (cuuint64_t)(A.ny + 2 * A.halo)};
+    cuuint32_t box[2] = {PR_BW, PR_BH};
+    cuuint32_t estr[2] = {1, 1};
+    for (int k = 0; k < 6; k++) {
+        bool cell = (k == 5);
+        cuuint64_t stride[1] = {(cuuint64_t)A.rp * (cell ? 4 : 8)};
+        CUresult r = encode(cell ? &h->maps.cell : &h->maps.rec[k], cell ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                            2, cell ? (void*)A.cell : (void*)A.rec[k], dims, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(h, PICLES_ERR_CUDA, "cuTensorMapEncodeTiled(plane %d) failed with CUresult %d", k, (int)r);
+    }
+    CK(project_remesh_configure());
+    return 0;
+}
 
 static void free_grid(picles_t* h) {
     for (void* p : h->allocs) cudaFree(p);
@@ -215,8 +248,9 @@ int picles_set_grid(picles_t* h, int Nx, int Ny, int bx, int by, int j0, int ny_
     free_grid(h);
     DeviceArrays& A = h->A;
     A.Nx = Nx; A.Ny = Ny; A.bx = bx; A.by = by; A.j0 = j0; A.ny = ny_local; A.halo = halo;
+    A.rp = (Nx + REC_PITCH_ALIGN - 1) / REC_PITCH_ALIGN * REC_PITCH_ALIGN;
     int64_t n = (int64_t)Nx * ny_local;
-    int64_t ne = (int64_t)Nx * (ny_local + 2 * halo);
+    int64_t ne = (int64_t)A.rp * (ny_local + 2 * halo);
     for (int k = 0; k < 5; k++) DALLOC(A.z[k], n);
     DALLOC(A.t, n); DALLOC(A.dt, n); DALLOC(A.qold, n);
     DALLOC(A.iter, n);
@@ -242,7 +276,7 @@ int picles_set_grid(picles_t* h, int Nx, int Ny, int bx, int by, int j0, int ny_
     launch_fill_i32(A.cell, ne, -1, h->sms, h->stream);
     for (int k = 0; k < 3; k++) CK(cudaMemsetAsync(A.S[k], 0, (size_t)n * 8, h->stream));
     CK(cudaMemsetAsync(A.flags, 0, (size_t)n, h->stream));
-    h->halo_bytes = (int64_t)halo * Nx * (5 * 8 + 4);
+    h->halo_bytes = (int64_t)halo * A.rp * (5 * 8 + 4);
     if (halo > 0) {
         DALLOC(h->send_lo, h->halo_bytes); DALLOC(h->send_hi, h->halo_bytes);
         DALLOC(h->recv_lo, h->halo_bytes); DALLOC(h->recv_hi, h->halo_bytes);
@@ -252,6 +286,8 @@ int picles_set_grid(picles_t* h, int Nx, int Ny, int bx, int by, int j0, int ny_
     }
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
+    int rc_maps = make_project_maps(h);
+    if (rc_maps) return rc_maps;
     /* |ocean_points| of this strip */
     h->n_active = -1; /* resolved at seed (depends on the model's periodic_boundary) */
     h->have_grid = true;
@@ -396,9 +432,8 @@ int picles_step_project_remesh(picles_t* h, double t, double dt_model) {
     (void)t;
     /* a halo exchange may have run since the advance: ms_project brackets the gather alone */
     CK(cudaEventRecord(h->ev[2], h->stream));
-    launch_project(h->A, h->P.periodic_boundary ? 2 : 1, h->accumulate, h->d_counters, h->sms, h->stream);
+    launch_project_remesh(h->maps, h->A, h->P, dt_model, h->P.periodic_boundary ? 2 : 1, h->accumulate, h->d_counters, h->stream);
     CK(cudaEventRecord(h->ev[3], h->stream));
-    launch_remesh(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream);
     CK(cudaEventRecord(h->ev[4], h->stream));
     CK(cudaGetLastError());
     rc = finish_counters(h);
@@ -424,9 +459,8 @@ int picles_step(picles_t* h, double t, double dt_model, const double* u_t, const
     launch_advance(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream);
     CK(cudaEventRecord(h->ev[1], h->stream));
     CK(cudaEventRecord(h->ev[2], h->stream));
-    launch_project(h->A, h->P.periodic_boundary ? 2 : 1, h->accumulate, h->d_counters, h->sms, h->stream);
+    launch_project_remesh(h->maps, h->A, h->P, dt_model, h->P.periodic_boundary ? 2 : 1, h->accumulate, h->d_counters, h->stream);
     CK(cudaEventRecord(h->ev[3], h->stream));
-    launch_remesh(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream);
     CK(cudaEventRecord(h->ev[4], h->stream));
     CK(cudaGetLastError());
     rc = finish_counters(h);

@@ -2,6 +2,7 @@
 #ifndef PICLES_DEVICE_H
 #define PICLES_DEVICE_H
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -14,8 +15,26 @@
 #ifndef ADV_MIN_BLOCKS
 #define ADV_MIN_BLOCKS 3
 #endif
-#define PRJ_THREADS 256
-#define RMS_THREADS 256
+/* projection gather + remesh: one block per tile of PR_TX x PR_TY target nodes; the record
+   tile (targets + a halo) is staged in shared memory by TMA */
+#define PR_THREADS 256
+#define PR_TX 64
+#define PR_TY 16
+/* halo cells staged around the targets: PR_HY rows (= the largest reach the tiled path
+   serves) and PR_HX columns.  TMA needs the box's first element 16-byte aligned in the
+   inner dimension (measured: profiles/micro/tma_probe.cu — a misaligned start raises
+   "illegal instruction"), so the int32 cell plane forces PR_HX to a multiple of 4. */
+#define PR_HY 2
+#define PR_HX 4
+#define PR_BW (PR_TX + 2 * PR_HX)
+#define PR_BH (PR_TY + 2 * PR_HY)
+#define PR_NODES_PER_THREAD ((PR_TX * PR_TY) / PR_THREADS)
+#ifndef PR_MIN_BLOCKS
+#define PR_MIN_BLOCKS 3
+#endif
+/* row pitch of the record planes: multiple of 4 elements, so int32 rows are 16-byte
+   multiples as TMA tensor maps require */
+#define REC_PITCH_ALIGN 4
 /* largest particle reach (cells) the projection gather supports; == PH_REACH_MAX */
 #define PH_REACH_MAX_ABI 15
 
@@ -23,12 +42,13 @@ namespace picles {
 
 /*
  * All planes are ny*Nx doubles, x fastest, for the rows this strip owns; `rec`/`cell`
- * have (ny + 2*halo)*Nx entries (neighbour rows below and above).
+ * have (ny + 2*halo) rows of pitch rp >= Nx (neighbour rows below and above).
  */
 struct DeviceArrays {
     int Nx, Ny;       /* global shape */
     int bx, by;       /* PICLES_BND_* */
     int j0, ny, halo; /* strip: first global row (0-based), rows owned, halo rows */
+    int rp;           /* row pitch (elements) of the record planes rec[] / cell */
     double* z[5];     /* lne, c̄_x, c̄_y, x, y */
     double *t, *dt, *qold;
     int32_t* iter;
@@ -55,9 +75,15 @@ void launch_seed(const DeviceArrays& A, const picles_params_t& P, const double* 
                  cudaStream_t st);
 void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
                     cudaStream_t st);
-void launch_project(const DeviceArrays& A, int n_classes, int accumulate, const DeviceCounters* dc, int sms, cudaStream_t st);
-void launch_remesh(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
-                   cudaStream_t st);
+/* TMA tensor maps of the six record planes (box PR_BW x PR_BH) */
+struct ProjectMaps {
+    CUtensorMap rec[5];
+    CUtensorMap cell;
+};
+int project_remesh_smem_bytes();
+cudaError_t project_remesh_configure();
+void launch_project_remesh(const ProjectMaps& maps, const DeviceArrays& A, const picles_params_t& P, double DT,
+                           int n_classes, int accumulate, DeviceCounters* dc, cudaStream_t st);
 void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cudaStream_t st);
 void launch_halo_pack(const DeviceArrays& A, char* lo, char* hi, int sms, cudaStream_t st);
 void launch_halo_unpack(const DeviceArrays& A, const char* lo, const char* hi, DeviceCounters* dc, int sms, cudaStream_t st);

@@ -3,15 +3,16 @@
  *
  *   k_seed      SeedParticle for every node                      (run.jl:199-247, core_2D.jl:434-488)
  *   k_advance   advance! : adaptive RK over DT + deposit record  (mapping_2D.jl:118-243)  FP64-bound
- *   k_project   ParticleToNode! as a deterministic gather         (mapping_2D.jl:59-73,
- *                                                                  ParticleInCell.jl:341-538) HBM-bound
- *   k_remesh    remesh!/NodeToParticle!                           (mapping_2D.jl:250-356)  HBM-bound
+ *   k_project_remesh  ParticleToNode! as a deterministic gather   (mapping_2D.jl:59-73,
+ *                     over TMA-staged record tiles, fused with     ParticleInCell.jl:341-538)
+ *                     remesh!/NodeToParticle!                     (mapping_2D.jl:250-356)  HBM-bound
  *   k_energy    sum of State[:,:,1]                               (run.jl:23-25)
  *
  * Layout in HBM (one y-strip per GPU): every per-node quantity is its own plane of
  * ny*Nx doubles with i (x) fastest — the memory order of the reference's column-major
  * (Nx,Ny[,3]) arrays — so a warp touches 32 consecutive doubles (256 B) per plane.
- * Deposit records carry `halo` extra rows on both sides for the neighbour strips.
+ * Deposit records carry `halo` extra rows on both sides for the neighbour strips and a
+ * row pitch rounded up to 4 elements (16-byte rows for the TMA tensor maps).
  *
  * Compiled with --fmad=false: physics.h spells out every fused multiply-add so the
  * results are bit-identical to the CPU oracle.
@@ -86,6 +87,13 @@ __device__ __forceinline__ void store_record(const DeviceArrays& A, int64_t le, 
     A.cell[le] = r.cell;
 }
 
+/* index of node l (= jr*Nx + i) in the record planes */
+__device__ __forceinline__ int64_t rec_index(const DeviceArrays& A, int64_t l) {
+    if (A.rp == A.Nx) return l + (int64_t)A.halo * A.Nx;
+    int64_t jr = l / A.Nx;
+    return (jr + A.halo) * A.rp + (l - jr * A.Nx);
+}
+
 /* ---- seed ------------------------------------------------------------------ */
 __global__ void __launch_bounds__(256) k_seed(DeviceArrays A, picles_params_t P, const double* __restrict__ u0,
                                               const double* __restrict__ v0) {
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(256) k_seed(DeviceArrays A, picles_params_t P,
         Record r;
         r.e = r.mx = r.my = r.wxc = r.wyc = 0.0;
         r.cell = PH_CELL_INVALID;
-        store_record(A, l + (int64_t)A.halo * A.Nx, r);
+        store_record(A, rec_index(A, l), r);
     }
 }
 
@@ -123,9 +131,9 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc) {
     tally_zero(c);
     int64_t n = (int64_t)A.Nx * A.ny;
     for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x) {
-        int64_t le = l + (int64_t)A.halo * A.Nx;
         uint8_t flags = A.flags[l];
         if (!(flags & PICLES_PF_ACTIVE)) continue; /* record stays invalid (set at seed) */
+        int64_t le = rec_index(A, l);
         Particle p;
         load_particle(A, l, p);
         double M[4];
@@ -140,69 +148,213 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc) {
     tally_flush(c, dc);
 }
 
-/* ---- projection gather --------------------------------------------------------- */
+/* ---- projection gather + remesh ---------------------------------------------------- */
 /*
- * One thread per target node; the per-target arithmetic (fast interior path and the
- * generic wrap/fold path) is gather_node() in physics.h so the CPU tests can run the
- * very same code.  Neighbouring threads read overlapping record windows, which L1/L2
- * serve; HBM sees each record once.
+ * One block per tile of PR_TX x PR_TY target nodes.  One thread arms an mbarrier and issues
+ * six TMA tile loads (cp.async.bulk.tensor.2d): the five record planes and the cell plane
+ * over the targets plus a halo of PR_HX x PR_HY cells.  Boxes that stick out of the planes are
+ * zero-filled by the TMA unit; a zero cell decodes to an offset that never matches, i.e.
+ * "no deposit", which is exactly what lies beyond a non-periodic edge.  While the tiles are in
+ * flight every thread loads the remesh inputs of its PR_NODES_PER_THREAD nodes (flags, wind at
+ * t), so the node loop below touches HBM only to store.
+ *
+ * Per node: sum the window from shared memory (gather_window, compile-time offsets) in the
+ * reference's order, store State, and — the node value still being in registers — run
+ * NodeToParticle! for the node's particle.  Nodes whose window crosses a periodic seam or the
+ * tripolar fold, and steps whose reach exceeds PR_HY, take gather_node() on the planes in HBM.
  */
-__global__ void __launch_bounds__(PRJ_THREADS) k_project(DeviceArrays A, int n_classes, int accumulate, const DeviceCounters* __restrict__ dc) {
-    RecView V;
-    V.Nx = A.Nx; V.Ny = A.Ny; V.bx = A.bx; V.by = A.by; V.j0 = A.j0; V.ny = A.ny; V.halo = A.halo;
-    V.e = A.rec[0]; V.mx = A.rec[1]; V.my = A.rec[2]; V.wx = A.rec[3]; V.wy = A.rec[4];
-    V.cell = A.cell;
+/* GetVariablesAtVertex with results in registers (hot: remesh branch A) */
+struct Vtx3 { double u0, u1, u2; };
+__device__ __noinline__ Vtx3 vertex_values_cold(double e, double mx, double my) {
+    Particle p;
+    vertex_t<OpsSafe>(e, mx, my, p, (unsigned*)0);
+    Vtx3 r = {p.u0, p.u1, p.u2};
+    return r;
+}
+__device__ __forceinline__ void vertex_values(double e, double mx, double my, double& u0, double& u1, double& u2) {
+#if defined(__CUDA_ARCH__)
+    unsigned bad = 0;
+    double m_amp = OpsFast::sqrtz(mx * mx + my * my, &bad);
+    double den = 2.0 * (m_amp * m_amp);
+    u0 = OpsFast::log_(e, &bad);
+    u1 = OpsFast::divz(mx * e, den, &bad);
+    u2 = OpsFast::divz(my * e, den, &bad);
+    if (bad) {
+        Vtx3 r = vertex_values_cold(e, mx, my);
+        u0 = r.u0; u1 = r.u1; u2 = r.u2;
+    }
+#endif
+}
+
+struct PRTile {
+    double rec[5][PR_BH * PR_BW];
+    int32_t cell[PR_BH * PR_BW];
+    unsigned long long mbar;
+};
+static_assert(PR_NODES_PER_THREAD <= 4, "flags of a thread's nodes are packed in 32 bits");
+static_assert((PR_BH * PR_BW * 8) % 128 == 0 && (PR_BW * 4) % 16 == 0 && PR_HX % 4 == 0 && PR_TX % 4 == 0 && PR_HX >= PR_HY,
+              "TMA tile alignment");
+#define PR_TILE_BYTES (5 * PR_BH * PR_BW * 8 + PR_BH * PR_BW * 4)
+
+/*
+ * Everything of the node loop that is not "reach-1 window from the tile, then remesh branch A"
+ * is deferred to this out-of-line pass, so the hot loop contains no call and keeps its state
+ * in registers.  `mask` bit k: node k still needs its gather (window crossing a periodic seam
+ * or the tripolar fold, reach > 1, two deposit classes, untiled step); bit 4+k: node k was
+ * gathered but its remesh is not branch A (wind-sea reseed or switch-off).  Returns the remesh
+ * branch counts (A, B, C, D) of the nodes handled here.
+ */
+__device__ __noinline__ int4 cold_nodes(const DeviceArrays* Ap, const picles_params_t* Pp, const PRTile* Tp, uint32_t mask,
+                                        uint32_t fl_all, int i, int jr0, int tx, int ty, int R, int n_classes, int accumulate,
+                                        bool tiled, double DT) {
+    const DeviceArrays& A = *Ap;
+    const picles_params_t& P = *Pp;
+    const PRTile& T = *Tp;
+    Tally c;
+    tally_zero(c);
+    for (int k = 0; k < PR_NODES_PER_THREAD; k++) {
+        if (!(mask & (0x11u << k))) continue;
+        const int jl = ty + k * (PR_THREADS / PR_TX);
+        const int jr = jr0 + jl;
+        const int I = i + 1, J = jr + 1 + A.j0;
+        const int64_t l = (int64_t)jr * A.Nx + i;
+        const uint8_t flags = (uint8_t)(fl_all >> (8 * k));
+        double s0, s1, s2;
+        if (mask & (1u << k)) {
+            s0 = s1 = s2 = 0.0;
+            if (accumulate) { s0 = A.S[0][l]; s1 = A.S[1][l]; s2 = A.S[2][l]; }
+            const bool fast_x = (A.bx == PICLES_BND_NONPERIODIC) || (I > R && I <= A.Nx - R);
+            const bool fast_y = (A.by == PICLES_BND_NONPERIODIC) || (A.by == PICLES_BND_PERIODIC && J > R && J <= A.Ny - R) ||
+                                (A.by == PICLES_BND_TRIPOLAR_NORTH && J <= A.Ny - R);
+            if (tiled && fast_x && fast_y) {
+                const int64_t base = (int64_t)(jl + PR_HY) * PR_BW + (tx + PR_HX);
+                if (n_classes == 1) gather_window<2, PR_BW, 1>(T.rec[0], T.rec[1], T.rec[2], T.rec[3], T.rec[4], T.cell, PR_BW, base, s0, s1, s2);
+                else if (R <= 1) gather_window<1, PR_BW, 2>(T.rec[0], T.rec[1], T.rec[2], T.rec[3], T.rec[4], T.cell, PR_BW, base, s0, s1, s2);
+                else gather_window<2, PR_BW, 2>(T.rec[0], T.rec[1], T.rec[2], T.rec[3], T.rec[4], T.cell, PR_BW, base, s0, s1, s2);
+            } else {
+                RecView V;
+                V.Nx = A.Nx; V.Ny = A.Ny; V.bx = A.bx; V.by = A.by; V.j0 = A.j0; V.ny = A.ny; V.halo = A.halo; V.pitch = A.rp;
+                V.e = A.rec[0]; V.mx = A.rec[1]; V.my = A.rec[2]; V.wx = A.rec[3]; V.wy = A.rec[4];
+                V.cell = A.cell;
+                gather_node(V, I, J, R, n_classes, s0, s1, s2);
+            }
+            A.S[0][l] = s0; A.S[1][l] = s1; A.S[2][l] = s2;
+        } else {
+            s0 = A.S[0][l]; s1 = A.S[1][l]; s2 = A.S[2][l];
+        }
+        if (!(flags & PICLES_PF_ACTIVE)) continue;
+        const double wu = A.u_t[l], wv = A.v_t[l];
+        Particle p;
+        load_particle(A, l, p);
+        remesh_particle(P, p, s0, s1, s2, wu, wv, DT, c);
+        store_particle(A, l, p);
+    }
+    return make_int4(c.A, c.B, c.C, c.D);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* mbar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :
+                 : "r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(smem_u32(mbar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(PR_THREADS, PR_MIN_BLOCKS)
+k_project_remesh(const __grid_constant__ ProjectMaps maps, const __grid_constant__ DeviceArrays A,
+                 const __grid_constant__ picles_params_t P, double DT, int n_classes,
+                 int accumulate, DeviceCounters* dc) {
+    extern __shared__ __align__(128) unsigned char pr_smem[];
+    /* TMA destinations must be 128-byte aligned whatever static shared memory precedes them */
+    PRTile& T = *reinterpret_cast<PRTile*>(pr_smem + ((128u - (smem_u32(pr_smem) & 127u)) & 127u));
+    const int i0 = blockIdx.x * PR_TX, jr0 = blockIdx.y * PR_TY;
     /* deposits landing on this strip come from its own particles (reach) and from the
        neighbours' rows received into the halo (reach_halo) */
     int R = min(max(dc->reach, dc->reach_halo), PH_REACH_MAX);
     if (A.ny != A.Ny) R = min(R, A.halo); /* strips: the host rejects reach > halo (PICLES_ERR_HALO) */
-    /* 2-D launch: blockIdx.y strides rows, threads run along x (no integer division) */
-    for (int jr = blockIdx.y; jr < A.ny; jr += gridDim.y) {
-        const int J = jr + 1 + A.j0; /* global 1-based target row */
-        for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < A.Nx; i0 += gridDim.x * blockDim.x) {
-            const int I = i0 + 1;
-            const int64_t l = (int64_t)jr * A.Nx + i0;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-            if (accumulate) { s0 = A.S[0][l]; s1 = A.S[1][l]; s2 = A.S[2][l]; }
-            gather_node(V, I, J, R, n_classes, s0, s1, s2);
-            A.S[0][l] = s0;
-            A.S[1][l] = s1;
-            A.S[2][l] = s2;
+    const bool tiled = (R <= PR_HY);
+    if (tiled) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&T.mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&T.mbar)), "r"(PR_TILE_BYTES)
+                         : "memory");
+            const int c0 = i0 - PR_HX, c1 = jr0 + A.halo - PR_HY;
+#pragma unroll
+            for (int k = 0; k < 5; k++) tma_load_2d(T.rec[k], &maps.rec[k], c0, c1, &T.mbar);
+            tma_load_2d(T.cell, &maps.cell, c0, c1, &T.mbar);
         }
     }
-}
-
-/* ---- remesh -------------------------------------------------------------------- */
-__global__ void __launch_bounds__(RMS_THREADS) k_remesh(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc) {
-    Tally c;
-    tally_zero(c);
-    int64_t n = (int64_t)A.Nx * A.ny;
-    for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x) {
-        uint8_t flags = A.flags[l];
+    /* the flags of my nodes, issued while the tiles are in flight (branch A of the remesh
+       needs nothing else; the wind is only read on the rare reseed / switch-off branches) */
+    const int tx = threadIdx.x & (PR_TX - 1), ty = threadIdx.x / PR_TX;
+    const int i = i0 + tx;
+    uint32_t fl_all = 0;
+#pragma unroll
+    for (int k = 0; k < PR_NODES_PER_THREAD; k++) {
+        const int jr = jr0 + ty + k * (PR_THREADS / PR_TX);
+        if (i < A.Nx && jr < A.ny) fl_all |= (uint32_t)A.flags[(int64_t)jr * A.Nx + i] << (8 * k);
+    }
+    if (tiled) {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done)
+                         : "r"(smem_u32(&T.mbar))
+                         : "memory");
+        }
+    }
+    int nA = 0; /* remesh branch-A count of this thread */
+    uint32_t cold = 0; /* nodes deferred to cold_nodes() */
+    const bool hot_window = tiled && (n_classes == 1) && (R <= 1);
+#pragma unroll 1
+    for (int k = 0; k < PR_NODES_PER_THREAD; k++) {
+        const int jl = ty + k * (PR_THREADS / PR_TX); /* row inside the tile */
+        const int jr = jr0 + jl;
+        if (i >= A.Nx || jr >= A.ny) continue;
+        const int I = i + 1, J = jr + 1 + A.j0; /* global 1-based node */
+        const bool fast_x = (A.bx == PICLES_BND_NONPERIODIC) || (I > R && I <= A.Nx - R);
+        const bool fast_y = (A.by == PICLES_BND_NONPERIODIC) || (A.by == PICLES_BND_PERIODIC && J > R && J <= A.Ny - R) ||
+                            (A.by == PICLES_BND_TRIPOLAR_NORTH && J <= A.Ny - R);
+        if (!(hot_window && fast_x && fast_y)) { cold |= 1u << k; continue; }
+        const int64_t l = (int64_t)jr * A.Nx + i;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        if (accumulate) { s0 = A.S[0][l]; s1 = A.S[1][l]; s2 = A.S[2][l]; }
+        const int64_t base = (int64_t)(jl + PR_HY) * PR_BW + (tx + PR_HX);
+        gather_window<1, PR_BW, 1>(T.rec[0], T.rec[1], T.rec[2], T.rec[3], T.rec[4], T.cell, PR_BW, base, s0, s1, s2);
+        A.S[0][l] = s0;
+        A.S[1][l] = s1;
+        A.S[2][l] = s2;
+        /* ---- remesh! for the particle whose home is this node ---- */
+        const uint32_t flags = (fl_all >> (8 * k)) & 0xffu;
         if (!(flags & PICLES_PF_ACTIVE)) continue;
-        double e = A.S[0][l], mx = A.S[1][l], my = A.S[2][l];
-        double wu = A.u_t[l], wv = A.v_t[l];
-        bool boundary = (flags & PICLES_PF_BOUNDARY) != 0;
-        bool enough = (e >= P.minimal_state[0]) && (mx * mx + my * my >= P.minimal_state[1]);
-        bool windy = (wu * wu + wv * wv >= P.wind_min_squared);
-        Particle p;
-        if (!boundary && enough) {
-            /* branch A touches only u, flags: skip the loads it does not need */
-            p.flags = flags; p.status = 0; p.iter = 0; p.qold = 0.0; p.t = 0.0; p.dt = 0.0;
-            remesh_particle(P, p, e, mx, my, wu, wv, DT, c);
-            A.z[0][l] = p.u0; A.z[1][l] = p.u1; A.z[2][l] = p.u2; A.z[3][l] = p.u3; A.z[4][l] = p.u4;
-            A.flags[l] = p.flags;
-        } else if (windy) {
-            load_particle(A, l, p);
-            remesh_particle(P, p, e, mx, my, wu, wv, DT, c);
-            store_particle(A, l, p);
-        } else {
-            p.flags = flags;
-            remesh_particle(P, p, e, mx, my, wu, wv, DT, c);
-            if (p.flags != flags) A.flags[l] = p.flags;
-        }
+        const bool enough = (s0 >= P.minimal_state[0]) && (s1 * s1 + s2 * s2 >= P.minimal_state[1]);
+        if ((flags & PICLES_PF_BOUNDARY) || !enough) { cold |= 16u << k; continue; }
+        /* branch A: GetVariablesAtVertex; touches only u and flags */
+        double u0, u1, u2;
+        vertex_values(s0, s1, s2, u0, u1, u2);
+        uint32_t nf = flags | PICLES_PF_DT_RESET;
+        if (P.on_persist) nf |= PICLES_PF_ON;
+        nA++;
+        A.z[0][l] = u0; A.z[1][l] = u1; A.z[2][l] = u2; A.z[3][l] = 0.0; A.z[4][l] = 0.0;
+        if (nf != flags) A.flags[l] = (uint8_t)nf;
     }
-    tally_flush(c, dc);
+    int nB = 0, nC = 0, nD = 0;
+    if (cold) {
+        int4 cc = cold_nodes(&A, &P, &T, cold, fl_all, i, jr0, tx, ty, R, n_classes, accumulate, tiled, DT);
+        nA += cc.x; nB = cc.y; nC = cc.z; nD = cc.w;
+    }
+    /* branch counts: one warp reduction each, one global atomic per warp and non-zero count */
+    nA = warp_sum(nA); nB = warp_sum(nB); nC = warp_sum(nC); nD = warp_sum(nD);
+    if ((threadIdx.x & 31) == 0) {
+        if (nA) atomicAdd(&dc->sums[8], (unsigned long long)nA);
+        if (nB) atomicAdd(&dc->sums[9], (unsigned long long)nB);
+        if (nC) atomicAdd(&dc->sums[10], (unsigned long long)nC);
+        if (nD) atomicAdd(&dc->sums[11], (unsigned long long)nD);
+    }
 }
 
 /* ---- energy sum (deterministic two-stage) ---------------------------------------- */
@@ -221,10 +373,10 @@ __global__ void __launch_bounds__(256) k_energy(const double* __restrict__ e, in
 
 /* ---- halo pack / unpack: H rows of the 5 record planes + cell plane -------------- */
 __global__ void k_halo_pack(DeviceArrays A, char* __restrict__ send_lo, char* __restrict__ send_hi) {
-    int64_t m = (int64_t)A.halo * A.Nx;
+    int64_t m = (int64_t)A.halo * A.rp;
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < m; q += (int64_t)gridDim.x * blockDim.x) {
-        int64_t lo = (int64_t)A.halo * A.Nx + q;                 /* first owned rows */
-        int64_t hi = (int64_t)A.ny * A.Nx + q;                   /* last owned rows (ext index = ny+halo-halo) */
+        int64_t lo = (int64_t)A.halo * A.rp + q;                 /* first owned rows */
+        int64_t hi = (int64_t)A.ny * A.rp + q;                   /* last owned rows (ext index = ny+halo-halo) */
 #pragma unroll
         for (int k = 0; k < 5; k++) {
             ((double*)send_lo)[k * m + q] = A.rec[k][lo];
@@ -236,11 +388,11 @@ __global__ void k_halo_pack(DeviceArrays A, char* __restrict__ send_lo, char* __
 }
 __global__ void k_halo_unpack(DeviceArrays A, const char* __restrict__ recv_lo, const char* __restrict__ recv_hi,
                               DeviceCounters* dc) {
-    int64_t m = (int64_t)A.halo * A.Nx;
+    int64_t m = (int64_t)A.halo * A.rp;
     int32_t reach = 0;
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < m; q += (int64_t)gridDim.x * blockDim.x) {
         int64_t lo = q;                                           /* lower halo rows */
-        int64_t hi = (int64_t)(A.ny + A.halo) * A.Nx + q;         /* upper halo rows */
+        int64_t hi = (int64_t)(A.ny + A.halo) * A.rp + q;         /* upper halo rows */
 #pragma unroll
         for (int k = 0; k < 5; k++) {
             A.rec[k][lo] = ((const double*)recv_lo)[k * m + q];
@@ -348,17 +500,14 @@ void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, 
     else k_advance<false><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc);
 }
 
-void launch_project(const DeviceArrays& A, int n_classes, int accumulate, const DeviceCounters* dc, int sms, cudaStream_t st) {
-    int gx = (A.Nx + PRJ_THREADS - 1) / PRJ_THREADS;
-    int gy = A.ny < 65535 ? A.ny : 65535;
-    (void)sms;
-    k_project<<<dim3(gx, gy), PRJ_THREADS, 0, st>>>(A, n_classes, accumulate, dc);
+int project_remesh_smem_bytes() { return (int)sizeof(PRTile) + 128; }
+cudaError_t project_remesh_configure() {
+    return cudaFuncSetAttribute(k_project_remesh, cudaFuncAttributeMaxDynamicSharedMemorySize, project_remesh_smem_bytes());
 }
-
-void launch_remesh(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
-                   cudaStream_t st) {
-    int64_t n = (int64_t)A.Nx * A.ny;
-    k_remesh<<<grid_for(n, RMS_THREADS, sms, 8), RMS_THREADS, 0, st>>>(A, P, DT, dc);
+void launch_project_remesh(const ProjectMaps& maps, const DeviceArrays& A, const picles_params_t& P, double DT,
+                           int n_classes, int accumulate, DeviceCounters* dc, cudaStream_t st) {
+    dim3 grid((A.Nx + PR_TX - 1) / PR_TX, (A.ny + PR_TY - 1) / PR_TY);
+    k_project_remesh<<<grid, PR_THREADS, project_remesh_smem_bytes(), st>>>(maps, A, P, DT, n_classes, accumulate, dc);
 }
 
 void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cudaStream_t st) {
@@ -366,11 +515,11 @@ void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cud
 }
 
 void launch_halo_pack(const DeviceArrays& A, char* lo, char* hi, int sms, cudaStream_t st) {
-    int64_t m = (int64_t)A.halo * A.Nx;
+    int64_t m = (int64_t)A.halo * A.rp;
     if (m > 0) k_halo_pack<<<grid_for(m, 256, sms, 4), 256, 0, st>>>(A, lo, hi);
 }
 void launch_halo_unpack(const DeviceArrays& A, const char* lo, const char* hi, DeviceCounters* dc, int sms, cudaStream_t st) {
-    int64_t m = (int64_t)A.halo * A.Nx;
+    int64_t m = (int64_t)A.halo * A.rp;
     if (m > 0) k_halo_unpack<<<grid_for(m, 256, sms, 4), 256, 0, st>>>(A, lo, hi, dc);
 }
 void launch_fill_i32(int32_t* p, int64_t n, int32_t v, int sms, cudaStream_t st) {

@@ -130,7 +130,7 @@ static void shim_project_remesh_all(Shim* h, double DT, int R, const double* u_t
     const int Nx = h->Nx;
     for (auto& s : h->s) {
         RecView V;
-        V.Nx = Nx; V.Ny = h->Ny; V.bx = h->bx; V.by = h->by; V.j0 = s.j0; V.ny = s.ny; V.halo = s.halo;
+        V.Nx = Nx; V.Ny = h->Ny; V.bx = h->bx; V.by = h->by; V.j0 = s.j0; V.ny = s.ny; V.halo = s.halo; V.pitch = Nx;
         V.e = s.rec[0].data(); V.mx = s.rec[1].data(); V.my = s.rec[2].data(); V.wx = s.rec[3].data(); V.wy = s.rec[4].data();
         V.cell = s.cell.data();
         int64_t n = (int64_t)Nx * s.ny, off = local_winds ? 0 : (int64_t)s.j0 * Nx;
