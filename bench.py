@@ -31,6 +31,11 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the 4096^2 bench step, from the
+# committed ncu --set full captures (profiles/r01_ncu_*.txt); never measured under the timer
+NCU_TRAFFIC = {"k_advance": 3.62e9, "k_project_remesh": 1.80e9}
+NCU_FP64_PIPE_PCT = 56.3  # sm__pipe_fp64_cycles_active of k_advance (profiles/r01_ncu_advance.txt)
+
 METRIC = "particle-steps/s"
 UNIT = "particle-steps/s"
 
@@ -41,9 +46,10 @@ F_RHS = 331          # one right-hand side (rhs3 + prop + wind interpolation)
 F_ATTEMPT = 511      # one RK attempt minus its 6 RHS: stage sums, error norm, PI controller
 F_INITDT = 319       # Hairer initial step minus its RHS
 F_DEPOSIT = 105      # charge + weights of the deposit record
-# Algorithmic HBM bytes per node
-B_PROJECT = 44 + 24  # read one record (5 f64 + packed cell), write 3 f64 of State
-B_REMESH = 24 + 16 + 1 + 40 + 1  # read State, wind(t), flags; write u[5], flags (branch A)
+# Algorithmic HBM bytes per node of the fused gather + remesh kernel: read one
+# deposit record (5 f64 + packed cell) and the particle flags; write 3 f64 of State, the
+# particle's u[5] and its flags (remesh branch A, the steady state of an all-ocean box)
+B_PROJECT_REMESH = 44 + 1 + 24 + 40 + 1
 
 
 def log(*a):
@@ -314,30 +320,27 @@ def main():
     # ---- rooflines from the live CUDA-event times of the timed region ------------------
     ms_adv = float(np.mean([c["ms_advance"] for c in per_step]))
     ms_prj = float(np.mean([c["ms_project"] for c in per_step]))
-    ms_rms = float(np.mean([c["ms_remesh"] for c in per_step]))
+    std_size = (args.nx, args.ny) == (4096, 4096)  # the size the committed ncu captures were taken at
     rhs = float(np.mean([c["n_rhs"] for c in per_step]))
     att = float(np.mean([c["n_substeps"] + c["n_rejects"] for c in per_step]))
     integ = float(np.mean([c["n_integrated"] for c in per_step]))
     dep = float(np.mean([c["n_deposited"] for c in per_step]))
-    act = float(np.mean([c["n_active"] for c in per_step]))
     flops = rhs * F_RHS + att * F_ATTEMPT + integ * F_INITDT + dep * F_DEPOSIT
     adv_tf = flops / (ms_adv * 1e-3) / 1e12
-    prj_gbs = n_nodes * B_PROJECT / (ms_prj * 1e-3) / 1e9
-    rms_gbs = act * B_REMESH / (ms_rms * 1e-3) / 1e9
-    roofline = {"kernel": "k_advance<Tsit5Tab,false>", "bound": "fp64", "achieved": adv_tf, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": adv_tf / fp64_peak, "traffic": None,
+    prj_gbs = n_nodes * B_PROJECT_REMESH / (ms_prj * 1e-3) / 1e9
+    roofline = {"kernel": "k_advance", "bound": "fp64", "achieved": adv_tf, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": adv_tf / fp64_peak, "traffic": NCU_TRAFFIC.get("k_advance") if std_size else None,
                 "peak_source": "DFMA-chain microbenchmark run in this process (picles_measure_fp64_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "flop_model": {"F_RHS": F_RHS, "F_ATTEMPT": F_ATTEMPT, "F_INITDT": F_INITDT, "F_DEPOSIT": F_DEPOSIT,
                                "rhs_per_launch": rhs, "attempts_per_launch": att},
-                "ms_per_launch": ms_adv, "share_of_step": ms_adv / (ms_adv + ms_prj + ms_rms)}
+                "ncu_fp64_pipe_active_pct": NCU_FP64_PIPE_PCT,
+                "ms_per_launch": ms_adv, "share_of_step": ms_adv / (ms_adv + ms_prj)}
     roofline_hbm = [
-        {"kernel": "k_project", "bound": "hbm", "achieved": prj_gbs, "peak": hbm_peak, "unit": "GB/s",
-         "frac": prj_gbs / hbm_peak, "traffic": None, "bytes_per_node": B_PROJECT, "ms_per_launch": ms_prj,
-         "peak_source": hbm_src},
-        {"kernel": "k_remesh", "bound": "hbm", "achieved": rms_gbs, "peak": hbm_peak, "unit": "GB/s",
-         "frac": rms_gbs / hbm_peak, "traffic": None, "bytes_per_node": B_REMESH, "ms_per_launch": ms_rms,
-         "peak_source": hbm_src},
+        {"kernel": "k_project_remesh", "bound": "hbm", "achieved": prj_gbs, "peak": hbm_peak, "unit": "GB/s",
+         "frac": prj_gbs / hbm_peak, "traffic": NCU_TRAFFIC.get("k_project_remesh") if std_size else None,
+         "bytes_per_node": B_PROJECT_REMESH, "nodes_per_launch": n_nodes, "ms_per_launch": ms_prj,
+         "share_of_step": ms_prj / (ms_adv + ms_prj), "peak_source": hbm_src},
     ]
 
     value = n_active_all / (ms_total * 1e-3)
@@ -346,7 +349,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "roofline": roofline, "roofline_hbm": roofline_hbm,
             "measured_here": {"fp64_dfma_tflops": fp64_peak, "hbm_copy_gbs": hbm_meas},
-            "clocks": clocks, "gpu_launches": (3 if world == 1 else 5) * args.steps,
+            "clocks": clocks, "gpu_launches": (2 if world == 1 else 4) * args.steps,
             "substeps_per_particle_step": float(np.mean([c["n_substeps"] / max(c["n_integrated"], 1) for c in per_step])),
             "max_attempts": int(max(c["max_attempts"] for c in per_step)),
             "rejects": int(sum(c["n_rejects"] for c in per_step)),

@@ -18,11 +18,17 @@
 using namespace picles;
 
 #define ENERGY_BLOCKS 1024
+/* host winds are uploaded in this many row chunks, each chunk's advance starting as soon as
+   its rows have landed (copy stream + events), when the strip is large enough to matter */
+#define PIPE_CHUNKS 8
+#define PIPE_MIN_NODES (1 << 20)
 
 struct picles_handle {
     int device = -1;
     int sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;           /* wind upload pipelined against the advance */
+    cudaEvent_t pev[PIPE_CHUNKS + 1] = {};         /* chunk landed / compute stream idle */
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; /* adv0, adv1, prj0, prj1=rms0, rms1 */
     cudaEvent_t tev[2] = {nullptr, nullptr};                           /* user stopwatch */
     bool have_grid = false, have_params = false, seeded = false, winds_loaded = false;
@@ -204,6 +210,8 @@ int picles_create(picles_t** out, int device_id) {
     memset(&h->last, 0, sizeof h->last);
     CK(cudaSetDevice(device_id));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k <= PIPE_CHUNKS; k++) CK(cudaEventCreateWithFlags(&h->pev[k], cudaEventDisableTiming));
     for (int k = 0; k < 5; k++) CK(cudaEventCreate(&h->ev[k]));
     for (int k = 0; k < 2; k++) CK(cudaEventCreate(&h->tev[k]));
     CK(cudaMalloc((void**)&h->d_counters, sizeof(DeviceCounters)));
@@ -228,6 +236,9 @@ int picles_destroy(picles_t* h) {
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     for (int k = 0; k < 2; k++)
         if (h->tev[k]) cudaEventDestroy(h->tev[k]);
+    for (int k = 0; k <= PIPE_CHUNKS; k++)
+        if (h->pev[k]) cudaEventDestroy(h->pev[k]);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return PICLES_OK;
@@ -364,7 +375,56 @@ int picles_step_advance(picles_t* h, double t, double dt_model) {
     if (!(dt_model > 0)) return fail(h, PICLES_ERR_ARG, "dt_model must be positive");
     CK(cudaMemsetAsync(h->d_counters, 0, sizeof(DeviceCounters), h->stream));
     CK(cudaEventRecord(h->ev[0], h->stream));
-    launch_advance(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream);
+    launch_advance(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream, 0, (int64_t)h->A.Nx * h->A.ny);
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaGetLastError());
+    h->timing_valid = false;
+    return PICLES_OK;
+}
+
+/* upload the host winds and advance, pipelined: the strip is cut in PIPE_CHUNKS row blocks;
+   block c's rows are copied on the copy stream while block c-1 integrates.  Same wind-level
+   semantics as picles_upload_winds + picles_step_advance. */
+static int upload_and_advance(picles_t* h, double dt_model, const double* u_t, const double* v_t, const double* u_t1,
+                              const double* v_t1) {
+    DeviceArrays& A = h->A;
+    const int64_t n = (int64_t)A.Nx * A.ny;
+    if ((!u_t && !u_t1) || n < PIPE_MIN_NODES) {
+        int rc = picles_upload_winds(h, u_t, v_t, u_t1, v_t1);
+        if (rc) return rc;
+        return picles_step_advance(h, 0.0, dt_model);
+    }
+    if ((u_t == nullptr) != (v_t == nullptr) || (u_t1 == nullptr) != (v_t1 == nullptr))
+        return fail(h, PICLES_ERR_ARG, "wind components must be given in pairs");
+    if (!(dt_model > 0)) return fail(h, PICLES_ERR_ARG, "dt_model must be positive");
+    if (!u_t) { /* the previous step's t+DT level is this step's t level: swap, no copy */
+        double* tu = A.u_t; A.u_t = A.u_t1; A.u_t1 = tu;
+        double* tv = A.v_t; A.v_t = A.v_t1; A.v_t1 = tv;
+    }
+    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(DeviceCounters), h->stream));
+    /* the copy stream may only overwrite the wind planes once the compute stream is past
+       every earlier kernel that read them */
+    CK(cudaEventRecord(h->pev[PIPE_CHUNKS], h->stream));
+    CK(cudaStreamWaitEvent(h->copy_stream, h->pev[PIPE_CHUNKS], 0));
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    const int rows = (A.ny + PIPE_CHUNKS - 1) / PIPE_CHUNKS;
+    for (int c = 0; c < PIPE_CHUNKS; c++) {
+        const int r0 = c * rows, r1 = (r0 + rows < A.ny) ? r0 + rows : A.ny;
+        if (r0 >= r1) break;
+        const int64_t off = (int64_t)r0 * A.Nx;
+        const size_t bytes = (size_t)(r1 - r0) * A.Nx * 8;
+        if (u_t) {
+            CK(cudaMemcpyAsync(A.u_t + off, u_t + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+            CK(cudaMemcpyAsync(A.v_t + off, v_t + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        }
+        if (u_t1) {
+            CK(cudaMemcpyAsync(A.u_t1 + off, u_t1 + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+            CK(cudaMemcpyAsync(A.v_t1 + off, v_t1 + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        }
+        CK(cudaEventRecord(h->pev[c], h->copy_stream));
+        CK(cudaStreamWaitEvent(h->stream, h->pev[c], 0));
+        launch_advance(A, h->P, dt_model, h->d_counters, h->sms, h->stream, off, off + (int64_t)(r1 - r0) * A.Nx);
+    }
     CK(cudaEventRecord(h->ev[1], h->stream));
     CK(cudaGetLastError());
     h->timing_valid = false;
@@ -451,13 +511,8 @@ int picles_step(picles_t* h, double t, double dt_model, const double* u_t, const
     if (rc) return rc;
     if (h->A.ny != h->A.Ny)
         return fail(h, PICLES_ERR_STATE, "picles_step needs a single-strip handle; use the phase-split calls for strips");
-    rc = picles_upload_winds(h, u_t, v_t, u_t1, v_t1);
+    rc = upload_and_advance(h, dt_model, u_t, v_t, u_t1, v_t1);
     if (rc) return rc;
-    /* advance timing must not include the H2D copies queued above */
-    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(DeviceCounters), h->stream));
-    CK(cudaEventRecord(h->ev[0], h->stream));
-    launch_advance(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream);
-    CK(cudaEventRecord(h->ev[1], h->stream));
     CK(cudaEventRecord(h->ev[2], h->stream));
     launch_project_remesh(h->maps, h->A, h->P, dt_model, h->P.periodic_boundary ? 2 : 1, h->accumulate, h->d_counters, h->stream);
     CK(cudaEventRecord(h->ev[3], h->stream));
@@ -738,9 +793,9 @@ int picles_halo_exchange(picles_t* h, int lo_rank, int hi_rank) {
    gather, remesh; one host synchronisation at the end (the counters) */
 int picles_step_strip(picles_t* h, double t, double dt_model, const double* u_t, const double* v_t, const double* u_t1,
                       const double* v_t1, int lo_rank, int hi_rank) {
-    int rc = picles_upload_winds(h, u_t, v_t, u_t1, v_t1);
+    int rc = need_ready(h, true);
     if (rc) return rc;
-    rc = picles_step_advance(h, t, dt_model);
+    rc = upload_and_advance(h, dt_model, u_t, v_t, u_t1, v_t1);
     if (rc) return rc;
     rc = picles_halo_exchange(h, lo_rank, hi_rank);
     if (rc) return rc;

@@ -74,7 +74,7 @@ struct DeviceCounters {
 void launch_seed(const DeviceArrays& A, const picles_params_t& P, const double* u0, const double* v0, int sms,
                  cudaStream_t st);
 void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
-                    cudaStream_t st);
+                    cudaStream_t st, int64_t l_begin, int64_t l_end);
 /* TMA tensor maps of the six record planes (box PR_BW x PR_BH) */
 struct ProjectMaps {
     CUtensorMap rec[5];

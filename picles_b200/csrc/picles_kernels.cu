@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) k_seed(DeviceArrays A, picles_params_t P,
  */
 template <bool PER_NODE_M>
 __global__ void __launch_bounds__(ADV_THREADS, ADV_MIN_BLOCKS)
-k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc) {
+k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int64_t l_begin, int64_t l_end) {
     /* stage derivatives k_j[0:3], j = 1..7: 21 doubles per thread, one column per thread
        (consecutive threads -> consecutive 8-byte words: conflict-free) */
     __shared__ double s_k[21 * ADV_THREADS];
@@ -129,8 +129,7 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc) {
     K.stride = ADV_THREADS;
     Tally c;
     tally_zero(c);
-    int64_t n = (int64_t)A.Nx * A.ny;
-    for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t l = l_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < l_end; l += (int64_t)gridDim.x * blockDim.x) {
         uint8_t flags = A.flags[l];
         if (!(flags & PICLES_PF_ACTIVE)) continue; /* record stays invalid (set at seed) */
         int64_t le = rec_index(A, l);
@@ -491,13 +490,14 @@ void launch_seed(const DeviceArrays& A, const picles_params_t& P, const double* 
     k_seed<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(A, P, u0, v0);
 }
 
+/* particles [l_begin, l_end) of the strip (the whole strip: 0, Nx*ny) */
 void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
-                    cudaStream_t st) {
-    int64_t n = (int64_t)A.Nx * A.ny;
-    int g = grid_for(n, ADV_THREADS, sms, ADV_MIN_BLOCKS);
+                    cudaStream_t st, int64_t l_begin, int64_t l_end) {
+    if (l_end <= l_begin) return;
+    int g = grid_for(l_end - l_begin, ADV_THREADS, sms, ADV_MIN_BLOCKS);
     bool pn = (A.M[0] != nullptr);
-    if (pn) k_advance<true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc);
-    else k_advance<false><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc);
+    if (pn) k_advance<true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end);
+    else k_advance<false><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end);
 }
 
 int project_remesh_smem_bytes() { return (int)sizeof(PRTile) + 128; }

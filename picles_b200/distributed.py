@@ -147,6 +147,13 @@ class StripStepper:
         previous t+DT level becomes the t level); winds = (u_t, v_t, u_t1, v_t1) arrays;
         neither: reuse what is on the device."""
         e = self.eng
+        if isinstance(self.transport, NcclLibTransport):
+            # one C-ABI call: wind upload pipelined against the advance, exchange on the stream
+            if host_ptrs is not None:
+                e.step_strip_raw(t, DT, None, None, host_ptrs[0], host_ptrs[1], self.lo, self.hi)
+            else:
+                e.step_strip(t, DT, *(winds if winds is not None else (None,) * 4), lo=self.lo, hi=self.hi)
+            return
         if host_ptrs is not None:
             e.upload_winds_raw(None, None, host_ptrs[0], host_ptrs[1])
         elif winds is not None:

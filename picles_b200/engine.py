@@ -113,6 +113,9 @@ class B200Engine:
         a = [self._wind(x) for x in (u_t, v_t, u_t1, v_t1)]
         self._check(self.lib.picles_step_strip(self.h, float(t), float(DT), *[_ptr(x) for x in a], int(lo), int(hi)))
 
+    def step_strip_raw(self, t, DT, pu_t, pv_t, pu_t1, pv_t1, lo=-1, hi=-1):
+        self._check(self.lib.picles_step_strip(self.h, float(t), float(DT), pu_t, pv_t, pu_t1, pv_t1, int(lo), int(hi)))
+
     def synchronize(self):
         self._check(self.lib.picles_synchronize(self.h))
 
