@@ -177,6 +177,29 @@ int picles_set_grid(picles_t* h, int Nx, int Ny, int bx, int by,
                     int j0, int ny_local, int halo,
                     const uint8_t* mask, const double* M, const double* M_const,
                     const double* pc_coef);
+/*
+ * Same as picles_set_grid for grids with a per-node metric (MOM6GridMesh), but the
+ * projection kernel and the great-circle coefficient are formed ON THE DEVICE from the raw
+ * mesh planes of this strip (ny_local*Nx each, host):
+ *   M  = [cos a/dx  sin a/dy; -sin a/dx  cos a/dy],  a = angle_dx*pi/180
+ *                                  ProjetionKernel(Gi, stats), TripolarGridMOM6.jl:448-459
+ *   pc = sign(lat)*min(sign(lat)*tand(lat), 60)/R_earth
+ *                                  SphericalPropagationCorrection, spherical_grid_corrections.jl:13,49-51
+ * with the deterministic sin/cos/tand of pmath_trig.h (bit-identical to the CPU oracle).
+ */
+int picles_set_grid_metric(picles_t* h, int Nx, int Ny, int bx, int by,
+                           int j0, int ny_local, int halo, const uint8_t* mask,
+                           const double* dx, const double* dy, const double* angle_dx,
+                           const double* lat, double R_earth);
+/* read back the metric in use: M = 4 planes (M11,M12,M21,M22) of ny_local*Nx, pc = 1 plane */
+int picles_get_metric(picles_t* h, double* M, double* pc);
+/*
+ * make_boundaries(mask, Nx, Ny) (mask_utils.jl:14-22,38-55) on the device for a whole grid:
+ * ocean[Nx*Ny] (1 ocean / 0 land) -> total[Nx*Ny] with PICLES_MASK_* values.  bx/by: only
+ * PICLES_BND_NONPERIODIC axes get their edges marked 3.  Needs no grid to be set.
+ */
+int picles_make_boundaries(picles_t* h, int Nx, int Ny, int bx, int by,
+                           const uint8_t* ocean, uint8_t* total);
 int picles_set_params(picles_t* h, const picles_params_t* p);
 
 /* ---- the path ---------------------------------------------------------- */

@@ -76,7 +76,8 @@ def load(variant: str = "default"):
     lib.oracle_corner_target.argtypes = [i32, i32, i32, i32, i64, i64]
     lib.oracle_integrate_one.argtypes = [C.POINTER(PiclesParams), vp, d, vp, vp, vp, vp, vp, i32, d, d, d, d, d,
                                          C.POINTER(PiclesCounters), vp]
-    for f in ("exp", "log", "tanh", "sech", "cosh", "eps"):
+    lib.oracle_grid_metric.argtypes = [i64, vp, vp, vp, vp, d, vp, vp]
+    for f in ("exp", "log", "tanh", "sech", "cosh", "eps", "sin", "cos", "sind", "cosd", "tand"):
         getattr(lib, "oracle_pm_" + f).argtypes = [i64, vp, vp]
     lib.oracle_pm_pow.argtypes = [i64, vp, vp, vp]
     lib.oracle_uses_libm.restype = i32
@@ -269,6 +270,16 @@ def pm(func, x, y=None, variant="default"):
     else:
         getattr(lib, "oracle_pm_" + func)(x.size, _dp(x), _dp(out))
     return out
+
+
+def grid_metric(dx, dy, angle_dx, lat, R_earth=6.3710e6, variant="default"):
+    """per-node projection kernel planes (4, ...) and great-circle coefficient"""
+    lib = load(variant)
+    dx, dy, angle_dx, lat = (_f64(np.broadcast_to(a, np.shape(dx))) for a in (dx, dy, angle_dx, lat))
+    M = np.empty((4,) + dx.shape)
+    pc = np.empty(dx.shape)
+    lib.oracle_grid_metric(dx.size, _dp(dx), _dp(dy), _dp(angle_dx), _dp(lat), float(R_earth), _dp(M), _dp(pc))
+    return M, pc
 
 
 def max_threads():

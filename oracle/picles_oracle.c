@@ -39,6 +39,7 @@
 
 #include "../include/picles_b200.h"
 #include "../picles_b200/csrc/pmath.h"
+#include "../picles_b200/csrc/pmath_trig.h"
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -858,6 +859,23 @@ VEC_HOOK(oracle_pm_tanh, pm_tanh(a))
 VEC_HOOK(oracle_pm_sech, pm_sech(a))
 VEC_HOOK(oracle_pm_cosh, pm_cosh(a))
 VEC_HOOK(oracle_pm_eps, pm_eps(a))
+static double hook_sin(double a) { double s, c; pm_sincos(a, &s, &c); return s; }
+static double hook_cos(double a) { double s, c; pm_sincos(a, &s, &c); return c; }
+static double hook_sind(double a) { double s, c; pm_sincosd(a, &s, &c); return s; }
+static double hook_cosd(double a) { double s, c; pm_sincosd(a, &s, &c); return c; }
+VEC_HOOK(oracle_pm_sin, hook_sin(a))
+VEC_HOOK(oracle_pm_cos, hook_cos(a))
+VEC_HOOK(oracle_pm_sind, hook_sind(a))
+VEC_HOOK(oracle_pm_cosd, hook_cosd(a))
+VEC_HOOK(oracle_pm_tand, pm_tand(a))
+/* grid metric of n nodes: ProjetionKernel(Gi, stats) (TripolarGridMOM6.jl:448-459) and
+   SphericalPropagationCorrection(ij_mesh, stats) (spherical_grid_corrections.jl:13,49-51);
+   M: 4 planes (M11, M12, M21, M22) of n */
+void oracle_grid_metric(int64_t n, const double* dx, const double* dy, const double* angle_dx, const double* lat,
+                        double R_earth, double* M, double* pc) {
+    for (int64_t l = 0; l < n; l++)
+        pm_grid_metric_node(dx[l], dy[l], angle_dx[l], lat[l], R_earth, &M[l], &M[n + l], &M[2 * n + l], &M[3 * n + l], &pc[l]);
+}
 void oracle_pm_pow(int64_t n, const double* x, const double* y, double* out) {
     for (int64_t i = 0; i < n; i++) out[i] = pm_pow(x[i], y[i]);
 }

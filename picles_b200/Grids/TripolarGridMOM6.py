@@ -127,7 +127,12 @@ class MOM6GridMesh:
         self.PropagationCorrection = SphericalPropagationCorrection
 
     def device_metric(self):
-        return dict(M=ProjetionKernel(self.data), M_const=None, pc=SphericalPropagationCorrection(self.data.y))
+        """M / pc: host evaluation of the reference formulas (numpy); raw: the mesh planes the
+        library turns into the same quantities on the device (picles_set_grid_metric), which is
+        what the B200 model uses."""
+        return dict(M=ProjetionKernel(self.data), M_const=None, pc=SphericalPropagationCorrection(self.data.y),
+                    raw=dict(dx=self.data.dx, dy=self.data.dy, angle_dx=self.data.angle_dx, lat=self.data.y,
+                             R_earth=6.3710e6))
 
 
 def synthetic_supergrid(nx, ny, k=2, lat_min=-78.0, lat_max=89.5, cap_lat=65.0, R=6.371e6):

@@ -125,11 +125,19 @@ class WaveGrowth2D:
             j0, ny, halo = self._strip if self._strip else (0, self.Ny, 0)
             rows = slice(j0, j0 + ny)
             plane = lambda a: np.ascontiguousarray(np.asarray(a)[:, rows].T)  # (Nx,Ny) F-view -> (ny,Nx) C
-            M = None if met["M"] is None else np.stack([plane(met["M"][k]) for k in range(4)])
-            pc = None if met["pc"] is None else plane(met["pc"])
+            raw = met.get("raw")
+            if raw is not None:   # per-node metric: formed on the device from the raw mesh planes
+                metric = {k: plane(raw[k]) for k in ("dx", "dy", "angle_dx", "lat")}
+                metric["R_earth"] = raw["R_earth"]
+                M = pc = None
+            else:
+                metric = None
+                M = None if met["M"] is None else np.stack([plane(met["M"][k]) for k in range(4)])
+                pc = None if met["pc"] is None else plane(met["pc"])
             self._engine = B200Engine(self.Nx, self.Ny, g.stats.Nx.code, g.stats.Ny.code,
                                       plane(g.data.mask).astype(np.uint8), self.params, M=M, M_const=met["M_const"],
-                                      pc=pc, device=self.architecture.devices[0], j0=j0, ny_local=ny, halo=halo)
+                                      pc=pc, device=self.architecture.devices[0], j0=j0, ny_local=ny, halo=halo,
+                                      metric=metric)
             self._rows = rows
         return self._engine
 

@@ -107,6 +107,10 @@ SYMBOLS = {
     "picles_last_error": (C.c_char_p, [_vp]),
     "picles_set_grid": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   _vp, _vp, _vp, _vp]),
+    "picles_set_grid_metric": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         _vp, _vp, _vp, _vp, _vp, C.c_double]),
+    "picles_get_metric": (C.c_int, [_vp, _vp, _vp]),
+    "picles_make_boundaries": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "picles_set_params": (C.c_int, [_vp, C.POINTER(PiclesParams)]),
     "picles_seed": (C.c_int, [_vp, _vp, _vp]),
     "picles_step": (C.c_int, [_vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp]),

@@ -244,14 +244,24 @@ int picles_destroy(picles_t* h) {
     return PICLES_OK;
 }
 
-int picles_set_grid(picles_t* h, int Nx, int Ny, int bx, int by, int j0, int ny_local, int halo,
-                    const uint8_t* mask, const double* M, const double* M_const, const double* pc_coef) {
+/* raw metric arrays of the strip's nodes (host): what ProjetionKernel(ij_mesh, stats) and
+   SphericalPropagationCorrection(ij_mesh, stats) consume */
+struct RawMetric {
+    const double *dx, *dy, *angle_dx, *lat;
+    double R_earth;
+};
+
+static int set_grid_impl(picles_t* h, int Nx, int Ny, int bx, int by, int j0, int ny_local, int halo,
+                         const uint8_t* mask, const double* M, const double* M_const, const double* pc_coef,
+                         const RawMetric* raw) {
     if (!h) return fail(nullptr, PICLES_ERR_ARG, "null handle");
     if (Nx < 1 || Ny < 1 || ny_local < 1 || j0 < 0 || j0 + ny_local > Ny || halo < 0)
         return fail(h, PICLES_ERR_ARG, "bad grid shape Nx=%d Ny=%d j0=%d ny=%d halo=%d", Nx, Ny, j0, ny_local, halo);
     if (bx < 0 || bx > 1 || by < 0 || by > 2) return fail(h, PICLES_ERR_ARG, "bad boundary types bx=%d by=%d", bx, by);
     if (!mask) return fail(h, PICLES_ERR_ARG, "mask is required");
-    if (!M && !M_const) return fail(h, PICLES_ERR_ARG, "one of M / M_const is required");
+    if (!M && !M_const && !raw) return fail(h, PICLES_ERR_ARG, "one of M / M_const is required");
+    if (raw && (!raw->dx || !raw->dy || !raw->angle_dx || !raw->lat || !(raw->R_earth > 0)))
+        return fail(h, PICLES_ERR_ARG, "dx, dy, angle_dx, lat and a positive R_earth are required");
     if (halo > PH_REACH_MAX_ABI) return fail(h, PICLES_ERR_ARG, "halo %d exceeds the supported reach %d", halo, PH_REACH_MAX_ABI);
     if (ny_local != Ny && halo > ny_local) return fail(h, PICLES_ERR_ARG, "halo %d wider than the strip (%d rows)", halo, ny_local);
     CK(cudaSetDevice(h->device));
@@ -276,10 +286,26 @@ int picles_set_grid(picles_t* h, int Nx, int Ny, int bx, int by, int j0, int ny_
             DALLOC(A.M[k], n);
             CK(cudaMemcpyAsync(A.M[k], M + k * n, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
         }
+    } else if (raw) {
+        /* grid-metric lookup on the device: per-node kernel and great-circle coefficient */
+        double* tmp = nullptr;
+        cudaError_t e = cudaMalloc((void**)&tmp, (size_t)n * 4 * 8);
+        if (e != cudaSuccess) return fail(h, PICLES_ERR_ALLOC, "cudaMalloc(metric staging): %s", cudaGetErrorString(e));
+        const double* src[4] = {raw->dx, raw->dy, raw->angle_dx, raw->lat};
+        for (int k = 0; k < 4; k++) {
+            e = cudaMemcpyAsync(tmp + k * n, src[k], (size_t)n * 8, cudaMemcpyHostToDevice, h->stream);
+            if (e != cudaSuccess) { cudaFree(tmp); return fail(h, PICLES_ERR_CUDA, "metric upload: %s", cudaGetErrorString(e)); }
+        }
+        for (int k = 0; k < 4; k++) DALLOC(A.M[k], n);
+        DALLOC(A.pc, n);
+        launch_grid_metric(n, tmp, tmp + n, tmp + 2 * n, tmp + 3 * n, raw->R_earth, A.M[0], A.M[1], A.M[2], A.M[3], A.pc, h->sms, h->stream);
+        e = cudaStreamSynchronize(h->stream);
+        cudaFree(tmp);
+        if (e != cudaSuccess) return fail(h, PICLES_ERR_CUDA, "k_grid_metric: %s", cudaGetErrorString(e));
     } else {
         for (int k = 0; k < 4; k++) { A.M[k] = nullptr; A.Mc[k] = M_const[k]; }
     }
-    if (pc_coef) {
+    if (pc_coef && !raw) {
         DALLOC(A.pc, n);
         CK(cudaMemcpyAsync(A.pc, pc_coef, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
     }
@@ -302,6 +328,58 @@ int picles_set_grid(picles_t* h, int Nx, int Ny, int bx, int by, int j0, int ny_
     /* |ocean_points| of this strip */
     h->n_active = -1; /* resolved at seed (depends on the model's periodic_boundary) */
     h->have_grid = true;
+    return PICLES_OK;
+}
+
+int picles_set_grid(picles_t* h, int Nx, int Ny, int bx, int by, int j0, int ny_local, int halo,
+                    const uint8_t* mask, const double* M, const double* M_const, const double* pc_coef) {
+    return set_grid_impl(h, Nx, Ny, bx, by, j0, ny_local, halo, mask, M, M_const, pc_coef, nullptr);
+}
+
+int picles_set_grid_metric(picles_t* h, int Nx, int Ny, int bx, int by, int j0, int ny_local, int halo,
+                           const uint8_t* mask, const double* dx, const double* dy, const double* angle_dx,
+                           const double* lat, double R_earth) {
+    RawMetric raw = {dx, dy, angle_dx, lat, R_earth};
+    return set_grid_impl(h, Nx, Ny, bx, by, j0, ny_local, halo, mask, nullptr, nullptr, nullptr, &raw);
+}
+
+int picles_get_metric(picles_t* h, double* M, double* pc) {
+    if (!h || !h->have_grid) return fail(h, PICLES_ERR_STATE, "grid not set");
+    CK(cudaSetDevice(h->device));
+    const DeviceArrays& A = h->A;
+    int64_t n = (int64_t)A.Nx * A.ny;
+    if (M) {
+        if (A.M[0]) {
+            for (int k = 0; k < 4; k++) CK(cudaMemcpyAsync(M + k * n, A.M[k], (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            for (int k = 0; k < 4; k++)
+                for (int64_t l = 0; l < n; l++) M[k * n + l] = A.Mc[k];
+        }
+    }
+    if (pc) {
+        if (A.pc) CK(cudaMemcpyAsync(pc, A.pc, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+        else memset(pc, 0, (size_t)n * 8);
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return PICLES_OK;
+}
+
+/* make_boundaries(mask, Nx, Ny) on the device: ocean (1) / land (0) -> total mask 0..3 */
+int picles_make_boundaries(picles_t* h, int Nx, int Ny, int bx, int by, const uint8_t* ocean, uint8_t* total) {
+    if (!h || !ocean || !total || Nx < 1 || Ny < 1 || bx < 0 || bx > 1 || by < 0 || by > 2)
+        return fail(h, PICLES_ERR_ARG, "picles_make_boundaries: bad argument");
+    CK(cudaSetDevice(h->device));
+    size_t n = (size_t)Nx * Ny;
+    uint8_t* d = nullptr;
+    if (cudaMalloc((void**)&d, 2 * n) != cudaSuccess) return fail(h, PICLES_ERR_ALLOC, "cannot allocate %zu bytes", 2 * n);
+    cudaError_t e = cudaMemcpyAsync(d, ocean, n, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        launch_make_boundaries(d, d + n, Nx, Ny, bx, by, h->sms, h->stream);
+        e = cudaMemcpyAsync(total, d + n, n, cudaMemcpyDeviceToHost, h->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(h, PICLES_ERR_CUDA, "picles_make_boundaries: %s", cudaGetErrorString(e));
     return PICLES_OK;
 }
 

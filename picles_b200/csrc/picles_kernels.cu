@@ -22,6 +22,7 @@
 
 #include "physics.h"
 #include "picles_device.h"
+#include "pmath_trig.h"
 
 namespace picles {
 
@@ -409,6 +410,43 @@ __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) p[q] = v;
 }
 
+/* ---- grid lookups -------------------------------------------------------------------- */
+/* per-node projection kernel M = [cosα/dx sinα/dy; −sinα/dx cosα/dy] and great-circle
+   coefficient from the raw metric planes (TripolarGridMOM6.jl:448-459,
+   spherical_grid_corrections.jl:13); coalesced plane reads and writes, 72 B/node */
+__global__ void __launch_bounds__(256) k_grid_metric(int64_t n, const double* __restrict__ dx, const double* __restrict__ dy,
+                                                     const double* __restrict__ angle_dx, const double* __restrict__ lat,
+                                                     double R_earth, double* __restrict__ M11, double* __restrict__ M12,
+                                                     double* __restrict__ M21, double* __restrict__ M22, double* __restrict__ pc) {
+    for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x) {
+        double a, b, c, d, p;
+        pm_grid_metric_node(dx[l], dy[l], angle_dx[l], lat[l], R_earth, &a, &b, &c, &d, &p);
+        M11[l] = a; M12[l] = b; M21[l] = c; M22[l] = d; pc[l] = p;
+    }
+}
+/* make_boundaries (mask_utils.jl:14-22,38-55): land nodes with an ocean 4-neighbour (circular
+   shifts, as circshift) become 2, edges of non-periodic axes 3.  The +-1 row/column reads
+   of neighbouring threads overlap and are served by L1. */
+__global__ void __launch_bounds__(256) k_make_boundaries(const uint8_t* __restrict__ ocean, uint8_t* __restrict__ total,
+                                                         int Nx, int Ny, int bx, int by) {
+    for (int j = blockIdx.y; j < Ny; j += gridDim.y) {
+        const int jm = (j == 0) ? Ny - 1 : j - 1, jp = (j == Ny - 1) ? 0 : j + 1;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Nx; i += gridDim.x * blockDim.x) {
+            const int im = (i == 0) ? Nx - 1 : i - 1, ip = (i == Nx - 1) ? 0 : i + 1;
+            const int64_t row = (int64_t)j * Nx;
+            int self = ocean[row + i] != 0;
+            int b = 0;
+            if (!self)
+                b = (ocean[row + im] != 0) | (ocean[row + ip] != 0) | (ocean[(int64_t)jm * Nx + i] != 0) |
+                    (ocean[(int64_t)jp * Nx + i] != 0);
+            int v = self + 2 * b;
+            if (bx == PICLES_BND_NONPERIODIC && (i == 0 || i == Nx - 1)) v = 3;
+            if (by == PICLES_BND_NONPERIODIC && (j == 0 || j == Ny - 1)) v = 3;
+            total[row + i] = (uint8_t)v;
+        }
+    }
+}
+
 /* ---- roofline denominators measured in place ------------------------------------ */
 /* 8 independent DFMA chains per thread: the FP64 pipe's issue-rate ceiling */
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
@@ -521,6 +559,15 @@ void launch_halo_pack(const DeviceArrays& A, char* lo, char* hi, int sms, cudaSt
 void launch_halo_unpack(const DeviceArrays& A, const char* lo, const char* hi, DeviceCounters* dc, int sms, cudaStream_t st) {
     int64_t m = (int64_t)A.halo * A.rp;
     if (m > 0) k_halo_unpack<<<grid_for(m, 256, sms, 4), 256, 0, st>>>(A, lo, hi, dc);
+}
+void launch_grid_metric(int64_t n, const double* dx, const double* dy, const double* angle_dx, const double* lat,
+                        double R_earth, double* M11, double* M12, double* M21, double* M22, double* pc, int sms, cudaStream_t st) {
+    if (n > 0) k_grid_metric<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(n, dx, dy, angle_dx, lat, R_earth, M11, M12, M21, M22, pc);
+}
+void launch_make_boundaries(const uint8_t* ocean, uint8_t* total, int Nx, int Ny, int bx, int by, int sms, cudaStream_t st) {
+    (void)sms;
+    dim3 grid((Nx + 255) / 256, Ny < 65535 ? Ny : 65535);
+    k_make_boundaries<<<grid, 256, 0, st>>>(ocean, total, Nx, Ny, bx, by);
 }
 void launch_fill_i32(int32_t* p, int64_t n, int32_t v, int sms, cudaStream_t st) {
     if (n > 0) k_fill_i32<<<grid_for(n, 256, sms, 4), 256, 0, st>>>(p, n, v);

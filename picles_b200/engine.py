@@ -20,8 +20,10 @@ def _ptr(a):
 
 class B200Engine:
     def __init__(self, Nx, Ny, bx, by, mask, params: PiclesParams, M=None, M_const=None, pc=None, device=0,
-                 j0=0, ny_local=None, halo=0):
-        """mask/M/pc cover the rows this strip owns: (ny_local, Nx), (4, ny_local, Nx), (ny_local, Nx)."""
+                 j0=0, ny_local=None, halo=0, metric=None):
+        """mask/M/pc cover the rows this strip owns: (ny_local, Nx), (4, ny_local, Nx), (ny_local, Nx).
+        metric = dict(dx, dy, angle_dx, lat[, R_earth]) of (ny_local, Nx) planes: the per-node
+        kernel and great-circle coefficient are then formed on the device (picles_set_grid_metric)."""
         self.lib = load_library()
         self.Nx, self.Ny = int(Nx), int(Ny)
         self.j0 = int(j0)
@@ -34,8 +36,15 @@ class B200Engine:
         Mp = np.ascontiguousarray(np.asarray(M, np.float64).reshape(4, self.ny, self.Nx)) if M is not None else None
         Mc = np.ascontiguousarray(np.asarray(M_const, np.float64).reshape(4)) if M_const is not None else None
         pcp = np.ascontiguousarray(np.asarray(pc, np.float64).reshape(self.ny, self.Nx)) if pc is not None else None
-        self._check(self.lib.picles_set_grid(self.h, self.Nx, self.Ny, int(bx), int(by), self.j0, self.ny, self.halo,
-                                             _ptr(mask), _ptr(Mp), _ptr(Mc), _ptr(pcp)))
+        if metric is not None:
+            raw = [np.ascontiguousarray(np.asarray(metric[k], np.float64).reshape(self.ny, self.Nx))
+                   for k in ("dx", "dy", "angle_dx", "lat")]
+            self._check(self.lib.picles_set_grid_metric(self.h, self.Nx, self.Ny, int(bx), int(by), self.j0, self.ny,
+                                                        self.halo, _ptr(mask), *[_ptr(a) for a in raw],
+                                                        float(metric.get("R_earth", 6.3710e6))))
+        else:
+            self._check(self.lib.picles_set_grid(self.h, self.Nx, self.Ny, int(bx), int(by), self.j0, self.ny,
+                                                 self.halo, _ptr(mask), _ptr(Mp), _ptr(Mc), _ptr(pcp)))
         self.params = params
         self._check(self.lib.picles_set_params(self.h, C.byref(params)))
 
@@ -142,6 +151,20 @@ class B200Engine:
         status = np.empty(sh, np.int32)
         self._check(self.lib.picles_get_particles(self.h, _ptr(z), _ptr(t), _ptr(dt), _ptr(flags), _ptr(status)))
         return dict(z=z, t=t, dt=dt, flags=flags, status=status)
+
+    def metric(self):
+        """(M, pc) in use: M (4, ny, Nx) planes M11, M12, M21, M22; pc (ny, Nx)."""
+        M = np.empty((4, self.ny, self.Nx))
+        pc = np.empty((self.ny, self.Nx))
+        self._check(self.lib.picles_get_metric(self.h, _ptr(M), _ptr(pc)))
+        return M, pc
+
+    def make_boundaries(self, ocean, bx, by):
+        """make_boundaries(mask, Nx, Ny) on the device: ocean (Ny, Nx) 0/1 -> total mask 0..3."""
+        o = np.ascontiguousarray(np.asarray(ocean, np.uint8))
+        out = np.empty_like(o)
+        self._check(self.lib.picles_make_boundaries(self.h, o.shape[1], o.shape[0], int(bx), int(by), _ptr(o), _ptr(out)))
+        return out
 
     def counters(self):
         c = PiclesCounters()

@@ -201,6 +201,63 @@ def test_gpu_pipelined_wind_upload_equals_phase_split(gpu_lib):
     assert a.counters()["n_substeps"] == b.counters()["n_substeps"]
 
 
+def test_gpu_grid_metric_and_masks_bit_exact(gpu_lib):
+    """k_grid_metric and k_make_boundaries (the device-side grid lookups) against the oracle:
+    per-node projection kernel and great-circle coefficient with the same bits, total masks
+    identical (incl. the 21x11 fixture of src/Grids/mask_utils_test.jl: 30 / 60)."""
+    import oracle
+    from common import BND_PERIODIC, BND_TRIPOLAR_NORTH, tripolar_grid
+    rng = np.random.default_rng(7)
+    Nx, Ny = 96, 70
+    g = tripolar_grid(Nx, Ny)
+    dx = rng.uniform(500.0, 120e3, (Ny, Nx))
+    dy = rng.uniform(500.0, 120e3, (Ny, Nx))
+    ang = rng.uniform(-180.0, 180.0, (Ny, Nx))
+    lat = np.linspace(-89.9, 89.9, Ny)[:, None] + 0 * dx
+    from picles_b200.engine import B200Engine
+    e = B200Engine(Nx, Ny, BND_PERIODIC, BND_TRIPOLAR_NORTH, g["mask"], default_params(),
+                   metric=dict(dx=dx, dy=dy, angle_dx=ang, lat=lat))
+    M, pc = e.metric()
+    Mo, pco = oracle.grid_metric(dx, dy, ang, lat)
+    assert np.array_equal(M.view(np.uint64), Mo.view(np.uint64))
+    assert np.array_equal(pc.view(np.uint64), pco.view(np.uint64))
+    # masks
+    ocean = np.ones((11, 21), np.uint8)
+    ocean[4:10, 9:20] = 0
+    tot = e.make_boundaries(ocean, BND_NONPERIODIC, BND_NONPERIODIC)
+    assert np.array_equal(tot, oracle.make_boundaries(ocean, BND_NONPERIODIC, BND_NONPERIODIC))
+    assert (tot == 2).sum() == 30 and (tot == 3).sum() == 60 and (tot == 0).sum() == 36 and (tot == 1).sum() == 105
+    big = (rng.uniform(size=(301, 517)) > 0.35).astype(np.uint8)
+    for bx, by in ((0, 0), (1, 0), (1, 1), (1, 2), (0, 1)):
+        assert np.array_equal(e.make_boundaries(big, bx, by), oracle.make_boundaries(big, bx, by))
+
+
+def test_gpu_tripolar_run_with_device_formed_metric(gpu_lib):
+    """the tripolar scenario with its kernel and great-circle term formed on the device from
+    (dx, dy, angle_dx, lat), against the oracle fed with oracle.grid_metric of the same planes."""
+    import oracle
+    from common import tripolar_grid
+    Nx, Ny = 48, 36
+    ocean = np.ones((Ny, Nx), np.uint8)
+    ocean[:2, :] = 0
+    ocean[10:16, 8:15] = 0
+    g = tripolar_grid(Nx, Ny, ocean=ocean)
+    lon = -280.0 + (np.arange(Nx) + 0.5) * 360.0 / Nx
+    lat = -70.0 + (np.arange(Ny) + 0.5) * 159.0 / Ny
+    LON, LAT = np.meshgrid(lon, lat)
+    ang = 40.0 * np.clip((LAT - 60.0) / 30.0, 0.0, 1.0) * np.sin(np.deg2rad(2 * (LON + 280.0)))
+    dx = np.maximum(6.371e6 * np.cos(np.deg2rad(LAT)) * np.deg2rad(360.0 / Nx), 2000.0) / 60.0
+    dy = np.full_like(dx, 6.371e6 * np.deg2rad(159.0 / Ny)) / 60.0
+    M, pc = oracle.grid_metric(dx, dy, ang, LAT)
+    g = dict(g, M=M, pc=pc)
+    P = default_params(DT=1200.0, periodic_boundary=True)
+    from picles_b200.engine import B200Engine
+    e = B200Engine(Nx, Ny, g["bx"], g["by"], g["mask"], P, metric=dict(dx=dx, dy=dy, angle_dx=ang, lat=LAT))
+    wind = lambda t: (15.0, -10.0 * np.cos(5 * t / (3600 * 2 * np.pi)))
+    run_pair(make_oracle(g, P), e, wind, 1200.0, 5, compare_models)
+    assert e.counters()["reach"] >= 1
+
+
 def test_gpu_state_roundtrip_and_accessors(gpu_lib):
     g = cartesian_grid(33, 17)
     P = default_params()

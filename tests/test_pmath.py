@@ -1,5 +1,6 @@
 """pmath.h (the deterministic math layer shared by device and oracle) against numpy/libm."""
 import numpy as np
+import pytest
 
 import oracle
 
@@ -75,3 +76,48 @@ def test_libm_build_of_the_oracle_agrees_to_1e_9():
     a, b = res[0][0], res[1][0]
     nz = np.abs(a) > 0
     assert np.max(np.abs(a[nz] - b[nz]) / np.abs(a[nz])) < 1e-9
+
+
+def test_trig_for_the_grid_metric_within_1_ulp():
+    """pmath_trig.h: sin/cos in radians (Cody-Waite + fdlibm kernels) against libm, sind/cosd/tand
+    with exact reduction in degrees against the radian functions at a quarter of the argument
+    error; exact values at multiples of 30 / 45 / 90 degrees."""
+    for lo, hi in ((-7, 7), (-1e-3, 1e-3), (-400, 400), (-1e5, 1e5)):
+        x = RNG.uniform(lo, hi, 200000)
+        assert ulp_err(oracle.pm("sin", x), np.sin(x)) <= 1.0
+        assert ulp_err(oracle.pm("cos", x), np.cos(x)) <= 1.0
+    d = np.array([0.0, 30.0, 90.0, 180.0, 270.0, 360.0, -90.0, -30.0])
+    assert np.array_equal(oracle.pm("sind", d), [0.0, 0.5, 1.0, 0.0, -1.0, 0.0, -1.0, -0.5])
+    assert np.array_equal(oracle.pm("cosd", np.array([0.0, 60.0, 90.0, 180.0, 270.0, -60.0])), [1.0, 0.5, 0.0, -1.0, 0.0, 0.5])
+    assert np.array_equal(oracle.pm("tand", np.array([0.0, 45.0, -45.0, 90.0])), [0.0, 1.0, -1.0, np.inf])
+    # tan(radians(lat)) carries the rounding of the degree->radian conversion, amplified near
+    # the poles, so the reference here is 200-bit arithmetic
+    mpmath = pytest.importorskip("mpmath")
+    mpmath.mp.prec = 200
+    lat = RNG.uniform(-89.99, 89.99, 2000)
+    ref = np.array([float(mpmath.tan(mpmath.mpf(float(v)) * mpmath.pi / 180)) for v in lat])
+    assert ulp_err(oracle.pm("tand", lat), ref) <= 2.0
+    ref = np.array([float(mpmath.sin(mpmath.mpf(float(v)) * mpmath.pi / 180)) for v in 4 * lat])
+    assert ulp_err(oracle.pm("sind", 4 * lat), ref) <= 1.0
+    small = RNG.uniform(-1.0, 1.0, 100000)
+    assert ulp_err(oracle.pm("tand", small), np.tan(np.deg2rad(small))) <= 4.0
+
+
+def test_grid_metric_matches_the_reference_formulas():
+    """oracle.grid_metric (the arithmetic k_grid_metric runs on the device) against a numpy
+    restatement of TripolarGridMOM6.jl:448-459 and spherical_grid_corrections.jl:13."""
+    n = 20000
+    dx = RNG.uniform(500.0, 120e3, n)
+    dy = RNG.uniform(500.0, 120e3, n)
+    ang = RNG.uniform(-180.0, 180.0, n)
+    lat = RNG.uniform(-89.0, 89.9, n)
+    M, pc = oracle.grid_metric(dx, dy, ang, lat)
+    ca, sa = np.cos(ang * np.pi / 180), np.sin(ang * np.pi / 180)
+    ref = np.stack([ca / dx, sa / dy, -sa / dx, ca / dy])
+    assert np.max(np.abs(M - ref) / np.maximum(np.abs(ref), 1e-300)) < 1e-12
+    sg = np.sign(lat)
+    ref_pc = sg * np.minimum(sg * np.tan(np.deg2rad(lat)), 60.0) / 6.3710e6
+    assert np.max(np.abs(pc - ref_pc) / np.abs(ref_pc)) < 1e-12
+    # the cap at 60 binds above atan(60) = 89.045 degrees, on both hemispheres
+    _, pcs = oracle.grid_metric(np.ones(3), np.ones(3), np.zeros(3), np.array([89.5, -89.5, 0.0]))
+    assert pcs[0] == 60.0 / 6.3710e6 and pcs[1] == -60.0 / 6.3710e6 and pcs[2] == 0.0
