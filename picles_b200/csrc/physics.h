@@ -100,18 +100,29 @@ PM_HD const Tableau& tableau(int solver) {
 #endif
 }
 
-/* stage-derivative store k_j[c], j = 1..7, c = 0..2: shared memory on the device (one
-   column per thread), a local array on the host */
+/* per-thread scratch of one integration: the stage derivatives k_j[c] (j = 1..7, c = 0..2) and
+   the loop-carried scalars that are touched once per stage or less (slots below).  Shared
+   memory on the device, one column per thread (consecutive threads -> consecutive 8-byte
+   words: conflict-free), so the registers go to the right-hand side; a local array on the
+   host. */
+enum {
+    KS_U3 = 21, KS_U4, KS_X7, KS_Y7, KS_XE, KS_YE, KS_TSTOP, KS_LQ, KS_QOLD, KS_DT0, KS_D1N, KS_DTMIN,
+    KS_WDU, KS_WDV, KS_WT0, KS_WIDT, KS_SLOTS
+};
 struct KLocal {
-    double k[7][3];
-    PM_HDM double get(int j, int c) const { return k[j - 1][c]; }
-    PM_HDM void set(int j, int c, double v) { k[j - 1][c] = v; }
+    double k[KS_SLOTS];
+    PM_HDM double get(int j, int c) const { return k[(j - 1) * 3 + c]; }
+    PM_HDM void set(int j, int c, double v) { k[(j - 1) * 3 + c] = v; }
+    PM_HDM double ld(int slot) const { return k[slot]; }
+    PM_HDM void st(int slot, double v) { k[slot] = v; }
 };
 struct KStrided {
     double* base; /* &smem[threadIdx.x] */
     int stride;   /* blockDim.x */
     PM_HDM double get(int j, int c) const { return base[((j - 1) * 3 + c) * stride]; }
     PM_HDM void set(int j, int c, double v) { base[((j - 1) * 3 + c) * stride] = v; }
+    PM_HDM double ld(int slot) const { return base[slot * stride]; }
+    PM_HDM void st(int slot, double v) { base[slot * stride] = v; }
 };
 
 /* per-thread view of one particle (ODEIntegrator fields that survive between steps) */
@@ -273,6 +284,11 @@ template <class O>
 PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx, double cy, double u, double v,
                 double us, double pc, double& d0, double& d1, double& d2, unsigned* bad) {
     double r_g = P.r_g;
+#ifdef PH_HOIST_EXP
+    /* independent of the c̄ chain below: issued first so its polynomial overlaps the serial
+       sqrt -> div -> div head of the evaluation */
+    double e2_early = pm_exp(2.0 * lne);
+#endif
     double cbar = O::sqrt_(cx * cx + cy * cy, bad);
     double c_gp = O::div_pre(fabs(cbar), r_g, H.y_rg, bad);
     double kp = O::div(9.81, 4.0 * pm_max(c_gp * c_gp, 1e-2), bad);
@@ -295,7 +311,11 @@ PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx,
         pw = (twon == 4.0) ? r2 * r2 : r2;
         if (twon != 4.0 && twon != 2.0) pw = O::pow_(r, twon, bad); /* general q: uniform, cold */
         /* n == 2 (q = -1/4): exp(n*lne) and exp(2*lne) are the same evaluation */
+#ifdef PH_HOIST_EXP
+        double e2 = e2_early;
+#else
         double e2 = pm_exp(2.0 * lne);
+#endif
         double en = (P.n == 2.0) ? e2 : pm_exp(P.n * lne);
         Dt = P.dissipation ? en * pw : 0.0;
         double k2 = kp * kp;
@@ -331,28 +351,35 @@ PM_HD void prop(const picles_params_t& P, const double* M, double cx, double cy,
 }
 
 /* wind at stage time ts (linear between the two staged levels) and its speed.  A wind
-   that does not change over DT (du = dv = 0) gives u0, v0 and the hoisted us0 exactly. */
-template <class O>
-PM_HD void stage_wind(const Wind& w, const Hoist& H, double ts, double& u, double& v, double& us, unsigned* bad) {
+   that does not change over DT (du = dv = 0) gives u0, v0 and the hoisted us0 exactly; the
+   increments and the time base of an unsteady wind live in the scratch slots. */
+template <class O, class KS>
+PM_HD void stage_wind(double wu0, double wv0, const Hoist& H, const KS& K, double ts, double& u, double& v, double& us,
+                      unsigned* bad) {
     if (H.steady) {
-        u = w.u0; v = w.v0; us = H.us0;
+        u = wu0; v = wv0; us = H.us0;
     } else {
-        double s = (ts - w.t_start) * w.inv_DT;
-        u = fma(w.du, s, w.u0);
-        v = fma(w.dv, s, w.v0);
+        double s = (ts - K.ld(KS_WT0)) * K.ld(KS_WIDT);
+        u = fma(K.ld(KS_WDU), s, wu0);
+        v = fma(K.ld(KS_WDV), s, wv0);
         us = O::sqrtz(u * u + v * v, bad);
     }
 }
 
 /* IEEE right-hand side, one shared out-of-line copy: the FSAL reset, the initial-step
-   heuristic, and the fallback of the fast path */
-PM_HD_NOINLINE_DECL void f3_cold(const picles_params_t& P, const Wind& w, double pc, double lne, double cx, double cy,
-                                 double ts, double& d0, double& d1, double& d2) {
+   heuristic, and the fallback of the fast path.  Everything by value: nothing of the
+   caller is forced into local memory. */
+struct D3 { double d0, d1, d2; };
+PM_HD_NOINLINE_DECL D3 f3_cold(const picles_params_t* Pp, double wu0, double wv0, double wdu, double wdv, double wt0,
+                               double widt, double pc, double lne, double cx, double cy, double ts) {
     Hoist H;
     H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false;
-    double u, v, us;
-    stage_wind<OpsSafe>(w, H, ts, u, v, us, (unsigned*)0);
-    rhs3<OpsSafe>(P, H, lne, cx, cy, u, v, us, pc, d0, d1, d2, (unsigned*)0);
+    double s = (ts - wt0) * widt;
+    double u = fma(wdu, s, wu0), v = fma(wdv, s, wv0);
+    double us = sqrt(u * u + v * v);
+    D3 r;
+    rhs3<OpsSafe>(*Pp, H, lne, cx, cy, u, v, us, pc, r.d0, r.d1, r.d2, (unsigned*)0);
+    return r;
 }
 
 /* loop invariants of the hot right-hand side */
@@ -368,17 +395,22 @@ PM_HD void make_hoist(const picles_params_t& P, const Wind& w, Hoist& H) {
 }
 
 /* hot right-hand side of the stage loop */
-PM_HD void f3(const picles_params_t& P, const Wind& w, const Hoist& H, double pc, double lne, double cx, double cy,
-              double ts, double& d0, double& d1, double& d2) {
+template <class KS>
+PM_HD void f3(const picles_params_t& P, double wu0, double wv0, const Hoist& H, const KS& K, double pc, double lne, double cx,
+              double cy, double ts, double& d0, double& d1, double& d2) {
 #if defined(__CUDA_ARCH__)
     double u, v, us;
     unsigned bad = 0;
-    stage_wind<OpsFast>(w, H, ts, u, v, us, &bad);
+    stage_wind<OpsFast>(wu0, wv0, H, K, ts, u, v, us, &bad);
     rhs3<OpsFast>(P, H, lne, cx, cy, u, v, us, pc, d0, d1, d2, &bad);
-    if (bad) f3_cold(P, w, pc, lne, cx, cy, ts, d0, d1, d2); /* rare: denormal/huge/non-finite operands */
+    if (bad) { /* rare: denormal/huge/non-finite operands */
+        D3 r = f3_cold(&P, wu0, wv0, K.ld(KS_WDU), K.ld(KS_WDV), K.ld(KS_WT0), K.ld(KS_WIDT), pc, lne, cx, cy, ts);
+        d0 = r.d0; d1 = r.d1; d2 = r.d2;
+    }
 #else
     (void)H;
-    f3_cold(P, w, pc, lne, cx, cy, ts, d0, d1, d2);
+    D3 r = f3_cold(&P, wu0, wv0, K.ld(KS_WDU), K.ld(KS_WDV), K.ld(KS_WT0), K.ld(KS_WIDT), pc, lne, cx, cy, ts);
+    d0 = r.d0; d1 = r.d1; d2 = r.d2;
 #endif
 }
 
@@ -511,12 +543,15 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
     const Tableau& T = tableau(P.solver);
     Hoist H;
     make_hoist(P, w, H);
+    const double wu0 = w.u0, wv0 = w.v0;
+    K.st(KS_WDU, w.du); K.st(KS_WDV, w.dv); K.st(KS_WT0, w.t_start); K.st(KS_WIDT, w.inv_DT);
     double t = p.t;
-    const double tstop = t + DT;
-    double u0 = p.u0, u1 = p.u1, u2 = p.u2, u3 = p.u3, u4 = p.u4;
+    K.st(KS_TSTOP, t + DT);
+    double u0 = p.u0, u1 = p.u1, u2 = p.u2;
+    K.st(KS_U3, p.u3); K.st(KS_U4, p.u4);
     double dt = p.dt;
-    double qold = p.qold;
-    double lq = pm_log(qold);
+    K.st(KS_QOLD, p.qold);
+    K.st(KS_LQ, pm_log(p.qold));
     const double LQ0 = PH_LOG_QOLDINIT; /* pm_log(1e-4), pinned by tests/test_pmath.py */
     int32_t iter = p.iter;
     int32_t nrhs = 0, attempts = 0;
@@ -526,14 +561,14 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
 
     int ph = 1;
     double n0 = u0, n1 = u1, n2 = u2, ts = t; /* argument of the next right-hand side */
-    double x7 = 0.0, y7 = 0.0, xe = 0.0, ye = 0.0, dt0 = 0.0, d1n = 0.0;
-    double dtmin_t = P.dtmin;
+    K.st(KS_X7, 0.0); K.st(KS_Y7, 0.0); K.st(KS_XE, 0.0); K.st(KS_YE, 0.0); K.st(KS_DT0, 0.0); K.st(KS_D1N, 0.0);
+    K.st(KS_DTMIN, P.dtmin);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (;;) {
         double d0, d1, d2;
-        f3(P, w, H, pc, n0, n1, n2, ts, d0, d1, d2);
+        f3(P, wu0, wv0, H, K, pc, n0, n1, n2, ts, d0, d1, d2);
         nrhs++;
         if (ph >= 2) {
             K.set(ph, 0, d0); K.set(ph, 1, d1); K.set(ph, 2, d2);
@@ -541,10 +576,10 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
             prop(P, M, n1, n2, kx, ky);
             if (ph < 7) {
                 double a7 = T.a[7][ph];
-                if (a7 != 0.0) { x7 = fma(a7, kx, x7); y7 = fma(a7, ky, y7); }
+                if (a7 != 0.0) { K.st(KS_X7, fma(a7, kx, K.ld(KS_X7))); K.st(KS_Y7, fma(a7, ky, K.ld(KS_Y7))); }
             }
             double bs = T.bt[ph];
-            if (bs != 0.0) { xe = fma(bs, kx, xe); ye = fma(bs, ky, ye); }
+            if (bs != 0.0) { K.st(KS_XE, fma(bs, kx, K.ld(KS_XE))); K.st(KS_YE, fma(bs, ky, K.ld(KS_YE))); }
             if (ph < 7) {
                 /* argument of stage s = ph+1 >= 3 */
                 int s = ++ph;
@@ -561,7 +596,8 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
                 continue;
             }
             /* all seven stages done: (n0,n1,n2) is u_new */
-            double n3 = fma(dt, x7, u3), n4 = fma(dt, y7, u4);
+            const double u3 = K.ld(KS_U3), u4 = K.ld(KS_U4);
+            double n3 = fma(dt, K.ld(KS_X7), u3), n4 = fma(dt, K.ld(KS_Y7), u4);
             double b1 = T.bt[1];
             double e0 = b1 * K.get(1, 0), e1 = b1 * K.get(1, 1), e2 = b1 * K.get(1, 2);
             for (int j = 2; j <= 7; j++) {
@@ -569,6 +605,7 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
                 if (bj != 0.0) { e0 = fma(bj, K.get(j, 0), e0); e1 = fma(bj, K.get(j, 1), e1); e2 = fma(bj, K.get(j, 2), e2); }
             }
             StepCtl sc;
+            const double xe = K.ld(KS_XE), ye = K.ld(KS_YE), lq = K.ld(KS_LQ);
 #if defined(__CUDA_ARCH__)
             unsigned bad = 0;
             step_control<OpsFast>(P, T, dt, e0, e1, e2, xe, ye, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, lq, sc, &bad);
@@ -577,22 +614,24 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
             step_control_cold(P, T, dt, e0, e1, e2, xe, ye, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, lq, sc);
 #endif
             double EEst = sc.EEst;
-            bool accept = (EEst <= 1.0) || (P.force_dtmin && fabs(dt) <= dtmin_t);
+            bool accept = (EEst <= 1.0) || (P.force_dtmin && fabs(dt) <= K.ld(KS_DTMIN));
             if (accept) {
                 /* step_accept_controller!, fixed_t_for_floatingpoint_error!, calc_dt_propose! */
                 bool big = (EEst > PH_QOLDINIT) || (EEst != EEst);
-                qold = big ? EEst : PH_QOLDINIT; /* max(EEst, qoldinit) */
-                lq = big ? sc.lE : LQ0;
+                K.st(KS_QOLD, big ? EEst : PH_QOLDINIT); /* max(EEst, qoldinit) */
+                K.st(KS_LQ, big ? sc.lE : LQ0);
                 double dtnew = dt / sc.q;
                 double ttmp = t + dt;
+                const double tstop = K.ld(KS_TSTOP);
                 t = (fabs(ttmp - tstop) < 100.0 * pm_eps(tstop)) ? tstop : ttmp;
                 double dtp = pm_min(P.dtmax, dtnew);
                 dtp = pm_max(dtp, pm_max(pm_eps(t), P.dtmin));
                 dt = dtp;
-                u0 = n0; u1 = n1; u2 = n2; u3 = n3; u4 = n4;
+                u0 = n0; u1 = n1; u2 = n2;
+                K.st(KS_U3, n3); K.st(KS_U4, n4);
                 K.set(1, 0, K.get(7, 0)); K.set(1, 1, K.get(7, 1)); K.set(1, 2, K.get(7, 2)); /* FSAL */
                 c.substeps++;
-                if ((u0 != u0) | (u1 != u1) | (u2 != u2) | (u3 != u3) | (u4 != u4)) {
+                if ((u0 != u0) | (u1 != u1) | (u2 != u2) | (n3 != n3) | (n4 != n4)) {
                     p.status |= PICLES_PST_UNSTABLE; c.failed++; break;
                 }
             } else {
@@ -605,8 +644,9 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
             K.set(1, 0, d0); K.set(1, 1, d1); K.set(1, 2, d2);
             if (need_reset) {
                 need_reset = false;
-                double k3, k4, dtr;
+                double k3, k4, dtr, dt0, d1n;
                 prop(P, M, u1, u2, k3, k4);
+                const double u3 = K.ld(KS_U3), u4 = K.ld(KS_U4);
                 bool final_;
 #if defined(__CUDA_ARCH__)
                 unsigned bad = 0;
@@ -615,6 +655,7 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
 #else
                 final_ = initdt_a_cold(P, u0, u1, u2, u3, u4, d0, d1, d2, k3, k4, dtr, dt0, d1n);
 #endif
+                K.st(KS_DT0, dt0); K.st(KS_D1N, d1n);
                 if (final_) {
                     dt = dtr;
                 } else {
@@ -629,6 +670,7 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
             prop(P, M, u1, u2, k3, k4);
             prop(P, M, n1, n2, f3x, f4x);
             double k0 = K.get(1, 0), k1 = K.get(1, 1), k2 = K.get(1, 2);
+            const double u3 = K.ld(KS_U3), u4 = K.ld(KS_U4), dt0 = K.ld(KS_DT0), d1n = K.ld(KS_D1N);
 #if defined(__CUDA_ARCH__)
             unsigned bad = 0;
             dt = initdt_b<OpsFast>(P, u0, u1, u2, u3, u4, k0, k1, k2, k3, k4, d0, d1, d2, f3x, f4x, dt0, d1n, &bad);
@@ -638,9 +680,11 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
 #endif
         }
         /* ---- header of the next attempt: loopheader!, check_error! ---- */
+        const double tstop = K.ld(KS_TSTOP);
         if (!(t < tstop)) break;
         iter++;
-        dtmin_t = pm_max(pm_eps(t), P.dtmin);
+        const double dtmin_t = pm_max(pm_eps(t), P.dtmin);
+        K.st(KS_DTMIN, dtmin_t);
         dt = pm_min(P.dtmax, dt);
         dt = pm_max(dt, dtmin_t);
         dt = pm_min(dt, tstop - t);
@@ -651,16 +695,16 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
         {
             double kx, ky;
             prop(P, M, u1, u2, kx, ky);
-            x7 = T.a[7][1] * kx; y7 = T.a[7][1] * ky;
-            xe = T.bt[1] * kx; ye = T.bt[1] * ky;
+            K.st(KS_X7, T.a[7][1] * kx); K.st(KS_Y7, T.a[7][1] * ky);
+            K.st(KS_XE, T.bt[1] * kx); K.st(KS_YE, T.bt[1] * ky);
             double a = dt * T.a[2][1];
             n0 = fma(a, K.get(1, 0), u0); n1 = fma(a, K.get(1, 1), u1); n2 = fma(a, K.get(1, 2), u2);
             ts = fma(T.c[1], dt, t);
             ph = 2;
         }
     }
-    p.u0 = u0; p.u1 = u1; p.u2 = u2; p.u3 = u3; p.u4 = u4;
-    p.t = t; p.dt = dt; p.qold = qold; p.iter = iter;
+    p.u0 = u0; p.u1 = u1; p.u2 = u2; p.u3 = K.ld(KS_U3); p.u4 = K.ld(KS_U4);
+    p.t = t; p.dt = dt; p.qold = K.ld(KS_QOLD); p.iter = iter;
     c.rhs += nrhs;
     c.integrated++;
     if (attempts > c.max_attempts) c.max_attempts = attempts;

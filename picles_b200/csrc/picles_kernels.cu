@@ -19,6 +19,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "physics.h"
 #include "picles_device.h"
@@ -119,12 +120,17 @@ __global__ void __launch_bounds__(256) k_seed(DeviceArrays A, picles_params_t P,
  * whose particle reached t+DT wait at the loop exit for the slowest lane of the warp
  * (neighbouring nodes carry near-identical states, so attempt counts are close).
  */
+#ifdef ADV_MAXNREG /* register cap given directly; ADV_MIN_BLOCKS then only sizes the grid */
+#define ADV_BOUNDS __maxnreg__(ADV_MAXNREG)
+#else
+#define ADV_BOUNDS __launch_bounds__(ADV_THREADS, ADV_MIN_BLOCKS)
+#endif
 template <bool PER_NODE_M>
-__global__ void __launch_bounds__(ADV_THREADS, ADV_MIN_BLOCKS)
+__global__ void ADV_BOUNDS
 k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int64_t l_begin, int64_t l_end) {
     /* stage derivatives k_j[0:3], j = 1..7: 21 doubles per thread, one column per thread
        (consecutive threads -> consecutive 8-byte words: conflict-free) */
-    __shared__ double s_k[21 * ADV_THREADS];
+    __shared__ double s_k[KS_SLOTS * ADV_THREADS];
     KStrided K;
     K.base = &s_k[threadIdx.x];
     K.stride = ADV_THREADS;
@@ -534,8 +540,28 @@ void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, 
     if (l_end <= l_begin) return;
     int g = grid_for(l_end - l_begin, ADV_THREADS, sms, ADV_MIN_BLOCKS);
     bool pn = (A.M[0] != nullptr);
-    if (pn) k_advance<true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end);
-    else k_advance<false><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end);
+    /* the register file, not shared memory, must be what bounds the resident blocks: ask for
+       the largest shared-memory carveout (the driver's default split left room for fewer
+       blocks than the registers allow when blocks are small; profiles/README.md) */
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_advance<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_advance<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    size_t dyn = 0;
+#ifdef ADV_OCCUPANCY_EXPERIMENT /* profiles/: unused dynamic shared memory caps the resident blocks per SM */
+    static int dyn_env = -1;
+    if (dyn_env < 0) {
+        const char* e = getenv("PICLES_ADV_DYN_SMEM");
+        dyn_env = e ? atoi(e) : 0;
+        cudaFuncSetAttribute(k_advance<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_env);
+        cudaFuncSetAttribute(k_advance<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_env);
+    }
+    dyn = (size_t)dyn_env;
+#endif
+    if (pn) k_advance<true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+    else k_advance<false><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
 }
 
 int project_remesh_smem_bytes() { return (int)sizeof(PRTile) + 128; }
