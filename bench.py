@@ -168,7 +168,26 @@ def cpu_arm(steps, warmup, sample_n=512, threads=None):
                 ms_per_step=dt / steps * 1e3, substeps_per_particle_step=c["n_substeps"] / max(c["n_integrated"], 1))
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Everything libraries print on fd 1 (NCCL's version banner, …) goes to stderr; the one
+    JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -206,7 +225,7 @@ def main():
                 "gpu_launches": 0,
                 "note": "Julia is not installed on this image: the reference's CPU path is timed as its C port "
                         "(oracle/), all host threads; BASELINE.md quotes 4-7e4 particle-steps/s for the Julia original"}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     # ---- our arm -------------------------------------------------------------------
@@ -361,7 +380,7 @@ def main():
     if not args.no_cpu_baseline:
         cb = cpu_arm(min(args.steps, 3), args.warmup, args.cpu_sample)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
