@@ -279,6 +279,8 @@ static int set_grid_impl(picles_t* h, int Nx, int Ny, int bx, int by, int j0, in
     DALLOC(A.u_t, n); DALLOC(A.v_t, n); DALLOC(A.u_t1, n); DALLOC(A.v_t1, n);
     for (int k = 0; k < 5; k++) DALLOC(A.rec[k], ne);
     DALLOC(A.cell, ne);
+    DALLOC(A.rowreach, ny_local + 2 * halo);
+    CK(cudaMemsetAsync(A.rowreach, 0, (size_t)(ny_local + 2 * halo) * 4, h->stream));
     for (int k = 0; k < 3; k++) DALLOC(A.S[k], n);
     CK(cudaMemcpyAsync(A.mask, mask, (size_t)n, cudaMemcpyHostToDevice, h->stream));
     if (M) {
@@ -452,6 +454,7 @@ int picles_step_advance(picles_t* h, double t, double dt_model) {
     (void)t;
     if (!(dt_model > 0)) return fail(h, PICLES_ERR_ARG, "dt_model must be positive");
     CK(cudaMemsetAsync(h->d_counters, 0, sizeof(DeviceCounters), h->stream));
+    CK(cudaMemsetAsync(h->A.rowreach, 0, (size_t)(h->A.ny + 2 * h->A.halo) * 4, h->stream));
     CK(cudaEventRecord(h->ev[0], h->stream));
     launch_advance(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream, 0, (int64_t)h->A.Nx * h->A.ny);
     CK(cudaEventRecord(h->ev[1], h->stream));
@@ -480,6 +483,7 @@ static int upload_and_advance(picles_t* h, double dt_model, const double* u_t, c
         double* tv = A.v_t; A.v_t = A.v_t1; A.v_t1 = tv;
     }
     CK(cudaMemsetAsync(h->d_counters, 0, sizeof(DeviceCounters), h->stream));
+    CK(cudaMemsetAsync(A.rowreach, 0, (size_t)(A.ny + 2 * A.halo) * 4, h->stream));
     /* the copy stream may only overwrite the wind planes once the compute stream is past
        every earlier kernel that read them */
     CK(cudaEventRecord(h->pev[PIPE_CHUNKS], h->stream));
@@ -564,13 +568,16 @@ static int finish_counters(picles_t* h) {
     return PICLES_OK;
 }
 
+/* tile geometry of the gather for this step, guessed from the previous step's reach */
+static int wide_tiles(const picles_t* h) { return h->last.reach > PR_HY_NARROW && h->last.reach <= PR_HY_WIDE; }
+
 int picles_step_project_remesh(picles_t* h, double t, double dt_model) {
     int rc = need_ready(h, true);
     if (rc) return rc;
     (void)t;
     /* a halo exchange may have run since the advance: ms_project brackets the gather alone */
     CK(cudaEventRecord(h->ev[2], h->stream));
-    launch_project_remesh(h->maps, h->A, h->P, dt_model, h->P.periodic_boundary ? 2 : 1, h->accumulate, h->d_counters, h->stream);
+    launch_project_remesh(h->maps, h->A, h->P, dt_model, h->P.periodic_boundary ? 2 : 1, h->accumulate, wide_tiles(h), h->d_counters, h->stream);
     CK(cudaEventRecord(h->ev[3], h->stream));
     CK(cudaEventRecord(h->ev[4], h->stream));
     CK(cudaGetLastError());
@@ -592,7 +599,7 @@ int picles_step(picles_t* h, double t, double dt_model, const double* u_t, const
     rc = upload_and_advance(h, dt_model, u_t, v_t, u_t1, v_t1);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev[2], h->stream));
-    launch_project_remesh(h->maps, h->A, h->P, dt_model, h->P.periodic_boundary ? 2 : 1, h->accumulate, h->d_counters, h->stream);
+    launch_project_remesh(h->maps, h->A, h->P, dt_model, h->P.periodic_boundary ? 2 : 1, h->accumulate, wide_tiles(h), h->d_counters, h->stream);
     CK(cudaEventRecord(h->ev[3], h->stream));
     CK(cudaEventRecord(h->ev[4], h->stream));
     CK(cudaGetLastError());

@@ -15,20 +15,21 @@
 #ifndef ADV_MIN_BLOCKS
 #define ADV_MIN_BLOCKS 3
 #endif
-/* projection gather + remesh: one block per tile of PR_TX x PR_TY target nodes; the record
-   tile (targets + a halo) is staged in shared memory by TMA */
+/* projection gather + remesh: one block per tile of PR_TX x TY target nodes; the record tile
+   (targets + a halo) is staged in shared memory by TMA.  The TMA box is always PR_BW x PR_BH
+   = 72 x 20 elements; it is cut either as 16 target rows + 2 halo rows (reach <= 2, the common
+   case) or as 12 target rows + 4 halo rows (reach 3-4: the small cells near a pole), chosen
+   per launch from the previous step's reach.  TMA needs the box's first element 16-byte
+   aligned in the inner dimension (measured: profiles/micro/tma_probe.cu — a misaligned start
+   raises "illegal instruction"), so the int32 cell plane forces the x-halo PR_HX to a
+   multiple of 4. */
 #define PR_THREADS 256
 #define PR_TX 64
-#define PR_TY 16
-/* halo cells staged around the targets: PR_HY rows (= the largest reach the tiled path
-   serves) and PR_HX columns.  TMA needs the box's first element 16-byte aligned in the
-   inner dimension (measured: profiles/micro/tma_probe.cu — a misaligned start raises
-   "illegal instruction"), so the int32 cell plane forces PR_HX to a multiple of 4. */
-#define PR_HY 2
 #define PR_HX 4
 #define PR_BW (PR_TX + 2 * PR_HX)
-#define PR_BH (PR_TY + 2 * PR_HY)
-#define PR_NODES_PER_THREAD ((PR_TX * PR_TY) / PR_THREADS)
+#define PR_BH 20
+#define PR_HY_NARROW 2
+#define PR_HY_WIDE 4
 #ifndef PR_MIN_BLOCKS
 #define PR_MIN_BLOCKS 3
 #endif
@@ -59,6 +60,7 @@ struct DeviceArrays {
     double* pc;                      /* great-circle coefficient plane, or nullptr */
     double* rec[5];                  /* deposit records: e, m_x, m_y, w_x(ceil), w_y(ceil) */
     int32_t* cell;                   /* packed floor offsets + class, PH_CELL_INVALID if none */
+    int32_t* rowreach;               /* per record row (ny + 2*halo): max reach of its deposits this step */
     double* S[3];                    /* State planes e, m_x, m_y */
 };
 
@@ -68,7 +70,7 @@ struct DeviceCounters {
     int32_t reach;        /* max reach of this strip's own deposits */
     int32_t max_attempts;
     int32_t reach_halo;   /* max reach of the records received into the halo rows */
-    int32_t pad_;
+    int32_t class1;       /* a deposit of the second class (a mask-3 particle of a periodic model) exists */
 };
 
 void launch_seed(const DeviceArrays& A, const picles_params_t& P, const double* u0, const double* v0, int sms,
@@ -83,7 +85,7 @@ struct ProjectMaps {
 int project_remesh_smem_bytes();
 cudaError_t project_remesh_configure();
 void launch_project_remesh(const ProjectMaps& maps, const DeviceArrays& A, const picles_params_t& P, double DT,
-                           int n_classes, int accumulate, DeviceCounters* dc, cudaStream_t st);
+                           int n_classes, int accumulate, int wide, DeviceCounters* dc, cudaStream_t st);
 void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cudaStream_t st);
 void launch_halo_pack(const DeviceArrays& A, char* lo, char* hi, int sms, cudaStream_t st);
 void launch_halo_unpack(const DeviceArrays& A, const char* lo, const char* hi, DeviceCounters* dc, int sms, cudaStream_t st);

@@ -150,24 +150,31 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int6
         advance_particle(P, p, A.mask[l], DT, A.u_t[l], A.v_t[l], A.u_t1[l], A.v_t1[l], M, pc, r, c, K);
         store_particle(A, l, p);
         store_record(A, le, r);
+        if (r.cell != PH_CELL_INVALID) {
+            /* per-row reach (lets the gather size its window tile by tile) and class presence */
+            const int rr = cell_reach(r.cell);
+            int32_t* slot = &A.rowreach[le / A.rp];
+            if (rr > __ldcg(slot)) atomicMax(slot, rr);
+            if (((uint32_t)r.cell >> 28) & 1u) dc->class1 = 1;
+        }
     }
     tally_flush(c, dc);
 }
 
 /* ---- projection gather + remesh ---------------------------------------------------- */
 /*
- * One block per tile of PR_TX x PR_TY target nodes.  One thread arms an mbarrier and issues
+ * One block per tile of PR_TX x TY target nodes (TY = PR_BH - 2*HY).  One thread arms an mbarrier and issues
  * six TMA tile loads (cp.async.bulk.tensor.2d): the five record planes and the cell plane
- * over the targets plus a halo of PR_HX x PR_HY cells.  Boxes that stick out of the planes are
+ * over the targets plus a halo of PR_HX x HY cells.  Boxes that stick out of the planes are
  * zero-filled by the TMA unit; a zero cell decodes to an offset that never matches, i.e.
  * "no deposit", which is exactly what lies beyond a non-periodic edge.  While the tiles are in
- * flight every thread loads the remesh inputs of its PR_NODES_PER_THREAD nodes (flags, wind at
+ * flight every thread loads the remesh inputs of its 3-4 nodes (flags, wind at
  * t), so the node loop below touches HBM only to store.
  *
  * Per node: sum the window from shared memory (gather_window, compile-time offsets) in the
  * reference's order, store State, and — the node value still being in registers — run
  * NodeToParticle! for the node's particle.  Nodes whose window crosses a periodic seam or the
- * tripolar fold, and steps whose reach exceeds PR_HY, take gather_node() on the planes in HBM.
+ * tripolar fold, and tiles whose reach exceeds HY, take gather_node() on the planes in HBM.
  */
 /* GetVariablesAtVertex with results in registers (hot: remesh branch A) */
 struct Vtx3 { double u0, u1, u2; };
@@ -197,10 +204,33 @@ struct PRTile {
     int32_t cell[PR_BH * PR_BW];
     unsigned long long mbar;
 };
-static_assert(PR_NODES_PER_THREAD <= 4, "flags of a thread's nodes are packed in 32 bits");
-static_assert((PR_BH * PR_BW * 8) % 128 == 0 && (PR_BW * 4) % 16 == 0 && PR_HX % 4 == 0 && PR_TX % 4 == 0 && PR_HX >= PR_HY,
-              "TMA tile alignment");
+static_assert((PR_BH * PR_BW * 8) % 128 == 0 && (PR_BW * 4) % 16 == 0 && PR_HX % 4 == 0 && PR_TX % 4 == 0 &&
+              PR_HX >= PR_HY_WIDE && (PR_BH - 2 * PR_HY_WIDE) % (PR_THREADS / PR_TX) == 0 &&
+              (PR_BH - 2 * PR_HY_NARROW) % (PR_THREADS / PR_TX) == 0 && (PR_BH - 2 * PR_HY_NARROW) / (PR_THREADS / PR_TX) <= 4,
+              "TMA tile alignment / nodes per thread (their flags are packed in 32 bits)");
 #define PR_TILE_BYTES (5 * PR_BH * PR_BW * 8 + PR_BH * PR_BW * 4)
+
+/* window of run-time reach R from a staged tile (reach 3-4 of the wide tile geometry) */
+template <int NCLS>
+__device__ __forceinline__ void gather_window_rt(const PRTile& T, int base, int R, double& s0, double& s1, double& s2) {
+    for (int cls = 0; cls < NCLS; cls++)
+        for (int dj = -R; dj <= R; dj++)
+            for (int di = -R; di <= R; di++) {
+                const int le = base + dj * PR_BW + di;
+                const uint32_t cell = (uint32_t)T.cell[le];
+                const unsigned dx = (unsigned)(PH_CELL_BIAS - di) - (cell & 0x3fffu);
+                const unsigned dy = (unsigned)(PH_CELL_BIAS - dj) - ((cell >> 14) & 0x3fffu);
+                if (dx > 1u || dy > 1u) continue;
+                if (NCLS > 1 && (int)((cell >> 28) & 1u) != cls) continue;
+                const double wxc = T.rec[3][le], wyc = T.rec[4][le];
+                const double wx = dx ? wxc : 1.0 - wxc;
+                const double wy = dy ? wyc : 1.0 - wyc;
+                const double w = wx * wy;
+                s0 += w * T.rec[0][le];
+                s1 += w * T.rec[1][le];
+                s2 += w * T.rec[2][le];
+            }
+}
 
 /*
  * Everything of the node loop that is not "reach-1 window from the tile, then remesh branch A"
@@ -210,15 +240,16 @@ static_assert((PR_BH * PR_BW * 8) % 128 == 0 && (PR_BW * 4) % 16 == 0 && PR_HX %
  * gathered but its remesh is not branch A (wind-sea reseed or switch-off).  Returns the remesh
  * branch counts (A, B, C, D) of the nodes handled here.
  */
+template <int HY>
 __device__ __noinline__ int4 cold_nodes(const DeviceArrays* Ap, const picles_params_t* Pp, const PRTile* Tp, uint32_t mask,
-                                        uint32_t fl_all, int i, int jr0, int tx, int ty, int R, int n_classes, int accumulate,
-                                        bool tiled, double DT) {
+                                        uint32_t fl_all, int i, int jr0, int tx, int ty, int R, int Rt, int n_classes,
+                                        int accumulate, bool tiled, double DT) {
     const DeviceArrays& A = *Ap;
     const picles_params_t& P = *Pp;
     const PRTile& T = *Tp;
     Tally c;
     tally_zero(c);
-    for (int k = 0; k < PR_NODES_PER_THREAD; k++) {
+    for (int k = 0; k < (PR_BH - 2 * HY) / (PR_THREADS / PR_TX); k++) {
         if (!(mask & (0x11u << k))) continue;
         const int jl = ty + k * (PR_THREADS / PR_TX);
         const int jr = jr0 + jl;
@@ -233,10 +264,9 @@ __device__ __noinline__ int4 cold_nodes(const DeviceArrays* Ap, const picles_par
             const bool fast_y = (A.by == PICLES_BND_NONPERIODIC) || (A.by == PICLES_BND_PERIODIC && J > R && J <= A.Ny - R) ||
                                 (A.by == PICLES_BND_TRIPOLAR_NORTH && J <= A.Ny - R);
             if (tiled && fast_x && fast_y) {
-                const int64_t base = (int64_t)(jl + PR_HY) * PR_BW + (tx + PR_HX);
-                if (n_classes == 1) gather_window<2, PR_BW, 1>(T.rec[0], T.rec[1], T.rec[2], T.rec[3], T.rec[4], T.cell, PR_BW, base, s0, s1, s2);
-                else if (R <= 1) gather_window<1, PR_BW, 2>(T.rec[0], T.rec[1], T.rec[2], T.rec[3], T.rec[4], T.cell, PR_BW, base, s0, s1, s2);
-                else gather_window<2, PR_BW, 2>(T.rec[0], T.rec[1], T.rec[2], T.rec[3], T.rec[4], T.cell, PR_BW, base, s0, s1, s2);
+                const int base = (jl + HY) * PR_BW + (tx + PR_HX);
+                if (n_classes == 1) gather_window_rt<1>(T, base, Rt, s0, s1, s2);
+                else gather_window_rt<2>(T, base, Rt, s0, s1, s2);
             } else {
                 RecView V;
                 V.Nx = A.Nx; V.Ny = A.Ny; V.bx = A.bx; V.by = A.by; V.j0 = A.j0; V.ny = A.ny; V.halo = A.halo; V.pitch = A.rp;
@@ -266,6 +296,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
                  : "memory");
 }
 
+template <int HY>
 __global__ void __launch_bounds__(PR_THREADS, PR_MIN_BLOCKS)
 k_project_remesh(const __grid_constant__ ProjectMaps maps, const __grid_constant__ DeviceArrays A,
                  const __grid_constant__ picles_params_t P, double DT, int n_classes,
@@ -273,26 +304,42 @@ k_project_remesh(const __grid_constant__ ProjectMaps maps, const __grid_constant
     extern __shared__ __align__(128) unsigned char pr_smem[];
     /* TMA destinations must be 128-byte aligned whatever static shared memory precedes them */
     PRTile& T = *reinterpret_cast<PRTile*>(pr_smem + ((128u - (smem_u32(pr_smem) & 127u)) & 127u));
-    const int i0 = blockIdx.x * PR_TX, jr0 = blockIdx.y * PR_TY;
+    constexpr int TY = PR_BH - 2 * HY;                 /* target rows of a tile */
+    constexpr int NPT = TY / (PR_THREADS / PR_TX);     /* nodes per thread */
+    const int i0 = blockIdx.x * PR_TX, jr0 = blockIdx.y * TY;
     /* deposits landing on this strip come from its own particles (reach) and from the
        neighbours' rows received into the halo (reach_halo) */
     int R = min(max(dc->reach, dc->reach_halo), PH_REACH_MAX);
     if (A.ny != A.Ny) R = min(R, A.halo); /* strips: the host rejects reach > halo (PICLES_ERR_HALO) */
-    const bool tiled = (R <= PR_HY);
-    if (tiled) {
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&T.mbar)));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    /* two passes over the window are only needed when deposits of both classes exist */
+    if (!dc->class1) n_classes = 1;
+    /* reach of the records that can land on this tile: rows within R of its targets.  A few
+       fast rows (the shrinking cells near a pole) then do not widen every tile's window. */
+    __shared__ int s_rt;
+    if (threadIdx.x < 32) {
+        const int first = jr0 + A.halo - R, count = TY + 2 * R, rows = A.ny + 2 * A.halo;
+        int rt = 0;
+        for (int q = threadIdx.x; q < count; q += 32) {
+            const int row = first + q;
+            if (row >= 0 && row < rows) rt = max(rt, A.rowreach[row]);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&T.mbar)), "r"(PR_TILE_BYTES)
-                         : "memory");
-            const int c0 = i0 - PR_HX, c1 = jr0 + A.halo - PR_HY;
+        rt = warp_max(rt);
+        if (threadIdx.x == 0) s_rt = rt;
+    }
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&T.mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int Rt = min(s_rt, R);       /* window of this tile's fast-zone nodes */
+    const bool tiled = (Rt <= HY);
+    if (tiled && threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&T.mbar)), "r"(PR_TILE_BYTES)
+                     : "memory");
+        const int c0 = i0 - PR_HX, c1 = jr0 + A.halo - HY;
 #pragma unroll
-            for (int k = 0; k < 5; k++) tma_load_2d(T.rec[k], &maps.rec[k], c0, c1, &T.mbar);
-            tma_load_2d(T.cell, &maps.cell, c0, c1, &T.mbar);
-        }
+        for (int k = 0; k < 5; k++) tma_load_2d(T.rec[k], &maps.rec[k], c0, c1, &T.mbar);
+        tma_load_2d(T.cell, &maps.cell, c0, c1, &T.mbar);
     }
     /* the flags of my nodes, issued while the tiles are in flight (branch A of the remesh
        needs nothing else; the wind is only read on the rare reseed / switch-off branches) */
@@ -300,7 +347,7 @@ k_project_remesh(const __grid_constant__ ProjectMaps maps, const __grid_constant
     const int i = i0 + tx;
     uint32_t fl_all = 0;
 #pragma unroll
-    for (int k = 0; k < PR_NODES_PER_THREAD; k++) {
+    for (int k = 0; k < NPT; k++) {
         const int jr = jr0 + ty + k * (PR_THREADS / PR_TX);
         if (i < A.Nx && jr < A.ny) fl_all |= (uint32_t)A.flags[(int64_t)jr * A.Nx + i] << (8 * k);
     }
@@ -315,9 +362,9 @@ k_project_remesh(const __grid_constant__ ProjectMaps maps, const __grid_constant
     }
     int nA = 0; /* remesh branch-A count of this thread */
     uint32_t cold = 0; /* nodes deferred to cold_nodes() */
-    const bool hot_window = tiled && (n_classes == 1) && (R <= 1);
+    const bool hot_window = tiled && (n_classes == 1);
 #pragma unroll 1
-    for (int k = 0; k < PR_NODES_PER_THREAD; k++) {
+    for (int k = 0; k < NPT; k++) {
         const int jl = ty + k * (PR_THREADS / PR_TX); /* row inside the tile */
         const int jr = jr0 + jl;
         if (i >= A.Nx || jr >= A.ny) continue;
@@ -329,8 +376,10 @@ k_project_remesh(const __grid_constant__ ProjectMaps maps, const __grid_constant
         const int64_t l = (int64_t)jr * A.Nx + i;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         if (accumulate) { s0 = A.S[0][l]; s1 = A.S[1][l]; s2 = A.S[2][l]; }
-        const int64_t base = (int64_t)(jl + PR_HY) * PR_BW + (tx + PR_HX);
-        gather_window<1, PR_BW, 1>(T.rec[0], T.rec[1], T.rec[2], T.rec[3], T.rec[4], T.cell, PR_BW, base, s0, s1, s2);
+        const int64_t base = (int64_t)(jl + HY) * PR_BW + (tx + PR_HX);
+        if (Rt <= 1) gather_window<1, PR_BW, 1>(T.rec[0], T.rec[1], T.rec[2], T.rec[3], T.rec[4], T.cell, PR_BW, base, s0, s1, s2);
+        else if (Rt == 2) gather_window<2, PR_BW, 1>(T.rec[0], T.rec[1], T.rec[2], T.rec[3], T.rec[4], T.cell, PR_BW, base, s0, s1, s2);
+        else gather_window_rt<1>(T, (int)base, Rt, s0, s1, s2);
         A.S[0][l] = s0;
         A.S[1][l] = s1;
         A.S[2][l] = s2;
@@ -350,7 +399,7 @@ k_project_remesh(const __grid_constant__ ProjectMaps maps, const __grid_constant
     }
     int nB = 0, nC = 0, nD = 0;
     if (cold) {
-        int4 cc = cold_nodes(&A, &P, &T, cold, fl_all, i, jr0, tx, ty, R, n_classes, accumulate, tiled, DT);
+        int4 cc = cold_nodes<HY>(&A, &P, &T, cold, fl_all, i, jr0, tx, ty, R, Rt, n_classes, accumulate, tiled, DT);
         nA += cc.x; nB = cc.y; nC = cc.z; nD = cc.w;
     }
     /* branch counts: one warp reduction each, one global atomic per warp and non-zero count */
@@ -407,7 +456,13 @@ __global__ void k_halo_unpack(DeviceArrays A, const char* __restrict__ recv_lo, 
         int32_t clo = ((const int32_t*)(recv_lo + 5 * m * 8))[q], chi = ((const int32_t*)(recv_hi + 5 * m * 8))[q];
         A.cell[lo] = clo;
         A.cell[hi] = chi;
-        reach = max(reach, max(cell_reach(clo), cell_reach(chi)));
+        const int rlo = cell_reach(clo), rhi = cell_reach(chi);
+        const int row = (int)(q / A.rp);
+        if (rlo > 0 && rlo > __ldcg(&A.rowreach[row])) atomicMax(&A.rowreach[row], rlo);
+        if (rhi > 0 && rhi > __ldcg(&A.rowreach[A.ny + A.halo + row])) atomicMax(&A.rowreach[A.ny + A.halo + row], rhi);
+        if ((clo != PH_CELL_INVALID && (((uint32_t)clo >> 28) & 1u)) || (chi != PH_CELL_INVALID && (((uint32_t)chi >> 28) & 1u)))
+            dc->class1 = 1;
+        reach = max(reach, max(rlo, rhi));
     }
     reach = warp_max(reach);
     if ((threadIdx.x & 31) == 0 && reach) atomicMax(&dc->reach_halo, reach);
@@ -566,12 +621,18 @@ void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, 
 
 int project_remesh_smem_bytes() { return (int)sizeof(PRTile) + 128; }
 cudaError_t project_remesh_configure() {
-    return cudaFuncSetAttribute(k_project_remesh, cudaFuncAttributeMaxDynamicSharedMemorySize, project_remesh_smem_bytes());
+    cudaError_t e = cudaFuncSetAttribute(k_project_remesh<PR_HY_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, project_remesh_smem_bytes());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_project_remesh<PR_HY_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, project_remesh_smem_bytes());
 }
+/* wide: cut the 72 x 20 box as 12 target rows + 4 halo rows (previous step's reach was 3-4)
+   instead of 16 + 2; a wrong guess only sends tiles through the generic gather */
 void launch_project_remesh(const ProjectMaps& maps, const DeviceArrays& A, const picles_params_t& P, double DT,
-                           int n_classes, int accumulate, DeviceCounters* dc, cudaStream_t st) {
-    dim3 grid((A.Nx + PR_TX - 1) / PR_TX, (A.ny + PR_TY - 1) / PR_TY);
-    k_project_remesh<<<grid, PR_THREADS, project_remesh_smem_bytes(), st>>>(maps, A, P, DT, n_classes, accumulate, dc);
+                           int n_classes, int accumulate, int wide, DeviceCounters* dc, cudaStream_t st) {
+    const int TY = PR_BH - 2 * (wide ? PR_HY_WIDE : PR_HY_NARROW);
+    dim3 grid((A.Nx + PR_TX - 1) / PR_TX, (A.ny + TY - 1) / TY);
+    if (wide) k_project_remesh<PR_HY_WIDE><<<grid, PR_THREADS, project_remesh_smem_bytes(), st>>>(maps, A, P, DT, n_classes, accumulate, dc);
+    else k_project_remesh<PR_HY_NARROW><<<grid, PR_THREADS, project_remesh_smem_bytes(), st>>>(maps, A, P, DT, n_classes, accumulate, dc);
 }
 
 void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cudaStream_t st) {
