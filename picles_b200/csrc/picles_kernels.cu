@@ -595,15 +595,6 @@ void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, 
     if (l_end <= l_begin) return;
     int g = grid_for(l_end - l_begin, ADV_THREADS, sms, ADV_MIN_BLOCKS);
     bool pn = (A.M[0] != nullptr);
-    /* the register file, not shared memory, must be what bounds the resident blocks: ask for
-       the largest shared-memory carveout (the driver's default split left room for fewer
-       blocks than the registers allow when blocks are small; profiles/README.md) */
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_advance<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_advance<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
-    }
     size_t dyn = 0;
 #ifdef ADV_OCCUPANCY_EXPERIMENT /* profiles/: unused dynamic shared memory caps the resident blocks per SM */
     static int dyn_env = -1;

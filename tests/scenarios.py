@@ -113,6 +113,81 @@ def sc_tripolar_propagation_only():
     return g, P, _const(5.0, 5.0), 1800.0, 5
 
 
+def sc_emax_clamp():
+    """advance!: lne > log_energy_maximum -> clamp + pending dt reset (mapping_2D.jl:222-233)."""
+    g = cartesian_grid(20, 16)
+    return g, default_params(log_energy_maximum=float(np.log(2e-3))), _const(14.0, 9.0), 900.0, 6
+
+
+def sc_maxiters():
+    """integrator stops with retcode MaxIters for every particle (status code, not a call
+    failure) and stays dead on the following steps; remesh keeps resetting u from the nodes."""
+    g = cartesian_grid(18, 14)
+    P = default_params()
+    P.maxiters = 4
+    return g, P, _const(10.0, 10.0), 600.0, 4
+
+
+def sc_dtmin_no_force():
+    """force_dtmin=false with a large dtmin: DtLessThanMin retcode."""
+    g = cartesian_grid(16, 12)
+    return g, default_params(force_dtmin=False, dt=1e-3, dtmin=10.0), _const(10.0, 10.0), 600.0, 3
+
+
+def sc_nan_wind():
+    """a patch of NaN wind: integration goes NaN, advance! reseeds from the (NaN) wind, the NaN
+    charge poisons the four nodes it is deposited on and spreads by one cell per step."""
+    g = cartesian_grid(24, 20)
+
+    def wind(t):
+        u = np.full((20, 24), 10.0)
+        v = np.full((20, 24), 6.0)
+        if t > 0:
+            u[8:10, 10:13] = np.nan
+        return u, v
+
+    return g, default_params(), wind, 600.0, 4
+
+
+def sc_nan_defaults():
+    """ParticleDefaults with a NaN energy: the integrator gives up (NaN dt), advance! takes the
+    NaN fix-up (mapping_2D.jl:196-209) and the NaN charge poisons the nodes it lands on."""
+    g = cartesian_grid(14, 10)
+    return g, default_params(defaults=[float("nan"), 0.5, 0.4, 0.0, 0.0]), _const(10.0, 6.0), 600.0, 3
+
+
+def sc_inf_defaults():
+    """ParticleDefaults with an infinite energy: the Inf fix-up (mapping_2D.jl:211-220)."""
+    g = cartesian_grid(14, 10)
+    return g, default_params(defaults=[float("inf"), 0.5, 0.4, 0.0, 0.0]), _const(10.0, 6.0), 600.0, 3
+
+
+def sc_all_land():
+    """no ocean at all: nothing is iterated, State stays zero."""
+    g = cartesian_grid(12, 9, ocean=np.zeros((9, 12), np.uint8))
+    return g, default_params(), _const(10.0, 10.0), 600.0, 2
+
+
+def sc_calm():
+    """wind below sqrt(2) everywhere: minimal particles, seeded off, never switched on
+    (remesh branch D only), nothing deposited."""
+    g = cartesian_grid(15, 11)
+    return g, default_params(), _const(0.6, -0.5), 600.0, 3
+
+
+def sc_tiny():
+    """3 x 3: a single interior particle whose deposits fall on grid-boundary nodes."""
+    g = cartesian_grid(3, 3)
+    return g, default_params(), _const(10.0, -10.0), 600.0, 4
+
+
+def sc_odd_periodic_strip():
+    """periodic in both axes with odd sizes and Nx not a multiple of 4 (pitched record rows),
+    fast particles: reach 2-3, wrap in x and y, two deposit classes absent."""
+    g = cartesian_grid(17, 13, dx=500.0, dy=400.0, bx=BND_PERIODIC, by=BND_PERIODIC)
+    return g, default_params(periodic_boundary=True), _const(-13.0, 11.0), 1200.0, 5
+
+
 SCENARIOS = {
     "minimal": sc_minimal,
     "minimal_dp5": sc_minimal_dp5,
@@ -124,6 +199,16 @@ SCENARIOS = {
     "growing_winds_persist": sc_growing_winds_persist,
     "tripolar": sc_tripolar,
     "tripolar_propagation_only": sc_tripolar_propagation_only,
+    "emax_clamp": sc_emax_clamp,
+    "maxiters": sc_maxiters,
+    "dtmin_no_force": sc_dtmin_no_force,
+    "nan_wind": sc_nan_wind,
+    "nan_defaults": sc_nan_defaults,
+    "inf_defaults": sc_inf_defaults,
+    "all_land": sc_all_land,
+    "calm": sc_calm,
+    "tiny": sc_tiny,
+    "odd_periodic_strip": sc_odd_periodic_strip,
 }
 
 

@@ -28,8 +28,9 @@ def test_strips_bit_exact(name, nstrips, halo):
 def test_scenarios_exercise_their_paths():
     """Guard against vacuous parity: the scenarios must actually hit wrap, fold, off
     particles, both remesh branches and reach >= 2."""
-    seen = dict(reach2=False, D=False, B=False, reseed=False, rejects=False)
-    for name in ("periodic_grid", "growing_winds", "growing_winds_persist", "tripolar"):
+    seen = dict(reach2=False, D=False, B=False, reseed=False, rejects=False, fixups=False, failed=False)
+    for name in ("periodic_grid", "growing_winds", "growing_winds_persist", "tripolar", "emax_clamp", "maxiters",
+                 "dtmin_no_force", "nan_wind", "nan_defaults", "inf_defaults", "odd_periodic_strip"):
         g, P, wind, DT, n = SCENARIOS[name]()
         o = make_oracle(g, P)
         u0, v0 = wind(0.0)
@@ -44,6 +45,8 @@ def test_scenarios_exercise_their_paths():
             seen["B"] |= c["n_remesh_B"] > 0
             seen["reseed"] |= c["n_reseed_advance"] > 0
             seen["rejects"] |= c["n_rejects"] > 0
+            seen["fixups"] |= c["n_fixups"] > 0
+            seen["failed"] |= c["n_failed"] > 0
     assert all(seen.values()), seen
 
 
