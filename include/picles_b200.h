@@ -268,6 +268,22 @@ int picles_get_counters(picles_t* h, picles_counters_t* c);
    per-step scalar read-back */
 int picles_state_energy_sum(picles_t* h, double* sum_e);
 
+/* ---- output path (the "next" row after the step itself) ------------------------- */
+/* derived fields of the node State, computed on the device, any output may be NULL
+   (ny_local*Nx each):  Hs = 4*sqrt(e)                     src/visualization/movie_2D.jl:50
+                        c_x, c_y = m*e/(2|m|^2)            GetGroupVelocity, src/Operators/core_2D.jl:138-147 */
+int picles_get_fields(picles_t* h, double* Hs, double* c_x, double* c_y);
+/* pinned host memory for asynchronous transfers (hosts without their own CUDA binding) */
+int picles_host_alloc(void** p, int64_t nbytes);
+int picles_host_free(void* p);
+/* asynchronous State snapshot for the stores of run! (CashStore / StateStore pushes,
+   src/Simulations/run.jl:94-112): returns at once; State is copied device-to-device on the
+   compute stream and device-to-host on a second stream while the following steps run.
+   S_host (3 planes, pinned for true overlap) is valid after picles_snapshot_wait; one
+   snapshot may be in flight per handle (a second begin waits for the first). */
+int picles_snapshot_begin(picles_t* h, double* S_host);
+int picles_snapshot_wait(picles_t* h);
+
 /* device pointers for zero-copy consumers (torch / CUDA.jl): planes as above */
 int picles_state_dev(picles_t* h, double** S_dev /* out: 3 plane pointers e, m_x, m_y */);
 int picles_wind_dev(picles_t* h, double** u_t_dev, double** v_t_dev,

@@ -60,6 +60,7 @@ def load(variant: str = "default"):
     lib.oracle_get_counters.argtypes = [vp, C.POINTER(PiclesCounters)]
     lib.oracle_n_ocean.restype = i64
     lib.oracle_n_ocean.argtypes = [vp]
+    lib.oracle_fields.argtypes = [vp, vp, vp, vp]
     lib.oracle_stiff_triggers.restype = i64
     lib.oracle_stiff_triggers.argtypes = [vp]
     lib.oracle_get_ocean_points.argtypes = [vp, vp]
@@ -171,6 +172,12 @@ class Oracle:
         idx = np.empty(n, dtype=np.int64)
         self.lib.oracle_get_ocean_points(self.h, _dp(idx))
         return idx
+
+    def fields(self):
+        sh = (self.Ny, self.Nx)
+        Hs, cx, cy = np.empty(sh), np.empty(sh), np.empty(sh)
+        self.lib.oracle_fields(self.h, _dp(Hs), _dp(cx), _dp(cy))
+        return dict(Hs=Hs, c_x=cx, c_y=cy)
 
     def stiff_triggers(self):
         return int(self.lib.oracle_stiff_triggers(self.h))

@@ -783,6 +783,17 @@ void oracle_get_aux(const oracle_t* o, double* qold, int64_t* iter) {
 }
 void oracle_get_counters(const oracle_t* o, picles_counters_t* c) { *c = o->C; }
 int64_t oracle_n_ocean(const oracle_t* o) { return o->n_ocean; }
+/* derived output fields: Hs = 4*sqrt(e) (movie_2D.jl:50), GetGroupVelocity (core_2D.jl:138-147) */
+void oracle_fields(const oracle_t* o, double* Hs, double* cx, double* cy) {
+    int64_t n = (int64_t)o->Nx * o->Ny;
+    for (int64_t l = 0; l < n; l++) {
+        double e = o->S[l], mx = o->S[n + l], my = o->S[2 * n + l];
+        double m_amp = sqrt(mx * mx + my * my);
+        Hs[l] = 4.0 * sqrt(e);
+        cx[l] = mx * e / (2.0 * (m_amp * m_amp));
+        cy[l] = my * e / (2.0 * (m_amp * m_amp));
+    }
+}
 int64_t oracle_stiff_triggers(const oracle_t* o) { return o->stiff_triggers; }
 void oracle_get_ocean_points(const oracle_t* o, int64_t* idx) { memcpy(idx, o->ocean, o->n_ocean * sizeof(int64_t)); }
 

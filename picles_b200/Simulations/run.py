@@ -93,19 +93,41 @@ def run(sim, store=False, pickup=False, cash_store=False, debug=False):
     sim.running = sim.stop_time >= sim.model.clock.time
     if not sim.running:
         log.info("stop_time exceeded, run not executed")
+    eng = sim.model.engine
+    # CashStore pushes are asynchronous snapshots where the engine offers them (B200Engine):
+    # the device-to-host copy of step n overlaps the integration of step n+1
+    snap = hasattr(eng, "snapshot_begin") and cash_store
+    pending = None
+
+    def collect():
+        nonlocal pending
+        if pending is not None:
+            eng.snapshot_wait()
+            sim.store.store.append(np.array(pending.transpose(2, 1, 0), copy=True))   # (Nx, Ny, 3) like model.State
+            sim.store.iteration += 1
+            pending = None
+
     if cash_store:
         sim.store = CashStore([], 1)
         sim.store.iteration += 1
         sim.store.store.append(np.array(sim.model.State, copy=True))
+        if snap:
+            stage = eng.pinned_state_buffer()
     while sim.running:
         time_step(sim.model, sim.Δt, debug=debug, zero_state_first=True)
         if debug and len(sim.model.FailedCollection) > 0:
             log.info("debug mode: found failed particles: %s; break", sim.model.FailedCollection)
             break
         if cash_store:
-            sim.store.store.append(np.array(sim.model.State, copy=True))
-            sim.store.iteration += 1
+            if snap:
+                collect()
+                eng.snapshot_begin(stage)
+                pending = stage
+            else:
+                sim.store.store.append(np.array(sim.model.State, copy=True))
+                sim.store.iteration += 1
         sim.running = sim.stop_time >= sim.model.clock.time
         if sim.verbose:
             log.info("%s", sim.model.clock)
+    collect()
     sim.run_wall_time += 1e-9 * (time.perf_counter_ns() - t0)

@@ -46,6 +46,10 @@ struct picles_handle {
     int64_t n_active = 0;
     bool timing_valid = false;
     int accumulate = 0; /* PICLES_OPT_ACCUMULATE_STATE */
+    double* snap = nullptr;       /* staging copy of State for asynchronous snapshots (3 planes) */
+    cudaStream_t snap_stream = nullptr; /* D2H of snapshots: its own stream, so wind uploads are not queued behind it */
+    cudaEvent_t snap_ev[2] = {nullptr, nullptr}; /* staging copy done / D2H done */
+    bool snap_pending = false;
     void* comm = nullptr; /* ncclComm_t of the strip communicator */
     int comm_rank = -1, comm_size = 0;
     char err[512];
@@ -120,10 +124,13 @@ static int make_project_maps(picles_t* h) {
 }
 
 static void free_grid(picles_t* h) {
+    if (h->snap_stream) cudaStreamSynchronize(h->snap_stream); /* a snapshot may still read the staging copy */
     for (void* p : h->allocs) cudaFree(p);
     h->allocs.clear();
     memset(&h->A, 0, sizeof h->A);
     h->send_lo = h->send_hi = h->recv_lo = h->recv_hi = nullptr;
+    h->snap = nullptr;
+    h->snap_pending = false;
     h->have_grid = h->seeded = h->winds_loaded = false;
 }
 
@@ -211,9 +218,11 @@ int picles_create(picles_t** out, int device_id) {
     CK(cudaSetDevice(device_id));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->snap_stream, cudaStreamNonBlocking));
     for (int k = 0; k <= PIPE_CHUNKS; k++) CK(cudaEventCreateWithFlags(&h->pev[k], cudaEventDisableTiming));
     for (int k = 0; k < 5; k++) CK(cudaEventCreate(&h->ev[k]));
     for (int k = 0; k < 2; k++) CK(cudaEventCreate(&h->tev[k]));
+    for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&h->snap_ev[k], cudaEventDisableTiming));
     CK(cudaMalloc((void**)&h->d_counters, sizeof(DeviceCounters)));
     CK(cudaMallocHost((void**)&h->h_counters, sizeof(DeviceCounters)));
     CK(cudaMalloc((void**)&h->d_partial, ENERGY_BLOCKS * sizeof(double)));
@@ -226,6 +235,8 @@ int picles_destroy(picles_t* h) {
     if (!h) return PICLES_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    if (h->snap_stream) cudaStreamSynchronize(h->snap_stream);
     if (h->comm && g_nccl.destroy) { g_nccl.destroy(h->comm); h->comm = nullptr; }
     free_grid(h);
     if (h->d_counters) cudaFree(h->d_counters);
@@ -236,9 +247,12 @@ int picles_destroy(picles_t* h) {
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     for (int k = 0; k < 2; k++)
         if (h->tev[k]) cudaEventDestroy(h->tev[k]);
+    for (int k = 0; k < 2; k++)
+        if (h->snap_ev[k]) cudaEventDestroy(h->snap_ev[k]);
     for (int k = 0; k <= PIPE_CHUNKS; k++)
         if (h->pev[k]) cudaEventDestroy(h->pev[k]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->snap_stream) cudaStreamDestroy(h->snap_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return PICLES_OK;
@@ -798,6 +812,74 @@ int picles_measure_hbm_copy(picles_t* h, int mib, double* gbs) {
     cudaFree(b);
     CK(cudaGetLastError());
     *gbs = best;
+    return PICLES_OK;
+}
+
+/* ---- output path ------------------------------------------------------------------------ */
+int picles_get_fields(picles_t* h, double* Hs, double* c_x, double* c_y) {
+    int rc = need_ready(h, false);
+    if (rc) return rc;
+    const DeviceArrays& A = h->A;
+    const int64_t n = (int64_t)A.Nx * A.ny;
+    const int nout = (Hs != nullptr) + (c_x != nullptr) + (c_y != nullptr);
+    if (nout == 0) return PICLES_OK;
+    double* d = nullptr;
+    if (cudaMalloc((void**)&d, (size_t)n * 8 * nout) != cudaSuccess) return fail(h, PICLES_ERR_ALLOC, "cannot allocate the field planes");
+    double* p = d;
+    double* dHs = Hs ? p : nullptr; if (Hs) p += n;
+    double* dcx = c_x ? p : nullptr; if (c_x) p += n;
+    double* dcy = c_y ? p : nullptr;
+    launch_fields(n, A.S[0], A.S[1], A.S[2], dHs, dcx, dcy, h->sms, h->stream);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && Hs) e = cudaMemcpyAsync(Hs, dHs, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && c_x) e = cudaMemcpyAsync(c_x, dcx, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && c_y) e = cudaMemcpyAsync(c_y, dcy, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(h, PICLES_ERR_CUDA, "picles_get_fields: %s", cudaGetErrorString(e));
+    return PICLES_OK;
+}
+
+int picles_host_alloc(void** p, int64_t nbytes) {
+    picles_t* h = nullptr;
+    if (!p || nbytes < 1) return fail(nullptr, PICLES_ERR_ARG, "picles_host_alloc: bad argument");
+    CK(cudaMallocHost(p, (size_t)nbytes));
+    return PICLES_OK;
+}
+int picles_host_free(void* p) {
+    picles_t* h = nullptr;
+    if (p) CK(cudaFreeHost(p));
+    return PICLES_OK;
+}
+
+/* State snapshot that does not stall the stepping: a device-to-device copy into a staging
+   buffer on the compute stream (ordered before the next step overwrites State), then the
+   device-to-host copy on the copy stream while the next steps run. */
+int picles_snapshot_begin(picles_t* h, double* S_host) {
+    int rc = need_ready(h, false);
+    if (rc) return rc;
+    if (!S_host) return fail(h, PICLES_ERR_ARG, "null output");
+    if (h->snap_pending) {
+        rc = picles_snapshot_wait(h);
+        if (rc) return rc;
+    }
+    const int64_t n = (int64_t)h->A.Nx * h->A.ny;
+    if (!h->snap) DALLOC(h->snap, 3 * n);
+    for (int k = 0; k < 3; k++)
+        CK(cudaMemcpyAsync(h->snap + k * n, h->A.S[k], (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaEventRecord(h->snap_ev[0], h->stream));
+    CK(cudaStreamWaitEvent(h->snap_stream, h->snap_ev[0], 0));
+    CK(cudaMemcpyAsync(S_host, h->snap, (size_t)n * 8 * 3, cudaMemcpyDeviceToHost, h->snap_stream));
+    CK(cudaEventRecord(h->snap_ev[1], h->snap_stream));
+    h->snap_pending = true;
+    return PICLES_OK;
+}
+int picles_snapshot_wait(picles_t* h) {
+    if (!h) return fail(nullptr, PICLES_ERR_ARG, "null handle");
+    if (!h->snap_pending) return PICLES_OK;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->snap_ev[1]));
+    h->snap_pending = false;
     return PICLES_OK;
 }
 

@@ -92,6 +92,8 @@ void launch_halo_unpack(const DeviceArrays& A, const char* lo, const char* hi, D
 void launch_grid_metric(int64_t n, const double* dx, const double* dy, const double* angle_dx, const double* lat,
                         double R_earth, double* M11, double* M12, double* M21, double* M22, double* pc, int sms, cudaStream_t st);
 void launch_make_boundaries(const uint8_t* ocean, uint8_t* total, int Nx, int Ny, int bx, int by, int sms, cudaStream_t st);
+void launch_fields(int64_t n, const double* e, const double* mx, const double* my, double* Hs, double* cx, double* cy,
+                   int sms, cudaStream_t st);
 void launch_fill_i32(int32_t* p, int64_t n, int32_t v, int sms, cudaStream_t st);
 void launch_selftest_math(uint64_t seed, int iters, unsigned long long* out, int sms, cudaStream_t st);
 void launch_fp64_peak(double* out, int iters, int sms, cudaStream_t st, int64_t* fmas);

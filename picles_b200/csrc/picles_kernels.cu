@@ -508,6 +508,26 @@ __global__ void __launch_bounds__(256) k_make_boundaries(const uint8_t* __restri
     }
 }
 
+/* ---- derived output fields ------------------------------------------------------------ */
+/* Hs = 4*sqrt(e) (visualization/movie_2D.jl:50) and the mean group velocity
+   c = m*e/(2|m|^2) of GetGroupVelocity (core_2D.jl:138-147); nullptr outputs are skipped.
+   IEEE sqrt and division: identical to the host arithmetic. */
+__global__ void __launch_bounds__(256) k_fields(int64_t n, const double* __restrict__ e, const double* __restrict__ mx,
+                                                const double* __restrict__ my, double* __restrict__ Hs,
+                                                double* __restrict__ cx, double* __restrict__ cy) {
+    for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x) {
+        const double ev = e[l];
+        if (Hs) Hs[l] = 4.0 * sqrt(ev);
+        if (cx || cy) {
+            const double a = mx[l], b = my[l];
+            const double m_amp = sqrt(a * a + b * b);
+            const double den = 2.0 * (m_amp * m_amp);
+            if (cx) cx[l] = a * ev / den;
+            if (cy) cy[l] = b * ev / den;
+        }
+    }
+}
+
 /* ---- roofline denominators measured in place ------------------------------------ */
 /* 8 independent DFMA chains per thread: the FP64 pipe's issue-rate ceiling */
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
@@ -646,6 +666,10 @@ void launch_make_boundaries(const uint8_t* ocean, uint8_t* total, int Nx, int Ny
     (void)sms;
     dim3 grid((Nx + 255) / 256, Ny < 65535 ? Ny : 65535);
     k_make_boundaries<<<grid, 256, 0, st>>>(ocean, total, Nx, Ny, bx, by);
+}
+void launch_fields(int64_t n, const double* e, const double* mx, const double* my, double* Hs, double* cx, double* cy,
+                   int sms, cudaStream_t st) {
+    if (n > 0) k_fields<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(n, e, mx, my, Hs, cx, cy);
 }
 void launch_fill_i32(int32_t* p, int64_t n, int32_t v, int sms, cudaStream_t st) {
     if (n > 0) k_fill_i32<<<grid_for(n, 256, sms, 4), 256, 0, st>>>(p, n, v);

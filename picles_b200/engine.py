@@ -57,8 +57,12 @@ class B200Engine:
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h:
+            self.lib.picles_snapshot_wait(self.h)
             self.lib.picles_destroy(self.h)
             self.h = None
+            for p in getattr(self, "_pinned", []):
+                self.lib.picles_host_free(p)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -165,6 +169,29 @@ class B200Engine:
         out = np.empty_like(o)
         self._check(self.lib.picles_make_boundaries(self.h, o.shape[1], o.shape[0], int(bx), int(by), _ptr(o), _ptr(out)))
         return out
+
+    def fields(self):
+        """derived output fields on the device: dict(Hs=4*sqrt(e), c_x, c_y) of (ny, Nx)."""
+        out = [np.empty((self.ny, self.Nx)) for _ in range(3)]
+        self._check(self.lib.picles_get_fields(self.h, *[_ptr(a) for a in out]))
+        return dict(Hs=out[0], c_x=out[1], c_y=out[2])
+
+    def pinned_state_buffer(self):
+        """(3, ny, Nx) float64 array in pinned host memory (freed with the engine)."""
+        nbytes = 3 * self.ny * self.Nx * 8
+        p = C.c_void_p()
+        self._check(self.lib.picles_host_alloc(C.byref(p), nbytes), None)
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        buf = (C.c_double * (3 * self.ny * self.Nx)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.float64).reshape(3, self.ny, self.Nx)
+
+    def snapshot_begin(self, S_host):
+        """start an asynchronous copy of State into S_host (3, ny, Nx); stepping may continue."""
+        assert S_host.dtype == np.float64 and S_host.flags["C_CONTIGUOUS"] and S_host.size == 3 * self.ny * self.Nx
+        self._check(self.lib.picles_snapshot_begin(self.h, _ptr(S_host)))
+
+    def snapshot_wait(self):
+        self._check(self.lib.picles_snapshot_wait(self.h))
 
     def counters(self):
         c = PiclesCounters()
