@@ -230,6 +230,7 @@ struct OpsSafe {
     static PM_HDM double sqrtz(double x, unsigned*) { return sqrt(x); }
     static PM_HDM double tanh_(double x, unsigned*) { return pm_tanh_safe(x); }
     static PM_HDM double sech(double x, unsigned*) { return pm_sech_safe(x); }
+    static PM_HDM double exp_(double x, unsigned*) { return pm_exp(x); }
     static PM_HDM double pow_(double x, double y, unsigned*) { return pm_pow_safe(x, y); }
     static PM_HDM double log_(double x, unsigned*) { return pm_log_safe(x); }
     static PM_HDM double log10_(double x, unsigned*) { return pm_log10_safe(x); }
@@ -246,6 +247,7 @@ struct OpsFast {
     static __device__ __forceinline__ double sqrtz(double x, unsigned* bad) { return pm_sqrtz_fast(x, bad); }
     static __device__ __forceinline__ double tanh_(double x, unsigned* bad) { return pm_tanh_fast(x, bad); }
     static __device__ __forceinline__ double sech(double x, unsigned* bad) { return pm_sech_fast(x, bad); }
+    static __device__ __forceinline__ double exp_(double x, unsigned* bad) { return pm_expx_fast(x, bad); }
     static __device__ __forceinline__ double pow_(double x, double y, unsigned* bad) { return pm_pow_fast(x, y, bad); }
     static __device__ __forceinline__ double log_(double x, unsigned* bad) { return pm_log_fast(x, bad); }
     static __device__ __forceinline__ double log10_(double x, unsigned* bad) { return pm_log10_fast(x, bad); }
@@ -287,7 +289,7 @@ PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx,
 #ifdef PH_HOIST_EXP
     /* independent of the c̄ chain below: issued first so its polynomial overlaps the serial
        sqrt -> div -> div head of the evaluation */
-    double e2_early = pm_exp(2.0 * lne);
+    double e2_early = O::exp_(2.0 * lne, bad);
 #endif
     double cbar = O::sqrt_(cx * cx + cy * cy, bad);
     double c_gp = O::div_pre(fabs(cbar), r_g, H.y_rg, bad);
@@ -314,9 +316,9 @@ PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx,
 #ifdef PH_HOIST_EXP
         double e2 = e2_early;
 #else
-        double e2 = pm_exp(2.0 * lne);
+        double e2 = O::exp_(2.0 * lne, bad);
 #endif
-        double en = (P.n == 2.0) ? e2 : pm_exp(P.n * lne);
+        double en = (P.n == 2.0) ? e2 : O::exp_(P.n * lne, bad);
         Dt = P.dissipation ? en * pw : 0.0;
         double k2 = kp * kp;
         Scg = P.peak_shift ? P.C_alpha * Dp * (k2 * k2) * e2 : 0.0;

@@ -55,7 +55,11 @@ PM_FN double PMV(pm_pow)(double x, double y PM_BADP) {
 PM_FN double PMV(pm_tanh)(double x PM_BADP) {
     double ax = fabs(x);
     double y = (ax > 25.0) ? 50.0 : 2.0 * ax;
+#ifdef PM_FAST_RANGE
+    *pm_bad |= (x != x) ? 1u : 0u; /* fast instantiation: NaN raises the flag instead of passing through selects */
+#else
     y = (x != x) ? 0.0 : y;
+#endif
     double p, r;
     int k = pm_exp_reduce(y, &p, &r); /* 0 <= k <= 73 */
     double em = r * p;
@@ -64,7 +68,11 @@ PM_FN double PMV(pm_tanh)(double x PM_BADP) {
     double t = PM_DIVZ(em1, em1 + 2.0);
     t = (ax > 22.0) ? 1.0 : t;
     t = (x < 0.0) ? -t : t;
+#ifdef PM_FAST_RANGE
+    return t;
+#else
     return (x != x) ? x : t;
+#endif
 }
 
 /* sech(x) = 2e/(e^2+1), e = exp(min(|x|,350)); only ever used squared inside
@@ -72,8 +80,26 @@ PM_FN double PMV(pm_tanh)(double x PM_BADP) {
 PM_FN double PMV(pm_sech)(double x PM_BADP) {
     double ax = fabs(x);
     ax = (ax > 350.0) ? 350.0 : ax;
+#ifdef PM_FAST_RANGE
+    *pm_bad |= (x != x) ? 1u : 0u;
+#else
     ax = (x != x) ? 0.0 : ax;
+#endif
     double e = pm_exp_core(ax);
     double t = PM_DIV(2.0 * e, fma(e, e, 1.0));
+#ifdef PM_FAST_RANGE
+    return t;
+#else
     return (x != x) ? x : t;
+#endif
+}
+
+/* exp(x): the fast instantiation flags everything outside [-700, 700] (and NaN) */
+PM_FN double PMV(pm_expx)(double x PM_BADP) {
+#ifdef PM_FAST_RANGE
+    *pm_bad |= (fabs(x) <= 700.0) ? 0u : 1u;
+    return pm_exp_core(x);
+#else
+    return pm_exp(x);
+#endif
 }
