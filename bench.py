@@ -32,9 +32,9 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, _p)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the 4096^2 bench step, from the
-# committed ncu --set full captures (profiles/r01_ncu_*.txt); never measured under the timer
-NCU_TRAFFIC = {"k_advance": 3.62e9, "k_project_remesh": 1.80e9}
-NCU_FP64_PIPE_PCT = 56.3  # sm__pipe_fp64_cycles_active of k_advance (profiles/r01_ncu_advance.txt)
+# committed ncu --set full captures (profiles/r01_ncu_final.txt); never measured under the timer
+NCU_TRAFFIC = {"k_advance": 3.61e9, "k_project_remesh": 1.80e9}
+NCU_FP64_PIPE_PCT = 56.8  # sm__pipe_fp64_cycles_active of k_advance (profiles/r01_ncu_final.txt)
 
 METRIC = "particle-steps/s"
 UNIT = "particle-steps/s"
@@ -190,7 +190,7 @@ def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=4096)

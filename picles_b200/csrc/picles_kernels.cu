@@ -316,7 +316,9 @@ k_project_remesh(const __grid_constant__ ProjectMaps maps, const __grid_constant
     /* reach of the records that can land on this tile: rows within R of its targets.  A few
        fast rows (the shrinking cells near a pole) then do not widen every tile's window. */
     __shared__ int s_rt;
-    if (threadIdx.x < 32) {
+    if (R <= 1) { /* nothing to narrow */
+        if (threadIdx.x == 0) s_rt = R;
+    } else if (threadIdx.x < 32) {
         const int first = jr0 + A.halo - R, count = TY + 2 * R, rows = A.ny + 2 * A.halo;
         int rt = 0;
         for (int q = threadIdx.x; q < count; q += 32) {
