@@ -22,13 +22,15 @@ using namespace picles;
    its rows have landed (copy stream + events), when the strip is large enough to matter */
 #define PIPE_CHUNKS 8
 #define PIPE_MIN_NODES (1 << 20)
+#define PIPE_EVENTS (PIPE_CHUNKS + 5) /* chunk landed x8, boundary blocks x2, boundary advanced, halo exchanged, compute stream idle */
 
 struct picles_handle {
     int device = -1;
     int sms = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;           /* wind upload pipelined against the advance */
-    cudaEvent_t pev[PIPE_CHUNKS + 1] = {};         /* chunk landed / compute stream idle */
+    cudaEvent_t pev[PIPE_EVENTS] = {};
+    cudaStream_t comm_stream = nullptr;           /* halo exchange overlapped with the interior advance */
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; /* adv0, adv1, prj0, prj1=rms0, rms1 */
     cudaEvent_t tev[2] = {nullptr, nullptr};                           /* user stopwatch */
     bool have_grid = false, have_params = false, seeded = false, winds_loaded = false;
@@ -219,7 +221,8 @@ int picles_create(picles_t** out, int device_id) {
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->snap_stream, cudaStreamNonBlocking));
-    for (int k = 0; k <= PIPE_CHUNKS; k++) CK(cudaEventCreateWithFlags(&h->pev[k], cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < PIPE_EVENTS; k++) CK(cudaEventCreateWithFlags(&h->pev[k], cudaEventDisableTiming));
     for (int k = 0; k < 5; k++) CK(cudaEventCreate(&h->ev[k]));
     for (int k = 0; k < 2; k++) CK(cudaEventCreate(&h->tev[k]));
     for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&h->snap_ev[k], cudaEventDisableTiming));
@@ -237,6 +240,7 @@ int picles_destroy(picles_t* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     if (h->snap_stream) cudaStreamSynchronize(h->snap_stream);
+    if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
     if (h->comm && g_nccl.destroy) { g_nccl.destroy(h->comm); h->comm = nullptr; }
     free_grid(h);
     if (h->d_counters) cudaFree(h->d_counters);
@@ -249,8 +253,9 @@ int picles_destroy(picles_t* h) {
         if (h->tev[k]) cudaEventDestroy(h->tev[k]);
     for (int k = 0; k < 2; k++)
         if (h->snap_ev[k]) cudaEventDestroy(h->snap_ev[k]);
-    for (int k = 0; k <= PIPE_CHUNKS; k++)
+    for (int k = 0; k < PIPE_EVENTS; k++)
         if (h->pev[k]) cudaEventDestroy(h->pev[k]);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->snap_stream) cudaStreamDestroy(h->snap_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -477,53 +482,75 @@ int picles_step_advance(picles_t* h, double t, double dt_model) {
     return PICLES_OK;
 }
 
-/* upload the host winds and advance, pipelined: the strip is cut in PIPE_CHUNKS row blocks;
-   block c's rows are copied on the copy stream while block c-1 integrates.  Same wind-level
-   semantics as picles_upload_winds + picles_step_advance. */
-static int upload_and_advance(picles_t* h, double dt_model, const double* u_t, const double* v_t, const double* u_t1,
-                              const double* v_t1) {
+/* ---- upload + advance, pipelined over row blocks -------------------------------------------
+ * begin_advance: wind-level bookkeeping (same semantics as picles_upload_winds), counters and
+ * per-row reach zeroed, start event.  advance_rows: the host winds of rows [r0, r1) are copied on
+ * the copy stream and the advance of those rows starts as soon as they have landed, so block c
+ * integrates while block c+1 is still in flight. */
+static int begin_advance(picles_t* h, double dt_model, const double* u_t, const double* v_t, const double* u_t1,
+                         const double* v_t1) {
     DeviceArrays& A = h->A;
-    const int64_t n = (int64_t)A.Nx * A.ny;
-    if ((!u_t && !u_t1) || n < PIPE_MIN_NODES) {
-        int rc = picles_upload_winds(h, u_t, v_t, u_t1, v_t1);
-        if (rc) return rc;
-        return picles_step_advance(h, 0.0, dt_model);
-    }
     if ((u_t == nullptr) != (v_t == nullptr) || (u_t1 == nullptr) != (v_t1 == nullptr))
         return fail(h, PICLES_ERR_ARG, "wind components must be given in pairs");
     if (!(dt_model > 0)) return fail(h, PICLES_ERR_ARG, "dt_model must be positive");
-    if (!u_t) { /* the previous step's t+DT level is this step's t level: swap, no copy */
+    if (!u_t && u_t1) { /* the previous step's t+DT level is this step's t level: swap, no copy */
         double* tu = A.u_t; A.u_t = A.u_t1; A.u_t1 = tu;
         double* tv = A.v_t; A.v_t = A.v_t1; A.v_t1 = tv;
     }
     CK(cudaMemsetAsync(h->d_counters, 0, sizeof(DeviceCounters), h->stream));
     CK(cudaMemsetAsync(A.rowreach, 0, (size_t)(A.ny + 2 * A.halo) * 4, h->stream));
-    /* the copy stream may only overwrite the wind planes once the compute stream is past
-       every earlier kernel that read them */
-    CK(cudaEventRecord(h->pev[PIPE_CHUNKS], h->stream));
-    CK(cudaStreamWaitEvent(h->copy_stream, h->pev[PIPE_CHUNKS], 0));
-    CK(cudaEventRecord(h->ev[0], h->stream));
-    const int rows = (A.ny + PIPE_CHUNKS - 1) / PIPE_CHUNKS;
-    for (int c = 0; c < PIPE_CHUNKS; c++) {
-        const int r0 = c * rows, r1 = (r0 + rows < A.ny) ? r0 + rows : A.ny;
-        if (r0 >= r1) break;
-        const int64_t off = (int64_t)r0 * A.Nx;
-        const size_t bytes = (size_t)(r1 - r0) * A.Nx * 8;
-        if (u_t) {
-            CK(cudaMemcpyAsync(A.u_t + off, u_t + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
-            CK(cudaMemcpyAsync(A.v_t + off, v_t + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
-        }
-        if (u_t1) {
-            CK(cudaMemcpyAsync(A.u_t1 + off, u_t1 + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
-            CK(cudaMemcpyAsync(A.v_t1 + off, v_t1 + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
-        }
-        CK(cudaEventRecord(h->pev[c], h->copy_stream));
-        CK(cudaStreamWaitEvent(h->stream, h->pev[c], 0));
-        launch_advance(A, h->P, dt_model, h->d_counters, h->sms, h->stream, off, off + (int64_t)(r1 - r0) * A.Nx);
+    if (u_t || u_t1) {
+        /* the copy stream may only overwrite the wind planes once the compute stream is past
+           every earlier kernel that read them */
+        CK(cudaEventRecord(h->pev[PIPE_EVENTS - 1], h->stream));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->pev[PIPE_EVENTS - 1], 0));
     }
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    h->timing_valid = false;
+    return PICLES_OK;
+}
+static int advance_rows(picles_t* h, double dt_model, const double* u_t, const double* v_t, const double* u_t1,
+                        const double* v_t1, int r0, int r1, cudaEvent_t landed) {
+    DeviceArrays& A = h->A;
+    if (r0 >= r1) return PICLES_OK;
+    const int64_t off = (int64_t)r0 * A.Nx;
+    const size_t bytes = (size_t)(r1 - r0) * A.Nx * 8;
+    if (u_t) {
+        CK(cudaMemcpyAsync(A.u_t + off, u_t + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaMemcpyAsync(A.v_t + off, v_t + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    }
+    if (u_t1) {
+        CK(cudaMemcpyAsync(A.u_t1 + off, u_t1 + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaMemcpyAsync(A.v_t1 + off, v_t1 + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    }
+    if (u_t || u_t1) {
+        CK(cudaEventRecord(landed, h->copy_stream));
+        CK(cudaStreamWaitEvent(h->stream, landed, 0));
+    }
+    launch_advance(A, h->P, dt_model, h->d_counters, h->sms, h->stream, off, off + (int64_t)(r1 - r0) * A.Nx);
+    return PICLES_OK;
+}
+/* rows [r0, r1) in up to PIPE_CHUNKS blocks (one block when nothing is uploaded or the range is small) */
+static int advance_range(picles_t* h, double dt_model, const double* u_t, const double* v_t, const double* u_t1,
+                         const double* v_t1, int r0, int r1) {
+    const int64_t n = (int64_t)(r1 - r0) * h->A.Nx;
+    const int nch = ((u_t || u_t1) && n >= PIPE_MIN_NODES) ? PIPE_CHUNKS : 1;
+    const int rows = (r1 - r0 + nch - 1) / nch;
+    for (int c = 0; c < nch; c++) {
+        const int a = r0 + c * rows, b = (a + rows < r1) ? a + rows : r1;
+        int rc = advance_rows(h, dt_model, u_t, v_t, u_t1, v_t1, a, b, h->pev[c]);
+        if (rc) return rc;
+    }
+    return PICLES_OK;
+}
+static int upload_and_advance(picles_t* h, double dt_model, const double* u_t, const double* v_t, const double* u_t1,
+                              const double* v_t1) {
+    int rc = begin_advance(h, dt_model, u_t, v_t, u_t1, v_t1);
+    if (rc) return rc;
+    rc = advance_range(h, dt_model, u_t, v_t, u_t1, v_t1, 0, h->A.ny);
+    if (rc) return rc;
     CK(cudaEventRecord(h->ev[1], h->stream));
     CK(cudaGetLastError());
-    h->timing_valid = false;
     return PICLES_OK;
 }
 
@@ -925,9 +952,7 @@ int picles_comm_destroy(picles_t* h) {
 
 /* pack -> grouped ncclSend/ncclRecv with the two y-neighbours -> unpack, all enqueued on the
    handle's stream: no host synchronisation between the advance and the gather */
-int picles_halo_exchange(picles_t* h, int lo_rank, int hi_rank) {
-    int rc = need_ready(h, true);
-    if (rc) return rc;
+static int exchange_on(picles_t* h, int lo_rank, int hi_rank, cudaStream_t st) {
     if (h->A.halo == 0) return PICLES_OK;
     if ((lo_rank >= 0 || hi_rank >= 0) && !h->comm)
         return fail(h, PICLES_ERR_STATE, "picles_comm_init must be called before picles_halo_exchange");
@@ -936,7 +961,7 @@ int picles_halo_exchange(picles_t* h, int lo_rank, int hi_rank) {
         /* a periodic ring of one strip would be its own neighbour: not a strip decomposition */
         return fail(h, PICLES_ERR_ARG, "bad neighbour ranks lo=%d hi=%d (rank %d of %d)", lo_rank, hi_rank, h->comm_rank, h->comm_size);
     }
-    launch_halo_pack(h->A, h->send_lo, h->send_hi, h->sms, h->stream);
+    launch_halo_pack(h->A, h->send_lo, h->send_hi, h->sms, st);
     CK(cudaGetLastError());
     if (lo_rank >= 0 || hi_rank >= 0) {
         size_t nb = (size_t)h->halo_bytes;
@@ -945,27 +970,57 @@ int picles_halo_exchange(picles_t* h, int lo_rank, int hi_rank) {
            neighbour's lower halo.  Sends are issued lo,hi and receives hi,lo so that a
            periodic ring of two strips (lo_rank == hi_rank) pairs them up correctly:
            NCCL matches the operations between two ranks in issue order. */
-        if (lo_rank >= 0) NCK(g_nccl.send(h->send_lo, nb, 0 /* ncclInt8 */, lo_rank, h->comm, h->stream));
-        if (hi_rank >= 0) NCK(g_nccl.send(h->send_hi, nb, 0, hi_rank, h->comm, h->stream));
-        if (hi_rank >= 0) NCK(g_nccl.recv(h->recv_hi, nb, 0, hi_rank, h->comm, h->stream));
-        if (lo_rank >= 0) NCK(g_nccl.recv(h->recv_lo, nb, 0, lo_rank, h->comm, h->stream));
+        if (lo_rank >= 0) NCK(g_nccl.send(h->send_lo, nb, 0 /* ncclInt8 */, lo_rank, h->comm, st));
+        if (hi_rank >= 0) NCK(g_nccl.send(h->send_hi, nb, 0, hi_rank, h->comm, st));
+        if (hi_rank >= 0) NCK(g_nccl.recv(h->recv_hi, nb, 0, hi_rank, h->comm, st));
+        if (lo_rank >= 0) NCK(g_nccl.recv(h->recv_lo, nb, 0, lo_rank, h->comm, st));
         NCK(g_nccl.group_end());
     }
-    launch_halo_unpack(h->A, h->recv_lo, h->recv_hi, h->d_counters, h->sms, h->stream);
+    launch_halo_unpack(h->A, h->recv_lo, h->recv_hi, h->d_counters, h->sms, st);
     CK(cudaGetLastError());
     return PICLES_OK;
 }
 
-/* one model step of a strip, exchange included: upload winds, advance, halo exchange,
-   gather, remesh; one host synchronisation at the end (the counters) */
+int picles_halo_exchange(picles_t* h, int lo_rank, int hi_rank) {
+    int rc = need_ready(h, true);
+    if (rc) return rc;
+    return exchange_on(h, lo_rank, hi_rank, h->stream);
+}
+
+/* one model step of a strip, exchange included; one host synchronisation at the end (the
+   counters).  The first and last `halo` rows are advanced first; their deposit records travel
+   to the neighbours on a second stream (pack, ncclSend/ncclRecv, unpack) while the interior
+   rows integrate, so neither the exchange nor a slower neighbour shows up in the step time. */
 int picles_step_strip(picles_t* h, double t, double dt_model, const double* u_t, const double* v_t, const double* u_t1,
                       const double* v_t1, int lo_rank, int hi_rank) {
     int rc = need_ready(h, true);
     if (rc) return rc;
-    rc = upload_and_advance(h, dt_model, u_t, v_t, u_t1, v_t1);
+    const DeviceArrays& A = h->A;
+    const bool overlap = A.halo > 0 && (lo_rank >= 0 || hi_rank >= 0) && A.ny > 2 * A.halo;
+    if (!overlap) {
+        rc = upload_and_advance(h, dt_model, u_t, v_t, u_t1, v_t1);
+        if (rc) return rc;
+        rc = exchange_on(h, lo_rank, hi_rank, h->stream);
+        if (rc) return rc;
+        return picles_step_project_remesh(h, t, dt_model);
+    }
+    rc = begin_advance(h, dt_model, u_t, v_t, u_t1, v_t1);
     if (rc) return rc;
-    rc = picles_halo_exchange(h, lo_rank, hi_rank);
+    rc = advance_rows(h, dt_model, u_t, v_t, u_t1, v_t1, 0, A.halo, h->pev[PIPE_CHUNKS]);
     if (rc) return rc;
+    rc = advance_rows(h, dt_model, u_t, v_t, u_t1, v_t1, A.ny - A.halo, A.ny, h->pev[PIPE_CHUNKS + 1]);
+    if (rc) return rc;
+    cudaEvent_t advanced = h->pev[PIPE_CHUNKS + 2], exchanged = h->pev[PIPE_CHUNKS + 3];
+    CK(cudaEventRecord(advanced, h->stream));                  /* boundary records written */
+    CK(cudaStreamWaitEvent(h->comm_stream, advanced, 0));
+    rc = exchange_on(h, lo_rank, hi_rank, h->comm_stream);
+    if (rc) return rc;
+    CK(cudaEventRecord(exchanged, h->comm_stream));            /* halo rows in place */
+    rc = advance_range(h, dt_model, u_t, v_t, u_t1, v_t1, A.halo, A.ny - A.halo);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamWaitEvent(h->stream, exchanged, 0));
     return picles_step_project_remesh(h, t, dt_model);
 }
 
