@@ -284,6 +284,16 @@ int picles_host_free(void* p);
 int picles_snapshot_begin(picles_t* h, double* S_host);
 int picles_snapshot_wait(picles_t* h);
 
+/* ---- checkpoint / resume --------------------------------------------------------- */
+/* The reference cannot resume (run!(…; pickup=false) is unused, src/Simulations/run.jl:36).
+   Here the particle planes, the node State and the pending wind level are the complete state
+   of the path: save writes them into a caller-owned host blob of picles_checkpoint_size
+   bytes; load restores them into a handle with the same grid and parameters (set_grid* and
+   set_params called, picles_seed not needed).  A resumed run continues bit-identically. */
+int picles_checkpoint_size(picles_t* h, int64_t* nbytes);
+int picles_checkpoint_save(picles_t* h, void* blob, int64_t nbytes);
+int picles_checkpoint_load(picles_t* h, const void* blob, int64_t nbytes);
+
 /* device pointers for zero-copy consumers (torch / CUDA.jl): planes as above */
 int picles_state_dev(picles_t* h, double** S_dev /* out: 3 plane pointers e, m_x, m_y */);
 int picles_wind_dev(picles_t* h, double** u_t_dev, double** v_t_dev,

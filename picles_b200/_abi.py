@@ -130,6 +130,9 @@ SYMBOLS = {
     "picles_step_strip": (C.c_int, [_vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
     "picles_get_state": (C.c_int, [_vp, _vp]),
     "picles_set_state": (C.c_int, [_vp, _vp]),
+    "picles_checkpoint_size": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "picles_checkpoint_save": (C.c_int, [_vp, _vp, C.c_int64]),
+    "picles_checkpoint_load": (C.c_int, [_vp, _vp, C.c_int64]),
     "picles_get_fields": (C.c_int, [_vp, _vp, _vp, _vp]),
     "picles_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_int64]),
     "picles_host_free": (C.c_int, [_vp]),

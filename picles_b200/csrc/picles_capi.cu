@@ -910,6 +910,99 @@ int picles_snapshot_wait(picles_t* h) {
     return PICLES_OK;
 }
 
+/* ---- checkpoint / resume ------------------------------------------------------------------
+ * The particle planes (u[5], t, dt, qold, iter, flags, status), the node State and the wind
+ * level that the next step takes as its t level are the complete state of the path (the
+ * reference has no checkpointing: run!(…; pickup=false) is unused, run.jl:36).  Layout of the
+ * blob: a 64-byte header {magic, version, Nx, ny, j0, Ny, bx, by, halo, n_bytes} then the planes in
+ * the order below, each ny*Nx elements. */
+struct CkptHeader {
+    uint64_t magic;
+    int32_t version, Nx, ny, j0, Ny, bx, by, halo;
+    int64_t n_bytes;
+    int64_t reserved[2];
+};
+static_assert(sizeof(CkptHeader) == 64, "checkpoint header layout");
+#define CKPT_MAGIC 0x50694342323030ull /* "PiCB200" */
+
+static int64_t ckpt_bytes(const DeviceArrays& A) {
+    const int64_t n = (int64_t)A.Nx * A.ny;
+    return (int64_t)sizeof(CkptHeader) + n * (8 * (5 + 3 + 3 + 2) + 4 + 1 + 1);
+}
+int picles_checkpoint_size(picles_t* h, int64_t* nbytes) {
+    if (!h || !h->have_grid || !nbytes) return fail(h, PICLES_ERR_STATE, "grid not set");
+    *nbytes = ckpt_bytes(h->A);
+    return PICLES_OK;
+}
+/* the planes of a checkpoint, in blob order */
+static int ckpt_planes(picles_t* h, void** ptr, size_t* bytes) {
+    DeviceArrays& A = h->A;
+    const size_t n = (size_t)A.Nx * A.ny;
+    int k = 0;
+    for (int c = 0; c < 5; c++) { ptr[k] = A.z[c]; bytes[k++] = n * 8; }
+    ptr[k] = A.t; bytes[k++] = n * 8;
+    ptr[k] = A.dt; bytes[k++] = n * 8;
+    ptr[k] = A.qold; bytes[k++] = n * 8;
+    for (int c = 0; c < 3; c++) { ptr[k] = A.S[c]; bytes[k++] = n * 8; }
+    ptr[k] = A.u_t1; bytes[k++] = n * 8; /* becomes the t level of the next step */
+    ptr[k] = A.v_t1; bytes[k++] = n * 8;
+    ptr[k] = A.iter; bytes[k++] = n * 4;
+    ptr[k] = A.flags; bytes[k++] = n;
+    ptr[k] = A.status; bytes[k++] = n;
+    return k;
+}
+int picles_checkpoint_save(picles_t* h, void* blob, int64_t nbytes) {
+    int rc = need_ready(h, true);
+    if (rc) return rc;
+    if (!blob || nbytes < ckpt_bytes(h->A)) return fail(h, PICLES_ERR_ARG, "checkpoint buffer too small (%lld < %lld bytes)", (long long)nbytes, (long long)ckpt_bytes(h->A));
+    const DeviceArrays& A = h->A;
+    CkptHeader hd = {CKPT_MAGIC, PICLES_ABI_VERSION, A.Nx, A.ny, A.j0, A.Ny, A.bx, A.by, A.halo, ckpt_bytes(A), {0, 0}};
+    memcpy(blob, &hd, sizeof hd);
+    void* ptr[16];
+    size_t bytes[16];
+    const int np = ckpt_planes(h, ptr, bytes);
+    char* out = (char*)blob + sizeof hd;
+    for (int k = 0; k < np; k++) {
+        CK(cudaMemcpyAsync(out, ptr[k], bytes[k], cudaMemcpyDeviceToHost, h->stream));
+        out += bytes[k];
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return PICLES_OK;
+}
+/* the handle must have the same grid (picles_set_grid*) and parameters as the one that saved */
+int picles_checkpoint_load(picles_t* h, const void* blob, int64_t nbytes) {
+    int rc = need_ready(h, false);
+    if (rc) return rc;
+    if (!blob || nbytes < (int64_t)sizeof(CkptHeader)) return fail(h, PICLES_ERR_ARG, "not a checkpoint");
+    CkptHeader hd;
+    memcpy(&hd, blob, sizeof hd);
+    const DeviceArrays& A = h->A;
+    if (hd.magic != CKPT_MAGIC || hd.version != PICLES_ABI_VERSION) return fail(h, PICLES_ERR_ARG, "not a checkpoint of this library version");
+    if (hd.Nx != A.Nx || hd.ny != A.ny || hd.j0 != A.j0 || hd.Ny != A.Ny || hd.bx != A.bx || hd.by != A.by)
+        return fail(h, PICLES_ERR_ARG, "checkpoint is for a %dx%d strip at row %d of %d; this handle owns %dx%d at row %d of %d", hd.Nx,
+                    hd.ny, hd.j0, hd.Ny, A.Nx, A.ny, A.j0, A.Ny);
+    if (nbytes < hd.n_bytes || hd.n_bytes != ckpt_bytes(A)) return fail(h, PICLES_ERR_ARG, "truncated checkpoint");
+    void* ptr[16];
+    size_t bytes[16];
+    const int np = ckpt_planes(h, ptr, bytes);
+    const char* in = (const char*)blob + sizeof hd;
+    for (int k = 0; k < np; k++) {
+        CK(cudaMemcpyAsync(ptr[k], in, bytes[k], cudaMemcpyHostToDevice, h->stream));
+        in += bytes[k];
+    }
+    /* no deposit records are carried over: every step rewrites them before they are read */
+    const int64_t ne = (int64_t)A.rp * (A.ny + 2 * A.halo);
+    launch_fill_i32(A.cell, ne, -1, h->sms, h->stream);
+    CK(cudaMemcpyAsync(A.u_t, A.u_t1, (size_t)A.Nx * A.ny * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(A.v_t, A.v_t1, (size_t)A.Nx * A.ny * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    h->seeded = true;
+    h->winds_loaded = true;
+    memset(&h->last, 0, sizeof h->last);
+    return PICLES_OK;
+}
+
 /* ---- strip communicator: halo exchange over NVLink inside the library ----------------- */
 int picles_comm_unique_id(char* id128, const char* nccl_path) {
     picles_t* h = nullptr;

@@ -193,6 +193,19 @@ class B200Engine:
     def snapshot_wait(self):
         self._check(self.lib.picles_snapshot_wait(self.h))
 
+    def checkpoint(self):
+        """the complete state of the path as one uint8 array (picles_checkpoint_save)"""
+        n = C.c_int64()
+        self._check(self.lib.picles_checkpoint_size(self.h, C.byref(n)))
+        blob = np.empty(n.value, np.uint8)
+        self._check(self.lib.picles_checkpoint_save(self.h, _ptr(blob), n.value))
+        return blob
+
+    def restore(self, blob):
+        """resume from a checkpoint() of an engine with the same grid and parameters"""
+        blob = np.ascontiguousarray(blob, np.uint8)
+        self._check(self.lib.picles_checkpoint_load(self.h, _ptr(blob), blob.size))
+
     def counters(self):
         c = PiclesCounters()
         self._check(self.lib.picles_get_counters(self.h, C.byref(c)))

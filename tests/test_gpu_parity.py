@@ -292,6 +292,41 @@ def test_gpu_output_fields_and_async_snapshots(gpu_lib):
         assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
 
 
+@pytest.mark.parametrize("name", ["growing_winds_persist", "tripolar", "maxiters"])
+def test_gpu_checkpoint_resume_is_bit_identical(gpu_lib, name):
+    """run k steps, checkpoint, continue; a fresh handle restored from the blob continues with the
+    same bits (particle controller memory, pending dt resets, retcodes and wind level included)."""
+    g, P, wind, DT, n = SCENARIOS[name]()
+    a = engine_for(g, P)
+    a.seed(*wind(0.0))
+    t = 0.0
+    for _ in range(3):
+        a.step(t, DT, *wind(t), *wind(t + DT))
+        t += DT
+    blob = a.checkpoint()
+    b = engine_for(g, P)
+    b.restore(blob)
+    tb = t
+    for _ in range(3):
+        a.step(t, DT, None, None, *wind(t + DT))       # only the new level is uploaded, as run! does
+        t += DT
+    for _ in range(3):
+        b.step(tb, DT, None, None, *wind(tb + DT))
+        tb += DT
+    assert np.array_equal(a.state().view(np.uint64), b.state().view(np.uint64))
+    pa, pb = a.particles(), b.particles()
+    for k in ("z", "t", "dt"):
+        assert np.array_equal(pa[k].view(np.uint64), pb[k].view(np.uint64)), k
+    assert np.array_equal(pa["flags"], pb["flags"]) and np.array_equal(pa["status"], pb["status"])
+    ca, cb = a.counters(), b.counters()
+    assert all(ca[k] == cb[k] for k in ("n_substeps", "n_rhs", "n_rejects", "n_failed", "reach"))
+    # a blob of another grid is refused
+    other = engine_for(cartesian_grid(9, 7), default_params())
+    from picles_b200 import PiclesError
+    with pytest.raises(PiclesError, match="ERR_ARG"):
+        other.restore(blob)
+
+
 def test_gpu_state_roundtrip_and_accessors(gpu_lib):
     g = cartesian_grid(33, 17)
     P = default_params()
