@@ -188,6 +188,14 @@ def sc_odd_periodic_strip():
     return g, default_params(periodic_boundary=True), _const(-13.0, 11.0), 1200.0, 5
 
 
+def sc_fast_box():
+    """fine Cartesian box (150 x 90, larger than a gather tile) with particles crossing 2-4 cells
+    per step: reach 2, then 3, then 4 — the reach-2 window and the wide (12 + 4 rows) tile
+    geometry of the gather, on interior nodes."""
+    g = cartesian_grid(150, 90, dx=700.0, dy=800.0)
+    return g, default_params(DT=900.0), _const(13.0, -9.0), 900.0, 6
+
+
 SCENARIOS = {
     "minimal": sc_minimal,
     "minimal_dp5": sc_minimal_dp5,
@@ -209,6 +217,7 @@ SCENARIOS = {
     "calm": sc_calm,
     "tiny": sc_tiny,
     "odd_periodic_strip": sc_odd_periodic_strip,
+    "fast_box": sc_fast_box,
 }
 
 

@@ -109,7 +109,8 @@ def test_gpu_matches_oracle_bit_exact(gpu_lib, name):
 
 
 @pytest.mark.parametrize("name,nstrips,halo", [("minimal", 2, 2), ("periodic_grid", 2, 5), ("tripolar", 3, 6),
-                                               ("land_block", 4, 2)])
+                                               ("land_block", 4, 2), ("fast_box", 3, 5), ("periodic_x_only", 2, 3),
+                                               ("growing_winds_persist", 2, 2)])
 def test_gpu_strips_match_oracle(gpu_lib, name, nstrips, halo):
     g, P, wind, DT, n = SCENARIOS[name]()
     run_pair(make_oracle(g, P), StripSet(g, P, nstrips, halo), wind, DT, n, compare_models)
