@@ -368,7 +368,11 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "roofline": roofline, "roofline_hbm": roofline_hbm,
             "measured_here": {"fp64_dfma_tflops": fp64_peak, "hbm_copy_gbs": hbm_meas},
-            "clocks": clocks, "gpu_launches": (2 if world == 1 else 4) * args.steps,
+            "clocks": clocks,
+            # ours, per step of the resident-input region: k_advance + k_project_remesh; on strips the
+            # advance is three launches (two boundary blocks first, then the interior) plus
+            # k_halo_pack and k_halo_unpack around NCCL's own send/recv kernel
+            "gpu_launches": (2 if world == 1 else 6) * args.steps,
             "substeps_per_particle_step": float(np.mean([c["n_substeps"] / max(c["n_integrated"], 1) for c in per_step])),
             "max_attempts": int(max(c["max_attempts"] for c in per_step)),
             "rejects": int(sum(c["n_rejects"] for c in per_step)),
