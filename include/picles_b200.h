@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define PICLES_ABI_VERSION 1
+#define PICLES_ABI_VERSION 2
 
 typedef struct picles_handle picles_t;
 
@@ -221,6 +221,21 @@ int picles_step(picles_t* h, double t, double dt_model,
 /* Phase-split form of picles_step (same arithmetic):                          */
 int picles_upload_winds(picles_t* h, const double* u_t, const double* v_t,
                         const double* u_t1, const double* v_t1);
+/*
+ * Intermediate wind levels of the NEXT step (wind ingestion).  The reference
+ * calls the wind closures u(x,y,t), v(x,y,t) at every Runge-Kutta stage time
+ * (particle_waves_v5.jl:489-495); this library integrates against wind levels staged per model
+ * step.  With the two levels t, t+dt_model the wind is linear in time over the step (exact for
+ * steady winds and for gridded winds that are linear between their time knots,
+ * tests/T03_PIC_tripolar_realistic.jl:61-73).  n_mid > 0 adds the levels at
+ * t + k*dt_model/(n_mid+1), k = 1..n_mid: the wind at a stage time is then the polynomial of
+ * degree n_mid+1 through all levels, which converges to the closure value for smooth winds
+ * (measured in tests/test_wind_levels.py).  u_mid / v_mid: n_mid planes of ny_local*Nx each,
+ * host.  The levels are consumed by the next picles_step / picles_step_strip /
+ * picles_step_advance call; n_mid = 0 clears them.
+ */
+#define PICLES_WIND_MID_MAX 3
+int picles_set_wind_midlevels(picles_t* h, int n_mid, const double* u_mid, const double* v_mid);
 int picles_step_advance(picles_t* h, double t, double dt_model);   /* async on the handle's stream */
 /* device pointers + byte count of the packed halo rows to send to / receive from the
    lower (j0-1) and upper (j0+ny_local) neighbour; valid after picles_step_advance */
@@ -257,6 +272,34 @@ int picles_step_strip(picles_t* h, double t, double dt_model,
                       const double* u_t, const double* v_t,
                       const double* u_t1, const double* v_t1,
                       int lo_rank, int hi_rank);
+
+/* ---- wind ingestion: a device-resident wind mesh --------------------------------------- */
+/*
+ * Gridded winds kept on the device, so a step uploads nothing: the reference builds its wind
+ * closures from gridded data as Interpolations.LinearInterpolation((x, y, t), U,
+ * extrapolation_bc=Periodic()) (tests/T03_PIC_tripolar_realistic.jl:61-73,
+ * src/Utils/WindEmulator.jl:18-43) and calls them at the home node of every particle.
+ *   nxw, nyw, ntw   knots per axis (each >= 2); xw, yw, tw strictly increasing knot vectors
+ *   U, V            ntw slices of nyw*nxw values, x fastest (Julia: U[ix, iy, it])
+ *   node_x, node_y  coordinates of this strip's nodes, ny_local*Nx each (grid.data.x, grid.data.y)
+ * Sampling is multilinear in (x, y, t); a coordinate outside its knot range is wrapped with
+ * period (last knot - first knot), as extrapolation_bc = Periodic() does.  The mesh stays
+ * resident until the next picles_set_wind_mesh / picles_set_grid call (all arrays are copied).
+ */
+int picles_set_wind_mesh(picles_t* h, int nxw, int nyw, int ntw,
+                         const double* xw, const double* yw, const double* tw,
+                         const double* U, const double* V,
+                         const double* node_x, const double* node_y);
+/* the mesh sampled at this strip's nodes at time t, to host (ny_local*Nx each): the values the
+   closure u.(grid.data.x, grid.data.y, t) would return */
+int picles_sample_wind_mesh(picles_t* h, double t, double* u_out, double* v_out);
+/* picles_seed with the wind of the mesh at time t0 */
+int picles_seed_wind_mesh(picles_t* h, double t0);
+/* picles_step (single strip) / picles_step_strip (lo_rank, hi_rank as there; pass -1, -1 on a
+   single-strip handle) with every wind level sampled on the device from the mesh: levels t and
+   t+dt_model plus n_mid intermediate ones (0..PICLES_WIND_MID_MAX).  The previous step's t+dt
+   level is reused as this step's t level when the times match. */
+int picles_step_wind_mesh(picles_t* h, double t, double dt_model, int n_mid, int lo_rank, int hi_rank);
 
 /* ---- state access ------------------------------------------------------ */
 int picles_get_state(picles_t* h, double* S /* ny_local*Nx*3: planes e, m_x, m_y */);

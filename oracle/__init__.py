@@ -51,6 +51,9 @@ def load(variant: str = "default"):
     lib.oracle_destroy.argtypes = [vp]
     lib.oracle_set_threads.argtypes = [vp, i32]
     lib.oracle_set_accumulate.argtypes = [vp, i32]
+    lib.oracle_set_wind_midlevels.argtypes = [vp, i32, vp, vp]
+    lib.oracle_set_wind_closure.argtypes = [vp, vp, vp, vp]
+    lib.oracle_wind_mesh_sample.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i64, vp, vp, d, vp, vp]
     lib.oracle_seed.argtypes = [vp, vp, vp]
     lib.oracle_step.argtypes = [vp, d, d, vp, vp, vp, vp]
     lib.oracle_get_state.argtypes = [vp, vp]
@@ -130,6 +133,33 @@ class Oracle:
         u0 = _f64(np.broadcast_to(u0, (self.Ny, self.Nx)))
         v0 = _f64(np.broadcast_to(v0, (self.Ny, self.Nx)))
         self.lib.oracle_seed(self.h, _dp(u0), _dp(v0))
+
+    def set_wind_midlevels(self, u_mid, v_mid):
+        """intermediate wind levels (t + k*DT/(n+1), k = 1..n) of the next step only"""
+        sh = (self.Ny, self.Nx)
+        n = len(u_mid)
+        um = _f64(np.stack([np.broadcast_to(x, sh) for x in u_mid])) if n else None
+        vm = _f64(np.stack([np.broadcast_to(x, sh) for x in v_mid])) if n else None
+        self.lib.oracle_set_wind_midlevels(self.h, n, _dp(um), _dp(vm))
+
+    def set_wind_closure(self, fn, x, y):
+        """reference semantics: fn(x, y, t) -> (u, v) is called at the home node and the stage
+        time of every right-hand side (small grids only: a Python callback per evaluation)"""
+        if fn is None:
+            self._cb = None
+            self.lib.oracle_set_wind_closure(self.h, None, None, None)
+            return
+        CB = C.CFUNCTYPE(None, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+        def tramp(xx, yy, tt, pu, pv):
+            u, v = fn(xx, yy, tt)
+            pu[0] = u
+            pv[0] = v
+
+        self._cb = CB(tramp)
+        sh = (self.Ny, self.Nx)
+        xa, ya = _f64(np.broadcast_to(x, sh)), _f64(np.broadcast_to(y, sh))
+        self.lib.oracle_set_wind_closure(self.h, C.cast(self._cb, C.c_void_p), _dp(xa), _dp(ya))
 
     def step(self, t, DT, u_t, v_t, u_t1, v_t1):
         sh = (self.Ny, self.Nx)
@@ -287,6 +317,19 @@ def grid_metric(dx, dy, angle_dx, lat, R_earth=6.3710e6, variant="default"):
     pc = np.empty(dx.shape)
     lib.oracle_grid_metric(dx.size, _dp(dx), _dp(dy), _dp(angle_dx), _dp(lat), float(R_earth), _dp(M), _dp(pc))
     return M, pc
+
+
+def wind_mesh_sample(xw, yw, tw, U, V, x, y, t, variant="default"):
+    """Interpolations.LinearInterpolation((xw, yw, tw), U, extrapolation_bc=Periodic()) at the
+    points (x, y) and time t; U, V: (nt, ny, nx) C-ordered == Julia U[ix, iy, it]"""
+    lib = load(variant)
+    xw, yw, tw, U, V = _f64(xw), _f64(yw), _f64(tw), _f64(U), _f64(V)
+    x = _f64(x)
+    y = _f64(np.broadcast_to(y, x.shape))
+    u, v = np.empty(x.shape), np.empty(x.shape)
+    lib.oracle_wind_mesh_sample(xw.size, yw.size, tw.size, _dp(xw), _dp(yw), _dp(tw), _dp(U), _dp(V), x.size, _dp(x),
+                                _dp(y), float(t), _dp(u), _dp(v))
+    return u, v
 
 
 def max_threads():

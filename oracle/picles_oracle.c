@@ -24,8 +24,10 @@
  * Compile with -ffp-contract=off: every fused multiply-add below is explicit.
  *
  * Deliberate, documented forks from the as-run reference:
- *   - winds are staged meshes at the step's t and t+DT, linear in time in between
- *     (the reference calls the closure at every RK stage time);
+ *   - winds are staged meshes at the step's t and t+DT (plus optional equally spaced
+ *     intermediate levels), a polynomial in time through the levels in between (the
+ *     reference calls the closure at every RK stage time; oracle_set_wind_closure runs
+ *     exactly that, as the yardstick the staged-level runs are measured against);
  *   - auto_dt_reset! is evaluated lazily at the start of the next advance (same
  *     arithmetic, same inputs);
  *   - the AutoTsit5 stiff (Rosenbrock23) branch is not taken; the stiffness trigger
@@ -98,6 +100,13 @@ typedef struct oracle {
     int64_t stiff_triggers; /* times AutoTsit5 would have switched */
     int nthreads;
     int accumulate; /* 0: State .= 0 before the step (run!); 1: bare time_step! */
+    /* intermediate wind levels of the next step (consumed by it): n_mid planes of Nx*Ny */
+    int n_mid;
+    double *u_mid, *v_mid;
+    /* reference semantics: the wind closures u(x,y,t), v(x,y,t) called at the home node and the
+       stage time (particle_waves_v5.jl:489-495); x, y = grid.data.x / grid.data.y */
+    void (*wind_fn)(double x, double y, double t, double* u, double* v);
+    double *x, *y;
 } oracle_t;
 
 /* ------------------------------------------------------------------------ */
@@ -278,19 +287,46 @@ static const tableau_t DP5 = {
     {0, -71.0 / 57600.0, 0.0, 71.0 / 16695.0, -71.0 / 1920.0, 17253.0 / 339200.0, -22.0 / 525.0, 1.0 / 40.0},
     0.17, 0.04, 5};
 
+#define WIND_SEG_MAX (PICLES_WIND_MID_MAX + 1)
 typedef struct {
     const oracle_t* o;
     const double* M;
     double pc;
-    double u0, v0, du, dv; /* wind at the step's t level and (t1 - t) increment */
+    int nseg;                                   /* time segments of the staged wind: levels - 1 */
+    double cu[WIND_SEG_MAX + 1], cv[WIND_SEG_MAX + 1]; /* Newton coefficients of the levels in time */
     double t_start, inv_DT;
+    double x, y;                                /* home-node coordinates (closure mode) */
 } rhs_ctx_t;
 
-/* wind at stage time ts: linear between the two staged levels (documented fork) */
+/* Newton forward-difference form of the polynomial through nseg+1 equally spaced levels w[k]
+   (k = 0: the step's t level, k = nseg: t+DT):  c[m] = Delta^m w_0 / m!.  Two levels: c[1] = w1-w0. */
+static void wind_coefficients(const double* w, int nseg, double* c) {
+    static const double inv_fact[WIND_SEG_MAX + 1] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0};
+    double d[WIND_SEG_MAX + 1] = {0};
+    for (int k = 0; k <= nseg; k++) d[k] = w[k];
+    c[0] = d[0];
+    for (int m = 1; m <= nseg; m++) {
+        for (int k = 0; k <= nseg - m; k++) d[k] = d[k + 1] - d[k];
+        c[m] = (m >= 2) ? d[0] * inv_fact[m] : d[0];
+    }
+}
+
+/* wind at stage time ts: the polynomial in time through the staged levels (documented fork:
+   linear for the two levels t, t+DT), or the closure itself when one is set */
 static inline void f_eval(const rhs_ctx_t* c, const double* z, double ts, double* dz, int64_t* nrhs) {
-    double s = (ts - c->t_start) * c->inv_DT;
-    double u = fma(c->du, s, c->u0);
-    double v = fma(c->dv, s, c->v0);
+    double u, v;
+    if (c->o->wind_fn) {
+        c->o->wind_fn(c->x, c->y, ts, &u, &v);
+    } else {
+        double sg = (ts - c->t_start) * ((double)c->nseg * c->inv_DT);
+        double pu = c->cu[c->nseg], pv = c->cv[c->nseg];
+        for (int m = c->nseg - 1; m >= 0; m--) {
+            double a = sg - (double)m;
+            pu = fma(pu, a, c->cu[m]);
+            pv = fma(pv, a, c->cv[m]);
+        }
+        u = pu; v = pv;
+    }
     rhs(&c->o->P, z, u, v, c->M, c->pc, dz);
     (*nrhs)++;
 }
@@ -590,11 +626,38 @@ oracle_t* oracle_create(int Nx, int Ny, int bx, int by, const uint8_t* mask, con
 void oracle_destroy(oracle_t* o) {
     if (!o) return;
     free(o->mask); free(o->M); free(o->pc); free(o->part); free(o->ocean); free(o->S);
+    free(o->u_mid); free(o->v_mid); free(o->x); free(o->y);
     free(o);
 }
 
 void oracle_set_threads(oracle_t* o, int n) { o->nthreads = n < 1 ? 1 : n; }
 void oracle_set_accumulate(oracle_t* o, int on) { o->accumulate = on ? 1 : 0; }
+/* intermediate wind levels at t + k*DT/(n_mid+1), k = 1..n_mid, for the next oracle_step only */
+void oracle_set_wind_midlevels(oracle_t* o, int n_mid, const double* u_mid, const double* v_mid) {
+    size_t n = (size_t)o->Nx * o->Ny;
+    free(o->u_mid); free(o->v_mid);
+    o->u_mid = o->v_mid = NULL;
+    o->n_mid = n_mid;
+    if (n_mid > 0) {
+        o->u_mid = (double*)malloc(n_mid * n * sizeof(double));
+        o->v_mid = (double*)malloc(n_mid * n * sizeof(double));
+        memcpy(o->u_mid, u_mid, n_mid * n * sizeof(double));
+        memcpy(o->v_mid, v_mid, n_mid * n * sizeof(double));
+    }
+}
+/* reference semantics for the wind: call the closures at the home node and the stage time.
+   fn == NULL returns to staged levels. */
+void oracle_set_wind_closure(oracle_t* o, void (*fn)(double, double, double, double*, double*), const double* x,
+                             const double* y) {
+    size_t n = (size_t)o->Nx * o->Ny;
+    free(o->x); free(o->y);
+    o->x = o->y = NULL;
+    o->wind_fn = fn;
+    if (fn) {
+        o->x = (double*)malloc(n * sizeof(double)); memcpy(o->x, x, n * sizeof(double));
+        o->y = (double*)malloc(n * sizeof(double)); memcpy(o->y, y, n * sizeof(double));
+    }
+}
 
 /* init_particles! / SeedParticle, run.jl:199-247, core_2D.jl:434-488 */
 void oracle_seed(oracle_t* o, const double* u0, const double* v0) {
@@ -651,8 +714,18 @@ static int advance_particle(oracle_t* o, int64_t l, double DT, const double* u_t
         node_M(o, l, M);
         rhs_ctx_t c;
         c.o = o; c.M = M; c.pc = o->pc ? o->pc[l] : 0.0;
-        c.u0 = u_t[l]; c.v0 = v_t[l]; c.du = u_t1[l] - u_t[l]; c.dv = v_t1[l] - v_t[l];
+        {
+            int64_t n = (int64_t)o->Nx * o->Ny;
+            double wu[WIND_SEG_MAX + 1], wv[WIND_SEG_MAX + 1];
+            c.nseg = o->n_mid + 1;
+            wu[0] = u_t[l]; wv[0] = v_t[l];
+            for (int k = 1; k <= o->n_mid; k++) { wu[k] = o->u_mid[(k - 1) * n + l]; wv[k] = o->v_mid[(k - 1) * n + l]; }
+            wu[c.nseg] = u_t1[l]; wv[c.nseg] = v_t1[l];
+            wind_coefficients(wu, c.nseg, c.cu);
+            wind_coefficients(wv, c.nseg, c.cv);
+        }
         c.t_start = t_start; c.inv_DT = 1.0 / DT;
+        c.x = o->x ? o->x[l] : 0.0; c.y = o->y ? o->y[l] : 0.0;
         integrate(o, p, &c, DT, C, &o->stiff_triggers);
     } else { /* :172-185: wind at t_start+DT == the staged t1 level */
         double wu = u_t1[l], wv = v_t1[l];
@@ -757,6 +830,7 @@ void oracle_step(oracle_t* o, double t, double DT, const double* u_t, const doub
     free(on_local);
     for (int64_t m = 0; m < o->n_ocean; m++) remesh_particle(o, o->ocean[m], DT, u_t, v_t, &C);
     o->C = C;
+    o->n_mid = 0; /* intermediate levels are consumed by one step */
 }
 
 void oracle_get_state(const oracle_t* o, double* S) {
@@ -796,6 +870,60 @@ void oracle_fields(const oracle_t* o, double* Hs, double* cx, double* cy) {
 }
 int64_t oracle_stiff_triggers(const oracle_t* o) { return o->stiff_triggers; }
 void oracle_get_ocean_points(const oracle_t* o, int64_t* idx) { memcpy(idx, o->ocean, o->n_ocean * sizeof(int64_t)); }
+
+/* ------------------------------------------------------------------------ */
+/* gridded winds: Interpolations.LinearInterpolation((x,y,t), U, extrapolation_bc=Periodic())   */
+/* tests/T03_PIC_tripolar_realistic.jl:61-73, src/Utils/WindEmulator.jl:18-43.  Interpolations.jl  */
+/* is a third-party dependency absent from /root/reference (Project.toml, no [compat] bound); its  */
+/* published rule is restated: periodic(y,l,u) = mod(y-l, u-l) + l on every axis, knot interval  */
+/* i = clamp(searchsortedfirst(knots, y) - 1, 1, n-1), weights (1-d, d) with d = (y-k_i)/(k_i+1-k_i), */
+/* value = nested weighted sum, first axis outermost.                                             */
+/* ------------------------------------------------------------------------ */
+static double julia_mod(double x, double y) { /* Base.mod(::Float64, ::Float64) */
+    double r = fmod(x, y);
+    if (r == 0.0) return copysign(r, y);
+    if ((r > 0.0) != (y > 0.0)) return r + y;
+    return r;
+}
+static void knot_interval(const double* k, int n, double y, int* i, double* d) {
+    int first = 0; /* searchsortedfirst: number of knots < y */
+    while (first < n && k[first] < y) first++;
+    int idx = first - 1; /* 0-based */
+    if (idx < 0) idx = 0;
+    if (idx > n - 2) idx = n - 2;
+    *i = idx;
+    *d = (y - k[idx]) / (k[idx + 1] - k[idx]);
+}
+static double trilinear(const double* A, int nx, int ny, int ix, int iy, int it, double dx, double dy, double dt) {
+    double acc = 0.0;
+    const double wx[2] = {1.0 - dx, dx}, wy[2] = {1.0 - dy, dy}, wt[2] = {1.0 - dt, dt};
+    double sx[2];
+    for (int a = 0; a < 2; a++) {
+        double sy[2];
+        for (int b = 0; b < 2; b++) {
+            const double* p = A + (ix + a) + (int64_t)nx * (iy + b) + (int64_t)nx * ny * it;
+            sy[b] = wt[0] * p[0] + wt[1] * p[(int64_t)nx * ny];
+        }
+        sx[a] = wy[0] * sy[0] + wy[1] * sy[1];
+    }
+    acc = wx[0] * sx[0] + wx[1] * sx[1];
+    return acc;
+}
+void oracle_wind_mesh_sample(int nx, int ny, int nt, const double* xw, const double* yw, const double* tw,
+                             const double* U, const double* V, int64_t n, const double* x, const double* y, double t,
+                             double* u_out, double* v_out) {
+    int it;
+    double dt;
+    knot_interval(tw, nt, julia_mod(t - tw[0], tw[nt - 1] - tw[0]) + tw[0], &it, &dt);
+    for (int64_t l = 0; l < n; l++) {
+        int ix, iy;
+        double dx, dy;
+        knot_interval(xw, nx, julia_mod(x[l] - xw[0], xw[nx - 1] - xw[0]) + xw[0], &ix, &dx);
+        knot_interval(yw, ny, julia_mod(y[l] - yw[0], yw[ny - 1] - yw[0]) + yw[0], &iy, &dy);
+        u_out[l] = trilinear(U, nx, ny, ix, iy, it, dx, dy, dt);
+        v_out[l] = trilinear(V, nx, ny, ix, iy, it, dx, dy, dt);
+    }
+}
 
 /* ------------------------------------------------------------------------ */
 /* unit hooks for tests                                                       */
@@ -850,8 +978,14 @@ void oracle_integrate_one(const picles_params_t* P, const double* M, double pc, 
     p.t = *t; p.dt = *dt; p.qold = *qold; p.iter = *iter; p.dt_reset = (uint8_t)dt_reset; p.on = 1;
     p.status = *status;
     rhs_ctx_t c;
-    c.o = &o; c.M = M; c.pc = pc; c.u0 = wu0; c.v0 = wv0; c.du = wu1 - wu0; c.dv = wv1 - wv0;
-    c.t_start = p.t; c.inv_DT = 1.0 / DT;
+    c.o = &o; c.M = M; c.pc = pc;
+    {
+        double wu[2] = {wu0, wu1}, wv[2] = {wv0, wv1};
+        c.nseg = 1;
+        wind_coefficients(wu, 1, c.cu);
+        wind_coefficients(wv, 1, c.cv);
+    }
+    c.t_start = p.t; c.inv_DT = 1.0 / DT; c.x = 0.0; c.y = 0.0;
     picles_counters_t C;
     memset(&C, 0, sizeof C);
     integrate(&o, &p, &c, DT, &C, &o.stiff_triggers);

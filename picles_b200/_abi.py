@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PICLES_B200_LIB", os.path.join(HERE, "libpicles_b200.so"))
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums (include/picles_b200.h)
 BND_NONPERIODIC, BND_PERIODIC, BND_TRIPOLAR_NORTH = 0, 1, 2
@@ -115,6 +115,7 @@ SYMBOLS = {
     "picles_seed": (C.c_int, [_vp, _vp, _vp]),
     "picles_step": (C.c_int, [_vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp]),
     "picles_upload_winds": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "picles_set_wind_midlevels": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "picles_step_advance": (C.c_int, [_vp, C.c_double, C.c_double]),
     "picles_halo_buffers": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
                                       C.POINTER(C.c_int64)]),
@@ -128,6 +129,10 @@ SYMBOLS = {
     "picles_comm_destroy": (C.c_int, [_vp]),
     "picles_halo_exchange": (C.c_int, [_vp, C.c_int, C.c_int]),
     "picles_step_strip": (C.c_int, [_vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
+    "picles_set_wind_mesh": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "picles_sample_wind_mesh": (C.c_int, [_vp, C.c_double, _vp, _vp]),
+    "picles_seed_wind_mesh": (C.c_int, [_vp, C.c_double]),
+    "picles_step_wind_mesh": (C.c_int, [_vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]),
     "picles_get_state": (C.c_int, [_vp, _vp]),
     "picles_set_state": (C.c_int, [_vp, _vp]),
     "picles_checkpoint_size": (C.c_int, [_vp, C.POINTER(C.c_int64)]),

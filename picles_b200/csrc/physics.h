@@ -46,6 +46,7 @@
 #define PH_CELL_INVALID ((int32_t)-1)
 #define PH_CELL_BIAS 8192
 #define PH_REACH_MAX 15
+#define PH_WIND_SEG_MAX (PICLES_WIND_MID_MAX + 1) /* time segments of the staged wind: levels - 1 */
 
 namespace picles {
 
@@ -107,7 +108,10 @@ PM_HD const Tableau& tableau(int solver) {
    host. */
 enum {
     KS_U3 = 21, KS_U4, KS_X7, KS_Y7, KS_XE, KS_YE, KS_TSTOP, KS_LQ, KS_QOLD, KS_DT0, KS_D1N, KS_DTMIN,
-    KS_WDU, KS_WDV, KS_WT0, KS_WIDT, KS_SLOTS
+    KS_WT0, KS_WIDT,
+    KS_WCU,                            /* Newton coefficients c_1..c_4 of the wind's u component in time */
+    KS_WCV = KS_WCU + PH_WIND_SEG_MAX, /* ... and of v */
+    KS_SLOTS = KS_WCV + PH_WIND_SEG_MAX
 };
 struct KLocal {
     double k[KS_SLOTS];
@@ -134,17 +138,41 @@ struct Particle {
     uint8_t status; /* PICLES_PST_* */
 };
 
-/* wind at the home node: level t and the increment to level t+DT */
+/* wind at the home node: nseg+1 levels equally spaced over [t, t+DT] (lvl[0] = level t,
+   lvl[nseg] = level t+DT; nseg = 1 unless intermediate levels were staged) */
 struct Wind {
-    double u0, v0, du, dv;
+    double ul[PH_WIND_SEG_MAX + 1], vl[PH_WIND_SEG_MAX + 1];
+    int nseg;
     double t_start, inv_DT;
 };
+
+/* Newton forward-difference coefficients of the interpolant through equally spaced levels:
+   w(sigma) = c0 + sigma*(c1 + (sigma-1)*(c2 + (sigma-2)*(c3 + (sigma-3)*c4))), sigma = nseg*(t - t0)/DT,
+   c_m = Delta^m w_0 / m!.  Two levels: c1 = w1 - w0, the linear rule.  In place: l[0..nseg] -> c[0..nseg]. */
+PM_HD void wind_newton(double* l, int nseg) {
+    /* compile-time trip counts, predicated on nseg: every index is an immediate after unrolling,
+       so the levels stay in registers on the device */
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int m = 1; m <= PH_WIND_SEG_MAX; m++) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = PH_WIND_SEG_MAX; k >= m; k--)
+            if (k <= nseg) l[k] = l[k] - l[k - 1];
+    }
+    if (nseg >= 2) l[2] = l[2] * 0.5;
+    if (nseg >= 3) l[3] = l[3] * (1.0 / 6.0);
+    if (nseg >= 4) l[4] = l[4] * (1.0 / 24.0);
+}
 
 /* loop invariants of one particle's integration, hoisted out of the stage loop */
 struct Hoist {
     double y_rg, y_eT; /* Newton reciprocals of r_g and e_T (fast path only) */
     double us0;        /* sqrt(u0^2+v0^2): the wind speed when the wind does not change over DT */
-    bool steady;       /* du == 0 && dv == 0 */
+    bool steady;       /* every time coefficient of the staged wind is zero */
+    int nseg;          /* time segments of the staged wind (levels - 1) */
 };
 
 /* per-thread counter deltas */
@@ -352,32 +380,41 @@ PM_HD void prop(const picles_params_t& P, const double* M, double cx, double cy,
     }
 }
 
-/* wind at stage time ts (linear between the two staged levels) and its speed.  A wind
-   that does not change over DT (du = dv = 0) gives u0, v0 and the hoisted us0 exactly; the
-   increments and the time base of an unsteady wind live in the scratch slots. */
+/* wind at stage time ts: the polynomial through the staged levels (linear for the two levels
+   t, t+DT).  A wind that does not change over DT gives u0, v0 and the hoisted us0 exactly; the
+   time coefficients and the time base of an unsteady wind live in the scratch slots. */
+template <class KS>
+PM_HD void stage_uv(double wu0, double wv0, const Hoist& H, const KS& K, double ts, double& u, double& v) {
+    double sg = (ts - K.ld(KS_WT0)) * K.ld(KS_WIDT);
+    int m = H.nseg - 1;
+    double pu = K.ld(KS_WCU + m), pv = K.ld(KS_WCV + m);
+    for (; m >= 1; m--) {
+        double a = sg - (double)m;
+        pu = fma(pu, a, K.ld(KS_WCU + m - 1));
+        pv = fma(pv, a, K.ld(KS_WCV + m - 1));
+    }
+    u = fma(pu, sg, wu0);
+    v = fma(pv, sg, wv0);
+}
 template <class O, class KS>
 PM_HD void stage_wind(double wu0, double wv0, const Hoist& H, const KS& K, double ts, double& u, double& v, double& us,
                       unsigned* bad) {
     if (H.steady) {
         u = wu0; v = wv0; us = H.us0;
     } else {
-        double s = (ts - K.ld(KS_WT0)) * K.ld(KS_WIDT);
-        u = fma(K.ld(KS_WDU), s, wu0);
-        v = fma(K.ld(KS_WDV), s, wv0);
+        stage_uv(wu0, wv0, H, K, ts, u, v);
         us = O::sqrtz(u * u + v * v, bad);
     }
 }
 
-/* IEEE right-hand side, one shared out-of-line copy: the FSAL reset, the initial-step
-   heuristic, and the fallback of the fast path.  Everything by value: nothing of the
-   caller is forced into local memory. */
+/* IEEE right-hand side, one shared out-of-line copy: the fallback of the fast path (and the
+   only path on the host).  Everything by value: nothing of the caller is forced into local
+   memory. */
 struct D3 { double d0, d1, d2; };
-PM_HD_NOINLINE_DECL D3 f3_cold(const picles_params_t* Pp, double wu0, double wv0, double wdu, double wdv, double wt0,
-                               double widt, double pc, double lne, double cx, double cy, double ts) {
+PM_HD_NOINLINE_DECL D3 f3_cold(const picles_params_t* Pp, double u, double v, double pc, double lne, double cx,
+                               double cy) {
     Hoist H;
-    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false;
-    double s = (ts - wt0) * widt;
-    double u = fma(wdu, s, wu0), v = fma(wdv, s, wv0);
+    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false; H.nseg = 1;
     double us = sqrt(u * u + v * v);
     D3 r;
     rhs3<OpsSafe>(*Pp, H, lne, cx, cy, u, v, us, pc, r.d0, r.d1, r.d2, (unsigned*)0);
@@ -385,15 +422,16 @@ PM_HD_NOINLINE_DECL D3 f3_cold(const picles_params_t* Pp, double wu0, double wv0
 }
 
 /* loop invariants of the hot right-hand side */
-PM_HD void make_hoist(const picles_params_t& P, const Wind& w, Hoist& H) {
+PM_HD void make_hoist(const picles_params_t& P, double wu0, double wv0, bool steady, int nseg, Hoist& H) {
 #if defined(__CUDA_ARCH__)
     H.y_rg = pm_rcp_newton(P.r_g);
     H.y_eT = pm_rcp_newton(P.e_T);
 #else
     H.y_rg = 0.0; H.y_eT = 0.0;
 #endif
-    H.steady = (w.du == 0.0) && (w.dv == 0.0);
-    H.us0 = sqrt(w.u0 * w.u0 + w.v0 * w.v0);
+    H.steady = steady;
+    H.nseg = nseg;
+    H.us0 = sqrt(wu0 * wu0 + wv0 * wv0);
 }
 
 /* hot right-hand side of the stage loop */
@@ -406,12 +444,13 @@ PM_HD void f3(const picles_params_t& P, double wu0, double wv0, const Hoist& H, 
     stage_wind<OpsFast>(wu0, wv0, H, K, ts, u, v, us, &bad);
     rhs3<OpsFast>(P, H, lne, cx, cy, u, v, us, pc, d0, d1, d2, &bad);
     if (bad) { /* rare: denormal/huge/non-finite operands */
-        D3 r = f3_cold(&P, wu0, wv0, K.ld(KS_WDU), K.ld(KS_WDV), K.ld(KS_WT0), K.ld(KS_WIDT), pc, lne, cx, cy, ts);
+        D3 r = f3_cold(&P, u, v, pc, lne, cx, cy);
         d0 = r.d0; d1 = r.d1; d2 = r.d2;
     }
 #else
-    (void)H;
-    D3 r = f3_cold(&P, wu0, wv0, K.ld(KS_WDU), K.ld(KS_WDV), K.ld(KS_WT0), K.ld(KS_WIDT), pc, lne, cx, cy, ts);
+    double u = wu0, v = wv0;
+    if (!H.steady) stage_uv(wu0, wv0, H, K, ts, u, v);
+    D3 r = f3_cold(&P, u, v, pc, lne, cx, cy);
     d0 = r.d0; d1 = r.d1; d2 = r.d2;
 #endif
 }
@@ -544,9 +583,29 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
     if (p.status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE)) return;
     const Tableau& T = tableau(P.solver);
     Hoist H;
-    make_hoist(P, w, H);
-    const double wu0 = w.u0, wv0 = w.v0;
-    K.st(KS_WDU, w.du); K.st(KS_WDV, w.dv); K.st(KS_WT0, w.t_start); K.st(KS_WIDT, w.inv_DT);
+    const double wu0 = w.ul[0], wv0 = w.vl[0];
+    {
+        /* time coefficients of the staged wind -> scratch slots (two levels: c1 = the increment) */
+        double cu[PH_WIND_SEG_MAX + 1], cv[PH_WIND_SEG_MAX + 1];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int m = 0; m <= PH_WIND_SEG_MAX; m++) { cu[m] = w.ul[m]; cv[m] = w.vl[m]; }
+        wind_newton(cu, w.nseg);
+        wind_newton(cv, w.nseg);
+        bool steady = true;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int m = 1; m <= PH_WIND_SEG_MAX; m++) {
+            if (m <= w.nseg) {
+                K.st(KS_WCU + m - 1, cu[m]); K.st(KS_WCV + m - 1, cv[m]);
+                steady = steady && (cu[m] == 0.0) && (cv[m] == 0.0);
+            }
+        }
+        make_hoist(P, wu0, wv0, steady, w.nseg, H);
+    }
+    K.st(KS_WT0, w.t_start); K.st(KS_WIDT, (double)w.nseg * w.inv_DT);
     double t = p.t;
     K.st(KS_TSTOP, t + DT);
     double u0 = p.u0, u1 = p.u1, u2 = p.u2;
@@ -973,14 +1032,24 @@ PM_HD void gather_node(const RecView& V, int I, int J, int R, int n_classes, dou
 }
 
 /* ---- advance! (everything except the scatter, which the gather replaces) ----- */
+/* um/vm: the nmid intermediate wind levels at t + k*DT/(nmid+1), k = 1..nmid (nmid = 0: none) */
 template <class KS>
 PM_HD void advance_particle(const picles_params_t& P, Particle& p, int mask, double DT, double wu0, double wv0,
-                            double wu1, double wv1, const double* M, double pc, Record& rec, Tally& c, KS& K) {
+                            double wu1, double wv1, int nmid, const double* um, const double* vm, const double* M,
+                            double pc, Record& rec, Tally& c, KS& K) {
     double t_start = p.t;
     bool on = (p.flags & PICLES_PF_ON) != 0;
     if (on) {
         Wind w;
-        w.u0 = wu0; w.v0 = wv0; w.du = wu1 - wu0; w.dv = wv1 - wv0;
+        w.nseg = nmid + 1;
+        w.ul[0] = wu0; w.vl[0] = wv0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 1; k <= PH_WIND_SEG_MAX; k++) { /* levels 1..nseg: the intermediate ones, then t+DT */
+            w.ul[k] = (k <= nmid) ? um[k - 1] : ((k == nmid + 1) ? wu1 : 0.0);
+            w.vl[k] = (k <= nmid) ? vm[k - 1] : ((k == nmid + 1) ? wv1 : 0.0);
+        }
         w.t_start = t_start; w.inv_DT = 1.0 / DT;
         integrate(P, w, M, pc, DT, p, c, K);
     } else {

@@ -52,6 +52,11 @@ struct picles_handle {
     cudaStream_t snap_stream = nullptr; /* D2H of snapshots: its own stream, so wind uploads are not queued behind it */
     cudaEvent_t snap_ev[2] = {nullptr, nullptr}; /* staging copy done / D2H done */
     bool snap_pending = false;
+    DeviceWindMesh wm = {};        /* resident wind mesh + node coordinates (picles_set_wind_mesh) */
+    std::vector<void*> wm_allocs;
+    bool have_wind_mesh = false;
+    bool wm_t1_valid = false;      /* the t1 wind level was sampled from the mesh at wm_t1_time */
+    double wm_t1_time = 0.0;
     void* comm = nullptr; /* ncclComm_t of the strip communicator */
     int comm_rank = -1, comm_size = 0;
     char err[512];
@@ -129,6 +134,10 @@ static void free_grid(picles_t* h) {
     if (h->snap_stream) cudaStreamSynchronize(h->snap_stream); /* a snapshot may still read the staging copy */
     for (void* p : h->allocs) cudaFree(p);
     h->allocs.clear();
+    for (void* p : h->wm_allocs) cudaFree(p);
+    h->wm_allocs.clear();
+    h->wm = DeviceWindMesh{};
+    h->have_wind_mesh = h->wm_t1_valid = false;
     memset(&h->A, 0, sizeof h->A);
     h->send_lo = h->send_hi = h->recv_lo = h->recv_hi = nullptr;
     h->snap = nullptr;
@@ -425,6 +434,22 @@ static int need_ready(picles_t* h, bool seeded) {
     return 0;
 }
 
+/* SeedParticle from the wind already in the t1 slots (the first step's t level, see picles_step) */
+static int seed_from_t1(picles_t* h) {
+    DeviceArrays& A = h->A;
+    int64_t n = (int64_t)A.Nx * A.ny;
+    launch_seed(A, h->P, A.u_t1, A.v_t1, h->sms, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(A.u_t, A.u_t1, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(A.v_t, A.v_t1, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    A.n_mid = 0;
+    h->seeded = true;
+    h->winds_loaded = true;
+    memset(&h->last, 0, sizeof h->last);
+    return PICLES_OK;
+}
+
 int picles_seed(picles_t* h, const double* u0, const double* v0) {
     int rc = need_ready(h, false);
     if (rc) return rc;
@@ -434,14 +459,35 @@ int picles_seed(picles_t* h, const double* u0, const double* v0) {
     /* stage the t=0 wind in the t1 slots: the first step's t level (see picles_step) */
     CK(cudaMemcpyAsync(A.u_t1, u0, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(A.v_t1, v0, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
-    launch_seed(A, h->P, A.u_t1, A.v_t1, h->sms, h->stream);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(A.u_t, A.u_t1, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(A.v_t, A.v_t1, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    h->seeded = true;
-    h->winds_loaded = true;
-    memset(&h->last, 0, sizeof h->last);
+    h->wm_t1_valid = false;
+    return seed_from_t1(h);
+}
+
+/* intermediate wind levels of the next step (host planes -> device, consumed by the next advance) */
+static int ensure_mid_planes(picles_t* h, int n_mid) {
+    DeviceArrays& A = h->A;
+    const int64_t n = (int64_t)A.Nx * A.ny;
+    for (int k = 0; k < n_mid; k++) {
+        if (!A.u_mid[k]) { DALLOC(A.u_mid[k], n); DALLOC(A.v_mid[k], n); }
+    }
+    return PICLES_OK;
+}
+int picles_set_wind_midlevels(picles_t* h, int n_mid, const double* u_mid, const double* v_mid) {
+    int rc = need_ready(h, true);
+    if (rc) return rc;
+    if (n_mid < 0 || n_mid > PICLES_WIND_MID_MAX) return fail(h, PICLES_ERR_ARG, "n_mid = %d outside 0..%d", n_mid, PICLES_WIND_MID_MAX);
+    if (n_mid > 0 && (!u_mid || !v_mid)) return fail(h, PICLES_ERR_ARG, "picles_set_wind_midlevels: level arrays are required");
+    DeviceArrays& A = h->A;
+    rc = ensure_mid_planes(h, n_mid);
+    if (rc) return rc;
+    const int64_t n = (int64_t)A.Nx * A.ny;
+    /* same stream as the kernels: ordered after the previous step's advance, before the next one */
+    for (int k = 0; k < n_mid; k++) {
+        CK(cudaMemcpyAsync(A.u_mid[k], u_mid + (int64_t)k * n, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(A.v_mid[k], v_mid + (int64_t)k * n, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (n_mid > 0) CK(cudaStreamSynchronize(h->stream)); /* the host arrays may be reused on return */
+    A.n_mid = n_mid;
     return PICLES_OK;
 }
 
@@ -452,6 +498,7 @@ int picles_upload_winds(picles_t* h, const double* u_t, const double* v_t, const
     size_t bytes = (size_t)A.Nx * A.ny * 8;
     if ((u_t == nullptr) != (v_t == nullptr) || (u_t1 == nullptr) != (v_t1 == nullptr))
         return fail(h, PICLES_ERR_ARG, "wind components must be given in pairs");
+    if (u_t || u_t1) h->wm_t1_valid = false;
     if (u_t) {
         CK(cudaMemcpyAsync(A.u_t, u_t, bytes, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(A.v_t, v_t, bytes, cudaMemcpyHostToDevice, h->stream));
@@ -493,6 +540,7 @@ static int begin_advance(picles_t* h, double dt_model, const double* u_t, const 
     if ((u_t == nullptr) != (v_t == nullptr) || (u_t1 == nullptr) != (v_t1 == nullptr))
         return fail(h, PICLES_ERR_ARG, "wind components must be given in pairs");
     if (!(dt_model > 0)) return fail(h, PICLES_ERR_ARG, "dt_model must be positive");
+    if (u_t || u_t1) h->wm_t1_valid = false;
     if (!u_t && u_t1) { /* the previous step's t+DT level is this step's t level: swap, no copy */
         double* tu = A.u_t; A.u_t = A.u_t1; A.u_t1 = tu;
         double* tv = A.v_t; A.v_t = A.v_t1; A.v_t1 = tv;
@@ -619,6 +667,7 @@ int picles_step_project_remesh(picles_t* h, double t, double dt_model) {
     /* a halo exchange may have run since the advance: ms_project brackets the gather alone */
     CK(cudaEventRecord(h->ev[2], h->stream));
     launch_project_remesh(h->maps, h->A, h->P, dt_model, h->P.periodic_boundary ? 2 : 1, h->accumulate, wide_tiles(h), h->d_counters, h->stream);
+    h->A.n_mid = 0; /* intermediate wind levels are consumed by one step */
     CK(cudaEventRecord(h->ev[3], h->stream));
     CK(cudaEventRecord(h->ev[4], h->stream));
     CK(cudaGetLastError());
@@ -641,6 +690,7 @@ int picles_step(picles_t* h, double t, double dt_model, const double* u_t, const
     if (rc) return rc;
     CK(cudaEventRecord(h->ev[2], h->stream));
     launch_project_remesh(h->maps, h->A, h->P, dt_model, h->P.periodic_boundary ? 2 : 1, h->accumulate, wide_tiles(h), h->d_counters, h->stream);
+    h->A.n_mid = 0; /* intermediate wind levels are consumed by one step */
     CK(cudaEventRecord(h->ev[3], h->stream));
     CK(cudaEventRecord(h->ev[4], h->stream));
     CK(cudaGetLastError());
@@ -999,6 +1049,8 @@ int picles_checkpoint_load(picles_t* h, const void* blob, int64_t nbytes) {
     CK(cudaGetLastError());
     h->seeded = true;
     h->winds_loaded = true;
+    h->wm_t1_valid = false;
+    h->A.n_mid = 0;
     memset(&h->last, 0, sizeof h->last);
     return PICLES_OK;
 }
@@ -1115,6 +1167,106 @@ int picles_step_strip(picles_t* h, double t, double dt_model, const double* u_t,
     CK(cudaGetLastError());
     CK(cudaStreamWaitEvent(h->stream, exchanged, 0));
     return picles_step_project_remesh(h, t, dt_model);
+}
+
+/* ---- wind ingestion: resident wind mesh ---------------------------------------------------- */
+static int wm_alloc_copy(picles_t* h, double** dst, const double* src, int64_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (size_t)count * sizeof(double));
+    if (e != cudaSuccess) return fail(h, PICLES_ERR_ALLOC, "cudaMalloc(%lld bytes): %s", (long long)(count * sizeof(double)), cudaGetErrorString(e));
+    h->wm_allocs.push_back(q);
+    e = cudaMemcpyAsync(q, src, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) return fail(h, PICLES_ERR_CUDA, "wind mesh upload: %s", cudaGetErrorString(e));
+    *dst = (double*)q;
+    return 0;
+}
+static bool strictly_increasing(const double* k, int n) {
+    for (int i = 0; i < n; i++) {
+        if (!(k[i] == k[i]) || (i > 0 && !(k[i] > k[i - 1]))) return false;
+    }
+    return true;
+}
+int picles_set_wind_mesh(picles_t* h, int nxw, int nyw, int ntw, const double* xw, const double* yw, const double* tw,
+                         const double* U, const double* V, const double* node_x, const double* node_y) {
+    if (!h || !h->have_grid) return fail(h, PICLES_ERR_STATE, "picles_set_grid must be called first");
+    if (nxw < 2 || nyw < 2 || ntw < 2) return fail(h, PICLES_ERR_ARG, "wind mesh needs at least 2 knots per axis (%d, %d, %d)", nxw, nyw, ntw);
+    if (!xw || !yw || !tw || !U || !V || !node_x || !node_y) return fail(h, PICLES_ERR_ARG, "picles_set_wind_mesh: null array");
+    if (!strictly_increasing(xw, nxw) || !strictly_increasing(yw, nyw) || !strictly_increasing(tw, ntw))
+        return fail(h, PICLES_ERR_ARG, "wind mesh knot vectors must be strictly increasing");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    for (void* p : h->wm_allocs) cudaFree(p);
+    h->wm_allocs.clear();
+    h->have_wind_mesh = h->wm_t1_valid = false;
+    DeviceWindMesh& W = h->wm;
+    W = DeviceWindMesh{};
+    W.nx = nxw; W.ny = nyw; W.nt = ntw;
+    const int64_t n = (int64_t)h->A.Nx * h->A.ny, nm = (int64_t)nxw * nyw * ntw;
+    int rc;
+    if ((rc = wm_alloc_copy(h, &W.xw, xw, nxw)) || (rc = wm_alloc_copy(h, &W.yw, yw, nyw)) ||
+        (rc = wm_alloc_copy(h, &W.tw, tw, ntw)) || (rc = wm_alloc_copy(h, &W.U, U, nm)) ||
+        (rc = wm_alloc_copy(h, &W.V, V, nm)) || (rc = wm_alloc_copy(h, &W.node_x, node_x, n)) ||
+        (rc = wm_alloc_copy(h, &W.node_y, node_y, n)))
+        return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_wind_mesh = true;
+    return PICLES_OK;
+}
+
+int picles_sample_wind_mesh(picles_t* h, double t, double* u_out, double* v_out) {
+    if (!h || !h->have_wind_mesh) return fail(h, PICLES_ERR_STATE, "picles_set_wind_mesh must be called first");
+    if (!u_out || !v_out) return fail(h, PICLES_ERR_ARG, "null output");
+    CK(cudaSetDevice(h->device));
+    const int64_t n = (int64_t)h->A.Nx * h->A.ny;
+    double* tmp = nullptr;
+    if (cudaMalloc((void**)&tmp, (size_t)n * 16) != cudaSuccess) return fail(h, PICLES_ERR_ALLOC, "cannot allocate %lld bytes", (long long)n * 16);
+    launch_wind_sample(h->wm, n, t, tmp, tmp + n, h->sms, h->stream);
+    cudaError_t e = cudaMemcpyAsync(u_out, tmp, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(v_out, tmp + n, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(h, PICLES_ERR_CUDA, "k_wind_sample: %s", cudaGetErrorString(e));
+    return PICLES_OK;
+}
+
+int picles_seed_wind_mesh(picles_t* h, double t0) {
+    int rc = need_ready(h, false);
+    if (rc) return rc;
+    if (!h->have_wind_mesh) return fail(h, PICLES_ERR_STATE, "picles_set_wind_mesh must be called first");
+    DeviceArrays& A = h->A;
+    launch_wind_sample(h->wm, (int64_t)A.Nx * A.ny, t0, A.u_t1, A.v_t1, h->sms, h->stream);
+    h->wm_t1_valid = true;
+    h->wm_t1_time = t0;
+    return seed_from_t1(h);
+}
+
+int picles_step_wind_mesh(picles_t* h, double t, double dt_model, int n_mid, int lo_rank, int hi_rank) {
+    int rc = need_ready(h, true);
+    if (rc) return rc;
+    if (!h->have_wind_mesh) return fail(h, PICLES_ERR_STATE, "picles_set_wind_mesh must be called first");
+    if (!(dt_model > 0)) return fail(h, PICLES_ERR_ARG, "dt_model must be positive");
+    if (n_mid < 0 || n_mid > PICLES_WIND_MID_MAX) return fail(h, PICLES_ERR_ARG, "n_mid = %d outside 0..%d", n_mid, PICLES_WIND_MID_MAX);
+    DeviceArrays& A = h->A;
+    const int64_t n = (int64_t)A.Nx * A.ny;
+    rc = ensure_mid_planes(h, n_mid);
+    if (rc) return rc;
+    if (h->wm_t1_valid && h->wm_t1_time == t) { /* the previous step's t+dt level is this step's t level */
+        double* tu = A.u_t; A.u_t = A.u_t1; A.u_t1 = tu;
+        double* tv = A.v_t; A.v_t = A.v_t1; A.v_t1 = tv;
+    } else {
+        launch_wind_sample(h->wm, n, t, A.u_t, A.v_t, h->sms, h->stream);
+    }
+    const double t1 = t + dt_model;
+    launch_wind_sample(h->wm, n, t1, A.u_t1, A.v_t1, h->sms, h->stream);
+    for (int k = 1; k <= n_mid; k++)
+        launch_wind_sample(h->wm, n, t + dt_model * (double)k / (double)(n_mid + 1), A.u_mid[k - 1], A.v_mid[k - 1], h->sms, h->stream);
+    CK(cudaGetLastError());
+    A.n_mid = n_mid;
+    h->wm_t1_valid = true;
+    h->wm_t1_time = t1;
+    if (A.ny == A.Ny && lo_rank < 0 && hi_rank < 0) return picles_step(h, t, dt_model, nullptr, nullptr, nullptr, nullptr);
+    return picles_step_strip(h, t, dt_model, nullptr, nullptr, nullptr, nullptr, lo_rank, hi_rank);
 }
 
 } /* extern "C" */

@@ -55,6 +55,8 @@ struct DeviceArrays {
     int32_t* iter;
     uint8_t *flags, *status, *mask;
     double *u_t, *v_t, *u_t1, *v_t1; /* staged winds at t and t+DT */
+    double *u_mid[PICLES_WIND_MID_MAX], *v_mid[PICLES_WIND_MID_MAX]; /* intermediate levels (allocated on first use) */
+    int n_mid;                       /* intermediate levels staged for the next advance (0: linear in time) */
     double* M[4];                    /* per-node projection kernel planes, or nullptr */
     double Mc[4];                    /* uniform projection kernel */
     double* pc;                      /* great-circle coefficient plane, or nullptr */
@@ -86,6 +88,13 @@ int project_remesh_smem_bytes();
 cudaError_t project_remesh_configure();
 void launch_project_remesh(const ProjectMaps& maps, const DeviceArrays& A, const picles_params_t& P, double DT,
                            int n_classes, int accumulate, int wide, DeviceCounters* dc, cudaStream_t st);
+/* gridded wind field resident on the device (wind_mesh.h) + the node coordinates it is sampled at */
+struct DeviceWindMesh {
+    int nx, ny, nt;
+    double *xw, *yw, *tw, *U, *V;
+    double *node_x, *node_y; /* ny*Nx each */
+};
+void launch_wind_sample(const DeviceWindMesh& W, int64_t n, double t, double* u_out, double* v_out, int sms, cudaStream_t st);
 void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cudaStream_t st);
 void launch_halo_pack(const DeviceArrays& A, char* lo, char* hi, int sms, cudaStream_t st);
 void launch_halo_unpack(const DeviceArrays& A, const char* lo, const char* hi, DeviceCounters* dc, int sms, cudaStream_t st);

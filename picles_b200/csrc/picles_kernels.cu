@@ -24,6 +24,7 @@
 #include "physics.h"
 #include "picles_device.h"
 #include "pmath_trig.h"
+#include "wind_mesh.h"
 
 namespace picles {
 
@@ -147,7 +148,14 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int6
         else { M[0] = A.Mc[0]; M[1] = A.Mc[1]; M[2] = A.Mc[2]; M[3] = A.Mc[3]; }
         double pc = A.pc ? A.pc[l] : 0.0;
         Record r;
-        advance_particle(P, p, A.mask[l], DT, A.u_t[l], A.v_t[l], A.u_t1[l], A.v_t1[l], M, pc, r, c, K);
+        double um[PH_WIND_SEG_MAX], vm[PH_WIND_SEG_MAX];
+#pragma unroll
+        for (int k = 0; k < PICLES_WIND_MID_MAX; k++) {
+            if (k < A.n_mid) { um[k] = A.u_mid[k][l]; vm[k] = A.v_mid[k][l]; }
+            else { um[k] = 0.0; vm[k] = 0.0; }
+        }
+        um[PH_WIND_SEG_MAX - 1] = 0.0; vm[PH_WIND_SEG_MAX - 1] = 0.0;
+        advance_particle(P, p, A.mask[l], DT, A.u_t[l], A.v_t[l], A.u_t1[l], A.v_t1[l], A.n_mid, um, vm, M, pc, r, c, K);
         store_particle(A, l, p);
         store_record(A, le, r);
         if (r.cell != PH_CELL_INVALID) {
@@ -597,6 +605,23 @@ __global__ void k_selftest_math(uint64_t seed, int iters, unsigned long long* ou
     atomicAdd(&out[3], n_sqrt); atomicAdd(&out[4], bad_sqrt); atomicAdd(&out[5], mis_sqrt);
 }
 
+/* ---- wind ingestion: sample the resident wind mesh at the nodes ---------------------------
+ * One thread per node: 16 B of coordinates in, 16 B of wind out (HBM-bound); the mesh (coarse:
+ * knots and 2 x 2 x 2 corner values per component) is served by L1/L2.  The time interval is the
+ * same for all nodes and located once per thread from the (tiny) time knot vector. */
+__global__ void __launch_bounds__(256) k_wind_sample(DeviceWindMesh D, int64_t n, double t, double* __restrict__ u_out,
+                                                     double* __restrict__ v_out) {
+    WindMesh W;
+    W.nx = D.nx; W.ny = D.ny; W.nt = D.nt; W.xw = D.xw; W.yw = D.yw; W.tw = D.tw; W.U = D.U; W.V = D.V;
+    const WindMeshTime T = wm_time(W, t);
+    for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x) {
+        double u, v;
+        wm_sample(W, T, D.node_x[l], D.node_y[l], u, v);
+        u_out[l] = u;
+        v_out[l] = v;
+    }
+}
+
 /* ---- launchers ------------------------------------------------------------------ */
 static int grid_for(int64_t n, int threads, int sms, int blocks_per_sm) {
     int64_t need = (n + threads - 1) / threads;
@@ -648,6 +673,9 @@ void launch_project_remesh(const ProjectMaps& maps, const DeviceArrays& A, const
     else k_project_remesh<PR_HY_NARROW><<<grid, PR_THREADS, project_remesh_smem_bytes(), st>>>(maps, A, P, DT, n_classes, accumulate, dc);
 }
 
+void launch_wind_sample(const DeviceWindMesh& W, int64_t n, double t, double* u_out, double* v_out, int sms, cudaStream_t st) {
+    if (n > 0) k_wind_sample<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(W, n, t, u_out, v_out);
+}
 void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cudaStream_t st) {
     k_energy<<<nblocks, 256, 0, st>>>(e, n, partial);
 }

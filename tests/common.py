@@ -78,6 +78,7 @@ def make_oracle(grid, P, variant="default", threads=1):
 
 def _build_shim():
     deps = [SHIM_SRC, os.path.join(ROOT, "picles_b200", "csrc", "physics.h"),
+            os.path.join(ROOT, "picles_b200", "csrc", "wind_mesh.h"),
             os.path.join(ROOT, "picles_b200", "csrc", "pmath.h"), os.path.join(ROOT, "include", "picles_b200.h")]
     if os.path.exists(SHIM_SO) and all(os.path.getmtime(SHIM_SO) >= os.path.getmtime(d) for d in deps):
         return
@@ -103,6 +104,8 @@ def shim_lib():
         lib.shim_create.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(PiclesParams)]
         lib.shim_destroy.argtypes = [vp]
         lib.shim_set_accumulate.argtypes = [vp, i32]
+        lib.shim_set_wind_midlevels.argtypes = [vp, i32, vp, vp, i64]
+        lib.shim_wind_mesh_sample.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i64, vp, vp, d, vp, vp]
         lib.shim_seed.argtypes = [vp, vp, vp]
         lib.shim_step.argtypes = [vp, d, d, vp, vp, vp, vp]
         lib.shim_get_state.argtypes = [vp, vp]
@@ -164,6 +167,13 @@ class HostShim:
     def seed(self, u0, v0):
         a, b = self._full(u0), self._full(v0)
         self.lib.shim_seed(self.h, _p(a), _p(b))
+
+    def set_wind_midlevels(self, u_mid, v_mid):
+        """intermediate wind levels of the next step: sequences of (Ny, Nx) arrays"""
+        n = len(u_mid)
+        um = np.ascontiguousarray(np.stack([self._full(x) for x in u_mid])) if n else np.zeros((0, self.Ny, self.Nx))
+        vm = np.ascontiguousarray(np.stack([self._full(x) for x in v_mid])) if n else np.zeros((0, self.Ny, self.Nx))
+        self.lib.shim_set_wind_midlevels(self.h, n, _p(um), _p(vm), self.Ny * self.Nx)
 
     def step(self, t, DT, u_t, v_t, u_t1, v_t1):
         a = [self._full(x) for x in (u_t, v_t, u_t1, v_t1)]

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../picles_b200/csrc/physics.h"
+#include "../picles_b200/csrc/wind_mesh.h"
 
 using namespace picles;
 
@@ -32,6 +33,8 @@ struct Shim {
     Tally tally;
     int accumulate = 0;
     int reach_halo = 0; /* per-process strips: max reach of the received halo records */
+    int n_mid = 0;      /* intermediate wind levels of the next step (global planes, consumed by it) */
+    std::vector<double> u_mid, v_mid;
 };
 
 static void load(const Strip& s, int64_t l, Particle& p) {
@@ -83,6 +86,22 @@ Shim* shim_create(int Nx, int Ny, int bx, int by, int nstrips, int halo, const u
 }
 void shim_destroy(Shim* h) { delete h; }
 void shim_set_accumulate(Shim* h, int on) { h->accumulate = on ? 1 : 0; }
+/* n_mid planes with the extent of the wind arrays of the next step call (global for shim_step,
+   strip-local for shim_strip_advance) */
+void shim_set_wind_midlevels(Shim* h, int n_mid, const double* u_mid, const double* v_mid, int64_t plane) {
+    h->n_mid = n_mid;
+    h->u_mid.assign(u_mid, u_mid + (size_t)n_mid * plane);
+    h->v_mid.assign(v_mid, v_mid + (size_t)n_mid * plane);
+}
+/* the device-side wind mesh sampler (wind_mesh.h) on the host */
+void shim_wind_mesh_sample(int nx, int ny, int nt, const double* xw, const double* yw, const double* tw, const double* U,
+                           const double* V, int64_t n, const double* x, const double* y, double t, double* u_out,
+                           double* v_out) {
+    WindMesh W;
+    W.nx = nx; W.ny = ny; W.nt = nt; W.xw = xw; W.yw = yw; W.tw = tw; W.U = U; W.V = V;
+    const WindMeshTime T = wm_time(W, t);
+    for (int64_t l = 0; l < n; l++) wm_sample(W, T, x[l], y[l], u_out[l], v_out[l]);
+}
 
 void shim_seed(Shim* h, const double* u0, const double* v0) {
     for (auto& s : h->s) {
@@ -115,7 +134,14 @@ static void shim_advance_all(Shim* h, double DT, const double* u_t, const double
             Tally c;
             tally_zero(c);
             KLocal K;
-            advance_particle(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l], v_t1[off + l], M, pc, r, c, K);
+            double um[PH_WIND_SEG_MAX] = {0, 0, 0, 0}, vm[PH_WIND_SEG_MAX] = {0, 0, 0, 0};
+            {
+                /* mid-level planes have the extent of the wind arrays: global, or strip-local */
+                const int64_t plane = local_winds ? n : (int64_t)Nx * h->Ny;
+                for (int k = 0; k < h->n_mid; k++) { um[k] = h->u_mid[k * plane + off + l]; vm[k] = h->v_mid[k * plane + off + l]; }
+            }
+            advance_particle(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l], v_t1[off + l], h->n_mid, um, vm, M,
+                             pc, r, c, K);
             tally_add(T, c);
             store(s, l, p);
             int64_t le = l + (int64_t)s.halo * Nx;
@@ -158,6 +184,7 @@ void shim_step(Shim* h, double t, double DT, const double* u_t, const double* v_
     Tally T;
     tally_zero(T);
     shim_advance_all(h, DT, u_t, v_t, u_t1, v_t1, T, false);
+    h->n_mid = 0;
     /* halo exchange: my first/last H owned rows -> neighbour's upper/lower halo rows */
     int H = h->halo, ns = h->nstrips;
     if (ns > 1 && H > 0) {
@@ -227,6 +254,7 @@ void shim_strip_advance(Shim* h, double DT, const double* u_t, const double* v_t
     Tally T;
     tally_zero(T);
     shim_advance_all(h, DT, u_t, v_t, u_t1, v_t1, T, true);
+    h->n_mid = 0;
     h->tally = T;
     h->reach_halo = 0;
 }
