@@ -318,18 +318,52 @@ def main():
         ms_e2e = max(ms_e2e, wall_e2e)  # host-side work (API, staging) counts end to end
         e2e = dict(ms=ms_e2e, n=n_e2e, h2d=2 * n_nodes * 8, d2h=ctypes.sizeof(ctypes.c_double) * 1024 + 88)
 
+    # ---- timed region C: end to end with a device-resident wind mesh (wind ingestion) ----------
+    # Same workload; the wind comes from a gridded field kept on the device (9 x 9 x 3 knots of
+    # u = v = 10 m/s, the reference's LinearInterpolation((x,y,t), U, Periodic()) closure) and is
+    # sampled at the nodes by k_wind_sample every step: no wind bytes cross PCIe.
+    e2e_mesh = None
+    if not args.no_e2e:
+        xw = np.linspace(-1.0e4, 2000.0 * W["Nx"] + 1.0e4, 9)
+        yw = np.linspace(-1.0e4, 2000.0 * W["Ny"] + 1.0e4, 9)
+        tw = np.array([0.0, 1.0e6, 2.0e6])
+        Uw = np.full((3, 9, 9), 10.0)
+        nx_ = np.broadcast_to(np.arange(W["Nx"]) * 2000.0, (W["ny"], W["Nx"]))
+        ny_ = np.broadcast_to(((W["j0"] + np.arange(W["ny"])) * 2000.0)[:, None], (W["ny"], W["Nx"]))
+        eng.set_wind_mesh(xw, yw, tw, Uw, Uw, nx_, ny_)
+        lo, hi = (stepper.lo, stepper.hi) if stepper is not None else (-1, -1)
+        eng.step_wind_mesh(t, 600.0, 0, lo, hi)
+        t += 600.0
+        barrier()
+        t0 = time.perf_counter()
+        eng.timer_start()
+        n_mesh = 0
+        for _ in range(args.steps):
+            eng.step_wind_mesh(t, 600.0, 0, lo, hi)
+            t += 600.0
+            _ = eng.energy_sum()
+            n_mesh += eng.counters()["n_active"]
+        ms_mesh = eng.timer_stop()
+        barrier()
+        ms_mesh = max(ms_mesh, (time.perf_counter() - t0) * 1e3)
+        e2e_mesh = dict(ms=ms_mesh, n=n_mesh, ms_sample=eng.measure_wind_sample(t, 20))
+
     # ---- reduce over ranks: max time, sum of work ------------------------------------
     if dist is not None:
         import torch
-        tt = torch.tensor([ms_total, e2e["ms"] if e2e else 0.0], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([ms_total, e2e["ms"] if e2e else 0.0, e2e_mesh["ms"] if e2e_mesh else 0.0],
+                          dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ww = torch.tensor([float(n_active), float(e2e["n"]) if e2e else 0.0], dtype=torch.float64, device="cuda")
+        ww = torch.tensor([float(n_active), float(e2e["n"]) if e2e else 0.0, float(e2e_mesh["n"]) if e2e_mesh else 0.0],
+                          dtype=torch.float64, device="cuda")
         dist.all_reduce(ww, op=dist.ReduceOp.SUM)
-        ms_total, ms_e2e_all = tt.tolist()
-        n_active_all, n_e2e_all = ww.tolist()
+        ms_total, ms_e2e_all, ms_mesh_all = tt.tolist()
+        n_active_all, n_e2e_all, n_mesh_all = ww.tolist()
     else:
         ms_e2e_all = e2e["ms"] if e2e else 0.0
+        ms_mesh_all = e2e_mesh["ms"] if e2e_mesh else 0.0
         n_active_all, n_e2e_all = float(n_active), float(e2e["n"]) if e2e else 0.0
+        n_mesh_all = float(e2e_mesh["n"]) if e2e_mesh else 0.0
 
     if rank != 0:
         if dist is not None:
@@ -381,6 +415,19 @@ def main():
         line["e2e"] = {"value": n_e2e_all / (ms_e2e_all * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                        "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": ms_e2e_all / args.steps,
                        "api": "picles_step through the C ABI with pinned host wind buffers + picles_state_energy_sum"}
+    if e2e_mesh:
+        # the same metric with the wind ingested on the device; k_wind_sample: 16 B of node
+        # coordinates in + 16 B of wind out per node (the mesh itself is L2-resident)
+        gbs = n_nodes * 32 / (e2e_mesh["ms_sample"] * 1e-3) / 1e9
+        line["e2e_wind_mesh"] = {"value": n_mesh_all / (ms_mesh_all * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
+                                 "d2h_bytes_per_step": e2e["d2h"] if e2e else 0, "ms_per_step": ms_mesh_all / args.steps,
+                                 "api": "picles_step_wind_mesh (wind sampled on the device from a resident wind mesh) "
+                                        "+ picles_state_energy_sum"}
+        line["roofline_hbm"].append({"kernel": "k_wind_sample", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+                                     "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "bytes_per_node": 32,
+                                     "nodes_per_launch": n_nodes, "ms_per_launch": e2e_mesh["ms_sample"],
+                                     "share_of_step": e2e_mesh["ms_sample"] / (ms_adv + ms_prj + e2e_mesh["ms_sample"]),
+                                     "peak_source": hbm_src})
     if not args.no_cpu_baseline:
         cb = cpu_arm(min(args.steps, 3), args.warmup, args.cpu_sample)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -30,6 +30,16 @@ class B200(AbstractArchitecture):
     (picles_b200.distributed)."""
 
     devices: Tuple[int, ...] = (0,)
+    #: wind levels staged per model step (2..5).  The reference calls the wind closures at every
+    #: Runge-Kutta stage time; here they are evaluated on the host mesh at `wind_levels` equally
+    #: spaced times of each step and interpolated in time on the device (2: linear, exact for
+    #: steady winds; 5: within 1e-9 of the closure for the time-varying winds of the reference's
+    #: scripts, tests/test_wind_levels.py).
+    wind_levels: int = 2
+
+    def __post_init__(self):
+        if not 2 <= int(self.wind_levels) <= 5:
+            raise ValueError("wind_levels must be between 2 and 5")
 
 
 class AbstractBoundary:

@@ -114,6 +114,8 @@ class WaveGrowth2D:
         self._engine = None
         self._wind_level_time = None
         self._seeded = False
+        from ..Utils.WindEmulator import GriddedWinds
+        self._gridded_winds = self.winds if isinstance(self.winds, GriddedWinds) else None
 
     # ---- device plumbing ---------------------------------------------------------
     @property
@@ -139,11 +141,15 @@ class WaveGrowth2D:
                                       pc=pc, device=self.architecture.devices[0], j0=j0, ny_local=ny, halo=halo,
                                       metric=metric)
             self._rows = rows
+            if self._gridded_winds is not None:  # upload the wind mesh once; sampled on the device
+                self._gridded_winds.bind(self._engine, plane(g.data.x), plane(g.data.y))
         return self._engine
 
     def _wind_planes(self, t):
         """(u, v) at time t on this model's rows, as (ny, Nx) C-ordered planes."""
-        _ = self.engine
+        eng = self.engine
+        if self._gridded_winds is not None:
+            return eng.sample_wind_mesh(t)
         X = self.grid.data.x[:, self._rows]
         Y = self.grid.data.y[:, self._rows]
         u = eval_wind(self.winds.u, X, Y, t)

@@ -54,8 +54,11 @@ class Simulation:
 def init_particles(model, defaults=None, verbose=False):
     """init_particles!(model; defaults): SeedParticle for every node with the wind at t = 0
     (run.jl:199-247) — one picles_seed call."""
-    u0, v0 = model._wind_planes(0.0)
-    model.engine.seed(u0, v0)
+    if model._gridded_winds is not None:
+        model.engine.seed_wind_mesh(0.0)
+    else:
+        u0, v0 = model._wind_planes(0.0)
+        model.engine.seed(u0, v0)
     model._wind_level_time = 0.0
     model._seeded = True
 

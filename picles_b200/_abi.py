@@ -156,6 +156,7 @@ SYMBOLS = {
     "picles_selftest_math": (C.c_int, [_vp, C.c_uint64, C.c_int, C.POINTER(C.c_int64)]),
     "picles_measure_fp64_peak": (C.c_int, [_vp, _dp]),
     "picles_measure_hbm_copy": (C.c_int, [_vp, C.c_int, _dp]),
+    "picles_measure_wind_sample": (C.c_int, [_vp, C.c_double, C.c_int, _dp]),
 }
 
 _lib = None

@@ -1230,6 +1230,28 @@ int picles_sample_wind_mesh(picles_t* h, double t, double* u_out, double* v_out)
     return PICLES_OK;
 }
 
+/* CUDA-event time of k_wind_sample over this strip (mean of `reps` launches after one warm-up),
+   written into the first intermediate-level planes: the roofline of the ingestion kernel */
+int picles_measure_wind_sample(picles_t* h, double t, int reps, double* ms_per_launch) {
+    if (!h || !h->have_wind_mesh) return fail(h, PICLES_ERR_STATE, "picles_set_wind_mesh must be called first");
+    if (reps < 1 || !ms_per_launch) return fail(h, PICLES_ERR_ARG, "picles_measure_wind_sample: bad argument");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_mid_planes(h, 1);
+    if (rc) return rc;
+    DeviceArrays& A = h->A;
+    const int64_t n = (int64_t)A.Nx * A.ny;
+    launch_wind_sample(h->wm, n, t, A.u_mid[0], A.v_mid[0], h->sms, h->stream);
+    CK(cudaEventRecord(h->tev[0], h->stream));
+    for (int r = 0; r < reps; r++) launch_wind_sample(h->wm, n, t, A.u_mid[0], A.v_mid[0], h->sms, h->stream);
+    CK(cudaEventRecord(h->tev[1], h->stream));
+    CK(cudaEventSynchronize(h->tev[1]));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->tev[0], h->tev[1]));
+    *ms_per_launch = (double)ms / reps;
+    return PICLES_OK;
+}
+
 int picles_seed_wind_mesh(picles_t* h, double t0) {
     int rc = need_ready(h, false);
     if (rc) return rc;

@@ -162,3 +162,18 @@ class StripStepper:
         if self.transport is not None:
             self.transport.exchange(self.lo, self.hi)
         e.step_project_remesh(t, DT)
+
+    def step_wind_mesh(self, t, DT, n_mid=0):
+        """one strip step with every wind level sampled from the engine's resident wind mesh
+        (picles_set_wind_mesh): one C-ABI call with the in-library exchange, phase-split otherwise"""
+        e = self.eng
+        if self.transport is None or isinstance(self.transport, NcclLibTransport):
+            e.step_wind_mesh(t, DT, n_mid, self.lo, self.hi)
+            return
+        if n_mid:
+            lv = [e.sample_wind_mesh(t + DT * float(k) / float(n_mid + 1)) for k in range(1, n_mid + 1)]
+            e.set_wind_midlevels([a for a, _ in lv], [b for _, b in lv])
+        e.upload_winds(*e.sample_wind_mesh(t), *e.sample_wind_mesh(t + DT))
+        e.step_advance(t, DT)
+        self.transport.exchange(self.lo, self.hi)
+        e.step_project_remesh(t, DT)

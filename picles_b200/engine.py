@@ -88,6 +88,42 @@ class B200Engine:
         a = [self._wind(x) for x in (u_t, v_t, u_t1, v_t1)]
         self._check(self.lib.picles_step(self.h, float(t), float(DT), *[_ptr(x) for x in a]))
 
+    def set_wind_midlevels(self, u_mid=(), v_mid=()):
+        """intermediate wind levels of the NEXT step at t + k*DT/(n+1), k = 1..n (n <= 3): the wind
+        at a stage time is then the polynomial through all n+2 levels instead of the linear rule."""
+        n = len(u_mid)
+        if n == 0:
+            self._check(self.lib.picles_set_wind_midlevels(self.h, 0, None, None))
+            return
+        um = np.ascontiguousarray(np.stack([self._wind(x) for x in u_mid]))
+        vm = np.ascontiguousarray(np.stack([self._wind(x) for x in v_mid]))
+        self._check(self.lib.picles_set_wind_midlevels(self.h, n, _ptr(um), _ptr(vm)))
+
+    # wind ingestion: gridded winds resident on the device
+    def set_wind_mesh(self, xw, yw, tw, U, V, node_x, node_y):
+        """LinearInterpolation((xw, yw, tw), U, extrapolation_bc=Periodic()) kept on the device.
+        U, V: (nt, ny_w, nx_w) (== Julia U[ix, iy, it]); node_x, node_y: (ny, Nx) coordinates of
+        this strip's nodes (grid.data.x, grid.data.y)."""
+        f = lambda a: np.ascontiguousarray(np.asarray(a, np.float64))
+        xw, yw, tw, U, V = f(xw), f(yw), f(tw), f(U), f(V)
+        if U.shape != (tw.size, yw.size, xw.size) or V.shape != U.shape:
+            raise ValueError(f"U, V must have shape (nt, ny, nx) = {(tw.size, yw.size, xw.size)}")
+        nx_, ny_ = self._wind(node_x), self._wind(node_y)
+        self._check(self.lib.picles_set_wind_mesh(self.h, xw.size, yw.size, tw.size, _ptr(xw), _ptr(yw), _ptr(tw),
+                                                  _ptr(U), _ptr(V), _ptr(nx_), _ptr(ny_)))
+
+    def sample_wind_mesh(self, t):
+        u, v = np.empty((self.ny, self.Nx)), np.empty((self.ny, self.Nx))
+        self._check(self.lib.picles_sample_wind_mesh(self.h, float(t), _ptr(u), _ptr(v)))
+        return u, v
+
+    def seed_wind_mesh(self, t0=0.0):
+        self._check(self.lib.picles_seed_wind_mesh(self.h, float(t0)))
+
+    def step_wind_mesh(self, t, DT, n_mid=0, lo=-1, hi=-1):
+        """one model step with every wind level sampled on the device from the resident mesh"""
+        self._check(self.lib.picles_step_wind_mesh(self.h, float(t), float(DT), int(n_mid), int(lo), int(hi)))
+
     def step_raw(self, t, DT, pu_t=None, pv_t=None, pu_t1=None, pv_t1=None):
         """Same as step() with raw host pointers (ints), e.g. of pinned torch tensors."""
         self._check(self.lib.picles_step(self.h, float(t), float(DT), pu_t, pv_t, pu_t1, pv_t1))
@@ -243,6 +279,12 @@ class B200Engine:
     def measure_hbm_copy(self, mib=2048):
         v = C.c_double()
         self._check(self.lib.picles_measure_hbm_copy(self.h, int(mib), C.byref(v)))
+        return v.value
+
+    def measure_wind_sample(self, t=0.0, reps=20):
+        """ms per launch of k_wind_sample over this strip (CUDA events)"""
+        v = C.c_double()
+        self._check(self.lib.picles_measure_wind_sample(self.h, float(t), int(reps), C.byref(v)))
         return v.value
 
     def energy_sum(self):

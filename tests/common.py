@@ -270,6 +270,27 @@ class ShimEngine(HostShim):
         c["n_active"] = c["n_remesh_A"] + c["n_remesh_B"] + c["n_remesh_C"] + c["n_remesh_D"]
         return c
 
+    # wind ingestion: the device-side sampler (wind_mesh.h) run on the host
+    def set_wind_mesh(self, xw, yw, tw, U, V, node_x, node_y):
+        f = lambda a: np.ascontiguousarray(np.asarray(a, np.float64))
+        self._mesh = (f(xw), f(yw), f(tw), f(U), f(V), self._full(node_x).copy(), self._full(node_y).copy())
+
+    def sample_wind_mesh(self, t):
+        xw, yw, tw, U, V, nx, ny = self._mesh
+        u, v = np.empty(nx.shape), np.empty(nx.shape)
+        self.lib.shim_wind_mesh_sample(xw.size, yw.size, tw.size, _p(xw), _p(yw), _p(tw), _p(U), _p(V), nx.size, _p(nx),
+                                       _p(ny), float(t), _p(u), _p(v))
+        return u, v
+
+    def seed_wind_mesh(self, t0=0.0):
+        self.seed(*self.sample_wind_mesh(t0))
+
+    def step_wind_mesh(self, t, DT, n_mid=0, lo=-1, hi=-1):
+        if n_mid:
+            lv = [self.sample_wind_mesh(t + DT * float(k) / float(n_mid + 1)) for k in range(1, n_mid + 1)]
+            self.set_wind_midlevels([a for a, _ in lv], [b for _, b in lv])
+        self.step(t, DT, *self.sample_wind_mesh(t), *self.sample_wind_mesh(t + DT))
+
 
 class ShimStripEngine:
     """One y-strip of the host build of the device code behind the phase-split interface of
@@ -312,6 +333,26 @@ class ShimStripEngine:
             self._w[0], self._w[1] = self._w[2], self._w[3]
         if u_t1 is not None:
             self._w[2], self._w[3] = self._loc(u_t1), self._loc(v_t1)
+
+    def set_wind_midlevels(self, u_mid=(), v_mid=()):
+        n = len(u_mid)
+        um = np.ascontiguousarray(np.stack([self._loc(x) for x in u_mid])) if n else np.zeros((0, self.ny, self.Nx))
+        vm = np.ascontiguousarray(np.stack([self._loc(x) for x in v_mid])) if n else np.zeros((0, self.ny, self.Nx))
+        self.lib.shim_set_wind_midlevels(self.h, n, _p(um), _p(vm), self.ny * self.Nx)
+
+    def set_wind_mesh(self, xw, yw, tw, U, V, node_x, node_y):
+        f = lambda a: np.ascontiguousarray(np.asarray(a, np.float64))
+        self._mesh = (f(xw), f(yw), f(tw), f(U), f(V), self._loc(node_x).copy(), self._loc(node_y).copy())
+
+    def sample_wind_mesh(self, t):
+        xw, yw, tw, U, V, nx, ny = self._mesh
+        u, v = np.empty(nx.shape), np.empty(nx.shape)
+        self.lib.shim_wind_mesh_sample(xw.size, yw.size, tw.size, _p(xw), _p(yw), _p(tw), _p(U), _p(V), nx.size, _p(nx),
+                                       _p(ny), float(t), _p(u), _p(v))
+        return u, v
+
+    def seed_wind_mesh(self, t0=0.0):
+        self.seed(*self.sample_wind_mesh(t0))
 
     def step_advance(self, t, DT):
         self.lib.shim_strip_advance(self.h, float(DT), *[_p(x) for x in self._w])

@@ -13,7 +13,20 @@ for _p in (os.path.dirname(HERE), HERE):
         sys.path.insert(0, _p)
 
 
-def run(rank, world, port, name, halo, result_path, backend="gloo", transport="torch-p2p"):
+def mesh_of(g, DT, nsteps, seed=7):
+    """a synthetic wind mesh covering the scenario's grid and duration (knots off the step
+    boundaries so kinks fall inside steps)"""
+    rng = np.random.default_rng(seed)
+    x0, x1, y0, y1 = g["x"].min(), g["x"].max(), g["y"].min(), g["y"].max()
+    px, py = 0.07 * (x1 - x0) + 1.0, 0.07 * (y1 - y0) + 1.0
+    xw, yw = np.linspace(x0 - px, x1 + px, 8), np.linspace(y0 - py, y1 + py, 7)
+    tw = np.linspace(0.0, DT * nsteps * 1.13, 5)
+    U = 9.0 + 4.0 * rng.random((tw.size, yw.size, xw.size))
+    V = 5.0 + 4.0 * rng.random((tw.size, yw.size, xw.size))
+    return xw, yw, tw, U, V
+
+
+def run(rank, world, port, name, halo, result_path, backend="gloo", transport="torch-p2p", wind_mode="host", n_mid=0):
     """backend gloo: host build of the device code per rank (CPU tests);
     backend nccl: one B200Engine per rank on cuda:<rank> (GPU tests, world <= device count)."""
     import torch.distributed as dist
@@ -42,8 +55,17 @@ def run(rank, world, port, name, halo, result_path, backend="gloo", transport="t
             eng = ShimStripEngine(g, P, j0, j1, halo)
         st = StripStepper(eng, rank, world, periodic_y=(g["by"] == BND_PERIODIC), transport=transport)
         full = lambda a: np.broadcast_to(np.asarray(a, np.float64), (g["Ny"], g["Nx"]))
+        if wind_mode == "mesh":
+            # wind ingestion: the strip samples its own nodes from the resident wind mesh
+            import oracle
+            mesh = mesh_of(g, DT, nsteps)
+            eng.set_wind_mesh(*mesh, g["x"][j0:j1], g["y"][j0:j1])
+            wind = lambda t: oracle.wind_mesh_sample(*mesh, g["x"], g["y"], t)
         u0, v0 = wind(0.0)
-        eng.seed(full(u0)[j0:j1], full(v0)[j0:j1])
+        if wind_mode == "mesh":
+            eng.seed_wind_mesh(0.0)
+        else:
+            eng.seed(full(u0)[j0:j1], full(v0)[j0:j1])
         ref = None
         if rank == 0:
             ref = make_oracle(g, P)
@@ -51,8 +73,16 @@ def run(rank, world, port, name, halo, result_path, backend="gloo", transport="t
         t = 0.0
         for _ in range(nsteps):
             w = [full(x) for x in (*wind(t), *wind(t + DT))]
-            st.step(t, DT, winds=[x[j0:j1] for x in w])
+            mids = [wind(t + DT * float(k) / float(n_mid + 1)) for k in range(1, n_mid + 1)]
+            if wind_mode == "mesh":
+                st.step_wind_mesh(t, DT, n_mid)
+            else:
+                if n_mid:
+                    eng.set_wind_midlevels([full(a)[j0:j1] for a, _ in mids], [full(b)[j0:j1] for _, b in mids])
+                st.step(t, DT, winds=[x[j0:j1] for x in w])
             if ref is not None:
+                if n_mid:
+                    ref.set_wind_midlevels([full(a) for a, _ in mids], [full(b) for _, b in mids])
                 ref.step(t, DT, *w)
             t += DT
             parts = [None] * world if rank == 0 else None

@@ -26,6 +26,21 @@ def test_strips_over_gloo_match_oracle(tmp_path, name, world, halo):
     assert out.read_text() == "ok"
 
 
+@pytest.mark.parametrize("name,world,halo,wind_mode,n_mid", [("minimal", 2, 2, "mesh", 0), ("tripolar", 2, 6, "mesh", 2),
+                                                             ("growing_winds", 2, 2, "host", 3)])
+def test_strips_with_ingested_winds_over_gloo(tmp_path, name, world, halo, wind_mode, n_mid):
+    """wind ingestion on strips: each rank samples its own rows from the wind mesh (mesh) or
+    stages intermediate levels of its rows (host); the single-domain oracle gets the oracle's
+    restatement of the sampler"""
+    import torch.multiprocessing as mp
+
+    import dist_worker
+    out = tmp_path / "result"
+    mp.spawn(dist_worker.run, args=(world, _free_port(), name, halo, str(out), "gloo", "torch-p2p", wind_mode, n_mid),
+             nprocs=world, join=True)
+    assert out.read_text() == "ok"
+
+
 def test_strip_bounds_and_neighbours():
     assert strip_bounds(10, 3) == [(0, 3), (3, 6), (6, 10)]
     assert [b - a for a, b in strip_bounds(4096 * 8, 8)] == [4096] * 8

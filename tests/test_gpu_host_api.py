@@ -72,3 +72,38 @@ def test_gpu_tripolar_model_with_device_formed_metric(gpu_lib):
         o.step(t, DT, *W(t), *W(t + DT))
         t += DT
         compare_models(o, model.engine)
+
+
+def test_gpu_gridded_winds_through_run(gpu_lib):
+    """winds = wind_interpolator(wind_grid) (src/Utils/WindEmulator.jl:18-43) on B200: the wind
+    mesh is uploaded once and sampled on the device for every level of every step (wind_levels=3);
+    `winds.u(x, y, t)` is served by the device too.  Oracle: its own restatement of the
+    interpolation, levels fed by hand."""
+    import oracle
+    from picles_b200.Architectures import B200
+    from picles_b200.Simulations import Simulation, run
+    from picles_b200.Utils.WindEmulator import wind_interpolator
+    rng = np.random.default_rng(2)
+    xi, yi = np.linspace(-5e3, 110e3, 9), np.linspace(-5e3, 110e3, 8)
+    ti = np.array([0.0, 1500.0, 3100.0, 7300.0])
+    ug = 9.0 + 3.0 * rng.random((xi.size, yi.size, ti.size))
+    vg = 6.0 + 3.0 * rng.random((xi.size, yi.size, ti.size))
+    winds = wind_interpolator(dict(u=ug, v=vg, x=xi, y=yi, t=ti))
+    model, DT = example_00_minimal(architecture=B200(wind_levels=3))
+    model.winds = winds
+    model._gridded_winds = winds
+    sim = Simulation(model, Δt=DT, stop_time=1 * hours)
+    run(sim)
+    g = grid_dict_from_mesh(model.grid)
+    U, V = ug.transpose(2, 1, 0), vg.transpose(2, 1, 0)
+    samp = lambda t: oracle.wind_mesh_sample(xi, yi, ti, U, V, g["x"], g["y"], t)
+    assert bits_equal(winds.u(None, None, 450.0).T, samp(450.0)[0])
+    o = make_oracle(g, default_params())
+    o.seed(*samp(0.0))
+    t = 0.0
+    for _ in range(model.clock.iteration):
+        um, vm = samp(t + DT * 1.0 / 2.0)
+        o.set_wind_midlevels([um], [vm])
+        o.step(t, DT, *samp(t), *samp(t + DT))
+        t += DT
+    compare_models(o, model.engine)

@@ -34,6 +34,21 @@ def test_strips_over_nccl_match_oracle(gpu_lib, tmp_path, name, world, halo, tra
     assert out.read_text() == "ok"
 
 
+@pytest.mark.parametrize("name,world,halo,n_mid", [("minimal", 2, 2, 0), ("tripolar", 2, 6, 2)])
+def test_strips_with_device_wind_mesh_over_nccl(gpu_lib, tmp_path, name, world, halo, n_mid):
+    """picles_step_wind_mesh on strips: every rank samples its rows from its resident wind mesh,
+    exchange inside the library, bit-exact against the single-domain oracle"""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+
+    import dist_worker
+    out = tmp_path / "result"
+    mp.spawn(dist_worker.run, args=(world, _free_port(), name, halo, str(out), "nccl", "nccl-lib", "mesh", n_mid),
+             nprocs=world, join=True)
+    assert out.read_text() == "ok"
+
+
 def test_halo_exchange_without_neighbours_is_pack_unpack(gpu_lib):
     """single strip handle with a halo and no neighbours: picles_step_strip == picles_step"""
     import numpy as np

@@ -186,3 +186,68 @@ def test_unsupported_requests_fail_loudly():
         PW.ODESettings(Parameters={}, log_energy_minimum=0, saving_step=1, timestep=1, total_time=1,
                        solver="Rosenbrock23").solver_id()
     assert B200().devices == (0,)
+
+
+# ---- wind ingestion through the host API ---------------------------------------------------
+
+def test_wind_levels_option_stages_intermediate_levels():
+    """B200(wind_levels=4): the closures are evaluated at 4 equally spaced times of every step
+    and the run equals the oracle fed with the same levels by hand"""
+    w = 5.0 / (3600.0 * 2.0 * math.pi)
+    u = lambda x, y, t: 15.0 + 0.0 * x
+    v = lambda x, y, t: -10.0 * math.cos(w * t) + 0.0 * x
+    model, DT = example_00_minimal(grid=TwoDCartesianGridMesh(40e3, 11, 30e3, 9), architecture=B200(wind_levels=4))
+    model.winds.u, model.winds.v = u, v
+    attach_shim(model)
+    sim = Simulation(model, Δt=DT, stop_time=30 * minutes)
+    run(sim)
+    g = grid_dict_from_mesh(model.grid)
+    o = make_oracle(g, default_params())
+    full = lambda val: np.full((g["Ny"], g["Nx"]), val)
+    o.seed(full(15.0), full(v(0, 0, 0.0)))
+    t = 0.0
+    for _ in range(model.clock.iteration):
+        tm = [t + DT * float(k) / 3.0 for k in (1, 2)]
+        o.set_wind_midlevels([full(15.0) for _ in tm], [full(v(0, 0, x)) for x in tm])
+        o.step(t, DT, full(15.0), full(v(0, 0, t)), full(15.0), full(v(0, 0, t + DT)))
+        t += DT
+    compare_models(o, model.engine)
+    with pytest.raises(ValueError):
+        B200(wind_levels=7)
+
+
+def test_gridded_winds_are_sampled_by_the_engine():
+    """winds=wind_interpolator(wind_grid): the mesh is handed to the engine once and every level
+    of every step comes from the sampler; the run equals the oracle driven with the oracle's own
+    restatement of LinearInterpolation(..., extrapolation_bc=Periodic())"""
+    import oracle
+    from picles_b200.Utils.WindEmulator import wind_interpolator
+    rng = np.random.default_rng(5)
+    xi = np.linspace(-5e3, 45e3, 6)
+    yi = np.linspace(-5e3, 35e3, 5)
+    ti = np.array([0.0, 900.0, 1800.0, 3600.0])
+    ug = 9.0 + 3.0 * rng.random((xi.size, yi.size, ti.size))
+    vg = 6.0 + 3.0 * rng.random((xi.size, yi.size, ti.size))
+    winds = wind_interpolator(dict(u=ug, v=vg, x=xi, y=yi, t=ti))
+    with pytest.raises(RuntimeError):
+        winds.u(0.0, 0.0, 0.0)           # no CPU evaluation path
+    model, DT = example_00_minimal(grid=TwoDCartesianGridMesh(40e3, 11, 30e3, 9), architecture=B200(wind_levels=3))
+    model.winds = winds
+    model._gridded_winds = winds
+    attach_shim(model)
+    g = grid_dict_from_mesh(model.grid)
+    winds.bind(model.engine, g["x"], g["y"])
+    sim = Simulation(model, Δt=DT, stop_time=40 * minutes)
+    run(sim)
+    assert winds.u(None, None, 450.0).shape == (11, 9)
+    o = make_oracle(g, default_params())
+    U, V = ug.transpose(2, 1, 0), vg.transpose(2, 1, 0)
+    samp = lambda t: oracle.wind_mesh_sample(xi, yi, ti, U, V, g["x"], g["y"], t)
+    o.seed(*samp(0.0))
+    t = 0.0
+    for _ in range(model.clock.iteration):
+        um, vm = samp(t + DT * 1.0 / 2.0)
+        o.set_wind_midlevels([um], [vm])
+        o.step(t, DT, *samp(t), *samp(t + DT))
+        t += DT
+    compare_models(o, model.engine)
