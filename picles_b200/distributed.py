@@ -30,6 +30,42 @@ def strip_bounds(Ny: int, world: int):
     return [(Ny * r // world, Ny * (r + 1) // world) for r in range(world)]
 
 
+def strip_bounds_weighted(row_cost, world: int, min_rows: int = 1):
+    """[(j0, j1)) rows of every rank for rows of unequal cost (land, pole rows): contiguous strips
+    whose summed cost is as even as a prefix-sum split allows.  row_cost: one non-negative weight
+    per global row; every strip keeps at least `min_rows` rows (>= the halo width)."""
+    c = np.maximum(np.asarray(row_cost, np.float64), 0.0)
+    Ny = c.size
+    if world * min_rows > Ny:
+        raise ValueError(f"{Ny} rows cannot hold {world} strips of at least {min_rows} rows")
+    cum = np.concatenate([[0.0], np.cumsum(c)])
+    cuts = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        j = int(np.searchsorted(cum, target))
+        if j > 0 and abs(cum[j - 1] - target) <= abs(cum[min(j, Ny)] - target):
+            j -= 1
+        j = max(j, cuts[-1] + min_rows)
+        j = min(j, Ny - (world - r) * min_rows)
+        cuts.append(j)
+    cuts.append(Ny)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def row_cost_model(mask, periodic_boundary: bool, reach_rows=None, gather_weight: float = 0.075, reach_weight: float = 0.3):
+    """cost of every global row in particle units, for strip_bounds_weighted: the active particles
+    of the row (the advance is ~98 % of a step) plus the gather/remesh of all its nodes
+    (gather_weight per node) and, for rows whose deposits reach further than one cell
+    (reach_rows: per-row reach estimate, e.g. the small cells near a tripolar pole), reach_weight
+    per node and cell of extra reach: the window grows as (2R+1)^2."""
+    m = np.asarray(mask)
+    active = (m == 1) | ((m == 3) if periodic_boundary else False)
+    cost = active.sum(axis=1).astype(np.float64) + gather_weight * m.shape[1]
+    if reach_rows is not None:
+        cost = cost + reach_weight * m.shape[1] * np.maximum(np.asarray(reach_rows, np.float64) - 1.0, 0.0)
+    return cost
+
+
 def neighbours(rank: int, world: int, periodic_y: bool):
     """(lo, hi): ranks owning the rows below / above this strip, -1 at a domain edge."""
     if world == 1:

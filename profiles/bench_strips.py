@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--halo", type=int, default=6)
+    ap.add_argument("--balance", action="store_true",
+                    help="cut the strips by cost (active particles + gather, picles_b200.distributed.row_cost_model) "
+                         "instead of by rows")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -42,7 +45,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from picles_b200.distributed import StripStepper, strip_bounds
+    from picles_b200.distributed import StripStepper, row_cost_model, strip_bounds, strip_bounds_weighted
     from picles_b200.engine import B200Engine
 
     if a.config == "C5":
@@ -53,7 +56,15 @@ def main():
     P = default_params(DT=1200.0, periodic_boundary=True)
     DT = 1200.0
     wind = lambda t: (15.0, -10.0 * np.cos(5 * t / (3600 * 2 * np.pi)))  # tests/T03_PIC_tripolar_aqua.jl:67-68
-    j0, j1 = strip_bounds(Ny, world)[rank]
+    if a.balance and world > 1:
+        # per-row reach estimate from the metric: group speed of the young sea of the first steps
+        # (~3 m/s) x DT in cells of the row's smallest spacing
+        cell = 1.0 / np.maximum(np.abs(g["M"][0]), np.abs(g["M"][3])).max(axis=1)
+        reach_rows = np.maximum(np.ceil(3.0 * DT / cell), 1.0)
+        bounds = strip_bounds_weighted(row_cost_model(g["mask"], True, reach_rows), world, min_rows=max(a.halo, 1))
+    else:
+        bounds = strip_bounds(Ny, world)
+    j0, j1 = bounds[rank]
     halo = a.halo if world > 1 else 0
     eng = B200Engine(Nx, Ny, g["bx"], g["by"], g["mask"][j0:j1], P, M=g["M"][:, j0:j1], pc=g["pc"][j0:j1],
                      device=local_rank, j0=j0, ny_local=j1 - j0, halo=halo)
@@ -90,7 +101,9 @@ def main():
     if rank == 0:
         ms_max = max(p["ms"] for p in parts)
         active = sum(p["active"] for p in parts)
-        line = {"config": name, "n_gpus": world, "scaling": "strong", "partition": f"{world} y-strips of {Nx}x{Ny}, halo {halo} rows",
+        line = {"config": name, "n_gpus": world, "scaling": "strong",
+                "partition": f"{world} y-strips of {Nx}x{Ny}, halo {halo} rows, cut by {'cost' if a.balance else 'rows'}",
+                "rows_per_rank": [p["rows"] for p in parts],
                 "nodes": Nx * Ny, "steps": a.steps, "warmup": a.warmup, "particle_steps_per_s": active / (ms_max * 1e-3),
                 "ms_per_step": ms_max / a.steps, "ms_per_step_per_rank": [p["ms"] / a.steps for p in parts],
                 "ms_advance_per_rank": [p["adv"] for p in parts], "ms_project_remesh_per_rank": [p["prj"] for p in parts],

@@ -6,7 +6,7 @@ import socket
 
 import pytest
 
-from picles_b200.distributed import neighbours, strip_bounds
+from picles_b200.distributed import neighbours, row_cost_model, strip_bounds, strip_bounds_weighted
 
 
 def _free_port():
@@ -48,3 +48,25 @@ def test_strip_bounds_and_neighbours():
     assert neighbours(0, 4, False) == (-1, 1) and neighbours(3, 4, False) == (2, -1)
     assert neighbours(0, 4, True) == (3, 1) and neighbours(3, 4, True) == (2, 0)
     assert neighbours(0, 2, True) == (1, 1)  # two-strip ring: both neighbours are the other rank
+
+
+def test_weighted_strip_bounds():
+    import numpy as np
+    # equal costs: the plain split
+    assert strip_bounds_weighted(np.ones(12), 3) == [(0, 4), (4, 8), (8, 12)]
+    # a land slab in the first third moves the cuts towards the ocean rows
+    cost = np.r_[np.zeros(40), np.ones(80)]
+    b = strip_bounds_weighted(cost, 4, min_rows=2)
+    assert b[0][0] == 0 and b[-1][1] == 120 and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+    sums = [cost[a:c].sum() for a, c in b]
+    assert max(sums) - min(sums) <= 1.0
+    # min_rows is honoured even when the cost is concentrated
+    b = strip_bounds_weighted(np.r_[np.zeros(30), [100.0], np.zeros(5)], 4, min_rows=3)
+    assert all(c - a >= 3 for a, c in b)
+    with pytest.raises(ValueError):
+        strip_bounds_weighted(np.ones(5), 3, min_rows=2)
+    mask = np.ones((6, 10), np.uint8)
+    mask[:2] = 0
+    mask[:, 0] = 3
+    c = row_cost_model(mask, periodic_boundary=False, reach_rows=[1, 1, 1, 1, 2, 3])
+    assert c[0] == pytest.approx(0.75) and c[2] == pytest.approx(9.75) and c[5] > c[4] > c[3]
