@@ -44,6 +44,12 @@ Base.@kwdef struct B200 <: AbstractArchitecture
     rank::Int = 0
     nranks::Int = 1
     halo::Int = 2
+    # wind ingestion (include/picles_b200.h: picles_set_wind_midlevels / picles_set_wind_mesh)
+    wind_levels::Int = 2          # 2..5 levels staged per step; the closures are called at wind_levels
+                                  # equally spaced times of [t, t+Δt] and interpolated in time on the device
+    wind_mesh = nothing           # (x=, y=, t=, u=U[ix,iy,it], v=V[ix,iy,it]): gridded winds kept on the device
+                                  # (the data behind LinearInterpolation((x,y,t), U, extrapolation_bc=Periodic()),
+                                  # tests/T03_PIC_tripolar_realistic.jl:61-73); model.winds is then not called
 end
 
 # ---- C structs (include/picles_b200.h) -------------------------------------------------------
@@ -76,6 +82,8 @@ mutable struct B200Context
     lo::Int; hi::Int                 # neighbour ranks (-1: none)
     u_t1::Matrix{Float64}; v_t1::Matrix{Float64}   # staging of the wind at t+Δt
     first_step::Bool
+    n_mid::Int                       # intermediate wind levels per step (arch.wind_levels - 2)
+    mesh_winds::Bool                 # winds sampled on the device from the resident wind mesh
 end
 
 function check(h::Ptr{Cvoid}, rc::Integer)
@@ -141,9 +149,21 @@ function b200_init_particles!(model, arch::B200; nccl_id::Union{Nothing,Vector{U
     end
     P = flatten_params(model, arch)
     check(h, ccall((:picles_set_params, LIB), Cint, (Ptr{Cvoid}, Ref{PiclesParams}), h, P))
-    u0 = stage_wind(model.winds.u, grid, rows, 0.0)
-    v0 = stage_wind(model.winds.v, grid, rows, 0.0)
-    check(h, ccall((:picles_seed, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), h, u0, v0))
+    2 <= arch.wind_levels <= 5 || error("wind_levels must be between 2 and 5")
+    mesh_winds = arch.wind_mesh !== nothing
+    if mesh_winds
+        w = arch.wind_mesh           # U[ix, iy, it] column-major == nt slices of ny*nx, x fastest
+        check(h, ccall((:picles_set_wind_mesh, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+            h, length(w.x), length(w.y), length(w.t), Float64.(collect(w.x)), Float64.(collect(w.y)), Float64.(collect(w.t)),
+            Float64.(w.u), Float64.(w.v), Float64.(grid.data.x[:, rows]), Float64.(grid.data.y[:, rows])))
+        check(h, ccall((:picles_seed_wind_mesh, LIB), Cint, (Ptr{Cvoid}, Cdouble), h, 0.0))
+        u0 = v0 = zeros(0, 0)
+    else
+        u0 = stage_wind(model.winds.u, grid, rows, 0.0)
+        v0 = stage_wind(model.winds.v, grid, rows, 0.0)
+        check(h, ccall((:picles_seed, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), h, u0, v0))
+    end
     lo = hi = -1
     if arch.nranks > 1
         # rank 0 creates the id with picles_comm_unique_id and broadcasts it (MPI.Bcast! / Distributed)
@@ -153,7 +173,7 @@ function b200_init_particles!(model, arch::B200; nccl_id::Union{Nothing,Vector{U
         lo = arch.rank > 0 ? arch.rank - 1 : (per ? arch.nranks - 1 : -1)
         hi = arch.rank < arch.nranks - 1 ? arch.rank + 1 : (per ? 0 : -1)
     end
-    ctx = B200Context(h, Nx, Ny, j0, j1 - j0, lo, hi, u0, v0, true)
+    ctx = B200Context(h, Nx, Ny, j0, j1 - j0, lo, hi, u0, v0, true, arch.wind_levels - 2, mesh_winds)
     b200_fetch_state!(model, ctx)                   # State after seeding (init_z0_to_State!)
     return ctx
 end
@@ -164,6 +184,25 @@ b200_nccl_unique_id() = (id = zeros(UInt8, 128); check(C_NULL, ccall((:picles_co
 function b200_time_step!(model, ctx::B200Context, Δt::Float64; fetch_state::Bool=true)
     t = model.clock.time
     rows = ctx.j0+1:ctx.j0+ctx.ny
+    if ctx.mesh_winds
+        # every wind level of the step is sampled on the device from the resident wind mesh: no upload
+        check(ctx.handle, ccall((:picles_step_wind_mesh, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Cint, Cint, Cint),
+            ctx.handle, t, Δt, ctx.n_mid, ctx.lo, ctx.hi))
+        fetch_state && b200_fetch_state!(model, ctx)
+        return nothing
+    end
+    if ctx.n_mid > 0
+        # intermediate levels at t + Δt*k/(n_mid+1), k = 1..n_mid (the expression the library documents)
+        um = Array{Float64,3}(undef, ctx.Nx, ctx.ny, ctx.n_mid)
+        vm = similar(um)
+        for k in 1:ctx.n_mid
+            tk = t + Δt * Float64(k) / Float64(ctx.n_mid + 1)
+            um[:, :, k] = stage_wind(model.winds.u, model.grid, rows, tk)
+            vm[:, :, k] = stage_wind(model.winds.v, model.grid, rows, tk)
+        end
+        check(ctx.handle, ccall((:picles_set_wind_midlevels, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cdouble}),
+            ctx.handle, ctx.n_mid, um, vm))
+    end
     # wind at t+Δt on the mesh; the level uploaded last step becomes this step's t level inside the library
     ctx.u_t1 = stage_wind(model.winds.u, model.grid, rows, t + Δt)
     ctx.v_t1 = stage_wind(model.winds.v, model.grid, rows, t + Δt)
