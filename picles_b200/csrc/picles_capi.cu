@@ -1191,6 +1191,7 @@ int picles_set_wind_mesh(picles_t* h, int nxw, int nyw, int ntw, const double* x
     if (!h || !h->have_grid) return fail(h, PICLES_ERR_STATE, "picles_set_grid must be called first");
     if (nxw < 2 || nyw < 2 || ntw < 2) return fail(h, PICLES_ERR_ARG, "wind mesh needs at least 2 knots per axis (%d, %d, %d)", nxw, nyw, ntw);
     if (!xw || !yw || !tw || !U || !V || !node_x || !node_y) return fail(h, PICLES_ERR_ARG, "picles_set_wind_mesh: null array");
+    if ((int64_t)nxw * nyw >= ((int64_t)1 << 31)) return fail(h, PICLES_ERR_ARG, "wind mesh slices are limited to 2^31 values");
     if (!strictly_increasing(xw, nxw) || !strictly_increasing(yw, nyw) || !strictly_increasing(tw, ntw))
         return fail(h, PICLES_ERR_ARG, "wind mesh knot vectors must be strictly increasing");
     CK(cudaSetDevice(h->device));

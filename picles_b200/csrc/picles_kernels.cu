@@ -612,13 +612,29 @@ __global__ void k_selftest_math(uint64_t seed, int iters, unsigned long long* ou
 __global__ void __launch_bounds__(256) k_wind_sample(DeviceWindMesh D, int64_t n, double t, double* __restrict__ u_out,
                                                      double* __restrict__ v_out) {
     WindMesh W;
-    W.nx = D.nx; W.ny = D.ny; W.nt = D.nt; W.xw = D.xw; W.yw = D.yw; W.tw = D.tw; W.U = D.U; W.V = D.V;
+    W.nx = D.nx; W.ny = D.ny; W.nt = D.nt; W.xw = D.xw; W.yw = D.yw; W.tw = D.tw;
     const WindMeshTime T = wm_time(W, t);
-    for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x) {
+    /* the time slice is the same for every node: fold it into the base pointers */
+    const int64_t st = (int64_t)D.nx * D.ny;
+    W.U = D.U + st * T.it; W.V = D.V + st * T.it;
+    WindMeshTime T0 = T;
+    T0.it = 0;
+    const double* __restrict__ nx = D.node_x;
+    const double* __restrict__ ny = D.node_y;
+    /* software pipeline: the coordinates of the next node are in flight (HBM latency) while this
+       one is located and blended (L1/L2 latency) */
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double xn = 0.0, yn = 0.0;
+    if (l < n) { xn = __ldcs(nx + l); yn = __ldcs(ny + l); }
+    for (; l < n; l += stride) {
+        const double x = xn, y = yn;
+        const int64_t l2 = l + stride;
+        if (l2 < n) { xn = __ldcs(nx + l2); yn = __ldcs(ny + l2); }
         double u, v;
-        wm_sample(W, T, D.node_x[l], D.node_y[l], u, v);
-        u_out[l] = u;
-        v_out[l] = v;
+        wm_sample(W, T0, x, y, u, v);
+        __stcs(u_out + l, u);
+        __stcs(v_out + l, v);
     }
 }
 
