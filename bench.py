@@ -33,8 +33,8 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the 4096^2 bench step, from the
 # committed ncu --set full captures (profiles/r01_ncu_final.txt); never measured under the timer
-NCU_TRAFFIC = {"k_advance": 3.61e9, "k_project_remesh": 1.80e9}
-NCU_FP64_PIPE_PCT = 56.8  # sm__pipe_fp64_cycles_active of k_advance (profiles/r01_ncu_final.txt)
+NCU_TRAFFIC = {"k_advance": 3.61e9, "k_project_remesh": 1.80e9, "k_wind_sample": 0.49e9}
+NCU_FP64_PIPE_PCT = 57.6  # sm__pipe_fp64_cycles_active of k_advance (profiles/r01_ncu_final.txt)
 
 METRIC = "particle-steps/s"
 UNIT = "particle-steps/s"
@@ -424,7 +424,8 @@ def main():
                                  "api": "picles_step_wind_mesh (wind sampled on the device from a resident wind mesh) "
                                         "+ picles_state_energy_sum"}
         line["roofline_hbm"].append({"kernel": "k_wind_sample", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
-                                     "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "bytes_per_node": 32,
+                                     "unit": "GB/s", "frac": gbs / hbm_peak,
+                                     "traffic": NCU_TRAFFIC.get("k_wind_sample") if std_size else None, "bytes_per_node": 32,
                                      "nodes_per_launch": n_nodes, "ms_per_launch": e2e_mesh["ms_sample"],
                                      "share_of_step": e2e_mesh["ms_sample"] / (ms_adv + ms_prj + e2e_mesh["ms_sample"]),
                                      "peak_source": hbm_src})
