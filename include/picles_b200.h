@@ -59,7 +59,16 @@ enum { PICLES_BND_NONPERIODIC = 0, PICLES_BND_PERIODIC = 1, PICLES_BND_TRIPOLAR_
 /* total mask values: mask_utils.jl:26-30 */
 enum { PICLES_MASK_LAND = 0, PICLES_MASK_OCEAN = 1, PICLES_MASK_LAND_BOUNDARY = 2, PICLES_MASK_GRID_BOUNDARY = 3 };
 /* solver ids: ODESettings.solver (particle_waves_v5.jl:47) */
-enum { PICLES_SOLVER_TSIT5 = 0, PICLES_SOLVER_DP5 = 1 };
+enum {
+    PICLES_SOLVER_TSIT5 = 0,
+    PICLES_SOLVER_DP5 = 1,
+    /* AutoTsit5(Rosenbrock23()), the ODESettings default: Tsit5 with OrdinaryDiffEq's AutoSwitch
+       stiffness monitor (Hairer II p. 22 eigenvalue estimate, stiff for more than 10 consecutive
+       attempts -> Rosenbrock23 with an automatic-differentiation Jacobian, dt doubled; back after
+       more than 3 non-stiff attempts, dt halved).  On every configuration where the monitor never
+       fires it is Tsit5, bit for bit. */
+    PICLES_SOLVER_AUTOTSIT5 = 2
+};
 
 /* per-particle status bits (picles_get_particles) */
 enum {
@@ -150,6 +159,8 @@ typedef struct {
     double ms_advance;       /* CUDA-event times of the three kernels of the last step */
     double ms_project;
     double ms_remesh;
+    int64_t n_stiff_switches;/* AutoTsit5: switches Tsit5 -> Rosenbrock23 this step */
+    int64_t n_stiff_attempts;/* AutoTsit5: Rosenbrock23 attempts this step (accepted + rejected) */
 } picles_counters_t;
 
 /* ---- lifecycle --------------------------------------------------------- */
@@ -307,6 +318,9 @@ int picles_set_state(picles_t* h, const double* S);
 int picles_get_particles(picles_t* h, double* z /* 5 planes of ny_local*Nx */,
                          double* t, double* dt, uint8_t* flags, int32_t* status);
 int picles_get_counters(picles_t* h, picles_counters_t* c);
+/* AutoSwitch state of every particle (ny_local*Nx): the signed run length of the stiffness test
+   (positive: consecutive stiff attempts, negative: non-stiff), +64 when Rosenbrock23 is current */
+int picles_get_solver_state(picles_t* h, int8_t* as);
 /* sum over this strip of State[:,:,0] (mean_of_state, run.jl:23-25, times n) — a cheap
    per-step scalar read-back */
 int picles_state_energy_sum(picles_t* h, double* sum_e);

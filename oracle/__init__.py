@@ -61,6 +61,7 @@ def load(variant: str = "default"):
     lib.oracle_get_particles.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.oracle_get_aux.argtypes = [vp, vp, vp]
     lib.oracle_get_counters.argtypes = [vp, C.POINTER(PiclesCounters)]
+    lib.oracle_get_solver_state.argtypes = [vp, vp]
     lib.oracle_n_ocean.restype = i64
     lib.oracle_n_ocean.argtypes = [vp]
     lib.oracle_fields.argtypes = [vp, vp, vp, vp]
@@ -80,6 +81,9 @@ def load(variant: str = "default"):
     lib.oracle_corner_target.argtypes = [i32, i32, i32, i32, i64, i64]
     lib.oracle_integrate_one.argtypes = [C.POINTER(PiclesParams), vp, d, vp, vp, vp, vp, vp, i32, d, d, d, d, d,
                                          C.POINTER(PiclesCounters), vp]
+    lib.oracle_integrate_one_as.argtypes = [C.POINTER(PiclesParams), vp, d, vp, vp, vp, vp, vp, i32, d, d, d, d, d,
+                                            C.POINTER(PiclesCounters), vp, vp]
+    lib.oracle_rhs_jacobian.argtypes = [C.POINTER(PiclesParams), vp, d, d, d, d, vp, d, vp, vp]
     lib.oracle_grid_metric.argtypes = [i64, vp, vp, vp, vp, d, vp, vp]
     for f in ("exp", "log", "tanh", "sech", "cosh", "eps", "sin", "cos", "sind", "cosd", "tand"):
         getattr(lib, "oracle_pm_" + f).argtypes = [i64, vp, vp]
@@ -209,6 +213,12 @@ class Oracle:
         self.lib.oracle_fields(self.h, _dp(Hs), _dp(cx), _dp(cy))
         return dict(Hs=Hs, c_x=cx, c_y=cy)
 
+    def solver_state(self):
+        """AutoSwitch state per particle: run length of the stiffness test, +64 while Rosenbrock23 is current"""
+        a = np.empty((self.Ny, self.Nx), dtype=np.int8)
+        self.lib.oracle_get_solver_state(self.h, _dp(a))
+        return a
+
     def stiff_triggers(self):
         return int(self.lib.oracle_stiff_triggers(self.h))
 
@@ -278,8 +288,18 @@ def corner_target(Nx, Ny, bx, by, i, j, variant="default"):
     return int(load(variant).oracle_corner_target(Nx, Ny, bx, by, int(i), int(j)))
 
 
+def rhs_jacobian(params, z, u, v, ut=0.0, vt=0.0, M=(1.0, 0.0, 0.0, 1.0), pc=0.0, variant="default"):
+    """(J, dT): df/dz (5x5) and df/dt of the right-hand side by forward-mode dual numbers"""
+    lib = load(variant)
+    z, M = _f64(z), _f64(M)
+    J, dT = np.empty((5, 5)), np.empty(5)
+    lib.oracle_rhs_jacobian(C.byref(params), _dp(z), float(u), float(v), float(ut), float(vt), _dp(M), float(pc), _dp(J),
+                            _dp(dT))
+    return J, dT
+
+
 def integrate_one(params, u5, t=0.0, dt=None, qold=1e-4, it=0, dt_reset=False, wind0=(10.0, 10.0), wind1=None,
-                  DT=600.0, M=(1 / 2000.0, 0.0, 0.0, 1 / 2000.0), pc=0.0, status=0, variant="default"):
+                  DT=600.0, M=(1 / 2000.0, 0.0, 0.0, 1 / 2000.0), pc=0.0, status=0, variant="default", as_state=None):
     lib = load(variant)
     u5 = _f64(u5).copy()
     M = _f64(M)
@@ -290,11 +310,12 @@ def integrate_one(params, u5, t=0.0, dt=None, qold=1e-4, it=0, dt_reset=False, w
     st = np.array([status], dtype=np.int32)
     wind1 = wind0 if wind1 is None else wind1
     c = PiclesCounters()
-    lib.oracle_integrate_one(C.byref(params), _dp(M), float(pc), _dp(u5), _dp(tt), _dp(dd), _dp(qq), _dp(ii),
-                             int(dt_reset), float(wind0[0]), float(wind0[1]), float(wind1[0]), float(wind1[1]),
-                             float(DT), C.byref(c), _dp(st))
+    as2 = np.array(as_state if as_state is not None else (0, 0), dtype=np.int32)
+    lib.oracle_integrate_one_as(C.byref(params), _dp(M), float(pc), _dp(u5), _dp(tt), _dp(dd), _dp(qq), _dp(ii),
+                                int(dt_reset), float(wind0[0]), float(wind0[1]), float(wind1[0]), float(wind1[1]),
+                                float(DT), C.byref(c), _dp(st), _dp(as2))
     return dict(u=u5, t=float(tt[0]), dt=float(dd[0]), qold=float(qq[0]), iter=int(ii[0]), status=int(st[0]),
-                counters=c.as_dict())
+                counters=c.as_dict(), as_state=(int(as2[0]), int(as2[1])))
 
 
 def pm(func, x, y=None, variant="default"):

@@ -30,8 +30,9 @@
  *     exactly that, as the yardstick the staged-level runs are measured against);
  *   - auto_dt_reset! is evaluated lazily at the start of the next advance (same
  *     arithmetic, same inputs);
- *   - the AutoTsit5 stiff (Rosenbrock23) branch is not taken; the stiffness trigger
- *     is counted instead;
+ *   - solver Tsit5: the AutoTsit5 stiffness trigger is only counted; solver AutoTsit5
+ *     (PICLES_SOLVER_AUTOTSIT5) runs OrdinaryDiffEq's AutoSwitch + Rosenbrock23 as restated
+ *     below (published algorithm, from the call sites; third-party arithmetic unpinned);
  *   - rand_sign() for an exactly-zero wind component (FetchRelations.jl:365) is +1.
  */
 #include <math.h>
@@ -42,6 +43,7 @@
 #include "../include/picles_b200.h"
 #include "../picles_b200/csrc/pmath.h"
 #include "../picles_b200/csrc/pmath_trig.h"
+#include "../picles_b200/csrc/pmath_dual.h"
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -83,6 +85,8 @@ typedef struct {
     uint8_t exists;   /* mask != 0 (a real integrator was built, core_2D.jl:455-458) */
     int32_t status;
     int32_t stiff_run; /* consecutive stiff-looking steps (AutoTsit5 monitor) */
+    int32_t as_count;  /* AutoSwitchCache.count: +n consecutive stiff attempts, -n non-stiff */
+    uint8_t as_stiff;  /* AutoSwitchCache.is_stiffalg: Rosenbrock23 is the current algorithm */
 } particle_t;
 
 typedef struct oracle {
@@ -251,6 +255,64 @@ static void rhs(const picles_params_t* P, const double* z, double u, double v,
     }
 }
 
+/* The same right-hand side on dual numbers (partials w.r.t. lne, c̄_x, c̄_y and the wind
+   components): what ForwardDiff evaluates for Rosenbrock23's Jacobian and time gradient
+   (autodiff = true, the default of Rosenbrock23()).  Same operation sequence as rhs(). */
+static pmd_t alpha_func_dual(pmd_t us, pmd_t cgp) { /* IfElse.ifelse(a > 500, 500, a), :215-225 */
+    pmd_t a = pmd_div(us, pmd_scale(2.0, cgp));
+    return (a.v > 500.0) ? pmd_const(500.0) : a;
+}
+static void rhs_dual(const picles_params_t* P, pmd_t lne, pmd_t cx, pmd_t cy, pmd_t u, pmd_t v, const double* M,
+                     double pc, pmd_t* dz) {
+    pmd_t r_g = pmd_const(P->r_g);
+    pmd_t cbar = pmd_sqrt(pmd_add(pmd_sqr(cx), pmd_sqr(cy)));
+    pmd_t us = pmd_sqrt(pmd_add(pmd_sqr(u), pmd_sqr(v)));
+    pmd_t c_gp = pmd_div(pmd_abs(cbar), r_g);
+    pmd_t kp = pmd_cdiv(9.81, pmd_scale(4.0, pmd_maxc(pmd_sqr(c_gp), 1e-2)));
+    pmd_t wp = pmd_cdiv(9.81, pmd_scale(2.0, pmd_maxc(pmd_abs(c_gp), 0.1)));
+    pmd_t gx = pmd_div(cx, r_g), gy = pmd_div(cy, r_g);
+    pmd_t alpha = alpha_func_dual(us, c_gp);
+    pmd_t sg = pmd_sqrt(pmd_add(pmd_sqr(gx), pmd_sqr(gy)));
+    pmd_t msg = pmd_maxc(sg, 1e-4);
+    pmd_t alpha_p = pmd_div(pmd_add(pmd_mul(u, gx), pmd_mul(v, gy)), pmd_scale(2.0, pmd_sqr(msg)));
+    pmd_t Hp = pmd_scale(0.5, pmd_addc(pmd_tanh(pmd_scale(P->p, pmd_addc(alpha_p, -0.85))), 1.0));
+    pmd_t sch = pmd_sech(pmd_scale(10.0, pmd_addc(alpha_p, -0.85)));
+    pmd_t Dp = pmd_addc(pmd_scale(-1.25, pmd_sqr(sch)), 1.0);
+    pmd_t It = pmd_const(0.0), Dt = pmd_const(0.0), Scg = pmd_const(0.0), Sdir = pmd_const(0.0);
+    if (P->input) It = pmd_mul(pmd_scale(P->C_e, Hp), pmd_sqr(alpha));
+    if (P->dissipation) {
+        pmd_t r = pmd_div(kp, pmd_const(P->e_T)), pw;
+        double twon = 2.0 * P->n;
+        if (twon == 4.0) pw = pmd_sqr(pmd_sqr(r));
+        else if (twon == 2.0) pw = pmd_sqr(r);
+        else pw = pmd_pow_given(r, twon, pm_pow(r.v, twon), pm_pow(r.v, twon - 1.0));
+        Dt = pmd_mul(pmd_exp(pmd_scale(P->n, lne)), pw);
+    }
+    if (P->peak_shift) Scg = pmd_mul(pmd_mul(pmd_scale(P->C_alpha, Dp), pmd_sqr(pmd_sqr(kp))), pmd_exp(pmd_scale(2.0, lne)));
+    if (P->direction) {
+        pmd_t a2 = alpha_func_dual(us, sg);
+        pmd_t prod = pmd_mul(us, sg);
+        pmd_t s2 = pmd_const(0.0);
+        if (!(prod.v == 0.0)) {
+            pmd_t t1 = pmd_mul(pmd_mul(u, v), pmd_sub(pmd_scale(2.0, pmd_sqr(gy)), pmd_sqr(sg)));
+            pmd_t t2 = pmd_mul(pmd_mul(gx, gy), pmd_sub(pmd_scale(2.0, pmd_sqr(v)), pmd_sqr(us)));
+            s2 = pmd_mul(pmd_cdiv(2.0, pmd_sqr(prod)), pmd_sub(t1, t2));
+        }
+        Sdir = pmd_mul(pmd_mul(pmd_scale(P->C_varphi, pmd_sqr(a2)), Hp), s2);
+    }
+    pmd_t Ssph = pmd_scale(pc, cx);
+    pmd_t wrs = pmd_mul(pmd_mul(wp, r_g), Scg);
+    dz[0] = pmd_add(wrs, pmd_mul(wp, pmd_sub(It, Dt)));
+    dz[1] = pmd_add(pmd_add(pmd_neg(pmd_mul(cx, wrs)), pmd_mul(cy, Sdir)), pmd_mul(cy, Ssph));
+    dz[2] = pmd_sub(pmd_sub(pmd_neg(pmd_mul(cy, wrs)), pmd_mul(cx, Sdir)), pmd_mul(cx, Ssph));
+    if (P->propagation) {
+        dz[3] = pmd_add(pmd_scale(M[0], cx), pmd_scale(M[1], cy));
+        dz[4] = pmd_add(pmd_scale(M[2], cx), pmd_scale(M[3], cy));
+    } else {
+        dz[3] = pmd_const(0.0); dz[4] = pmd_const(0.0);
+    }
+}
+
 /* ------------------------------------------------------------------------ */
 /* OrdinaryDiffEq restatement                                 */
 /* ------------------------------------------------------------------------ */
@@ -338,7 +400,7 @@ static inline double rms5(const double* x) { /* ODE_DEFAULT_NORM */
 }
 
 /* ode_determine_initdt (Hairer), in-place branch; f0 = f(u0,t) is supplied */
-static double initdt(const rhs_ctx_t* c, const double* u0, double t, const double* f0, int64_t* nrhs) {
+static double initdt(const rhs_ctx_t* c, const double* u0, double t, const double* f0, int64_t* nrhs, double order) {
     const picles_params_t* P = &c->o->P;
     double dtmin = pm_nextfloat_pos(P->dtmin);
     const double smalldt = 1e-6;
@@ -363,8 +425,120 @@ static double initdt(const rhs_ctx_t* c, const double* u0, double t, const doubl
     double mx = pm_max(d1, d2);
     double dt1;
     if (mx <= 1e-15) dt1 = pm_max(1e-6, dt0 * 1e-3);
-    else dt1 = O_EXP10(-(2.0 + O_LOG10(mx)) / 5.0);
+    else dt1 = O_EXP10(-(2.0 + O_LOG10(mx)) / order); /* get_current_alg_order: 5 (Tsit5, DP5), 2 (Rosenbrock23) */
     return pm_max(dtmin, pm_min(pm_min(100.0 * dt0, dt1), P->dtmax));
+}
+
+/* ---- Rosenbrock23 (the stiff algorithm of AutoTsit5(Rosenbrock23())) -----------------------
+ * OrdinaryDiffEq's Rosenbrock23 (Shampine's ode23s): d = 1/(2+sqrt 2), c32 = 6+sqrt 2,
+ *   W = I - dt*d*J,  k1 = W\(f0 + dt*d*dT),  f1 = f(u + dt/2 k1, t + dt/2),
+ *   k2 = W\(f1 - k1) + k1,  u1 = u + dt k2,  f2 = f(u1, t + dt),
+ *   k3 = W\(f2 - c32 (k2 - f1) - 2 (k1 - f0) + dt dT),  utilde = dt/6 (k1 - 2 k2 + k3),
+ * J = df/du and dT = df/dt by automatic differentiation at (u, t) (rhs_dual), the 5x5 system by
+ * LU with partial pivoting.  In a composite algorithm the step also leaves eigen_est = opnorm(J, Inf)
+ * for the AutoSwitch test.  Third-party arithmetic: the operation order inside OrdinaryDiffEq /
+ * LinearSolve is not pinned by the reference. */
+static void wind_value_and_rate(const rhs_ctx_t* c, double ts, double* u, double* v, double* ut, double* vt) {
+    if (c->o->wind_fn) { /* closure mode: central difference for the time gradient */
+        double up, vp, um, vm, h = 1.0;
+        c->o->wind_fn(c->x, c->y, ts, u, v);
+        c->o->wind_fn(c->x, c->y, ts + h, &up, &vp);
+        c->o->wind_fn(c->x, c->y, ts - h, &um, &vm);
+        *ut = (up - um) / (2.0 * h); *vt = (vp - vm) / (2.0 * h);
+        return;
+    }
+    double scale = (double)c->nseg * c->inv_DT;
+    double sg = (ts - c->t_start) * scale;
+    double pu = c->cu[c->nseg], pv = c->cv[c->nseg], du = 0.0, dv = 0.0;
+    for (int m = c->nseg - 1; m >= 0; m--) {
+        double a = sg - (double)m;
+        du = fma(du, a, pu); dv = fma(dv, a, pv);
+        pu = fma(pu, a, c->cu[m]); pv = fma(pv, a, c->cv[m]);
+    }
+    *u = pu; *v = pv;
+    *ut = du * scale; *vt = dv * scale;
+}
+
+/* LU with partial pivoting, in place; returns 0 if a pivot is exactly zero */
+static int lu5(double A[5][5], int* piv) {
+    for (int k = 0; k < 5; k++) {
+        int p = k;
+        double big = fabs(A[k][k]);
+        for (int i = k + 1; i < 5; i++)
+            if (fabs(A[i][k]) > big) { big = fabs(A[i][k]); p = i; }
+        piv[k] = p;
+        if (p != k)
+            for (int j = 0; j < 5; j++) { double tmp = A[k][j]; A[k][j] = A[p][j]; A[p][j] = tmp; }
+        if (A[k][k] == 0.0) return 0;
+        for (int i = k + 1; i < 5; i++) {
+            A[i][k] = A[i][k] / A[k][k];
+            for (int j = k + 1; j < 5; j++) A[i][j] = A[i][j] - A[i][k] * A[k][j];
+        }
+    }
+    return 1;
+}
+static void lu5_solve(double A[5][5], const int* piv, double* b) {
+    for (int k = 0; k < 5; k++) {
+        double tmp = b[k]; b[k] = b[piv[k]]; b[piv[k]] = tmp;
+        for (int i = k + 1; i < 5; i++) b[i] = b[i] - A[i][k] * b[k];
+    }
+    for (int k = 4; k >= 0; k--) {
+        for (int j = k + 1; j < 5; j++) b[k] = b[k] - A[k][j] * b[j];
+        b[k] = b[k] / A[k][k];
+    }
+}
+
+/* one Rosenbrock23 attempt from (u, t) with f0 = f(u, t); fills unew, f2 = f(unew, t+dt), the
+   scaled error estimate and eigen_est; returns 0 when W is singular (EEst = NaN: rejected) */
+static void rosenbrock23_attempt(const rhs_ctx_t* c, const double* u, double t, double dt, const double* f0,
+                                 double* unew, double* f2, double* EEst, double* eigen_est, int64_t* nrhs) {
+    const picles_params_t* P = &c->o->P;
+    const double d = 1.0 / (2.0 + sqrt(2.0)), c32 = 6.0 + sqrt(2.0);
+    double gam = dt * d, dto2 = dt / 2.0, dto6 = dt / 6.0;
+    double wu, wv, wut, wvt;
+    wind_value_and_rate(c, t, &wu, &wv, &wut, &wvt);
+    pmd_t dz[5];
+    rhs_dual(P, pmd_var(u[0], 0), pmd_var(u[1], 1), pmd_var(u[2], 2), pmd_var(wu, 3), pmd_var(wv, 4), c->M, c->pc, dz);
+    (*nrhs)++;
+    double J[5][5], dT[5], W[5][5];
+    double nrm = 0.0;
+    for (int i = 0; i < 5; i++) {
+        double row = 0.0;
+        for (int j = 0; j < 5; j++) {
+            J[i][j] = (j < 3) ? dz[i].d[j] : 0.0; /* the system does not depend on the particle position */
+            row += fabs(J[i][j]);
+        }
+        nrm = pm_max(nrm, row);
+        dT[i] = dz[i].d[3] * wut + dz[i].d[4] * wvt;
+    }
+    *eigen_est = nrm;
+    for (int i = 0; i < 5; i++)
+        for (int j = 0; j < 5; j++) W[i][j] = ((i == j) ? 1.0 : 0.0) - gam * J[i][j];
+    int piv[5];
+    if (!lu5(W, piv)) {
+        for (int i = 0; i < 5; i++) { unew[i] = u[i]; f2[i] = f0[i]; }
+        *EEst = pm_nan();
+        return;
+    }
+    double k1[5], k2[5], k3[5], f1[5], tmp[5];
+    for (int i = 0; i < 5; i++) k1[i] = f0[i] + gam * dT[i];
+    lu5_solve(W, piv, k1);
+    for (int i = 0; i < 5; i++) tmp[i] = u[i] + dto2 * k1[i];
+    f_eval(c, tmp, t + dto2, f1, nrhs);
+    for (int i = 0; i < 5; i++) k2[i] = f1[i] - k1[i];
+    lu5_solve(W, piv, k2);
+    for (int i = 0; i < 5; i++) k2[i] = k2[i] + k1[i];
+    for (int i = 0; i < 5; i++) unew[i] = u[i] + dt * k2[i];
+    f_eval(c, unew, t + dt, f2, nrhs);
+    for (int i = 0; i < 5; i++) k3[i] = f2[i] - c32 * (k2[i] - f1[i]) - 2.0 * (k1[i] - f0[i]) + dt * dT[i];
+    lu5_solve(W, piv, k3);
+    double r[5];
+    for (int i = 0; i < 5; i++) {
+        double ut = dto6 * (k1[i] - 2.0 * k2[i] + k3[i]);
+        double sc = fma(pm_max(fabs(u[i]), fabs(unew[i])), P->reltol, P->abstol);
+        r[i] = ut / sc;
+    }
+    *EEst = rms5(r);
 }
 
 /* step!(integrator, DT, true): integrate one particle from t to t+DT */
@@ -372,17 +546,19 @@ static void integrate(oracle_t* o, particle_t* p, const rhs_ctx_t* c, double DT,
                       int64_t* stiff_triggers) {
     const picles_params_t* P = &o->P;
     const tableau_t* T = (P->solver == PICLES_SOLVER_DP5) ? &DP5 : &TSIT5;
+    const int autosw = (P->solver == PICLES_SOLVER_AUTOTSIT5);
     if (p->status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE)) return; /* dead retcode */
     double t = p->t;
     double tstop = t + DT;
     double u[5], k[8][5];
     int64_t nrhs = 0;
     memcpy(u, p->u, sizeof u);
+    int stiff = autosw && p->as_stiff;
     /* u_modified -> reset_fsal!: k1 = f(u,t) */
     f_eval(c, u, t, k[1], &nrhs);
     double dt = p->dt;
     if (p->dt_reset) {
-        dt = initdt(c, u, t, k[1], &nrhs);
+        dt = initdt(c, u, t, k[1], &nrhs, stiff ? 2.0 : 5.0);
         p->dt_reset = 0;
     }
     double qold = p->qold;
@@ -405,37 +581,48 @@ static void integrate(oracle_t* o, particle_t* p, const rhs_ctx_t* c, double DT,
         }
         attempts++;
         /* perform_step! */
-        double tmp[5], un[5], g6[5];
-        {
-            double a = dt * T->a[2][1];
-            for (int i = 0; i < 5; i++) tmp[i] = fma(a, k[1][i], u[i]);
-            f_eval(c, tmp, fma(T->c[1], dt, t), k[2], &nrhs);
-        }
-        for (int s = 3; s <= 7; s++) {
-            for (int i = 0; i < 5; i++) {
-                double inner = T->a[s][1] * k[1][i];
-                for (int j = 2; j < s; j++)
-                    if (T->a[s][j] != 0.0) inner = fma(T->a[s][j], k[j][i], inner);
-                tmp[i] = fma(dt, inner, u[i]);
+        double tmp[5], un[5], g6[5], fnew[5];
+        double EEst, eig = 0.0;
+        /* PIController exponents of the current algorithm (reset_alg_dependent_opts!):
+           beta2 = 2/(5 order), beta1 = 7/(10 order) */
+        double beta1 = stiff ? 0.35 : T->beta1, beta2 = stiff ? 0.2 : T->beta2;
+        if (stiff) {
+            rosenbrock23_attempt(c, u, t, dt, k[1], un, fnew, &EEst, &eig, &nrhs);
+            C->n_stiff_attempts++;
+        } else {
+            {
+                double a = dt * T->a[2][1];
+                for (int i = 0; i < 5; i++) tmp[i] = fma(a, k[1][i], u[i]);
+                f_eval(c, tmp, fma(T->c[1], dt, t), k[2], &nrhs);
             }
-            double ts = (s >= 6) ? (t + dt) : fma(T->c[s - 1], dt, t);
-            f_eval(c, tmp, ts, k[s], &nrhs);
-            if (s == 6) memcpy(g6, tmp, sizeof g6); /* argument of k6: g6 of the stiffness monitor */
-            if (s == 7) memcpy(un, tmp, sizeof un);
+            for (int s = 3; s <= 7; s++) {
+                for (int i = 0; i < 5; i++) {
+                    double inner = T->a[s][1] * k[1][i];
+                    for (int j = 2; j < s; j++)
+                        if (T->a[s][j] != 0.0) inner = fma(T->a[s][j], k[j][i], inner);
+                    tmp[i] = fma(dt, inner, u[i]);
+                }
+                double ts = (s >= 6) ? (t + dt) : fma(T->c[s - 1], dt, t);
+                f_eval(c, tmp, ts, k[s], &nrhs);
+                if (s == 6) memcpy(g6, tmp, sizeof g6); /* argument of k6: g6 of the stiffness monitor */
+                if (s == 7) memcpy(un, tmp, sizeof un);
+            }
+            memcpy(fnew, k[7], sizeof fnew);
+            /* error estimate */
+            double r[5];
+            for (int i = 0; i < 5; i++) {
+                double inner = T->bt[1] * k[1][i];
+                for (int j = 2; j <= 7; j++)
+                    if (T->bt[j] != 0.0) inner = fma(T->bt[j], k[j][i], inner);
+                double ut = dt * inner;
+                double sc = fma(pm_max(fabs(u[i]), fabs(un[i])), P->reltol, P->abstol);
+                r[i] = ut / sc;
+            }
+            EEst = rms5(r);
+            /* Tsit5 in a composite algorithm: eigen_est = max_i |k7-k6| / |g7-g6| (Hairer II, p. 22) */
+            if (T == &TSIT5)
+                for (int i = 0; i < 5; i++) eig = pm_max(eig, fabs((k[7][i] - k[6][i]) / (un[i] - g6[i])));
         }
-        double k7s[5];
-        memcpy(k7s, k[7], sizeof k7s);
-        /* error estimate */
-        double r[5];
-        for (int i = 0; i < 5; i++) {
-            double inner = T->bt[1] * k[1][i];
-            for (int j = 2; j <= 7; j++)
-                if (T->bt[j] != 0.0) inner = fma(T->bt[j], k[j][i], inner);
-            double ut = dt * inner;
-            double sc = fma(pm_max(fabs(u[i]), fabs(un[i])), P->reltol, P->abstol);
-            r[i] = ut / sc;
-        }
-        double EEst = rms5(r);
         /* stepsize_controller! (PIController): q = EEst^beta1 / qold^beta2, evaluated as
            exp(beta1*log(EEst) - beta2*log(qold)); OrdinaryDiffEq evaluates the two powers
            with an approximate `fastpow`, so the last bits are not pinned by the reference */
@@ -443,9 +630,9 @@ static void integrate(oracle_t* o, particle_t* p, const rhs_ctx_t* c, double DT,
         if (EEst == 0.0) {
             q = 1.0 / qmax;
         } else {
-            double t1 = T->beta1 * O_LOG(EEst);
+            double t1 = beta1 * O_LOG(EEst);
             q11 = O_EXP(t1);
-            q = O_EXP(t1 - T->beta2 * O_LOG(qold));
+            q = O_EXP(t1 - beta2 * O_LOG(qold));
             q = pm_max(1.0 / qmax, pm_min(1.0 / qmin, q / gamma));
         }
         int accept = (EEst <= 1.0) || (P->force_dtmin && fabs(dt) <= dtmin_t);
@@ -461,7 +648,7 @@ static void integrate(oracle_t* o, particle_t* p, const rhs_ctx_t* c, double DT,
             dtp = pm_max(dtp, pm_max(pm_eps(t), P->dtmin));
             dt = dtp;
             memcpy(u, un, sizeof u);
-            memcpy(k[1], k[7], sizeof k[1]); /* FSAL */
+            memcpy(k[1], fnew, sizeof k[1]); /* FSAL: k7 (Tsit5/DP5), f(u1, t+dt) (Rosenbrock23) */
             C->n_substeps++;
             int bad = 0;
             for (int i = 0; i < 5; i++) bad |= (u[i] != u[i]);
@@ -471,21 +658,41 @@ static void integrate(oracle_t* o, particle_t* p, const rhs_ctx_t* c, double DT,
             dt = dt / pm_min(1.0 / qmin, q11 / gamma);
             C->n_rejects++;
         }
-        /* AutoTsit5(Rosenbrock23) stiffness monitor, counted only:
-           eigen_est = max_i |k7-k6| / |g7-g6| ; stiff if |eigen_est*dt/3.5068| > 0.9
-           for more than 10 consecutive attempts */
+        /* AutoSwitch (AutoTsit5 defaults: maxstiffstep 10, maxnonstiffstep 3, nonstifftol = stifftol
+           = 9//10, dtfac 2, stability_size(Tsit5) = 3.5068), evaluated with the eigenvalue estimate
+           of the attempt just made and the step size the controller proposes:
+           solver Tsit5 only counts how often the switch would have happened */
         if (T == &TSIT5) {
-            double est = 0.0;
-            for (int i = 0; i < 5; i++) est = pm_max(est, fabs((k7s[i] - k[6][i]) / (un[i] - g6[i])));
-            double stiffness = fabs(est * dt / 3.5068);
-            if (stiffness > 0.9) p->stiff_run = (p->stiff_run < 0) ? 1 : p->stiff_run + 1;
-            else p->stiff_run = (p->stiff_run > 0) ? -1 : p->stiff_run - 1;
-            if (p->stiff_run > 10) {
+            double stiffness = fabs(eig * dt / 3.5068);
+            if (autosw) {
+                int is = stiffness > 0.9;
+                int32_t cnt = p->as_count;
+                cnt = is ? ((cnt < 0) ? 1 : cnt + 1) : ((cnt > 0) ? -1 : cnt - 1);
+                if (cnt > 60) cnt = 60;
+                if (cnt < -60) cnt = -60;
+                int switched = 0;
+                if (!stiff && cnt > 10) {
+                    dt = dt * 2.0; stiff = 1; switched = 1; C->n_stiff_switches++;
 #ifdef _OPENMP
 #pragma omp atomic
 #endif
-                (*stiff_triggers)++;
-                p->stiff_run = 0;
+                    (*stiff_triggers)++;
+                } else if (stiff && cnt < -3) {
+                    dt = dt / 2.0; stiff = 0; switched = 1;
+                }
+                p->as_count = cnt;
+                /* choose_algorithm!: initialize!(integrator, new cache) re-evaluates fsalfirst = f(uprev, t) */
+                if (switched && t < tstop) f_eval(c, u, t, k[1], &nrhs);
+            } else {
+                if (stiffness > 0.9) p->stiff_run = (p->stiff_run < 0) ? 1 : p->stiff_run + 1;
+                else p->stiff_run = (p->stiff_run > 0) ? -1 : p->stiff_run - 1;
+                if (p->stiff_run > 10) {
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+                    (*stiff_triggers)++;
+                    p->stiff_run = 0;
+                }
             }
         }
     }
@@ -494,6 +701,7 @@ static void integrate(oracle_t* o, particle_t* p, const rhs_ctx_t* c, double DT,
     p->dt = dt;
     p->qold = qold;
     p->iter = iter;
+    p->as_stiff = (uint8_t)stiff;
     C->n_rhs += nrhs;
     C->n_integrated++;
     if (attempts > C->max_attempts) C->max_attempts = attempts;
@@ -771,12 +979,14 @@ static void remesh_particle(oracle_t* o, int64_t l, double DT, const double* u_t
     } else if (!p->boundary && (wu * wu + wv * wv >= P->wind_min_squared)) { /* :328-336 */
         reset_particle_values(P, wu, wv, DT, p->u);
         p->qold = QOLDINIT; p->iter = 0; p->status = 0; /* reinit! */
+        p->as_count = 0; p->as_stiff = 0;                /* ... with a fresh AutoSwitch state */
         p->dt_reset = 1;
         on = 1;
         C->n_remesh_B++;
     } else if (p->boundary && (wu * wu + wv * wv >= P->wind_min_squared)) { /* :338-344 */
         reset_particle_values(P, wu, wv, DT, p->u);
         p->qold = QOLDINIT; p->iter = 0; p->status = 0;
+        p->as_count = 0; p->as_stiff = 0;
         p->dt_reset = 1;
         on = 1;
         C->n_remesh_C++;
@@ -813,6 +1023,7 @@ void oracle_step(oracle_t* o, double t, double DT, const double* u_t, const doub
                 C.n_integrated += Cl.n_integrated; C.n_substeps += Cl.n_substeps; C.n_rejects += Cl.n_rejects;
                 C.n_rhs += Cl.n_rhs; C.n_reseed_advance += Cl.n_reseed_advance; C.n_fixups += Cl.n_fixups;
                 C.n_failed += Cl.n_failed;
+                C.n_stiff_switches += Cl.n_stiff_switches; C.n_stiff_attempts += Cl.n_stiff_attempts;
                 if (Cl.max_attempts > C.max_attempts) C.max_attempts = Cl.max_attempts;
             }
         }
@@ -856,6 +1067,11 @@ void oracle_get_aux(const oracle_t* o, double* qold, int64_t* iter) {
     for (int64_t l = 0; l < n; l++) { if (qold) qold[l] = o->part[l].qold; if (iter) iter[l] = o->part[l].iter; }
 }
 void oracle_get_counters(const oracle_t* o, picles_counters_t* c) { *c = o->C; }
+/* AutoSwitch state as picles_get_solver_state packs it */
+void oracle_get_solver_state(const oracle_t* o, int8_t* as) {
+    int64_t n = (int64_t)o->Nx * o->Ny;
+    for (int64_t l = 0; l < n; l++) as[l] = (int8_t)(o->part[l].as_count + (o->part[l].as_stiff ? 64 : 0));
+}
 int64_t oracle_n_ocean(const oracle_t* o) { return o->n_ocean; }
 /* derived output fields: Hs = 4*sqrt(e) (movie_2D.jl:50), GetGroupVelocity (core_2D.jl:138-147) */
 void oracle_fields(const oracle_t* o, double* Hs, double* cx, double* cy) {
@@ -965,10 +1181,12 @@ int64_t oracle_corner_target(int Nx, int Ny, int bx, int by, int64_t i, int64_t 
     } else { ii = wrap_index(i, Nx); jj = wrap_index(j, Ny); }
     return (ii - 1) + (jj - 1) * (int64_t)Nx;
 }
-/* single-particle driver: integrate u over DT with constant wind; returns substeps */
-void oracle_integrate_one(const picles_params_t* P, const double* M, double pc, double* u5, double* t,
-                          double* dt, double* qold, int64_t* iter, int dt_reset, double wu0, double wv0,
-                          double wu1, double wv1, double DT, picles_counters_t* C_out, int32_t* status) {
+/* single-particle driver: integrate u over DT with the wind linear between two levels;
+   as2 = {AutoSwitch count, is_stiffalg} in/out (NULL: a fresh non-stiff integrator) */
+void oracle_integrate_one_as(const picles_params_t* P, const double* M, double pc, double* u5, double* t,
+                             double* dt, double* qold, int64_t* iter, int dt_reset, double wu0, double wv0,
+                             double wu1, double wv1, double DT, picles_counters_t* C_out, int32_t* status,
+                             int32_t* as2) {
     oracle_t o;
     memset(&o, 0, sizeof o);
     o.P = *P;
@@ -977,6 +1195,7 @@ void oracle_integrate_one(const picles_params_t* P, const double* M, double pc, 
     memcpy(p.u, u5, sizeof p.u);
     p.t = *t; p.dt = *dt; p.qold = *qold; p.iter = *iter; p.dt_reset = (uint8_t)dt_reset; p.on = 1;
     p.status = *status;
+    if (as2) { p.as_count = as2[0]; p.as_stiff = (uint8_t)(as2[1] != 0); }
     rhs_ctx_t c;
     c.o = &o; c.M = M; c.pc = pc;
     {
@@ -991,7 +1210,23 @@ void oracle_integrate_one(const picles_params_t* P, const double* M, double pc, 
     integrate(&o, &p, &c, DT, &C, &o.stiff_triggers);
     memcpy(u5, p.u, sizeof p.u);
     *t = p.t; *dt = p.dt; *qold = p.qold; *iter = p.iter; *status = p.status;
+    if (as2) { as2[0] = p.as_count; as2[1] = p.as_stiff; }
     if (C_out) *C_out = C;
+}
+void oracle_integrate_one(const picles_params_t* P, const double* M, double pc, double* u5, double* t,
+                          double* dt, double* qold, int64_t* iter, int dt_reset, double wu0, double wv0,
+                          double wu1, double wv1, double DT, picles_counters_t* C_out, int32_t* status) {
+    oracle_integrate_one_as(P, M, pc, u5, t, dt, qold, iter, dt_reset, wu0, wv0, wu1, wv1, DT, C_out, status, NULL);
+}
+/* Jacobian (5x5, row-major) and time gradient of the right-hand side by dual numbers */
+void oracle_rhs_jacobian(const picles_params_t* P, const double* z, double u, double v, double ut, double vt,
+                         const double* M, double pc, double* J25, double* dT5) {
+    pmd_t dz[5];
+    rhs_dual(P, pmd_var(z[0], 0), pmd_var(z[1], 1), pmd_var(z[2], 2), pmd_var(u, 3), pmd_var(v, 4), M, pc, dz);
+    for (int i = 0; i < 5; i++) {
+        for (int j = 0; j < 5; j++) J25[i * 5 + j] = (j < 3) ? dz[i].d[j] : 0.0;
+        dT5[i] = dz[i].d[3] * ut + dz[i].d[4] * vt;
+    }
 }
 
 #define VEC_HOOK(name, expr)                                         \

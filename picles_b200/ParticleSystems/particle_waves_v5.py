@@ -10,7 +10,7 @@ import math
 from dataclasses import dataclass, field
 from typing import Any, Callable, Optional
 
-SOLVERS = {"Tsit5": 0, "AutoTsit5": 0, "AutoTsit5(Rosenbrock23())": 0, "DP5": 1}
+SOLVERS = {"Tsit5": 0, "AutoTsit5": 2, "AutoTsit5(Rosenbrock23())": 2, "DP5": 1}
 
 
 def magic_fractions(q: float = -1 / 4.0):

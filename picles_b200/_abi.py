@@ -17,7 +17,7 @@ ABI_VERSION = 2
 # enums (include/picles_b200.h)
 BND_NONPERIODIC, BND_PERIODIC, BND_TRIPOLAR_NORTH = 0, 1, 2
 MASK_LAND, MASK_OCEAN, MASK_LAND_BOUNDARY, MASK_GRID_BOUNDARY = 0, 1, 2, 3
-SOLVER_TSIT5, SOLVER_DP5 = 0, 1
+SOLVER_TSIT5, SOLVER_DP5, SOLVER_AUTOTSIT5 = 0, 1, 2
 PST_OK, PST_MAXITERS, PST_DTMIN, PST_UNSTABLE = 0, 1, 2, 4
 PST_NAN_RESET, PST_INF_RESET, PST_EMAX_CLAMP = 8, 16, 32
 PF_ON, PF_BOUNDARY, PF_DT_RESET, PF_ACTIVE = 1, 2, 4, 8
@@ -89,6 +89,8 @@ class PiclesCounters(C.Structure):
         ("ms_advance", C.c_double),
         ("ms_project", C.c_double),
         ("ms_remesh", C.c_double),
+        ("n_stiff_switches", C.c_int64),
+        ("n_stiff_attempts", C.c_int64),
     ]
 
     def as_dict(self):
@@ -145,6 +147,7 @@ SYMBOLS = {
     "picles_snapshot_wait": (C.c_int, [_vp]),
     "picles_get_particles": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "picles_get_counters": (C.c_int, [_vp, C.POINTER(PiclesCounters)]),
+    "picles_get_solver_state": (C.c_int, [_vp, _vp]),
     "picles_state_energy_sum": (C.c_int, [_vp, _dp]),
     "picles_state_dev": (C.c_int, [_vp, C.POINTER(_vp)]),
     "picles_wind_dev": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),

@@ -109,6 +109,7 @@ PM_HD const Tableau& tableau(int solver) {
 enum {
     KS_U3 = 21, KS_U4, KS_X7, KS_Y7, KS_XE, KS_YE, KS_TSTOP, KS_LQ, KS_QOLD, KS_DT0, KS_D1N, KS_DTMIN,
     KS_WT0, KS_WIDT,
+    KS_X6, KS_Y6, /* AutoTsit5 monitor: propagation part of the argument of stage 6 */
     KS_WCU,                            /* Newton coefficients c_1..c_4 of the wind's u component in time */
     KS_WCV = KS_WCU + PH_WIND_SEG_MAX, /* ... and of v */
     KS_SLOTS = KS_WCV + PH_WIND_SEG_MAX
@@ -136,7 +137,10 @@ struct Particle {
     int32_t iter;
     uint8_t flags;  /* PICLES_PF_* */
     uint8_t status; /* PICLES_PST_* */
+    int8_t as;      /* AutoTsit5: run length of the stiffness test, +64 while Rosenbrock23 is current */
 };
+#define PH_AS_STIFF 64
+#define PH_AS_CLAMP 60
 
 /* wind at the home node: nseg+1 levels equally spaced over [t, t+DT] (lvl[0] = level t,
    lvl[nseg] = level t+DT; nseg = 1 unless intermediate levels were staged) */
@@ -179,12 +183,14 @@ struct Hoist {
 struct Tally {
     int32_t integrated, substeps, rejects, rhs, reseed, fixups, failed, deposited, A, B, C, D;
     int32_t reach, max_attempts;
+    int32_t stiff_switches, stiff_attempts; /* AutoTsit5: Tsit5 -> Rosenbrock23 switches, Rosenbrock23 attempts */
 };
 PM_HD void tally_zero(Tally& c) {
     c.integrated = c.substeps = c.rejects = c.rhs = c.reseed = c.fixups = c.failed = c.deposited = 0;
     c.A = c.B = c.C = c.D = 0;
     c.reach = 0;
     c.max_attempts = 0;
+    c.stiff_switches = c.stiff_attempts = 0;
 }
 
 /* deposit record written by the advance kernel and read by the projection gather */
@@ -497,7 +503,7 @@ PM_HD bool initdt_a(const picles_params_t& P, double u0, double u1, double u2, d
 template <class O>
 PM_HD double initdt_b(const picles_params_t& P, double u0, double u1, double u2, double u3, double u4, double k0,
                       double k1, double k2, double k3, double k4, double f0, double f1, double f2, double f3x,
-                      double f4x, double dt0, double d1, unsigned* bad) {
+                      double f4x, double dt0, double d1, double order, unsigned* bad) {
     double dtmin = pm_nextfloat_pos(P.dtmin);
     bool same = (k0 == f0) & (k1 == f1) & (k2 == f2) & (k3 == f3x) & (k4 == f4x);
     double s0 = fma(fabs(u0), P.reltol, P.abstol);
@@ -511,7 +517,7 @@ PM_HD double initdt_b(const picles_params_t& P, double u0, double u1, double u2,
     double mx = pm_max(d1, d2);
     bool flat = (mx <= 1e-15);
     double lg = O::log10_(flat ? 1.0 : mx, bad);
-    double dt1 = flat ? pm_max(1e-6, dt0 * 1e-3) : pm_exp10(O::div(-(2.0 + lg), 5.0, bad));
+    double dt1 = flat ? pm_max(1e-6, dt0 * 1e-3) : pm_exp10(O::div(-(2.0 + lg), order, bad)); /* get_current_alg_order: 5, or 2 under Rosenbrock23 */
     double dt = pm_max(dtmin, pm_min(pm_min(100.0 * dt0, dt1), P.dtmax));
     return same ? pm_max(dtmin, 100.0 * dt0) : dt;
 }
@@ -523,8 +529,8 @@ PM_HD_NOINLINE_DECL bool initdt_a_cold(const picles_params_t& P, double u0, doub
 }
 PM_HD_NOINLINE_DECL double initdt_b_cold(const picles_params_t& P, double u0, double u1, double u2, double u3,
                                          double u4, double k0, double k1, double k2, double k3, double k4, double f0,
-                                         double f1, double f2, double f3x, double f4x, double dt0, double d1) {
-    return initdt_b<OpsSafe>(P, u0, u1, u2, u3, u4, k0, k1, k2, k3, k4, f0, f1, f2, f3x, f4x, dt0, d1, (unsigned*)0);
+                                         double f1, double f2, double f3x, double f4x, double dt0, double d1, double order) {
+    return initdt_b<OpsSafe>(P, u0, u1, u2, u3, u4, k0, k1, k2, k3, k4, f0, f1, f2, f3x, f4x, dt0, d1, order, (unsigned*)0);
 }
 
 /* ---- error estimate + PI controller of one attempt -------------------------------- */
@@ -577,10 +583,22 @@ PM_HD_NOINLINE_DECL void step_control_cold(const picles_params_t& P, const Table
  * k_j[3:4] = M*c̄_j are folded into the running sums of stage 7 (x7,y7) and of the error
  * estimate (xe,ye) as each k_j appears — the same fma chain as storing them.
  */
+/*
+ * AutoTsit5 (P.solver == PICLES_SOLVER_AUTOTSIT5): every attempt also leaves OrdinaryDiffEq's
+ * stiffness estimate eigen_est = max_i |k7_i - k6_i| / |g7_i - g6_i| (Hairer II, p. 22; g6, g7 the
+ * arguments of stages 6 and 7) and the AutoSwitch run length as_count is updated with
+ * |eigen_est * dt / 3.5068| > 9/10; more than ten stiff attempts in a row hand the particle to
+ * Rosenbrock23 (stiff.h, out of line).  Return value: 0 = step complete or integrator stopped;
+ * 1 = Rosenbrock23 is the current algorithm at the start of the step (k1 = f(u, t) is in K);
+ * 2 = AutoSwitch switched just now (dt doubled).  tstop = p.t + DT of the first entry; attempts
+ * accumulates over re-entries.
+ */
 template <class KS>
-PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, double pc, double DT, Particle& p,
-                     Tally& c, KS& K) {
-    if (p.status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE)) return;
+PM_HD int integrate(const picles_params_t& P, const Wind& w, const double* M, double pc, double tstop_in, Particle& p,
+                    Tally& c, KS& K, int& as_count, bool& as_stiff, int& attempts_io) {
+    if (p.status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE)) return 0;
+    const bool autosw = (P.solver == PICLES_SOLVER_AUTOTSIT5);
+    int ret = 0;
     const Tableau& T = tableau(P.solver);
     Hoist H;
     const double wu0 = w.ul[0], wv0 = w.vl[0];
@@ -607,7 +625,7 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
     }
     K.st(KS_WT0, w.t_start); K.st(KS_WIDT, (double)w.nseg * w.inv_DT);
     double t = p.t;
-    K.st(KS_TSTOP, t + DT);
+    K.st(KS_TSTOP, tstop_in);
     double u0 = p.u0, u1 = p.u1, u2 = p.u2;
     K.st(KS_U3, p.u3); K.st(KS_U4, p.u4);
     double dt = p.dt;
@@ -615,8 +633,9 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
     K.st(KS_LQ, pm_log(p.qold));
     const double LQ0 = PH_LOG_QOLDINIT; /* pm_log(1e-4), pinned by tests/test_pmath.py */
     int32_t iter = p.iter;
-    int32_t nrhs = 0, attempts = 0;
+    int32_t nrhs = 0, attempts = attempts_io;
     const double qmin = 0.2, gamma = 0.9;
+    const double order = (autosw && as_stiff) ? 2.0 : 5.0;
     bool need_reset = (p.flags & PICLES_PF_DT_RESET) != 0;
     p.flags &= (uint8_t)~PICLES_PF_DT_RESET;
 
@@ -624,6 +643,7 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
     double n0 = u0, n1 = u1, n2 = u2, ts = t; /* argument of the next right-hand side */
     K.st(KS_X7, 0.0); K.st(KS_Y7, 0.0); K.st(KS_XE, 0.0); K.st(KS_YE, 0.0); K.st(KS_DT0, 0.0); K.st(KS_D1N, 0.0);
     K.st(KS_DTMIN, P.dtmin);
+    K.st(KS_X6, 0.0); K.st(KS_Y6, 0.0);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -641,6 +661,10 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
             }
             double bs = T.bt[ph];
             if (bs != 0.0) { K.st(KS_XE, fma(bs, kx, K.ld(KS_XE))); K.st(KS_YE, fma(bs, ky, K.ld(KS_YE))); }
+            if (autosw && ph < 6) {
+                double a6 = T.a[6][ph];
+                if (a6 != 0.0) { K.st(KS_X6, fma(a6, kx, K.ld(KS_X6))); K.st(KS_Y6, fma(a6, ky, K.ld(KS_Y6))); }
+            }
             if (ph < 7) {
                 /* argument of stage s = ph+1 >= 3 */
                 int s = ++ph;
@@ -675,6 +699,26 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
             step_control_cold(P, T, dt, e0, e1, e2, xe, ye, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, lq, sc);
 #endif
             double EEst = sc.EEst;
+            double eig = 0.0;
+            if (autosw) {
+                /* g6 = u + dt * sum_j a6j k_j, rebuilt from the stored stage derivatives */
+                double a1 = T.a[6][1];
+                double i0 = a1 * K.get(1, 0), i1 = a1 * K.get(1, 1), i2 = a1 * K.get(1, 2);
+                for (int j = 2; j < 6; j++) {
+                    double aj = T.a[6][j];
+                    if (aj != 0.0) { i0 = fma(aj, K.get(j, 0), i0); i1 = fma(aj, K.get(j, 1), i1); i2 = fma(aj, K.get(j, 2), i2); }
+                }
+                const double g60 = fma(dt, i0, u0), g61 = fma(dt, i1, u1), g62 = fma(dt, i2, u2);
+                const double g63 = fma(dt, K.ld(KS_X6), u3), g64 = fma(dt, K.ld(KS_Y6), u4);
+                double k6x, k6y, k7x, k7y;
+                prop(P, M, g61, g62, k6x, k6y);
+                prop(P, M, n1, n2, k7x, k7y);
+                eig = pm_max(eig, fabs((K.get(7, 0) - K.get(6, 0)) / (n0 - g60)));
+                eig = pm_max(eig, fabs((K.get(7, 1) - K.get(6, 1)) / (n1 - g61)));
+                eig = pm_max(eig, fabs((K.get(7, 2) - K.get(6, 2)) / (n2 - g62)));
+                eig = pm_max(eig, fabs((k7x - k6x) / (n3 - g63)));
+                eig = pm_max(eig, fabs((k7y - k6y) / (n4 - g64)));
+            }
             bool accept = (EEst <= 1.0) || (P.force_dtmin && fabs(dt) <= K.ld(KS_DTMIN));
             if (accept) {
                 /* step_accept_controller!, fixed_t_for_floatingpoint_error!, calc_dt_propose! */
@@ -700,6 +744,21 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
                 double q11 = (EEst == 0.0) ? 1.0 : pm_exp(sc.t1);
                 dt = dt / pm_min(1.0 / qmin, q11 / gamma);
                 c.rejects++;
+            }
+            if (autosw) {
+                /* AutoSwitch: maxstiffstep 10, nonstifftol 9//10, dtfac 2, stability_size(Tsit5) 3.5068 */
+                const bool is = fabs(eig * dt / 3.5068) > 0.9;
+                int cnt = as_count;
+                cnt = is ? ((cnt < 0) ? 1 : cnt + 1) : ((cnt > 0) ? -1 : cnt - 1);
+                cnt = (cnt > PH_AS_CLAMP) ? PH_AS_CLAMP : ((cnt < -PH_AS_CLAMP) ? -PH_AS_CLAMP : cnt);
+                as_count = cnt;
+                if (cnt > 10) {
+                    dt = dt * 2.0;
+                    as_stiff = true;
+                    c.stiff_switches++;
+                    ret = 2;
+                    break;
+                }
             }
         } else if (ph == 1) {
             K.set(1, 0, d0); K.set(1, 1, d1); K.set(1, 2, d2);
@@ -734,15 +793,16 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
             const double u3 = K.ld(KS_U3), u4 = K.ld(KS_U4), dt0 = K.ld(KS_DT0), d1n = K.ld(KS_D1N);
 #if defined(__CUDA_ARCH__)
             unsigned bad = 0;
-            dt = initdt_b<OpsFast>(P, u0, u1, u2, u3, u4, k0, k1, k2, k3, k4, d0, d1, d2, f3x, f4x, dt0, d1n, &bad);
-            if (bad) dt = initdt_b_cold(P, u0, u1, u2, u3, u4, k0, k1, k2, k3, k4, d0, d1, d2, f3x, f4x, dt0, d1n);
+            dt = initdt_b<OpsFast>(P, u0, u1, u2, u3, u4, k0, k1, k2, k3, k4, d0, d1, d2, f3x, f4x, dt0, d1n, order, &bad);
+            if (bad) dt = initdt_b_cold(P, u0, u1, u2, u3, u4, k0, k1, k2, k3, k4, d0, d1, d2, f3x, f4x, dt0, d1n, order);
 #else
-            dt = initdt_b_cold(P, u0, u1, u2, u3, u4, k0, k1, k2, k3, k4, d0, d1, d2, f3x, f4x, dt0, d1n);
+            dt = initdt_b_cold(P, u0, u1, u2, u3, u4, k0, k1, k2, k3, k4, d0, d1, d2, f3x, f4x, dt0, d1n, order);
 #endif
         }
         /* ---- header of the next attempt: loopheader!, check_error! ---- */
         const double tstop = K.ld(KS_TSTOP);
         if (!(t < tstop)) break;
+        if (autosw && as_stiff) { ret = 1; break; } /* Rosenbrock23 is current: its attempts run out of line */
         iter++;
         const double dtmin_t = pm_max(pm_eps(t), P.dtmin);
         K.st(KS_DTMIN, dtmin_t);
@@ -758,6 +818,7 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
             prop(P, M, u1, u2, kx, ky);
             K.st(KS_X7, T.a[7][1] * kx); K.st(KS_Y7, T.a[7][1] * ky);
             K.st(KS_XE, T.bt[1] * kx); K.st(KS_YE, T.bt[1] * ky);
+            if (autosw) { K.st(KS_X6, T.a[6][1] * kx); K.st(KS_Y6, T.a[6][1] * ky); }
             double a = dt * T.a[2][1];
             n0 = fma(a, K.get(1, 0), u0); n1 = fma(a, K.get(1, 1), u1); n2 = fma(a, K.get(1, 2), u2);
             ts = fma(T.c[1], dt, t);
@@ -767,8 +828,8 @@ PM_HD void integrate(const picles_params_t& P, const Wind& w, const double* M, d
     p.u0 = u0; p.u1 = u1; p.u2 = u2; p.u3 = K.ld(KS_U3); p.u4 = K.ld(KS_U4);
     p.t = t; p.dt = dt; p.qold = K.ld(KS_QOLD); p.iter = iter;
     c.rhs += nrhs;
-    c.integrated++;
-    if (attempts > c.max_attempts) c.max_attempts = attempts;
+    attempts_io = attempts;
+    return ret;
 }
 
 /* ---- ParticleInCell ------------------------------------------------------- */
@@ -1031,6 +1092,12 @@ PM_HD void gather_node(const RecView& V, int I, int J, int R, int n_classes, dou
     }
 }
 
+/* the Rosenbrock23 attempts of a particle AutoSwitch has declared stiff (stiff.h, out of line);
+   true: handed back to Tsit5 with time left in the step */
+PM_HD_NOINLINE_DECL bool stiff_phase(const picles_params_t* Pp, const Wind* w, const double* M, double pc, double tstop,
+                                     Particle* p, int* as_count, bool* as_stiff, int* attempts, bool have_f0, double f00,
+                                     double f01, double f02, Tally* c);
+
 /* ---- advance! (everything except the scatter, which the gather replaces) ----- */
 /* um/vm: the nmid intermediate wind levels at t + k*DT/(nmid+1), k = 1..nmid (nmid = 0: none) */
 template <class KS>
@@ -1051,7 +1118,27 @@ PM_HD void advance_particle(const picles_params_t& P, Particle& p, int mask, dou
             w.vl[k] = (k <= nmid) ? vm[k - 1] : ((k == nmid + 1) ? wv1 : 0.0);
         }
         w.t_start = t_start; w.inv_DT = 1.0 / DT;
-        integrate(P, w, M, pc, DT, p, c, K);
+        if (!(p.status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE))) {
+            const bool autosw = (P.solver == PICLES_SOLVER_AUTOTSIT5);
+            const double tstop = t_start + DT;
+            int attempts = 0;
+            int as_count = 0;
+            bool as_stiff = false;
+            if (autosw) {
+                as_stiff = p.as > PH_AS_CLAMP;
+                as_count = as_stiff ? (int)p.as - PH_AS_STIFF : (int)p.as;
+            }
+            for (;;) { /* one pass unless AutoSwitch moves the particle between Tsit5 and Rosenbrock23 */
+                const int code = integrate(P, w, M, pc, tstop, p, c, K, as_count, as_stiff, attempts);
+                if (code == 0) break;
+                if (!stiff_phase(&P, &w, M, pc, tstop, &p, &as_count, &as_stiff, &attempts, code == 1, K.get(1, 0),
+                                 K.get(1, 1), K.get(1, 2), &c))
+                    break;
+            }
+            if (autosw) p.as = (int8_t)(as_count + (as_stiff ? PH_AS_STIFF : 0));
+            c.integrated++;
+            if (attempts > c.max_attempts) c.max_attempts = attempts;
+        }
     } else {
         if (wu1 * wu1 + wv1 * wv1 >= P.wind_min_squared) {
             reset_particle_values(P, wu1, wv1, DT, p);
@@ -1109,12 +1196,14 @@ PM_HD void remesh_particle(const picles_params_t& P, Particle& p, double e, doub
     } else if (!boundary && (wu * wu + wv * wv >= P.wind_min_squared)) {
         reset_particle_values(P, wu, wv, DT, p);
         p.qold = PH_QOLDINIT; p.iter = 0; p.status = 0;
+        p.as = 0; /* reinit!: a fresh AutoSwitch state */
         p.flags |= PICLES_PF_DT_RESET;
         on = true;
         c.B++;
     } else if (boundary && (wu * wu + wv * wv >= P.wind_min_squared)) {
         reset_particle_values(P, wu, wv, DT, p);
         p.qold = PH_QOLDINIT; p.iter = 0; p.status = 0;
+        p.as = 0;
         p.flags |= PICLES_PF_DT_RESET;
         on = true;
         c.C++;
@@ -1130,7 +1219,7 @@ PM_HD void remesh_particle(const picles_params_t& P, Particle& p, double e, doub
 PM_HD bool seed_particle(const picles_params_t& P, int mask, double wu, double wv, Particle& p, double& e,
                          double& mx, double& my) {
     p.u0 = p.u1 = p.u2 = p.u3 = p.u4 = 0.0;
-    p.t = 0.0; p.dt = 0.0; p.qold = 0.0; p.iter = 0; p.flags = 0; p.status = 0;
+    p.t = 0.0; p.dt = 0.0; p.qold = 0.0; p.iter = 0; p.flags = 0; p.status = 0; p.as = 0;
     e = mx = my = 0.0;
     if (mask == PICLES_MASK_LAND) return false;
     bool on;

@@ -304,6 +304,8 @@ static int set_grid_impl(picles_t* h, int Nx, int Ny, int bx, int by, int j0, in
     DALLOC(A.t, n); DALLOC(A.dt, n); DALLOC(A.qold, n);
     DALLOC(A.iter, n);
     DALLOC(A.flags, n); DALLOC(A.status, n); DALLOC(A.mask, n);
+    DALLOC(A.as, n);
+    CK(cudaMemsetAsync(A.as, 0, (size_t)n, h->stream));
     DALLOC(A.u_t, n); DALLOC(A.v_t, n); DALLOC(A.u_t1, n); DALLOC(A.v_t1, n);
     for (int k = 0; k < 5; k++) DALLOC(A.rec[k], ne);
     DALLOC(A.cell, ne);
@@ -415,7 +417,8 @@ int picles_make_boundaries(picles_t* h, int Nx, int Ny, int bx, int by, const ui
 
 int picles_set_params(picles_t* h, const picles_params_t* p) {
     if (!h || !p) return fail(h, PICLES_ERR_ARG, "null argument");
-    if (p->solver != PICLES_SOLVER_TSIT5 && p->solver != PICLES_SOLVER_DP5) return fail(h, PICLES_ERR_ARG, "unknown solver id %d", p->solver);
+    if (p->solver != PICLES_SOLVER_TSIT5 && p->solver != PICLES_SOLVER_DP5 && p->solver != PICLES_SOLVER_AUTOTSIT5)
+        return fail(h, PICLES_ERR_ARG, "unknown solver id %d", p->solver);
     if (!p->adaptive) return fail(h, PICLES_ERR_ARG, "adaptive=false is not supported");
     if (!(p->abstol > 0) || !(p->reltol > 0) || !(p->dtmin >= 0) || !(p->dt > 0) || !(p->dtmax > 0) || !(p->r_g > 0) || !(p->e_T > 0))
         return fail(h, PICLES_ERR_ARG, "non-positive tolerance / step / constant in params");
@@ -647,6 +650,7 @@ static int finish_counters(picles_t* h) {
     c.n_failed = (int64_t)d.sums[6]; c.n_deposited = (int64_t)d.sums[7];
     c.n_remesh_A = (int64_t)d.sums[8]; c.n_remesh_B = (int64_t)d.sums[9]; c.n_remesh_C = (int64_t)d.sums[10];
     c.n_remesh_D = (int64_t)d.sums[11];
+    c.n_stiff_switches = (int64_t)d.sums[12]; c.n_stiff_attempts = (int64_t)d.sums[13];
     c.n_active = c.n_remesh_A + c.n_remesh_B + c.n_remesh_C + c.n_remesh_D;
     c.reach = d.reach; c.max_attempts = d.max_attempts;
     float ms = 0.f;
@@ -744,6 +748,15 @@ int picles_get_particles(picles_t* h, double* z, double* t, double* dt, uint8_t*
     }
     CK(cudaStreamSynchronize(h->stream));
     if (status) for (int64_t l = 0; l < n; l++) status[l] = st8[(size_t)l];
+    return PICLES_OK;
+}
+
+int picles_get_solver_state(picles_t* h, int8_t* as) {
+    int rc = need_ready(h, false);
+    if (rc) return rc;
+    if (!as) return fail(h, PICLES_ERR_ARG, "null output");
+    CK(cudaMemcpyAsync(as, h->A.as, (size_t)h->A.Nx * h->A.ny, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return PICLES_OK;
 }
 
@@ -977,7 +990,7 @@ static_assert(sizeof(CkptHeader) == 64, "checkpoint header layout");
 
 static int64_t ckpt_bytes(const DeviceArrays& A) {
     const int64_t n = (int64_t)A.Nx * A.ny;
-    return (int64_t)sizeof(CkptHeader) + n * (8 * (5 + 3 + 3 + 2) + 4 + 1 + 1);
+    return (int64_t)sizeof(CkptHeader) + n * (8 * (5 + 3 + 3 + 2) + 4 + 1 + 1 + 1);
 }
 int picles_checkpoint_size(picles_t* h, int64_t* nbytes) {
     if (!h || !h->have_grid || !nbytes) return fail(h, PICLES_ERR_STATE, "grid not set");
@@ -999,6 +1012,7 @@ static int ckpt_planes(picles_t* h, void** ptr, size_t* bytes) {
     ptr[k] = A.iter; bytes[k++] = n * 4;
     ptr[k] = A.flags; bytes[k++] = n;
     ptr[k] = A.status; bytes[k++] = n;
+    ptr[k] = A.as; bytes[k++] = n;
     return k;
 }
 int picles_checkpoint_save(picles_t* h, void* blob, int64_t nbytes) {
@@ -1008,8 +1022,8 @@ int picles_checkpoint_save(picles_t* h, void* blob, int64_t nbytes) {
     const DeviceArrays& A = h->A;
     CkptHeader hd = {CKPT_MAGIC, PICLES_ABI_VERSION, A.Nx, A.ny, A.j0, A.Ny, A.bx, A.by, A.halo, ckpt_bytes(A), {0, 0}};
     memcpy(blob, &hd, sizeof hd);
-    void* ptr[16];
-    size_t bytes[16];
+    void* ptr[20];
+    size_t bytes[20];
     const int np = ckpt_planes(h, ptr, bytes);
     char* out = (char*)blob + sizeof hd;
     for (int k = 0; k < np; k++) {
@@ -1032,8 +1046,8 @@ int picles_checkpoint_load(picles_t* h, const void* blob, int64_t nbytes) {
         return fail(h, PICLES_ERR_ARG, "checkpoint is for a %dx%d strip at row %d of %d; this handle owns %dx%d at row %d of %d", hd.Nx,
                     hd.ny, hd.j0, hd.Ny, A.Nx, A.ny, A.j0, A.Ny);
     if (nbytes < hd.n_bytes || hd.n_bytes != ckpt_bytes(A)) return fail(h, PICLES_ERR_ARG, "truncated checkpoint");
-    void* ptr[16];
-    size_t bytes[16];
+    void* ptr[20];
+    size_t bytes[20];
     const int np = ckpt_planes(h, ptr, bytes);
     const char* in = (const char*)blob + sizeof hd;
     for (int k = 0; k < np; k++) {

@@ -54,6 +54,7 @@ struct DeviceArrays {
     double *t, *dt, *qold;
     int32_t* iter;
     uint8_t *flags, *status, *mask;
+    int8_t* as;                      /* AutoTsit5: AutoSwitch state per particle (run length, +64 = Rosenbrock23 current) */
     double *u_t, *v_t, *u_t1, *v_t1; /* staged winds at t and t+DT */
     double *u_mid[PICLES_WIND_MID_MAX], *v_mid[PICLES_WIND_MID_MAX]; /* intermediate levels (allocated on first use) */
     int n_mid;                       /* intermediate levels staged for the next advance (0: linear in time) */
@@ -67,8 +68,8 @@ struct DeviceArrays {
 };
 
 struct DeviceCounters {
-    /* integrated, substeps, rejects, rhs, reseed, fixups, failed, deposited, A, B, C, D */
-    unsigned long long sums[12];
+    /* integrated, substeps, rejects, rhs, reseed, fixups, failed, deposited, A, B, C, D, stiff switches, stiff attempts */
+    unsigned long long sums[14];
     int32_t reach;        /* max reach of this strip's own deposits */
     int32_t max_attempts;
     int32_t reach_halo;   /* max reach of the records received into the halo rows */

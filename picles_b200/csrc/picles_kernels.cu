@@ -21,7 +21,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
-#include "physics.h"
+#include "stiff.h"
 #include "picles_device.h"
 #include "pmath_trig.h"
 #include "wind_mesh.h"
@@ -42,7 +42,7 @@ __device__ __forceinline__ int32_t warp_max(int32_t v) {
     return v;
 }
 
-#define TALLY_NSUM 12
+#define TALLY_NSUM 14
 __device__ void tally_flush(const Tally& c, DeviceCounters* dc) {
     __shared__ int32_t s_sum[TALLY_NSUM];
     __shared__ int32_t s_max[2];
@@ -50,7 +50,7 @@ __device__ void tally_flush(const Tally& c, DeviceCounters* dc) {
     if (threadIdx.x < 2) s_max[threadIdx.x] = 0;
     __syncthreads();
     int32_t v[TALLY_NSUM] = {c.integrated, c.substeps, c.rejects, c.rhs, c.reseed, c.fixups,
-                             c.failed, c.deposited, c.A, c.B, c.C, c.D};
+                             c.failed, c.deposited, c.A, c.B, c.C, c.D, c.stiff_switches, c.stiff_attempts};
     int lane = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < TALLY_NSUM; k++) {
@@ -77,6 +77,13 @@ __device__ __forceinline__ void load_particle(const DeviceArrays& A, int64_t l, 
     p.iter = A.iter[l];
     p.flags = A.flags[l];
     p.status = A.status[l];
+    p.as = 0; /* the AutoSwitch plane is touched only under PICLES_SOLVER_AUTOTSIT5 (load_as / store_as) */
+}
+__device__ __forceinline__ void load_as(const DeviceArrays& A, const picles_params_t& P, int64_t l, Particle& p) {
+    if (P.solver == PICLES_SOLVER_AUTOTSIT5) p.as = A.as[l];
+}
+__device__ __forceinline__ void store_as(const DeviceArrays& A, const picles_params_t& P, int64_t l, const Particle& p) {
+    if (P.solver == PICLES_SOLVER_AUTOTSIT5) A.as[l] = p.as;
 }
 __device__ __forceinline__ void store_particle(const DeviceArrays& A, int64_t l, const Particle& p) {
     A.z[0][l] = p.u0; A.z[1][l] = p.u1; A.z[2][l] = p.u2; A.z[3][l] = p.u3; A.z[4][l] = p.u4;
@@ -106,6 +113,7 @@ __global__ void __launch_bounds__(256) k_seed(DeviceArrays A, picles_params_t P,
         double e, mx, my;
         seed_particle(P, A.mask[l], u0[l], v0[l], p, e, mx, my);
         store_particle(A, l, p);
+        A.as[l] = 0;
         A.S[0][l] = e; A.S[1][l] = mx; A.S[2][l] = my;
         Record r;
         r.e = r.mx = r.my = r.wxc = r.wyc = 0.0;
@@ -143,6 +151,7 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int6
         int64_t le = rec_index(A, l);
         Particle p;
         load_particle(A, l, p);
+        load_as(A, P, l, p);
         double M[4];
         if (PER_NODE_M) { M[0] = A.M[0][l]; M[1] = A.M[1][l]; M[2] = A.M[2][l]; M[3] = A.M[3][l]; }
         else { M[0] = A.Mc[0]; M[1] = A.Mc[1]; M[2] = A.Mc[2]; M[3] = A.Mc[3]; }
@@ -157,6 +166,7 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int6
         um[PH_WIND_SEG_MAX - 1] = 0.0; vm[PH_WIND_SEG_MAX - 1] = 0.0;
         advance_particle(P, p, A.mask[l], DT, A.u_t[l], A.v_t[l], A.u_t1[l], A.v_t1[l], A.n_mid, um, vm, M, pc, r, c, K);
         store_particle(A, l, p);
+        store_as(A, P, l, p);
         store_record(A, le, r);
         if (r.cell != PH_CELL_INVALID) {
             /* per-row reach (lets the gather size its window tile by tile) and class presence */
@@ -290,8 +300,10 @@ __device__ __noinline__ int4 cold_nodes(const DeviceArrays* Ap, const picles_par
         const double wu = A.u_t[l], wv = A.v_t[l];
         Particle p;
         load_particle(A, l, p);
+        load_as(A, P, l, p);
         remesh_particle(P, p, s0, s1, s2, wu, wv, DT, c);
         store_particle(A, l, p);
+        store_as(A, P, l, p);
     }
     return make_int4(c.A, c.B, c.C, c.D);
 }

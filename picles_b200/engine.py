@@ -247,6 +247,13 @@ class B200Engine:
         self._check(self.lib.picles_get_counters(self.h, C.byref(c)))
         return c.as_dict()
 
+    def solver_state(self):
+        """AutoSwitch state per particle (AutoTsit5): run length of the stiffness test, +64 while
+        Rosenbrock23 is the current algorithm"""
+        a = np.empty((self.ny, self.Nx), np.int8)
+        self._check(self.lib.picles_get_solver_state(self.h, _ptr(a)))
+        return a
+
     def set_accumulate(self, on: bool):
         """False: run! semantics (State zeroed before the step); True: bare time_step!."""
         self._check(self.lib.picles_set_option(self.h, 1, int(bool(on))))

@@ -78,7 +78,8 @@ def make_oracle(grid, P, variant="default", threads=1):
 
 def _build_shim():
     deps = [SHIM_SRC, os.path.join(ROOT, "picles_b200", "csrc", "physics.h"),
-            os.path.join(ROOT, "picles_b200", "csrc", "wind_mesh.h"),
+            os.path.join(ROOT, "picles_b200", "csrc", "wind_mesh.h"), os.path.join(ROOT, "picles_b200", "csrc", "stiff.h"),
+            os.path.join(ROOT, "picles_b200", "csrc", "pmath_dual.h"),
             os.path.join(ROOT, "picles_b200", "csrc", "pmath.h"), os.path.join(ROOT, "include", "picles_b200.h")]
     if os.path.exists(SHIM_SO) and all(os.path.getmtime(SHIM_SO) >= os.path.getmtime(d) for d in deps):
         return
@@ -112,6 +113,8 @@ def shim_lib():
         lib.shim_set_state.argtypes = [vp, vp]
         lib.shim_get_particles.argtypes = [vp] + [vp] * 7
         lib.shim_get_tally.argtypes = [vp, vp]
+        lib.shim_get_solver_state.argtypes = [vp, vp]
+        lib.shim_get_solver_state_local.argtypes = [vp, vp]
         lib.shim_corner_target.restype = i64
         lib.shim_corner_target.argtypes = [i32, i32, i32, i32, i64, i64]
         lib.shim_rhs.argtypes = [C.POINTER(PiclesParams), vp, d, d, vp, d, vp]
@@ -136,7 +139,8 @@ def _p(a):
 
 
 TALLY_NAMES = ["n_integrated", "n_substeps", "n_rejects", "n_rhs", "n_reseed_advance", "n_fixups", "n_failed",
-               "n_deposited", "n_remesh_A", "n_remesh_B", "n_remesh_C", "n_remesh_D", "reach", "max_attempts"]
+               "n_deposited", "n_remesh_A", "n_remesh_B", "n_remesh_C", "n_remesh_D", "reach", "max_attempts",
+               "n_stiff_switches", "n_stiff_attempts"]
 
 
 class HostShim:
@@ -202,9 +206,14 @@ class HostShim:
         return dict(z=z, t=t, dt=dt, qold=qold, iter=it, flags=fl, status=st)
 
     def counters(self):
-        out = np.empty(14, np.int32)
+        out = np.empty(16, np.int32)
         self.lib.shim_get_tally(self.h, _p(out))
         return dict(zip(TALLY_NAMES, [int(v) for v in out]))
+
+    def solver_state(self):
+        a = np.empty((self.Ny, self.Nx), np.int8)
+        self.lib.shim_get_solver_state(self.h, _p(a))
+        return a
 
 
 def bits_equal(a, b):
@@ -388,7 +397,7 @@ class ShimStripEngine:
         return dict(z=z, t=t, dt=dt, qold=qold, iter=it, flags=fl, status=st)
 
     def counters(self):
-        out = np.empty(14, np.int32)
+        out = np.empty(16, np.int32)
         self.lib.shim_get_tally(self.h, _p(out))
         return dict(zip(TALLY_NAMES, [int(v) for v in out]))
 

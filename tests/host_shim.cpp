@@ -12,7 +12,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../picles_b200/csrc/physics.h"
+#include "../picles_b200/csrc/stiff.h"
 #include "../picles_b200/csrc/wind_mesh.h"
 
 using namespace picles;
@@ -22,6 +22,7 @@ struct Strip {
     std::vector<double> z[5], t, dt, qold, ut, vt, ut1, vt1, rec[5], S[3], M[4], pc;
     std::vector<int32_t> iter, cell;
     std::vector<uint8_t> flags, status, mask;
+    std::vector<int8_t> as;
 };
 
 struct Shim {
@@ -40,10 +41,12 @@ struct Shim {
 static void load(const Strip& s, int64_t l, Particle& p) {
     p.u0 = s.z[0][l]; p.u1 = s.z[1][l]; p.u2 = s.z[2][l]; p.u3 = s.z[3][l]; p.u4 = s.z[4][l];
     p.t = s.t[l]; p.dt = s.dt[l]; p.qold = s.qold[l]; p.iter = s.iter[l]; p.flags = s.flags[l]; p.status = s.status[l];
+    p.as = s.as[l];
 }
 static void store(Strip& s, int64_t l, const Particle& p) {
     s.z[0][l] = p.u0; s.z[1][l] = p.u1; s.z[2][l] = p.u2; s.z[3][l] = p.u3; s.z[4][l] = p.u4;
     s.t[l] = p.t; s.dt[l] = p.dt; s.qold[l] = p.qold; s.iter[l] = p.iter; s.flags[l] = p.flags; s.status[l] = p.status;
+    s.as[l] = p.as;
 }
 static void tally_add(Tally& a, const Tally& b) {
     a.integrated += b.integrated; a.substeps += b.substeps; a.rejects += b.rejects; a.rhs += b.rhs;
@@ -51,6 +54,7 @@ static void tally_add(Tally& a, const Tally& b) {
     a.A += b.A; a.B += b.B; a.C += b.C; a.D += b.D;
     if (b.reach > a.reach) a.reach = b.reach;
     if (b.max_attempts > a.max_attempts) a.max_attempts = b.max_attempts;
+    a.stiff_switches += b.stiff_switches; a.stiff_attempts += b.stiff_attempts;
 }
 
 extern "C" {
@@ -76,7 +80,7 @@ Shim* shim_create(int Nx, int Ny, int bx, int by, int nstrips, int halo, const u
         s.ut.assign(n, 0.0); s.vt.assign(n, 0.0); s.ut1.assign(n, 0.0); s.vt1.assign(n, 0.0);
         for (int k = 0; k < 3; k++) s.S[k].assign(n, 0.0);
         s.iter.assign(n, 0); s.cell.assign(ne, PH_CELL_INVALID);
-        s.flags.assign(n, 0); s.status.assign(n, 0);
+        s.flags.assign(n, 0); s.status.assign(n, 0); s.as.assign(n, 0);
         s.mask.assign(mask + (int64_t)s.j0 * Nx, mask + (int64_t)s.j0 * Nx + n);
         if (M) for (int k = 0; k < 4; k++) s.M[k].assign(M + k * plane + (int64_t)s.j0 * Nx, M + k * plane + (int64_t)s.j0 * Nx + n);
         if (pc) s.pc.assign(pc + (int64_t)s.j0 * Nx, pc + (int64_t)s.j0 * Nx + n);
@@ -231,7 +235,7 @@ Shim* shim_create_strip(int Nx, int Ny, int bx, int by, int j0, int ny, int halo
     s.t.assign(n, 0.0); s.dt.assign(n, 0.0); s.qold.assign(n, 0.0);
     for (int k = 0; k < 3; k++) s.S[k].assign(n, 0.0);
     s.iter.assign(n, 0); s.cell.assign(ne, PH_CELL_INVALID);
-    s.flags.assign(n, 0); s.status.assign(n, 0);
+    s.flags.assign(n, 0); s.status.assign(n, 0); s.as.assign(n, 0);
     s.mask.assign(mask, mask + n);
     if (M) for (int k = 0; k < 4; k++) s.M[k].assign(M + k * n, M + (k + 1) * n);
     if (pc) s.pc.assign(pc, pc + n);
@@ -342,8 +346,13 @@ void shim_get_particles_local(const Shim* h, double* z, double* t, double* dt, d
     memcpy(flags, s.flags.data(), n);
     for (int64_t l = 0; l < n; l++) status[l] = s.status[l];
 }
-/* integrated, substeps, rejects, rhs, reseed, fixups, failed, deposited, A, B, C, D, reach, max_attempts */
-void shim_get_tally(const Shim* h, int32_t* out14) { memcpy(out14, &h->tally, 14 * sizeof(int32_t)); }
+/* integrated, substeps, rejects, rhs, reseed, fixups, failed, deposited, A, B, C, D, reach, max_attempts,
+   stiff_switches, stiff_attempts */
+void shim_get_tally(const Shim* h, int32_t* out16) { memcpy(out16, &h->tally, 16 * sizeof(int32_t)); }
+void shim_get_solver_state(const Shim* h, int8_t* as) {
+    for (auto& s : h->s) memcpy(as + (int64_t)s.j0 * h->Nx, s.as.data(), s.as.size());
+}
+void shim_get_solver_state_local(const Shim* h, int8_t* as) { memcpy(as, h->s[0].as.data(), h->s[0].as.size()); }
 
 int64_t shim_corner_target(int Nx, int Ny, int bx, int by, int64_t i, int64_t j) {
     int64_t ii, jj;

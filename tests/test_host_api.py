@@ -83,7 +83,8 @@ def test_params_flattening_matches_reference_defaults():
     assert P.log_energy_maximum == math.log(17) and P.wind_min_squared == 4.0
     assert list(P.minimal_state) == FetchRelations.MinimalState(2, 2, DT)
     assert P.minimal_state[0] == pytest.approx(1.253106339976604e-6, rel=1e-14)
-    assert P.has_defaults == 0 and P.periodic_boundary == 0 and P.solver == 0
+    assert P.has_defaults == 0 and P.periodic_boundary == 0
+    assert P.solver == 2                                      # ODESettings default: AutoTsit5(Rosenbrock23())
     assert P.dtmax == 6 * days
 
 
