@@ -71,9 +71,12 @@ def workload(nx, ny_per_gpu, n_gpus, rank):
     return dict(Nx=nx, Ny=Ny, j0=j0, ny=ny_per_gpu, mask=mask, M_const=np.array([1 / 2000.0, 0.0, 0.0, 1 / 2000.0]))
 
 
+SOLVER = "Tsit5"
+
+
 def params():
     from common import default_params
-    return default_params(DT=600.0)
+    return default_params(DT=600.0, solver=SOLVER)
 
 
 class ClockSampler:
@@ -199,7 +202,12 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--solver", default="Tsit5", choices=["Tsit5", "DP5", "AutoTsit5"],
+                    help="ODESettings.solver; AutoTsit5 = the reference's default AutoTsit5(Rosenbrock23()): the same "
+                         "arithmetic as Tsit5 on this workload (the stiffness monitor never fires) plus the monitor")
     args = ap.parse_args()
+    global SOLVER
+    SOLVER = args.solver
     if args.warmup < 3:
         log("warmup raised to 3 (timing rules)")
         args.warmup = 3
@@ -209,7 +217,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": f"homogeneous box {args.nx}x{args.ny * max(world, 1)} Cartesian (BASELINE configs[1]: "
                           f"T04_2D_reg_test_large_grid/bench06 scaled), dx=dy=2km, u=v=10 m/s, DT=600 s, "
-                          f"Tsit5 abstol=1e-4 reltol=1e-3 dt=1e-3 dtmin=1e-4 force_dtmin",
+                          f"{args.solver} abstol=1e-4 reltol=1e-3 dt=1e-3 dtmin=1e-4 force_dtmin",
               "nx": args.nx, "ny_per_gpu": args.ny, "parallelism": f"y-strips x{max(world, 1)}",
               "l2_policy": "inputs_exceed_l2 (3.3 GB of per-node planes per GPU >> 126 MB L2)"}
 

@@ -110,6 +110,7 @@ enum {
     KS_U3 = 21, KS_U4, KS_X7, KS_Y7, KS_XE, KS_YE, KS_TSTOP, KS_LQ, KS_QOLD, KS_DT0, KS_D1N, KS_DTMIN,
     KS_WT0, KS_WIDT,
     KS_X6, KS_Y6, /* AutoTsit5 monitor: propagation part of the argument of stage 6 */
+    KS_AS,        /* AutoTsit5: AutoSwitch run length (as a double; +PH_AS_STIFF once switched) */
     KS_WCU,                            /* Newton coefficients c_1..c_4 of the wind's u component in time */
     KS_WCV = KS_WCU + PH_WIND_SEG_MAX, /* ... and of v */
     KS_SLOTS = KS_WCV + PH_WIND_SEG_MAX
@@ -569,6 +570,65 @@ PM_HD_NOINLINE_DECL void step_control_cold(const picles_params_t& P, const Table
     step_control<OpsSafe>(P, T, dt, e0, e1, e2, xe, ye, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, lq, sc, (unsigned*)0);
 }
 
+/* time coefficients of the staged wind -> scratch slots (two levels: c1 = the increment), and the
+   loop invariants of the right-hand side; once per particle and model step */
+template <class KS>
+PM_HD void wind_to_slots(const picles_params_t& P, const Wind& w, KS& K, Hoist& H) {
+    double cu[PH_WIND_SEG_MAX + 1], cv[PH_WIND_SEG_MAX + 1];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int m = 0; m <= PH_WIND_SEG_MAX; m++) { cu[m] = w.ul[m]; cv[m] = w.vl[m]; }
+    wind_newton(cu, w.nseg);
+    wind_newton(cv, w.nseg);
+    bool steady = true;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int m = 1; m <= PH_WIND_SEG_MAX; m++) {
+        if (m <= w.nseg) {
+            K.st(KS_WCU + m - 1, cu[m]); K.st(KS_WCV + m - 1, cv[m]);
+            steady = steady && (cu[m] == 0.0) && (cv[m] == 0.0);
+        }
+    }
+    make_hoist(P, w.ul[0], w.vl[0], steady, w.nseg, H);
+    K.st(KS_WT0, w.t_start); K.st(KS_WIDT, (double)w.nseg * w.inv_DT);
+}
+
+/* Tsit5 inside a composite algorithm: eigen_est = max_i |k7_i - k6_i| / |g7_i - g6_i| (Hairer II,
+   p. 22).  g7 = u_new (n), g6 = u + dt * sum_j a6j k_j rebuilt from the stored stage derivatives and
+   the running sums X6, Y6.  Once per attempt, AutoTsit5 only. */
+template <class O, class KS>
+PM_HD double stiffness_estimate(const picles_params_t& P, const Tableau& T, const double* M, const KS& K, double dt,
+                                double u0, double u1, double u2, double u3, double u4, double n0, double n1, double n2,
+                                double n3, double n4, unsigned* bad) {
+    double a1 = T.a[6][1];
+    double i0 = a1 * K.get(1, 0), i1 = a1 * K.get(1, 1), i2 = a1 * K.get(1, 2);
+    for (int j = 2; j < 6; j++) {
+        double aj = T.a[6][j];
+        if (aj != 0.0) { i0 = fma(aj, K.get(j, 0), i0); i1 = fma(aj, K.get(j, 1), i1); i2 = fma(aj, K.get(j, 2), i2); }
+    }
+    const double g60 = fma(dt, i0, u0), g61 = fma(dt, i1, u1), g62 = fma(dt, i2, u2);
+    const double g63 = fma(dt, K.ld(KS_X6), u3), g64 = fma(dt, K.ld(KS_Y6), u4);
+    double k6x, k6y, k7x, k7y;
+    prop(P, M, g61, g62, k6x, k6y);
+    prop(P, M, n1, n2, k7x, k7y);
+    double eig = 0.0;
+    eig = pm_max(eig, fabs(O::divz(K.get(7, 0) - K.get(6, 0), n0 - g60, bad)));
+    eig = pm_max(eig, fabs(O::divz(K.get(7, 1) - K.get(6, 1), n1 - g61, bad)));
+    eig = pm_max(eig, fabs(O::divz(K.get(7, 2) - K.get(6, 2), n2 - g62, bad)));
+    eig = pm_max(eig, fabs(O::divz(k7x - k6x, n3 - g63, bad)));
+    eig = pm_max(eig, fabs(O::divz(k7y - k6y, n4 - g64, bad)));
+    return eig;
+}
+template <class KS>
+PM_HD_NOINLINE_DECL double stiffness_estimate_cold(const picles_params_t* Pp, const Tableau* Tp, double m0, double m1, double m2,
+                                                   double m3, KS K, double dt, double u0, double u1, double u2, double u3,
+                                                   double u4, double n0, double n1, double n2, double n3, double n4) {
+    const double M[4] = {m0, m1, m2, m3};
+    return stiffness_estimate<OpsSafe>(*Pp, *Tp, M, K, dt, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, (unsigned*)0);
+}
+
 /* ---- step!(integrator, DT, true): advance particle p from p.t to p.t + DT ------------ */
 /*
  * Every right-hand side of the integration — the FSAL reset k1 = f(u,t), the second
@@ -584,46 +644,23 @@ PM_HD_NOINLINE_DECL void step_control_cold(const picles_params_t& P, const Table
  * estimate (xe,ye) as each k_j appears — the same fma chain as storing them.
  */
 /*
- * AutoTsit5 (P.solver == PICLES_SOLVER_AUTOTSIT5): every attempt also leaves OrdinaryDiffEq's
- * stiffness estimate eigen_est = max_i |k7_i - k6_i| / |g7_i - g6_i| (Hairer II, p. 22; g6, g7 the
- * arguments of stages 6 and 7) and the AutoSwitch run length as_count is updated with
- * |eigen_est * dt / 3.5068| > 9/10; more than ten stiff attempts in a row hand the particle to
- * Rosenbrock23 (stiff.h, out of line).  Return value: 0 = step complete or integrator stopped;
- * 1 = Rosenbrock23 is the current algorithm at the start of the step (k1 = f(u, t) is in K);
- * 2 = AutoSwitch switched just now (dt doubled).  tstop = p.t + DT of the first entry; attempts
- * accumulates over re-entries.
+ * AutoTsit5 (P.solver == PICLES_SOLVER_AUTOTSIT5, AUTOSW instantiation): every attempt also leaves
+ * OrdinaryDiffEq's stiffness estimate and the AutoSwitch run length (kept in a scratch slot) is
+ * updated with |eigen_est * dt / 3.5068| > 9/10; more than ten stiff attempts in a row hand the
+ * particle to Rosenbrock23 (stiff.h, out of line): the loop is left with dt doubled and `true` is
+ * returned.  A particle whose current algorithm is Rosenbrock23 at the start of a step never
+ * enters here (advance_particle).  tstop = p.t + DT of the first entry; attempts accumulates over
+ * re-entries.
  */
-template <class KS>
-PM_HD int integrate(const picles_params_t& P, const Wind& w, const double* M, double pc, double tstop_in, Particle& p,
-                    Tally& c, KS& K, int& as_count, bool& as_stiff, int& attempts_io) {
-    if (p.status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE)) return 0;
-    const bool autosw = (P.solver == PICLES_SOLVER_AUTOTSIT5);
-    int ret = 0;
+template <bool AUTOSW, class KS>
+PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv0, const Hoist& H, const double* M, double pc,
+                     double tstop_in, Particle& p, Tally& c, KS& K, int& as_count, int& attempts_io) {
+    if (p.status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE)) return false;
+    /* compile-time switch: the kernels are instantiated with and without the monitor, so the
+       Tsit5 / DP5 loop carries none of it */
+    const bool autosw = AUTOSW && (P.solver == PICLES_SOLVER_AUTOTSIT5);
+    bool switched = false;
     const Tableau& T = tableau(P.solver);
-    Hoist H;
-    const double wu0 = w.ul[0], wv0 = w.vl[0];
-    {
-        /* time coefficients of the staged wind -> scratch slots (two levels: c1 = the increment) */
-        double cu[PH_WIND_SEG_MAX + 1], cv[PH_WIND_SEG_MAX + 1];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int m = 0; m <= PH_WIND_SEG_MAX; m++) { cu[m] = w.ul[m]; cv[m] = w.vl[m]; }
-        wind_newton(cu, w.nseg);
-        wind_newton(cv, w.nseg);
-        bool steady = true;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int m = 1; m <= PH_WIND_SEG_MAX; m++) {
-            if (m <= w.nseg) {
-                K.st(KS_WCU + m - 1, cu[m]); K.st(KS_WCV + m - 1, cv[m]);
-                steady = steady && (cu[m] == 0.0) && (cv[m] == 0.0);
-            }
-        }
-        make_hoist(P, wu0, wv0, steady, w.nseg, H);
-    }
-    K.st(KS_WT0, w.t_start); K.st(KS_WIDT, (double)w.nseg * w.inv_DT);
     double t = p.t;
     K.st(KS_TSTOP, tstop_in);
     double u0 = p.u0, u1 = p.u1, u2 = p.u2;
@@ -635,7 +672,8 @@ PM_HD int integrate(const picles_params_t& P, const Wind& w, const double* M, do
     int32_t iter = p.iter;
     int32_t nrhs = 0, attempts = attempts_io;
     const double qmin = 0.2, gamma = 0.9;
-    const double order = (autosw && as_stiff) ? 2.0 : 5.0;
+    const double order = 5.0; /* get_current_alg_order of Tsit5 / DP5 */
+    if (autosw) K.st(KS_AS, (double)as_count);
     bool need_reset = (p.flags & PICLES_PF_DT_RESET) != 0;
     p.flags &= (uint8_t)~PICLES_PF_DT_RESET;
 
@@ -701,23 +739,13 @@ PM_HD int integrate(const picles_params_t& P, const Wind& w, const double* M, do
             double EEst = sc.EEst;
             double eig = 0.0;
             if (autosw) {
-                /* g6 = u + dt * sum_j a6j k_j, rebuilt from the stored stage derivatives */
-                double a1 = T.a[6][1];
-                double i0 = a1 * K.get(1, 0), i1 = a1 * K.get(1, 1), i2 = a1 * K.get(1, 2);
-                for (int j = 2; j < 6; j++) {
-                    double aj = T.a[6][j];
-                    if (aj != 0.0) { i0 = fma(aj, K.get(j, 0), i0); i1 = fma(aj, K.get(j, 1), i1); i2 = fma(aj, K.get(j, 2), i2); }
-                }
-                const double g60 = fma(dt, i0, u0), g61 = fma(dt, i1, u1), g62 = fma(dt, i2, u2);
-                const double g63 = fma(dt, K.ld(KS_X6), u3), g64 = fma(dt, K.ld(KS_Y6), u4);
-                double k6x, k6y, k7x, k7y;
-                prop(P, M, g61, g62, k6x, k6y);
-                prop(P, M, n1, n2, k7x, k7y);
-                eig = pm_max(eig, fabs((K.get(7, 0) - K.get(6, 0)) / (n0 - g60)));
-                eig = pm_max(eig, fabs((K.get(7, 1) - K.get(6, 1)) / (n1 - g61)));
-                eig = pm_max(eig, fabs((K.get(7, 2) - K.get(6, 2)) / (n2 - g62)));
-                eig = pm_max(eig, fabs((k7x - k6x) / (n3 - g63)));
-                eig = pm_max(eig, fabs((k7y - k6y) / (n4 - g64)));
+#if defined(__CUDA_ARCH__)
+                unsigned bad = 0;
+                eig = stiffness_estimate<OpsFast>(P, T, M, K, dt, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, &bad);
+                if (bad) eig = stiffness_estimate_cold(&P, &T, M[0], M[1], M[2], M[3], K, dt, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4);
+#else
+                eig = stiffness_estimate_cold(&P, &T, M[0], M[1], M[2], M[3], K, dt, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4);
+#endif
             }
             bool accept = (EEst <= 1.0) || (P.force_dtmin && fabs(dt) <= K.ld(KS_DTMIN));
             if (accept) {
@@ -748,15 +776,14 @@ PM_HD int integrate(const picles_params_t& P, const Wind& w, const double* M, do
             if (autosw) {
                 /* AutoSwitch: maxstiffstep 10, nonstifftol 9//10, dtfac 2, stability_size(Tsit5) 3.5068 */
                 const bool is = fabs(eig * dt / 3.5068) > 0.9;
-                int cnt = as_count;
+                int cnt = (int)K.ld(KS_AS);
                 cnt = is ? ((cnt < 0) ? 1 : cnt + 1) : ((cnt > 0) ? -1 : cnt - 1);
                 cnt = (cnt > PH_AS_CLAMP) ? PH_AS_CLAMP : ((cnt < -PH_AS_CLAMP) ? -PH_AS_CLAMP : cnt);
-                as_count = cnt;
+                K.st(KS_AS, (double)cnt);
                 if (cnt > 10) {
                     dt = dt * 2.0;
-                    as_stiff = true;
                     c.stiff_switches++;
-                    ret = 2;
+                    switched = true;
                     break;
                 }
             }
@@ -802,7 +829,6 @@ PM_HD int integrate(const picles_params_t& P, const Wind& w, const double* M, do
         /* ---- header of the next attempt: loopheader!, check_error! ---- */
         const double tstop = K.ld(KS_TSTOP);
         if (!(t < tstop)) break;
-        if (autosw && as_stiff) { ret = 1; break; } /* Rosenbrock23 is current: its attempts run out of line */
         iter++;
         const double dtmin_t = pm_max(pm_eps(t), P.dtmin);
         K.st(KS_DTMIN, dtmin_t);
@@ -829,7 +855,8 @@ PM_HD int integrate(const picles_params_t& P, const Wind& w, const double* M, do
     p.t = t; p.dt = dt; p.qold = K.ld(KS_QOLD); p.iter = iter;
     c.rhs += nrhs;
     attempts_io = attempts;
-    return ret;
+    if (autosw) as_count = (int)K.ld(KS_AS);
+    return switched;
 }
 
 /* ---- ParticleInCell ------------------------------------------------------- */
@@ -1092,61 +1119,25 @@ PM_HD void gather_node(const RecView& V, int I, int J, int R, int n_classes, dou
     }
 }
 
-/* the Rosenbrock23 attempts of a particle AutoSwitch has declared stiff (stiff.h, out of line);
-   true: handed back to Tsit5 with time left in the step */
-PM_HD_NOINLINE_DECL bool stiff_phase(const picles_params_t* Pp, const Wind* w, const double* M, double pc, double tstop,
-                                     Particle* p, int* as_count, bool* as_stiff, int* attempts, bool have_f0, double f00,
-                                     double f01, double f02, Tally* c);
-
-/* ---- advance! (everything except the scatter, which the gather replaces) ----- */
-/* um/vm: the nmid intermediate wind levels at t + k*DT/(nmid+1), k = 1..nmid (nmid = 0: none) */
-template <class KS>
-PM_HD void advance_particle(const picles_params_t& P, Particle& p, int mask, double DT, double wu0, double wv0,
-                            double wu1, double wv1, int nmid, const double* um, const double* vm, const double* M,
-                            double pc, Record& rec, Tally& c, KS& K) {
-    double t_start = p.t;
-    bool on = (p.flags & PICLES_PF_ON) != 0;
-    if (on) {
-        Wind w;
-        w.nseg = nmid + 1;
-        w.ul[0] = wu0; w.vl[0] = wv0;
+/* levels 0..nseg of one particle's staged wind: t, the intermediate ones, t+DT */
+PM_HD void make_wind(Wind& w, int nmid, double wu0, double wv0, double wu1, double wv1, const double* um, const double* vm,
+                     double t_start, double DT) {
+    w.nseg = nmid + 1;
+    w.ul[0] = wu0; w.vl[0] = wv0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int k = 1; k <= PH_WIND_SEG_MAX; k++) { /* levels 1..nseg: the intermediate ones, then t+DT */
-            w.ul[k] = (k <= nmid) ? um[k - 1] : ((k == nmid + 1) ? wu1 : 0.0);
-            w.vl[k] = (k <= nmid) ? vm[k - 1] : ((k == nmid + 1) ? wv1 : 0.0);
-        }
-        w.t_start = t_start; w.inv_DT = 1.0 / DT;
-        if (!(p.status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE))) {
-            const bool autosw = (P.solver == PICLES_SOLVER_AUTOTSIT5);
-            const double tstop = t_start + DT;
-            int attempts = 0;
-            int as_count = 0;
-            bool as_stiff = false;
-            if (autosw) {
-                as_stiff = p.as > PH_AS_CLAMP;
-                as_count = as_stiff ? (int)p.as - PH_AS_STIFF : (int)p.as;
-            }
-            for (;;) { /* one pass unless AutoSwitch moves the particle between Tsit5 and Rosenbrock23 */
-                const int code = integrate(P, w, M, pc, tstop, p, c, K, as_count, as_stiff, attempts);
-                if (code == 0) break;
-                if (!stiff_phase(&P, &w, M, pc, tstop, &p, &as_count, &as_stiff, &attempts, code == 1, K.get(1, 0),
-                                 K.get(1, 1), K.get(1, 2), &c))
-                    break;
-            }
-            if (autosw) p.as = (int8_t)(as_count + (as_stiff ? PH_AS_STIFF : 0));
-            c.integrated++;
-            if (attempts > c.max_attempts) c.max_attempts = attempts;
-        }
-    } else {
-        if (wu1 * wu1 + wv1 * wv1 >= P.wind_min_squared) {
-            reset_particle_values(P, wu1, wv1, DT, p);
-            p.flags |= PICLES_PF_DT_RESET;
-            on = true;
-            c.reseed++;
-        }
+    for (int k = 1; k <= PH_WIND_SEG_MAX; k++) {
+        w.ul[k] = (k <= nmid) ? um[k - 1] : ((k == nmid + 1) ? wu1 : 0.0);
+        w.vl[k] = (k <= nmid) ? vm[k - 1] : ((k == nmid + 1) ? wv1 : 0.0);
     }
+    w.t_start = t_start; w.inv_DT = 1.0 / DT;
+}
+
+/* tail of advance!: NaN / Inf / e_max fix-ups (mapping_2D.jl:196-235) and the deposit record that
+   replaces ParticleToNode! */
+PM_HD void advance_finish(const picles_params_t& P, Particle& p, bool on, int mask, double DT, double wu0, double wv0,
+                          double wu1, double wv1, Record& rec, Tally& c) {
     bool anynan = (p.u0 != p.u0) | (p.u1 != p.u1) | (p.u2 != p.u2);
     bool anyinf = pm_isinf(p.u0) | pm_isinf(p.u1) | pm_isinf(p.u2);
     if (anynan) {
@@ -1181,6 +1172,132 @@ PM_HD void advance_particle(const picles_params_t& P, Particle& p, int mask, dou
             c.deposited++;
         }
     }
+}
+
+/*
+ * advance! of one particle.  um/vm: the nmid intermediate wind levels at t + k*DT/(nmid+1),
+ * k = 1..nmid (nmid = 0: none).  Returns true only in the AUTOSW instantiation, when AutoSwitch
+ * needs Rosenbrock23 for this particle (it is the current algorithm at the start of the step, or
+ * the monitor switched just now): p then holds the state reached so far (t < t_start + DT),
+ * attempts_out the attempts made, nothing else has been done, and the caller finishes the step
+ * with advance_resume() — out of line, so the hot loop here shares no registers with the cold code.
+ */
+template <bool AUTOSW, class KS>
+PM_HD bool advance_particle(const picles_params_t& P, Particle& p, int mask, double DT, double wu0, double wv0,
+                            double wu1, double wv1, int nmid, const double* um, const double* vm, const double* M,
+                            double pc, Record& rec, Tally& c, KS& K, int& attempts_out) {
+    double t_start = p.t;
+    bool on = (p.flags & PICLES_PF_ON) != 0;
+    if (on) {
+        if (!(p.status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE))) {
+            const bool autosw = AUTOSW && (P.solver == PICLES_SOLVER_AUTOTSIT5);
+            const double tstop = t_start + DT;
+            int attempts = 0;
+            int as_count = 0;
+            if (autosw) {
+                if (p.as > PH_AS_CLAMP) { attempts_out = 0; return true; } /* Rosenbrock23 is current */
+                as_count = (int)p.as;
+            }
+            Hoist H;
+            {
+                Wind w;
+                make_wind(w, nmid, wu0, wv0, wu1, wv1, um, vm, t_start, DT);
+                wind_to_slots(P, w, K, H);
+            }
+            const bool switched = integrate<AUTOSW>(P, wu0, wv0, H, M, pc, tstop, p, c, K, as_count, attempts);
+            if (autosw) {
+                p.as = (int8_t)(as_count + (switched ? PH_AS_STIFF : 0));
+                if (switched && (p.t < tstop)) { attempts_out = attempts; return true; }
+            }
+            c.integrated++;
+            if (attempts > c.max_attempts) c.max_attempts = attempts;
+        }
+    } else {
+        if (wu1 * wu1 + wv1 * wv1 >= P.wind_min_squared) {
+            reset_particle_values(P, wu1, wv1, DT, p);
+            p.flags |= PICLES_PF_DT_RESET;
+            on = true;
+            c.reseed++;
+        }
+    }
+    advance_finish(P, p, on, mask, DT, wu0, wv0, wu1, wv1, rec, c);
+    return false;
+}
+
+/* the Rosenbrock23 attempts of a particle AutoSwitch has declared stiff (stiff.h, out of line).
+   Everything the cold code touches travels in one struct.  true: handed back to Tsit5 with time
+   left in the step */
+struct WindPoly {
+    int nseg;
+    double cu[PH_WIND_SEG_MAX + 1], cv[PH_WIND_SEG_MAX + 1]; /* c[0] = the level at t_start */
+    double t0, scale;                                         /* sigma = (ts - t0) * scale */
+};
+struct StiffArgs {
+    WindPoly W;
+    double M[4];
+    Particle p;
+    int as_count, as_stiff, attempts;
+    Tally c;
+};
+PM_HD_NOINLINE_DECL bool stiff_phase(const picles_params_t* Pp, StiffArgs* a, double pc, double tstop);
+
+/* wind levels and projection kernel of one particle, by value (cold call) */
+struct ResumeArgs {
+    int mask, nmid, attempts;
+    double DT, t_start, wu0, wv0, wu1, wv1, um[PH_WIND_SEG_MAX], vm[PH_WIND_SEG_MAX], M[4], pc;
+};
+/*
+ * The rest of advance! for a particle advance_particle<true> handed over: alternate between
+ * Rosenbrock23 (stiff_phase) and Tsit5 (a second, cold copy of the integration loop) until the step
+ * is complete, then the common tail.  tally: a zeroed Tally of the caller, merged afterwards.
+ */
+template <class KS>
+PM_HD_NOINLINE_DECL void advance_resume(const picles_params_t* Pp, const ResumeArgs* Rp, Particle* pp, Record* rec, Tally* cp, KS K) {
+    const picles_params_t& P = *Pp;
+    const ResumeArgs& R = *Rp;
+    Particle& p = *pp;
+    Tally& c = *cp;
+    const double tstop = R.t_start + R.DT;
+    Hoist H;
+    {
+        Wind w;
+        make_wind(w, R.nmid, R.wu0, R.wv0, R.wu1, R.wv1, R.um, R.vm, R.t_start, R.DT);
+        wind_to_slots(P, w, K, H);
+    }
+    int attempts = R.attempts;
+    bool as_stiff = p.as > PH_AS_CLAMP;
+    int as_count = as_stiff ? (int)p.as - PH_AS_STIFF : (int)p.as;
+    bool stiff_now = as_stiff;
+    for (;;) {
+        if (stiff_now) {
+            StiffArgs a; /* the wind polynomial back from the scratch slots */
+            a.W.nseg = H.nseg;
+            a.W.cu[0] = R.wu0; a.W.cv[0] = R.wv0;
+            for (int m = 1; m <= PH_WIND_SEG_MAX; m++) {
+                a.W.cu[m] = (m <= H.nseg) ? K.ld(KS_WCU + m - 1) : 0.0;
+                a.W.cv[m] = (m <= H.nseg) ? K.ld(KS_WCV + m - 1) : 0.0;
+            }
+            a.W.t0 = K.ld(KS_WT0); a.W.scale = K.ld(KS_WIDT);
+            a.M[0] = R.M[0]; a.M[1] = R.M[1]; a.M[2] = R.M[2]; a.M[3] = R.M[3];
+            a.p = p;
+            a.as_count = as_count; a.as_stiff = 1; a.attempts = attempts;
+            tally_zero(a.c);
+            const bool back = stiff_phase(Pp, &a, R.pc, tstop);
+            p = a.p;
+            as_count = a.as_count; as_stiff = a.as_stiff != 0; attempts = a.attempts;
+            c.substeps += a.c.substeps; c.rejects += a.c.rejects; c.rhs += a.c.rhs; c.failed += a.c.failed;
+            c.stiff_attempts += a.c.stiff_attempts;
+            if (!back) break;
+        }
+        stiff_now = integrate<true>(P, R.wu0, R.wv0, H, R.M, R.pc, tstop, p, c, K, as_count, attempts);
+        if (!stiff_now) break;
+        as_stiff = true;
+        if (!(p.t < tstop)) break; /* switched on the last attempt of the step */
+    }
+    p.as = (int8_t)(as_count + (as_stiff ? PH_AS_STIFF : 0));
+    c.integrated++;
+    if (attempts > c.max_attempts) c.max_attempts = attempts;
+    advance_finish(P, p, true, R.mask, R.DT, R.wu0, R.wv0, R.wu1, R.wv1, *rec, c);
 }
 
 /* ---- remesh! / NodeToParticle! ---------------------------------------------- */

@@ -43,6 +43,13 @@ __device__ __forceinline__ int32_t warp_max(int32_t v) {
 }
 
 #define TALLY_NSUM 14
+__device__ __forceinline__ void tally_merge(Tally& a, const Tally& b) {
+    a.integrated += b.integrated; a.substeps += b.substeps; a.rejects += b.rejects; a.rhs += b.rhs;
+    a.reseed += b.reseed; a.fixups += b.fixups; a.failed += b.failed; a.deposited += b.deposited;
+    a.A += b.A; a.B += b.B; a.C += b.C; a.D += b.D;
+    a.reach = max(a.reach, b.reach); a.max_attempts = max(a.max_attempts, b.max_attempts);
+    a.stiff_switches += b.stiff_switches; a.stiff_attempts += b.stiff_attempts;
+}
 __device__ void tally_flush(const Tally& c, DeviceCounters* dc) {
     __shared__ int32_t s_sum[TALLY_NSUM];
     __shared__ int32_t s_max[2];
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(256) k_seed(DeviceArrays A, picles_params_t P,
 #else
 #define ADV_BOUNDS __launch_bounds__(ADV_THREADS, ADV_MIN_BLOCKS)
 #endif
-template <bool PER_NODE_M>
+template <bool PER_NODE_M, bool AUTOSW>
 __global__ void ADV_BOUNDS
 k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int64_t l_begin, int64_t l_end) {
     /* stage derivatives k_j[0:3], j = 1..7: 21 doubles per thread, one column per thread
@@ -151,7 +158,7 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int6
         int64_t le = rec_index(A, l);
         Particle p;
         load_particle(A, l, p);
-        load_as(A, P, l, p);
+        if (AUTOSW) load_as(A, P, l, p);
         double M[4];
         if (PER_NODE_M) { M[0] = A.M[0][l]; M[1] = A.M[1][l]; M[2] = A.M[2][l]; M[3] = A.M[3][l]; }
         else { M[0] = A.Mc[0]; M[1] = A.Mc[1]; M[2] = A.Mc[2]; M[3] = A.Mc[3]; }
@@ -164,9 +171,27 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int6
             else { um[k] = 0.0; vm[k] = 0.0; }
         }
         um[PH_WIND_SEG_MAX - 1] = 0.0; vm[PH_WIND_SEG_MAX - 1] = 0.0;
-        advance_particle(P, p, A.mask[l], DT, A.u_t[l], A.v_t[l], A.u_t1[l], A.v_t1[l], A.n_mid, um, vm, M, pc, r, c, K);
+        const double t_start = p.t;
+        int attempts = 0;
+        const bool pending = advance_particle<AUTOSW>(P, p, A.mask[l], DT, A.u_t[l], A.v_t[l], A.u_t1[l], A.v_t1[l], A.n_mid, um,
+                                                      vm, M, pc, r, c, K, attempts);
+        if (AUTOSW && pending) {
+            /* AutoSwitch handed the particle to Rosenbrock23: the rest of its step runs out of line */
+            ResumeArgs R;
+            R.mask = A.mask[l]; R.nmid = A.n_mid; R.attempts = attempts;
+            R.DT = DT; R.t_start = t_start;
+            R.wu0 = A.u_t[l]; R.wv0 = A.v_t[l]; R.wu1 = A.u_t1[l]; R.wv1 = A.v_t1[l];
+#pragma unroll
+            for (int k = 0; k < PH_WIND_SEG_MAX; k++) { R.um[k] = um[k]; R.vm[k] = vm[k]; }
+            R.M[0] = M[0]; R.M[1] = M[1]; R.M[2] = M[2]; R.M[3] = M[3];
+            R.pc = pc;
+            Tally c2;
+            tally_zero(c2);
+            advance_resume(&P, &R, &p, &r, &c2, K);
+            tally_merge(c, c2);
+        }
         store_particle(A, l, p);
-        store_as(A, P, l, p);
+        if (AUTOSW) store_as(A, P, l, p);
         store_record(A, le, r);
         if (r.cell != PH_CELL_INVALID) {
             /* per-row reach (lets the gather size its window tile by tile) and class presence */
@@ -676,13 +701,19 @@ void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, 
     if (dyn_env < 0) {
         const char* e = getenv("PICLES_ADV_DYN_SMEM");
         dyn_env = e ? atoi(e) : 0;
-        cudaFuncSetAttribute(k_advance<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_env);
-        cudaFuncSetAttribute(k_advance<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_env);
+        cudaFuncSetAttribute(k_advance<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_env);
+        cudaFuncSetAttribute(k_advance<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_env);
     }
     dyn = (size_t)dyn_env;
 #endif
-    if (pn) k_advance<true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
-    else k_advance<false><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+    /* AutoTsit5 runs the instantiation that carries the stiffness monitor and the Rosenbrock23 branch */
+    if (P.solver == PICLES_SOLVER_AUTOTSIT5) {
+        if (pn) k_advance<true, true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+        else k_advance<false, true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+    } else {
+        if (pn) k_advance<true, false><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+        else k_advance<false, false><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+    }
 }
 
 int project_remesh_smem_bytes() { return (int)sizeof(PRTile) + 128; }

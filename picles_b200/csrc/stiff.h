@@ -23,13 +23,6 @@
 
 namespace picles {
 
-/* the staged wind of one particle as a polynomial in time (physics.h: wind_newton) */
-struct WindPoly {
-    int nseg;
-    double cu[PH_WIND_SEG_MAX + 1], cv[PH_WIND_SEG_MAX + 1]; /* c[0] = the level at t_start */
-    double t0, scale;                                         /* sigma = (ts - t0) * scale */
-};
-
 PM_HD_NOINLINE_DECL void wind_poly_eval(const WindPoly* W, double ts, double* u, double* v, double* ut, double* vt) {
     double sg = (ts - W->t0) * W->scale;
     double pu = W->cu[W->nseg], pv = W->cv[W->nseg], du = 0.0, dv = 0.0;
@@ -207,12 +200,13 @@ PM_HD_NOINLINE_DECL void rosenbrock23_attempt(const picles_params_t* Pp, const W
 /*
  * The attempts of one particle while Rosenbrock23 is the current algorithm: from p.t towards
  * tstop, until the step is complete, the integrator stops (status bits), or AutoSwitch hands the
- * particle back to Tsit5 (as_stiff cleared).  have_f0: f0[0:3] = f(u, t) was already evaluated by
- * the caller (start of a model step); otherwise initialize! evaluates it here.
+ * particle back to Tsit5 (as_stiff cleared).  Entry evaluates f0 = f(u, t) — reset_fsal! at the
+ * start of a model step, initialize! of the Rosenbrock23 cache after a switch — and, when an
+ * auto_dt_reset! is pending, the initial-step heuristic with the order of Rosenbrock23 (2).
  */
 PM_HD_NOINLINE_DECL void stiff_integrate(const picles_params_t* Pp, const WindPoly* W, const double* M, double pc,
                                          double tstop, Particle* pp, int* as_count, int* as_stiff, int* attempts_io,
-                                         bool have_f0, double f00, double f01, double f02, Tally* cp) {
+                                         Tally* cp) {
     const picles_params_t& P = *Pp;
     Particle& p = *pp;
     Tally& c = *cp;
@@ -223,12 +217,21 @@ PM_HD_NOINLINE_DECL void stiff_integrate(const picles_params_t* Pp, const WindPo
     int cnt = *as_count;
     bool stiff = true;
     double f0[5];
-    if (have_f0) {
-        f0[0] = f00; f0[1] = f01; f0[2] = f02;
-        prop(P, M, u[1], u[2], f0[3], f0[4]);
-    } else {
-        f5_cold(Pp, W, M, pc, u, t, f0);
-        nrhs++;
+    f5_cold(Pp, W, M, pc, u, t, f0);
+    nrhs++;
+    if (p.flags & PICLES_PF_DT_RESET) { /* ode_determine_initdt with get_current_alg_order = 2 */
+        p.flags &= (uint8_t)~PICLES_PF_DT_RESET;
+        double dtr, dt0, d1n;
+        if (initdt_a_cold(P, u[0], u[1], u[2], u[3], u[4], f0[0], f0[1], f0[2], f0[3], f0[4], dtr, dt0, d1n)) {
+            dt = dtr;
+        } else {
+            double u1[5], f1[5];
+            for (int i = 0; i < 5; i++) u1[i] = fma(dt0, f0[i], u[i]);
+            f5_cold(Pp, W, M, pc, u1, t + dt0, f1);
+            nrhs++;
+            dt = initdt_b_cold(P, u[0], u[1], u[2], u[3], u[4], f0[0], f0[1], f0[2], f0[3], f0[4], f1[0], f1[1], f1[2], f1[3],
+                               f1[4], dt0, d1n, 2.0);
+        }
     }
     const double qmin = 0.2, qmax = 10.0, gamma = 0.9;
     const double beta1 = 0.35, beta2 = 0.2;
@@ -291,21 +294,11 @@ PM_HD_NOINLINE_DECL void stiff_integrate(const picles_params_t* Pp, const WindPo
     *attempts_io = attempts;
 }
 
-/* declared in physics.h: builds the wind polynomial of the particle and runs the stiff attempts */
-PM_HD_NOINLINE_DECL bool stiff_phase(const picles_params_t* Pp, const Wind* w, const double* M, double pc, double tstop,
-                                     Particle* p, int* as_count, bool* as_stiff, int* attempts, bool have_f0, double f00,
-                                     double f01, double f02, Tally* c) {
-    WindPoly W;
-    W.nseg = w->nseg;
-    for (int m = 0; m <= PH_WIND_SEG_MAX; m++) { W.cu[m] = w->ul[m]; W.cv[m] = w->vl[m]; }
-    wind_newton(W.cu, W.nseg);
-    wind_newton(W.cv, W.nseg);
-    W.t0 = w->t_start;
-    W.scale = (double)w->nseg * w->inv_DT;
-    int stiff = 1;
-    stiff_integrate(Pp, &W, M, pc, tstop, p, as_count, &stiff, attempts, have_f0, f00, f01, f02, c);
-    *as_stiff = (stiff != 0);
-    return !stiff && (p->t < tstop) && !(p->status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE));
+/* declared in physics.h */
+PM_HD_NOINLINE_DECL bool stiff_phase(const picles_params_t* Pp, StiffArgs* a, double pc, double tstop) {
+    stiff_integrate(Pp, &a->W, a->M, pc, tstop, &a->p, &a->as_count, &a->as_stiff, &a->attempts, &a->c);
+    return !a->as_stiff && (a->p.t < tstop) &&
+           !(a->p.status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE));
 }
 
 } /* namespace picles */

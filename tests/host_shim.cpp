@@ -144,8 +144,23 @@ static void shim_advance_all(Shim* h, double DT, const double* u_t, const double
                 const int64_t plane = local_winds ? n : (int64_t)Nx * h->Ny;
                 for (int k = 0; k < h->n_mid; k++) { um[k] = h->u_mid[k * plane + off + l]; vm[k] = h->v_mid[k * plane + off + l]; }
             }
-            advance_particle(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l], v_t1[off + l], h->n_mid, um, vm, M,
-                             pc, r, c, K);
+            const double t_start = p.t;
+            int attempts = 0;
+            const bool pending = advance_particle<true>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l],
+                                                        v_t1[off + l], h->n_mid, um, vm, M, pc, r, c, K, attempts);
+            if (pending) { /* as the kernel: the stiff part of the step runs through advance_resume */
+                ResumeArgs R;
+                R.mask = s.mask[l]; R.nmid = h->n_mid; R.attempts = attempts;
+                R.DT = DT; R.t_start = t_start;
+                R.wu0 = u_t[off + l]; R.wv0 = v_t[off + l]; R.wu1 = u_t1[off + l]; R.wv1 = v_t1[off + l];
+                for (int k = 0; k < PH_WIND_SEG_MAX; k++) { R.um[k] = um[k]; R.vm[k] = vm[k]; }
+                memcpy(R.M, M, sizeof R.M);
+                R.pc = pc;
+                Tally c2;
+                tally_zero(c2);
+                advance_resume(&h->P, &R, &p, &r, &c2, K);
+                tally_add(c, c2);
+            }
             tally_add(T, c);
             store(s, l, p);
             int64_t le = l + (int64_t)s.halo * Nx;
