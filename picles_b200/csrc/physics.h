@@ -44,6 +44,7 @@
 #define PH_QOLDINIT 1e-4
 #define PH_LOG_QOLDINIT (-0x1.26bb1bbb55515p+3) /* = pm_log(PH_QOLDINIT) */
 #define PH_CELL_INVALID ((int32_t)-1)
+#define PH_CELL_PENDING ((int32_t)-2) /* AutoTsit5: the particle's step is finished by the resume kernel */
 #define PH_CELL_BIAS 8192
 #define PH_REACH_MAX 15
 #define PH_WIND_SEG_MAX (PICLES_WIND_MID_MAX + 1) /* time segments of the staged wind: levels - 1 */
@@ -738,7 +739,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
 #endif
             double EEst = sc.EEst;
             double eig = 0.0;
-            if (autosw) {
+            if (autosw) { /* inline: an out-of-line monitor measured 6 % slower (call per attempt) */
 #if defined(__CUDA_ARCH__)
                 unsigned bad = 0;
                 eig = stiffness_estimate<OpsFast>(P, T, M, K, dt, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, &bad);

@@ -306,6 +306,7 @@ static int set_grid_impl(picles_t* h, int Nx, int Ny, int bx, int by, int j0, in
     DALLOC(A.flags, n); DALLOC(A.status, n); DALLOC(A.mask, n);
     DALLOC(A.as, n);
     CK(cudaMemsetAsync(A.as, 0, (size_t)n, h->stream));
+    DALLOC(A.pending, n);
     DALLOC(A.u_t, n); DALLOC(A.v_t, n); DALLOC(A.u_t1, n); DALLOC(A.v_t1, n);
     for (int k = 0; k < 5; k++) DALLOC(A.rec[k], ne);
     DALLOC(A.cell, ne);

@@ -55,6 +55,7 @@ struct DeviceArrays {
     int32_t* iter;
     uint8_t *flags, *status, *mask;
     int8_t* as;                      /* AutoTsit5: AutoSwitch state per particle (run length, +64 = Rosenbrock23 current) */
+    int32_t* pending;                /* AutoTsit5: strip-local indices of the particles parked for k_advance_resume */
     double *u_t, *v_t, *u_t1, *v_t1; /* staged winds at t and t+DT */
     double *u_mid[PICLES_WIND_MID_MAX], *v_mid[PICLES_WIND_MID_MAX]; /* intermediate levels (allocated on first use) */
     int n_mid;                       /* intermediate levels staged for the next advance (0: linear in time) */
@@ -74,6 +75,7 @@ struct DeviceCounters {
     int32_t max_attempts;
     int32_t reach_halo;   /* max reach of the records received into the halo rows */
     int32_t class1;       /* a deposit of the second class (a mask-3 particle of a periodic model) exists */
+    int32_t n_pending;    /* AutoTsit5: particles parked by k_advance this step (entries of DeviceArrays::pending) */
 };
 
 void launch_seed(const DeviceArrays& A, const picles_params_t& P, const double* u0, const double* v0, int sms,

@@ -176,25 +176,70 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int6
         const bool pending = advance_particle<AUTOSW>(P, p, A.mask[l], DT, A.u_t[l], A.v_t[l], A.u_t1[l], A.v_t1[l], A.n_mid, um,
                                                       vm, M, pc, r, c, K, attempts);
         if (AUTOSW && pending) {
-            /* AutoSwitch handed the particle to Rosenbrock23: the rest of its step runs out of line */
-            ResumeArgs R;
-            R.mask = A.mask[l]; R.nmid = A.n_mid; R.attempts = attempts;
-            R.DT = DT; R.t_start = t_start;
-            R.wu0 = A.u_t[l]; R.wv0 = A.v_t[l]; R.wu1 = A.u_t1[l]; R.wv1 = A.v_t1[l];
-#pragma unroll
-            for (int k = 0; k < PH_WIND_SEG_MAX; k++) { R.um[k] = um[k]; R.vm[k] = vm[k]; }
-            R.M[0] = M[0]; R.M[1] = M[1]; R.M[2] = M[2]; R.M[3] = M[3];
-            R.pc = pc;
-            Tally c2;
-            tally_zero(c2);
-            advance_resume(&P, &R, &p, &r, &c2, K);
-            tally_merge(c, c2);
+            /* AutoSwitch handed the particle to Rosenbrock23: park the state reached so far; the
+               resume kernel that follows finishes the step (the record slot carries what it needs) */
+            r.cell = PH_CELL_PENDING;
+            r.e = t_start; r.mx = (double)attempts;
+            r.my = r.wxc = r.wyc = 0.0;
+            A.pending[atomicAdd(&dc->n_pending, 1)] = (int32_t)l;
         }
         store_particle(A, l, p);
         if (AUTOSW) store_as(A, P, l, p);
         store_record(A, le, r);
-        if (r.cell != PH_CELL_INVALID) {
+        if (r.cell != PH_CELL_INVALID && !(AUTOSW && r.cell == PH_CELL_PENDING)) {
             /* per-row reach (lets the gather size its window tile by tile) and class presence */
+            const int rr = cell_reach(r.cell);
+            int32_t* slot = &A.rowreach[le / A.rp];
+            if (rr > __ldcg(slot)) atomicMax(slot, rr);
+            if (((uint32_t)r.cell >> 28) & 1u) dc->class1 = 1;
+        }
+    }
+    tally_flush(c, dc);
+}
+
+/*
+ * AutoTsit5 only: the particles k_advance parked (cell == PH_CELL_PENDING) finish their step here —
+ * Rosenbrock23 attempts, possibly back to Tsit5 and forth — with the cold code of stiff.h.  A
+ * handful of particles per step at most (none on most configurations): k_advance appends their
+ * indices to a list, so this kernel costs one launch when the list is empty.  One block per SM,
+ * all registers: nothing here is tuned.
+ */
+template <bool PER_NODE_M>
+__global__ void __launch_bounds__(ADV_THREADS, 1)
+k_advance_resume(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int64_t l_begin, int64_t l_end) {
+    __shared__ double s_k[KS_SLOTS * ADV_THREADS];
+    KStrided K;
+    K.base = &s_k[threadIdx.x];
+    K.stride = ADV_THREADS;
+    Tally c;
+    tally_zero(c);
+    (void)l_begin; (void)l_end;
+    const int n_pending = dc->n_pending; /* entries parked earlier in the step are skipped by their cell marker */
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_pending; q += gridDim.x * blockDim.x) {
+        const int64_t l = A.pending[q];
+        const int64_t le = rec_index(A, l);
+        if (A.cell[le] != PH_CELL_PENDING) continue;
+        Particle p;
+        load_particle(A, l, p);
+        load_as(A, P, l, p);
+        ResumeArgs R;
+        R.mask = A.mask[l]; R.nmid = A.n_mid; R.attempts = (int)A.rec[1][le];
+        R.DT = DT; R.t_start = A.rec[0][le];
+        R.wu0 = A.u_t[l]; R.wv0 = A.v_t[l]; R.wu1 = A.u_t1[l]; R.wv1 = A.v_t1[l];
+        for (int k = 0; k < PH_WIND_SEG_MAX; k++) {
+            const bool have = k < A.n_mid && k < PICLES_WIND_MID_MAX;
+            R.um[k] = have ? A.u_mid[k][l] : 0.0;
+            R.vm[k] = have ? A.v_mid[k][l] : 0.0;
+        }
+        if (PER_NODE_M) { R.M[0] = A.M[0][l]; R.M[1] = A.M[1][l]; R.M[2] = A.M[2][l]; R.M[3] = A.M[3][l]; }
+        else { R.M[0] = A.Mc[0]; R.M[1] = A.Mc[1]; R.M[2] = A.Mc[2]; R.M[3] = A.Mc[3]; }
+        R.pc = A.pc ? A.pc[l] : 0.0;
+        Record r;
+        advance_resume(&P, &R, &p, &r, &c, K);
+        store_particle(A, l, p);
+        store_as(A, P, l, p);
+        store_record(A, le, r);
+        if (r.cell != PH_CELL_INVALID) {
             const int rr = cell_reach(r.cell);
             int32_t* slot = &A.rowreach[le / A.rp];
             if (rr > __ldcg(slot)) atomicMax(slot, rr);
@@ -708,8 +753,14 @@ void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, 
 #endif
     /* AutoTsit5 runs the instantiation that carries the stiffness monitor and the Rosenbrock23 branch */
     if (P.solver == PICLES_SOLVER_AUTOTSIT5) {
-        if (pn) k_advance<true, true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
-        else k_advance<false, true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+        const int gr = grid_for(l_end - l_begin, ADV_THREADS, sms, 1);
+        if (pn) {
+            k_advance<true, true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+            k_advance_resume<true><<<gr, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end);
+        } else {
+            k_advance<false, true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+            k_advance_resume<false><<<gr, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end);
+        }
     } else {
         if (pn) k_advance<true, false><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
         else k_advance<false, false><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);

@@ -46,19 +46,19 @@ def test_gpu_autotsit5_equals_tsit5_without_switches(gpu_lib, name):
 
 
 def test_gpu_autotsit5_checkpoint_carries_the_switch_state(gpu_lib):
-    """save in the middle of the growing-wind run (particles under Rosenbrock23), restore into a
-    fresh handle, continue: bit-identical to the uninterrupted run"""
+    """save after the first step of the growing-wind run (hundreds of particles under
+    Rosenbrock23), restore into a fresh handle, continue: bit-identical to the uninterrupted run"""
     g, P, wind, DT, nsteps = SCENARIOS["growing_winds"]()
     P = with_solver(P, AUTOTSIT5)
     a, b = engine_for(g, P), engine_for(g, P)
     a.seed(*wind(0.0))
     t = 0.0
-    for _ in range(5):
+    for _ in range(1):
         a.step(t, DT, *wind(t), *wind(t + DT))
         t += DT
-    assert (a.solver_state() > 60).any()
+    assert (a.solver_state() > 60).sum() > 100
     b.restore(a.checkpoint())
-    for _ in range(3):
+    for _ in range(4):
         for e in (a, b):
             e.step(t, DT, *wind(t), *wind(t + DT))
         t += DT
