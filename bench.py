@@ -301,6 +301,36 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     n_active = sum(c["n_active"] for c in per_step)  # particle-steps of this rank in the region
 
+    # ---- the reference's default solver on the same workload ---------------------------------
+    # ODESettings.solver defaults to AutoTsit5(Rosenbrock23()) (particle_waves_v5.jl:47).  On this
+    # workload its stiffness monitor never fires (n_stiff_switches = 0, tested), so its results are
+    # the Tsit5 results bit for bit; the monitor-carrying kernel is timed here for the record.
+    auto_variant = None
+    if world == 1 and args.solver == "Tsit5" and not args.no_e2e:
+        from common import default_params
+        eng2 = B200Engine(W["Nx"], W["Ny"], 0, 0, W["mask"], default_params(DT=600.0, solver="AutoTsit5"),
+                          M_const=W["M_const"], device=local_rank)
+        eng2.seed(10.0, 10.0)
+        t2 = 0.0
+        for _ in range(args.warmup):
+            eng2.step(t2, 600.0)
+            t2 += 600.0
+        k2 = min(args.steps, 5)
+        rows2 = []
+        eng2.synchronize()
+        eng2.timer_start()
+        for _ in range(k2):
+            eng2.step(t2, 600.0)
+            t2 += 600.0
+            rows2.append(eng2.counters())
+        ms2 = eng2.timer_stop()
+        auto_variant = {"solver": "AutoTsit5(Rosenbrock23())", "steps": k2,
+                        "value": sum(r["n_active"] for r in rows2) / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / k2,
+                        "ms_advance": float(np.mean([r["ms_advance"] for r in rows2])),
+                        "n_stiff_switches": int(sum(r["n_stiff_switches"] for r in rows2)),
+                        "n_stiff_attempts": int(sum(r["n_stiff_attempts"] for r in rows2))}
+        eng2.close()
+
     # ---- timed region B: end to end through host buffers ----------------------------
     e2e = None
     if not args.no_e2e:
@@ -423,6 +453,8 @@ def main():
         line["e2e"] = {"value": n_e2e_all / (ms_e2e_all * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                        "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": ms_e2e_all / args.steps,
                        "api": "picles_step through the C ABI with pinned host wind buffers + picles_state_energy_sum"}
+    if auto_variant:
+        line["default_solver_variant"] = auto_variant
     if e2e_mesh:
         # the same metric with the wind ingested on the device; k_wind_sample: 16 B of node
         # coordinates in + 16 B of wind out per node (the mesh itself is L2-resident)

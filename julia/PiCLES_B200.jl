@@ -74,6 +74,7 @@ struct PiclesCounters              # picles_counters_t
     n_remesh_A::Int64; n_remesh_B::Int64; n_remesh_C::Int64; n_remesh_D::Int64
     reach::Int32; max_attempts::Int32
     ms_advance::Cdouble; ms_project::Cdouble; ms_remesh::Cdouble
+    n_stiff_switches::Int64; n_stiff_attempts::Int64
 end
 
 mutable struct B200Context
@@ -99,7 +100,9 @@ e_T_func(γ, p, q, n; C_e=2.16e-4, c_β=4e-2, c_D=2e-3, c_e=1.3e-6, c_α=11.8) =
     sqrt(c_e * c_α^(-p / q) / (γ * c_β * c_D)^(1 / n))
 
 boundary_code(N) = occursin("TripolarNorth", string(typeof(N))) ? 2 : occursin("N_Periodic", string(typeof(N))) ? 1 : 0
-solver_code(s) = occursin("DP5", string(typeof(s))) ? 1 : 0     # Tsit5 / AutoTsit5(...) -> 0 (stiff branch not taken)
+# DP5 -> 1; AutoTsit5(Rosenbrock23()) (a CompositeAlgorithm, the ODESettings default) -> 2: Tsit5 with
+# OrdinaryDiffEq's AutoSwitch monitor and the Rosenbrock23 branch; Tsit5 -> 0
+solver_code(s) = (n = string(typeof(s)); occursin("Composite", n) ? 2 : occursin("DP5", n) ? 1 : 0)
 
 function flatten_params(model, arch::B200)
     S = model.ODEsettings

@@ -659,8 +659,13 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
     if (p.status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE)) return false;
     /* compile-time switch: the kernels are instantiated with and without the monitor, so the
        Tsit5 / DP5 loop carries none of it */
+#if defined(__CUDA_ARCH__)
+    const bool autosw = AUTOSW; /* the monitor-carrying kernels are launched for PICLES_SOLVER_AUTOTSIT5 only */
+#else
     const bool autosw = AUTOSW && (P.solver == PICLES_SOLVER_AUTOTSIT5);
+#endif
     bool switched = false;
+    double x6r = 0.0, y6r = 0.0; /* AutoTsit5: running sums of a6j*k_j[3:4], parked in K before the monitor reads them */
     const Tableau& T = tableau(P.solver);
     double t = p.t;
     K.st(KS_TSTOP, tstop_in);
@@ -702,7 +707,8 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
             if (bs != 0.0) { K.st(KS_XE, fma(bs, kx, K.ld(KS_XE))); K.st(KS_YE, fma(bs, ky, K.ld(KS_YE))); }
             if (autosw && ph < 6) {
                 double a6 = T.a[6][ph];
-                if (a6 != 0.0) { K.st(KS_X6, fma(a6, kx, K.ld(KS_X6))); K.st(KS_Y6, fma(a6, ky, K.ld(KS_Y6))); }
+                if (a6 != 0.0) { x6r = fma(a6, kx, x6r); y6r = fma(a6, ky, y6r); }
+                if (ph == 5) { K.st(KS_X6, x6r); K.st(KS_Y6, y6r); }
             }
             if (ph < 7) {
                 /* argument of stage s = ph+1 >= 3 */
@@ -845,7 +851,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
             prop(P, M, u1, u2, kx, ky);
             K.st(KS_X7, T.a[7][1] * kx); K.st(KS_Y7, T.a[7][1] * ky);
             K.st(KS_XE, T.bt[1] * kx); K.st(KS_YE, T.bt[1] * ky);
-            if (autosw) { K.st(KS_X6, T.a[6][1] * kx); K.st(KS_Y6, T.a[6][1] * ky); }
+            if (autosw) { x6r = T.a[6][1] * kx; y6r = T.a[6][1] * ky; }
             double a = dt * T.a[2][1];
             n0 = fma(a, K.get(1, 0), u0); n1 = fma(a, K.get(1, 1), u1); n2 = fma(a, K.get(1, 2), u2);
             ts = fma(T.c[1], dt, t);
