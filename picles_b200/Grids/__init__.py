@@ -1,1 +1,1 @@
-from . import CartesianGrid, TripolarGridMOM6, mask_utils, spherical_grid_corrections  # noqa: F401
+from . import CartesianGrid, SphericalGrid, TripolarGridMOM6, mask_utils, spherical_grid_corrections  # noqa: F401

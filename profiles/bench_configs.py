@@ -51,6 +51,8 @@ def configs():
            (lambda t: (10.0, 10.0)), 600.0)
     g = cartesian_grid(2048, 2048, dx=4000.0, dy=4000.0)
     yield "C3 growing/decaying winds 2048x2048, on/off thresholds", g, default_params(DT=1200.0, wind_min_squared=2.0), growing(g["x"][0]), 1200.0
+    yield ("C3 growing/decaying winds 2048x2048, default solver AutoTsit5(Rosenbrock23()): the stiff branch is active", g,
+           default_params(DT=1200.0, wind_min_squared=2.0, solver="AutoTsit5"), growing(g["x"][0]), 1200.0)
     yield "C4 tripolar aqua 2880x2160 (synthetic)", tripolar(2880, 2160, False), default_params(DT=1200.0, periodic_boundary=True), tw, 1200.0
     yield "C5 tripolar + land 4320x3840 (synthetic)", tripolar(4320, 3840, True), default_params(DT=1200.0, periodic_boundary=True), tw, 1200.0
 
@@ -59,8 +61,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--only", default=None, help="substring of the config names to run")
     a = ap.parse_args()
     for name, g, P, wind, DT in configs():
+        if a.only and a.only not in name:
+            continue
         e = engine_for(g, P)
         u0, v0 = wind(0.0)
         e.seed(u0, v0)
@@ -90,6 +95,7 @@ def main():
             "rhs_per_particle_step": sum(r["n_rhs"] for r in rows) / integ,
             "max_attempts": max(r["max_attempts"] for r in rows), "rejects": sum(r["n_rejects"] for r in rows),
             "failed": sum(r["n_failed"] for r in rows), "reach": max(r["reach"] for r in rows),
+            "stiff_switches": sum(r["n_stiff_switches"] for r in rows), "stiff_attempts": sum(r["n_stiff_attempts"] for r in rows),
             "remesh_ABCD": [rows[-1]["n_remesh_" + c] for c in "ABCD"]}), flush=True)
         e.close()
 

@@ -107,3 +107,22 @@ def test_gpu_gridded_winds_through_run(gpu_lib):
         o.step(t, DT, *samp(t), *samp(t + DT))
         t += DT
     compare_models(o, model.engine)
+
+
+def test_gpu_spherical_grid_model(gpu_lib):
+    """TwoDSphericalGridMesh (src/Grids/SphericalGrid.jl) on B200: per-node kernel planes and the
+    great-circle coefficient through picles_set_grid; x periodic, y closed"""
+    from picles_b200.Architectures import B200
+    from picles_b200.Grids.SphericalGrid import TwoDSphericalGridMesh
+    from picles_b200.Simulations import Simulation, run
+    grid = TwoDSphericalGridMesh(-20.0, 20.0, 41, 10.0, 40.0, 31, periodic_boundary=(True, False))
+    model, DT = example_00_minimal(grid=grid, periodic_boundary=True, architecture=B200())
+    sim = Simulation(model, Δt=DT, stop_time=1 * hours)
+    run(sim)
+    o = make_oracle(grid_dict_from_mesh(grid), default_params(periodic_boundary=True))
+    o.seed(10.0, 10.0)
+    t = 0.0
+    for _ in range(model.clock.iteration):
+        o.step(t, DT, 10.0, 10.0, 10.0, 10.0)
+        t += DT
+    compare_models(o, model.engine)

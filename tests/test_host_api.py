@@ -252,3 +252,38 @@ def test_gridded_winds_are_sampled_by_the_engine():
         o.step(t, DT, *samp(t), *samp(t + DT))
         t += DT
     compare_models(o, model.engine)
+
+
+def test_spherical_grid_mesh_through_the_model():
+    """TwoDSphericalGridMesh (src/Grids/SphericalGrid.jl): spacing in metres from the lon/lat mesh,
+    the per-node kernel exactly as the reference writes it (cos of dy*pi/180, dy in metres) and the
+    great-circle coefficient; a model on it steps like the oracle given the same planes"""
+    from picles_b200.Grids.SphericalGrid import TwoDSphericalGridMesh, cal_dx_meters
+    grid = TwoDSphericalGridMesh(-20.0, 20.0, 21, 10.0, 40.0, 16, periodic_boundary=(True, False))
+    st, d = grid.stats, grid.data
+    assert isinstance(st.Nx, N_Periodic) and isinstance(st.Ny, N_NonPeriodic)
+    assert st.dx_deg == 2.0 and st.dy_deg == 2.0
+    assert d.x[0, 0] == -20.0 and d.x[-1, 0] == 20.0 and d.y[0, -1] == 40.0
+    R = 6371.0e3
+    assert d.dy[3, 5] == pytest.approx(2.0 * np.pi / 180 * R, rel=1e-15)
+    assert d.dx[3, 5] == pytest.approx(2.0 * np.pi / 180 * R * np.cos(np.deg2rad(d.y[3, 5])), rel=1e-14)
+    assert d.dx[0, 5] == pytest.approx(d.dx[3, 5], rel=1e-14)            # one-sided end difference, same spacing
+    met = grid.device_metric()
+    i, j = 4, 7
+    assert met["M"][0][i, j] == 1.0 / (np.cos(d.dy[i, j] * np.pi / 180) * d.dx[i, j])      # the reference's formula, as is
+    assert met["M"][3][i, j] == 1.0 / d.dy[i, j] and np.all(met["M"][1] == 0) and np.all(met["M"][2] == 0)
+    assert met["pc"][i, j] == pytest.approx(np.tan(np.deg2rad(d.y[i, j])) / 6.3710e6, rel=1e-14)
+    assert np.all(d.mask[:, 0] == 3) and np.all(d.mask[:, -1] == 3) and np.all(d.mask[:, 1:-1] == 1)   # x periodic
+    model, DT = example_00_minimal(grid=grid, periodic_boundary=True)
+    attach_shim(model)
+    sim = Simulation(model, Δt=DT, stop_time=30 * minutes)
+    run(sim)
+    g = grid_dict_from_mesh(grid)
+    o = make_oracle(g, default_params(periodic_boundary=True))
+    o.seed(10.0, 10.0)
+    t = 0.0
+    for _ in range(model.clock.iteration):
+        o.step(t, DT, 10.0, 10.0, 10.0, 10.0)
+        t += DT
+    compare_models(o, model.engine)
+    assert np.nanmax(model.State[:, :, 0]) > 0
