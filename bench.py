@@ -74,9 +74,19 @@ def workload(nx, ny_per_gpu, n_gpus, rank):
 SOLVER = "Tsit5"
 
 
-def params():
-    from common import default_params
-    return default_params(DT=600.0, solver=SOLVER)
+def params(solver=None):
+    """example_00_minimal.jl:17-67 settings (T04_2D_reg_test uses the same), flattened by the host
+    mirror of the reference API — no test or oracle module is involved on the b200 arm."""
+    from picles_b200 import FetchRelations as FR
+    from picles_b200.ParticleSystems import particle_waves_v5 as PW
+    from picles_b200.params import make_params
+    DT = 600.0
+    pars, cid, _ = PW.ODEParameters(r_g=0.85)
+    ps = PW.particle_equations(None, None, γ=cid.γ, q=cid.q)
+    sets = PW.ODESettings(Parameters=pars, log_energy_minimum=FR.MinimalWindsea(10, 10, DT)["lne"], saving_step=DT,
+                          timestep=DT, total_time=6 * 86400.0, dt=1e-3, dtmin=1e-4, force_dtmin=True,
+                          solver=solver or SOLVER)
+    return make_params(sets, ps, FR.MinimalState(2, 2, DT), defaults=None, periodic_boundary=False, on_persist=False)
 
 
 class ClockSampler:
@@ -307,8 +317,7 @@ def main():
     # the Tsit5 results bit for bit; the monitor-carrying kernel is timed here for the record.
     auto_variant = None
     if world == 1 and args.solver == "Tsit5" and not args.no_e2e:
-        from common import default_params
-        eng2 = B200Engine(W["Nx"], W["Ny"], 0, 0, W["mask"], default_params(DT=600.0, solver="AutoTsit5"),
+        eng2 = B200Engine(W["Nx"], W["Ny"], 0, 0, W["mask"], params("AutoTsit5"),
                           M_const=W["M_const"], device=local_rank)
         eng2.seed(10.0, 10.0)
         t2 = 0.0

@@ -5,14 +5,13 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
-from bench import workload  # noqa: E402
-from common import default_params  # noqa: E402
+from bench import params, workload  # noqa: E402
 from picles_b200.engine import B200Engine  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 W = workload(n, n, 1, 0)
-e = B200Engine(W["Nx"], W["Ny"], 0, 0, W["mask"], default_params(DT=600.0, solver="AutoTsit5"), M_const=W["M_const"])
+e = B200Engine(W["Nx"], W["Ny"], 0, 0, W["mask"], params("AutoTsit5"), M_const=W["M_const"])
 e.seed(10.0, 10.0)
 t = 0.0
 for k in range(steps):

@@ -10,13 +10,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
-from common import default_params  # noqa: E402
+from bench import params  # noqa: E402
 from picles_b200.engine import B200Engine  # noqa: E402
 
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 ny = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 mask = np.ones((ny, nx), np.uint8)
-eng = B200Engine(nx, ny, 0, 0, mask, default_params(), M_const=np.array([5e-4, 0, 0, 5e-4]))
+eng = B200Engine(nx, ny, 0, 0, mask, params(), M_const=np.array([5e-4, 0, 0, 5e-4]))
 X = np.broadcast_to(np.arange(nx) * 2000.0, (ny, nx))
 Y = np.broadcast_to((np.arange(ny) * 2000.0)[:, None], (ny, nx))
 rng = np.random.default_rng(0)
