@@ -123,3 +123,12 @@ def test_rosenbrock23_converges_to_an_independent_stiff_solver():
         assert r["counters"]["n_stiff_attempts"] >= 4
         errs.append(np.max(np.abs(r["u"] - ref) / np.maximum(np.abs(ref), 1e-3)))
     assert errs[0] < 5e-3 and errs[2] < errs[0] / 50 and errs[2] < 2e-5
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_every_scenario_under_autotsit5(name):
+    """all parity scenarios (edge cases included: NaN winds, maxiters, dtmin, all land, ...) with the
+    solver id switched to AutoTsit5: device code == oracle"""
+    g, P, wind, DT, nsteps = SCENARIOS[name]()
+    P = with_solver(P, AUTOTSIT5)
+    run_pair(make_oracle(g, P), HostShim(g, P), wind, DT, nsteps, compare_with_solver_state)

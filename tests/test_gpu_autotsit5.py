@@ -64,3 +64,19 @@ def test_gpu_autotsit5_checkpoint_carries_the_switch_state(gpu_lib):
         t += DT
     assert bits_equal(a.state(), b.state())
     assert np.array_equal(a.solver_state(), b.solver_state())
+
+
+@pytest.mark.parametrize("name", ["nan_wind", "maxiters", "dtmin_no_force", "emax_clamp", "calm", "land_block", "fast_box"])
+def test_gpu_edge_scenarios_under_autotsit5(gpu_lib, name):
+    g, P, wind, DT, nsteps = SCENARIOS[name]()
+    P = with_solver(P, AUTOTSIT5)
+    run_pair(make_oracle(g, P), engine_for(g, P), wind, DT, nsteps, cmp_state)
+
+
+def test_gpu_autotsit5_in_strips(gpu_lib):
+    """three strip handles on one GPU (host-driven exchange): parked particles are resumed per
+    strip, fields equal the single-domain oracle"""
+    g, P, wind, DT, nsteps = SCENARIOS["growing_winds"]()
+    P = with_solver(P, AUTOTSIT5)
+    ref, dut = make_oracle(g, P), StripSet(g, P, 3, 2)
+    run_pair(ref, dut, wind, DT, nsteps, lambda a, b: compare_models(a, b, check_aux=False))
