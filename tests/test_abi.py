@@ -78,3 +78,40 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
                 assert "picles_oracle" not in txt and "oracle/" not in txt.replace("the oracle/", ""), f
+
+
+def test_julia_glue_ccalls_match_the_header():
+    """julia/PiCLES_B200.jl cannot be executed here (no Julia in the image), so its ccall sites are
+    checked statically: every symbol exists in the C ABI and is called with as many arguments as
+    the header declares, with pointer/scalar kinds in the right places; the Julia mirrors of the two
+    structs list the header's fields in order."""
+    src = open(os.path.join(ROOT, "julia", "PiCLES_B200.jl"), encoding="utf-8").read()
+    calls = re.findall(r"ccall\(\(:(picles_\w+), LIB\),\s*(\w+),\s*\(([^)]*)\)", src, flags=re.S)
+    assert len(calls) >= 12
+    seen = set()
+    for name, ret, argt in calls:
+        assert name in _abi.SYMBOLS, name
+        res, args = _abi.SYMBOLS[name]
+        jl = [a.strip() for a in argt.split(",") if a.strip()]
+        assert len(jl) == len(args), f"{name}: Julia passes {len(jl)} arguments, the header declares {len(args)}"
+        for k, (ja, ca) in enumerate(zip(jl, args)):
+            is_ptr_c = ca in (_abi._vp, C.c_char_p) or hasattr(ca, "contents") or isinstance(ca, type(C.POINTER(C.c_int)))
+            is_ptr_jl = ja.startswith(("Ptr{", "Ref{")) or ja == "Cstring"
+            if ca is C.c_double:
+                assert ja == "Cdouble", (name, k, ja)
+            elif ca is C.c_int:
+                assert ja == "Cint", (name, k, ja)
+            else:
+                assert is_ptr_jl and is_ptr_c, (name, k, ja, ca)
+        assert ret == ("Cstring" if res is C.c_char_p else "Cint"), name
+        seen.add(name)
+    for must in ("picles_create", "picles_set_grid", "picles_set_grid_metric", "picles_set_params", "picles_seed",
+                 "picles_step", "picles_step_strip", "picles_get_state", "picles_get_counters", "picles_comm_init",
+                 "picles_set_wind_midlevels", "picles_set_wind_mesh", "picles_step_wind_mesh"):
+        assert must in seen, must
+    # struct mirrors: same field names in the same order as the ctypes mirrors (checked against the header above)
+    for jl_name, ct in (("PiclesParams", _abi.PiclesParams), ("PiclesCounters", _abi.PiclesCounters)):
+        body = re.search(r"struct %s\b(.*?)\nend" % jl_name, src, flags=re.S).group(1)
+        body = re.sub(r"#.*", "", body)
+        fields = re.findall(r"(\w+)::", body)
+        assert fields == [f for f, *_ in ct._fields_], jl_name
