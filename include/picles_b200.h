@@ -311,6 +311,10 @@ int picles_seed_wind_mesh(picles_t* h, double t0);
    t+dt_model plus n_mid intermediate ones (0..PICLES_WIND_MID_MAX).  The previous step's t+dt
    level is reused as this step's t level when the times match. */
 int picles_step_wind_mesh(picles_t* h, double t, double dt_model, int n_mid, int lo_rank, int hi_rank);
+/* the wind half of picles_step_wind_mesh alone, for hosts that drive the phase-split calls
+   (picles_step_advance / halo exchange / picles_step_project_remesh) themselves: every level of the
+   step [t, t+dt_model] is sampled into the device planes; nothing is integrated */
+int picles_stage_wind_mesh(picles_t* h, double t, double dt_model, int n_mid);
 
 /* ---- state access ------------------------------------------------------ */
 int picles_get_state(picles_t* h, double* S /* ny_local*Nx*3: planes e, m_x, m_y */);

@@ -135,6 +135,7 @@ SYMBOLS = {
     "picles_sample_wind_mesh": (C.c_int, [_vp, C.c_double, _vp, _vp]),
     "picles_seed_wind_mesh": (C.c_int, [_vp, C.c_double]),
     "picles_step_wind_mesh": (C.c_int, [_vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]),
+    "picles_stage_wind_mesh": (C.c_int, [_vp, C.c_double, C.c_double, C.c_int]),
     "picles_get_state": (C.c_int, [_vp, _vp]),
     "picles_set_state": (C.c_int, [_vp, _vp]),
     "picles_checkpoint_size": (C.c_int, [_vp, C.POINTER(C.c_int64)]),

@@ -1279,7 +1279,9 @@ int picles_seed_wind_mesh(picles_t* h, double t0) {
     return seed_from_t1(h);
 }
 
-int picles_step_wind_mesh(picles_t* h, double t, double dt_model, int n_mid, int lo_rank, int hi_rank) {
+/* every wind level of the step [t, t+dt_model] sampled from the mesh into the device planes: what
+   picles_upload_winds + picles_set_wind_midlevels do from host arrays */
+int picles_stage_wind_mesh(picles_t* h, double t, double dt_model, int n_mid) {
     int rc = need_ready(h, true);
     if (rc) return rc;
     if (!h->have_wind_mesh) return fail(h, PICLES_ERR_STATE, "picles_set_wind_mesh must be called first");
@@ -1303,6 +1305,13 @@ int picles_step_wind_mesh(picles_t* h, double t, double dt_model, int n_mid, int
     A.n_mid = n_mid;
     h->wm_t1_valid = true;
     h->wm_t1_time = t1;
+    return PICLES_OK;
+}
+
+int picles_step_wind_mesh(picles_t* h, double t, double dt_model, int n_mid, int lo_rank, int hi_rank) {
+    int rc = picles_stage_wind_mesh(h, t, dt_model, n_mid);
+    if (rc) return rc;
+    const DeviceArrays& A = h->A;
     if (A.ny == A.Ny && lo_rank < 0 && hi_rank < 0) return picles_step(h, t, dt_model, nullptr, nullptr, nullptr, nullptr);
     return picles_step_strip(h, t, dt_model, nullptr, nullptr, nullptr, nullptr, lo_rank, hi_rank);
 }

@@ -206,10 +206,13 @@ class StripStepper:
         if self.transport is None or isinstance(self.transport, NcclLibTransport):
             e.step_wind_mesh(t, DT, n_mid, self.lo, self.hi)
             return
-        if n_mid:
-            lv = [e.sample_wind_mesh(t + DT * float(k) / float(n_mid + 1)) for k in range(1, n_mid + 1)]
-            e.set_wind_midlevels([a for a, _ in lv], [b for _, b in lv])
-        e.upload_winds(*e.sample_wind_mesh(t), *e.sample_wind_mesh(t + DT))
+        if hasattr(e, "stage_wind_mesh"):      # B200Engine: levels sampled on the device, nothing uploaded
+            e.stage_wind_mesh(t, DT, n_mid)
+        else:                                   # host build of the device code (CPU tests)
+            if n_mid:
+                lv = [e.sample_wind_mesh(t + DT * float(k) / float(n_mid + 1)) for k in range(1, n_mid + 1)]
+                e.set_wind_midlevels([a for a, _ in lv], [b for _, b in lv])
+            e.upload_winds(*e.sample_wind_mesh(t), *e.sample_wind_mesh(t + DT))
         e.step_advance(t, DT)
         self.transport.exchange(self.lo, self.hi)
         e.step_project_remesh(t, DT)

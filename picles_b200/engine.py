@@ -124,6 +124,11 @@ class B200Engine:
         """one model step with every wind level sampled on the device from the resident mesh"""
         self._check(self.lib.picles_step_wind_mesh(self.h, float(t), float(DT), int(n_mid), int(lo), int(hi)))
 
+    def stage_wind_mesh(self, t, DT, n_mid=0):
+        """sample every wind level of [t, t+DT] from the resident mesh into the device planes
+        (the phase-split calls then run without any wind upload)"""
+        self._check(self.lib.picles_stage_wind_mesh(self.h, float(t), float(DT), int(n_mid)))
+
     def step_raw(self, t, DT, pu_t=None, pv_t=None, pu_t1=None, pv_t1=None):
         """Same as step() with raw host pointers (ints), e.g. of pinned torch tensors."""
         self._check(self.lib.picles_step(self.h, float(t), float(DT), pu_t, pv_t, pu_t1, pv_t1))

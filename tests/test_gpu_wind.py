@@ -131,3 +131,42 @@ def test_gpu_wind_mesh_errors(gpu_lib):
         e.set_wind_mesh(xw[::-1].copy(), yw, tw, U, V, g["x"], g["y"])
     with pytest.raises(PiclesError, match="n_mid"):
         e.set_wind_midlevels([g["x"]] * 4, [g["x"]] * 4)
+
+
+def test_gpu_stage_wind_mesh_with_phase_split_strips(gpu_lib):
+    """three strip handles on one GPU, host-driven exchange: every strip stages its own wind levels
+    from its resident mesh (picles_stage_wind_mesh), then the phase-split calls run as usual"""
+    from dist_worker import mesh_of
+    from scenarios import SCENARIOS
+    g, P, _, DT, nsteps = SCENARIOS["minimal"]()
+    mesh = mesh_of(g, DT, nsteps)
+    samp = lambda t: oracle.wind_mesh_sample(*mesh, g["x"], g["y"], t)
+    ref = make_oracle(g, P)
+    dut = StripSet(g, P, 3, 2)
+    for (a, b), e in zip(dut.bounds, dut.e):
+        e.set_wind_mesh(*mesh, g["x"][a:b], g["y"][a:b])
+        e.seed_wind_mesh(0.0)
+    ref.seed(*samp(0.0))
+    t = 0.0
+    for _ in range(nsteps):
+        mids = [samp(t + DT * float(k) / 3.0) for k in (1, 2)]
+        ref.set_wind_midlevels([m[0] for m in mids], [m[1] for m in mids])
+        ref.step(t, DT, *samp(t), *samp(t + DT))
+        for e in dut.e:                      # StripSet.step with staged instead of uploaded winds
+            e.stage_wind_mesh(t, DT, 2)
+            e.step_advance(t, DT)
+            e.halo_pack()
+        for e in dut.e:
+            e.synchronize()
+        bufs = [e.halo_buffers() for e in dut.e]
+        for r, e in enumerate(dut.e):
+            (slo, shi, rlo, rhi), nb = bufs[r]
+            if r - 1 >= 0:
+                e.copy_dev(rlo, bufs[r - 1][0][1], nb)
+            if r + 1 < dut.ns:
+                e.copy_dev(rhi, bufs[r + 1][0][0], nb)
+            e.halo_unpack()
+        for e in dut.e:
+            e.step_project_remesh(t, DT)
+        t += DT
+        compare_models(ref, dut, check_aux=False)
