@@ -1,6 +1,6 @@
-"""Small end-to-end exercise of every kernel for compute-sanitizer (memcheck): seed, steps with
+"""Small end-to-end exercise of every kernel (a driver for memory checkers; compute-sanitizer is closed on this pool, so it was only run plain): seed, steps with
 host winds + intermediate levels, wind mesh steps, AutoTsit5 with parked particles, strips with
-pack/unpack, fields, checkpoint.  usage: compute-sanitizer --tool memcheck python profiles/sanitize_small.py"""
+pack/unpack, fields, checkpoint.  usage: python profiles/exercise_all_kernels.py"""
 import copy
 import os
 import sys
