@@ -110,7 +110,7 @@ PM_HD const Tableau& tableau(int solver) {
 enum {
     KS_U3 = 21, KS_U4, KS_X7, KS_Y7, KS_XE, KS_YE, KS_TSTOP, KS_LQ, KS_QOLD, KS_DT0, KS_D1N, KS_DTMIN,
     KS_WT0, KS_WIDT,
-    KS_X6, KS_Y6, /* AutoTsit5 monitor: propagation part of the argument of stage 6 */
+    KS_G60, KS_G61, /* AutoTsit5 monitor: argument of stage 6, components 0 and 1 (component 2: KS_DT0, idle during attempts) */
     KS_AS,        /* AutoTsit5: AutoSwitch run length (as a double; +PH_AS_STIFF once switched) */
     KS_WCU,                            /* Newton coefficients c_1..c_4 of the wind's u component in time */
     KS_WCV = KS_WCU + PH_WIND_SEG_MAX, /* ... and of v */
@@ -597,37 +597,84 @@ PM_HD void wind_to_slots(const picles_params_t& P, const Wind& w, KS& K, Hoist& 
 }
 
 /* Tsit5 inside a composite algorithm: eigen_est = max_i |k7_i - k6_i| / |g7_i - g6_i| (Hairer II,
-   p. 22).  g7 = u_new (n), g6 = u + dt * sum_j a6j k_j rebuilt from the stored stage derivatives and
-   the running sums X6, Y6.  Once per attempt, AutoTsit5 only. */
-template <class O, class KS>
-PM_HD double stiffness_estimate(const picles_params_t& P, const Tableau& T, const double* M, const KS& K, double dt,
-                                double u0, double u1, double u2, double u3, double u4, double n0, double n1, double n2,
-                                double n3, double n4, unsigned* bad) {
-    double a1 = T.a[6][1];
-    double i0 = a1 * K.get(1, 0), i1 = a1 * K.get(1, 1), i2 = a1 * K.get(1, 2);
-    for (int j = 2; j < 6; j++) {
-        double aj = T.a[6][j];
-        if (aj != 0.0) { i0 = fma(aj, K.get(j, 0), i0); i1 = fma(aj, K.get(j, 1), i1); i2 = fma(aj, K.get(j, 2), i2); }
-    }
-    const double g60 = fma(dt, i0, u0), g61 = fma(dt, i1, u1), g62 = fma(dt, i2, u2);
-    const double g63 = fma(dt, K.ld(KS_X6), u3), g64 = fma(dt, K.ld(KS_Y6), u4);
+   p. 22).  g7 = u_new (n); g6 = the argument of stage 6: its first three components were saved
+   when the stage was set up, the propagation part comes from the running sums x6, y6.
+   num[i] = k7_i - k6_i, den[i] = g7_i - g6_i.  Once per attempt, AutoTsit5 only. */
+template <class KS>
+PM_HD void stiffness_terms(const picles_params_t& P, const double* M, const KS& K, double dt, double x6, double y6, double u3,
+                           double u4, double n0, double n1, double n2, double n3, double n4, double* num, double* den) {
+    const double g60 = K.ld(KS_G60), g61 = K.ld(KS_G61), g62 = K.ld(KS_DT0); /* saved when stage 6 was set up */
+    const double g63 = fma(dt, x6, u3), g64 = fma(dt, y6, u4);
     double k6x, k6y, k7x, k7y;
     prop(P, M, g61, g62, k6x, k6y);
     prop(P, M, n1, n2, k7x, k7y);
-    double eig = 0.0;
-    eig = pm_max(eig, fabs(O::divz(K.get(7, 0) - K.get(6, 0), n0 - g60, bad)));
-    eig = pm_max(eig, fabs(O::divz(K.get(7, 1) - K.get(6, 1), n1 - g61, bad)));
-    eig = pm_max(eig, fabs(O::divz(K.get(7, 2) - K.get(6, 2), n2 - g62, bad)));
-    eig = pm_max(eig, fabs(O::divz(k7x - k6x, n3 - g63, bad)));
-    eig = pm_max(eig, fabs(O::divz(k7y - k6y, n4 - g64, bad)));
-    return eig;
+    num[0] = K.get(7, 0) - K.get(6, 0); den[0] = n0 - g60;
+    num[1] = K.get(7, 1) - K.get(6, 1); den[1] = n1 - g61;
+    num[2] = K.get(7, 2) - K.get(6, 2); den[2] = n2 - g62;
+    num[3] = k7x - k6x; den[3] = n3 - g63;
+    num[4] = k7y - k6y; den[4] = n4 - g64;
 }
-template <class KS>
-PM_HD_NOINLINE_DECL double stiffness_estimate_cold(const picles_params_t* Pp, const Tableau* Tp, double m0, double m1, double m2,
-                                                   double m3, KS K, double dt, double u0, double u1, double u2, double u3,
-                                                   double u4, double n0, double n1, double n2, double n3, double n4) {
-    const double M[4] = {m0, m1, m2, m3};
-    return stiffness_estimate<OpsSafe>(*Pp, *Tp, M, K, dt, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, (unsigned*)0);
+/* the AutoSwitch test as OrdinaryDiffEq evaluates it: |eigen_est * dt / stability_size| > nonstifftol
+   with eigen_est = max_i |num_i / den_i| (IEEE divisions), dt the step the controller proposes */
+PM_HD_NOINLINE_DECL bool stiffness_test_exact(double a0, double a1, double a2, double a3, double a4, double b0, double b1,
+                                              double b2, double b3, double b4, double dt_next) {
+    double eig = 0.0;
+    eig = pm_max(eig, fabs(a0 / b0));
+    eig = pm_max(eig, fabs(a1 / b1));
+    eig = pm_max(eig, fabs(a2 / b2));
+    eig = pm_max(eig, fabs(a3 / b3));
+    eig = pm_max(eig, fabs(a4 / b4));
+    return fabs(eig * dt_next / 3.5068) > 0.9;
+}
+/*
+ * The same decision without a division.  With c = 0.9 * 3.5068 and p_i = |num_i| * dt, d_i = |den_i|:
+ *   p_i <  c (1 - 1e-13) d_i  for every i  =>  every rounded |num_i/den_i| * dt / 3.5068 ends below 0.9
+ *                                              (three roundings of 1.1e-16 each): not stiff;
+ *   p_i >  c (1 + 1e-13) d_i  for some i, every other component decided one way or the other
+ *                                          =>  that quotient alone carries the maximum above 0.9: stiff.
+ * A quotient 0/0 (a component that did not move in the attempt) is NaN, which makes eigen_est NaN
+ * and the test false whatever the other components are; x/0 is Inf and makes it true unless a NaN
+ * is about: decided as well (both occur in the first, rounding-noise-sized attempts after a reset).  A component is undecided
+ * inside the 1e-13 band, when d_i is so small (< 1e-200) that p_i could underflow out of the
+ * argument, and whenever a comparison involves NaN or Inf/Inf.  Only
+ * undecided attempts take the exact test, out of line: in practice none, so no warp diverges into
+ * it.  Bit-identical decisions (tests/test_autotsit5.py compares every attempt's outcome through
+ * the switch counts and the State).
+ */
+PM_HD bool stiffness_test(const double* num, const double* den, double dt_next) {
+    const double c_lo = 3.15612 * (1.0 - 1e-13), c_hi = 3.15612 * (1.0 + 1e-13);
+    /* level 1 (all most attempts need): every component clearly below the threshold */
+    bool all_clear = true;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 5; i++) {
+        const double di = fabs(den[i]);
+        all_clear = all_clear & (di > 1e-200) & (fabs(num[i]) * dt_next < c_lo * di);
+    }
+    if (all_clear) return false;
+    /* level 2: the stiff side and the degenerate quotients */
+    bool all_decided = true, any_stiff = false, any_nan = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 5; i++) {
+        const double pi = fabs(num[i]) * dt_next, di = fabs(den[i]);
+        const bool ok = di > 1e-200;             /* false for NaN too */
+        const bool clear = ok & (pi < c_lo * di);
+        const bool stiff = ok & (pi > c_hi * di);
+        const bool zz = (num[i] == 0.0) & (den[i] == 0.0); /* 0/0 */
+        /* x/0, x finite and non-zero: the quotient is Inf, and Inf * dt / 3.5068 > 0.9 for dt > 0 */
+        const bool xz = (den[i] == 0.0) & (fabs(num[i]) > 0.0) & (fabs(num[i]) < 1.7976931348623157e308) & (dt_next > 0.0);
+        all_decided = all_decided & (clear | stiff | zz | xz);
+        any_stiff = any_stiff | stiff | xz;
+        any_nan = any_nan | zz;
+    }
+#ifdef PH_COUNT_EXACT
+    g_tests++; if (!all_decided) g_exact++;
+#endif
+    if (all_decided) return any_stiff & !any_nan;
+    return stiffness_test_exact(num[0], num[1], num[2], num[3], num[4], den[0], den[1], den[2], den[3], den[4], dt_next);
 }
 
 /* ---- step!(integrator, DT, true): advance particle p from p.t to p.t + DT ------------ */
@@ -687,7 +734,6 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
     double n0 = u0, n1 = u1, n2 = u2, ts = t; /* argument of the next right-hand side */
     K.st(KS_X7, 0.0); K.st(KS_Y7, 0.0); K.st(KS_XE, 0.0); K.st(KS_YE, 0.0); K.st(KS_DT0, 0.0); K.st(KS_D1N, 0.0);
     K.st(KS_DTMIN, P.dtmin);
-    K.st(KS_X6, 0.0); K.st(KS_Y6, 0.0);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -708,21 +754,35 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
             if (autosw && ph < 6) {
                 double a6 = T.a[6][ph];
                 if (a6 != 0.0) { x6r = fma(a6, kx, x6r); y6r = fma(a6, ky, y6r); }
-                if (ph == 5) { K.st(KS_X6, x6r); K.st(KS_Y6, y6r); }
             }
             if (ph < 7) {
                 /* argument of stage s = ph+1 >= 3 */
                 int s = ++ph;
                 double a1 = T.a[s][1];
                 double i0 = a1 * K.get(1, 0), i1 = a1 * K.get(1, 1), i2 = a1 * K.get(1, 2);
-                for (int j = 2; j < s; j++) {
-                    double aj = T.a[s][j];
-                    if (aj != 0.0) {
-                        i0 = fma(aj, K.get(j, 0), i0); i1 = fma(aj, K.get(j, 1), i1); i2 = fma(aj, K.get(j, 2), i2);
+                if (AUTOSW) {
+                    /* the monitor-carrying loop sits at the edge of the instruction cache (profiles/README.md):
+                       the same sums, rolled */
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                    for (int j = 2; j < s; j++) {
+                        double aj = T.a[s][j];
+                        if (aj != 0.0) {
+                            i0 = fma(aj, K.get(j, 0), i0); i1 = fma(aj, K.get(j, 1), i1); i2 = fma(aj, K.get(j, 2), i2);
+                        }
+                    }
+                } else {
+                    for (int j = 2; j < s; j++) {
+                        double aj = T.a[s][j];
+                        if (aj != 0.0) {
+                            i0 = fma(aj, K.get(j, 0), i0); i1 = fma(aj, K.get(j, 1), i1); i2 = fma(aj, K.get(j, 2), i2);
+                        }
                     }
                 }
                 n0 = fma(dt, i0, u0); n1 = fma(dt, i1, u1); n2 = fma(dt, i2, u2);
                 ts = (s >= 6) ? (t + dt) : fma(T.c[s - 1], dt, t);
+                if (autosw && s == 6) { K.st(KS_G60, n0); K.st(KS_G61, n1); K.st(KS_DT0, n2); } /* g6 of the monitor */
                 continue;
             }
             /* all seven stages done: (n0,n1,n2) is u_new */
@@ -730,9 +790,19 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
             double n3 = fma(dt, K.ld(KS_X7), u3), n4 = fma(dt, K.ld(KS_Y7), u4);
             double b1 = T.bt[1];
             double e0 = b1 * K.get(1, 0), e1 = b1 * K.get(1, 1), e2 = b1 * K.get(1, 2);
-            for (int j = 2; j <= 7; j++) {
-                double bj = T.bt[j];
-                if (bj != 0.0) { e0 = fma(bj, K.get(j, 0), e0); e1 = fma(bj, K.get(j, 1), e1); e2 = fma(bj, K.get(j, 2), e2); }
+            if (AUTOSW) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                for (int j = 2; j <= 7; j++) {
+                    double bj = T.bt[j];
+                    if (bj != 0.0) { e0 = fma(bj, K.get(j, 0), e0); e1 = fma(bj, K.get(j, 1), e1); e2 = fma(bj, K.get(j, 2), e2); }
+                }
+            } else {
+                for (int j = 2; j <= 7; j++) {
+                    double bj = T.bt[j];
+                    if (bj != 0.0) { e0 = fma(bj, K.get(j, 0), e0); e1 = fma(bj, K.get(j, 1), e1); e2 = fma(bj, K.get(j, 2), e2); }
+                }
             }
             StepCtl sc;
             const double xe = K.ld(KS_XE), ye = K.ld(KS_YE), lq = K.ld(KS_LQ);
@@ -744,47 +814,49 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
             step_control_cold(P, T, dt, e0, e1, e2, xe, ye, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, lq, sc);
 #endif
             double EEst = sc.EEst;
-            double eig = 0.0;
-            if (autosw) { /* inline: an out-of-line monitor measured 6 % slower (call per attempt) */
-#if defined(__CUDA_ARCH__)
-                unsigned bad = 0;
-                eig = stiffness_estimate<OpsFast>(P, T, M, K, dt, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, &bad);
-                if (bad) eig = stiffness_estimate_cold(&P, &T, M[0], M[1], M[2], M[3], K, dt, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4);
-#else
-                eig = stiffness_estimate_cold(&P, &T, M[0], M[1], M[2], M[3], K, dt, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4);
-#endif
-            }
-            bool accept = (EEst <= 1.0) || (P.force_dtmin && fabs(dt) <= K.ld(KS_DTMIN));
+            const bool accept = (EEst <= 1.0) || (P.force_dtmin && fabs(dt) <= K.ld(KS_DTMIN));
+            /* the step size the controller proposes (and, accepted, the new time) first: the
+               AutoSwitch test below needs it while the state of the attempt is still intact */
+            double dt_next, t_next = t;
             if (accept) {
                 /* step_accept_controller!, fixed_t_for_floatingpoint_error!, calc_dt_propose! */
-                bool big = (EEst > PH_QOLDINIT) || (EEst != EEst);
-                K.st(KS_QOLD, big ? EEst : PH_QOLDINIT); /* max(EEst, qoldinit) */
-                K.st(KS_LQ, big ? sc.lE : LQ0);
                 double dtnew = dt / sc.q;
                 double ttmp = t + dt;
                 const double tstop = K.ld(KS_TSTOP);
-                t = (fabs(ttmp - tstop) < 100.0 * pm_eps(tstop)) ? tstop : ttmp;
+                t_next = (fabs(ttmp - tstop) < 100.0 * pm_eps(tstop)) ? tstop : ttmp;
                 double dtp = pm_min(P.dtmax, dtnew);
-                dtp = pm_max(dtp, pm_max(pm_eps(t), P.dtmin));
-                dt = dtp;
+                dt_next = pm_max(dtp, pm_max(pm_eps(t_next), P.dtmin));
+            } else {
+                /* step_reject_controller!: dt /= min(1/qmin, q11/gamma), q11 = EEst^beta1 */
+                double q11 = (EEst == 0.0) ? 1.0 : pm_exp(sc.t1);
+                dt_next = dt / pm_min(1.0 / qmin, q11 / gamma);
+            }
+            bool is_stiff = false;
+            if (autosw) {
+                double num[5], den[5];
+                stiffness_terms(P, M, K, dt, x6r, y6r, u3, u4, n0, n1, n2, n3, n4, num, den);
+                is_stiff = stiffness_test(num, den, dt_next);
+            }
+            if (accept) {
+                bool big = (EEst > PH_QOLDINIT) || (EEst != EEst);
+                K.st(KS_QOLD, big ? EEst : PH_QOLDINIT); /* max(EEst, qoldinit) */
+                K.st(KS_LQ, big ? sc.lE : LQ0);
+                t = t_next;
                 u0 = n0; u1 = n1; u2 = n2;
                 K.st(KS_U3, n3); K.st(KS_U4, n4);
                 K.set(1, 0, K.get(7, 0)); K.set(1, 1, K.get(7, 1)); K.set(1, 2, K.get(7, 2)); /* FSAL */
                 c.substeps++;
-                if ((u0 != u0) | (u1 != u1) | (u2 != u2) | (n3 != n3) | (n4 != n4)) {
-                    p.status |= PICLES_PST_UNSTABLE; c.failed++; break;
-                }
             } else {
-                /* step_reject_controller!: dt /= min(1/qmin, q11/gamma), q11 = EEst^beta1 */
-                double q11 = (EEst == 0.0) ? 1.0 : pm_exp(sc.t1);
-                dt = dt / pm_min(1.0 / qmin, q11 / gamma);
                 c.rejects++;
+            }
+            dt = dt_next;
+            if (accept && ((u0 != u0) | (u1 != u1) | (u2 != u2) | (n3 != n3) | (n4 != n4))) {
+                p.status |= PICLES_PST_UNSTABLE; c.failed++; break;
             }
             if (autosw) {
                 /* AutoSwitch: maxstiffstep 10, nonstifftol 9//10, dtfac 2, stability_size(Tsit5) 3.5068 */
-                const bool is = fabs(eig * dt / 3.5068) > 0.9;
                 int cnt = (int)K.ld(KS_AS);
-                cnt = is ? ((cnt < 0) ? 1 : cnt + 1) : ((cnt > 0) ? -1 : cnt - 1);
+                cnt = is_stiff ? ((cnt < 0) ? 1 : cnt + 1) : ((cnt > 0) ? -1 : cnt - 1);
                 cnt = (cnt > PH_AS_CLAMP) ? PH_AS_CLAMP : ((cnt < -PH_AS_CLAMP) ? -PH_AS_CLAMP : cnt);
                 K.st(KS_AS, (double)cnt);
                 if (cnt > 10) {
