@@ -435,6 +435,7 @@ PM_HD void make_hoist(const picles_params_t& P, double wu0, double wv0, bool ste
     H.y_rg = pm_rcp_newton(P.r_g);
     H.y_eT = pm_rcp_newton(P.e_T);
 #else
+    (void)P;
     H.y_rg = 0.0; H.y_eT = 0.0;
 #endif
     H.steady = steady;
