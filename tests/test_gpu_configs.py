@@ -114,3 +114,59 @@ def test_c5_tripolar_high_resolution_strips_properties(gpu_lib):
     act = (pa["flags"] & 8) != 0
     assert np.array_equal(pa["z"][:, act].view(np.uint64), pb["z"][:, act].view(np.uint64))
     assert one.counters()["n_substeps"] == four.counters()["n_substeps"]
+
+
+def test_wind_mesh_sampler_full_size(gpu_lib):
+    """k_wind_sample over the 4096 x 4096 bench grid from an ERA5-like 1-degree mesh (361 x 181 knots,
+    6-hourly), nodes spilling over the mesh on every side (periodic wrap), against the oracle's
+    restatement of LinearInterpolation(..., extrapolation_bc=Periodic()) — bit for bit on all 16.8 M nodes —
+    and the AutoTsit5 C3 run (stiff branch active at full size) against the translation-invariance property"""
+    import oracle
+    from picles_b200.engine import B200Engine
+    N = 4096
+    rng = np.random.default_rng(4)
+    xw = np.linspace(5.0e5, 7.5e6, 361)
+    yw = np.sort(rng.uniform(3.0e5, 7.9e6, 181))          # non-uniform in y
+    tw = np.arange(5) * 21600.0
+    U = rng.normal(8.0, 4.0, (tw.size, yw.size, xw.size))
+    V = rng.normal(-3.0, 5.0, (tw.size, yw.size, xw.size))
+    x = np.ascontiguousarray(np.broadcast_to(np.arange(N) * 2000.0, (N, N)))
+    y = np.ascontiguousarray(np.broadcast_to((np.arange(N) * 2000.0)[:, None], (N, N)))
+    e = B200Engine(N, N, 0, 0, np.ones((N, N), np.uint8), default_params(), M_const=np.array([5e-4, 0.0, 0.0, 5e-4]))
+    e.set_wind_mesh(xw, yw, tw, U, V, x, y)
+    for t in (12345.0, 86400.0 + 7.0):
+        ud, vd = e.sample_wind_mesh(t)
+        uo, vo = oracle.wind_mesh_sample(xw, yw, tw, U, V, x, y, t)
+        assert np.array_equal(ud.view(np.uint64), uo.view(np.uint64))
+        assert np.array_equal(vd.view(np.uint64), vo.view(np.uint64))
+
+
+def test_c3_autotsit5_stiff_branch_at_full_size(gpu_lib):
+    """configs[2] under ODESettings' default solver: thousands of particles go through Rosenbrock23
+    (k_advance_resume) per step; every interior row still carries the bits of the middle row of a
+    2048 x 24 box integrated by the CPU oracle with the same solver"""
+    import copy
+    N = 2048
+    P = copy.copy(default_params(DT=1200.0, wind_min_squared=2.0))
+    P.solver = 2
+    g = cartesian_grid(N, N, dx=4000.0, dy=4000.0)
+    gs = cartesian_grid(N, 24, dx=4000.0, dy=4000.0)
+    wind = growing_wind(g["x"][0])
+    winds = lambda t: [np.broadcast_to(a, (24, N)) for a in wind(t)]
+    eng = engine_for(g, P)
+    ref = make_oracle(gs, P, variant="omp", threads=8)
+    eng.seed(*wind(0.0))
+    ref.seed(*winds(0.0))
+    t, switches = 0.0, 0
+    for _ in range(4):
+        eng.step(t, 1200.0, *wind(t), *wind(t + 1200.0))
+        ref.step(t, 1200.0, *winds(t), *winds(t + 1200.0))
+        t += 1200.0
+        switches += eng.counters()["n_stiff_switches"]
+    assert switches > 1000
+    S, Sr = eng.state(), ref.state()
+    mid = Sr[:, 12, :]
+    for j in (8, 500, 1024, 2039):
+        assert np.array_equal(S[:, j, :].view(np.uint64), mid.view(np.uint64)), j
+    st = eng.solver_state()
+    assert np.array_equal(st[1024], ref.solver_state()[12])
