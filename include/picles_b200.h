@@ -347,8 +347,8 @@ int picles_snapshot_wait(picles_t* h);
 
 /* ---- checkpoint / resume --------------------------------------------------------- */
 /* The reference cannot resume (run!(…; pickup=false) is unused, src/Simulations/run.jl:36).
-   Here the particle planes, the node State and the pending wind level are the complete state
-   of the path: save writes them into a caller-owned host blob of picles_checkpoint_size
+   Here the particle planes (the AutoSwitch state of AutoTsit5 included), the node State and the
+   pending wind level are the complete state of the path: save writes them into a caller-owned host blob of picles_checkpoint_size
    bytes; load restores them into a handle with the same grid and parameters (set_grid* and
    set_params called, picles_seed not needed).  A resumed run continues bit-identically. */
 int picles_checkpoint_size(picles_t* h, int64_t* nbytes);
