@@ -734,7 +734,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
     int ph = 1;
     double n0 = u0, n1 = u1, n2 = u2, ts = t; /* argument of the next right-hand side */
     K.st(KS_X7, 0.0); K.st(KS_Y7, 0.0); K.st(KS_XE, 0.0); K.st(KS_YE, 0.0); K.st(KS_DT0, 0.0); K.st(KS_D1N, 0.0);
-    K.st(KS_DTMIN, P.dtmin);
+    K.st(KS_DTMIN, pm_max(pm_eps(t), P.dtmin)); /* max(eps(t), dtmin): kept current on every accepted step */
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -818,7 +818,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
             const bool accept = (EEst <= 1.0) || (P.force_dtmin && fabs(dt) <= K.ld(KS_DTMIN));
             /* the step size the controller proposes (and, accepted, the new time) first: the
                AutoSwitch test below needs it while the state of the attempt is still intact */
-            double dt_next, t_next = t;
+            double dt_next, t_next = t, dtmin_next = 0.0;
             if (accept) {
                 /* step_accept_controller!, fixed_t_for_floatingpoint_error!, calc_dt_propose! */
                 double dtnew = dt / sc.q;
@@ -826,7 +826,8 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
                 const double tstop = K.ld(KS_TSTOP);
                 t_next = (fabs(ttmp - tstop) < 100.0 * pm_eps(tstop)) ? tstop : ttmp;
                 double dtp = pm_min(P.dtmax, dtnew);
-                dt_next = pm_max(dtp, pm_max(pm_eps(t_next), P.dtmin));
+                dtmin_next = pm_max(pm_eps(t_next), P.dtmin);
+                dt_next = pm_max(dtp, dtmin_next);
             } else {
                 /* step_reject_controller!: dt /= min(1/qmin, q11/gamma), q11 = EEst^beta1 */
                 double q11 = (EEst == 0.0) ? 1.0 : pm_exp(sc.t1);
@@ -843,6 +844,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
                 K.st(KS_QOLD, big ? EEst : PH_QOLDINIT); /* max(EEst, qoldinit) */
                 K.st(KS_LQ, big ? sc.lE : LQ0);
                 t = t_next;
+                K.st(KS_DTMIN, dtmin_next); /* the loopheader! of the next attempt reads it */
                 u0 = n0; u1 = n1; u2 = n2;
                 K.st(KS_U3, n3); K.st(KS_U4, n4);
                 K.set(1, 0, K.get(7, 0)); K.set(1, 1, K.get(7, 1)); K.set(1, 2, K.get(7, 2)); /* FSAL */
@@ -910,8 +912,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
         const double tstop = K.ld(KS_TSTOP);
         if (!(t < tstop)) break;
         iter++;
-        const double dtmin_t = pm_max(pm_eps(t), P.dtmin);
-        K.st(KS_DTMIN, dtmin_t);
+        const double dtmin_t = K.ld(KS_DTMIN); /* = max(eps(t), dtmin) */
         dt = pm_min(P.dtmax, dt);
         dt = pm_max(dt, dtmin_t);
         dt = pm_min(dt, tstop - t);
