@@ -41,8 +41,10 @@ def load(variant: str = "default"):
     if variant in _libs:
         return _libs[variant]
     path = os.path.join(BUILD, _VARIANTS[variant])
-    src = os.path.join(HERE, "picles_oracle.c")
-    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+    csrc = os.path.join(os.path.dirname(HERE), "picles_b200", "csrc")
+    deps = [os.path.join(HERE, "picles_oracle.c"), os.path.join(os.path.dirname(HERE), "include", "picles_b200.h")]
+    deps += [os.path.join(csrc, h) for h in ("pmath.h", "pmath_body.h", "pmath_trig.h", "pmath_dual.h")]
+    if not os.path.exists(path) or any(os.path.getmtime(path) < os.path.getmtime(d) for d in deps):
         build()
     lib = C.CDLL(path)
     vp, d, i64, i32 = C.c_void_p, C.c_double, C.c_int64, C.c_int
