@@ -329,13 +329,13 @@ PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx,
 #endif
     double cbar = O::sqrt_(cx * cx + cy * cy, bad);
     double c_gp = O::div_pre(fabs(cbar), r_g, H.y_rg, bad);
-    double kp = O::div(9.81, 4.0 * pm_max(c_gp * c_gp, 1e-2), bad);
-    double wp = O::div(9.81, 2.0 * pm_max(fabs(c_gp), 0.1), bad);
+    double kp = O::div(9.81, 4.0 * pm_maxc(c_gp * c_gp, 1e-2), bad);
+    double wp = O::div(9.81, 2.0 * pm_maxc(fabs(c_gp), 0.1), bad);
     double gx = O::divz_pre(cx, r_g, H.y_rg, bad), gy = O::divz_pre(cy, r_g, H.y_rg, bad);
     double a1 = O::div(us, 2.0 * c_gp, bad); /* α_func(us, c_gp) */
     double alpha = (a1 > 500.0) ? 500.0 : a1;
     double sg = O::sqrt_(gx * gx + gy * gy, bad);
-    double msg = pm_max(sg, 1e-4);
+    double msg = pm_maxc(sg, 1e-4);
     double alpha_p = O::div(u * gx + v * gy, 2.0 * (msg * msg), bad);
     double Hp = 0.5 * (1.0 + O::tanh_(P.p * (alpha_p - 0.85), bad));
     double sch = O::sech(10.0 * (alpha_p - 0.85), bad);
