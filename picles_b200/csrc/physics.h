@@ -178,6 +178,7 @@ struct Hoist {
     double y_rg, y_eT; /* Newton reciprocals of r_g and e_T (fast path only) */
     double us0;        /* sqrt(u0^2+v0^2): the wind speed when the wind does not change over DT */
     bool steady;       /* every time coefficient of the staged wind is zero */
+    bool std_terms;    /* every source term on and n == 2 (the defaults): the right-hand side instantiated without its term switches */
     int nseg;          /* time segments of the staged wind (levels - 1) */
 };
 
@@ -318,9 +319,14 @@ PM_HD void vertex(double e, double mx, double my, Particle& p) {
 /* Straight-line: the term switches and guards are selects, so with O = OpsFast the whole
    evaluation is one basic block and its independent chains (tanh, sech, the two exps,
    the k_p / ω_p divisions) overlap in the FP64 pipe. */
-template <class O>
+template <class O, bool STD>
 PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx, double cy, double u, double v,
                 double us, double pc, double& d0, double& d1, double& d2, unsigned* bad) {
+    /* STD: the caller has checked that all four source terms are on and n == 2 (uniform over the
+       launch), so the switches below fold away; same arithmetic either way */
+    const bool t_input = STD || P.input, t_diss = STD || P.dissipation, t_peak = STD || P.peak_shift,
+               t_dir = STD || P.direction;
+    const double P_n = STD ? 2.0 : P.n;
     double r_g = P.r_g;
 #ifdef PH_HOIST_EXP
     /* independent of the c̄ chain below: issued first so its polynomial overlaps the serial
@@ -340,11 +346,11 @@ PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx,
     double Hp = 0.5 * (1.0 + O::tanh_(P.p * (alpha_p - 0.85), bad));
     double sch = O::sech(10.0 * (alpha_p - 0.85), bad);
     double Dp = 1.0 - 1.25 * (sch * sch);
-    double It = P.input ? P.C_e * Hp * (alpha * alpha) : 0.0;
+    double It = t_input ? P.C_e * Hp * (alpha * alpha) : 0.0;
     double Dt, Scg;
     {
         double r = O::div_pre(kp, P.e_T, H.y_eT, bad), pw;
-        double twon = 2.0 * P.n;
+        double twon = 2.0 * P_n;
         double r2 = r * r;
         pw = (twon == 4.0) ? r2 * r2 : r2;
         if (twon != 4.0 && twon != 2.0) pw = O::pow_(r, twon, bad); /* general q: uniform, cold */
@@ -354,10 +360,10 @@ PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx,
 #else
         double e2 = O::exp_(2.0 * lne, bad);
 #endif
-        double en = (P.n == 2.0) ? e2 : O::exp_(P.n * lne, bad);
-        Dt = P.dissipation ? en * pw : 0.0;
+        double en = (P_n == 2.0) ? e2 : O::exp_(P_n * lne, bad);
+        Dt = t_diss ? en * pw : 0.0;
         double k2 = kp * kp;
-        Scg = P.peak_shift ? P.C_alpha * Dp * (k2 * k2) * e2 : 0.0;
+        Scg = t_peak ? P.C_alpha * Dp * (k2 * k2) * e2 : 0.0;
     }
     double Sdir;
     {
@@ -369,7 +375,7 @@ PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx,
         double s2 = O::div(2.0, den, bad) *
                     (u * v * (2.0 * (gy * gy) - sg * sg) - gx * gy * (2.0 * (v * v) - us * us));
         s2 = zero ? 0.0 : s2;
-        Sdir = P.direction ? a2 * a2 * P.C_varphi * Hp * s2 : 0.0;
+        Sdir = t_dir ? a2 * a2 * P.C_varphi * Hp * s2 : 0.0;
     }
     double Ssph = cx * pc;
     d0 = wp * r_g * Scg + wp * (It - Dt);
@@ -396,6 +402,10 @@ PM_HD void stage_uv(double wu0, double wv0, const Hoist& H, const KS& K, double 
     double sg = (ts - K.ld(KS_WT0)) * K.ld(KS_WIDT);
     int m = H.nseg - 1;
     double pu = K.ld(KS_WCU + m), pv = K.ld(KS_WCV + m);
+    /* two levels (the default): the loop does not run; more levels are rare enough to stay rolled */
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (; m >= 1; m--) {
         double a = sg - (double)m;
         pu = fma(pu, a, K.ld(KS_WCU + m - 1));
@@ -422,10 +432,10 @@ struct D3 { double d0, d1, d2; };
 PM_HD_NOINLINE_DECL D3 f3_cold(const picles_params_t* Pp, double u, double v, double pc, double lne, double cx,
                                double cy) {
     Hoist H;
-    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false; H.nseg = 1;
+    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false; H.std_terms = false; H.nseg = 1;
     double us = sqrt(u * u + v * v);
     D3 r;
-    rhs3<OpsSafe>(*Pp, H, lne, cx, cy, u, v, us, pc, r.d0, r.d1, r.d2, (unsigned*)0);
+    rhs3<OpsSafe, false>(*Pp, H, lne, cx, cy, u, v, us, pc, r.d0, r.d1, r.d2, (unsigned*)0);
     return r;
 }
 
@@ -439,6 +449,11 @@ PM_HD void make_hoist(const picles_params_t& P, double wu0, double wv0, bool ste
     H.y_rg = 0.0; H.y_eT = 0.0;
 #endif
     H.steady = steady;
+#ifdef PH_NO_STD_TERMS /* profiles/: the switch-carrying right-hand side only */
+    H.std_terms = false;
+#else
+    H.std_terms = P.input && P.dissipation && P.peak_shift && P.direction && (P.n == 2.0);
+#endif
     H.nseg = nseg;
     H.us0 = sqrt(wu0 * wu0 + wv0 * wv0);
 }
@@ -450,8 +465,19 @@ PM_HD void f3(const picles_params_t& P, double wu0, double wv0, const Hoist& H, 
 #if defined(__CUDA_ARCH__)
     double u, v, us;
     unsigned bad = 0;
-    stage_wind<OpsFast>(wu0, wv0, H, K, ts, u, v, us, &bad);
-    rhs3<OpsFast>(P, H, lne, cx, cy, u, v, us, pc, d0, d1, d2, &bad);
+#ifndef PH_NO_STEADY_SPLIT
+    /* a wind that does not change over DT (the homogeneous-box configurations): its own copy of the
+       right-hand side, fed from the hoisted values directly — no wind branch at its head */
+    if (H.std_terms && H.steady) {
+        u = wu0; v = wv0;
+        rhs3<OpsFast, true>(P, H, lne, cx, cy, wu0, wv0, H.us0, pc, d0, d1, d2, &bad);
+    } else
+#endif
+    {
+        stage_wind<OpsFast>(wu0, wv0, H, K, ts, u, v, us, &bad);
+        if (H.std_terms) rhs3<OpsFast, true>(P, H, lne, cx, cy, u, v, us, pc, d0, d1, d2, &bad);
+        else rhs3<OpsFast, false>(P, H, lne, cx, cy, u, v, us, pc, d0, d1, d2, &bad);
+    }
     if (bad) { /* rare: denormal/huge/non-finite operands */
         D3 r = f3_cold(&P, u, v, pc, lne, cx, cy);
         d0 = r.d0; d1 = r.d1; d2 = r.d2;
@@ -701,7 +727,7 @@ PM_HD bool stiffness_test(const double* num, const double* den, double dt_next) 
  * enters here (advance_particle).  tstop = p.t + DT of the first entry; attempts accumulates over
  * re-entries.
  */
-template <bool AUTOSW, class KS>
+template <bool AUTOSW, bool TSIT5 = false, class KS>
 PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv0, const Hoist& H, const double* M, double pc,
                      double tstop_in, Particle& p, Tally& c, KS& K, int& as_count, int& attempts_io) {
     if (p.status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE)) return false;
@@ -714,7 +740,15 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
 #endif
     bool switched = false;
     double x6r = 0.0, y6r = 0.0; /* AutoTsit5: running sums of a6j*k_j[3:4], parked in K before the monitor reads them */
-    const Tableau& T = tableau(P.solver);
+    /* TSIT5: the kernel was launched for a solver whose tableau is Tsit5's (uniform over the launch),
+       which has no zero coefficient: the skip tests below fold away and the coefficient addresses
+       are compile-time.  Same arithmetic either way. */
+#if defined(__CUDA_ARCH__)
+    const bool nz = AUTOSW || TSIT5; /* the monitor-carrying kernels run the Tsit5 tableau too */
+#else
+    const bool nz = false; /* the host build serves every solver from one instantiation */
+#endif
+    const Tableau& T = nz ? tableau(PICLES_SOLVER_TSIT5) : tableau(P.solver);
     double t = p.t;
     K.st(KS_TSTOP, tstop_in);
     double u0 = p.u0, u1 = p.u1, u2 = p.u2;
@@ -748,13 +782,13 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
             prop(P, M, n1, n2, kx, ky);
             if (ph < 7) {
                 double a7 = T.a[7][ph];
-                if (a7 != 0.0) { K.st(KS_X7, fma(a7, kx, K.ld(KS_X7))); K.st(KS_Y7, fma(a7, ky, K.ld(KS_Y7))); }
+                if (nz || a7 != 0.0) { K.st(KS_X7, fma(a7, kx, K.ld(KS_X7))); K.st(KS_Y7, fma(a7, ky, K.ld(KS_Y7))); }
             }
             double bs = T.bt[ph];
-            if (bs != 0.0) { K.st(KS_XE, fma(bs, kx, K.ld(KS_XE))); K.st(KS_YE, fma(bs, ky, K.ld(KS_YE))); }
+            if (nz || bs != 0.0) { K.st(KS_XE, fma(bs, kx, K.ld(KS_XE))); K.st(KS_YE, fma(bs, ky, K.ld(KS_YE))); }
             if (autosw && ph < 6) {
                 double a6 = T.a[6][ph];
-                if (a6 != 0.0) { x6r = fma(a6, kx, x6r); y6r = fma(a6, ky, y6r); }
+                if (nz || a6 != 0.0) { x6r = fma(a6, kx, x6r); y6r = fma(a6, ky, y6r); }
             }
             if (ph < 7) {
                 /* argument of stage s = ph+1 >= 3 */
@@ -769,14 +803,14 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
 #endif
                     for (int j = 2; j < s; j++) {
                         double aj = T.a[s][j];
-                        if (aj != 0.0) {
+                        if (nz || aj != 0.0) {
                             i0 = fma(aj, K.get(j, 0), i0); i1 = fma(aj, K.get(j, 1), i1); i2 = fma(aj, K.get(j, 2), i2);
                         }
                     }
                 } else {
                     for (int j = 2; j < s; j++) {
                         double aj = T.a[s][j];
-                        if (aj != 0.0) {
+                        if (nz || aj != 0.0) {
                             i0 = fma(aj, K.get(j, 0), i0); i1 = fma(aj, K.get(j, 1), i1); i2 = fma(aj, K.get(j, 2), i2);
                         }
                     }
@@ -797,12 +831,12 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
 #endif
                 for (int j = 2; j <= 7; j++) {
                     double bj = T.bt[j];
-                    if (bj != 0.0) { e0 = fma(bj, K.get(j, 0), e0); e1 = fma(bj, K.get(j, 1), e1); e2 = fma(bj, K.get(j, 2), e2); }
+                    if (nz || bj != 0.0) { e0 = fma(bj, K.get(j, 0), e0); e1 = fma(bj, K.get(j, 1), e1); e2 = fma(bj, K.get(j, 2), e2); }
                 }
             } else {
                 for (int j = 2; j <= 7; j++) {
                     double bj = T.bt[j];
-                    if (bj != 0.0) { e0 = fma(bj, K.get(j, 0), e0); e1 = fma(bj, K.get(j, 1), e1); e2 = fma(bj, K.get(j, 2), e2); }
+                    if (nz || bj != 0.0) { e0 = fma(bj, K.get(j, 0), e0); e1 = fma(bj, K.get(j, 1), e1); e2 = fma(bj, K.get(j, 2), e2); }
                 }
             }
             StepCtl sc;
@@ -1263,7 +1297,7 @@ PM_HD void advance_finish(const picles_params_t& P, Particle& p, bool on, int ma
  * attempts_out the attempts made, nothing else has been done, and the caller finishes the step
  * with advance_resume() — out of line, so the hot loop here shares no registers with the cold code.
  */
-template <bool AUTOSW, class KS>
+template <bool AUTOSW, bool TSIT5 = false, class KS>
 PM_HD bool advance_particle(const picles_params_t& P, Particle& p, int mask, double DT, double wu0, double wv0,
                             double wu1, double wv1, int nmid, const double* um, const double* vm, const double* M,
                             double pc, Record& rec, Tally& c, KS& K, int& attempts_out) {
@@ -1285,7 +1319,7 @@ PM_HD bool advance_particle(const picles_params_t& P, Particle& p, int mask, dou
                 make_wind(w, nmid, wu0, wv0, wu1, wv1, um, vm, t_start, DT);
                 wind_to_slots(P, w, K, H);
             }
-            const bool switched = integrate<AUTOSW>(P, wu0, wv0, H, M, pc, tstop, p, c, K, as_count, attempts);
+            const bool switched = integrate<AUTOSW, TSIT5>(P, wu0, wv0, H, M, pc, tstop, p, c, K, as_count, attempts);
             if (autosw) {
                 p.as = (int8_t)(as_count + (switched ? PH_AS_STIFF : 0));
                 if (switched && (p.t < tstop)) { attempts_out = attempts; return true; }

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) k_seed(DeviceArrays A, picles_params_t P,
 #else
 #define ADV_BOUNDS __launch_bounds__(ADV_THREADS, ADV_MIN_BLOCKS)
 #endif
-template <bool PER_NODE_M, bool AUTOSW>
+template <bool PER_NODE_M, bool AUTOSW, bool TSIT5 = false>
 __global__ void ADV_BOUNDS
 k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int64_t l_begin, int64_t l_end) {
     /* stage derivatives k_j[0:3], j = 1..7: 21 doubles per thread, one column per thread
@@ -173,7 +173,7 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int6
         um[PH_WIND_SEG_MAX - 1] = 0.0; vm[PH_WIND_SEG_MAX - 1] = 0.0;
         const double t_start = p.t;
         int attempts = 0;
-        const bool pending = advance_particle<AUTOSW>(P, p, A.mask[l], DT, A.u_t[l], A.v_t[l], A.u_t1[l], A.v_t1[l], A.n_mid, um,
+        const bool pending = advance_particle<AUTOSW, TSIT5>(P, p, A.mask[l], DT, A.u_t[l], A.v_t[l], A.u_t1[l], A.v_t1[l], A.n_mid, um,
                                                       vm, M, pc, r, c, K, attempts);
         if (AUTOSW && pending) {
             /* AutoSwitch handed the particle to Rosenbrock23: park the state reached so far; the
@@ -762,7 +762,11 @@ void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, 
             k_advance_resume<false><<<gr, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end);
         }
     } else {
-        if (pn) k_advance<true, false><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+        /* Tsit5 has its own instantiation (compile-time tableau without zero coefficients); DP5 runs the generic one */
+        const bool ts5 = (P.solver == PICLES_SOLVER_TSIT5);
+        if (pn && ts5) k_advance<true, false, true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+        else if (pn) k_advance<true, false><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+        else if (ts5) k_advance<false, false, true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
         else k_advance<false, false><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
     }
 }
