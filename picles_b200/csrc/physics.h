@@ -335,8 +335,10 @@ PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx,
 #endif
     double cbar = O::sqrt_(cx * cx + cy * cy, bad);
     double c_gp = O::div_pre(fabs(cbar), r_g, H.y_rg, bad);
-    double kp = O::div(9.81, 4.0 * pm_maxc(c_gp * c_gp, 1e-2), bad);
-    double wp = O::div(9.81, 2.0 * pm_maxc(fabs(c_gp), 0.1), bad);
+    /* g/(4m) and g/(2m) with the power of two moved into the dividend: the same real quotient,
+       hence the same rounded one (neither can leave the normal range), one multiplication less each */
+    double kp = O::div(9.81 / 4.0, pm_maxc(c_gp * c_gp, 1e-2), bad);
+    double wp = O::div(9.81 / 2.0, pm_maxc(fabs(c_gp), 0.1), bad);
     double gx = O::divz_pre(cx, r_g, H.y_rg, bad), gy = O::divz_pre(cy, r_g, H.y_rg, bad);
     double a1 = O::div(us, 2.0 * c_gp, bad); /* α_func(us, c_gp) */
     double alpha = (a1 > 500.0) ? 500.0 : a1;
@@ -727,6 +729,11 @@ PM_HD bool stiffness_test(const double* num, const double* den, double dt_next) 
  * enters here (advance_particle).  tstop = p.t + DT of the first entry; attempts accumulates over
  * re-entries.
  */
+#ifdef PH_AUTOSW_UNROLLED /* profiles/: stage sums of the monitor-carrying instantiation unrolled as in the others */
+#define PH_AUTOSW_ROLLED false
+#else
+#define PH_AUTOSW_ROLLED AUTOSW
+#endif
 template <bool AUTOSW, bool TSIT5 = false, class KS>
 PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv0, const Hoist& H, const double* M, double pc,
                      double tstop_in, Particle& p, Tally& c, KS& K, int& as_count, int& attempts_io) {
@@ -795,7 +802,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
                 int s = ++ph;
                 double a1 = T.a[s][1];
                 double i0 = a1 * K.get(1, 0), i1 = a1 * K.get(1, 1), i2 = a1 * K.get(1, 2);
-                if (AUTOSW) {
+                if (PH_AUTOSW_ROLLED) {
                     /* the monitor-carrying loop sits at the edge of the instruction cache (profiles/README.md):
                        the same sums, rolled */
 #if defined(__CUDA_ARCH__)
@@ -825,7 +832,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
             double n3 = fma(dt, K.ld(KS_X7), u3), n4 = fma(dt, K.ld(KS_Y7), u4);
             double b1 = T.bt[1];
             double e0 = b1 * K.get(1, 0), e1 = b1 * K.get(1, 1), e2 = b1 * K.get(1, 2);
-            if (AUTOSW) {
+            if (PH_AUTOSW_ROLLED) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
