@@ -1224,6 +1224,14 @@ int picles_set_wind_mesh(picles_t* h, int nxw, int nyw, int ntw, const double* x
         (rc = wm_alloc_copy(h, &W.V, V, nm)) || (rc = wm_alloc_copy(h, &W.node_x, node_x, n)) ||
         (rc = wm_alloc_copy(h, &W.node_y, node_y, n)))
         return rc;
+    {
+        /* scratch of the two-pass sampler: one time-blended slice per component */
+        void* q = nullptr;
+        const size_t nb = (size_t)nxw * nyw * 16;
+        if (cudaMalloc(&q, nb) != cudaSuccess) return fail(h, PICLES_ERR_ALLOC, "cannot allocate %lld bytes", (long long)nb);
+        h->wm_allocs.push_back(q);
+        W.Ub = (double*)q; W.Vb = W.Ub + (int64_t)nxw * nyw;
+    }
     CK(cudaStreamSynchronize(h->stream));
     h->have_wind_mesh = true;
     return PICLES_OK;

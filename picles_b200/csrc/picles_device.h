@@ -96,6 +96,7 @@ struct DeviceWindMesh {
     int nx, ny, nt;
     double *xw, *yw, *tw, *U, *V;
     double *node_x, *node_y; /* ny*Nx each */
+    double *Ub, *Vb;         /* scratch: the slice blended in time for the level being sampled, nx*ny each */
 };
 void launch_wind_sample(const DeviceWindMesh& W, int64_t n, double t, double* u_out, double* v_out, int sms, cudaStream_t st);
 void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cudaStream_t st);

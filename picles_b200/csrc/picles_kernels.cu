@@ -691,16 +691,28 @@ __global__ void k_selftest_math(uint64_t seed, int iters, unsigned long long* ou
  * One thread per node: 16 B of coordinates in, 16 B of wind out (HBM-bound); the mesh (coarse:
  * knots and 2 x 2 x 2 corner values per component) is served by L1/L2.  The time interval is the
  * same for all nodes and located once per thread from the (tiny) time knot vector. */
-__global__ void __launch_bounds__(256) k_wind_sample(DeviceWindMesh D, int64_t n, double t, double* __restrict__ u_out,
+/* pass 1: the mesh slice at time t (nx*ny points, a few microseconds) */
+__global__ void __launch_bounds__(256) k_wind_timeblend(DeviceWindMesh D, double t) {
+    WindMesh W;
+    W.nx = D.nx; W.ny = D.ny; W.nt = D.nt; W.xw = D.xw; W.yw = D.yw; W.tw = D.tw; W.U = D.U; W.V = D.V;
+    const WindMeshTime T = wm_time(W, t);
+    const int64_t st = (int64_t)D.nx * D.ny;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < st; p += (int64_t)gridDim.x * blockDim.x) {
+        D.Ub[p] = wm_timeblend(D.U, st, T.it, T.dt, p);
+        D.Vb[p] = wm_timeblend(D.V, st, T.it, T.dt, p);
+    }
+}
+/* pass 2: every node */
+__global__ void __launch_bounds__(256) k_wind_sample(DeviceWindMesh D, int64_t n, double* __restrict__ u_out,
                                                      double* __restrict__ v_out) {
     WindMesh W;
-    W.nx = D.nx; W.ny = D.ny; W.nt = D.nt; W.xw = D.xw; W.yw = D.yw; W.tw = D.tw;
-    const WindMeshTime T = wm_time(W, t);
-    /* the time slice is the same for every node: fold it into the base pointers */
-    const int64_t st = (int64_t)D.nx * D.ny;
-    W.U = D.U + st * T.it; W.V = D.V + st * T.it;
-    WindMeshTime T0 = T;
-    T0.it = 0;
+    W.nx = D.nx; W.ny = D.ny; W.nt = D.nt; W.xw = D.xw; W.yw = D.yw; W.tw = D.tw; W.U = D.U; W.V = D.V;
+    WindMeshTime T;
+    T.it = 0; T.dt = 0.0;
+    T.x0 = W.xw[0]; T.x1 = W.xw[W.nx - 1]; T.y0 = W.yw[0]; T.y1 = W.yw[W.ny - 1];
+    T.inv_hx = wm_inv_h(W.xw, W.nx); T.inv_hy = wm_inv_h(W.yw, W.ny);
+    const double* __restrict__ Ub = D.Ub;
+    const double* __restrict__ Vb = D.Vb;
     const double* __restrict__ nx = D.node_x;
     const double* __restrict__ ny = D.node_y;
     /* software pipeline: the coordinates of the next node are in flight (HBM latency) while this
@@ -714,7 +726,7 @@ __global__ void __launch_bounds__(256) k_wind_sample(DeviceWindMesh D, int64_t n
         const int64_t l2 = l + stride;
         if (l2 < n) { xn = __ldcs(nx + l2); yn = __ldcs(ny + l2); }
         double u, v;
-        wm_sample(W, T0, x, y, u, v);
+        wm_sample2d(W, T, Ub, Vb, x, y, u, v);
         __stcs(u_out + l, u);
         __stcs(v_out + l, v);
     }
@@ -788,7 +800,9 @@ void launch_project_remesh(const ProjectMaps& maps, const DeviceArrays& A, const
 }
 
 void launch_wind_sample(const DeviceWindMesh& W, int64_t n, double t, double* u_out, double* v_out, int sms, cudaStream_t st) {
-    if (n > 0) k_wind_sample<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(W, n, t, u_out, v_out);
+    if (n <= 0) return;
+    k_wind_timeblend<<<grid_for((int64_t)W.nx * W.ny, 256, sms, 8), 256, 0, st>>>(W, t);
+    k_wind_sample<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(W, n, u_out, v_out);
 }
 void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cudaStream_t st) {
     k_energy<<<nblocks, 256, 0, st>>>(e, n, partial);

@@ -104,7 +104,19 @@ void shim_wind_mesh_sample(int nx, int ny, int nt, const double* xw, const doubl
     WindMesh W;
     W.nx = nx; W.ny = ny; W.nt = nt; W.xw = xw; W.yw = yw; W.tw = tw; W.U = U; W.V = V;
     const WindMeshTime T = wm_time(W, t);
-    for (int64_t l = 0; l < n; l++) wm_sample(W, T, x[l], y[l], u_out[l], v_out[l]);
+    /* the two passes of the device sampler (k_wind_timeblend, k_wind_sample), checked against the
+       one-pass form on every node */
+    const int64_t st = (int64_t)nx * ny;
+    std::vector<double> Ub(st), Vb(st);
+    for (int64_t p = 0; p < st; p++) { Ub[p] = wm_timeblend(U, st, T.it, T.dt, p); Vb[p] = wm_timeblend(V, st, T.it, T.dt, p); }
+    int rc = 0;
+    for (int64_t l = 0; l < n; l++) {
+        wm_sample2d(W, T, Ub.data(), Vb.data(), x[l], y[l], u_out[l], v_out[l]);
+        double u1, v1;
+        wm_sample(W, T, x[l], y[l], u1, v1);
+        if (memcmp(&u1, &u_out[l], 8) != 0 || memcmp(&v1, &v_out[l], 8) != 0) rc = 1; /* the two forms must agree bit for bit */
+    }
+    if (rc) { for (int64_t l = 0; l < n; l++) u_out[l] = v_out[l] = NAN; }
 }
 
 void shim_seed(Shim* h, const double* u0, const double* v0) {
