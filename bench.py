@@ -34,7 +34,7 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the 4096^2 bench step, from the
 # committed ncu --set full captures (profiles/r01_ncu_final.txt); never measured under the timer
 NCU_TRAFFIC = {"k_advance": 3.61e9, "k_project_remesh": 1.80e9, "k_wind_sample": 0.49e9}
-NCU_FP64_PIPE_PCT = 57.6  # sm__pipe_fp64_cycles_active of k_advance (profiles/r01_ncu_final.txt)
+NCU_FP64_PIPE_PCT = 60.1  # sm__pipe_fp64_cycles_active of k_advance (profiles/r01_ncu_final.txt)
 
 METRIC = "particle-steps/s"
 UNIT = "particle-steps/s"
@@ -42,7 +42,7 @@ UNIT = "particle-steps/s"
 # Algorithmic FP64 work (DESIGN.md §advance kernel): source-level operation counts of
 # physics.h with fma = 2, add/mul/compare-select = 1, div = sqrt = 8, exp = 30,
 # tanh = sech = log = 35, pow = 70 flop.
-F_RHS = 331          # one right-hand side (rhs3 + prop + wind interpolation)
+F_RHS = 329          # one right-hand side (rhs3 + prop + wind interpolation)
 F_ATTEMPT = 511      # one RK attempt minus its 6 RHS: stage sums, error norm, PI controller
 F_INITDT = 319       # Hairer initial step minus its RHS
 F_DEPOSIT = 105      # charge + weights of the deposit record
@@ -472,7 +472,8 @@ def main():
                                  "d2h_bytes_per_step": e2e["d2h"] if e2e else 0, "ms_per_step": ms_mesh_all / args.steps,
                                  "api": "picles_step_wind_mesh (wind sampled on the device from a resident wind mesh) "
                                         "+ picles_state_energy_sum"}
-        line["roofline_hbm"].append({"kernel": "k_wind_sample", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+        line["roofline_hbm"].append({"kernel": "k_wind_sample", "note": "k_wind_timeblend (mesh-sized, ~3 us) + k_wind_sample, timed as a pair",
+                                     "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
                                      "unit": "GB/s", "frac": gbs / hbm_peak,
                                      "traffic": NCU_TRAFFIC.get("k_wind_sample") if std_size else None, "bytes_per_node": 32,
                                      "nodes_per_launch": n_nodes, "ms_per_launch": e2e_mesh["ms_sample"],
