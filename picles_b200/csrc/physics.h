@@ -469,8 +469,12 @@ PM_HD void f3(const picles_params_t& P, double wu0, double wv0, const Hoist& H, 
     unsigned bad = 0;
 #ifndef PH_NO_STEADY_SPLIT
     /* a wind that does not change over DT (the homogeneous-box configurations): its own copy of the
-       right-hand side, fed from the hoisted values directly — no wind branch at its head */
-    if (H.std_terms && H.steady) {
+       right-hand side, fed from the hoisted values directly — no wind branch at its head.  Taken
+       only when every lane of the warp that is here is steady (a vote, so the choice never splits
+       a warp; a lane that votes yes is steady itself): a field that is constant up to rounding noise (a
+       constant wind mesh sampled at the nodes) mixes steady and unsteady lanes, and a split warp
+       would run both copies */
+    if (H.std_terms && __all_sync(__activemask(), H.steady)) {
         u = wu0; v = wv0;
         rhs3<OpsFast, true>(P, H, lne, cx, cy, wu0, wv0, H.us0, pc, d0, d1, d2, &bad);
     } else
