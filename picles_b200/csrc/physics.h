@@ -51,6 +51,12 @@
 
 namespace picles {
 
+#if !defined(__CUDACC__)
+/* tests/host_shim.cpp only: run the specialised copies (switch-free right-hand side, Tsit5
+   instantiation) on the host where the kernels would pick them, so the CPU suite covers them */
+inline int ph_host_specialised = 0;
+#endif
+
 /* ---- tableaus (OrdinaryDiffEq Tsit5ConstantCache / DP5ConstantCache) ----- */
 /* a[s][j]: weight of k_j in the argument of stage s (s = 2..7, j = 1..s-1; row 7 = b);
    c[s-1]: time fraction of stage s; bt[j]: error weights (btilde). */
@@ -491,6 +497,12 @@ PM_HD void f3(const picles_params_t& P, double wu0, double wv0, const Hoist& H, 
 #else
     double u = wu0, v = wv0;
     if (!H.steady) stage_uv(wu0, wv0, H, K, ts, u, v);
+#if !defined(__CUDACC__) /* tests/: the host build takes the switch-free copy where the kernels do */
+    if (ph_host_specialised && H.std_terms) {
+        rhs3<OpsSafe, true>(P, H, lne, cx, cy, u, v, sqrt(u * u + v * v), pc, d0, d1, d2, (unsigned*)0);
+        return;
+    }
+#endif
     D3 r = f3_cold(&P, u, v, pc, lne, cx, cy);
     d0 = r.d0; d1 = r.d1; d2 = r.d2;
 #endif
@@ -757,7 +769,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
 #if defined(__CUDA_ARCH__)
     const bool nz = AUTOSW || TSIT5; /* the monitor-carrying kernels run the Tsit5 tableau too */
 #else
-    const bool nz = false; /* the host build serves every solver from one instantiation */
+    const bool nz = TSIT5; /* the host build serves every solver from one AUTOSW instantiation; TSIT5 only when asked (tests) */
 #endif
     const Tableau& T = nz ? tableau(PICLES_SOLVER_TSIT5) : tableau(P.solver);
     double t = p.t;

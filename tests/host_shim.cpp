@@ -90,6 +90,9 @@ Shim* shim_create(int Nx, int Ny, int bx, int by, int nstrips, int halo, const u
 }
 void shim_destroy(Shim* h) { delete h; }
 void shim_set_accumulate(Shim* h, int on) { h->accumulate = on ? 1 : 0; }
+/* process-wide: take the specialised code paths (physics.h: ph_host_specialised) */
+void shim_set_specialised(int on) { ph_host_specialised = on ? 1 : 0; }
+int shim_get_specialised() { return ph_host_specialised; }
 /* n_mid planes with the extent of the wind arrays of the next step call (global for shim_step,
    strip-local for shim_strip_advance) */
 void shim_set_wind_midlevels(Shim* h, int n_mid, const double* u_mid, const double* v_mid, int64_t plane) {
@@ -158,8 +161,13 @@ static void shim_advance_all(Shim* h, double DT, const double* u_t, const double
             }
             const double t_start = p.t;
             int attempts = 0;
-            const bool pending = advance_particle<true>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l],
-                                                        v_t1[off + l], h->n_mid, um, vm, M, pc, r, c, K, attempts);
+            /* as launch_advance picks the kernel: Tsit5 has its own instantiation */
+            const bool pending = (ph_host_specialised && h->P.solver == PICLES_SOLVER_TSIT5)
+                ? advance_particle<false, true>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l],
+                                                v_t1[off + l], h->n_mid, um, vm, M, pc, r, c, K, attempts)
+                : advance_particle<true>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l],
+                                         v_t1[off + l], h->n_mid, um, vm, M, pc, r, c, K, attempts);
+
             if (pending) { /* as the kernel: the stiff part of the step runs through advance_resume */
                 ResumeArgs R;
                 R.mask = s.mask[l]; R.nmid = h->n_mid; R.attempts = attempts;

@@ -14,6 +14,22 @@ def test_single_strip_bit_exact(name):
     run_pair(make_oracle(g, P), HostShim(g, P), wind, DT, n, compare_models)
 
 
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_specialised_copies_bit_exact(name):
+    """The copies the kernels pick per launch — the right-hand side without its term switches
+    (every term on, n = 2), the Tsit5 instantiation with its compile-time tableau and no
+    zero-coefficient tests — give the oracle's bits too (host build with the same choices)."""
+    from common import shim_lib
+    lib = shim_lib()
+    lib.shim_set_specialised(1)
+    try:
+        assert lib.shim_get_specialised() == 1
+        g, P, wind, DT, n = SCENARIOS[name]()
+        run_pair(make_oracle(g, P), HostShim(g, P), wind, DT, n, compare_models)
+    finally:
+        lib.shim_set_specialised(0)
+
+
 @pytest.mark.parametrize("name,nstrips,halo", [
     ("minimal", 2, 2), ("minimal", 3, 1), ("periodic_grid", 2, 5), ("periodic_grid", 4, 5),
     ("land_block", 3, 2), ("tripolar", 2, 8), ("tripolar", 3, 6), ("growing_winds", 2, 2),
