@@ -344,9 +344,21 @@ PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx,
     /* g/(4m) and g/(2m) with the power of two moved into the dividend: the same real quotient,
        hence the same rounded one (neither can leave the normal range), one multiplication less each */
     double kp = O::div(9.81 / 4.0, pm_maxc(c_gp * c_gp, 1e-2), bad);
+#ifdef PH_SHARE_RCP /* profiles/: omega_p and alpha divide by the same number whenever |c_gp| > 0.1 — one reciprocal */
+    const double m_wp = pm_maxc(fabs(c_gp), 0.1);
+    const double d_wp = 2.0 * m_wp, d_a1 = 2.0 * c_gp;
+    const double y_wp = O::prep(d_wp);
+    /* 9.81/(2m): the quotient by d_wp = 2m is the same real number as (9.81/2)/m */
+    double wp = O::div_pre(9.81, d_wp, y_wp, bad);
+    double gx = O::divz_pre(cx, r_g, H.y_rg, bad), gy = O::divz_pre(cy, r_g, H.y_rg, bad);
+    double a1;
+    if (d_a1 == d_wp) a1 = O::div_pre(us, d_a1, y_wp, bad); /* same divisor bits: same Newton reciprocal */
+    else a1 = O::div(us, d_a1, bad);
+#else
     double wp = O::div(9.81 / 2.0, pm_maxc(fabs(c_gp), 0.1), bad);
     double gx = O::divz_pre(cx, r_g, H.y_rg, bad), gy = O::divz_pre(cy, r_g, H.y_rg, bad);
     double a1 = O::div(us, 2.0 * c_gp, bad); /* α_func(us, c_gp) */
+#endif
     double alpha = (a1 > 500.0) ? 500.0 : a1;
     double sg = O::sqrt_(gx * gx + gy * gy, bad);
     double msg = pm_maxc(sg, 1e-4);
@@ -745,6 +757,21 @@ PM_HD bool stiffness_test(const double* num, const double* den, double dt_next) 
  * enters here (advance_particle).  tstop = p.t + DT of the first entry; attempts accumulates over
  * re-entries.
  */
+/* sum_{j<S} a[S][j]*k_j of one stage with a compile-time stage number (profiles/ variant
+   PH_STAGE_SWITCH): ascending j, one fma per term — the arithmetic of the loop in integrate() */
+template <int S, class KS>
+PM_HD void stage_sum_ct(const Tableau& T, const KS& K, double& i0, double& i1, double& i2) {
+    const double a1 = T.a[S][1];
+    i0 = a1 * K.get(1, 0); i1 = a1 * K.get(1, 1); i2 = a1 * K.get(1, 2);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 2; j < S; j++) {
+        const double aj = T.a[S][j];
+        i0 = fma(aj, K.get(j, 0), i0); i1 = fma(aj, K.get(j, 1), i1); i2 = fma(aj, K.get(j, 2), i2);
+    }
+}
+
 #ifdef PH_AUTOSW_UNROLLED /* profiles/: stage sums of the monitor-carrying instantiation unrolled as in the others */
 #define PH_AUTOSW_ROLLED false
 #else
@@ -818,6 +845,17 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
                 int s = ++ph;
                 double a1 = T.a[s][1];
                 double i0 = a1 * K.get(1, 0), i1 = a1 * K.get(1, 1), i2 = a1 * K.get(1, 2);
+#ifdef PH_STAGE_SWITCH /* profiles/: one straight-line sum per stage (tableaus without zero coefficients only) */
+                if (nz && !PH_AUTOSW_ROLLED) {
+                    switch (s) {
+                    case 3: stage_sum_ct<3>(T, K, i0, i1, i2); break;
+                    case 4: stage_sum_ct<4>(T, K, i0, i1, i2); break;
+                    case 5: stage_sum_ct<5>(T, K, i0, i1, i2); break;
+                    case 6: stage_sum_ct<6>(T, K, i0, i1, i2); break;
+                    default: stage_sum_ct<7>(T, K, i0, i1, i2); break;
+                    }
+                } else
+#endif
                 if (PH_AUTOSW_ROLLED) {
                     /* the monitor-carrying loop sits at the edge of the instruction cache (profiles/README.md):
                        the same sums, rolled */
