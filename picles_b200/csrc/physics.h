@@ -184,6 +184,7 @@ struct Hoist {
     double y_rg, y_eT; /* Newton reciprocals of r_g and e_T (fast path only) */
     double us0;        /* sqrt(u0^2+v0^2): the wind speed when the wind does not change over DT */
     bool steady;       /* every time coefficient of the staged wind is zero */
+    double uv, tvu;    /* u*v and 2*(v*v) - us*us of a steady wind (profiles/ variant PH_HOIST_SDIR) */
     bool std_terms;    /* every source term on and n == 2 (the defaults): the right-hand side instantiated without its term switches */
     int nseg;          /* time segments of the staged wind (levels - 1) */
 };
@@ -325,7 +326,7 @@ PM_HD void vertex(double e, double mx, double my, Particle& p) {
 /* Straight-line: the term switches and guards are selects, so with O = OpsFast the whole
    evaluation is one basic block and its independent chains (tanh, sech, the two exps,
    the k_p / ω_p divisions) overlap in the FP64 pipe. */
-template <class O, bool STD>
+template <class O, bool STD, bool HW = false>
 PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx, double cy, double u, double v,
                 double us, double pc, double& d0, double& d1, double& d2, unsigned* bad) {
     /* STD: the caller has checked that all four source terms are on and n == 2 (uniform over the
@@ -392,8 +393,14 @@ PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx,
         double prod = us * sg;
         bool zero = (prod == 0.0);
         double den = zero ? 1.0 : prod * prod;
+#ifdef PH_HOIST_SDIR
+        /* HW: the wind-only factors come hoisted (steady wind; the same products, formed once) */
+        const double uv = HW ? H.uv : u * v, tvu = HW ? H.tvu : 2.0 * (v * v) - us * us;
+        double s2 = O::div(2.0, den, bad) * (uv * (2.0 * (gy * gy) - sg * sg) - gx * gy * tvu);
+#else
         double s2 = O::div(2.0, den, bad) *
                     (u * v * (2.0 * (gy * gy) - sg * sg) - gx * gy * (2.0 * (v * v) - us * us));
+#endif
         s2 = zero ? 0.0 : s2;
         Sdir = t_dir ? a2 * a2 * P.C_varphi * Hp * s2 : 0.0;
     }
@@ -452,7 +459,7 @@ struct D3 { double d0, d1, d2; };
 PM_HD_NOINLINE_DECL D3 f3_cold(const picles_params_t* Pp, double u, double v, double pc, double lne, double cx,
                                double cy) {
     Hoist H;
-    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false; H.std_terms = false; H.nseg = 1;
+    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false; H.std_terms = false; H.nseg = 1; H.uv = 0.0; H.tvu = 0.0;
     double us = sqrt(u * u + v * v);
     D3 r;
     rhs3<OpsSafe, false>(*Pp, H, lne, cx, cy, u, v, us, pc, r.d0, r.d1, r.d2, (unsigned*)0);
@@ -476,6 +483,12 @@ PM_HD void make_hoist(const picles_params_t& P, double wu0, double wv0, bool ste
 #endif
     H.nseg = nseg;
     H.us0 = sqrt(wu0 * wu0 + wv0 * wv0);
+#ifdef PH_HOIST_SDIR
+    H.uv = wu0 * wv0;
+    H.tvu = 2.0 * (wv0 * wv0) - H.us0 * H.us0;
+#else
+    H.uv = 0.0; H.tvu = 0.0;
+#endif
 }
 
 /* hot right-hand side of the stage loop */
@@ -494,7 +507,11 @@ PM_HD void f3(const picles_params_t& P, double wu0, double wv0, const Hoist& H, 
        would run both copies */
     if (H.std_terms && __all_sync(__activemask(), H.steady)) {
         u = wu0; v = wv0;
+#ifdef PH_HOIST_SDIR
+        rhs3<OpsFast, true, true>(P, H, lne, cx, cy, wu0, wv0, H.us0, pc, d0, d1, d2, &bad);
+#else
         rhs3<OpsFast, true>(P, H, lne, cx, cy, wu0, wv0, H.us0, pc, d0, d1, d2, &bad);
+#endif
     } else
 #endif
     {
@@ -511,6 +528,9 @@ PM_HD void f3(const picles_params_t& P, double wu0, double wv0, const Hoist& H, 
     if (!H.steady) stage_uv(wu0, wv0, H, K, ts, u, v);
 #if !defined(__CUDACC__) /* tests/: the host build takes the switch-free copy where the kernels do */
     if (ph_host_specialised && H.std_terms) {
+#ifdef PH_HOIST_SDIR
+        if (H.steady) { rhs3<OpsSafe, true, true>(P, H, lne, cx, cy, wu0, wv0, H.us0, pc, d0, d1, d2, (unsigned*)0); return; }
+#endif
         rhs3<OpsSafe, true>(P, H, lne, cx, cy, u, v, sqrt(u * u + v * v), pc, d0, d1, d2, (unsigned*)0);
         return;
     }
@@ -817,7 +837,16 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
 
     int ph = 1;
     double n0 = u0, n1 = u1, n2 = u2, ts = t; /* argument of the next right-hand side */
-    K.st(KS_X7, 0.0); K.st(KS_Y7, 0.0); K.st(KS_XE, 0.0); K.st(KS_YE, 0.0); K.st(KS_DT0, 0.0); K.st(KS_D1N, 0.0);
+#ifdef PH_REG_SUMS /* profiles/: the four running sums of the propagation components in registers, not in scratch slots */
+    double x7s = 0.0, y7s = 0.0, xes = 0.0, yes = 0.0;
+#define PH_SUM_LD(slot, r) (r)
+#define PH_SUM_ST(slot, r, v) ((r) = (v))
+#else
+#define PH_SUM_LD(slot, r) K.ld(slot)
+#define PH_SUM_ST(slot, r, v) K.st(slot, v)
+#endif
+    PH_SUM_ST(KS_X7, x7s, 0.0); PH_SUM_ST(KS_Y7, y7s, 0.0); PH_SUM_ST(KS_XE, xes, 0.0); PH_SUM_ST(KS_YE, yes, 0.0);
+    K.st(KS_DT0, 0.0); K.st(KS_D1N, 0.0);
     K.st(KS_DTMIN, pm_max(pm_eps(t), P.dtmin)); /* max(eps(t), dtmin): kept current on every accepted step */
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -832,10 +861,10 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
             prop(P, M, n1, n2, kx, ky);
             if (ph < 7) {
                 double a7 = T.a[7][ph];
-                if (nz || a7 != 0.0) { K.st(KS_X7, fma(a7, kx, K.ld(KS_X7))); K.st(KS_Y7, fma(a7, ky, K.ld(KS_Y7))); }
+                if (nz || a7 != 0.0) { PH_SUM_ST(KS_X7, x7s, fma(a7, kx, PH_SUM_LD(KS_X7, x7s))); PH_SUM_ST(KS_Y7, y7s, fma(a7, ky, PH_SUM_LD(KS_Y7, y7s))); }
             }
             double bs = T.bt[ph];
-            if (nz || bs != 0.0) { K.st(KS_XE, fma(bs, kx, K.ld(KS_XE))); K.st(KS_YE, fma(bs, ky, K.ld(KS_YE))); }
+            if (nz || bs != 0.0) { PH_SUM_ST(KS_XE, xes, fma(bs, kx, PH_SUM_LD(KS_XE, xes))); PH_SUM_ST(KS_YE, yes, fma(bs, ky, PH_SUM_LD(KS_YE, yes))); }
             if (autosw && ph < 6) {
                 double a6 = T.a[6][ph];
                 if (nz || a6 != 0.0) { x6r = fma(a6, kx, x6r); y6r = fma(a6, ky, y6r); }
@@ -883,7 +912,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
             }
             /* all seven stages done: (n0,n1,n2) is u_new */
             const double u3 = K.ld(KS_U3), u4 = K.ld(KS_U4);
-            double n3 = fma(dt, K.ld(KS_X7), u3), n4 = fma(dt, K.ld(KS_Y7), u4);
+            double n3 = fma(dt, PH_SUM_LD(KS_X7, x7s), u3), n4 = fma(dt, PH_SUM_LD(KS_Y7, y7s), u4);
             double b1 = T.bt[1];
             double e0 = b1 * K.get(1, 0), e1 = b1 * K.get(1, 1), e2 = b1 * K.get(1, 2);
             if (PH_AUTOSW_ROLLED) {
@@ -901,7 +930,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
                 }
             }
             StepCtl sc;
-            const double xe = K.ld(KS_XE), ye = K.ld(KS_YE), lq = K.ld(KS_LQ);
+            const double xe = PH_SUM_LD(KS_XE, xes), ye = PH_SUM_LD(KS_YE, yes), lq = K.ld(KS_LQ);
 #if defined(__CUDA_ARCH__)
             unsigned bad = 0;
             step_control<OpsFast>(P, T, dt, e0, e1, e2, xe, ye, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, lq, sc, &bad);
@@ -1018,8 +1047,8 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
         {
             double kx, ky;
             prop(P, M, u1, u2, kx, ky);
-            K.st(KS_X7, T.a[7][1] * kx); K.st(KS_Y7, T.a[7][1] * ky);
-            K.st(KS_XE, T.bt[1] * kx); K.st(KS_YE, T.bt[1] * ky);
+            PH_SUM_ST(KS_X7, x7s, T.a[7][1] * kx); PH_SUM_ST(KS_Y7, y7s, T.a[7][1] * ky);
+            PH_SUM_ST(KS_XE, xes, T.bt[1] * kx); PH_SUM_ST(KS_YE, yes, T.bt[1] * ky);
             if (autosw) { x6r = T.a[6][1] * kx; y6r = T.a[6][1] * ky; }
             double a = dt * T.a[2][1];
             n0 = fma(a, K.get(1, 0), u0); n1 = fma(a, K.get(1, 1), u1); n2 = fma(a, K.get(1, 2), u2);
@@ -1034,6 +1063,8 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
     if (autosw) as_count = (int)K.ld(KS_AS);
     return switched;
 }
+#undef PH_SUM_LD
+#undef PH_SUM_ST
 
 /* ---- ParticleInCell ------------------------------------------------------- */
 /* get_absolute_i_and_w(zp, i_node): floor offset and ceil-side weight */

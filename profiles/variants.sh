@@ -13,7 +13,9 @@ declare -A V=(
   [base]=""
   [stage_switch]="-DPH_STAGE_SWITCH"        # one straight-line stage sum per stage behind a switch (Tsit5 instantiation)
   [share_rcp]="-DPH_SHARE_RCP"              # omega_p and alpha share the Newton reciprocal of 2*c_gp
-  [both]="-DPH_STAGE_SWITCH -DPH_SHARE_RCP"
+  [reg_sums]="-DPH_REG_SUMS"                # running sums of the propagation components in registers instead of scratch slots
+  [hoist_sdir]="-DPH_HOIST_SDIR"            # wind-only factors of S_dir hoisted in the steady copy
+  [all4]="-DPH_STAGE_SWITCH -DPH_SHARE_RCP -DPH_REG_SUMS -DPH_HOIST_SDIR"
   [no_std]="-DPH_NO_STD_TERMS"              # the switch-carrying right-hand side only (what the specialisation buys)
   [no_steady_split]="-DPH_NO_STEADY_SPLIT"  # no separate copy for steady winds
   [autosw_unrolled]="-DPH_AUTOSW_UNROLLED"  # AutoTsit5 instantiation with unrolled stage sums
@@ -31,7 +33,7 @@ PY
   done ;;
 time)
   shift
-  names=("$@"); [ ${#names[@]} -eq 0 ] && names=(base stage_switch share_rcp both base)
+  names=("$@"); [ ${#names[@]} -eq 0 ] && names=(base stage_switch share_rcp reg_sums hoist_sdir all4 base)
   mkdir -p gpurun_out
   for n in "${names[@]}"; do
     PICLES_B200_LIB=$PWD/_exp/lib_$n.so python profiles/${PROF:-prof_step.py} 4096 12 > gpurun_out/variant_$n.log 2>&1

@@ -396,7 +396,7 @@ int64_t shim_corner_target(int Nx, int Ny, int bx, int by, int64_t i, int64_t j)
 }
 void shim_rhs(const picles_params_t* P, const double* z, double u, double v, const double* M, double pc, double* dz) {
     Hoist H;
-    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false; H.std_terms = false;
+    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false; H.std_terms = false; H.uv = 0.0; H.tvu = 0.0;
     rhs3<OpsSafe, false>(*P, H, z[0], z[1], z[2], u, v, sqrt(u * u + v * v), pc, dz[0], dz[1], dz[2], (unsigned*)0);
     prop(*P, M, z[1], z[2], dz[3], dz[4]);
 }
