@@ -688,9 +688,10 @@ __global__ void k_selftest_math(uint64_t seed, int iters, unsigned long long* ou
 }
 
 /* ---- wind ingestion: sample the resident wind mesh at the nodes ---------------------------
- * One thread per node: 16 B of coordinates in, 16 B of wind out (HBM-bound); the mesh (coarse:
- * knots and 2 x 2 x 2 corner values per component) is served by L1/L2.  The time interval is the
- * same for all nodes and located once per thread from the (tiny) time knot vector. */
+ * Two passes per level (wind_mesh.h).  The time interval and weight are the same for every node,
+ * so the blend in time is done once per mesh point (k_wind_timeblend, mesh-sized); k_wind_sample
+ * then runs one thread per node — 16 B of coordinates in, 16 B of wind out (HBM-bound) — on that
+ * slice: knots and 2 x 2 corner values per component, served by L1/L2. */
 /* pass 1: the mesh slice at time t (nx*ny points, a few microseconds) */
 __global__ void __launch_bounds__(256) k_wind_timeblend(DeviceWindMesh D, double t) {
     WindMesh W;
