@@ -797,7 +797,7 @@ PM_HD void stage_sum_ct(const Tableau& T, const KS& K, double& i0, double& i1, d
 #else
 #define PH_AUTOSW_ROLLED AUTOSW
 #endif
-template <bool AUTOSW, bool TSIT5 = false, class KS>
+template <bool AUTOSW, int TSIT5 = 0, class KS>
 PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv0, const Hoist& H, const double* M, double pc,
                      double tstop_in, Particle& p, Tally& c, KS& K, int& as_count, int& attempts_io) {
     if (p.status & (PICLES_PST_MAXITERS | PICLES_PST_DTMIN | PICLES_PST_UNSTABLE)) return false;
@@ -814,11 +814,15 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
        which has no zero coefficient: the skip tests below fold away and the coefficient addresses
        are compile-time.  Same arithmetic either way. */
 #if defined(__CUDA_ARCH__)
-    const bool nz = AUTOSW || TSIT5; /* the monitor-carrying kernels run the Tsit5 tableau too */
+    const bool nz = AUTOSW || TSIT5 == 1; /* the monitor-carrying kernels run the Tsit5 tableau too */
 #else
-    const bool nz = TSIT5; /* the host build serves every solver from one AUTOSW instantiation; TSIT5 only when asked (tests) */
+    const bool nz = TSIT5 == 1; /* the host build serves every solver from one AUTOSW instantiation; TSIT5 only when asked (tests) */
 #endif
-    const Tableau& T = nz ? tableau(PICLES_SOLVER_TSIT5) : tableau(P.solver);
+    /* TSIT5 == 2 (profiles/ variant PH_DP5_CT): DP5's tableau at compile time; its two zero coefficients,
+       a[7][2] and bt[2], are tested where they are and nowhere else */
+    const bool dz = !nz && TSIT5 == 2;
+    const Tableau& T = nz ? tableau(PICLES_SOLVER_TSIT5) : (dz ? tableau(PICLES_SOLVER_DP5) : tableau(P.solver));
+#define PH_COEF_ON(c, can_be_zero) (nz || (dz && !(can_be_zero)) || (c) != 0.0)
     double t = p.t;
     K.st(KS_TSTOP, tstop_in);
     double u0 = p.u0, u1 = p.u1, u2 = p.u2;
@@ -861,13 +865,13 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
             prop(P, M, n1, n2, kx, ky);
             if (ph < 7) {
                 double a7 = T.a[7][ph];
-                if (nz || a7 != 0.0) { PH_SUM_ST(KS_X7, x7s, fma(a7, kx, PH_SUM_LD(KS_X7, x7s))); PH_SUM_ST(KS_Y7, y7s, fma(a7, ky, PH_SUM_LD(KS_Y7, y7s))); }
+                if (PH_COEF_ON(a7, ph == 2)) { PH_SUM_ST(KS_X7, x7s, fma(a7, kx, PH_SUM_LD(KS_X7, x7s))); PH_SUM_ST(KS_Y7, y7s, fma(a7, ky, PH_SUM_LD(KS_Y7, y7s))); }
             }
             double bs = T.bt[ph];
-            if (nz || bs != 0.0) { PH_SUM_ST(KS_XE, xes, fma(bs, kx, PH_SUM_LD(KS_XE, xes))); PH_SUM_ST(KS_YE, yes, fma(bs, ky, PH_SUM_LD(KS_YE, yes))); }
+            if (PH_COEF_ON(bs, ph == 2)) { PH_SUM_ST(KS_XE, xes, fma(bs, kx, PH_SUM_LD(KS_XE, xes))); PH_SUM_ST(KS_YE, yes, fma(bs, ky, PH_SUM_LD(KS_YE, yes))); }
             if (autosw && ph < 6) {
                 double a6 = T.a[6][ph];
-                if (nz || a6 != 0.0) { x6r = fma(a6, kx, x6r); y6r = fma(a6, ky, y6r); }
+                if (PH_COEF_ON(a6, false)) { x6r = fma(a6, kx, x6r); y6r = fma(a6, ky, y6r); }
             }
             if (ph < 7) {
                 /* argument of stage s = ph+1 >= 3 */
@@ -893,14 +897,14 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
 #endif
                     for (int j = 2; j < s; j++) {
                         double aj = T.a[s][j];
-                        if (nz || aj != 0.0) {
+                        if (PH_COEF_ON(aj, s == 7 && j == 2)) {
                             i0 = fma(aj, K.get(j, 0), i0); i1 = fma(aj, K.get(j, 1), i1); i2 = fma(aj, K.get(j, 2), i2);
                         }
                     }
                 } else {
                     for (int j = 2; j < s; j++) {
                         double aj = T.a[s][j];
-                        if (nz || aj != 0.0) {
+                        if (PH_COEF_ON(aj, s == 7 && j == 2)) {
                             i0 = fma(aj, K.get(j, 0), i0); i1 = fma(aj, K.get(j, 1), i1); i2 = fma(aj, K.get(j, 2), i2);
                         }
                     }
@@ -921,12 +925,12 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
 #endif
                 for (int j = 2; j <= 7; j++) {
                     double bj = T.bt[j];
-                    if (nz || bj != 0.0) { e0 = fma(bj, K.get(j, 0), e0); e1 = fma(bj, K.get(j, 1), e1); e2 = fma(bj, K.get(j, 2), e2); }
+                    if (PH_COEF_ON(bj, j == 2)) { e0 = fma(bj, K.get(j, 0), e0); e1 = fma(bj, K.get(j, 1), e1); e2 = fma(bj, K.get(j, 2), e2); }
                 }
             } else {
                 for (int j = 2; j <= 7; j++) {
                     double bj = T.bt[j];
-                    if (nz || bj != 0.0) { e0 = fma(bj, K.get(j, 0), e0); e1 = fma(bj, K.get(j, 1), e1); e2 = fma(bj, K.get(j, 2), e2); }
+                    if (PH_COEF_ON(bj, j == 2)) { e0 = fma(bj, K.get(j, 0), e0); e1 = fma(bj, K.get(j, 1), e1); e2 = fma(bj, K.get(j, 2), e2); }
                 }
             }
             StepCtl sc;
@@ -1065,6 +1069,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
 }
 #undef PH_SUM_LD
 #undef PH_SUM_ST
+#undef PH_COEF_ON
 
 /* ---- ParticleInCell ------------------------------------------------------- */
 /* get_absolute_i_and_w(zp, i_node): floor offset and ceil-side weight */
@@ -1389,7 +1394,7 @@ PM_HD void advance_finish(const picles_params_t& P, Particle& p, bool on, int ma
  * attempts_out the attempts made, nothing else has been done, and the caller finishes the step
  * with advance_resume() — out of line, so the hot loop here shares no registers with the cold code.
  */
-template <bool AUTOSW, bool TSIT5 = false, class KS>
+template <bool AUTOSW, int TSIT5 = 0, class KS>
 PM_HD bool advance_particle(const picles_params_t& P, Particle& p, int mask, double DT, double wu0, double wv0,
                             double wu1, double wv1, int nmid, const double* um, const double* vm, const double* M,
                             double pc, Record& rec, Tally& c, KS& K, int& attempts_out) {

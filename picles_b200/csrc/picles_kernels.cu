@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) k_seed(DeviceArrays A, picles_params_t P,
 #else
 #define ADV_BOUNDS __launch_bounds__(ADV_THREADS, ADV_MIN_BLOCKS)
 #endif
-template <bool PER_NODE_M, bool AUTOSW, bool TSIT5 = false>
+template <bool PER_NODE_M, bool AUTOSW, int TSIT5 = 0>
 __global__ void ADV_BOUNDS
 k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int64_t l_begin, int64_t l_end) {
     /* stage derivatives k_j[0:3], j = 1..7: 21 doubles per thread, one column per thread
@@ -780,6 +780,9 @@ void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, 
         if (pn && ts5) k_advance<true, false, true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
         else if (pn) k_advance<true, false><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
         else if (ts5) k_advance<false, false, true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+#ifdef PH_DP5_CT /* profiles/: DP5 with its own instantiation too */
+        else if (P.solver == PICLES_SOLVER_DP5) k_advance<false, false, 2><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+#endif
         else k_advance<false, false><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
     }
 }

@@ -165,6 +165,11 @@ static void shim_advance_all(Shim* h, double DT, const double* u_t, const double
             const bool pending = (ph_host_specialised && h->P.solver == PICLES_SOLVER_TSIT5)
                 ? advance_particle<false, true>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l],
                                                 v_t1[off + l], h->n_mid, um, vm, M, pc, r, c, K, attempts)
+#ifdef PH_DP5_CT
+                : (ph_host_specialised && h->P.solver == PICLES_SOLVER_DP5)
+                ? advance_particle<false, 2>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l],
+                                             v_t1[off + l], h->n_mid, um, vm, M, pc, r, c, K, attempts)
+#endif
                 : advance_particle<true>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l],
                                          v_t1[off + l], h->n_mid, um, vm, M, pc, r, c, K, attempts);
 
