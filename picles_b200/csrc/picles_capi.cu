@@ -587,6 +587,20 @@ static int advance_range(picles_t* h, double dt_model, const double* u_t, const 
                          const double* v_t1, int r0, int r1) {
     const int64_t n = (int64_t)(r1 - r0) * h->A.Nx;
     const int nch = ((u_t || u_t1) && n >= PIPE_MIN_NODES) ? PIPE_CHUNKS : 1;
+    /* profiles/ (PICLES_PIPE_FIRST_ROWS=k): graded blocks — k rows first, each next block three times the one
+       before (an upload takes about a third of the advance of the same rows, so it still hides), the last
+       takes the rest.  Only the first block's upload is exposed: the smaller it is, the less of it shows. */
+    static const int first_rows = [] { const char* e = getenv("PICLES_PIPE_FIRST_ROWS"); return e ? atoi(e) : 0; }();
+    if (nch > 1 && first_rows > 0) {
+        int a = r0, len = first_rows;
+        for (int c = 0; c < PIPE_CHUNKS && a < r1; c++) {
+            const int b = (c == PIPE_CHUNKS - 1 || a + len >= r1) ? r1 : a + len;
+            int rc = advance_rows(h, dt_model, u_t, v_t, u_t1, v_t1, a, b, h->pev[c]);
+            if (rc) return rc;
+            a = b; len *= 3;
+        }
+        return PICLES_OK;
+    }
     const int rows = (r1 - r0 + nch - 1) / nch;
     for (int c = 0; c < nch; c++) {
         const int a = r0 + c * rows, b = (a + rows < r1) ? a + rows : r1;
