@@ -733,6 +733,46 @@ __global__ void __launch_bounds__(256) k_wind_sample(DeviceWindMesh D, int64_t n
     }
 }
 
+#ifdef PH_WIND_ROW4
+/* profiles/ variant: one thread per four consecutive nodes (wm_sample2d_x4: the y lookup shared along a
+   row), 16-byte loads and stores; the launcher falls back to k_wind_sample when a plane is not
+   16-byte aligned, and a scalar tail takes the last n % 4 nodes */
+__global__ void __launch_bounds__(256) k_wind_sample_x4(DeviceWindMesh D, int64_t n, double* __restrict__ u_out,
+                                                        double* __restrict__ v_out) {
+    WindMesh W;
+    W.nx = D.nx; W.ny = D.ny; W.nt = D.nt; W.xw = D.xw; W.yw = D.yw; W.tw = D.tw; W.U = D.U; W.V = D.V;
+    WindMeshTime T;
+    T.it = 0; T.dt = 0.0;
+    T.x0 = W.xw[0]; T.x1 = W.xw[W.nx - 1]; T.y0 = W.yw[0]; T.y1 = W.yw[W.ny - 1];
+    T.inv_hx = wm_inv_h(W.xw, W.nx); T.inv_hy = wm_inv_h(W.yw, W.ny);
+    const double* __restrict__ Ub = D.Ub;
+    const double* __restrict__ Vb = D.Vb;
+    const double2* __restrict__ nx2 = (const double2*)D.node_x;
+    const double2* __restrict__ ny2 = (const double2*)D.node_y;
+    const int64_t n4 = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double2 xa = {0, 0}, xb = {0, 0}, ya = {0, 0}, yb = {0, 0};
+    if (g < n4) { xa = __ldcs(nx2 + 2 * g); xb = __ldcs(nx2 + 2 * g + 1); ya = __ldcs(ny2 + 2 * g); yb = __ldcs(ny2 + 2 * g + 1); }
+    for (; g < n4; g += stride) {
+        const double x[4] = {xa.x, xa.y, xb.x, xb.y}, y[4] = {ya.x, ya.y, yb.x, yb.y};
+        const int64_t g2 = g + stride;
+        if (g2 < n4) { xa = __ldcs(nx2 + 2 * g2); xb = __ldcs(nx2 + 2 * g2 + 1); ya = __ldcs(ny2 + 2 * g2); yb = __ldcs(ny2 + 2 * g2 + 1); }
+        double u[4], v[4];
+        wm_sample2d_x4(W, T, Ub, Vb, x, y, u, v);
+        __stcs((double2*)u_out + 2 * g, make_double2(u[0], u[1])); __stcs((double2*)u_out + 2 * g + 1, make_double2(u[2], u[3]));
+        __stcs((double2*)v_out + 2 * g, make_double2(v[0], v[1])); __stcs((double2*)v_out + 2 * g + 1, make_double2(v[2], v[3]));
+    }
+    /* tail */
+    const int64_t l = 4 * n4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (l < n) {
+        double u, v;
+        wm_sample2d(W, T, Ub, Vb, D.node_x[l], D.node_y[l], u, v);
+        u_out[l] = u; v_out[l] = v;
+    }
+}
+#endif
+
 /* ---- launchers ------------------------------------------------------------------ */
 static int grid_for(int64_t n, int threads, int sms, int blocks_per_sm) {
     int64_t need = (n + threads - 1) / threads;
@@ -806,6 +846,12 @@ void launch_project_remesh(const ProjectMaps& maps, const DeviceArrays& A, const
 void launch_wind_sample(const DeviceWindMesh& W, int64_t n, double t, double* u_out, double* v_out, int sms, cudaStream_t st) {
     if (n <= 0) return;
     k_wind_timeblend<<<grid_for((int64_t)W.nx * W.ny, 256, sms, 8), 256, 0, st>>>(W, t);
+#ifdef PH_WIND_ROW4
+    if (n >= 4 && (((uintptr_t)W.node_x | (uintptr_t)W.node_y | (uintptr_t)u_out | (uintptr_t)v_out) & 15) == 0) {
+        k_wind_sample_x4<<<grid_for(n >> 2, 256, sms, 8), 256, 0, st>>>(W, n, u_out, v_out);
+        return;
+    }
+#endif
     k_wind_sample<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(W, n, u_out, v_out);
 }
 void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cudaStream_t st) {

@@ -16,6 +16,7 @@ declare -A V=(
   [reg_sums]="-DPH_REG_SUMS"                # running sums of the propagation components in registers instead of scratch slots
   [hoist_sdir]="-DPH_HOIST_SDIR"            # wind-only factors of S_dir hoisted in the steady copy
   [dp5_ct]="-DPH_DP5_CT"                    # DP5 (bench06 settings) with a compile-time tableau: time with PROF=prof_step_dp5.py
+  [wind_row4]="-DPH_WIND_ROW4"              # wind sampler: four nodes per thread, y lookup shared along a row; time with profiles/prof_wind.py
   [all4]="-DPH_STAGE_SWITCH -DPH_SHARE_RCP -DPH_REG_SUMS -DPH_HOIST_SDIR"
   [no_std]="-DPH_NO_STD_TERMS"              # the switch-carrying right-hand side only (what the specialisation buys)
   [no_steady_split]="-DPH_NO_STEADY_SPLIT"  # no separate copy for steady winds

@@ -119,6 +119,12 @@ void shim_wind_mesh_sample(int nx, int ny, int nt, const double* xw, const doubl
         wm_sample(W, T, x[l], y[l], u1, v1);
         if (memcmp(&u1, &u_out[l], 8) != 0 || memcmp(&v1, &v_out[l], 8) != 0) rc = 1; /* the two forms must agree bit for bit */
     }
+    /* ... and the four-nodes-at-once form (shared y lookup along a row) */
+    for (int64_t l = 0; l + 4 <= n; l += 4) {
+        double u4[4], v4[4];
+        wm_sample2d_x4(W, T, Ub.data(), Vb.data(), x + l, y + l, u4, v4);
+        if (memcmp(u4, u_out + l, 32) != 0 || memcmp(v4, v_out + l, 32) != 0) rc = 1;
+    }
     if (rc) { for (int64_t l = 0; l < n; l++) u_out[l] = v_out[l] = NAN; }
 }
 

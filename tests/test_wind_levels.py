@@ -179,6 +179,13 @@ def test_wind_mesh_sampler_matches_oracle_bitwise():
         uo, vo = oracle.wind_mesh_sample(xw, yw, tw, U, V, x, y, t)
         us, vs = shim_sample(xw, yw, tw, U, V, x, y, t)
         assert bits_equal(uo, us) and bits_equal(vo, vs)
+    # a regular node grid: the nodes of a row share y (what the four-nodes-at-once form of the device
+    # sampler reuses); rows of 37 nodes, so groups of four also straddle row ends
+    gx, gy = np.meshgrid(np.linspace(xw[0] - 5000.0, xw[-1] + 9000.0, 37), np.linspace(yw[0] - 700.0, yw[-1] + 700.0, 11))
+    for t in (0.0, 50000.5):
+        uo, vo = oracle.wind_mesh_sample(xw, yw, tw, U, V, gx.ravel(), gy.ravel(), t)
+        us, vs = shim_sample(xw, yw, tw, U, V, gx.ravel(), gy.ravel(), t)
+        assert bits_equal(uo, us) and bits_equal(vo, vs)
 
 
 def test_wind_mesh_sampler_against_scipy():
