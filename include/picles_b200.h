@@ -386,8 +386,9 @@ int picles_measure_fp64_peak(picles_t* h, double* tflops);
    out6 = {n_div, flagged_div, mismatch_div, n_sqrt, flagged_sqrt, mismatch_sqrt};
    a mismatch is an unflagged result that differs from a/b or sqrt(x): must be 0. */
 int picles_selftest_math(picles_t* h, uint64_t seed, int iters, int64_t* out6);
-/* CUDA-event time per launch of the wind-mesh sampling kernel over this strip (mean of `reps`
-   launches): 32 algorithmic bytes per node (coordinates in, wind out) against the HBM roofline */
+/* CUDA-event time per level of the wind-mesh sampling over this strip — the mesh-sized time blend
+   plus the per-node kernel, as one step launches them (mean of `reps` repetitions): 32 algorithmic
+   bytes per node (coordinates in, wind out) against the HBM roofline */
 int picles_measure_wind_sample(picles_t* h, double t, int reps, double* ms_per_launch);
 /* measured HBM copy bandwidth (read+write bytes / s) over a buffer of `mib` MiB */
 int picles_measure_hbm_copy(picles_t* h, int mib, double* gbs);
