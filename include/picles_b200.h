@@ -279,6 +279,20 @@ int picles_comm_unique_id(char* id128, const char* nccl_path);
 int picles_comm_init(picles_t* h, const char* id128, int rank, int nranks, const char* nccl_path);
 int picles_comm_destroy(picles_t* h);
 int picles_halo_exchange(picles_t* h, int lo_rank, int hi_rank);
+/*
+ * How many rows travel.  The `halo` of picles_set_grid* is the number of rows exchanged to begin with;
+ * the record planes of a strip hold room for rows_max = min(15, ny_local), the widest window the gather
+ * supports.  The reference enforces no CFL limit (ParticleInCell.jl:58-71), so a step may deposit further
+ * than the rows exchanged: the gather then changes nothing and
+ *   - picles_step_strip widens the exchange to the all-reduced reach (ncclAllReduce(max), 4 bytes) on every
+ *     strip and repeats exchange + gather by itself (the advance is not repeated);
+ *   - picles_step_project_remesh (host-driven exchange) returns PICLES_ERR_HALO naming the rows needed:
+ *     call picles_halo_widen on every strip, repeat the exchange and the call.  A host that all-reduces
+ *     picles_get_reach itself widens before the exchange and never sees the error.
+ * The exchange is never narrowed again.  A reach beyond rows_max is a PICLES_ERR_HALO that stands.
+ */
+int picles_halo_rows(picles_t* h, int* rows_exchanged, int* rows_max);
+int picles_halo_widen(picles_t* h, int rows);
 int picles_step_strip(picles_t* h, double t, double dt_model,
                       const double* u_t, const double* v_t,
                       const double* u_t1, const double* v_t1,
@@ -322,6 +336,12 @@ int picles_set_state(picles_t* h, const double* S);
 int picles_get_particles(picles_t* h, double* z /* 5 planes of ny_local*Nx */,
                          double* t, double* dt, uint8_t* flags, int32_t* status);
 int picles_get_counters(picles_t* h, picles_counters_t* c);
+/* the particles that integrated in the last step, by the number of Runge-Kutta attempts (accepted + rejected
+   substeps, both algorithms under AutoTsit5) they took: hist[a] for a < nbins - 1, the rest in the last bin.
+   The work per particle-step is data-dependent; this is its distribution. */
+int picles_get_attempt_histogram(picles_t* h, int64_t* hist, int nbins);
+/* kernels launched by this library in this process so far (every entry point counts the kernels it launches) */
+int64_t picles_launch_count(void);
 /* AutoSwitch state of every particle (ny_local*Nx): the signed run length of the stiffness test
    (positive: consecutive stiff attempts, negative: non-stiff), +64 when Rosenbrock23 is current */
 int picles_get_solver_state(picles_t* h, int8_t* as);

@@ -111,6 +111,12 @@ typedef struct oracle {
        stage time (particle_waves_v5.jl:489-495); x, y = grid.data.x / grid.data.y */
     void (*wind_fn)(double x, double y, double t, double* u, double* v);
     double *x, *y;
+    /* B-1 as run (on_persist == 0): a particle seeded off never integrates, so its integrator clock
+       stays at 0 and advance! tests the wind at t_end = integ.t + DT = DT on EVERY step
+       (mapping_2D.jl:132,172-176).  With staged winds that level is the first step's t+DT level:
+       kept here.  (The closure mode simply calls the closure at p->t + DT.) */
+    int64_t steps_since_seed;
+    double *u_lag, *v_lag;
 } oracle_t;
 
 /* ------------------------------------------------------------------------ */
@@ -835,6 +841,7 @@ void oracle_destroy(oracle_t* o) {
     if (!o) return;
     free(o->mask); free(o->M); free(o->pc); free(o->part); free(o->ocean); free(o->S);
     free(o->u_mid); free(o->v_mid); free(o->x); free(o->y);
+    free(o->u_lag); free(o->v_lag);
     free(o);
 }
 
@@ -902,6 +909,9 @@ void oracle_seed(oracle_t* o, const double* u0, const double* v0) {
         p->t = 0.0; p->dt = P->dt; p->qold = QOLDINIT; p->iter = 0;
     }
     for (int64_t m = 0; m < o->n_ocean; m++) o->part[o->ocean[m]].active = 1;
+    o->steps_since_seed = 0;
+    free(o->u_lag); free(o->v_lag);
+    o->u_lag = o->v_lag = NULL;
 }
 
 static inline void node_M(const oracle_t* o, int64_t l, double* M) {
@@ -917,6 +927,18 @@ static int advance_particle(oracle_t* o, int64_t l, double DT, const double* u_t
     particle_t* p = &o->part[l];
     double t_start = p->t; /* :132 */
     int on = p->on;
+    /* winds.u/v(x, y, t_start) and (x, y, t_start + DT) of THIS particle (:173-176, :201-204, :214-216).
+       The integrator clock of a particle that integrates every step is the model clock: the staged
+       t / t+DT levels.  One that never integrates (seeded off, `on` frozen: B-1 as run) keeps
+       t_start = 0, so its t_end is DT for ever: the level kept from the first step.  (Its t_start
+       level is only read by the Inf fix-up, which a reseed from a finite wind cannot reach.) */
+    double wu_start = u_t[l], wv_start = v_t[l], wu_end = u_t1[l], wv_end = v_t1[l];
+    if (o->wind_fn) {
+        o->wind_fn(o->x[l], o->y[l], t_start, &wu_start, &wv_start);
+        o->wind_fn(o->x[l], o->y[l], t_start + DT, &wu_end, &wv_end);
+    } else if (!on && !P->on_persist && o->u_lag) {
+        wu_end = o->u_lag[l]; wv_end = o->v_lag[l];
+    }
     if (on) { /* :149-170 */
         double M[4];
         node_M(o, l, M);
@@ -935,10 +957,9 @@ static int advance_particle(oracle_t* o, int64_t l, double DT, const double* u_t
         c.t_start = t_start; c.inv_DT = 1.0 / DT;
         c.x = o->x ? o->x[l] : 0.0; c.y = o->y ? o->y[l] : 0.0;
         integrate(o, p, &c, DT, C, &o->stiff_triggers);
-    } else { /* :172-185: wind at t_start+DT == the staged t1 level */
-        double wu = u_t1[l], wv = v_t1[l];
-        if (wu * wu + wv * wv >= P->wind_min_squared) {
-            reset_particle_values(P, wu, wv, DT, p->u);
+    } else { /* :172-185: wind at t_end = t_start + DT, t_start = the particle's own integrator clock */
+        if (wu_end * wu_end + wv_end * wv_end >= P->wind_min_squared) {
+            reset_particle_values(P, wu_end, wv_end, DT, p->u);
             p->dt_reset = 1; /* reset_PI_u!, :91-96 */
             on = 1;
             C->n_reseed_advance++;
@@ -948,10 +969,10 @@ static int advance_particle(oracle_t* o, int64_t l, double DT, const double* u_t
     int anynan = (p->u[0] != p->u[0]) | (p->u[1] != p->u[1]) | (p->u[2] != p->u[2]);
     int anyinf = pm_isinf(p->u[0]) | pm_isinf(p->u[1]) | pm_isinf(p->u[2]);
     if (anynan) {
-        reset_particle_values(P, u_t1[l], v_t1[l], DT, p->u); /* wind at t_end */
+        reset_particle_values(P, wu_end, wv_end, DT, p->u); /* wind at t_end */
         p->dt_reset = 1; p->status |= PICLES_PST_NAN_RESET; C->n_fixups++;
     } else if (anyinf) {
-        reset_particle_values(P, u_t[l], v_t[l], DT, p->u); /* wind at t_start */
+        reset_particle_values(P, wu_start, wv_start, DT, p->u); /* wind at t_start */
         p->dt_reset = 1; p->status |= PICLES_PST_INF_RESET; C->n_fixups++;
     } else if (p->u[0] > P->log_energy_maximum) {
         p->u[0] = P->log_energy_maximum;
@@ -1003,6 +1024,13 @@ void oracle_step(oracle_t* o, double t, double DT, const double* u_t, const doub
     (void)t;
     int64_t n = (int64_t)o->Nx * o->Ny;
     if (!o->accumulate) memset(o->S, 0, 3 * n * sizeof(double)); /* run.jl:75-79 */
+    if (!o->P.on_persist && o->steps_since_seed == 0 && !o->wind_fn) {
+        /* the level at integrator time 0 + DT, read on every later step by the particles seeded off */
+        free(o->u_lag); free(o->v_lag);
+        o->u_lag = (double*)malloc(n * sizeof(double)); memcpy(o->u_lag, u_t1, n * sizeof(double));
+        o->v_lag = (double*)malloc(n * sizeof(double)); memcpy(o->v_lag, v_t1, n * sizeof(double));
+    }
+    o->steps_since_seed++;
     picles_counters_t C;
     memset(&C, 0, sizeof C);
     C.n_active = o->n_ocean;

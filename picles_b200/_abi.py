@@ -115,6 +115,10 @@ SYMBOLS = {
     "picles_make_boundaries": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "picles_set_params": (C.c_int, [_vp, C.POINTER(PiclesParams)]),
     "picles_seed": (C.c_int, [_vp, _vp, _vp]),
+    "picles_halo_rows": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "picles_halo_widen": (C.c_int, [_vp, C.c_int]),
+    "picles_get_attempt_histogram": (C.c_int, [_vp, _vp, C.c_int]),
+    "picles_launch_count": (C.c_int64, []),
     "picles_step": (C.c_int, [_vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp]),
     "picles_upload_winds": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "picles_set_wind_midlevels": (C.c_int, [_vp, C.c_int, _vp, _vp]),

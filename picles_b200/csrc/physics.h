@@ -114,7 +114,7 @@ PM_HD const Tableau& tableau(int solver) {
    words: conflict-free), so the registers go to the right-hand side; a local array on the
    host. */
 enum {
-    KS_U3 = 21, KS_U4, KS_X7, KS_Y7, KS_XE, KS_YE, KS_TSTOP, KS_LQ, KS_QOLD, KS_DT0, KS_D1N, KS_DTMIN,
+    KS_U3 = 21, KS_U4, KS_TSTOP, KS_LQ, KS_QOLD, KS_DT0, KS_D1N, KS_DTMIN,
     KS_WT0, KS_WIDT,
     KS_G60, KS_G61, /* AutoTsit5 monitor: argument of stage 6, components 0 and 1 (component 2: KS_DT0, idle during attempts) */
     KS_AS,        /* AutoTsit5: AutoSwitch run length (as a double; +PH_AS_STIFF once switched) */
@@ -184,7 +184,6 @@ struct Hoist {
     double y_rg, y_eT; /* Newton reciprocals of r_g and e_T (fast path only) */
     double us0;        /* sqrt(u0^2+v0^2): the wind speed when the wind does not change over DT */
     bool steady;       /* every time coefficient of the staged wind is zero */
-    double uv, tvu;    /* u*v and 2*(v*v) - us*us of a steady wind (profiles/ variant PH_HOIST_SDIR) */
     bool std_terms;    /* every source term on and n == 2 (the defaults): the right-hand side instantiated without its term switches */
     int nseg;          /* time segments of the staged wind (levels - 1) */
 };
@@ -326,7 +325,7 @@ PM_HD void vertex(double e, double mx, double my, Particle& p) {
 /* Straight-line: the term switches and guards are selects, so with O = OpsFast the whole
    evaluation is one basic block and its independent chains (tanh, sech, the two exps,
    the k_p / ω_p divisions) overlap in the FP64 pipe. */
-template <class O, bool STD, bool HW = false>
+template <class O, bool STD>
 PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx, double cy, double u, double v,
                 double us, double pc, double& d0, double& d1, double& d2, unsigned* bad) {
     /* STD: the caller has checked that all four source terms are on and n == 2 (uniform over the
@@ -335,31 +334,14 @@ PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx,
                t_dir = STD || P.direction;
     const double P_n = STD ? 2.0 : P.n;
     double r_g = P.r_g;
-#ifdef PH_HOIST_EXP
-    /* independent of the c̄ chain below: issued first so its polynomial overlaps the serial
-       sqrt -> div -> div head of the evaluation */
-    double e2_early = O::exp_(2.0 * lne, bad);
-#endif
     double cbar = O::sqrt_(cx * cx + cy * cy, bad);
     double c_gp = O::div_pre(fabs(cbar), r_g, H.y_rg, bad);
     /* g/(4m) and g/(2m) with the power of two moved into the dividend: the same real quotient,
        hence the same rounded one (neither can leave the normal range), one multiplication less each */
     double kp = O::div(9.81 / 4.0, pm_maxc(c_gp * c_gp, 1e-2), bad);
-#ifdef PH_SHARE_RCP /* profiles/: omega_p and alpha divide by the same number whenever |c_gp| > 0.1 — one reciprocal */
-    const double m_wp = pm_maxc(fabs(c_gp), 0.1);
-    const double d_wp = 2.0 * m_wp, d_a1 = 2.0 * c_gp;
-    const double y_wp = O::prep(d_wp);
-    /* 9.81/(2m): the quotient by d_wp = 2m is the same real number as (9.81/2)/m */
-    double wp = O::div_pre(9.81, d_wp, y_wp, bad);
-    double gx = O::divz_pre(cx, r_g, H.y_rg, bad), gy = O::divz_pre(cy, r_g, H.y_rg, bad);
-    double a1;
-    if (d_a1 == d_wp) a1 = O::div_pre(us, d_a1, y_wp, bad); /* same divisor bits: same Newton reciprocal */
-    else a1 = O::div(us, d_a1, bad);
-#else
     double wp = O::div(9.81 / 2.0, pm_maxc(fabs(c_gp), 0.1), bad);
     double gx = O::divz_pre(cx, r_g, H.y_rg, bad), gy = O::divz_pre(cy, r_g, H.y_rg, bad);
     double a1 = O::div(us, 2.0 * c_gp, bad); /* α_func(us, c_gp) */
-#endif
     double alpha = (a1 > 500.0) ? 500.0 : a1;
     double sg = O::sqrt_(gx * gx + gy * gy, bad);
     double msg = pm_maxc(sg, 1e-4);
@@ -376,11 +358,7 @@ PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx,
         pw = (twon == 4.0) ? r2 * r2 : r2;
         if (twon != 4.0 && twon != 2.0) pw = O::pow_(r, twon, bad); /* general q: uniform, cold */
         /* n == 2 (q = -1/4): exp(n*lne) and exp(2*lne) are the same evaluation */
-#ifdef PH_HOIST_EXP
-        double e2 = e2_early;
-#else
         double e2 = O::exp_(2.0 * lne, bad);
-#endif
         double en = (P_n == 2.0) ? e2 : O::exp_(P_n * lne, bad);
         Dt = t_diss ? en * pw : 0.0;
         double k2 = kp * kp;
@@ -393,14 +371,8 @@ PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx,
         double prod = us * sg;
         bool zero = (prod == 0.0);
         double den = zero ? 1.0 : prod * prod;
-#ifdef PH_HOIST_SDIR
-        /* HW: the wind-only factors come hoisted (steady wind; the same products, formed once) */
-        const double uv = HW ? H.uv : u * v, tvu = HW ? H.tvu : 2.0 * (v * v) - us * us;
-        double s2 = O::div(2.0, den, bad) * (uv * (2.0 * (gy * gy) - sg * sg) - gx * gy * tvu);
-#else
         double s2 = O::div(2.0, den, bad) *
                     (u * v * (2.0 * (gy * gy) - sg * sg) - gx * gy * (2.0 * (v * v) - us * us));
-#endif
         s2 = zero ? 0.0 : s2;
         Sdir = t_dir ? a2 * a2 * P.C_varphi * Hp * s2 : 0.0;
     }
@@ -459,7 +431,7 @@ struct D3 { double d0, d1, d2; };
 PM_HD_NOINLINE_DECL D3 f3_cold(const picles_params_t* Pp, double u, double v, double pc, double lne, double cx,
                                double cy) {
     Hoist H;
-    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false; H.std_terms = false; H.nseg = 1; H.uv = 0.0; H.tvu = 0.0;
+    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false; H.std_terms = false; H.nseg = 1;
     double us = sqrt(u * u + v * v);
     D3 r;
     rhs3<OpsSafe, false>(*Pp, H, lne, cx, cy, u, v, us, pc, r.d0, r.d1, r.d2, (unsigned*)0);
@@ -476,19 +448,10 @@ PM_HD void make_hoist(const picles_params_t& P, double wu0, double wv0, bool ste
     H.y_rg = 0.0; H.y_eT = 0.0;
 #endif
     H.steady = steady;
-#ifdef PH_NO_STD_TERMS /* profiles/: the switch-carrying right-hand side only */
-    H.std_terms = false;
-#else
     H.std_terms = P.input && P.dissipation && P.peak_shift && P.direction && (P.n == 2.0);
-#endif
     H.nseg = nseg;
     H.us0 = sqrt(wu0 * wu0 + wv0 * wv0);
-#ifdef PH_HOIST_SDIR
-    H.uv = wu0 * wv0;
-    H.tvu = 2.0 * (wv0 * wv0) - H.us0 * H.us0;
-#else
-    H.uv = 0.0; H.tvu = 0.0;
-#endif
+   
 }
 
 /* hot right-hand side of the stage loop */
@@ -498,7 +461,6 @@ PM_HD void f3(const picles_params_t& P, double wu0, double wv0, const Hoist& H, 
 #if defined(__CUDA_ARCH__)
     double u, v, us;
     unsigned bad = 0;
-#ifndef PH_NO_STEADY_SPLIT
     /* a wind that does not change over DT (the homogeneous-box configurations): its own copy of the
        right-hand side, fed from the hoisted values directly — no wind branch at its head.  Taken
        only when every lane of the warp that is here is steady (a vote, so the choice never splits
@@ -507,14 +469,8 @@ PM_HD void f3(const picles_params_t& P, double wu0, double wv0, const Hoist& H, 
        would run both copies */
     if (H.std_terms && __all_sync(__activemask(), H.steady)) {
         u = wu0; v = wv0;
-#ifdef PH_HOIST_SDIR
-        rhs3<OpsFast, true, true>(P, H, lne, cx, cy, wu0, wv0, H.us0, pc, d0, d1, d2, &bad);
-#else
         rhs3<OpsFast, true>(P, H, lne, cx, cy, wu0, wv0, H.us0, pc, d0, d1, d2, &bad);
-#endif
-    } else
-#endif
-    {
+    } else {
         stage_wind<OpsFast>(wu0, wv0, H, K, ts, u, v, us, &bad);
         if (H.std_terms) rhs3<OpsFast, true>(P, H, lne, cx, cy, u, v, us, pc, d0, d1, d2, &bad);
         else rhs3<OpsFast, false>(P, H, lne, cx, cy, u, v, us, pc, d0, d1, d2, &bad);
@@ -528,9 +484,6 @@ PM_HD void f3(const picles_params_t& P, double wu0, double wv0, const Hoist& H, 
     if (!H.steady) stage_uv(wu0, wv0, H, K, ts, u, v);
 #if !defined(__CUDACC__) /* tests/: the host build takes the switch-free copy where the kernels do */
     if (ph_host_specialised && H.std_terms) {
-#ifdef PH_HOIST_SDIR
-        if (H.steady) { rhs3<OpsSafe, true, true>(P, H, lne, cx, cy, wu0, wv0, H.us0, pc, d0, d1, d2, (unsigned*)0); return; }
-#endif
         rhs3<OpsSafe, true>(P, H, lne, cx, cy, u, v, sqrt(u * u + v * v), pc, d0, d1, d2, (unsigned*)0);
         return;
     }
@@ -747,9 +700,6 @@ PM_HD bool stiffness_test(const double* num, const double* den, double dt_next) 
         any_stiff = any_stiff | stiff | xz;
         any_nan = any_nan | zz;
     }
-#ifdef PH_COUNT_EXACT
-    g_tests++; if (!all_decided) g_exact++;
-#endif
     if (all_decided) return any_stiff & !any_nan;
     return stiffness_test_exact(num[0], num[1], num[2], num[3], num[4], den[0], den[1], den[2], den[3], den[4], dt_next);
 }
@@ -777,26 +727,7 @@ PM_HD bool stiffness_test(const double* num, const double* den, double dt_next) 
  * enters here (advance_particle).  tstop = p.t + DT of the first entry; attempts accumulates over
  * re-entries.
  */
-/* sum_{j<S} a[S][j]*k_j of one stage with a compile-time stage number (profiles/ variant
-   PH_STAGE_SWITCH): ascending j, one fma per term — the arithmetic of the loop in integrate() */
-template <int S, class KS>
-PM_HD void stage_sum_ct(const Tableau& T, const KS& K, double& i0, double& i1, double& i2) {
-    const double a1 = T.a[S][1];
-    i0 = a1 * K.get(1, 0); i1 = a1 * K.get(1, 1); i2 = a1 * K.get(1, 2);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 2; j < S; j++) {
-        const double aj = T.a[S][j];
-        i0 = fma(aj, K.get(j, 0), i0); i1 = fma(aj, K.get(j, 1), i1); i2 = fma(aj, K.get(j, 2), i2);
-    }
-}
-
-#ifdef PH_AUTOSW_UNROLLED /* profiles/: stage sums of the monitor-carrying instantiation unrolled as in the others */
-#define PH_AUTOSW_ROLLED false
-#else
-#define PH_AUTOSW_ROLLED AUTOSW
-#endif
+#define PH_AUTOSW_ROLLED AUTOSW /* unrolled there too: 17.58 -> 17.77 ms (profiles/README.md) */
 template <bool AUTOSW, int TSIT5 = 0, class KS>
 PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv0, const Hoist& H, const double* M, double pc,
                      double tstop_in, Particle& p, Tally& c, KS& K, int& as_count, int& attempts_io) {
@@ -841,15 +772,9 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
 
     int ph = 1;
     double n0 = u0, n1 = u1, n2 = u2, ts = t; /* argument of the next right-hand side */
-#ifdef PH_REG_SUMS /* profiles/: the four running sums of the propagation components in registers, not in scratch slots */
+    /* running sums of the propagation components of stage 7 and of the error estimate: registers (in scratch
+       slots: +1.7 % time, profiles/README.md) */
     double x7s = 0.0, y7s = 0.0, xes = 0.0, yes = 0.0;
-#define PH_SUM_LD(slot, r) (r)
-#define PH_SUM_ST(slot, r, v) ((r) = (v))
-#else
-#define PH_SUM_LD(slot, r) K.ld(slot)
-#define PH_SUM_ST(slot, r, v) K.st(slot, v)
-#endif
-    PH_SUM_ST(KS_X7, x7s, 0.0); PH_SUM_ST(KS_Y7, y7s, 0.0); PH_SUM_ST(KS_XE, xes, 0.0); PH_SUM_ST(KS_YE, yes, 0.0);
     K.st(KS_DT0, 0.0); K.st(KS_D1N, 0.0);
     K.st(KS_DTMIN, pm_max(pm_eps(t), P.dtmin)); /* max(eps(t), dtmin): kept current on every accepted step */
 #if defined(__CUDA_ARCH__)
@@ -865,10 +790,10 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
             prop(P, M, n1, n2, kx, ky);
             if (ph < 7) {
                 double a7 = T.a[7][ph];
-                if (PH_COEF_ON(a7, ph == 2)) { PH_SUM_ST(KS_X7, x7s, fma(a7, kx, PH_SUM_LD(KS_X7, x7s))); PH_SUM_ST(KS_Y7, y7s, fma(a7, ky, PH_SUM_LD(KS_Y7, y7s))); }
+                if (PH_COEF_ON(a7, ph == 2)) { x7s = fma(a7, kx, x7s); y7s = fma(a7, ky, y7s); }
             }
             double bs = T.bt[ph];
-            if (PH_COEF_ON(bs, ph == 2)) { PH_SUM_ST(KS_XE, xes, fma(bs, kx, PH_SUM_LD(KS_XE, xes))); PH_SUM_ST(KS_YE, yes, fma(bs, ky, PH_SUM_LD(KS_YE, yes))); }
+            if (PH_COEF_ON(bs, ph == 2)) { xes = fma(bs, kx, xes); yes = fma(bs, ky, yes); }
             if (autosw && ph < 6) {
                 double a6 = T.a[6][ph];
                 if (PH_COEF_ON(a6, false)) { x6r = fma(a6, kx, x6r); y6r = fma(a6, ky, y6r); }
@@ -878,17 +803,6 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
                 int s = ++ph;
                 double a1 = T.a[s][1];
                 double i0 = a1 * K.get(1, 0), i1 = a1 * K.get(1, 1), i2 = a1 * K.get(1, 2);
-#ifdef PH_STAGE_SWITCH /* profiles/: one straight-line sum per stage (tableaus without zero coefficients only) */
-                if (nz && !PH_AUTOSW_ROLLED) {
-                    switch (s) {
-                    case 3: stage_sum_ct<3>(T, K, i0, i1, i2); break;
-                    case 4: stage_sum_ct<4>(T, K, i0, i1, i2); break;
-                    case 5: stage_sum_ct<5>(T, K, i0, i1, i2); break;
-                    case 6: stage_sum_ct<6>(T, K, i0, i1, i2); break;
-                    default: stage_sum_ct<7>(T, K, i0, i1, i2); break;
-                    }
-                } else
-#endif
                 if (PH_AUTOSW_ROLLED) {
                     /* the monitor-carrying loop sits at the edge of the instruction cache (profiles/README.md):
                        the same sums, rolled */
@@ -916,7 +830,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
             }
             /* all seven stages done: (n0,n1,n2) is u_new */
             const double u3 = K.ld(KS_U3), u4 = K.ld(KS_U4);
-            double n3 = fma(dt, PH_SUM_LD(KS_X7, x7s), u3), n4 = fma(dt, PH_SUM_LD(KS_Y7, y7s), u4);
+            double n3 = fma(dt, x7s, u3), n4 = fma(dt, y7s, u4);
             double b1 = T.bt[1];
             double e0 = b1 * K.get(1, 0), e1 = b1 * K.get(1, 1), e2 = b1 * K.get(1, 2);
             if (PH_AUTOSW_ROLLED) {
@@ -934,7 +848,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
                 }
             }
             StepCtl sc;
-            const double xe = PH_SUM_LD(KS_XE, xes), ye = PH_SUM_LD(KS_YE, yes), lq = K.ld(KS_LQ);
+            const double xe = xes, ye = yes, lq = K.ld(KS_LQ);
 #if defined(__CUDA_ARCH__)
             unsigned bad = 0;
             step_control<OpsFast>(P, T, dt, e0, e1, e2, xe, ye, u0, u1, u2, u3, u4, n0, n1, n2, n3, n4, lq, sc, &bad);
@@ -1051,8 +965,8 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
         {
             double kx, ky;
             prop(P, M, u1, u2, kx, ky);
-            PH_SUM_ST(KS_X7, x7s, T.a[7][1] * kx); PH_SUM_ST(KS_Y7, y7s, T.a[7][1] * ky);
-            PH_SUM_ST(KS_XE, xes, T.bt[1] * kx); PH_SUM_ST(KS_YE, yes, T.bt[1] * ky);
+            x7s = T.a[7][1] * kx; y7s = T.a[7][1] * ky;
+            xes = T.bt[1] * kx; yes = T.bt[1] * ky;
             if (autosw) { x6r = T.a[6][1] * kx; y6r = T.a[6][1] * ky; }
             double a = dt * T.a[2][1];
             n0 = fma(a, K.get(1, 0), u0); n1 = fma(a, K.get(1, 1), u1); n2 = fma(a, K.get(1, 2), u2);
@@ -1067,8 +981,6 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
     if (autosw) as_count = (int)K.ld(KS_AS);
     return switched;
 }
-#undef PH_SUM_LD
-#undef PH_SUM_ST
 #undef PH_COEF_ON
 
 /* ---- ParticleInCell ------------------------------------------------------- */
@@ -1423,6 +1335,7 @@ PM_HD bool advance_particle(const picles_params_t& P, Particle& p, int mask, dou
             }
             c.integrated++;
             if (attempts > c.max_attempts) c.max_attempts = attempts;
+            attempts_out = attempts;
         }
     } else {
         if (wu1 * wu1 + wv1 * wv1 >= P.wind_min_squared) {

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -22,7 +23,8 @@ using namespace picles;
    its rows have landed (copy stream + events), when the strip is large enough to matter */
 #define PIPE_CHUNKS 8
 #define PIPE_MIN_NODES (1 << 20)
-#define PIPE_EVENTS (PIPE_CHUNKS + 5) /* chunk landed x8, boundary blocks x2, boundary advanced, halo exchanged, compute stream idle */
+static_assert(PIPE_CHUNKS + 2 <= ADV_SLOTS, "one work queue per advance launch of a step");
+#define PIPE_EVENTS (PIPE_CHUNKS + 6) /* chunk landed x8, boundary blocks x2, boundary advanced, halo exchanged, interior advanced, compute stream idle */
 
 struct picles_handle {
     int device = -1;
@@ -42,12 +44,17 @@ struct picles_handle {
     double* d_partial = nullptr;
     double* h_partial = nullptr;          /* pinned */
     char *send_lo = nullptr, *send_hi = nullptr, *recv_lo = nullptr, *recv_hi = nullptr;
-    int64_t halo_bytes = 0;
+    int64_t halo_bytes = 0;                       /* capacity of each halo buffer (A.halo rows) */
+    int32_t* reach_send = nullptr;                /* staging word of the reach all-reduce */
+    int n_halo_widened = 0;                       /* steps that repeated exchange + gather with wider rows */
     std::vector<void*> allocs;
     picles_counters_t last;
     int64_t n_active = 0;
     bool timing_valid = false;
     int accumulate = 0; /* PICLES_OPT_ACCUMULATE_STATE */
+    int64_t steps_since_seed = 0; /* model steps taken since picles_seed (the integrator clocks started at 0 then) */
+    int32_t n_seed_off = 0;       /* active particles seeded off: under B-1 as run they read the lag wind level */
+    double *lag_u = nullptr, *lag_v = nullptr; /* storage of DeviceArrays::u_lag / v_lag (allocated on first use) */
     double* snap = nullptr;       /* staging copy of State for asynchronous snapshots (3 planes) */
     cudaStream_t snap_stream = nullptr; /* D2H of snapshots: its own stream, so wind uploads are not queued behind it */
     cudaEvent_t snap_ev[2] = {nullptr, nullptr}; /* staging copy done / D2H done */
@@ -140,8 +147,12 @@ static void free_grid(picles_t* h) {
     h->have_wind_mesh = h->wm_t1_valid = false;
     memset(&h->A, 0, sizeof h->A);
     h->send_lo = h->send_hi = h->recv_lo = h->recv_hi = nullptr;
+    h->reach_send = nullptr;
     h->snap = nullptr;
     h->snap_pending = false;
+    h->lag_u = h->lag_v = nullptr;
+    h->steps_since_seed = 0;
+    h->n_seed_off = 0;
     h->have_grid = h->seeded = h->winds_loaded = false;
 }
 
@@ -150,12 +161,13 @@ static void free_grid(picles_t* h) {
  * resolved with dlopen so a single-GPU host (or one that exchanges halos itself through
  * picles_halo_buffers) needs no NCCL at all; a host process that already loaded NCCL
  * (torch, NCCL.jl) shares that copy.  Only the types the six entry points need are
- * declared here (nccl.h: ncclUniqueId is 128 opaque bytes, ncclInt8 = 0). */
+ * declared here (nccl.h: ncclUniqueId is 128 opaque bytes, ncclInt8 = 0, ncclInt32 = 2, ncclMax = 2). */
 typedef struct { char internal[128]; } pk_nccl_id_t;
 typedef int (*pk_nccl_get_id_fn)(pk_nccl_id_t*);
 typedef int (*pk_nccl_init_rank_fn)(void**, int, pk_nccl_id_t, int);
 typedef int (*pk_nccl_destroy_fn)(void*);
 typedef int (*pk_nccl_sendrecv_fn)(void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*pk_nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*pk_nccl_group_fn)(void);
 typedef const char* (*pk_nccl_errstr_fn)(int);
 static struct {
@@ -164,6 +176,7 @@ static struct {
     pk_nccl_init_rank_fn init_rank = nullptr;
     pk_nccl_destroy_fn destroy = nullptr;
     pk_nccl_sendrecv_fn send = nullptr, recv = nullptr;
+    pk_nccl_allreduce_fn all_reduce = nullptr;
     pk_nccl_group_fn group_start = nullptr, group_end = nullptr;
     pk_nccl_errstr_fn errstr = nullptr;
 } g_nccl;
@@ -184,6 +197,7 @@ static int nccl_load(picles_t* h, const char* path) {
     PK_SYM(destroy, pk_nccl_destroy_fn, "ncclCommDestroy")
     PK_SYM(send, pk_nccl_sendrecv_fn, "ncclSend")
     PK_SYM(recv, pk_nccl_sendrecv_fn, "ncclRecv")
+    PK_SYM(all_reduce, pk_nccl_allreduce_fn, "ncclAllReduce")
     PK_SYM(group_start, pk_nccl_group_fn, "ncclGroupStart")
     PK_SYM(group_end, pk_nccl_group_fn, "ncclGroupEnd")
     PK_SYM(errstr, pk_nccl_errstr_fn, "ncclGetErrorString")
@@ -203,6 +217,23 @@ extern "C" {
 int picles_abi_version(void) { return PICLES_ABI_VERSION; }
 
 const char* picles_last_error(picles_t* h) { return h ? h->err : g_err; }
+
+static int create_resources(picles_t* h) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->snap_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < PIPE_EVENTS; k++) CK(cudaEventCreateWithFlags(&h->pev[k], cudaEventDisableTiming));
+    for (int k = 0; k < 5; k++) CK(cudaEventCreate(&h->ev[k]));
+    for (int k = 0; k < 2; k++) CK(cudaEventCreate(&h->tev[k]));
+    for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&h->snap_ev[k], cudaEventDisableTiming));
+    CK(cudaMalloc((void**)&h->d_counters, sizeof(DeviceCounters)));
+    CK(cudaMallocHost((void**)&h->h_counters, sizeof(DeviceCounters)));
+    CK(cudaMalloc((void**)&h->d_partial, ENERGY_BLOCKS * sizeof(double)));
+    CK(cudaMallocHost((void**)&h->h_partial, ENERGY_BLOCKS * sizeof(double)));
+    return PICLES_OK;
+}
 
 int picles_create(picles_t** out, int device_id) {
     picles_t* h = nullptr;
@@ -226,19 +257,12 @@ int picles_create(picles_t** out, int device_id) {
     h->sms = prop.multiProcessorCount;
     memset(&h->A, 0, sizeof h->A);
     memset(&h->last, 0, sizeof h->last);
-    CK(cudaSetDevice(device_id));
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->snap_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
-    for (int k = 0; k < PIPE_EVENTS; k++) CK(cudaEventCreateWithFlags(&h->pev[k], cudaEventDisableTiming));
-    for (int k = 0; k < 5; k++) CK(cudaEventCreate(&h->ev[k]));
-    for (int k = 0; k < 2; k++) CK(cudaEventCreate(&h->tev[k]));
-    for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&h->snap_ev[k], cudaEventDisableTiming));
-    CK(cudaMalloc((void**)&h->d_counters, sizeof(DeviceCounters)));
-    CK(cudaMallocHost((void**)&h->h_counters, sizeof(DeviceCounters)));
-    CK(cudaMalloc((void**)&h->d_partial, ENERGY_BLOCKS * sizeof(double)));
-    CK(cudaMallocHost((void**)&h->h_partial, ENERGY_BLOCKS * sizeof(double)));
+    int rc = create_resources(h);
+    if (rc) { /* nothing half-built survives a failed create: the caller holds no handle to clean up with */
+        snprintf(g_err, sizeof g_err, "%s", h->err);
+        picles_destroy(h);
+        return rc;
+    }
     *out = h;
     return PICLES_OK;
 }
@@ -292,11 +316,15 @@ static int set_grid_impl(picles_t* h, int Nx, int Ny, int bx, int by, int j0, in
         return fail(h, PICLES_ERR_ARG, "dx, dy, angle_dx, lat and a positive R_earth are required");
     if (halo > PH_REACH_MAX_ABI) return fail(h, PICLES_ERR_ARG, "halo %d exceeds the supported reach %d", halo, PH_REACH_MAX_ABI);
     if (ny_local != Ny && halo > ny_local) return fail(h, PICLES_ERR_ARG, "halo %d wider than the strip (%d rows)", halo, ny_local);
+    /* `halo` rows are exchanged to begin with; the record planes of a strip hold room for the widest exchange the
+       gather supports, so a step whose deposits reach further only repeats exchange + gather with more rows */
+    const int halo_x = halo;
+    if (ny_local != Ny && halo > 0) halo = (ny_local < PH_REACH_MAX_ABI) ? ny_local : PH_REACH_MAX_ABI;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     free_grid(h);
     DeviceArrays& A = h->A;
-    A.Nx = Nx; A.Ny = Ny; A.bx = bx; A.by = by; A.j0 = j0; A.ny = ny_local; A.halo = halo;
+    A.Nx = Nx; A.Ny = Ny; A.bx = bx; A.by = by; A.j0 = j0; A.ny = ny_local; A.halo = halo; A.hx = halo_x;
     A.rp = (Nx + REC_PITCH_ALIGN - 1) / REC_PITCH_ALIGN * REC_PITCH_ALIGN;
     int64_t n = (int64_t)Nx * ny_local;
     int64_t ne = (int64_t)A.rp * (ny_local + 2 * halo);
@@ -346,10 +374,11 @@ static int set_grid_impl(picles_t* h, int Nx, int Ny, int bx, int by, int j0, in
     launch_fill_i32(A.cell, ne, -1, h->sms, h->stream);
     for (int k = 0; k < 3; k++) CK(cudaMemsetAsync(A.S[k], 0, (size_t)n * 8, h->stream));
     CK(cudaMemsetAsync(A.flags, 0, (size_t)n, h->stream));
-    h->halo_bytes = (int64_t)halo * A.rp * (5 * 8 + 4);
+    h->halo_bytes = (int64_t)halo * A.rp * (5 * 8 + 4); /* capacity of each buffer; a message carries hx rows */
     if (halo > 0) {
         DALLOC(h->send_lo, h->halo_bytes); DALLOC(h->send_hi, h->halo_bytes);
         DALLOC(h->recv_lo, h->halo_bytes); DALLOC(h->recv_hi, h->halo_bytes);
+        DALLOC(h->reach_send, 1);
         /* until a neighbour delivers rows, received halos are "no deposit" */
         CK(cudaMemsetAsync(h->recv_lo, 0xff, (size_t)h->halo_bytes, h->stream));
         CK(cudaMemsetAsync(h->recv_hi, 0xff, (size_t)h->halo_bytes, h->stream));
@@ -442,11 +471,16 @@ static int need_ready(picles_t* h, bool seeded) {
 static int seed_from_t1(picles_t* h) {
     DeviceArrays& A = h->A;
     int64_t n = (int64_t)A.Nx * A.ny;
-    launch_seed(A, h->P, A.u_t1, A.v_t1, h->sms, h->stream);
+    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(DeviceCounters), h->stream));
+    launch_seed(A, h->P, A.u_t1, A.v_t1, h->d_counters, h->sms, h->stream);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(A.u_t, A.u_t1, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemcpyAsync(A.v_t, A.v_t1, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(&h->h_counters->n_seed_off, &h->d_counters->n_seed_off, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->n_seed_off = h->h_counters->n_seed_off;
+    h->steps_since_seed = 0;
+    A.u_lag = A.v_lag = nullptr; /* the first step's t+DT level IS the lag level */
     A.n_mid = 0;
     h->seeded = true;
     h->winds_loaded = true;
@@ -518,6 +552,22 @@ int picles_upload_winds(picles_t* h, const double* u_t, const double* v_t, const
     return PICLES_OK;
 }
 
+/* B-1 as run (`on` frozen at seed, on_persist == 0): a particle seeded off never integrates, its integrator
+   clock stays at 0 and advance! tests the wind at t_end = integ.t + DT = DT on every step
+   (mapping_2D.jl:132,172-176).  That level is the first step's t+DT level: kept here, behind the first
+   step's advance on the compute stream (by then every upload of the level has landed), and read by
+   k_advance from the second step on.  Nothing is kept when every particle was seeded on. */
+static int keep_lag_level(picles_t* h) {
+    DeviceArrays& A = h->A;
+    if (h->steps_since_seed != 0 || h->P.on_persist || h->n_seed_off == 0) return PICLES_OK;
+    const int64_t n = (int64_t)A.Nx * A.ny;
+    if (!h->lag_u) { DALLOC(h->lag_u, n); DALLOC(h->lag_v, n); }
+    CK(cudaMemcpyAsync(h->lag_u, A.u_t1, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->lag_v, A.v_t1, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    A.u_lag = h->lag_u; A.v_lag = h->lag_v;
+    return PICLES_OK;
+}
+
 int picles_step_advance(picles_t* h, double t, double dt_model) {
     int rc = need_ready(h, true);
     if (rc) return rc;
@@ -526,11 +576,11 @@ int picles_step_advance(picles_t* h, double t, double dt_model) {
     CK(cudaMemsetAsync(h->d_counters, 0, sizeof(DeviceCounters), h->stream));
     CK(cudaMemsetAsync(h->A.rowreach, 0, (size_t)(h->A.ny + 2 * h->A.halo) * 4, h->stream));
     CK(cudaEventRecord(h->ev[0], h->stream));
-    launch_advance(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream, 0, (int64_t)h->A.Nx * h->A.ny);
+    launch_advance(h->A, h->P, dt_model, h->d_counters, h->sms, h->stream, 0, (int64_t)h->A.Nx * h->A.ny, 0);
     CK(cudaEventRecord(h->ev[1], h->stream));
     CK(cudaGetLastError());
     h->timing_valid = false;
-    return PICLES_OK;
+    return keep_lag_level(h);
 }
 
 /* ---- upload + advance, pipelined over row blocks -------------------------------------------
@@ -562,7 +612,7 @@ static int begin_advance(picles_t* h, double dt_model, const double* u_t, const 
     return PICLES_OK;
 }
 static int advance_rows(picles_t* h, double dt_model, const double* u_t, const double* v_t, const double* u_t1,
-                        const double* v_t1, int r0, int r1, cudaEvent_t landed) {
+                        const double* v_t1, int r0, int r1, cudaEvent_t landed, int slot) {
     DeviceArrays& A = h->A;
     if (r0 >= r1) return PICLES_OK;
     const int64_t off = (int64_t)r0 * A.Nx;
@@ -579,7 +629,7 @@ static int advance_rows(picles_t* h, double dt_model, const double* u_t, const d
         CK(cudaEventRecord(landed, h->copy_stream));
         CK(cudaStreamWaitEvent(h->stream, landed, 0));
     }
-    launch_advance(A, h->P, dt_model, h->d_counters, h->sms, h->stream, off, off + (int64_t)(r1 - r0) * A.Nx);
+    launch_advance(A, h->P, dt_model, h->d_counters, h->sms, h->stream, off, off + (int64_t)(r1 - r0) * A.Nx, slot);
     return PICLES_OK;
 }
 /* rows [r0, r1) in up to PIPE_CHUNKS blocks (one block when nothing is uploaded or the range is small) */
@@ -595,7 +645,7 @@ static int advance_range(picles_t* h, double dt_model, const double* u_t, const 
         int a = r0, len = first_rows;
         for (int c = 0; c < PIPE_CHUNKS && a < r1; c++) {
             const int b = (c == PIPE_CHUNKS - 1 || a + len >= r1) ? r1 : a + len;
-            int rc = advance_rows(h, dt_model, u_t, v_t, u_t1, v_t1, a, b, h->pev[c]);
+            int rc = advance_rows(h, dt_model, u_t, v_t, u_t1, v_t1, a, b, h->pev[c], c);
             if (rc) return rc;
             a = b; len *= 3;
         }
@@ -604,7 +654,7 @@ static int advance_range(picles_t* h, double dt_model, const double* u_t, const 
     const int rows = (r1 - r0 + nch - 1) / nch;
     for (int c = 0; c < nch; c++) {
         const int a = r0 + c * rows, b = (a + rows < r1) ? a + rows : r1;
-        int rc = advance_rows(h, dt_model, u_t, v_t, u_t1, v_t1, a, b, h->pev[c]);
+        int rc = advance_rows(h, dt_model, u_t, v_t, u_t1, v_t1, a, b, h->pev[c], c);
         if (rc) return rc;
     }
     return PICLES_OK;
@@ -617,7 +667,7 @@ static int upload_and_advance(picles_t* h, double dt_model, const double* u_t, c
     if (rc) return rc;
     CK(cudaEventRecord(h->ev[1], h->stream));
     CK(cudaGetLastError());
-    return PICLES_OK;
+    return keep_lag_level(h);
 }
 
 int picles_get_reach(picles_t* h, int32_t* reach) {
@@ -629,13 +679,32 @@ int picles_get_reach(picles_t* h, int32_t* reach) {
     return PICLES_OK;
 }
 
+/* bytes of one halo message: hx rows of the five record planes and the cell plane */
+static int64_t halo_msg_bytes(const picles_t* h) { return (int64_t)h->A.hx * h->A.rp * (5 * 8 + 4); }
+
+int picles_halo_rows(picles_t* h, int* rows_exchanged, int* rows_max) {
+    if (!h || !h->have_grid) return fail(h, PICLES_ERR_STATE, "grid not set");
+    if (rows_exchanged) *rows_exchanged = h->A.hx;
+    if (rows_max) *rows_max = h->A.halo;
+    return PICLES_OK;
+}
+
+int picles_halo_widen(picles_t* h, int rows) {
+    if (!h || !h->have_grid) return fail(h, PICLES_ERR_STATE, "grid not set");
+    if (rows <= h->A.hx) return PICLES_OK; /* never narrowed: rows beyond hx would keep stale records */
+    if (rows > h->A.halo)
+        return fail(h, PICLES_ERR_HALO, "a halo of %d rows is asked for; this strip (%d rows) can exchange at most %d", rows, h->A.ny, h->A.halo);
+    h->A.hx = rows;
+    return PICLES_OK;
+}
+
 int picles_halo_buffers(picles_t* h, void** send_lo, void** send_hi, void** recv_lo, void** recv_hi, int64_t* nbytes) {
     if (!h || !h->have_grid) return fail(h, PICLES_ERR_STATE, "grid not set");
     if (send_lo) *send_lo = h->send_lo;
     if (send_hi) *send_hi = h->send_hi;
     if (recv_lo) *recv_lo = h->recv_lo;
     if (recv_hi) *recv_hi = h->recv_hi;
-    if (nbytes) *nbytes = h->halo_bytes;
+    if (nbytes) *nbytes = halo_msg_bytes(h);
     return PICLES_OK;
 }
 
@@ -679,23 +748,41 @@ static int finish_counters(picles_t* h) {
 /* tile geometry of the gather for this step, guessed from the previous step's reach */
 static int wide_tiles(const picles_t* h) { return h->last.reach > PR_HY_NARROW && h->last.reach <= PR_HY_WIDE; }
 
+/* gather + remesh, counters read back (the one host synchronisation of a step).  *need = 0, or — on a strip whose
+   deposits reach further than the hx rows that were exchanged — the rows needed: the kernel then changed nothing
+   (k_project_remesh) and the caller repeats exchange and gather with wider rows, or reports PICLES_ERR_HALO */
+static int project_remesh_once(picles_t* h, double dt_model, int* need) {
+    *need = 0;
+    /* a halo exchange may have run since the advance: ms_project brackets the gather alone */
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    launch_project_remesh(h->maps, h->A, h->P, dt_model, h->P.periodic_boundary ? 2 : 1, h->accumulate, wide_tiles(h), h->d_counters, h->stream);
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    CK(cudaGetLastError());
+    int rc = finish_counters(h);
+    if (rc) return rc;
+    if (h->A.ny != h->A.Ny && h->h_counters->halo_short > 0) {
+        *need = h->h_counters->halo_short;
+        CK(cudaMemsetAsync(&h->d_counters->halo_short, 0, sizeof(int32_t), h->stream));
+        return PICLES_OK;
+    }
+    h->A.n_mid = 0; /* intermediate wind levels are consumed by one step */
+    h->steps_since_seed++;
+    if (h->last.reach > PH_REACH_MAX_ABI)
+        return fail(h, PICLES_ERR_HALO, "particle reach %d cells exceeds the supported reach %d", h->last.reach, PH_REACH_MAX_ABI);
+    return PICLES_OK;
+}
+
 int picles_step_project_remesh(picles_t* h, double t, double dt_model) {
     int rc = need_ready(h, true);
     if (rc) return rc;
     (void)t;
-    /* a halo exchange may have run since the advance: ms_project brackets the gather alone */
-    CK(cudaEventRecord(h->ev[2], h->stream));
-    launch_project_remesh(h->maps, h->A, h->P, dt_model, h->P.periodic_boundary ? 2 : 1, h->accumulate, wide_tiles(h), h->d_counters, h->stream);
-    h->A.n_mid = 0; /* intermediate wind levels are consumed by one step */
-    CK(cudaEventRecord(h->ev[3], h->stream));
-    CK(cudaEventRecord(h->ev[4], h->stream));
-    CK(cudaGetLastError());
-    rc = finish_counters(h);
+    int need = 0;
+    rc = project_remesh_once(h, dt_model, &need);
     if (rc) return rc;
-    int limit = (h->A.ny != h->A.Ny) ? h->A.halo : PH_REACH_MAX_ABI;
-    if (h->last.reach > limit)
-        return fail(h, PICLES_ERR_HALO, "particle reach %d cells exceeds %s %d", h->last.reach,
-                    (h->A.ny != h->A.Ny) ? "the halo width" : "the supported reach", limit);
+    if (need > 0)
+        return fail(h, PICLES_ERR_HALO, "deposits reach %d rows but %d halo rows were exchanged; nothing was changed: "
+                    "picles_halo_widen(%d) on every strip, then repeat the exchange and this call", need, h->A.hx, need);
     return PICLES_OK;
 }
 
@@ -703,21 +790,13 @@ int picles_step(picles_t* h, double t, double dt_model, const double* u_t, const
                 const double* v_t1) {
     int rc = need_ready(h, true);
     if (rc) return rc;
+    (void)t;
     if (h->A.ny != h->A.Ny)
         return fail(h, PICLES_ERR_STATE, "picles_step needs a single-strip handle; use the phase-split calls for strips");
     rc = upload_and_advance(h, dt_model, u_t, v_t, u_t1, v_t1);
     if (rc) return rc;
-    CK(cudaEventRecord(h->ev[2], h->stream));
-    launch_project_remesh(h->maps, h->A, h->P, dt_model, h->P.periodic_boundary ? 2 : 1, h->accumulate, wide_tiles(h), h->d_counters, h->stream);
-    h->A.n_mid = 0; /* intermediate wind levels are consumed by one step */
-    CK(cudaEventRecord(h->ev[3], h->stream));
-    CK(cudaEventRecord(h->ev[4], h->stream));
-    CK(cudaGetLastError());
-    rc = finish_counters(h);
-    if (rc) return rc;
-    if (h->last.reach > PH_REACH_MAX_ABI)
-        return fail(h, PICLES_ERR_HALO, "particle reach %d cells exceeds the supported reach %d", h->last.reach, PH_REACH_MAX_ABI);
-    return PICLES_OK;
+    int need = 0;
+    return project_remesh_once(h, dt_model, &need);
 }
 
 int picles_synchronize(picles_t* h) {
@@ -780,6 +859,16 @@ int picles_get_counters(picles_t* h, picles_counters_t* c) {
     *c = h->last;
     return PICLES_OK;
 }
+
+int picles_get_attempt_histogram(picles_t* h, int64_t* hist, int nbins) {
+    if (!h || !hist || nbins < 1) return fail(h, PICLES_ERR_ARG, "picles_get_attempt_histogram: bad argument");
+    if (!h->timing_valid) return fail(h, PICLES_ERR_STATE, "no completed step to report");
+    for (int k = 0; k < nbins; k++) hist[k] = 0;
+    for (int k = 0; k < ADV_HIST_BINS; k++) hist[k < nbins ? k : nbins - 1] += (int64_t)h->h_counters->attempt_hist[k];
+    return PICLES_OK;
+}
+
+int64_t picles_launch_count(void) { return (int64_t)launch_count(); }
 
 int picles_state_energy_sum(picles_t* h, double* sum_e) {
     int rc = need_ready(h, false);
@@ -998,22 +1087,33 @@ struct CkptHeader {
     uint64_t magic;
     int32_t version, Nx, ny, j0, Ny, bx, by, halo;
     int64_t n_bytes;
-    int64_t reserved[2];
+    uint64_t params_hash; /* FNV-1a of the picles_params_t the run was made with */
+    uint64_t clock;       /* bit 0: the lag wind level follows the planes; bits 1..32: particles seeded off; bits 33..: steps since the seed */
 };
 static_assert(sizeof(CkptHeader) == 64, "checkpoint header layout");
 #define CKPT_MAGIC 0x50694342323030ull /* "PiCB200" */
 
-static int64_t ckpt_bytes(const DeviceArrays& A) {
-    const int64_t n = (int64_t)A.Nx * A.ny;
-    return (int64_t)sizeof(CkptHeader) + n * (8 * (5 + 3 + 3 + 2) + 4 + 1 + 1 + 1);
+static uint64_t params_hash(const picles_params_t& P) {
+    /* the two runs of fields around the padding word behind has_defaults (and the one at the tail) */
+    const unsigned char* b = (const unsigned char*)&P;
+    const size_t span[2][2] = {{0, offsetof(picles_params_t, has_defaults) + sizeof(int32_t)},
+                               {offsetof(picles_params_t, defaults), offsetof(picles_params_t, reserved)}};
+    uint64_t hsh = 1469598103934665603ull;
+    for (int r = 0; r < 2; r++)
+        for (size_t k = span[r][0]; k < span[r][1]; k++) { hsh ^= b[k]; hsh *= 1099511628211ull; }
+    return hsh;
+}
+static int64_t ckpt_bytes(const picles_t* h, bool with_lag) {
+    const int64_t n = (int64_t)h->A.Nx * h->A.ny;
+    return (int64_t)sizeof(CkptHeader) + n * (8 * (5 + 3 + 3 + 2 + (with_lag ? 2 : 0)) + 4 + 1 + 1 + 1);
 }
 int picles_checkpoint_size(picles_t* h, int64_t* nbytes) {
     if (!h || !h->have_grid || !nbytes) return fail(h, PICLES_ERR_STATE, "grid not set");
-    *nbytes = ckpt_bytes(h->A);
+    *nbytes = ckpt_bytes(h, h->A.u_lag != nullptr);
     return PICLES_OK;
 }
 /* the planes of a checkpoint, in blob order */
-static int ckpt_planes(picles_t* h, void** ptr, size_t* bytes) {
+static int ckpt_planes(picles_t* h, bool with_lag, void** ptr, size_t* bytes) {
     DeviceArrays& A = h->A;
     const size_t n = (size_t)A.Nx * A.ny;
     int k = 0;
@@ -1028,18 +1128,27 @@ static int ckpt_planes(picles_t* h, void** ptr, size_t* bytes) {
     ptr[k] = A.flags; bytes[k++] = n;
     ptr[k] = A.status; bytes[k++] = n;
     ptr[k] = A.as; bytes[k++] = n;
+    if (with_lag) {
+        ptr[k] = h->lag_u; bytes[k++] = n * 8;
+        ptr[k] = h->lag_v; bytes[k++] = n * 8;
+    }
     return k;
 }
 int picles_checkpoint_save(picles_t* h, void* blob, int64_t nbytes) {
     int rc = need_ready(h, true);
     if (rc) return rc;
-    if (!blob || nbytes < ckpt_bytes(h->A)) return fail(h, PICLES_ERR_ARG, "checkpoint buffer too small (%lld < %lld bytes)", (long long)nbytes, (long long)ckpt_bytes(h->A));
     const DeviceArrays& A = h->A;
-    CkptHeader hd = {CKPT_MAGIC, PICLES_ABI_VERSION, A.Nx, A.ny, A.j0, A.Ny, A.bx, A.by, A.halo, ckpt_bytes(A), {0, 0}};
+    /* intermediate wind levels staged for the next step are not part of the blob: a run resumed from it
+       would integrate that step against two levels only */
+    if (A.n_mid > 0) return fail(h, PICLES_ERR_STATE, "%d intermediate wind levels are staged for the next step; checkpoint before picles_set_wind_midlevels or after the step", A.n_mid);
+    const bool with_lag = A.u_lag != nullptr;
+    if (!blob || nbytes < ckpt_bytes(h, with_lag)) return fail(h, PICLES_ERR_ARG, "checkpoint buffer too small (%lld < %lld bytes)", (long long)nbytes, (long long)ckpt_bytes(h, with_lag));
+    CkptHeader hd = {CKPT_MAGIC, PICLES_ABI_VERSION, A.Nx, A.ny, A.j0, A.Ny, A.bx, A.by, A.halo, ckpt_bytes(h, with_lag), params_hash(h->P),
+                     (uint64_t)(with_lag ? 1 : 0) | ((uint64_t)(uint32_t)h->n_seed_off << 1) | ((uint64_t)h->steps_since_seed << 33)};
     memcpy(blob, &hd, sizeof hd);
-    void* ptr[20];
-    size_t bytes[20];
-    const int np = ckpt_planes(h, ptr, bytes);
+    void* ptr[24];
+    size_t bytes[24];
+    const int np = ckpt_planes(h, with_lag, ptr, bytes);
     char* out = (char*)blob + sizeof hd;
     for (int k = 0; k < np; k++) {
         CK(cudaMemcpyAsync(out, ptr[k], bytes[k], cudaMemcpyDeviceToHost, h->stream));
@@ -1048,22 +1157,29 @@ int picles_checkpoint_save(picles_t* h, void* blob, int64_t nbytes) {
     CK(cudaStreamSynchronize(h->stream));
     return PICLES_OK;
 }
-/* the handle must have the same grid (picles_set_grid*) and parameters as the one that saved */
+/* the handle must have the same grid (picles_set_grid*) and parameters (picles_set_params) as the one that saved:
+   both are checked */
 int picles_checkpoint_load(picles_t* h, const void* blob, int64_t nbytes) {
     int rc = need_ready(h, false);
     if (rc) return rc;
     if (!blob || nbytes < (int64_t)sizeof(CkptHeader)) return fail(h, PICLES_ERR_ARG, "not a checkpoint");
     CkptHeader hd;
     memcpy(&hd, blob, sizeof hd);
-    const DeviceArrays& A = h->A;
+    DeviceArrays& A = h->A;
     if (hd.magic != CKPT_MAGIC || hd.version != PICLES_ABI_VERSION) return fail(h, PICLES_ERR_ARG, "not a checkpoint of this library version");
     if (hd.Nx != A.Nx || hd.ny != A.ny || hd.j0 != A.j0 || hd.Ny != A.Ny || hd.bx != A.bx || hd.by != A.by)
         return fail(h, PICLES_ERR_ARG, "checkpoint is for a %dx%d strip at row %d of %d; this handle owns %dx%d at row %d of %d", hd.Nx,
                     hd.ny, hd.j0, hd.Ny, A.Nx, A.ny, A.j0, A.Ny);
-    if (nbytes < hd.n_bytes || hd.n_bytes != ckpt_bytes(A)) return fail(h, PICLES_ERR_ARG, "truncated checkpoint");
-    void* ptr[20];
-    size_t bytes[20];
-    const int np = ckpt_planes(h, ptr, bytes);
+    if (hd.params_hash != params_hash(h->P))
+        return fail(h, PICLES_ERR_ARG, "checkpoint was written with different parameters (picles_set_params): solver state, tolerances "
+                                       "and switches would not match the restored particles");
+    const bool with_lag = (hd.clock & 1u) != 0;
+    if (nbytes < hd.n_bytes || hd.n_bytes != ckpt_bytes(h, with_lag)) return fail(h, PICLES_ERR_ARG, "truncated checkpoint");
+    const int64_t n = (int64_t)A.Nx * A.ny;
+    if (with_lag && !h->lag_u) { DALLOC(h->lag_u, n); DALLOC(h->lag_v, n); }
+    void* ptr[24];
+    size_t bytes[24];
+    const int np = ckpt_planes(h, with_lag, ptr, bytes);
     const char* in = (const char*)blob + sizeof hd;
     for (int k = 0; k < np; k++) {
         CK(cudaMemcpyAsync(ptr[k], in, bytes[k], cudaMemcpyHostToDevice, h->stream));
@@ -1072,10 +1188,14 @@ int picles_checkpoint_load(picles_t* h, const void* blob, int64_t nbytes) {
     /* no deposit records are carried over: every step rewrites them before they are read */
     const int64_t ne = (int64_t)A.rp * (A.ny + 2 * A.halo);
     launch_fill_i32(A.cell, ne, -1, h->sms, h->stream);
-    CK(cudaMemcpyAsync(A.u_t, A.u_t1, (size_t)A.Nx * A.ny * 8, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(A.v_t, A.v_t1, (size_t)A.Nx * A.ny * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(A.u_t, A.u_t1, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(A.v_t, A.v_t1, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
+    A.u_lag = with_lag ? h->lag_u : nullptr;
+    A.v_lag = with_lag ? h->lag_v : nullptr;
+    h->n_seed_off = (int32_t)((hd.clock >> 1) & 0xffffffffu);
+    h->steps_since_seed = (int64_t)(hd.clock >> 33);
     h->seeded = true;
     h->winds_loaded = true;
     h->wm_t1_valid = false;
@@ -1127,7 +1247,7 @@ int picles_comm_destroy(picles_t* h) {
 /* pack -> grouped ncclSend/ncclRecv with the two y-neighbours -> unpack, all enqueued on the
    handle's stream: no host synchronisation between the advance and the gather */
 static int exchange_on(picles_t* h, int lo_rank, int hi_rank, cudaStream_t st) {
-    if (h->A.halo == 0) return PICLES_OK;
+    if (h->A.hx == 0) return PICLES_OK;
     if ((lo_rank >= 0 || hi_rank >= 0) && !h->comm)
         return fail(h, PICLES_ERR_STATE, "picles_comm_init must be called before picles_halo_exchange");
     if (lo_rank >= h->comm_size || hi_rank >= h->comm_size || (lo_rank >= 0 && lo_rank == h->comm_rank) ||
@@ -1138,7 +1258,7 @@ static int exchange_on(picles_t* h, int lo_rank, int hi_rank, cudaStream_t st) {
     launch_halo_pack(h->A, h->send_lo, h->send_hi, h->sms, st);
     CK(cudaGetLastError());
     if (lo_rank >= 0 || hi_rank >= 0) {
-        size_t nb = (size_t)h->halo_bytes;
+        size_t nb = (size_t)halo_msg_bytes(h);
         NCK(g_nccl.group_start());
         /* my first rows -> the lower neighbour's upper halo, my last rows -> the upper
            neighbour's lower halo.  Sends are issued lo,hi and receives hi,lo so that a
@@ -1161,41 +1281,74 @@ int picles_halo_exchange(picles_t* h, int lo_rank, int hi_rank) {
     return exchange_on(h, lo_rank, hi_rank, h->stream);
 }
 
+/* the largest reach of any strip, for the gather's check that enough halo rows were exchanged: a 4-byte
+   ncclAllReduce(max) of the strips' own reach, enqueued behind the advance (every rank of the communicator takes
+   part in every step) */
+static int reach_allreduce(picles_t* h, cudaStream_t st) {
+    if (!h->comm || h->comm_size < 2 || !h->reach_send) return PICLES_OK;
+    CK(cudaMemcpyAsync(h->reach_send, &h->d_counters->reach, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    NCK(g_nccl.all_reduce(h->reach_send, &h->d_counters->reach_all, 1, 2 /* ncclInt32 */, 2 /* ncclMax */, h->comm, st));
+    return PICLES_OK;
+}
+
 /* one model step of a strip, exchange included; one host synchronisation at the end (the
-   counters).  The first and last `halo` rows are advanced first; their deposit records travel
+   counters).  The first and last hx rows are advanced first; their deposit records travel
    to the neighbours on a second stream (pack, ncclSend/ncclRecv, unpack) while the interior
-   rows integrate, so neither the exchange nor a slower neighbour shows up in the step time. */
+   rows integrate, so neither the exchange nor a slower neighbour shows up in the step time.
+   The reference enforces no CFL limit (ParticleInCell.jl:58-71): when some particle of some strip
+   reached further than the hx rows exchanged, the gather refuses (it changes nothing), every strip
+   widens hx to the all-reduced reach and exchange + gather are repeated — the advance is not. */
 int picles_step_strip(picles_t* h, double t, double dt_model, const double* u_t, const double* v_t, const double* u_t1,
                       const double* v_t1, int lo_rank, int hi_rank) {
     int rc = need_ready(h, true);
     if (rc) return rc;
+    (void)t;
     const DeviceArrays& A = h->A;
-    const bool overlap = A.halo > 0 && (lo_rank >= 0 || hi_rank >= 0) && A.ny > 2 * A.halo;
+    const bool overlap = A.hx > 0 && (lo_rank >= 0 || hi_rank >= 0) && A.ny > 2 * A.hx;
     if (!overlap) {
         rc = upload_and_advance(h, dt_model, u_t, v_t, u_t1, v_t1);
         if (rc) return rc;
         rc = exchange_on(h, lo_rank, hi_rank, h->stream);
         if (rc) return rc;
-        return picles_step_project_remesh(h, t, dt_model);
+        rc = reach_allreduce(h, h->stream);
+        if (rc) return rc;
+    } else {
+        rc = begin_advance(h, dt_model, u_t, v_t, u_t1, v_t1);
+        if (rc) return rc;
+        rc = advance_rows(h, dt_model, u_t, v_t, u_t1, v_t1, 0, A.hx, h->pev[PIPE_CHUNKS], PIPE_CHUNKS);
+        if (rc) return rc;
+        rc = advance_rows(h, dt_model, u_t, v_t, u_t1, v_t1, A.ny - A.hx, A.ny, h->pev[PIPE_CHUNKS + 1], PIPE_CHUNKS + 1);
+        if (rc) return rc;
+        cudaEvent_t advanced = h->pev[PIPE_CHUNKS + 2], exchanged = h->pev[PIPE_CHUNKS + 3], interior = h->pev[PIPE_CHUNKS + 4];
+        CK(cudaEventRecord(advanced, h->stream));                  /* boundary records written */
+        CK(cudaStreamWaitEvent(h->comm_stream, advanced, 0));
+        rc = exchange_on(h, lo_rank, hi_rank, h->comm_stream);
+        if (rc) return rc;
+        rc = advance_range(h, dt_model, u_t, v_t, u_t1, v_t1, A.hx, A.ny - A.hx);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        CK(cudaGetLastError());
+        rc = keep_lag_level(h);
+        if (rc) return rc;
+        CK(cudaEventRecord(interior, h->stream));                  /* this strip's reach is final */
+        CK(cudaStreamWaitEvent(h->comm_stream, interior, 0));
+        rc = reach_allreduce(h, h->comm_stream);
+        if (rc) return rc;
+        CK(cudaEventRecord(exchanged, h->comm_stream));            /* halo rows in place, reach of every strip known */
+        CK(cudaStreamWaitEvent(h->stream, exchanged, 0));
     }
-    rc = begin_advance(h, dt_model, u_t, v_t, u_t1, v_t1);
-    if (rc) return rc;
-    rc = advance_rows(h, dt_model, u_t, v_t, u_t1, v_t1, 0, A.halo, h->pev[PIPE_CHUNKS]);
-    if (rc) return rc;
-    rc = advance_rows(h, dt_model, u_t, v_t, u_t1, v_t1, A.ny - A.halo, A.ny, h->pev[PIPE_CHUNKS + 1]);
-    if (rc) return rc;
-    cudaEvent_t advanced = h->pev[PIPE_CHUNKS + 2], exchanged = h->pev[PIPE_CHUNKS + 3];
-    CK(cudaEventRecord(advanced, h->stream));                  /* boundary records written */
-    CK(cudaStreamWaitEvent(h->comm_stream, advanced, 0));
-    rc = exchange_on(h, lo_rank, hi_rank, h->comm_stream);
-    if (rc) return rc;
-    CK(cudaEventRecord(exchanged, h->comm_stream));            /* halo rows in place */
-    rc = advance_range(h, dt_model, u_t, v_t, u_t1, v_t1, A.halo, A.ny - A.halo);
-    if (rc) return rc;
-    CK(cudaEventRecord(h->ev[1], h->stream));
-    CK(cudaGetLastError());
-    CK(cudaStreamWaitEvent(h->stream, exchanged, 0));
-    return picles_step_project_remesh(h, t, dt_model);
+    for (;;) {
+        int need = 0;
+        rc = project_remesh_once(h, dt_model, &need);
+        if (rc || need == 0) return rc;
+        /* every strip reads the same all-reduced reach, so every strip is here with the same `need` */
+        if (!h->comm && (lo_rank >= 0 || hi_rank >= 0)) return fail(h, PICLES_ERR_STATE, "no communicator");
+        rc = picles_halo_widen(h, need);
+        if (rc) return rc;
+        h->n_halo_widened++;
+        rc = exchange_on(h, lo_rank, hi_rank, h->stream);
+        if (rc) return rc;
+    }
 }
 
 /* ---- wind ingestion: resident wind mesh ---------------------------------------------------- */
@@ -1274,18 +1427,21 @@ int picles_measure_wind_sample(picles_t* h, double t, int reps, double* ms_per_l
     if (!h || !h->have_wind_mesh) return fail(h, PICLES_ERR_STATE, "picles_set_wind_mesh must be called first");
     if (reps < 1 || !ms_per_launch) return fail(h, PICLES_ERR_ARG, "picles_measure_wind_sample: bad argument");
     CK(cudaSetDevice(h->device));
-    int rc = ensure_mid_planes(h, 1);
-    if (rc) return rc;
     DeviceArrays& A = h->A;
     const int64_t n = (int64_t)A.Nx * A.ny;
-    launch_wind_sample(h->wm, n, t, A.u_mid[0], A.v_mid[0], h->sms, h->stream);
-    CK(cudaEventRecord(h->tev[0], h->stream));
-    for (int r = 0; r < reps; r++) launch_wind_sample(h->wm, n, t, A.u_mid[0], A.v_mid[0], h->sms, h->stream);
-    CK(cudaEventRecord(h->tev[1], h->stream));
-    CK(cudaEventSynchronize(h->tev[1]));
-    CK(cudaGetLastError());
+    /* its own scratch planes: the wind levels staged for the next step are left alone */
+    double* tmp = nullptr;
+    if (cudaMalloc((void**)&tmp, (size_t)n * 16) != cudaSuccess) return fail(h, PICLES_ERR_ALLOC, "cannot allocate %lld bytes", (long long)n * 16);
+    launch_wind_sample(h->wm, n, t, tmp, tmp + n, h->sms, h->stream);
+    cudaError_t e = cudaEventRecord(h->tev[0], h->stream);
+    for (int r = 0; r < reps; r++) launch_wind_sample(h->wm, n, t, tmp, tmp + n, h->sms, h->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(h->tev[1], h->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(h->tev[1]);
+    if (e == cudaSuccess) e = cudaGetLastError();
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, h->tev[0], h->tev[1]));
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, h->tev[0], h->tev[1]);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(h, PICLES_ERR_CUDA, "picles_measure_wind_sample: %s", cudaGetErrorString(e));
     *ms_per_launch = (double)ms / reps;
     return PICLES_OK;
 }

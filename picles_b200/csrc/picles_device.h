@@ -15,6 +15,10 @@
 #ifndef ADV_MIN_BLOCKS
 #define ADV_MIN_BLOCKS 3
 #endif
+/* advance launches per step that may be in flight on one DeviceCounters: the pipelined row blocks of an upload
+   (slots 0..7) and the two boundary blocks of a strip (8, 9) */
+#define ADV_SLOTS 12
+#define ADV_HIST_BINS 48
 /* projection gather + remesh: one block per tile of PR_TX x TY target nodes; the record tile
    (targets + a halo) is staged in shared memory by TMA.  The TMA box is always PR_BW x PR_BH
    = 72 x 20 elements; it is cut either as 16 target rows + 2 halo rows (reach <= 2, the common
@@ -48,7 +52,8 @@ namespace picles {
 struct DeviceArrays {
     int Nx, Ny;       /* global shape */
     int bx, by;       /* PICLES_BND_* */
-    int j0, ny, halo; /* strip: first global row (0-based), rows owned, halo rows */
+    int j0, ny, halo; /* strip: first global row (0-based), rows owned, halo rows the record planes hold on each side */
+    int hx;           /* halo rows exchanged with the y-neighbours this step (<= halo; widened when the reach asks for it) */
     int rp;           /* row pitch (elements) of the record planes rec[] / cell */
     double* z[5];     /* lne, c̄_x, c̄_y, x, y */
     double *t, *dt, *qold;
@@ -59,6 +64,9 @@ struct DeviceArrays {
     double *u_t, *v_t, *u_t1, *v_t1; /* staged winds at t and t+DT */
     double *u_mid[PICLES_WIND_MID_MAX], *v_mid[PICLES_WIND_MID_MAX]; /* intermediate levels (allocated on first use) */
     int n_mid;                       /* intermediate levels staged for the next advance (0: linear in time) */
+    double *u_lag, *v_lag;           /* B-1 as run: the wind at integrator time 0 + DT (the first step's t+DT level), read by the
+                                        particles that were seeded off and therefore never advance their own clock; nullptr
+                                        when there are none, under on_persist, and during the first step (== u_t1 then) */
     double* M[4];                    /* per-node projection kernel planes, or nullptr */
     double Mc[4];                    /* uniform projection kernel */
     double* pc;                      /* great-circle coefficient plane, or nullptr */
@@ -76,12 +84,21 @@ struct DeviceCounters {
     int32_t reach_halo;   /* max reach of the records received into the halo rows */
     int32_t class1;       /* a deposit of the second class (a mask-3 particle of a periodic model) exists */
     int32_t n_pending;    /* AutoTsit5: particles parked by k_advance this step (entries of DeviceArrays::pending) */
+    int32_t reach_all;    /* strips: max reach over every strip (all-reduced before the gather; 0 when the host validates the reach itself) */
+    int32_t halo_short;   /* strips: set by the gather when deposits reach further than the hx rows exchanged — it then changes nothing */
+    int32_t n_seed_off;   /* written by k_seed: active particles seeded off (they need the lag wind level under B-1 as run) */
+    /* work queue of the advance launches of one step: launch `slot` hands out its 32-particle chunks from next_chunk[slot] */
+    unsigned long long next_chunk[ADV_SLOTS];
+    /* particles that integrated this step by the number of Runge-Kutta attempts they took (last bin: >= ADV_HIST_BINS - 1) */
+    unsigned long long attempt_hist[ADV_HIST_BINS];
 };
 
-void launch_seed(const DeviceArrays& A, const picles_params_t& P, const double* u0, const double* v0, int sms,
-                 cudaStream_t st);
+void launch_seed(const DeviceArrays& A, const picles_params_t& P, const double* u0, const double* v0, DeviceCounters* dc,
+                 int sms, cudaStream_t st);
 void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
-                    cudaStream_t st, int64_t l_begin, int64_t l_end);
+                    cudaStream_t st, int64_t l_begin, int64_t l_end, int slot);
+/* kernels launched by this library since it was loaded (every launch_* call counts its kernels) */
+long long launch_count();
 /* TMA tensor maps of the six record planes (box PR_BW x PR_BH) */
 struct ProjectMaps {
     CUtensorMap rec[5];

@@ -21,6 +21,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "stiff.h"
 #include "picles_device.h"
 #include "pmath_trig.h"
@@ -29,6 +31,11 @@
 namespace picles {
 
 static_assert(PH_REACH_MAX == PH_REACH_MAX_ABI, "reach limits out of sync");
+
+/* every kernel this library launches is counted where it is launched (bench.py reports the count of its timed region) */
+static std::atomic<long long> g_launches{0};
+long long launch_count() { return g_launches.load(); }
+#define COUNT_LAUNCH(n) g_launches.fetch_add(n)
 
 /* ---- block-level tally reduction: one atomic set per block ------------------- */
 __device__ __forceinline__ int32_t warp_sum(int32_t v) {
@@ -113,12 +120,14 @@ __device__ __forceinline__ int64_t rec_index(const DeviceArrays& A, int64_t l) {
 
 /* ---- seed ------------------------------------------------------------------ */
 __global__ void __launch_bounds__(256) k_seed(DeviceArrays A, picles_params_t P, const double* __restrict__ u0,
-                                              const double* __restrict__ v0) {
+                                              const double* __restrict__ v0, DeviceCounters* dc) {
     int64_t n = (int64_t)A.Nx * A.ny;
+    int32_t n_off = 0; /* iterated particles seeded off */
     for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x) {
         Particle p;
         double e, mx, my;
         seed_particle(P, A.mask[l], u0[l], v0[l], p, e, mx, my);
+        if ((p.flags & PICLES_PF_ACTIVE) && !(p.flags & PICLES_PF_ON)) n_off++;
         store_particle(A, l, p);
         A.as[l] = 0;
         A.S[0][l] = e; A.S[1][l] = mx; A.S[2][l] = my;
@@ -127,14 +136,23 @@ __global__ void __launch_bounds__(256) k_seed(DeviceArrays A, picles_params_t P,
         r.cell = PH_CELL_INVALID;
         store_record(A, rec_index(A, l), r);
     }
+    n_off = warp_sum(n_off);
+    if ((threadIdx.x & 31) == 0 && n_off) atomicAdd(&dc->n_seed_off, n_off);
 }
 
 /* ---- advance ---------------------------------------------------------------- */
 /*
- * One thread per particle, grid-stride over the strip so a block owns many 32-particle
- * chunks and flushes its counters once.  The adaptive loop runs in SIMT lock-step: lanes
- * whose particle reached t+DT wait at the loop exit for the slowest lane of the warp
- * (neighbouring nodes carry near-identical states, so attempt counts are close).
+ * One thread per particle.  Work is handed out warp by warp: a warp takes the next chunk of 32
+ * consecutive particles of the launch's range from a counter in global memory (one atomic per
+ * chunk, i.e. per ~10^6 instructions), integrates it and comes back for more, until the range is
+ * exhausted.  Within a chunk the adaptive loop runs in SIMT lock-step (lanes whose particle reached
+ * t+DT wait at the loop exit for the slowest lane: neighbouring nodes carry near-identical states,
+ * measured 29.0-32.0 active lanes per instruction over the configurations, profiles/README.md);
+ * across chunks nobody waits: a warp that drew slow particles (40 attempts against a mean of 6.6 at
+ * the calm foot of a wind ramp) simply takes fewer chunks.  The static grid-stride assignment this
+ * replaces visited only Nx/32 / gcd(Nx/32, warps in flight) distinct x-positions per warp, so on a
+ * field that varies along x whole warps drew nothing but slow chunks and the launch ended on them
+ * (growing-wind configuration: 7.3 ms against 4.5 ms for a step with 4 % more instructions).
  */
 #ifdef ADV_MAXNREG /* register cap given directly; ADV_MIN_BLOCKS then only sizes the grid */
 #define ADV_BOUNDS __maxnreg__(ADV_MAXNREG)
@@ -143,58 +161,78 @@ __global__ void __launch_bounds__(256) k_seed(DeviceArrays A, picles_params_t P,
 #endif
 template <bool PER_NODE_M, bool AUTOSW, int TSIT5 = 0>
 __global__ void ADV_BOUNDS
-k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int64_t l_begin, int64_t l_end) {
+k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int64_t l_begin, int64_t l_end, int slot) {
     /* stage derivatives k_j[0:3], j = 1..7: 21 doubles per thread, one column per thread
        (consecutive threads -> consecutive 8-byte words: conflict-free) */
     __shared__ double s_k[KS_SLOTS * ADV_THREADS];
+    __shared__ int32_t s_hist[ADV_HIST_BINS];
     KStrided K;
     K.base = &s_k[threadIdx.x];
     K.stride = ADV_THREADS;
     Tally c;
     tally_zero(c);
-    for (int64_t l = l_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < l_end; l += (int64_t)gridDim.x * blockDim.x) {
-        uint8_t flags = A.flags[l];
-        if (!(flags & PICLES_PF_ACTIVE)) continue; /* record stays invalid (set at seed) */
-        int64_t le = rec_index(A, l);
-        Particle p;
-        load_particle(A, l, p);
-        if (AUTOSW) load_as(A, P, l, p);
-        double M[4];
-        if (PER_NODE_M) { M[0] = A.M[0][l]; M[1] = A.M[1][l]; M[2] = A.M[2][l]; M[3] = A.M[3][l]; }
-        else { M[0] = A.Mc[0]; M[1] = A.Mc[1]; M[2] = A.Mc[2]; M[3] = A.Mc[3]; }
-        double pc = A.pc ? A.pc[l] : 0.0;
-        Record r;
-        double um[PH_WIND_SEG_MAX], vm[PH_WIND_SEG_MAX];
+    if (threadIdx.x < ADV_HIST_BINS) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    unsigned long long* const queue = &dc->next_chunk[slot];
+    for (;;) {
+        unsigned long long chunk = 0;
+        if (lane == 0) chunk = atomicAdd(queue, 1ull);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        const int64_t l0 = l_begin + (int64_t)chunk * 32;
+        if (l0 >= l_end) break; /* uniform over the warp */
+        const int64_t l = l0 + lane;
+        const uint8_t flags = (l < l_end) ? A.flags[l] : (uint8_t)0;
+        if (flags & PICLES_PF_ACTIVE) { /* else: the record stays invalid (set at seed) */
+            int64_t le = rec_index(A, l);
+            Particle p;
+            load_particle(A, l, p);
+            if (AUTOSW) load_as(A, P, l, p);
+            double M[4];
+            if (PER_NODE_M) { M[0] = A.M[0][l]; M[1] = A.M[1][l]; M[2] = A.M[2][l]; M[3] = A.M[3][l]; }
+            else { M[0] = A.Mc[0]; M[1] = A.Mc[1]; M[2] = A.Mc[2]; M[3] = A.Mc[3]; }
+            double pc = A.pc ? A.pc[l] : 0.0;
+            Record r;
+            double um[PH_WIND_SEG_MAX], vm[PH_WIND_SEG_MAX];
 #pragma unroll
-        for (int k = 0; k < PICLES_WIND_MID_MAX; k++) {
-            if (k < A.n_mid) { um[k] = A.u_mid[k][l]; vm[k] = A.v_mid[k][l]; }
-            else { um[k] = 0.0; vm[k] = 0.0; }
-        }
-        um[PH_WIND_SEG_MAX - 1] = 0.0; vm[PH_WIND_SEG_MAX - 1] = 0.0;
-        const double t_start = p.t;
-        int attempts = 0;
-        const bool pending = advance_particle<AUTOSW, TSIT5>(P, p, A.mask[l], DT, A.u_t[l], A.v_t[l], A.u_t1[l], A.v_t1[l], A.n_mid, um,
-                                                      vm, M, pc, r, c, K, attempts);
-        if (AUTOSW && pending) {
-            /* AutoSwitch handed the particle to Rosenbrock23: park the state reached so far; the
-               resume kernel that follows finishes the step (the record slot carries what it needs) */
-            r.cell = PH_CELL_PENDING;
-            r.e = t_start; r.mx = (double)attempts;
-            r.my = r.wxc = r.wyc = 0.0;
-            A.pending[atomicAdd(&dc->n_pending, 1)] = (int32_t)l;
-        }
-        store_particle(A, l, p);
-        if (AUTOSW) store_as(A, P, l, p);
-        store_record(A, le, r);
-        if (r.cell != PH_CELL_INVALID && !(AUTOSW && r.cell == PH_CELL_PENDING)) {
-            /* per-row reach (lets the gather size its window tile by tile) and class presence */
-            const int rr = cell_reach(r.cell);
-            int32_t* slot = &A.rowreach[le / A.rp];
-            if (rr > __ldcg(slot)) atomicMax(slot, rr);
-            if (((uint32_t)r.cell >> 28) & 1u) dc->class1 = 1;
+            for (int k = 0; k < PICLES_WIND_MID_MAX; k++) {
+                if (k < A.n_mid) { um[k] = A.u_mid[k][l]; vm[k] = A.v_mid[k][l]; }
+                else { um[k] = 0.0; vm[k] = 0.0; }
+            }
+            um[PH_WIND_SEG_MAX - 1] = 0.0; vm[PH_WIND_SEG_MAX - 1] = 0.0;
+            const double t_start = p.t;
+            int attempts = -1;
+            /* winds(x, y, t_end) with t_end = integ.t + DT (mapping_2D.jl:172-176): a particle that was seeded off under
+               B-1 as run never advances its own clock, so its t_end stays at 0 + DT — the level kept from the first step */
+            double wu1 = A.u_t1[l], wv1 = A.v_t1[l];
+            if (A.u_lag && !(flags & PICLES_PF_ON)) { wu1 = A.u_lag[l]; wv1 = A.v_lag[l]; }
+            const bool pending = advance_particle<AUTOSW, TSIT5>(P, p, A.mask[l], DT, A.u_t[l], A.v_t[l], wu1, wv1, A.n_mid, um,
+                                                          vm, M, pc, r, c, K, attempts);
+            if (AUTOSW && pending) {
+                /* AutoSwitch handed the particle to Rosenbrock23: park the state reached so far; the
+                   resume kernel that follows finishes the step (the record slot carries what it needs) */
+                r.cell = PH_CELL_PENDING;
+                r.e = t_start; r.mx = (double)attempts;
+                r.my = r.wxc = r.wyc = 0.0;
+                A.pending[atomicAdd(&dc->n_pending, 1)] = (int32_t)l;
+            } else if (attempts >= 0) {
+                atomicAdd(&s_hist[attempts < ADV_HIST_BINS ? attempts : ADV_HIST_BINS - 1], 1);
+            }
+            store_particle(A, l, p);
+            if (AUTOSW) store_as(A, P, l, p);
+            store_record(A, le, r);
+            if (r.cell != PH_CELL_INVALID && !(AUTOSW && r.cell == PH_CELL_PENDING)) {
+                /* per-row reach (lets the gather size its window tile by tile) and class presence */
+                const int rr = cell_reach(r.cell);
+                int32_t* rslot = &A.rowreach[le / A.rp];
+                if (rr > __ldcg(rslot)) atomicMax(rslot, rr);
+                if (((uint32_t)r.cell >> 28) & 1u) dc->class1 = 1;
+            }
         }
     }
     tally_flush(c, dc);
+    if (threadIdx.x < ADV_HIST_BINS && s_hist[threadIdx.x])
+        atomicAdd(&dc->attempt_hist[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
 }
 
 /*
@@ -235,7 +273,14 @@ k_advance_resume(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* d
         else { R.M[0] = A.Mc[0]; R.M[1] = A.Mc[1]; R.M[2] = A.Mc[2]; R.M[3] = A.Mc[3]; }
         R.pc = A.pc ? A.pc[l] : 0.0;
         Record r;
+        const int32_t max_before = c.max_attempts;
+        c.max_attempts = 0;
         advance_resume(&P, &R, &p, &r, &c, K);
+        { /* c.max_attempts now holds this particle's attempts */
+            const int a = c.max_attempts;
+            atomicAdd(&dc->attempt_hist[a < ADV_HIST_BINS ? a : ADV_HIST_BINS - 1], 1ull);
+            c.max_attempts = max(max_before, a);
+        }
         store_particle(A, l, p);
         store_as(A, P, l, p);
         store_record(A, le, r);
@@ -400,7 +445,16 @@ k_project_remesh(const __grid_constant__ ProjectMaps maps, const __grid_constant
     /* deposits landing on this strip come from its own particles (reach) and from the
        neighbours' rows received into the halo (reach_halo) */
     int R = min(max(dc->reach, dc->reach_halo), PH_REACH_MAX);
-    if (A.ny != A.Ny) R = min(R, A.halo); /* strips: the host rejects reach > halo (PICLES_ERR_HALO) */
+    if (A.ny != A.Ny) {
+        /* strips: a deposit of a neighbour's particle can land here from as far as the largest reach of any strip.
+           If that is more than the hx rows exchanged, records are missing: touch nothing, say so, and let the host
+           repeat exchange and gather with wider rows (picles_step_strip does; the advance is not repeated) */
+        const int need = max(max(dc->reach, dc->reach_halo), dc->reach_all);
+        if (need > A.hx) {
+            if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) dc->halo_short = need;
+            return;
+        }
+    }
     /* two passes over the window are only needed when deposits of both classes exist */
     if (!dc->class1) n_classes = 1;
     /* reach of the records that can land on this tile: rows within R of its targets.  A few
@@ -520,10 +574,10 @@ __global__ void __launch_bounds__(256) k_energy(const double* __restrict__ e, in
 
 /* ---- halo pack / unpack: H rows of the 5 record planes + cell plane -------------- */
 __global__ void k_halo_pack(DeviceArrays A, char* __restrict__ send_lo, char* __restrict__ send_hi) {
-    int64_t m = (int64_t)A.halo * A.rp;
+    int64_t m = (int64_t)A.hx * A.rp;
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < m; q += (int64_t)gridDim.x * blockDim.x) {
-        int64_t lo = (int64_t)A.halo * A.rp + q;                 /* first owned rows */
-        int64_t hi = (int64_t)A.ny * A.rp + q;                   /* last owned rows (ext index = ny+halo-halo) */
+        int64_t lo = (int64_t)A.halo * A.rp + q;                 /* first hx owned rows */
+        int64_t hi = (int64_t)(A.halo + A.ny - A.hx) * A.rp + q; /* last hx owned rows */
 #pragma unroll
         for (int k = 0; k < 5; k++) {
             ((double*)send_lo)[k * m + q] = A.rec[k][lo];
@@ -535,11 +589,11 @@ __global__ void k_halo_pack(DeviceArrays A, char* __restrict__ send_lo, char* __
 }
 __global__ void k_halo_unpack(DeviceArrays A, const char* __restrict__ recv_lo, const char* __restrict__ recv_hi,
                               DeviceCounters* dc) {
-    int64_t m = (int64_t)A.halo * A.rp;
+    int64_t m = (int64_t)A.hx * A.rp;
     int32_t reach = 0;
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < m; q += (int64_t)gridDim.x * blockDim.x) {
-        int64_t lo = q;                                           /* lower halo rows */
-        int64_t hi = (int64_t)(A.ny + A.halo) * A.rp + q;         /* upper halo rows */
+        int64_t lo = (int64_t)(A.halo - A.hx) * A.rp + q;         /* the hx halo rows next to the first owned row */
+        int64_t hi = (int64_t)(A.ny + A.halo) * A.rp + q;         /* the hx halo rows behind the last owned row */
 #pragma unroll
         for (int k = 0; k < 5; k++) {
             A.rec[k][lo] = ((const double*)recv_lo)[k * m + q];
@@ -549,9 +603,10 @@ __global__ void k_halo_unpack(DeviceArrays A, const char* __restrict__ recv_lo, 
         A.cell[lo] = clo;
         A.cell[hi] = chi;
         const int rlo = cell_reach(clo), rhi = cell_reach(chi);
-        const int row = (int)(q / A.rp);
+        const int row = A.halo - A.hx + (int)(q / A.rp);
         if (rlo > 0 && rlo > __ldcg(&A.rowreach[row])) atomicMax(&A.rowreach[row], rlo);
-        if (rhi > 0 && rhi > __ldcg(&A.rowreach[A.ny + A.halo + row])) atomicMax(&A.rowreach[A.ny + A.halo + row], rhi);
+        const int row_hi = A.ny + A.halo + (int)(q / A.rp);
+        if (rhi > 0 && rhi > __ldcg(&A.rowreach[row_hi])) atomicMax(&A.rowreach[row_hi], rhi);
         if ((clo != PH_CELL_INVALID && (((uint32_t)clo >> 28) & 1u)) || (chi != PH_CELL_INVALID && (((uint32_t)chi >> 28) & 1u)))
             dc->class1 = 1;
         reach = max(reach, max(rlo, rhi));
@@ -781,49 +836,42 @@ static int grid_for(int64_t n, int threads, int sms, int blocks_per_sm) {
     return (int)(need < cap ? need : cap);
 }
 
-void launch_seed(const DeviceArrays& A, const picles_params_t& P, const double* u0, const double* v0, int sms,
-                 cudaStream_t st) {
+void launch_seed(const DeviceArrays& A, const picles_params_t& P, const double* u0, const double* v0, DeviceCounters* dc,
+                 int sms, cudaStream_t st) {
     int64_t n = (int64_t)A.Nx * A.ny;
-    k_seed<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(A, P, u0, v0);
+    k_seed<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(A, P, u0, v0, dc);
+    COUNT_LAUNCH(1);
 }
 
-/* particles [l_begin, l_end) of the strip (the whole strip: 0, Nx*ny) */
+/* particles [l_begin, l_end) of the strip (the whole strip: 0, Nx*ny); slot: the work queue of this launch
+   (DeviceCounters::next_chunk, zeroed with the counters at the start of the step) */
 void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
-                    cudaStream_t st, int64_t l_begin, int64_t l_end) {
+                    cudaStream_t st, int64_t l_begin, int64_t l_end, int slot) {
     if (l_end <= l_begin) return;
     int g = grid_for(l_end - l_begin, ADV_THREADS, sms, ADV_MIN_BLOCKS);
     bool pn = (A.M[0] != nullptr);
-    size_t dyn = 0;
-#ifdef ADV_OCCUPANCY_EXPERIMENT /* profiles/: unused dynamic shared memory caps the resident blocks per SM */
-    static int dyn_env = -1;
-    if (dyn_env < 0) {
-        const char* e = getenv("PICLES_ADV_DYN_SMEM");
-        dyn_env = e ? atoi(e) : 0;
-        cudaFuncSetAttribute(k_advance<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_env);
-        cudaFuncSetAttribute(k_advance<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_env);
-    }
-    dyn = (size_t)dyn_env;
-#endif
     /* AutoTsit5 runs the instantiation that carries the stiffness monitor and the Rosenbrock23 branch */
     if (P.solver == PICLES_SOLVER_AUTOTSIT5) {
         const int gr = grid_for(l_end - l_begin, ADV_THREADS, sms, 1);
         if (pn) {
-            k_advance<true, true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+            k_advance<true, true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
             k_advance_resume<true><<<gr, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end);
         } else {
-            k_advance<false, true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+            k_advance<false, true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
             k_advance_resume<false><<<gr, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end);
         }
+        COUNT_LAUNCH(2);
     } else {
         /* Tsit5 has its own instantiation (compile-time tableau without zero coefficients); DP5 runs the generic one */
         const bool ts5 = (P.solver == PICLES_SOLVER_TSIT5);
-        if (pn && ts5) k_advance<true, false, true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
-        else if (pn) k_advance<true, false><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
-        else if (ts5) k_advance<false, false, true><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+        if (pn && ts5) k_advance<true, false, true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
+        else if (pn) k_advance<true, false><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
+        else if (ts5) k_advance<false, false, true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
 #ifdef PH_DP5_CT /* profiles/: DP5 with its own instantiation too */
-        else if (P.solver == PICLES_SOLVER_DP5) k_advance<false, false, 2><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+        else if (P.solver == PICLES_SOLVER_DP5) k_advance<false, false, 2><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
 #endif
-        else k_advance<false, false><<<g, ADV_THREADS, dyn, st>>>(A, P, DT, dc, l_begin, l_end);
+        else k_advance<false, false><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
+        COUNT_LAUNCH(1);
     }
 }
 
@@ -841,10 +889,12 @@ void launch_project_remesh(const ProjectMaps& maps, const DeviceArrays& A, const
     dim3 grid((A.Nx + PR_TX - 1) / PR_TX, (A.ny + TY - 1) / TY);
     if (wide) k_project_remesh<PR_HY_WIDE><<<grid, PR_THREADS, project_remesh_smem_bytes(), st>>>(maps, A, P, DT, n_classes, accumulate, dc);
     else k_project_remesh<PR_HY_NARROW><<<grid, PR_THREADS, project_remesh_smem_bytes(), st>>>(maps, A, P, DT, n_classes, accumulate, dc);
+    COUNT_LAUNCH(1);
 }
 
 void launch_wind_sample(const DeviceWindMesh& W, int64_t n, double t, double* u_out, double* v_out, int sms, cudaStream_t st) {
     if (n <= 0) return;
+    COUNT_LAUNCH(2);
     k_wind_timeblend<<<grid_for((int64_t)W.nx * W.ny, 256, sms, 8), 256, 0, st>>>(W, t);
 #ifdef PH_WIND_ROW4
     if (n >= 4 && (((uintptr_t)W.node_x | (uintptr_t)W.node_y | (uintptr_t)u_out | (uintptr_t)v_out) & 15) == 0) {
@@ -856,43 +906,51 @@ void launch_wind_sample(const DeviceWindMesh& W, int64_t n, double t, double* u_
 }
 void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cudaStream_t st) {
     k_energy<<<nblocks, 256, 0, st>>>(e, n, partial);
+    COUNT_LAUNCH(1);
 }
 
 void launch_halo_pack(const DeviceArrays& A, char* lo, char* hi, int sms, cudaStream_t st) {
-    int64_t m = (int64_t)A.halo * A.rp;
-    if (m > 0) k_halo_pack<<<grid_for(m, 256, sms, 4), 256, 0, st>>>(A, lo, hi);
+    int64_t m = (int64_t)A.hx * A.rp;
+    if (m > 0) { k_halo_pack<<<grid_for(m, 256, sms, 4), 256, 0, st>>>(A, lo, hi); COUNT_LAUNCH(1); }
 }
 void launch_halo_unpack(const DeviceArrays& A, const char* lo, const char* hi, DeviceCounters* dc, int sms, cudaStream_t st) {
-    int64_t m = (int64_t)A.halo * A.rp;
-    if (m > 0) k_halo_unpack<<<grid_for(m, 256, sms, 4), 256, 0, st>>>(A, lo, hi, dc);
+    int64_t m = (int64_t)A.hx * A.rp;
+    if (m > 0) { k_halo_unpack<<<grid_for(m, 256, sms, 4), 256, 0, st>>>(A, lo, hi, dc); COUNT_LAUNCH(1); }
 }
 void launch_grid_metric(int64_t n, const double* dx, const double* dy, const double* angle_dx, const double* lat,
                         double R_earth, double* M11, double* M12, double* M21, double* M22, double* pc, int sms, cudaStream_t st) {
     if (n > 0) k_grid_metric<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(n, dx, dy, angle_dx, lat, R_earth, M11, M12, M21, M22, pc);
+    COUNT_LAUNCH(1);
 }
 void launch_make_boundaries(const uint8_t* ocean, uint8_t* total, int Nx, int Ny, int bx, int by, int sms, cudaStream_t st) {
     (void)sms;
     dim3 grid((Nx + 255) / 256, Ny < 65535 ? Ny : 65535);
     k_make_boundaries<<<grid, 256, 0, st>>>(ocean, total, Nx, Ny, bx, by);
+    COUNT_LAUNCH(1);
 }
 void launch_fields(int64_t n, const double* e, const double* mx, const double* my, double* Hs, double* cx, double* cy,
                    int sms, cudaStream_t st) {
     if (n > 0) k_fields<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(n, e, mx, my, Hs, cx, cy);
+    COUNT_LAUNCH(1);
 }
 void launch_fill_i32(int32_t* p, int64_t n, int32_t v, int sms, cudaStream_t st) {
     if (n > 0) k_fill_i32<<<grid_for(n, 256, sms, 4), 256, 0, st>>>(p, n, v);
+    COUNT_LAUNCH(1);
 }
 
 void launch_selftest_math(uint64_t seed, int iters, unsigned long long* out, int sms, cudaStream_t st) {
     k_selftest_math<<<sms * 8, 256, 0, st>>>(seed, iters, out);
+    COUNT_LAUNCH(1);
 }
 void launch_fp64_peak(double* out, int iters, int sms, cudaStream_t st, int64_t* fmas) {
     int blocks = sms * 8;
     k_fp64_peak<<<blocks, 256, 0, st>>>(out, iters);
     *fmas = (int64_t)blocks * 256 * (int64_t)iters * 64;
+    COUNT_LAUNCH(1);
 }
 void launch_copy_f64(double* dst, const double* src, int64_t n, int sms, cudaStream_t st) {
     k_copy_f64<<<sms * 16, 256, 0, st>>>((double2*)dst, (const double2*)src, n / 2);
+    COUNT_LAUNCH(1);
 }
 
 } /* namespace picles */

@@ -126,7 +126,12 @@ class TorchP2PTransport:
         import torch
         self.torch = torch
         self.eng = eng
+        self._views()
+
+    def _views(self):
+        torch, eng = self.torch, self.eng
         bufs, nb = eng.halo_buffers()
+        self.nb = nb
         self.on_device = not isinstance(bufs[0], np.ndarray)
         if self.on_device:
             dev = torch.device("cuda", eng.device)
@@ -134,9 +139,24 @@ class TorchP2PTransport:
         else:
             self.t = [torch.from_numpy(b) for b in bufs]
 
+    def validate_reach(self):
+        """SURVEY.md §8e: the halo width is validated every step by a max-all-reduce of the strips' reach;
+        deposits that reach further than the rows exchanged widen the exchange before it happens"""
+        import torch.distributed as dist
+        e = self.eng
+        if not hasattr(e, "halo_widen"):
+            return
+        r = self.torch.tensor([e.reach()], dtype=self.torch.int32, device=f"cuda:{e.device}" if self.on_device else "cpu")
+        dist.all_reduce(r, op=dist.ReduceOp.MAX)
+        need = int(r.item())
+        if need > e.halo_rows()[0]:
+            e.halo_widen(need)
+            self._views()
+
     def exchange(self, lo, hi):
         import torch.distributed as dist
         e = self.eng
+        self.validate_reach()
         e.halo_pack()
         send_lo, send_hi, recv_lo, recv_hi = self.t
         ops = []

@@ -150,6 +150,16 @@ class B200Engine:
         self._check(self.lib.picles_halo_buffers(self.h, *[C.byref(x) for x in p], C.byref(nb)))
         return [x.value for x in p], nb.value
 
+    def halo_rows(self):
+        """(rows exchanged with each y-neighbour, most the strip can exchange)"""
+        a, b = C.c_int(), C.c_int()
+        self._check(self.lib.picles_halo_rows(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def halo_widen(self, rows):
+        """exchange at least `rows` rows from now on (never narrowed)"""
+        self._check(self.lib.picles_halo_widen(self.h, int(rows)))
+
     def halo_pack(self):
         self._check(self.lib.picles_halo_pack(self.h))
 
@@ -251,6 +261,16 @@ class B200Engine:
         c = PiclesCounters()
         self._check(self.lib.picles_get_counters(self.h, C.byref(c)))
         return c.as_dict()
+
+    def attempt_histogram(self, nbins=48):
+        """particles that integrated in the last step by Runge-Kutta attempts taken (last bin: that many or more)"""
+        h = np.zeros(int(nbins), np.int64)
+        self._check(self.lib.picles_get_attempt_histogram(self.h, _ptr(h), int(nbins)))
+        return h
+
+    def launch_count(self):
+        """kernels launched by the library in this process so far"""
+        return int(self.lib.picles_launch_count())
 
     def solver_state(self):
         """AutoSwitch state per particle (AutoTsit5): run length of the stiffness test, +64 while

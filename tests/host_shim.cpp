@@ -23,6 +23,7 @@ struct Strip {
     std::vector<int32_t> iter, cell;
     std::vector<uint8_t> flags, status, mask;
     std::vector<int8_t> as;
+    std::vector<double> ulag, vlag; /* the lag wind level as the ABI layer keeps it (picles_capi.cu: keep_lag_level) */
 };
 
 struct Shim {
@@ -36,6 +37,7 @@ struct Shim {
     int reach_halo = 0; /* per-process strips: max reach of the received halo records */
     int n_mid = 0;      /* intermediate wind levels of the next step (global planes, consumed by it) */
     std::vector<double> u_mid, v_mid;
+    int64_t steps_since_seed = 0;
 };
 
 static void load(const Strip& s, int64_t l, Particle& p) {
@@ -129,7 +131,9 @@ void shim_wind_mesh_sample(int nx, int ny, int nt, const double* xw, const doubl
 }
 
 void shim_seed(Shim* h, const double* u0, const double* v0) {
+    h->steps_since_seed = 0;
     for (auto& s : h->s) {
+        s.ulag.clear(); s.vlag.clear();
         int64_t n = (int64_t)h->Nx * s.ny, off = (int64_t)s.j0 * h->Nx;
         for (int64_t l = 0; l < n; l++) {
             Particle p;
@@ -167,17 +171,20 @@ static void shim_advance_all(Shim* h, double DT, const double* u_t, const double
             }
             const double t_start = p.t;
             int attempts = 0;
+            /* as k_advance: a particle seeded off under B-1 as run reads the level kept from the first step */
+            double wu1 = u_t1[off + l], wv1 = v_t1[off + l];
+            if (!s.ulag.empty() && !(p.flags & PICLES_PF_ON)) { wu1 = s.ulag[l]; wv1 = s.vlag[l]; }
             /* as launch_advance picks the kernel: Tsit5 has its own instantiation */
             const bool pending = (ph_host_specialised && h->P.solver == PICLES_SOLVER_TSIT5)
-                ? advance_particle<false, true>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l],
-                                                v_t1[off + l], h->n_mid, um, vm, M, pc, r, c, K, attempts)
+                ? advance_particle<false, true>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], wu1,
+                                                wv1, h->n_mid, um, vm, M, pc, r, c, K, attempts)
 #ifdef PH_DP5_CT
                 : (ph_host_specialised && h->P.solver == PICLES_SOLVER_DP5)
-                ? advance_particle<false, 2>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l],
-                                             v_t1[off + l], h->n_mid, um, vm, M, pc, r, c, K, attempts)
+                ? advance_particle<false, 2>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], wu1,
+                                             wv1, h->n_mid, um, vm, M, pc, r, c, K, attempts)
 #endif
-                : advance_particle<true>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], u_t1[off + l],
-                                         v_t1[off + l], h->n_mid, um, vm, M, pc, r, c, K, attempts);
+                : advance_particle<true>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], wu1,
+                                         wv1, h->n_mid, um, vm, M, pc, r, c, K, attempts);
 
             if (pending) { /* as the kernel: the stiff part of the step runs through advance_resume */
                 ResumeArgs R;
@@ -198,7 +205,14 @@ static void shim_advance_all(Shim* h, double DT, const double* u_t, const double
             s.rec[0][le] = r.e; s.rec[1][le] = r.mx; s.rec[2][le] = r.my; s.rec[3][le] = r.wxc; s.rec[4][le] = r.wyc;
             s.cell[le] = r.cell;
         }
+        /* keep_lag_level of the ABI layer: behind the first step's advance, only when a particle was seeded off */
+        if (h->steps_since_seed == 0 && !h->P.on_persist) {
+            bool any_off = false;
+            for (int64_t l = 0; l < n; l++) any_off = any_off || ((s.flags[l] & PICLES_PF_ACTIVE) && !(s.flags[l] & PICLES_PF_ON));
+            if (any_off) { s.ulag.assign(u_t1 + off, u_t1 + off + n); s.vlag.assign(v_t1 + off, v_t1 + off + n); }
+        }
     }
+    h->steps_since_seed++;
 }
 
 static void shim_project_remesh_all(Shim* h, double DT, int R, const double* u_t, const double* v_t, Tally& T,
@@ -290,6 +304,8 @@ Shim* shim_create_strip(int Nx, int Ny, int bx, int by, int j0, int ny, int halo
 }
 void shim_strip_seed(Shim* h, const double* u0, const double* v0) {
     Strip& s = h->s[0];
+    h->steps_since_seed = 0;
+    s.ulag.clear(); s.vlag.clear();
     int64_t n = (int64_t)h->Nx * s.ny;
     for (int64_t l = 0; l < n; l++) {
         Particle p;
@@ -407,7 +423,7 @@ int64_t shim_corner_target(int Nx, int Ny, int bx, int by, int64_t i, int64_t j)
 }
 void shim_rhs(const picles_params_t* P, const double* z, double u, double v, const double* M, double pc, double* dz) {
     Hoist H;
-    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false; H.std_terms = false; H.uv = 0.0; H.tvu = 0.0;
+    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false; H.std_terms = false;
     rhs3<OpsSafe, false>(*P, H, z[0], z[1], z[2], u, v, sqrt(u * u + v * v), pc, dz[0], dz[1], dz[2], (unsigned*)0);
     prop(*P, M, z[1], z[2], dz[3], dz[4]);
 }

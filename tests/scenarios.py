@@ -82,6 +82,23 @@ def sc_growing_winds_persist():
     return sc_growing_winds(on_persist=True)
 
 
+def sc_pulse_winds():
+    """B-1 as run: the left half is calm at t = 0 (particles seeded off, `on` frozen), the wind there peaks
+    at t = DT and decays again.  advance! tests an off particle against winds(x, y, integ.t + DT) with
+    integ.t stuck at 0 (mapping_2D.jl:132,172-176): the DT level on every step, so these particles
+    re-deposit the same wind sea for ever; the right half integrates normally."""
+    g = cartesian_grid(40, 18)
+    DT = 900.0
+    P = default_params(DT=DT, wind_min_squared=2.0)
+    left = g["x"] < 40000.0
+
+    def wind(t):
+        a = 0.3 + 1.5 * np.exp(-((t - DT) / DT) ** 2)
+        return np.where(left, a, 9.0 + 2.0 * np.sin(t / 2000.0)), np.where(left, 0.3, 4.0)
+
+    return g, P, wind, DT, 6
+
+
 def sc_tripolar():
     """C4-style synthetic tripolar grid: periodic x, tripolar-north fold, per-node rotated
     kernel and great-circle term, land blobs and masked poles; winds as
@@ -205,6 +222,7 @@ SCENARIOS = {
     "land_block": sc_land_block,
     "growing_winds": sc_growing_winds,
     "growing_winds_persist": sc_growing_winds_persist,
+    "pulse_winds": sc_pulse_winds,
     "tripolar": sc_tripolar,
     "tripolar_propagation_only": sc_tripolar_propagation_only,
     "emax_clamp": sc_emax_clamp,

@@ -110,7 +110,8 @@ def test_gpu_matches_oracle_bit_exact(gpu_lib, name):
 
 @pytest.mark.parametrize("name,nstrips,halo", [("minimal", 2, 2), ("periodic_grid", 2, 5), ("tripolar", 3, 6),
                                                ("land_block", 4, 2), ("fast_box", 3, 5), ("periodic_x_only", 2, 3),
-                                               ("growing_winds_persist", 2, 2)])
+                                               ("growing_winds_persist", 2, 2), ("growing_winds", 3, 2),
+                                               ("pulse_winds", 2, 2)])
 def test_gpu_strips_match_oracle(gpu_lib, name, nstrips, halo):
     g, P, wind, DT, n = SCENARIOS[name]()
     run_pair(make_oracle(g, P), StripSet(g, P, nstrips, halo), wind, DT, n, compare_models)
@@ -293,7 +294,7 @@ def test_gpu_output_fields_and_async_snapshots(gpu_lib):
         assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
 
 
-@pytest.mark.parametrize("name", ["growing_winds_persist", "tripolar", "maxiters"])
+@pytest.mark.parametrize("name", ["growing_winds_persist", "tripolar", "maxiters", "pulse_winds"])
 def test_gpu_checkpoint_resume_is_bit_identical(gpu_lib, name):
     """run k steps, checkpoint, continue; a fresh handle restored from the blob continues with the
     same bits (particle controller memory, pending dt resets, retcodes and wind level included)."""
@@ -326,6 +327,14 @@ def test_gpu_checkpoint_resume_is_bit_identical(gpu_lib, name):
     from picles_b200 import PiclesError
     with pytest.raises(PiclesError, match="ERR_ARG"):
         other.restore(blob)
+    # ... and so is one written under other parameters (the restored controller / AutoSwitch state would not match)
+    P2 = default_params(DT=DT, dtmin=2e-4)
+    with pytest.raises(PiclesError, match="different parameters"):
+        engine_for(g, P2).restore(blob)
+    # intermediate wind levels staged for the next step are not part of a blob: saving then is refused
+    a.set_wind_midlevels([wind(t + DT / 2)[0]], [wind(t + DT / 2)[1]])
+    with pytest.raises(PiclesError, match="intermediate wind levels"):
+        a.checkpoint()
 
 
 def test_gpu_state_roundtrip_and_accessors(gpu_lib):

@@ -204,3 +204,76 @@ def test_wind_mesh_sampler_against_scipy():
     a, _ = oracle.wind_mesh_sample(xw, yw, tw, U, V, x, y, 1234.0)
     b, _ = oracle.wind_mesh_sample(xw, yw, tw, U, V, x + Lx, y - Ly, 1234.0 + Lt)
     assert np.max(np.abs(a - b)) < 1e-9
+
+
+# ---- B-1 as run: the wind a switched-off particle is tested against ---------------------------
+
+@pytest.mark.parametrize("shape", ["strengthening", "pulse"])
+def test_off_particles_test_the_wind_at_their_own_clock(shape):
+    """mapping_2D.jl:132,172-176: an off particle is tested against winds(x, y, integ.t + DT).  As the
+    reference runs (`on` frozen at seed, SURVEY B-1) a particle seeded off never integrates, so its
+    clock stays at 0 and that time is DT on every step.  The closure-mode oracle calls the closure
+    there literally; the staged-level paths (oracle and the device code) must take the same
+    decisions from the level they keep from the first step — and would not with the model-clock
+    level t + DT, which both winds make visible: one that is calm at DT and strengthens later (never
+    reseeded, the clock level would), and a pulse that peaks at DT (reseeded on every step, the clock
+    level would stop after the first)."""
+    g = cartesian_grid(12, 9)
+    DT, nsteps = 900.0, 7
+    P = default_params(DT=DT, wind_min_squared=2.0)
+
+    def amp(t):
+        if shape == "strengthening":
+            return 0.9 * (0.5 + t / DT)          # |u| = 1.35 at DT: speed^2 = 1.9125 < 2
+        return 0.3 + 1.5 * math.exp(-((t - DT) / DT) ** 2)  # 0.85 at 0, 1.8 at DT, back to 0.85 at 2 DT
+
+    def wind(x, y, t):
+        return (amp(t) if x < 12000.0 else 0.2), 0.3
+
+    def arrays(t):
+        u = np.where(g["x"] < 12000.0, amp(t), 0.2)
+        return u, np.full_like(u, 0.3)
+
+    exact = make_oracle(g, P)
+    exact.set_wind_closure(wind, g["x"], g["y"])
+    staged = make_oracle(g, P)
+    dev = HostShim(g, P)
+    for m in (exact, staged, dev):
+        m.seed(*arrays(0.0))
+    off = (staged.particles()["flags"] & 9) == 8  # iterated and seeded off: all of them
+    assert off.sum() == 10 * 7
+    windy = int((off & (g["x"] < 12000.0)).sum())
+    lag_rule, clock_rule = [], []
+    t = 0.0
+    for k in range(nsteps):
+        for m in (exact, staged, dev):
+            m.step(t, DT, *arrays(t), *arrays(t + DT))
+        u1, v1 = arrays(t + DT)
+        clock_rule.append(int(((u1 * u1 + v1 * v1 >= 2.0) & off).sum()))
+        t += DT
+        ce, cs, cd = exact.counters(), staged.counters(), dev.counters()
+        assert ce["n_reseed_advance"] == cs["n_reseed_advance"] == cd["n_reseed_advance"]
+        assert ce["n_deposited"] == cs["n_deposited"] == cd["n_deposited"]
+        for nm in ("n_remesh_A", "n_remesh_B", "n_remesh_D"):
+            assert ce[nm] == cs[nm] == cd[nm]
+        assert bits_equal(staged.state(), dev.state())
+        # nobody integrates (`on` is frozen off), so State holds re-deposited wind seas only and the closure
+        # run has nothing to differ by
+        assert ce["n_integrated"] == 0 and bits_equal(exact.state(), staged.state())
+        lag_rule.append(cs["n_reseed_advance"])
+    if shape == "strengthening":
+        assert lag_rule == [0] * nsteps and clock_rule[0] == 0 and clock_rule[-1] == windy
+    else:
+        assert lag_rule == [windy] * nsteps and clock_rule == [windy] + [0] * (nsteps - 1)
+    compare_models(staged, dev)
+    # as intended (on_persist): `on` follows the remesh, a particle that is switched on integrates from then on
+    P2 = default_params(DT=DT, wind_min_squared=2.0, on_persist=True)
+    a, b = make_oracle(g, P2), HostShim(g, P2)
+    for m in (a, b):
+        m.seed(*arrays(0.0))
+    t = 0.0
+    for k in range(nsteps):
+        for m in (a, b):
+            m.step(t, DT, *arrays(t), *arrays(t + DT))
+        t += DT
+    compare_models(a, b)
