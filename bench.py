@@ -3,13 +3,18 @@
 
   python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the C ABI)
   python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on all host cores
+  (N > 1: launched by torch.distributed.run, one rank per GPU)
 
 Workload (BASELINE.json configs[1]): T04_2D_reg_test_large_grid / bench06 homogeneous box
 scaled to 4096x4096 Cartesian, dx=dy=2 km, constant wind u=v=10 m/s, model step 10 min,
 example_00_minimal ODE settings (Tsit5 controller, dt=1e-3, dtmin=1e-4, force_dtmin).
 A "step" is one model step: State .= 0; advance! (adaptive RK over DT for every particle);
 ParticleToNode! projection; remesh!.  With N GPUs every rank owns a 4096x4096 y-strip of a
-4096 x (4096*N) box (weak scaling) and exchanges a halo of particle records per step.
+4096 x (4096*N) box (weak scaling: `value`) and exchanges a halo of particle records per step.
+Two more legs run when N > 1, untimed by the headline: `strong` — the FIXED 4096x4096 box cut in N
+strips, with the same box on one GPU timed by rank 0 in the same process (BASELINE.md's 85 % target
+is on this) — and `strip_parity` — a small growing-wind box stepped in N strips over NCCL and as one
+domain on rank 0, compared bit for bit.
 
 One JSON line is printed by rank 0.  See DESIGN.md §measurement for every field.
 """
@@ -27,14 +32,21 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "tests")):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the 4096^2 bench step, from the
-# committed ncu --set full captures (profiles/r01_ncu_final.txt); never measured under the timer
-NCU_TRAFFIC = {"k_advance": 3.61e9, "k_project_remesh": 1.80e9, "k_wind_sample": 0.49e9}
-NCU_FP64_PIPE_PCT = 60.1  # sm__pipe_fp64_cycles_active of k_advance (profiles/r01_ncu_final.txt)
+
+def ncu_record():
+    """What ncu measured, never under the timer: dram__bytes_read.sum + dram__bytes_write.sum per launch and
+    sm__pipe_fp64_cycles_active of the kernels of the 4096^2 bench step, read from the tracked summary that
+    profiles/ncu_to_json.py writes from the committed `ncu --set full` captures.  The file names the commit
+    the captured library was built from; the bench line carries that stamp next to the numbers."""
+    p = os.path.join(ROOT, "profiles", "ncu_metrics.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {"commit": None, "kernels": {}}
 
 METRIC = "particle-steps/s"
 UNIT = "particle-steps/s"
@@ -74,18 +86,17 @@ def workload(nx, ny_per_gpu, n_gpus, rank):
 SOLVER = "Tsit5"
 
 
-def params(solver=None):
+def params(solver=None, DT=600.0, wind_min_squared=4.0):
     """example_00_minimal.jl:17-67 settings (T04_2D_reg_test uses the same), flattened by the host
     mirror of the reference API — no test or oracle module is involved on the b200 arm."""
     from picles_b200 import FetchRelations as FR
     from picles_b200.ParticleSystems import particle_waves_v5 as PW
     from picles_b200.params import make_params
-    DT = 600.0
     pars, cid, _ = PW.ODEParameters(r_g=0.85)
     ps = PW.particle_equations(None, None, γ=cid.γ, q=cid.q)
     sets = PW.ODESettings(Parameters=pars, log_energy_minimum=FR.MinimalWindsea(10, 10, DT)["lne"], saving_step=DT,
                           timestep=DT, total_time=6 * 86400.0, dt=1e-3, dtmin=1e-4, force_dtmin=True,
-                          solver=solver or SOLVER)
+                          solver=solver or SOLVER, wind_min_squared=wind_min_squared)
     return make_params(sets, ps, FR.MinimalState(2, 2, DT), defaults=None, periodic_boundary=False, on_persist=False)
 
 
@@ -154,31 +165,47 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------
-def cpu_arm(steps, warmup, sample_n=512, threads=None):
-    """The reference arm / cpu_baseline: the oracle port (OpenMP over particles in the ODE
-    phase, serial canonical-order deposit) on the host cores, on a bounded sample of the
-    same workload: a sample_n x sample_n homogeneous box, the same step indices."""
-    import oracle
+def _cpu_run(sample_n, steps, warmup, threads):
+    """seed + warmup + `steps` timed model steps of a sample_n x sample_n homogeneous box on the CPU port"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))  # the CPU legs (and only they) use the tests' oracle builders
     from common import cartesian_grid, make_oracle
-    threads = threads or os.cpu_count() or 1
     g = cartesian_grid(sample_n, sample_n)
     o = make_oracle(g, params(), variant="omp", threads=threads)
-    o.seed(10.0, 10.0)
+    w = np.full((sample_n, sample_n), 10.0)  # one contiguous plane, passed for all four levels: nothing is copied per step
+    o.seed(w, w)
     t = 0.0
     for _ in range(warmup):
-        o.step(t, 600.0, 10.0, 10.0, 10.0, 10.0)
+        o.step(t, 600.0, w, w, w, w)
         t += 600.0
-    n_active = (sample_n - 2) ** 2
     t0 = time.perf_counter()
     for _ in range(steps):
-        o.step(t, 600.0, 10.0, 10.0, 10.0, 10.0)
+        o.step(t, 600.0, w, w, w, w)
         t += 600.0
     dt = time.perf_counter() - t0
     c = o.counters()
-    return dict(value=n_active * steps / dt, unit=UNIT, cores=threads, kind="port",
-                sample=f"{sample_n}x{sample_n} homogeneous box (same physics/settings), steps {warmup + 1}..{warmup + steps}, "
+    return dt, (sample_n - 2) ** 2, c["n_substeps"] / max(c["n_integrated"], 1)
+
+
+def cpu_arm(steps, warmup, sample_n=None, threads=None, full_n=4096, budget_s=240.0):
+    """The reference arm / cpu_baseline: the oracle port (OpenMP over particles in the ODE phase, serial
+    canonical-order deposit) on all host cores.  sample_n = None: the TRUE workload (full_n x full_n, the same
+    step indices) when a probe says warmup + steps fit `budget_s` on this host, else the largest power-of-two
+    sample that does; the line says which."""
+    threads = threads or os.cpu_count() or 1
+    chosen = sample_n
+    if chosen is None:
+        probe_n = 512
+        dt, n_act, _ = _cpu_run(probe_n, 1, 1, threads)
+        per_particle = dt / n_act
+        chosen = full_n
+        while chosen > probe_n and per_particle * (chosen - 2) ** 2 * (steps + warmup + 1.5) > budget_s:
+            chosen //= 2
+    dt, n_active, sub = _cpu_run(chosen, steps, warmup, threads)
+    what = "the full workload" if chosen == full_n else "a bounded sample of the workload"
+    return dict(value=n_active * steps / dt, unit=UNIT, cores=threads, kind="port", sample_n=chosen, is_full=(chosen == full_n),
+                sample=f"{chosen}x{chosen} homogeneous box ({what}; same physics/settings), steps {warmup + 1}..{warmup + steps}, "
                        f"oracle/picles_oracle.c with OpenMP over particles; {dt:.2f} s wall",
-                ms_per_step=dt / steps * 1e3, substeps_per_particle_step=c["n_substeps"] / max(c["n_integrated"], 1))
+                ms_per_step=dt / steps * 1e3, substeps_per_particle_step=sub)
 
 
 _REAL_STDOUT = None
@@ -199,6 +226,142 @@ def emit(line):
     out.flush()
 
 
+def growing_wind(x_nodes):
+    """BASELINE configs[2] shape (tests/T04_2D_growing_decaying_winds.jl:126-132): calm foot, linear ramp in x,
+    modulated in time so every step stages two different levels; on/off particle thresholds are in play"""
+    Lx = float(x_nodes.max())
+    x0 = 50.0 / 260.0 * Lx
+    ramp = np.where(x_nodes < x0, 0.01, (x_nodes - x0) / (Lx - x0))
+    return lambda t: (10.0 * ramp * (0.6 + 0.4 * np.sin(2 * np.pi * t / 7200.0)), 3.0 * ramp + 0.05)
+
+
+def strip_parity_leg(dist, rank, world, local_rank, nx=512, rows_per_rank=256, steps=6):
+    """N strips over NCCL (picles_step_strip: in-library exchange, reach all-reduce) against ONE domain on
+    rank 0's GPU, same box, same winds: State, particle state and flags compared bit for bit after every
+    step.  Growing/decaying winds: time-varying levels, particles seeded off, reseeds, both remesh branches."""
+    from picles_b200.distributed import StripStepper
+    from picles_b200.engine import B200Engine
+    DT = 1200.0
+    Ny = rows_per_rank * world
+    P = params(DT=DT, wind_min_squared=2.0)
+    mask = np.ones((Ny, nx), np.uint8)
+    mask[:, 0] = mask[:, -1] = 3
+    mask[0, :] = mask[-1, :] = 3
+    Mc = np.array([1 / 4000.0, 0.0, 0.0, 1 / 4000.0])
+    X = np.broadcast_to(np.arange(nx) * 4000.0, (Ny, nx))
+    wind = growing_wind(X)
+    full = lambda a: np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.float64), (Ny, nx)))
+    j0, j1 = rank * rows_per_rank, (rank + 1) * rows_per_rank
+    eng = B200Engine(nx, Ny, 0, 0, mask[j0:j1], P, M_const=Mc, device=local_rank, j0=j0, ny_local=j1 - j0, halo=2)
+    st = StripStepper(eng, rank, world, periodic_y=False)
+    ref = B200Engine(nx, Ny, 0, 0, mask, P, M_const=Mc, device=local_rank) if rank == 0 else None
+    u0, v0 = [full(a) for a in wind(0.0)]
+    eng.seed(u0[j0:j1], v0[j0:j1])
+    if ref is not None:
+        ref.seed(u0, v0)
+    t, bad, compared = 0.0, [], 0
+    for k in range(steps):
+        w = [full(a) for a in (*wind(t), *wind(t + DT))]
+        st.step(t, DT, winds=[a[j0:j1] for a in w])
+        if ref is not None:
+            ref.step(t, DT, *w)
+        t += DT
+        pr = eng.particles()
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object((eng.state(), pr["z"], pr["flags"], eng.counters()["n_active"]), parts, dst=0)
+        if rank == 0:
+            S = np.concatenate([q[0] for q in parts], axis=1)
+            Z = np.concatenate([q[1] for q in parts], axis=1)
+            F = np.concatenate([q[2] for q in parts], axis=0)
+            rp = ref.particles()
+            act = (rp["flags"] & 8) != 0
+            same = lambda a, b: bool(np.all((a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))))
+            if not same(ref.state(), S):
+                bad.append(f"State after step {k + 1}")
+            if not all(same(rp["z"][c][act], Z[c][act]) for c in range(5)):
+                bad.append(f"particles after step {k + 1}")
+            if not np.array_equal(rp["flags"][act], F[act]):
+                bad.append(f"flags after step {k + 1}")
+            if sum(q[3] for q in parts) != ref.counters()["n_active"]:
+                bad.append(f"n_active after step {k + 1}")
+            compared += 1
+    off = int(((ref.particles()["flags"] & 9) == 8).sum()) if ref is not None else 0
+    eng.close()
+    if ref is not None:
+        ref.close()
+        return {"result": "bit-exact" if not bad else "MISMATCH: " + "; ".join(bad[:4]), "strips": world,
+                "box": f"{nx}x{Ny} Cartesian, growing/decaying winds (BASELINE configs[2] shape), DT=1200 s, halo 2",
+                "steps_compared": compared, "compared": ["State", "particle u[5]", "particle flags", "n_active"],
+                "against": "the same box as ONE domain on rank 0's GPU (picles_step)", "transport": "NCCL inside the library (picles_step_strip)",
+                "particles_seeded_off": off}
+    return None
+
+
+def strong_leg(dist, rank, world, local_rank, args, barrier_all):
+    """the FIXED nx x nx box cut in `world` y-strips; the same box on ONE GPU is timed by
+    rank 0 in the same process, the same step indices (the work per step falls over the first steps)."""
+    import torch
+    from picles_b200.distributed import StripStepper, strip_bounds
+    from picles_b200.engine import B200Engine
+    n = args.nx
+    P = params()
+    Wf = workload(n, n, 1, 0)
+    j0, j1 = strip_bounds(n, world)[rank]
+    eng = B200Engine(n, n, 0, 0, Wf["mask"][j0:j1], P, M_const=Wf["M_const"], device=local_rank, j0=j0, ny_local=j1 - j0,
+                     halo=args.halo)
+    st = StripStepper(eng, rank, world, periodic_y=False)
+    eng.seed(10.0, 10.0)
+    t = 0.0
+    for _ in range(args.warmup):
+        st.step(t, 600.0)
+        t += 600.0
+    barrier_all(eng)
+    eng.timer_start()
+    n_act, ms_adv = 0, []
+    for _ in range(args.steps):
+        st.step(t, 600.0)
+        t += 600.0
+        c = eng.counters()
+        n_act += c["n_active"]
+        ms_adv.append(c["ms_advance"])
+    ms = eng.timer_stop()
+    barrier_all(eng)
+    tt = torch.tensor([ms, float(np.mean(ms_adv))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ww = torch.tensor([float(n_act)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+    rows = eng.halo_rows()[0]
+    eng.close()
+    one = None
+    if rank == 0:
+        e1 = B200Engine(n, n, 0, 0, Wf["mask"], P, M_const=Wf["M_const"], device=local_rank)
+        e1.seed(10.0, 10.0)
+        t1 = 0.0
+        for _ in range(args.warmup):
+            e1.step(t1, 600.0)
+            t1 += 600.0
+        e1.synchronize()
+        e1.timer_start()
+        n1 = 0
+        for _ in range(args.steps):
+            e1.step(t1, 600.0)
+            t1 += 600.0
+            n1 += e1.counters()["n_active"]
+        ms1 = e1.timer_stop()
+        e1.close()
+        one = n1 / (ms1 * 1e-3)
+    barrier_all(None)
+    if rank != 0:
+        return None
+    ms_all, adv_all = tt.tolist()
+    v = ww.item() / (ms_all * 1e-3)
+    return {"scaling": "strong", "workload": f"the fixed {n}x{n} box of config.workload cut in {world} y-strips of {n // world} rows",
+            "value": v, "unit": UNIT, "n_gpus": world, "ms_per_step": ms_all / args.steps, "ms_advance_max_rank": adv_all,
+            "halo_rows_exchanged": rows, "value_1gpu_same_run": one, "ms_per_step_1gpu": 1e3 * (n - 2) ** 2 / one,
+            "efficiency": v / (world * one), "target": 0.85,
+            "timing": "CUDA events around the K steps on every rank, max over ranks; rank 0 then times the same box as one domain"}
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -209,9 +372,12 @@ def main():
     ap.add_argument("--nx", type=int, default=4096)
     ap.add_argument("--ny", type=int, default=4096, help="rows per GPU")
     ap.add_argument("--halo", type=int, default=2)
-    ap.add_argument("--cpu-sample", type=int, default=1024)
+    ap.add_argument("--cpu-sample", type=int, default=None,
+                    help="side of the box the CPU port is timed on (default: the full workload when it fits the time budget, "
+                         "else the largest power-of-two sample that does; the cpu_baseline of the b200 arm always samples 1024)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="N > 1: skip the strong-scaling and strip-parity legs")
     ap.add_argument("--solver", default="Tsit5", choices=["Tsit5", "DP5", "AutoTsit5"],
                     help="ODESettings.solver; AutoTsit5 = the reference's default AutoTsit5(Rosenbrock23()): the same "
                          "arithmetic as Tsit5 on this workload (the stiffness monitor never fires) plus the monitor")
@@ -234,15 +400,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cb = cpu_arm(args.steps, args.warmup, args.cpu_sample)
+        # the reference's CPU path on ONE strip's workload (the per-GPU unit of the weak-scaling arm): nx x ny
+        cb = cpu_arm(args.steps, args.warmup, args.cpu_sample, full_n=args.nx)
+        if not cb["is_full"]:
+            config["workload"] += f" [this arm: timed on a {cb['sample_n']}x{cb['sample_n']} sample of it, see cpu_baseline.sample]"
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config, "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0,
+                "gpu_launches": 0, "sample_is_full_workload": cb["is_full"],
                 "note": "Julia is not installed on this image: the reference's CPU path is timed as its C port "
-                        "(oracle/), all host threads; BASELINE.md quotes 4-7e4 particle-steps/s for the Julia original"}
+                        "(oracle/), all host threads; BASELINE.md quotes 4-7e4 particle-steps/s for the Julia original. "
+                        "One host runs one box whatever --gpus says (the reference has no domain decomposition)"}
         emit(line)
         return 0
 
@@ -282,8 +452,9 @@ def main():
         else:
             stepper.step(t, 600.0, host_ptrs)
 
-    def barrier():
-        eng.synchronize()
+    def barrier(e=eng):
+        if e is not None:
+            e.synchronize()
         if dist is not None:
             dist.barrier()
             import torch
@@ -300,15 +471,19 @@ def main():
     if rank == 0:
         sampler.start()
     per_step = []
+    hist = np.zeros(48, np.int64)
     barrier()
+    launches0 = eng.launch_count()
     eng.timer_start()
     for _ in range(args.steps):
         do_step(t)
         t += 600.0
         per_step.append(eng.counters())
     ms_total = eng.timer_stop()
+    launches = eng.launch_count() - launches0  # counted by the library where it launches; timer_stop launches nothing
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    hist += eng.attempt_histogram()            # of the last timed step
     n_active = sum(c["n_active"] for c in per_step)  # particle-steps of this rank in the region
 
     # ---- the reference's default solver on the same workload ---------------------------------
@@ -342,6 +517,7 @@ def main():
 
     # ---- timed region B: end to end through host buffers ----------------------------
     e2e = None
+    e2e_store = None
     if not args.no_e2e:
         import torch
         # pinned host staging of the step's inputs: wind at t+DT evaluated on the host mesh
@@ -364,6 +540,30 @@ def main():
         wall_e2e = (time.perf_counter() - t0) * 1e3
         ms_e2e = max(ms_e2e, wall_e2e)  # host-side work (API, staging) counts end to end
         e2e = dict(ms=ms_e2e, n=n_e2e, h2d=2 * n_nodes * 8, d2h=ctypes.sizeof(ctypes.c_double) * 1024 + 88)
+
+        # ---- the same with the step's full result brought back: run!(...; cash_store=true) pushes State to the
+        # host after every step (src/Simulations/run.jl:104-112).  picles_snapshot_begin stages State on the compute
+        # stream and copies it to pinned host memory on its own stream while the next step integrates; the copy of
+        # the last step is waited for inside the timed region.
+        snap = eng.pinned_state_buffer()
+        do_step(t, ptrs)
+        t += 600.0
+        eng.snapshot_begin(snap)
+        eng.snapshot_wait()
+        barrier()
+        t0 = time.perf_counter()
+        eng.timer_start()
+        n_st = 0
+        for _ in range(args.steps):
+            do_step(t, ptrs)
+            t += 600.0
+            eng.snapshot_begin(snap)   # waits for the previous step's copy first: one snapshot in flight
+            n_st += eng.counters()["n_active"]
+        eng.snapshot_wait()
+        ms_st = eng.timer_stop()
+        barrier()
+        ms_st = max(ms_st, (time.perf_counter() - t0) * 1e3)
+        e2e_store = dict(ms=ms_st, n=n_st, checksum=float(snap[0].sum()))
 
     # ---- timed region C: end to end with a device-resident wind mesh (wind ingestion) ----------
     # Same workload; the wind comes from a gridded field kept on the device (9 x 9 x 3 knots of
@@ -398,19 +598,31 @@ def main():
     # ---- reduce over ranks: max time, sum of work ------------------------------------
     if dist is not None:
         import torch
-        tt = torch.tensor([ms_total, e2e["ms"] if e2e else 0.0, e2e_mesh["ms"] if e2e_mesh else 0.0],
-                          dtype=torch.float64, device="cuda")
+        tt = torch.tensor([ms_total, e2e["ms"] if e2e else 0.0, e2e_mesh["ms"] if e2e_mesh else 0.0,
+                           e2e_store["ms"] if e2e_store else 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ww = torch.tensor([float(n_active), float(e2e["n"]) if e2e else 0.0, float(e2e_mesh["n"]) if e2e_mesh else 0.0],
-                          dtype=torch.float64, device="cuda")
+        ww = torch.tensor([float(n_active), float(e2e["n"]) if e2e else 0.0, float(e2e_mesh["n"]) if e2e_mesh else 0.0,
+                           float(e2e_store["n"]) if e2e_store else 0.0, float(launches)], dtype=torch.float64, device="cuda")
         dist.all_reduce(ww, op=dist.ReduceOp.SUM)
-        ms_total, ms_e2e_all, ms_mesh_all = tt.tolist()
-        n_active_all, n_e2e_all, n_mesh_all = ww.tolist()
+        ms_total, ms_e2e_all, ms_mesh_all, ms_store_all = tt.tolist()
+        n_active_all, n_e2e_all, n_mesh_all, n_store_all, launches_all = ww.tolist()
     else:
         ms_e2e_all = e2e["ms"] if e2e else 0.0
         ms_mesh_all = e2e_mesh["ms"] if e2e_mesh else 0.0
+        ms_store_all = e2e_store["ms"] if e2e_store else 0.0
         n_active_all, n_e2e_all = float(n_active), float(e2e["n"]) if e2e else 0.0
         n_mesh_all = float(e2e_mesh["n"]) if e2e_mesh else 0.0
+        n_store_all = float(e2e_store["n"]) if e2e_store else 0.0
+        launches_all = float(launches)
+
+    # ---- N > 1: the strong-scaling record and NCCL strip parity (untimed by the headline) ----------
+    strong = parity = None
+    if dist is not None and not args.no_extra_legs:
+        eng.close()
+        eng = None
+        strong = strong_leg(dist, rank, world, local_rank, args, barrier)
+        parity = strip_parity_leg(dist, rank, world, local_rank)
+        barrier(None)
 
     if rank != 0:
         if dist is not None:
@@ -420,7 +632,10 @@ def main():
     # ---- rooflines from the live CUDA-event times of the timed region ------------------
     ms_adv = float(np.mean([c["ms_advance"] for c in per_step]))
     ms_prj = float(np.mean([c["ms_project"] for c in per_step]))
+    ncu = ncu_record()
     std_size = (args.nx, args.ny) == (4096, 4096)  # the size the committed ncu captures were taken at
+    nk = ncu.get("kernels", {}) if std_size else {}
+    ncu_src = {"file": "profiles/ncu_metrics.json", "library_commit": ncu.get("commit"), "captured_with": ncu.get("command")}
     rhs = float(np.mean([c["n_rhs"] for c in per_step]))
     att = float(np.mean([c["n_substeps"] + c["n_rejects"] for c in per_step]))
     integ = float(np.mean([c["n_integrated"] for c in per_step]))
@@ -429,39 +644,47 @@ def main():
     adv_tf = flops / (ms_adv * 1e-3) / 1e12
     prj_gbs = n_nodes * B_PROJECT_REMESH / (ms_prj * 1e-3) / 1e9
     roofline = {"kernel": "k_advance", "bound": "fp64", "achieved": adv_tf, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": adv_tf / fp64_peak, "traffic": NCU_TRAFFIC.get("k_advance") if std_size else None,
+                "unit": "TFLOP/s", "frac": adv_tf / fp64_peak, "traffic": nk.get("k_advance", {}).get("dram_bytes"),
                 "peak_source": "DFMA-chain microbenchmark run in this process (picles_measure_fp64_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "flop_model": {"F_RHS": F_RHS, "F_ATTEMPT": F_ATTEMPT, "F_INITDT": F_INITDT, "F_DEPOSIT": F_DEPOSIT,
                                "rhs_per_launch": rhs, "attempts_per_launch": att},
-                "ncu_fp64_pipe_active_pct": NCU_FP64_PIPE_PCT,
+                "ncu_fp64_pipe_active_pct": nk.get("k_advance", {}).get("fp64_pipe_pct"), "ncu_source": ncu_src,
                 "ms_per_launch": ms_adv, "share_of_step": ms_adv / (ms_adv + ms_prj)}
     roofline_hbm = [
         {"kernel": "k_project_remesh", "bound": "hbm", "achieved": prj_gbs, "peak": hbm_peak, "unit": "GB/s",
-         "frac": prj_gbs / hbm_peak, "traffic": NCU_TRAFFIC.get("k_project_remesh") if std_size else None,
+         "frac": prj_gbs / hbm_peak, "traffic": nk.get("k_project_remesh", {}).get("dram_bytes"), "ncu_source": ncu_src,
          "bytes_per_node": B_PROJECT_REMESH, "nodes_per_launch": n_nodes, "ms_per_launch": ms_prj,
          "share_of_step": ms_prj / (ms_adv + ms_prj), "peak_source": hbm_src},
     ]
 
     value = n_active_all / (ms_total * 1e-3)
+    nz = np.nonzero(hist)[0]
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "roofline": roofline, "roofline_hbm": roofline_hbm,
             "measured_here": {"fp64_dfma_tflops": fp64_peak, "hbm_copy_gbs": hbm_meas},
             "clocks": clocks,
-            # ours, per step of the resident-input region: k_advance + k_project_remesh; on strips the
-            # advance is three launches (two boundary blocks first, then the interior) plus
-            # k_halo_pack and k_halo_unpack around NCCL's own send/recv kernel
-            "gpu_launches": (2 if world == 1 else 6) * args.steps,
+            # counted by the library at every kernel launch (picles_launch_count), summed over ranks, resident-input region:
+            # per step and rank k_advance + k_project_remesh; on strips the advance is three launches (two boundary blocks
+            # first, then the interior) plus k_halo_pack and k_halo_unpack (NCCL's own kernels are not ours and not counted)
+            "gpu_launches": int(launches_all),
             "substeps_per_particle_step": float(np.mean([c["n_substeps"] / max(c["n_integrated"], 1) for c in per_step])),
             "max_attempts": int(max(c["max_attempts"] for c in per_step)),
+            "attempt_histogram_last_step": {str(int(k)): int(hist[k]) for k in nz},
             "rejects": int(sum(c["n_rejects"] for c in per_step)),
             "failed": int(sum(c["n_failed"] for c in per_step))}
     if e2e:
         line["e2e"] = {"value": n_e2e_all / (ms_e2e_all * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                        "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": ms_e2e_all / args.steps,
                        "api": "picles_step through the C ABI with pinned host wind buffers + picles_state_energy_sum"}
+    if e2e_store:
+        line["e2e_store"] = {"value": n_store_all / (ms_store_all * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                             "d2h_bytes_per_step": 3 * n_nodes * 8 + 88, "ms_per_step": ms_store_all / args.steps,
+                             "state_checksum": e2e_store["checksum"],
+                             "api": "picles_step with pinned host wind buffers + picles_snapshot_begin/wait of the whole State "
+                                    "into pinned host memory every step (run!(...; cash_store=true), run.jl:104-112)"}
     if auto_variant:
         line["default_solver_variant"] = auto_variant
     if e2e_mesh:
@@ -475,12 +698,16 @@ def main():
         line["roofline_hbm"].append({"kernel": "k_wind_sample", "note": "k_wind_timeblend (mesh-sized, ~3 us) + k_wind_sample, timed as a pair",
                                      "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
                                      "unit": "GB/s", "frac": gbs / hbm_peak,
-                                     "traffic": NCU_TRAFFIC.get("k_wind_sample") if std_size else None, "bytes_per_node": 32,
+                                     "traffic": nk.get("k_wind_sample", {}).get("dram_bytes"), "ncu_source": ncu_src, "bytes_per_node": 32,
                                      "nodes_per_launch": n_nodes, "ms_per_launch": e2e_mesh["ms_sample"],
                                      "share_of_step": e2e_mesh["ms_sample"] / (ms_adv + ms_prj + e2e_mesh["ms_sample"]),
                                      "peak_source": hbm_src})
+    if strong:
+        line["strong"] = strong
+    if parity:
+        line["strip_parity"] = parity
     if not args.no_cpu_baseline:
-        cb = cpu_arm(min(args.steps, 3), args.warmup, args.cpu_sample)
+        cb = cpu_arm(min(args.steps, 3), args.warmup, 1024 if args.cpu_sample is None else args.cpu_sample)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     emit(line)
     if dist is not None:

@@ -287,11 +287,16 @@ int picles_halo_exchange(picles_t* h, int lo_rank, int hi_rank);
  *   - picles_step_strip widens the exchange to the all-reduced reach (ncclAllReduce(max), 4 bytes) on every
  *     strip and repeats exchange + gather by itself (the advance is not repeated);
  *   - picles_step_project_remesh (host-driven exchange) returns PICLES_ERR_HALO naming the rows needed:
- *     call picles_halo_widen on every strip, repeat the exchange and the call.  A host that all-reduces
- *     picles_get_reach itself widens before the exchange and never sees the error.
+ *     call picles_halo_widen on every strip, repeat the exchange and the call.  The check sees this strip's own
+ *     reach and the reach of the rows it received; give it the all-reduced picles_get_reach of the step
+ *     (picles_set_global_reach) and every strip refuses together.  A host that widens from that all-reduced
+ *     reach before the exchange never sees the error.
  * The exchange is never narrowed again.  A reach beyond rows_max is a PICLES_ERR_HALO that stands.
  */
 int picles_halo_rows(picles_t* h, int* rows_exchanged, int* rows_max);
+/* host-driven exchange: the all-reduced (max over strips) picles_get_reach of this step, so that the gather's check
+   covers deposits of a neighbour's interior rows too; call between picles_step_advance and picles_step_project_remesh */
+int picles_set_global_reach(picles_t* h, int reach);
 int picles_halo_widen(picles_t* h, int rows);
 int picles_step_strip(picles_t* h, double t, double dt_model,
                       const double* u_t, const double* v_t,

@@ -117,6 +117,7 @@ SYMBOLS = {
     "picles_seed": (C.c_int, [_vp, _vp, _vp]),
     "picles_halo_rows": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "picles_halo_widen": (C.c_int, [_vp, C.c_int]),
+    "picles_set_global_reach": (C.c_int, [_vp, C.c_int]),
     "picles_get_attempt_histogram": (C.c_int, [_vp, _vp, C.c_int]),
     "picles_launch_count": (C.c_int64, []),
     "picles_step": (C.c_int, [_vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp]),

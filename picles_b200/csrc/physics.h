@@ -749,7 +749,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
 #else
     const bool nz = TSIT5 == 1; /* the host build serves every solver from one AUTOSW instantiation; TSIT5 only when asked (tests) */
 #endif
-    /* TSIT5 == 2 (profiles/ variant PH_DP5_CT): DP5's tableau at compile time; its two zero coefficients,
+    /* TSIT5 == 2: DP5's tableau at compile time; its two zero coefficients,
        a[7][2] and bt[2], are tested where they are and nowhere else */
     const bool dz = !nz && TSIT5 == 2;
     const Tableau& T = nz ? tableau(PICLES_SOLVER_TSIT5) : (dz ? tableau(PICLES_SOLVER_DP5) : tableau(P.solver));
@@ -1046,7 +1046,8 @@ PM_HD int32_t cell_reach(int32_t cell) {
 /* read-only view of the deposit records of one strip (+ halo rows) */
 struct RecView {
     int Nx, Ny, bx, by; /* global shape and boundary types */
-    int j0, ny, halo;   /* strip: first owned global row (0-based), rows owned, halo rows */
+    int j0, ny, halo;   /* strip: first owned global row (0-based), rows owned, halo rows the planes hold on each side */
+    int hx;             /* ... of which the hx next to the owned rows carry this step's neighbour records */
     int pitch;          /* elements between consecutive rows of the record planes (>= Nx) */
     const double *e, *mx, *my, *wx, *wy;
     const int32_t* cell;
@@ -1054,13 +1055,16 @@ struct RecView {
 
 /* local extended row of global 1-based row j, or -1 */
 PM_HD int ext_row(const RecView& V, int64_t j) {
+    /* only the hx halo rows next to the owned ones were exchanged: a row further out is not "that row,
+       empty" but a row this strip does not have — on a periodic ring it may still be there as a wrapped row */
+    const int64_t lo = V.halo - V.hx, hi = V.ny + V.halo + V.hx;
     int64_t r = j - 1 - V.j0 + V.halo;
-    if (r >= 0 && r < V.ny + 2 * V.halo) return (int)r;
+    if (r >= lo && r < hi) return (int)r;
     if (V.by == PICLES_BND_PERIODIC) { /* wrapped neighbour rows live in the halo */
         r = j + V.Ny - 1 - V.j0 + V.halo;
-        if (r >= 0 && r < V.ny + 2 * V.halo) return (int)r;
+        if (r >= lo && r < hi) return (int)r;
         r = j - V.Ny - 1 - V.j0 + V.halo;
-        if (r >= 0 && r < V.ny + 2 * V.halo) return (int)r;
+        if (r >= lo && r < hi) return (int)r;
     }
     return -1;
 }

@@ -46,6 +46,7 @@ struct picles_handle {
     char *send_lo = nullptr, *send_hi = nullptr, *recv_lo = nullptr, *recv_hi = nullptr;
     int64_t halo_bytes = 0;                       /* capacity of each halo buffer (A.halo rows) */
     int32_t* reach_send = nullptr;                /* staging word of the reach all-reduce */
+    int32_t reach_all_host = 0;                   /* picles_set_global_reach: staging word */
     int n_halo_widened = 0;                       /* steps that repeated exchange + gather with wider rows */
     std::vector<void*> allocs;
     picles_counters_t last;
@@ -695,6 +696,16 @@ int picles_halo_widen(picles_t* h, int rows) {
     if (rows > h->A.halo)
         return fail(h, PICLES_ERR_HALO, "a halo of %d rows is asked for; this strip (%d rows) can exchange at most %d", rows, h->A.ny, h->A.halo);
     h->A.hx = rows;
+    return PICLES_OK;
+}
+
+int picles_set_global_reach(picles_t* h, int reach) {
+    int rc = need_ready(h, true);
+    if (rc) return rc;
+    if (reach < 0) return fail(h, PICLES_ERR_ARG, "negative reach");
+    h->reach_all_host = reach;
+    CK(cudaMemcpyAsync(&h->d_counters->reach_all, &h->reach_all_host, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return PICLES_OK;
 }
 

@@ -402,7 +402,7 @@ __device__ __noinline__ int4 cold_nodes(const DeviceArrays* Ap, const picles_par
                 else gather_window_rt<2>(T, base, Rt, s0, s1, s2);
             } else {
                 RecView V;
-                V.Nx = A.Nx; V.Ny = A.Ny; V.bx = A.bx; V.by = A.by; V.j0 = A.j0; V.ny = A.ny; V.halo = A.halo; V.pitch = A.rp;
+                V.Nx = A.Nx; V.Ny = A.Ny; V.bx = A.bx; V.by = A.by; V.j0 = A.j0; V.ny = A.ny; V.halo = A.halo; V.hx = A.hx; V.pitch = A.rp;
                 V.e = A.rec[0]; V.mx = A.rec[1]; V.my = A.rec[2]; V.wx = A.rec[3]; V.wy = A.rec[4];
                 V.cell = A.cell;
                 gather_node(V, I, J, R, n_classes, s0, s1, s2);
@@ -788,10 +788,9 @@ __global__ void __launch_bounds__(256) k_wind_sample(DeviceWindMesh D, int64_t n
     }
 }
 
-#ifdef PH_WIND_ROW4
-/* profiles/ variant: one thread per four consecutive nodes (wm_sample2d_x4: the y lookup shared along a
-   row), 16-byte loads and stores; the launcher falls back to k_wind_sample when a plane is not
-   16-byte aligned, and a scalar tail takes the last n % 4 nodes */
+/* one thread per four consecutive nodes (wm_sample2d_x4: the y lookup shared along a row), 16-byte loads and
+   stores: 0.200 -> 0.163 ms at 4096^2.  The launcher falls back to k_wind_sample when a plane is not 16-byte
+   aligned, and a scalar tail takes the last n % 4 nodes */
 __global__ void __launch_bounds__(256) k_wind_sample_x4(DeviceWindMesh D, int64_t n, double* __restrict__ u_out,
                                                         double* __restrict__ v_out) {
     WindMesh W;
@@ -826,7 +825,6 @@ __global__ void __launch_bounds__(256) k_wind_sample_x4(DeviceWindMesh D, int64_
         u_out[l] = u; v_out[l] = v;
     }
 }
-#endif
 
 /* ---- launchers ------------------------------------------------------------------ */
 static int grid_for(int64_t n, int threads, int sms, int blocks_per_sm) {
@@ -862,14 +860,13 @@ void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, 
         }
         COUNT_LAUNCH(2);
     } else {
-        /* Tsit5 has its own instantiation (compile-time tableau without zero coefficients); DP5 runs the generic one */
+        /* Tsit5 has its own instantiation (compile-time tableau without zero coefficients) */
         const bool ts5 = (P.solver == PICLES_SOLVER_TSIT5);
         if (pn && ts5) k_advance<true, false, true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
         else if (pn) k_advance<true, false><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
         else if (ts5) k_advance<false, false, true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
-#ifdef PH_DP5_CT /* profiles/: DP5 with its own instantiation too */
+        /* ... and so has DP5 on a uniform kernel (the bench06 settings): -1.5 % */
         else if (P.solver == PICLES_SOLVER_DP5) k_advance<false, false, 2><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
-#endif
         else k_advance<false, false><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
         COUNT_LAUNCH(1);
     }
@@ -896,12 +893,10 @@ void launch_wind_sample(const DeviceWindMesh& W, int64_t n, double t, double* u_
     if (n <= 0) return;
     COUNT_LAUNCH(2);
     k_wind_timeblend<<<grid_for((int64_t)W.nx * W.ny, 256, sms, 8), 256, 0, st>>>(W, t);
-#ifdef PH_WIND_ROW4
     if (n >= 4 && (((uintptr_t)W.node_x | (uintptr_t)W.node_y | (uintptr_t)u_out | (uintptr_t)v_out) & 15) == 0) {
         k_wind_sample_x4<<<grid_for(n >> 2, 256, sms, 8), 256, 0, st>>>(W, n, u_out, v_out);
         return;
     }
-#endif
     k_wind_sample<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(W, n, u_out, v_out);
 }
 void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cudaStream_t st) {

@@ -149,6 +149,7 @@ class TorchP2PTransport:
         r = self.torch.tensor([e.reach()], dtype=self.torch.int32, device=f"cuda:{e.device}" if self.on_device else "cpu")
         dist.all_reduce(r, op=dist.ReduceOp.MAX)
         need = int(r.item())
+        e.set_global_reach(need)
         if need > e.halo_rows()[0]:
             e.halo_widen(need)
             self._views()

@@ -160,6 +160,10 @@ class B200Engine:
         """exchange at least `rows` rows from now on (never narrowed)"""
         self._check(self.lib.picles_halo_widen(self.h, int(rows)))
 
+    def set_global_reach(self, reach):
+        """the all-reduced reach of this step (host-driven exchange): lets the gather check the halo width exactly"""
+        self._check(self.lib.picles_set_global_reach(self.h, int(reach)))
+
     def halo_pack(self):
         self._check(self.lib.picles_halo_pack(self.h))
 

@@ -178,11 +178,9 @@ static void shim_advance_all(Shim* h, double DT, const double* u_t, const double
             const bool pending = (ph_host_specialised && h->P.solver == PICLES_SOLVER_TSIT5)
                 ? advance_particle<false, true>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], wu1,
                                                 wv1, h->n_mid, um, vm, M, pc, r, c, K, attempts)
-#ifdef PH_DP5_CT
-                : (ph_host_specialised && h->P.solver == PICLES_SOLVER_DP5)
+                : (ph_host_specialised && h->P.solver == PICLES_SOLVER_DP5 && !h->perM)
                 ? advance_particle<false, 2>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], wu1,
                                              wv1, h->n_mid, um, vm, M, pc, r, c, K, attempts)
-#endif
                 : advance_particle<true>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], wu1,
                                          wv1, h->n_mid, um, vm, M, pc, r, c, K, attempts);
 
@@ -220,7 +218,7 @@ static void shim_project_remesh_all(Shim* h, double DT, int R, const double* u_t
     const int Nx = h->Nx;
     for (auto& s : h->s) {
         RecView V;
-        V.Nx = Nx; V.Ny = h->Ny; V.bx = h->bx; V.by = h->by; V.j0 = s.j0; V.ny = s.ny; V.halo = s.halo; V.pitch = Nx;
+        V.Nx = Nx; V.Ny = h->Ny; V.bx = h->bx; V.by = h->by; V.j0 = s.j0; V.ny = s.ny; V.halo = s.halo; V.hx = s.halo; V.pitch = Nx;
         V.e = s.rec[0].data(); V.mx = s.rec[1].data(); V.my = s.rec[2].data(); V.wx = s.rec[3].data(); V.wy = s.rec[4].data();
         V.cell = s.cell.data();
         int64_t n = (int64_t)Nx * s.ny, off = local_winds ? 0 : (int64_t)s.j0 * Nx;

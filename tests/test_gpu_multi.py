@@ -21,7 +21,10 @@ def _ngpu():
 
 @pytest.mark.parametrize("name,world,halo,transport", [
     ("minimal", 2, 2, "nccl-lib"), ("periodic_grid", 2, 5, "nccl-lib"), ("growing_winds", 2, 2, "nccl-lib"),
-    ("minimal", 2, 2, "torch-p2p"), ("tripolar", 3, 6, "nccl-lib"), ("land_block", 4, 2, "nccl-lib")])
+    ("minimal", 2, 2, "torch-p2p"), ("tripolar", 3, 6, "nccl-lib"), ("land_block", 4, 2, "nccl-lib"),
+    # one halo row, particles crossing 2-4 cells per step: the exchange widens itself (all-reduced reach, repeated
+    # exchange + gather inside picles_step_strip; reach validated by the host for the torch transport)
+    ("fast_box", 2, 1, "nccl-lib"), ("fast_box", 2, 1, "torch-p2p"), ("pulse_winds", 2, 2, "nccl-lib")])
 def test_strips_over_nccl_match_oracle(gpu_lib, tmp_path, name, world, halo, transport):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")

@@ -118,6 +118,7 @@ def test_gpu_strips_match_oracle(gpu_lib, name, nstrips, halo):
 
 
 def test_gpu_reach_beyond_halo_is_an_error(gpu_lib):
+    """host-driven exchange with too few rows: the gather refuses (PICLES_ERR_HALO) and changes nothing"""
     from picles_b200 import PiclesError
     g, P, wind, DT, n = SCENARIOS["periodic_grid"]()
     s = StripSet(g, P, 2, 1)
@@ -126,8 +127,90 @@ def test_gpu_reach_beyond_halo_is_an_error(gpu_lib):
     with pytest.raises(PiclesError, match="ERR_HALO"):
         t = 0.0
         for _ in range(n):
+            before = s.state()
             s.step(t, DT, *wind(t), *wind(t + DT))
             t += DT
+    assert np.array_equal(s.state().view(np.uint64), before.view(np.uint64))  # State untouched by the refused gather
+
+
+@pytest.mark.parametrize("name,nstrips", [("fast_box", 3), ("periodic_grid", 2), ("odd_periodic_strip", 2)])
+def test_gpu_halo_widens_instead_of_failing(gpu_lib, name, nstrips):
+    """SURVEY.md §8e 'falling back to a wider exchange': strips created with a halo of ONE row while the
+    particles cross 2-4 cells per step.  The gather refuses, the host widens every strip to the rows the
+    error names and repeats exchange + gather (the advance is not repeated): bit-exact against the oracle."""
+    from picles_b200 import PiclesError
+    g, P, wind, DT, n = SCENARIOS[name]()
+
+    class Widening(StripSet):
+        widened = 0
+
+        def finish(self, t, DT):
+            for e in self.e:
+                e.halo_pack()
+            for e in self.e:
+                e.synchronize()
+            bufs = [e.halo_buffers() for e in self.e]
+            ns = self.ns
+            for r, e in enumerate(self.e):
+                (slo, shi, rlo, rhi), nb = bufs[r]
+                lo, hi = r - 1, r + 1
+                if self.periodic:
+                    lo, hi = (lo + ns) % ns, hi % ns
+                if 0 <= lo < ns:
+                    e.copy_dev(rlo, bufs[lo][0][1], nb)
+                if 0 <= hi < ns:
+                    e.copy_dev(rhi, bufs[hi][0][0], nb)
+                e.halo_unpack()
+            need = 0
+            for e in self.e:
+                try:
+                    e.step_project_remesh(t, DT)
+                except PiclesError as ex:
+                    assert "ERR_HALO" in str(ex)
+                    need = max(need, int(str(ex).split("picles_halo_widen(")[1].split(")")[0]))
+            return need
+
+    # all strips see the global reach when the host all-reduces it first (what StripStepper's torch-p2p path does)
+    class Validating(Widening):
+        def step(self, t, DT, ut, vt, ut1, vt1):
+            w = [self._full(x) for x in (ut, vt, ut1, vt1)]
+            for (a, b), e in zip(self.bounds, self.e):
+                e.upload_winds(*[x[a:b] for x in w])
+                e.step_advance(t, DT)
+            need = max(e.reach() for e in self.e)
+            if need > self.e[0].halo_rows()[0]:
+                type(self).widened += 1
+                for e in self.e:
+                    e.halo_widen(need)
+            assert self.finish(t, DT) == 0
+
+    s = Validating(g, P, nstrips, 1)
+    assert s.e[0].halo_rows()[0] == 1 and s.e[0].halo_rows()[1] >= 4
+    run_pair(make_oracle(g, P), s, wind, DT, n, compare_models)
+    assert Validating.widened >= 1 and s.e[0].halo_rows()[0] >= 2
+
+    # ... and the refusal itself: the strips exchange too few rows first, every gather refuses (each was told the
+    # global reach), all widen to the rows the error names and repeat exchange + gather — not the advance
+    class Refused(Widening):
+        def step(self, t, DT, ut, vt, ut1, vt1):
+            w = [self._full(x) for x in (ut, vt, ut1, vt1)]
+            for (a, b), e in zip(self.bounds, self.e):
+                e.upload_winds(*[x[a:b] for x in w])
+                e.step_advance(t, DT)
+            reach = max(e.reach() for e in self.e)
+            for e in self.e:
+                e.set_global_reach(reach)
+            need = self.finish(t, DT)
+            if need:
+                assert need == reach
+                type(self).widened += 1
+                for e in self.e:
+                    e.halo_widen(need)
+                assert self.finish(t, DT) == 0
+
+    s2 = Refused(g, P, nstrips, 1)
+    run_pair(make_oracle(g, P), s2, wind, DT, n, compare_models)
+    assert Refused.widened >= 1
 
 
 def test_gpu_medium_box_against_threaded_oracle(gpu_lib):
@@ -335,6 +418,26 @@ def test_gpu_checkpoint_resume_is_bit_identical(gpu_lib, name):
     a.set_wind_midlevels([wind(t + DT / 2)[0]], [wind(t + DT / 2)[1]])
     with pytest.raises(PiclesError, match="intermediate wind levels"):
         a.checkpoint()
+
+
+def test_gpu_attempt_histogram_and_launch_count(gpu_lib):
+    """the work per particle-step is data-dependent: its distribution is reported per step, and
+    the library counts the kernels it launches (bench.py's gpu_launches is this count, not arithmetic)"""
+    for name in ("growing_winds", "minimal"):
+        g, P, wind, DT, n = SCENARIOS[name]()
+        e = engine_for(g, P)
+        e.seed(*wind(0.0))
+        t = 0.0
+        for _ in range(3):
+            k0 = e.launch_count()
+            e.step(t, DT, *wind(t), *wind(t + DT))
+            assert e.launch_count() - k0 == 2          # k_advance + k_project_remesh
+            t += DT
+            c, h = e.counters(), e.attempt_histogram()
+            assert h.sum() == c["n_integrated"]
+            assert int(np.nonzero(h)[0].max()) == min(c["max_attempts"], h.size - 1)
+            assert int((h * np.arange(h.size)).sum()) == c["n_substeps"] + c["n_rejects"] or c["max_attempts"] >= h.size - 1
+        assert e.attempt_histogram(8).sum() == c["n_integrated"]
 
 
 def test_gpu_state_roundtrip_and_accessors(gpu_lib):
