@@ -20,6 +20,8 @@ _VARIANTS = {
     "default": "libpicles_oracle.so",
     "omp": "libpicles_oracle_omp.so",
     "libm": "libpicles_oracle_libm.so",
+    "fastpow": "libpicles_oracle_fastpow.so",      # controller powers in Float32 (sensitivity study)
+    "fastpow12": "libpicles_oracle_fastpow12.so",  # ... cut to 12 mantissa bits
 }
 _libs: dict = {}
 

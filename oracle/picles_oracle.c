@@ -69,6 +69,17 @@
 
 #define QOLDINIT 1e-4 /* OrdinaryDiffEq default qoldinit for adaptive algorithms */
 
+#if defined(ORACLE_CTRL_POW)
+static double ctrl_pow(double x, double y) {
+    float r = powf((float)x, (float)y);
+#if ORACLE_CTRL_POW >= 2
+    union { float f; uint32_t u; } c;
+    c.f = r; c.u &= 0xfffff800u; r = c.f; /* keep 12 of the 23 mantissa bits */
+#endif
+    return (double)r;
+}
+#endif
+
 /* ------------------------------------------------------------------------ */
 /* types                                                                      */
 /* ------------------------------------------------------------------------ */
@@ -636,10 +647,21 @@ static void integrate(oracle_t* o, particle_t* p, const rhs_ctx_t* c, double DT,
         if (EEst == 0.0) {
             q = 1.0 / qmax;
         } else {
+#if defined(ORACLE_CTRL_POW)
+            /* sensitivity builds only (oracle/_build/libpicles_oracle_fastpow*.so, tests/test_sensitivity.py): older
+               OrdinaryDiffEq versions form the two powers with `fastpow`, a Float32 approximation.  1: Float32
+               pow (6e-8 relative); 2: its result cut to 12 mantissa bits (2e-4 relative, the accuracy of the
+               fastlog2 polynomial behind fastpow).  Shows what an accept/reject or step-size perturbation of that
+               size does to the fields; never the checker of the CUDA path. */
+            q11 = ctrl_pow(EEst, beta1);
+            q = q11 / ctrl_pow(qold, beta2);
+            q = pm_max(1.0 / qmax, pm_min(1.0 / qmin, q / gamma));
+#else
             double t1 = beta1 * O_LOG(EEst);
             q11 = O_EXP(t1);
             q = O_EXP(t1 - beta2 * O_LOG(qold));
             q = pm_max(1.0 / qmax, pm_min(1.0 / qmin, q / gamma));
+#endif
         }
         int accept = (EEst <= 1.0) || (P->force_dtmin && fabs(dt) <= dtmin_t);
         if (accept) {

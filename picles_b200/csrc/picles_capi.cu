@@ -612,6 +612,25 @@ static int begin_advance(picles_t* h, double dt_model, const double* u_t, const 
     h->timing_valid = false;
     return PICLES_OK;
 }
+/* host winds of rows [r0, r1) onto the device on the copy stream; `consumer` waits until they have landed */
+static int upload_rows(picles_t* h, const double* u_t, const double* v_t, const double* u_t1, const double* v_t1, int r0,
+                       int r1, cudaEvent_t landed, cudaStream_t consumer) {
+    DeviceArrays& A = h->A;
+    if (r0 >= r1 || !(u_t || u_t1)) return PICLES_OK;
+    const int64_t off = (int64_t)r0 * A.Nx;
+    const size_t bytes = (size_t)(r1 - r0) * A.Nx * 8;
+    if (u_t) {
+        CK(cudaMemcpyAsync(A.u_t + off, u_t + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaMemcpyAsync(A.v_t + off, v_t + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    }
+    if (u_t1) {
+        CK(cudaMemcpyAsync(A.u_t1 + off, u_t1 + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaMemcpyAsync(A.v_t1 + off, v_t1 + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    }
+    CK(cudaEventRecord(landed, h->copy_stream));
+    CK(cudaStreamWaitEvent(consumer, landed, 0));
+    return PICLES_OK;
+}
 static int advance_rows(picles_t* h, double dt_model, const double* u_t, const double* v_t, const double* u_t1,
                         const double* v_t1, int r0, int r1, cudaEvent_t landed, int slot) {
     DeviceArrays& A = h->A;
@@ -1326,22 +1345,33 @@ int picles_step_strip(picles_t* h, double t, double dt_model, const double* u_t,
     } else {
         rc = begin_advance(h, dt_model, u_t, v_t, u_t1, v_t1);
         if (rc) return rc;
-        rc = advance_rows(h, dt_model, u_t, v_t, u_t1, v_t1, 0, A.hx, h->pev[PIPE_CHUNKS], PIPE_CHUNKS);
+        /* the two boundary row blocks: ONE launch on the communication stream, submitted first so that its few blocks
+           are resident before the interior launch (whose blocks stay until the work queue is empty) fills the SMs.
+           Behind each other on the compute stream the two small launches cost their full latency (~0.15 ms each,
+           one chunk per warp) with the GPU idle: the fixed cost that capped strong scaling. */
+        cudaEvent_t ready = h->pev[PIPE_CHUNKS + 2], exchanged = h->pev[PIPE_CHUNKS + 3], interior = h->pev[PIPE_CHUNKS + 4];
+        CK(cudaEventRecord(ready, h->stream));                     /* counters and per-row reach zeroed */
+        CK(cudaStreamWaitEvent(h->comm_stream, ready, 0));
+        rc = upload_rows(h, u_t, v_t, u_t1, v_t1, 0, A.hx, h->pev[PIPE_CHUNKS], h->comm_stream);
         if (rc) return rc;
-        rc = advance_rows(h, dt_model, u_t, v_t, u_t1, v_t1, A.ny - A.hx, A.ny, h->pev[PIPE_CHUNKS + 1], PIPE_CHUNKS + 1);
+        rc = upload_rows(h, u_t, v_t, u_t1, v_t1, A.ny - A.hx, A.ny, h->pev[PIPE_CHUNKS + 1], h->comm_stream);
         if (rc) return rc;
-        cudaEvent_t advanced = h->pev[PIPE_CHUNKS + 2], exchanged = h->pev[PIPE_CHUNKS + 3], interior = h->pev[PIPE_CHUNKS + 4];
-        CK(cudaEventRecord(advanced, h->stream));                  /* boundary records written */
-        CK(cudaStreamWaitEvent(h->comm_stream, advanced, 0));
-        rc = exchange_on(h, lo_rank, hi_rank, h->comm_stream);
+        launch_advance2(A, h->P, dt_model, h->d_counters, h->sms, h->comm_stream, 0, (int64_t)A.hx * A.Nx,
+                        (int64_t)(A.ny - A.hx) * A.Nx, (int64_t)A.ny * A.Nx, PIPE_CHUNKS);
+        CK(cudaGetLastError());
+        rc = exchange_on(h, lo_rank, hi_rank, h->comm_stream);     /* boundary records written: pack, send/recv, unpack */
         if (rc) return rc;
+        if (u_t || u_t1) { /* whole-plane readers on the compute stream (the lag-level copy, the remesh) see the boundary rows too */
+            CK(cudaStreamWaitEvent(h->stream, h->pev[PIPE_CHUNKS], 0));
+            CK(cudaStreamWaitEvent(h->stream, h->pev[PIPE_CHUNKS + 1], 0));
+        }
         rc = advance_range(h, dt_model, u_t, v_t, u_t1, v_t1, A.hx, A.ny - A.hx);
         if (rc) return rc;
         CK(cudaEventRecord(h->ev[1], h->stream));
         CK(cudaGetLastError());
         rc = keep_lag_level(h);
         if (rc) return rc;
-        CK(cudaEventRecord(interior, h->stream));                  /* this strip's reach is final */
+        CK(cudaEventRecord(interior, h->stream));                  /* interior records written */
         CK(cudaStreamWaitEvent(h->comm_stream, interior, 0));
         rc = reach_allreduce(h, h->comm_stream);
         if (rc) return rc;

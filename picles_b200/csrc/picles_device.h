@@ -97,6 +97,8 @@ void launch_seed(const DeviceArrays& A, const picles_params_t& P, const double* 
                  int sms, cudaStream_t st);
 void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
                     cudaStream_t st, int64_t l_begin, int64_t l_end, int slot);
+void launch_advance2(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
+                     cudaStream_t st, int64_t l_begin, int64_t l_end, int64_t l2_begin, int64_t l2_end, int slot);
 /* kernels launched by this library since it was loaded (every launch_* call counts its kernels) */
 long long launch_count();
 /* TMA tensor maps of the six record planes (box PR_BW x PR_BH) */

@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(256) k_seed(DeviceArrays A, picles_params_t P,
 #endif
 template <bool PER_NODE_M, bool AUTOSW, int TSIT5 = 0>
 __global__ void ADV_BOUNDS
-k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int64_t l_begin, int64_t l_end, int slot) {
+k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int64_t l_begin, int64_t l_end, int64_t l2_begin,
+          int64_t l2_end, int slot) {
     /* stage derivatives k_j[0:3], j = 1..7: 21 doubles per thread, one column per thread
        (consecutive threads -> consecutive 8-byte words: conflict-free) */
     __shared__ double s_k[KS_SLOTS * ADV_THREADS];
@@ -175,14 +176,19 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int6
     __syncthreads();
     const int lane = threadIdx.x & 31;
     unsigned long long* const queue = &dc->next_chunk[slot];
+    /* the launch covers [l_begin, l_end) and then [l2_begin, l2_end) (a strip's two boundary row blocks in one
+       launch; empty for everything else) */
+    const int64_t n1 = (l_end - l_begin + 31) >> 5;
     for (;;) {
         unsigned long long chunk = 0;
         if (lane == 0) chunk = atomicAdd(queue, 1ull);
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        const int64_t l0 = l_begin + (int64_t)chunk * 32;
-        if (l0 >= l_end) break; /* uniform over the warp */
+        const bool second = (int64_t)chunk >= n1;
+        const int64_t l0 = second ? l2_begin + ((int64_t)chunk - n1) * 32 : l_begin + (int64_t)chunk * 32;
+        const int64_t lim = second ? l2_end : l_end;
+        if (l0 >= lim) break; /* uniform over the warp */
         const int64_t l = l0 + lane;
-        const uint8_t flags = (l < l_end) ? A.flags[l] : (uint8_t)0;
+        const uint8_t flags = (l < lim) ? A.flags[l] : (uint8_t)0;
         if (flags & PICLES_PF_ACTIVE) { /* else: the record stays invalid (set at seed) */
             int64_t le = rec_index(A, l);
             Particle p;
@@ -841,35 +847,45 @@ void launch_seed(const DeviceArrays& A, const picles_params_t& P, const double* 
     COUNT_LAUNCH(1);
 }
 
-/* particles [l_begin, l_end) of the strip (the whole strip: 0, Nx*ny); slot: the work queue of this launch
-   (DeviceCounters::next_chunk, zeroed with the counters at the start of the step) */
-void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
-                    cudaStream_t st, int64_t l_begin, int64_t l_end, int slot) {
-    if (l_end <= l_begin) return;
-    int g = grid_for(l_end - l_begin, ADV_THREADS, sms, ADV_MIN_BLOCKS);
+/* particles [l_begin, l_end) and then [l2_begin, l2_end) of the strip (the whole strip: 0, Nx*ny and an empty
+   second range); slot: the work queue of this launch (DeviceCounters::next_chunk, zeroed with the counters at the
+   start of the step) */
+void launch_advance2(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
+                     cudaStream_t st, int64_t l_begin, int64_t l_end, int64_t l2_begin, int64_t l2_end, int slot) {
+    if (l2_end < l2_begin) l2_end = l2_begin;
+    if (l_end < l_begin) l_end = l_begin;
+    const int64_t count = (l_end - l_begin) + (l2_end - l2_begin);
+    if (count <= 0) return;
+    int g = grid_for(count, ADV_THREADS, sms, ADV_MIN_BLOCKS);
     bool pn = (A.M[0] != nullptr);
+#define ADV_ARGS A, P, DT, dc, l_begin, l_end, l2_begin, l2_end, slot
     /* AutoTsit5 runs the instantiation that carries the stiffness monitor and the Rosenbrock23 branch */
     if (P.solver == PICLES_SOLVER_AUTOTSIT5) {
-        const int gr = grid_for(l_end - l_begin, ADV_THREADS, sms, 1);
+        const int gr = grid_for(count, ADV_THREADS, sms, 1);
         if (pn) {
-            k_advance<true, true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
+            k_advance<true, true><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
             k_advance_resume<true><<<gr, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end);
         } else {
-            k_advance<false, true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
+            k_advance<false, true><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
             k_advance_resume<false><<<gr, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end);
         }
         COUNT_LAUNCH(2);
     } else {
         /* Tsit5 has its own instantiation (compile-time tableau without zero coefficients) */
         const bool ts5 = (P.solver == PICLES_SOLVER_TSIT5);
-        if (pn && ts5) k_advance<true, false, true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
-        else if (pn) k_advance<true, false><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
-        else if (ts5) k_advance<false, false, true><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
+        if (pn && ts5) k_advance<true, false, true><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
+        else if (pn) k_advance<true, false><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
+        else if (ts5) k_advance<false, false, true><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
         /* ... and so has DP5 on a uniform kernel (the bench06 settings): -1.5 % */
-        else if (P.solver == PICLES_SOLVER_DP5) k_advance<false, false, 2><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
-        else k_advance<false, false><<<g, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end, slot);
+        else if (P.solver == PICLES_SOLVER_DP5) k_advance<false, false, 2><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
+        else k_advance<false, false><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
         COUNT_LAUNCH(1);
     }
+#undef ADV_ARGS
+}
+void launch_advance(const DeviceArrays& A, const picles_params_t& P, double DT, DeviceCounters* dc, int sms,
+                    cudaStream_t st, int64_t l_begin, int64_t l_end, int slot) {
+    launch_advance2(A, P, DT, dc, sms, st, l_begin, l_end, l_end, l_end, slot);
 }
 
 int project_remesh_smem_bytes() { return (int)sizeof(PRTile) + 128; }
