@@ -145,7 +145,10 @@ function b200_init_particles!(model, arch::B200; nccl_id::Union{Nothing,Vector{U
             Float64.(grid.data.dx[:, rows]), Float64.(grid.data.dy[:, rows]), Float64.(grid.data.angle_dx[:, rows]),
             Float64.(grid.data.y[:, rows]), 6.3710e6))
     else                                             # TwoDCartesianGridMesh: uniform kernel
-        Mc = Float64[1 / grid.stats.dx, 0.0, 0.0, 1 / grid.stats.dy]
+        # the grid's own ProjetionKernel(stats) (CartesianGrid.jl:115-129): diag(1/dx, 1/dy), or — for a rotated grid,
+        # angle_dx != 0 — [cosα/dx sinα/dy; sinα/dx cosα/dy] (no minus sign: SURVEY B-8).  Row-major M11, M12, M21, M22
+        Mk = grid.ProjetionKernel(grid.stats)
+        Mc = Float64[Mk[1, 1], Mk[1, 2], Mk[2, 1], Mk[2, 2]]
         check(h, ccall((:picles_set_grid, LIB), Cint,
             (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Ptr{UInt8}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
             h, Nx, Ny, boundary_code(grid.stats.Nx), boundary_code(grid.stats.Ny), j0, j1 - j0, halo, mask, C_NULL, Mc, C_NULL))

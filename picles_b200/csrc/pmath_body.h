@@ -85,7 +85,11 @@ PM_FN double PMV(pm_sech)(double x PM_BADP) {
 #else
     ax = (x != x) ? 0.0 : ax;
 #endif
+#ifdef PM_FAST_RANGE
+    double e = pm_exp_core_inrange(ax); /* 0 <= ax <= 350 */
+#else
     double e = pm_exp_core(ax);
+#endif
     double t = PM_DIV(2.0 * e, fma(e, e, 1.0));
 #ifdef PM_FAST_RANGE
     return t;
@@ -98,7 +102,7 @@ PM_FN double PMV(pm_sech)(double x PM_BADP) {
 PM_FN double PMV(pm_expx)(double x PM_BADP) {
 #ifdef PM_FAST_RANGE
     *pm_bad |= (fabs(x) <= 700.0) ? 0u : 1u;
-    return pm_exp_core(x);
+    return pm_exp_core_inrange(x);
 #else
     return pm_exp(x);
 #endif

@@ -52,12 +52,14 @@ def strip_bounds_weighted(row_cost, world: int, min_rows: int = 1):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
-def row_cost_model(mask, periodic_boundary: bool, reach_rows=None, gather_weight: float = 0.075, reach_weight: float = 0.3):
+def row_cost_model(mask, periodic_boundary: bool, reach_rows=None, gather_weight: float = 0.068, reach_weight: float = 0.075):
     """cost of every global row in particle units, for strip_bounds_weighted: the active particles
     of the row (the advance is ~98 % of a step) plus the gather/remesh of all its nodes
     (gather_weight per node) and, for rows whose deposits reach further than one cell
     (reach_rows: per-row reach estimate, e.g. the small cells near a tripolar pole), reach_weight
-    per node and cell of extra reach: the window grows as (2R+1)^2."""
+    per node and cell of extra reach: the window grows as (2R+1)^2.  Weights from the measured kernel times of
+    the tripolar + land configuration on two strips (profiles/README.md, round 2): advance 1.12 ns per active
+    particle, gather + remesh 0.076 ns per node at reach 1 and 0.130 ns per node over the rows near the pole."""
     m = np.asarray(mask)
     active = (m == 1) | ((m == 3) if periodic_boundary else False)
     cost = active.sum(axis=1).astype(np.float64) + gather_weight * m.shape[1]
