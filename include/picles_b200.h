@@ -258,6 +258,9 @@ int picles_step_project_remesh(picles_t* h, double t, double dt_model);
 int picles_synchronize(picles_t* h);
 /* reach (cells) of the last advance on this strip; the caller all-reduces(max) it */
 int picles_get_reach(picles_t* h, int32_t* reach);
+/* the same per owned row (ny_local values): the largest reach of any deposit written by the particles of that row in
+   the last step — what sizes the gather's window tile by tile, and a measured input for cutting strips by cost */
+int picles_get_row_reach(picles_t* h, int32_t* reach_rows);
 
 /* ---- multi-GPU: y-strips, one handle per GPU/process ------------------------- */
 /*

@@ -115,6 +115,7 @@ SYMBOLS = {
     "picles_make_boundaries": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "picles_set_params": (C.c_int, [_vp, C.POINTER(PiclesParams)]),
     "picles_seed": (C.c_int, [_vp, _vp, _vp]),
+    "picles_get_row_reach": (C.c_int, [_vp, _vp]),
     "picles_halo_rows": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "picles_halo_widen": (C.c_int, [_vp, C.c_int]),
     "picles_set_global_reach": (C.c_int, [_vp, C.c_int]),

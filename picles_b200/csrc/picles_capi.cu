@@ -728,6 +728,16 @@ int picles_set_global_reach(picles_t* h, int reach) {
     return PICLES_OK;
 }
 
+int picles_get_row_reach(picles_t* h, int32_t* reach_rows) {
+    int rc = need_ready(h, true);
+    if (rc) return rc;
+    if (!reach_rows) return fail(h, PICLES_ERR_ARG, "null output");
+    const DeviceArrays& A = h->A;
+    CK(cudaMemcpyAsync(reach_rows, A.rowreach + A.halo, (size_t)A.ny * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PICLES_OK;
+}
+
 int picles_halo_buffers(picles_t* h, void** send_lo, void** send_hi, void** recv_lo, void** recv_hi, int64_t* nbytes) {
     if (!h || !h->have_grid) return fail(h, PICLES_ERR_STATE, "grid not set");
     if (send_lo) *send_lo = h->send_lo;
@@ -1359,13 +1369,15 @@ int picles_step_strip(picles_t* h, double t, double dt_model, const double* u_t,
         launch_advance2(A, h->P, dt_model, h->d_counters, h->sms, h->comm_stream, 0, (int64_t)A.hx * A.Nx,
                         (int64_t)(A.ny - A.hx) * A.Nx, (int64_t)A.ny * A.Nx, PIPE_CHUNKS);
         CK(cudaGetLastError());
-        rc = exchange_on(h, lo_rank, hi_rank, h->comm_stream);     /* boundary records written: pack, send/recv, unpack */
-        if (rc) return rc;
         if (u_t || u_t1) { /* whole-plane readers on the compute stream (the lag-level copy, the remesh) see the boundary rows too */
             CK(cudaStreamWaitEvent(h->stream, h->pev[PIPE_CHUNKS], 0));
             CK(cudaStreamWaitEvent(h->stream, h->pev[PIPE_CHUNKS + 1], 0));
         }
+        /* the interior is enqueued before the exchange: the host side of the NCCL group (tens of microseconds) must not
+           sit between the two advance launches */
         rc = advance_range(h, dt_model, u_t, v_t, u_t1, v_t1, A.hx, A.ny - A.hx);
+        if (rc) return rc;
+        rc = exchange_on(h, lo_rank, hi_rank, h->comm_stream);     /* boundary records written: pack, send/recv, unpack */
         if (rc) return rc;
         CK(cudaEventRecord(h->ev[1], h->stream));
         CK(cudaGetLastError());

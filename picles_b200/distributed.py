@@ -52,19 +52,31 @@ def strip_bounds_weighted(row_cost, world: int, min_rows: int = 1):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
-def row_cost_model(mask, periodic_boundary: bool, reach_rows=None, gather_weight: float = 0.068, reach_weight: float = 0.075):
+def row_cost_model(mask, periodic_boundary: bool, reach_rows=None, gather_weight: float = 0.068):
     """cost of every global row in particle units, for strip_bounds_weighted: the active particles
-    of the row (the advance is ~98 % of a step) plus the gather/remesh of all its nodes
-    (gather_weight per node) and, for rows whose deposits reach further than one cell
-    (reach_rows: per-row reach estimate, e.g. the small cells near a tripolar pole), reach_weight
-    per node and cell of extra reach: the window grows as (2R+1)^2.  Weights from the measured kernel times of
-    the tripolar + land configuration on two strips (profiles/README.md, round 2): advance 1.12 ns per active
-    particle, gather + remesh 0.076 ns per node at reach 1 and 0.130 ns per node over the rows near the pole."""
+    of the row (the advance is ~90-98 % of a step) plus the gather/remesh of all its nodes.  The gather
+    visits a window of (2R+1)^2 candidate sources per node, R = how many cells the deposits of the rows
+    around reach (reach_rows: per-row estimate, e.g. from the small cells near a tripolar pole), so its
+    cost per node is gather_weight * (2R+1)^2 / 9.  Weights from the measured kernel times of the
+    tripolar + land configuration (profiles/README.md, round 2): advance 1.12 ns per active particle,
+    gather + remesh 0.076 ns per node at reach 1 (0.068 particle units), 0.39 ns per node over the rows
+    near the pole (reach 3: 49/9 x 0.068 = 0.37)."""
     m = np.asarray(mask)
     active = (m == 1) | ((m == 3) if periodic_boundary else False)
-    cost = active.sum(axis=1).astype(np.float64) + gather_weight * m.shape[1]
-    if reach_rows is not None:
-        cost = cost + reach_weight * m.shape[1] * np.maximum(np.asarray(reach_rows, np.float64) - 1.0, 0.0)
+    R = np.ones(m.shape[0]) if reach_rows is None else np.maximum(np.asarray(reach_rows, np.float64), 1.0)
+    return active.sum(axis=1).astype(np.float64) + gather_weight * m.shape[1] * (2.0 * R + 1.0) ** 2 / 9.0
+
+
+def row_cost_measured(active_rows, nodes_per_row, reach_rows, bounds, ms_advance, ms_gather):
+    """cost of every global row from a calibration run on the strips `bounds`: each strip's measured advance
+    time spread over its rows by their active particles (captures regional differences in substeps), its measured
+    gather + remesh time spread over its rows by the window area (2R+1)^2 of the rows' measured reach.
+    active_rows, reach_rows: one value per global row; ms_advance, ms_gather: one value per strip."""
+    a = np.asarray(active_rows, np.float64)
+    w = nodes_per_row * (2.0 * np.maximum(np.asarray(reach_rows, np.float64), 1.0) + 1.0) ** 2
+    cost = np.zeros_like(a)
+    for (j0, j1), ta, tg in zip(bounds, ms_advance, ms_gather):
+        cost[j0:j1] = ta * a[j0:j1] / max(a[j0:j1].sum(), 1.0) + tg * w[j0:j1] / max(w[j0:j1].sum(), 1.0)
     return cost
 
 

@@ -192,6 +192,12 @@ class B200Engine:
         self._check(self.lib.picles_get_reach(self.h, C.byref(r)))
         return r.value
 
+    def row_reach(self):
+        """per owned row: the largest reach (cells) of the deposits its particles wrote in the last step"""
+        r = np.empty(self.ny, np.int32)
+        self._check(self.lib.picles_get_row_reach(self.h, _ptr(r)))
+        return r
+
     # -- accessors -----------------------------------------------------------------
     def state(self):
         S = np.empty((3, self.ny, self.Nx))

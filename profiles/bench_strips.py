@@ -29,9 +29,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--halo", type=int, default=6)
-    ap.add_argument("--balance", action="store_true",
-                    help="cut the strips by cost (active particles + gather, picles_b200.distributed.row_cost_model) "
-                         "instead of by rows")
+    ap.add_argument("--balance", nargs="?", const="model", default=None, choices=["model", "measured"],
+                    help="cut the strips by cost instead of by rows: 'model' = active particles + gather window "
+                         "(picles_b200.distributed.row_cost_model); 'measured' = a calibration run on equal strips first "
+                         "(per-strip kernel times and per-row reach, row_cost_measured), then the run proper on the re-cut strips")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -45,7 +46,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from picles_b200.distributed import StripStepper, row_cost_model, strip_bounds, strip_bounds_weighted
+    from picles_b200.distributed import StripStepper, row_cost_measured, row_cost_model, strip_bounds, strip_bounds_weighted
     from picles_b200.engine import B200Engine
 
     if a.config == "C5":
@@ -56,44 +57,61 @@ def main():
     P = default_params(DT=1200.0, periodic_boundary=True)
     DT = 1200.0
     wind = lambda t: (15.0, -10.0 * np.cos(5 * t / (3600 * 2 * np.pi)))  # tests/T03_PIC_tripolar_aqua.jl:67-68
-    if a.balance and world > 1:
+    loc_of = lambda j0, j1: (lambda x: np.ascontiguousarray(np.broadcast_to(np.asarray(x, np.float64), (j1 - j0, Nx))))
+    def run(bounds, nwarm, nsteps):
+        """seed + nwarm + nsteps steps on the strips `bounds`; timings and counters of the last nsteps"""
+        j0, j1 = bounds[rank]
+        halo = a.halo if world > 1 else 0
+        eng = B200Engine(Nx, Ny, g["bx"], g["by"], g["mask"][j0:j1], P, M=g["M"][:, j0:j1], pc=g["pc"][j0:j1],
+                         device=local_rank, j0=j0, ny_local=j1 - j0, halo=halo)
+        st = StripStepper(eng, rank, world, periodic_y=False)
+        loc = loc_of(j0, j1)
+        eng.seed(*[loc(x) for x in wind(0.0)])
+
+        def barrier():
+            eng.synchronize()
+            if dist is not None:
+                dist.barrier()
+                torch.cuda.synchronize()
+
+        t, rows, ms_total = 0.0, [], 0.0
+        for k in range(nwarm + nsteps):
+            eng.upload_winds(*[loc(x) for x in (*wind(t), *wind(t + DT))])   # resident before the timed step
+            barrier()
+            eng.timer_start()
+            st.step(t, DT)
+            ms = eng.timer_stop()
+            barrier()
+            t += DT
+            if k >= nwarm:
+                rows.append(eng.counters())
+                ms_total += ms
+        mine = dict(ms=ms_total, active=sum(r["n_active"] for r in rows), integ=sum(r["n_integrated"] for r in rows),
+                    sub=sum(r["n_substeps"] for r in rows), adv=float(np.mean([r["ms_advance"] for r in rows])),
+                    prj=float(np.mean([r["ms_project"] for r in rows])), reach=max(r["reach"] for r in rows),
+                    failed=sum(r["n_failed"] for r in rows), rows=j1 - j0, row_reach=eng.row_reach().tolist(),
+                    halo_rows=eng.halo_rows()[0])
+        eng.close()
+        return mine, halo
+
+    if a.balance == "model" and world > 1:
         # per-row reach estimate from the metric: group speed of the young sea of the first steps
         # (~3 m/s) x DT in cells of the row's smallest spacing
         cell = 1.0 / np.maximum(np.abs(g["M"][0]), np.abs(g["M"][3])).max(axis=1)
         reach_rows = np.maximum(np.ceil(3.0 * DT / cell), 1.0)
         bounds = strip_bounds_weighted(row_cost_model(g["mask"], True, reach_rows), world, min_rows=max(a.halo, 1))
+    elif a.balance == "measured" and world > 1:
+        eq = strip_bounds(Ny, world)
+        cal, _ = run(eq, a.warmup, 2)                 # calibration on equal strips, the same step indices as the warm-up
+        allc = [None] * world
+        dist.all_gather_object(allc, cal)
+        active_rows = ((g["mask"] == 1) | (g["mask"] == 3)).sum(axis=1)
+        reach_rows = np.concatenate([np.asarray(c["row_reach"]) for c in allc])
+        cost = row_cost_measured(active_rows, Nx, reach_rows, eq, [c["adv"] for c in allc], [c["prj"] for c in allc])
+        bounds = strip_bounds_weighted(cost, world, min_rows=max(a.halo, 1))
     else:
         bounds = strip_bounds(Ny, world)
-    j0, j1 = bounds[rank]
-    halo = a.halo if world > 1 else 0
-    eng = B200Engine(Nx, Ny, g["bx"], g["by"], g["mask"][j0:j1], P, M=g["M"][:, j0:j1], pc=g["pc"][j0:j1],
-                     device=local_rank, j0=j0, ny_local=j1 - j0, halo=halo)
-    st = StripStepper(eng, rank, world, periodic_y=False)
-    loc = lambda x: np.ascontiguousarray(np.broadcast_to(np.asarray(x, np.float64), (j1 - j0, Nx)))
-    eng.seed(*[loc(x) for x in wind(0.0)])
-
-    def barrier():
-        eng.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    t, rows, ms_total = 0.0, [], 0.0
-    for k in range(a.warmup + a.steps):
-        eng.upload_winds(*[loc(x) for x in (*wind(t), *wind(t + DT))])   # resident before the timed step
-        barrier()
-        eng.timer_start()
-        st.step(t, DT)
-        ms = eng.timer_stop()
-        barrier()
-        t += DT
-        if k >= a.warmup:
-            rows.append(eng.counters())
-            ms_total += ms
-    mine = dict(ms=ms_total, active=sum(r["n_active"] for r in rows), integ=sum(r["n_integrated"] for r in rows),
-                sub=sum(r["n_substeps"] for r in rows), adv=float(np.mean([r["ms_advance"] for r in rows])),
-                prj=float(np.mean([r["ms_project"] for r in rows])), reach=max(r["reach"] for r in rows),
-                failed=sum(r["n_failed"] for r in rows), rows=j1 - j0)
+    mine, halo = run(bounds, a.warmup, a.steps)
     parts = [mine]
     if dist is not None:
         parts = [None] * world if rank == 0 else None
@@ -102,7 +120,7 @@ def main():
         ms_max = max(p["ms"] for p in parts)
         active = sum(p["active"] for p in parts)
         line = {"config": name, "n_gpus": world, "scaling": "strong",
-                "partition": f"{world} y-strips of {Nx}x{Ny}, halo {halo} rows, cut by {'cost' if a.balance else 'rows'}",
+                "partition": f"{world} y-strips of {Nx}x{Ny}, halo {halo} rows, cut by {('cost (' + a.balance + ')') if a.balance else 'rows'}",
                 "rows_per_rank": [p["rows"] for p in parts],
                 "nodes": Nx * Ny, "steps": a.steps, "warmup": a.warmup, "particle_steps_per_s": active / (ms_max * 1e-3),
                 "ms_per_step": ms_max / a.steps, "ms_per_step_per_rank": [p["ms"] / a.steps for p in parts],

@@ -69,4 +69,13 @@ def test_weighted_strip_bounds():
     mask[:2] = 0
     mask[:, 0] = 3
     c = row_cost_model(mask, periodic_boundary=False, reach_rows=[1, 1, 1, 1, 2, 3])
-    assert c[0] == pytest.approx(0.75) and c[2] == pytest.approx(9.75) and c[5] > c[4] > c[3]
+    # land row: the gather of its 10 nodes only (0.068 each at reach 1); ocean row: + 9 active particles;
+    # reach 2 and 3: the window grows as (2R+1)^2
+    assert c[0] == pytest.approx(0.68) and c[2] == pytest.approx(9.68)
+    assert c[4] - 9 == pytest.approx(0.68 * 25 / 9) and c[5] - 9 == pytest.approx(0.68 * 49 / 9)
+    # measured costs: each strip's kernel times spread over its rows
+    from picles_b200.distributed import row_cost_measured
+    active = (mask == 1).sum(axis=1)
+    m = row_cost_measured(active, 10, [1, 1, 1, 1, 2, 3], [(0, 3), (3, 6)], ms_advance=[1.0, 3.0], ms_gather=[0.3, 0.9])
+    assert m[:3].sum() == pytest.approx(1.3) and m[3:].sum() == pytest.approx(3.9)
+    assert m[0] == m[1] == pytest.approx(0.1) and m[2] == pytest.approx(1.1) and m[5] > m[4] > m[3]
