@@ -993,8 +993,20 @@ PM_HD bool weights_1d(double zp, int32_t& f, double& wc) {
     return true;
 }
 
+/* pos % N (C remainder: the sign of pos) without the 64-bit division whenever |pos| < 2N — always, for a corner
+   within the supported reach of a node; the division stays behind for anything else, so the value is the same */
+PM_HD int64_t rem_near(int64_t pos, int64_t N) {
+    if (pos >= 0) {
+        if (pos < N) return pos;
+        if (pos < 2 * N) return pos - N;
+    } else {
+        if (pos > -N) return pos;
+        if (pos > -2 * N) return pos + N;
+    }
+    return pos % N;
+}
 PM_HD int64_t wrap_index(int64_t pos, int64_t N) {
-    pos = pos % N;
+    pos = rem_near(pos, N);
     if (pos < 0) pos += N;
     else if (pos == 0) pos += N;
     return pos;
@@ -1008,8 +1020,8 @@ PM_HD bool corner_target(int Nx, int Ny, int bx, int by, int64_t i, int64_t j, i
         return false;
     if ((by == PICLES_BND_TRIPOLAR_NORTH) && (j > Ny)) {
         if (bx != PICLES_BND_PERIODIC) return false;
-        if (i < 0) ii = Nx - (Nx + i % Nx);
-        else ii = Nx - i % Nx;
+        if (i < 0) ii = Nx - (Nx + rem_near(i, Nx));
+        else ii = Nx - rem_near(i, Nx);
         jj = 2 * (int64_t)Ny - j + 1;
         if (ii < 1 || ii > Nx || jj < 1 || jj > Ny) return false;
     } else {
@@ -1228,6 +1240,13 @@ PM_HD void gather_node(const RecView& V, int I, int J, int R, int n_classes, dou
                 int k;
                 unpack_cell(cell, fx, fy, k);
                 if (k != cls) continue;
+                if (V.by != PICLES_BND_PERIODIC) {
+                    /* rows first (no wrap in y here): a corner row jy lands on row J directly (jy == J <= Ny) or through
+                       the fold (2Ny - jy + 1 == J); most candidates of the cross product fail this and need none of the
+                       four corner evaluations */
+                    const int64_t jy0 = (int64_t)j + fy, jf = 2 * (int64_t)Ny + 1 - J;
+                    if (jy0 != J && jy0 + 1 != J && jy0 != jf && jy0 + 1 != jf) continue;
+                }
                 double wxc = V.wx[le], wyc = V.wy[le];
                 double ce = V.e[le], cmx = V.mx[le], cmy = V.my[le];
                 for (int q = 0; q < 4; q++) { /* (x0,y0),(x1,y0),(x0,y1),(x1,y1) */
