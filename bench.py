@@ -698,7 +698,7 @@ def main():
         line["roofline_hbm"].append({"kernel": "k_wind_sample", "note": "k_wind_timeblend (mesh-sized, ~3 us) + k_wind_sample, timed as a pair",
                                      "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
                                      "unit": "GB/s", "frac": gbs / hbm_peak,
-                                     "traffic": nk.get("k_wind_sample", {}).get("dram_bytes"), "ncu_source": ncu_src, "bytes_per_node": 32,
+                                     "traffic": (nk.get("k_wind_sample_x4") or nk.get("k_wind_sample", {})).get("dram_bytes"), "ncu_source": ncu_src, "bytes_per_node": 32,
                                      "nodes_per_launch": n_nodes, "ms_per_launch": e2e_mesh["ms_sample"],
                                      "share_of_step": e2e_mesh["ms_sample"] / (ms_adv + ms_prj + e2e_mesh["ms_sample"]),
                                      "peak_source": hbm_src})

@@ -29,7 +29,8 @@ PICK = {
     "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "warps_active_pct": "sm__warps_active.avg.pct_of_peak_sustained_active",
 }
-UNIT_SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e3, "msecond": 1e6, "nsecond": 1.0, "second": 1e9}
+UNIT_SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "us": 1e3, "ms": 1e6, "ns": 1.0, "s": 1e9,
+              "usecond": 1e3, "msecond": 1e6, "nsecond": 1.0, "second": 1e9}
 
 
 def main():
