@@ -271,6 +271,10 @@ struct OpsSafe {
     static PM_HDM double divz_pre(double a, double b, double, unsigned*) { return a / b; }
     static PM_HDM double sqrt_(double x, unsigned*) { return sqrt(x); }
     static PM_HDM double sqrtz(double x, unsigned*) { return sqrt(x); }
+    static PM_HDM double div_nc(double a, double b) { return a / b; }
+    static PM_HDM double div_pre_nc(double a, double b, double) { return a / b; }
+    static PM_HDM double sqrt_r(double x, unsigned*) { return sqrt(x); }
+    static PM_HDM double absnn(double x) { return fabs(x); }
     static PM_HDM double tanh_(double x, unsigned*) { return pm_tanh_safe(x); }
     static PM_HDM double sech(double x, unsigned*) { return pm_sech_safe(x); }
     static PM_HDM double exp_(double x, unsigned*) { return pm_exp(x); }
@@ -288,6 +292,11 @@ struct OpsFast {
     static __device__ __forceinline__ double divz_pre(double a, double b, double y, unsigned* bad) { return pm_divz_pre_fast(a, b, y, bad); }
     static __device__ __forceinline__ double sqrt_(double x, unsigned* bad) { return pm_sqrt_fast(x, bad); }
     static __device__ __forceinline__ double sqrtz(double x, unsigned* bad) { return pm_sqrtz_fast(x, bad); }
+    /* unchecked divisions and the range-limited root they lean on (pmath.h); |x| of a value known to be >= +0 */
+    static __device__ __forceinline__ double div_nc(double a, double b) { return pm_div_nc_fast(a, b); }
+    static __device__ __forceinline__ double div_pre_nc(double a, double b, double y) { return pm_div_pre_nc_fast(a, b, y); }
+    static __device__ __forceinline__ double sqrt_r(double x, unsigned* bad) { return pm_sqrt_r_fast(x, bad); }
+    static __device__ __forceinline__ double absnn(double x) { return x; }
     static __device__ __forceinline__ double tanh_(double x, unsigned* bad) { return pm_tanh_fast(x, bad); }
     static __device__ __forceinline__ double sech(double x, unsigned* bad) { return pm_sech_fast(x, bad); }
     static __device__ __forceinline__ double exp_(double x, unsigned* bad) { return pm_expx_fast(x, bad); }
@@ -334,25 +343,45 @@ PM_HD void rhs3(const picles_params_t& P, const Hoist& H, double lne, double cx,
                t_dir = STD || P.direction;
     const double P_n = STD ? 2.0 : P.n;
     double r_g = P.r_g;
-    double cbar = O::sqrt_(cx * cx + cy * cy, bad);
-    double c_gp = O::div_pre(fabs(cbar), r_g, H.y_rg, bad);
+    /*
+     * STD also says r_g, e_T in [2^-64, 2^64] and p finite (make_hoist).  Then four of the divisions below and
+     * the one inside sech cannot leave the premises of the fast path and carry no validity test (pmath.h):
+     *   cbar   passes sqrt_r only for cx^2+cy^2 in [2^-970, 2^576) -> cbar in [2^-485, 2^288), never NaN;
+     *   c_gp   = cbar / r_g in [2^-549, 2^352): dividend >= 2^-485, quotient normal;
+     *   kp     = 2.4525 / max(c_gp^2, 1e-2): divisor in [1e-2, 2^704), quotient in (2^-703, 245.25];
+     *   wp     = 4.905 / max(c_gp, 0.1): divisor in [0.1, 2^352);
+     *   kp/e_T : dividend in (2^-703, 245.25], quotient in (2^-767, 2^72).
+     * Whenever sqrt_r raises the flag these hold garbage, and the whole evaluation is repeated with the IEEE
+     * operators, as for every other flag.  cbar and c_gp are >= +0, so their fabs() is the identity.
+     */
+#if defined(PH_CHECK_ALL) /* profiles/: every division with its validity test, to time what leaving them out buys */
+    const bool NC = false;
+#else
+    const bool NC = STD;
+#endif
+    double cbar = NC ? O::sqrt_r(cx * cx + cy * cy, bad) : O::sqrt_(cx * cx + cy * cy, bad);
+    double c_gp = NC ? O::div_pre_nc(O::absnn(cbar), r_g, H.y_rg) : O::div_pre(fabs(cbar), r_g, H.y_rg, bad);
     /* g/(4m) and g/(2m) with the power of two moved into the dividend: the same real quotient,
        hence the same rounded one (neither can leave the normal range), one multiplication less each */
-    double kp = O::div(9.81 / 4.0, pm_maxc(c_gp * c_gp, 1e-2), bad);
-    double wp = O::div(9.81 / 2.0, pm_maxc(fabs(c_gp), 0.1), bad);
+    double kp = NC ? O::div_nc(9.81 / 4.0, pm_maxc(c_gp * c_gp, 1e-2)) : O::div(9.81 / 4.0, pm_maxc(c_gp * c_gp, 1e-2), bad);
+    double wp = NC ? O::div_nc(9.81 / 2.0, pm_maxc(O::absnn(c_gp), 0.1)) : O::div(9.81 / 2.0, pm_maxc(fabs(c_gp), 0.1), bad);
     double gx = O::divz_pre(cx, r_g, H.y_rg, bad), gy = O::divz_pre(cy, r_g, H.y_rg, bad);
     double a1 = O::div(us, 2.0 * c_gp, bad); /* α_func(us, c_gp) */
     double alpha = (a1 > 500.0) ? 500.0 : a1;
     double sg = O::sqrt_(gx * gx + gy * gy, bad);
     double msg = pm_maxc(sg, 1e-4);
     double alpha_p = O::div(u * gx + v * gy, 2.0 * (msg * msg), bad);
-    double Hp = 0.5 * (1.0 + O::tanh_(P.p * (alpha_p - 0.85), bad));
+    /* the fast tanh and sech do not test for NaN: alpha_p is NaN only if its division raised the flag, and with a
+       finite p (STD) neither argument can be NaN otherwise */
+    const double x_t = P.p * (alpha_p - 0.85);
+    if (!STD && bad) *bad |= (x_t != x_t) ? 1u : 0u;
+    double Hp = 0.5 * (1.0 + O::tanh_(x_t, bad));
     double sch = O::sech(10.0 * (alpha_p - 0.85), bad);
     double Dp = 1.0 - 1.25 * (sch * sch);
     double It = t_input ? P.C_e * Hp * (alpha * alpha) : 0.0;
     double Dt, Scg;
     {
-        double r = O::div_pre(kp, P.e_T, H.y_eT, bad), pw;
+        double r = NC ? O::div_pre_nc(kp, P.e_T, H.y_eT) : O::div_pre(kp, P.e_T, H.y_eT, bad), pw;
         double twon = 2.0 * P_n;
         double r2 = r * r;
         pw = (twon == 4.0) ? r2 * r2 : r2;
@@ -448,7 +477,9 @@ PM_HD void make_hoist(const picles_params_t& P, double wu0, double wv0, bool ste
     H.y_rg = 0.0; H.y_eT = 0.0;
 #endif
     H.steady = steady;
-    H.std_terms = P.input && P.dissipation && P.peak_shift && P.direction && (P.n == 2.0);
+    /* ... and parameters in the range the unchecked divisions of the switch-free copy assume (rhs3) */
+    const bool sane = (P.r_g >= 0x1p-64) && (P.r_g <= 0x1p64) && (P.e_T >= 0x1p-64) && (P.e_T <= 0x1p64) && (fabs(P.p) <= 0x1p64);
+    H.std_terms = P.input && P.dissipation && P.peak_shift && P.direction && (P.n == 2.0) && sane;
     H.nseg = nseg;
     H.us0 = sqrt(wu0 * wu0 + wv0 * wv0);
    

@@ -173,6 +173,7 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int6
     Tally c;
     tally_zero(c);
     if (threadIdx.x < ADV_HIST_BINS) s_hist[threadIdx.x] = 0;
+    pm_exptab_shared_init(); /* the exp table of the fast right-hand side (pmath.h) */
     __syncthreads();
     const int lane = threadIdx.x & 31;
     unsigned long long* const queue = &dc->next_chunk[slot];
@@ -258,6 +259,8 @@ k_advance_resume(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* d
     Tally c;
     tally_zero(c);
     (void)l_begin; (void)l_end;
+    pm_exptab_shared_init();
+    __syncthreads();
     const int n_pending = dc->n_pending; /* entries parked earlier in the step are skipped by their cell marker */
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_pending; q += gridDim.x * blockDim.x) {
         const int64_t l = A.pending[q];

@@ -51,23 +51,25 @@ PM_FN double PMV(pm_pow)(double x, double y PM_BADP) {
     return (y == 0.0) ? 1.0 : r;
 }
 
-/* tanh(x) = em1/(em1+2), em1 = expm1(2|x|) = 2^k*expm1(r) + (2^k - 1) */
+/* tanh(x) = em1/(em1+2), em1 = expm1(2|x|) */
 PM_FN double PMV(pm_tanh)(double x PM_BADP) {
     double ax = fabs(x);
     double y = (ax > 25.0) ? 50.0 : 2.0 * ax;
-#ifdef PM_FAST_RANGE
-    *pm_bad |= (x != x) ? 1u : 0u; /* fast instantiation: NaN raises the flag instead of passing through selects */
-#else
+#ifndef PM_FAST_RANGE
     y = (x != x) ? 0.0 : y;
 #endif
-    double p, r;
-    int k = pm_exp_reduce(y, &p, &r); /* 0 <= k <= 73 */
-    double em = r * p;
+    /* fast instantiation: a NaN argument is the CALLER's to flag (the right-hand side's argument is NaN only
+       if the quotient it comes from is, and that division raises the flag); nothing here tests for it */
+    double em, sj, sl;
+    int k = PM_EXP_REDUCE(y, &em, &sj, &sl); /* 0 <= k <= 72 */
+    /* expm1(y) = T (1 + em) - 1 with T = 2^k 2^(j/128) = th + tl: T - 1 is exact for T < 2 (and free of
+       cancellation above), and for y below ln2/256 it is em itself (T = 1, tl = 0) */
     double s = pm_pow2i(k);
-    double em1 = fma(s, em, s - 1.0);
+    double th = sj * s, tl = sl * s;
+    double em1 = fma(th, em, (th - 1.0) + tl);
     double t = PM_DIVZ(em1, em1 + 2.0);
     t = (ax > 22.0) ? 1.0 : t;
-    t = (x < 0.0) ? -t : t;
+    t = copysign(t, x); /* t >= 0: one bit operation instead of compare, negate and select */
 #ifdef PM_FAST_RANGE
     return t;
 #else
@@ -80,17 +82,17 @@ PM_FN double PMV(pm_tanh)(double x PM_BADP) {
 PM_FN double PMV(pm_sech)(double x PM_BADP) {
     double ax = fabs(x);
     ax = (ax > 350.0) ? 350.0 : ax;
-#ifdef PM_FAST_RANGE
-    *pm_bad |= (x != x) ? 1u : 0u;
-#else
-    ax = (x != x) ? 0.0 : ax;
+#ifndef PM_FAST_RANGE
+    ax = (x != x) ? 0.0 : ax; /* fast instantiation: NaN is the caller's to flag, as in pm_tanh */
 #endif
 #ifdef PM_FAST_RANGE
     double e = pm_exp_core_inrange(ax); /* 0 <= ax <= 350 */
 #else
     double e = pm_exp_core(ax);
 #endif
-    double t = PM_DIV(2.0 * e, fma(e, e, 1.0));
+    /* e in [1, 2^505]: dividend 2e in [2, 2^506], divisor e^2 + 1 in [2, 2^1010], quotient in [2^-505, 1] —
+       always inside the fast path's premises, so the division carries no validity test */
+    double t = PM_DIV_NC(2.0 * e, fma(e, e, 1.0));
 #ifdef PM_FAST_RANGE
     return t;
 #else
