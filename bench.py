@@ -11,10 +11,11 @@ example_00_minimal ODE settings (Tsit5 controller, dt=1e-3, dtmin=1e-4, force_dt
 A "step" is one model step: State .= 0; advance! (adaptive RK over DT for every particle);
 ParticleToNode! projection; remesh!.  With N GPUs every rank owns a 4096x4096 y-strip of a
 4096 x (4096*N) box (weak scaling: `value`) and exchanges a halo of particle records per step.
-Two more legs run when N > 1, untimed by the headline: `strong` — the FIXED 4096x4096 box cut in N
+Three more legs run when N > 1, untimed by the headline: `strong` — the FIXED 4096x4096 box cut in N
 strips, with the same box on one GPU timed by rank 0 in the same process (BASELINE.md's 85 % target
-is on this) — and `strip_parity` — a small growing-wind box stepped in N strips over NCCL and as one
-domain on rank 0, compared bit for bit.
+is on this); `strip_parity` — a small growing-wind box stepped in N strips over NCCL and as one
+domain on rank 0, compared bit for bit; and `strong_c5` — BASELINE configs[4], the 4320x3840 tripolar +
+land grid cut in N strips by measured cost, against the same grid on one GPU.
 
 One JSON line is printed by rank 0.  See DESIGN.md §measurement for every field.
 """
@@ -86,7 +87,7 @@ def workload(nx, ny_per_gpu, n_gpus, rank):
 SOLVER = "Tsit5"
 
 
-def params(solver=None, DT=600.0, wind_min_squared=4.0):
+def params(solver=None, DT=600.0, wind_min_squared=4.0, periodic_boundary=False):
     """example_00_minimal.jl:17-67 settings (T04_2D_reg_test uses the same), flattened by the host
     mirror of the reference API — no test or oracle module is involved on the b200 arm."""
     from picles_b200 import FetchRelations as FR
@@ -97,7 +98,7 @@ def params(solver=None, DT=600.0, wind_min_squared=4.0):
     sets = PW.ODESettings(Parameters=pars, log_energy_minimum=FR.MinimalWindsea(10, 10, DT)["lne"], saving_step=DT,
                           timestep=DT, total_time=6 * 86400.0, dt=1e-3, dtmin=1e-4, force_dtmin=True,
                           solver=solver or SOLVER, wind_min_squared=wind_min_squared)
-    return make_params(sets, ps, FR.MinimalState(2, 2, DT), defaults=None, periodic_boundary=False, on_persist=False)
+    return make_params(sets, ps, FR.MinimalState(2, 2, DT), defaults=None, periodic_boundary=periodic_boundary, on_persist=False)
 
 
 class ClockSampler:
@@ -362,6 +363,109 @@ def strong_leg(dist, rank, world, local_rank, args, barrier_all):
             "timing": "CUDA events around the K steps on every rank, max over ranks; rank 0 then times the same box as one domain"}
 
 
+def c5_grid(Nx=4320, Ny=3840, lat_min=-70.0, lat_max=89.0, R_earth=6.371e6):
+    """BASELINE configs[4] shape: a synthetic tripolar grid (x periodic, y tripolar-north) with a rotated per-node
+    projection kernel [cos/dx sin/dy; -sin/dx cos/dy] (TripolarGridMOM6.jl:448-459), the great-circle coefficient
+    (spherical_grid_corrections.jl:13), a masked southern cap and four round land masses; masks by the host mirror
+    of make_boundaries (mask_utils.jl:38-55).  The same grid as profiles/bench_configs.py "C5" (tests build theirs
+    through the oracle's make_boundaries; tests/test_gpu_configs.py holds the two bit-equal)."""
+    from picles_b200.Architectures import N_Periodic, N_TripolarNorth
+    from picles_b200.Grids.mask_utils import make_boundaries
+    lon = -280.0 + (np.arange(Nx) + 0.5) * 360.0 / Nx
+    lat = lat_min + (np.arange(Ny) + 0.5) * (lat_max - lat_min) / Ny
+    LON, LAT = np.meshgrid(lon, lat)
+    cap = np.clip((LAT - 60.0) / 30.0, 0.0, 1.0)
+    angle = 40.0 * cap * np.sin(np.deg2rad(2 * (LON + 280.0)))
+    dlon, dlat = 360.0 / Nx, (lat_max - lat_min) / Ny
+    dx = np.maximum(R_earth * np.cos(np.deg2rad(LAT)) * np.deg2rad(dlon), 2000.0)
+    dy = np.full_like(dx, R_earth * np.deg2rad(dlat))
+    ca, sa = np.cos(angle * np.pi / 180), np.sin(angle * np.pi / 180)
+    M = np.stack([ca / dx, sa / dy, -sa / dx, ca / dy]) * 1.2
+    sgn = np.sign(LAT)
+    pc = (sgn * np.minimum(sgn * np.tan(np.deg2rad(LAT)), 60.0)) / 6.3710e6
+    ocean = np.ones((Ny, Nx), np.uint8)
+    ocean[: max(2, Ny // 40), :] = 0
+    yy, xx = np.mgrid[0:Ny, 0:Nx]
+    for cx, cy, r in ((0.2, 0.45, 0.08), (0.55, 0.6, 0.1), (0.8, 0.3, 0.06), (0.5, 0.97, 0.04)):
+        ocean[((xx - cx * Nx) / Nx) ** 2 + ((yy - cy * Ny) / Ny) ** 2 < r * r] = 0
+    mask = np.ascontiguousarray(make_boundaries(ocean.T, N_Periodic(Nx), N_TripolarNorth(Ny)).T.astype(np.uint8))
+    return dict(Nx=Nx, Ny=Ny, bx=1, by=2, mask=mask, M=np.ascontiguousarray(M), pc=np.ascontiguousarray(pc))
+
+
+def strong_c5_leg(dist, rank, world, local_rank, steps, warmup, halo=6):
+    """BASELINE configs[4]: "T03_PIC_tripolar_land with synthetic land mask at high resolution, 8-GPU y-strip
+    partition" — ONE 4320x3840 tripolar + land grid cut in `world` y-strips (strong scaling), time-varying winds
+    resident before each timed step, halo exchange over NCCL inside the library.  Land and the small cells near
+    the pole make rows unequal, so the strips are cut by MEASURED cost: a calibration run on equal strips (per-strip
+    kernel times, per-row reach) first.  Rank 0 then times the same grid as one domain on its GPU, same steps."""
+    import torch
+    from picles_b200.distributed import StripStepper, row_cost_measured, strip_bounds, strip_bounds_weighted
+    from picles_b200.engine import B200Engine
+    g = c5_grid()
+    Nx, Ny = g["Nx"], g["Ny"]
+    DT = 1200.0
+    P = params(DT=DT, periodic_boundary=True)
+    wind = lambda t: (15.0, -10.0 * np.cos(5 * t / (3600 * 2 * np.pi)))  # tests/T03_PIC_tripolar_aqua.jl:67-68
+
+    def run(bounds, nwarm, nsteps, one_domain=False):
+        j0, j1 = (0, Ny) if one_domain else bounds[rank]
+        eng = B200Engine(Nx, Ny, g["bx"], g["by"], g["mask"][j0:j1], P, M=g["M"][:, j0:j1], pc=g["pc"][j0:j1], device=local_rank,
+                         j0=j0, ny_local=j1 - j0, halo=0 if one_domain else halo)
+        st = None if one_domain else StripStepper(eng, rank, world, periodic_y=False)
+        loc = lambda x: np.ascontiguousarray(np.broadcast_to(np.asarray(x, np.float64), (j1 - j0, Nx)))
+        eng.seed(*[loc(x) for x in wind(0.0)])
+        t, rows, ms_total = 0.0, [], 0.0
+        for k in range(nwarm + nsteps):
+            eng.upload_winds(*[loc(x) for x in (*wind(t), *wind(t + DT))])
+            eng.synchronize()
+            if not one_domain:
+                dist.barrier()
+                torch.cuda.synchronize()
+            eng.timer_start()
+            if one_domain:
+                eng.step(t, DT)
+            else:
+                st.step(t, DT)
+            ms = eng.timer_stop()
+            t += DT
+            if k >= nwarm:
+                rows.append(eng.counters())
+                ms_total += ms
+        out = dict(ms=ms_total, active=sum(r["n_active"] for r in rows), adv=float(np.mean([r["ms_advance"] for r in rows])),
+                   prj=float(np.mean([r["ms_project"] for r in rows])), failed=sum(r["n_failed"] for r in rows), rows=j1 - j0,
+                   row_reach=eng.row_reach().tolist(), halo_rows=eng.halo_rows()[0])
+        eng.close()
+        return out
+
+    eq = strip_bounds(Ny, world)
+    cal = run(eq, warmup, 2)
+    allc = [None] * world
+    dist.all_gather_object(allc, cal)
+    active_rows = ((g["mask"] == 1) | (g["mask"] == 3)).sum(axis=1)
+    reach_rows = np.concatenate([np.asarray(c["row_reach"]) for c in allc])
+    cost = row_cost_measured(active_rows, Nx, reach_rows, eq, [c["adv"] for c in allc], [c["prj"] for c in allc])
+    bounds = strip_bounds_weighted(cost, world, min_rows=max(halo, 1))
+    mine = run(bounds, warmup, steps)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0)
+    one = run(None, warmup, steps, one_domain=True) if rank == 0 else None
+    dist.barrier()
+    if rank != 0:
+        return None
+    ms_max = max(p["ms"] for p in parts)
+    v = sum(p["active"] for p in parts) / (ms_max * 1e-3)
+    v1 = one["active"] / (one["ms"] * 1e-3)
+    return {"scaling": "strong", "workload": f"tripolar + land {Nx}x{Ny} (synthetic; BASELINE configs[4]) cut in {world} y-strips by measured cost, "
+                                             f"DT=1200 s, u=15, v=-10 cos(5t/(3600 2pi)), periodic_boundary model, halo {halo} rows",
+            "value": v, "unit": UNIT, "n_gpus": world, "steps": steps, "ms_per_step": ms_max / steps,
+            "rows_per_rank": [p["rows"] for p in parts], "ms_per_step_per_rank": [p["ms"] / steps for p in parts],
+            "ms_advance_per_rank": [p["adv"] for p in parts], "ms_project_remesh_per_rank": [p["prj"] for p in parts],
+            "halo_rows_exchanged": max(p["halo_rows"] for p in parts), "failed": sum(p["failed"] for p in parts),
+            "value_1gpu_same_run": v1, "ms_per_step_1gpu": one["ms"] / steps, "efficiency": v / (world * v1), "target": 0.85,
+            "timing": "CUDA events around every step (winds uploaded before, barrier between steps), summed per rank, max over ranks; "
+                      "rank 0 then times the same grid as one domain"}
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -616,12 +720,13 @@ def main():
         launches_all = float(launches)
 
     # ---- N > 1: the strong-scaling record and NCCL strip parity (untimed by the headline) ----------
-    strong = parity = None
+    strong = parity = strong_c5 = None
     if dist is not None and not args.no_extra_legs:
         eng.close()
         eng = None
         strong = strong_leg(dist, rank, world, local_rank, args, barrier)
         parity = strip_parity_leg(dist, rank, world, local_rank)
+        strong_c5 = strong_c5_leg(dist, rank, world, local_rank, min(args.steps, 5), args.warmup)
         barrier(None)
 
     if rank != 0:
@@ -706,6 +811,8 @@ def main():
         line["strong"] = strong
     if parity:
         line["strip_parity"] = parity
+    if strong_c5:
+        line["strong_c5"] = strong_c5
     if not args.no_cpu_baseline:
         cb = cpu_arm(min(args.steps, 3), args.warmup, 1024 if args.cpu_sample is None else args.cpu_sample)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -184,6 +184,7 @@ struct Hoist {
     double y_rg, y_eT; /* Newton reciprocals of r_g and e_T (fast path only) */
     double us0;        /* sqrt(u0^2+v0^2): the wind speed when the wind does not change over DT */
     bool steady;       /* every time coefficient of the staged wind is zero */
+    bool steady_warp;  /* ... for every lane of the warp that was here when the invariants were formed (device) */
     bool std_terms;    /* every source term on and n == 2 (the defaults): the right-hand side instantiated without its term switches */
     int nseg;          /* time segments of the staged wind (levels - 1) */
 };
@@ -460,7 +461,7 @@ struct D3 { double d0, d1, d2; };
 PM_HD_NOINLINE_DECL D3 f3_cold(const picles_params_t* Pp, double u, double v, double pc, double lne, double cx,
                                double cy) {
     Hoist H;
-    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false; H.std_terms = false; H.nseg = 1;
+    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false; H.steady_warp = false; H.std_terms = false; H.nseg = 1;
     double us = sqrt(u * u + v * v);
     D3 r;
     rhs3<OpsSafe, false>(*Pp, H, lne, cx, cy, u, v, us, pc, r.d0, r.d1, r.d2, (unsigned*)0);
@@ -477,6 +478,14 @@ PM_HD void make_hoist(const picles_params_t& P, double wu0, double wv0, bool ste
     H.y_rg = 0.0; H.y_eT = 0.0;
 #endif
     H.steady = steady;
+#if defined(__CUDA_ARCH__)
+    /* one vote per particle and model step, here, instead of one per right-hand side: the lanes that reach a
+       right-hand side later are a subset of the lanes voting now (lanes only ever leave the integration loop), so
+       "all steady" now implies "all steady" there; a warp that says no takes the copy that reads the wind per lane */
+    H.steady_warp = __all_sync(__activemask(), steady);
+#else
+    H.steady_warp = steady;
+#endif
     /* ... and parameters in the range the unchecked divisions of the switch-free copy assume (rhs3) */
     const bool sane = (P.r_g >= 0x1p-64) && (P.r_g <= 0x1p64) && (P.e_T >= 0x1p-64) && (P.e_T <= 0x1p64) && (fabs(P.p) <= 0x1p64);
     H.std_terms = P.input && P.dissipation && P.peak_shift && P.direction && (P.n == 2.0) && sane;
@@ -498,7 +507,11 @@ PM_HD void f3(const picles_params_t& P, double wu0, double wv0, const Hoist& H, 
        a warp; a lane that votes yes is steady itself): a field that is constant up to rounding noise (a
        constant wind mesh sampled at the nodes) mixes steady and unsteady lanes, and a split warp
        would run both copies */
+#if defined(PH_VOTE_PER_RHS) /* profiles/: the vote at the head of every right-hand side, as before */
     if (H.std_terms && __all_sync(__activemask(), H.steady)) {
+#else
+    if (H.std_terms && H.steady_warp) {
+#endif
         u = wu0; v = wv0;
         rhs3<OpsFast, true>(P, H, lne, cx, cy, wu0, wv0, H.us0, pc, d0, d1, d2, &bad);
     } else {
@@ -785,6 +798,13 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
     const bool dz = !nz && TSIT5 == 2;
     const Tableau& T = nz ? tableau(PICLES_SOLVER_TSIT5) : (dz ? tableau(PICLES_SOLVER_DP5) : tableau(P.solver));
 #define PH_COEF_ON(c, can_be_zero) (nz || (dz && !(can_be_zero)) || (c) != 0.0)
+    /* prop() in the attempt loop: the Tsit5 / DP5 instantiations are launched with propagation on only
+       (launch_advance; the host build selects them the same way), so they carry no test per stage */
+#define PH_PROP(cx_, cy_, ox_, oy_)                                                              \
+    do {                                                                                         \
+        if (!AUTOSW && TSIT5 != 0) { ox_ = M[0] * (cx_) + M[1] * (cy_); oy_ = M[2] * (cx_) + M[3] * (cy_); } \
+        else prop(P, M, (cx_), (cy_), ox_, oy_);                                                 \
+    } while (0)
     double t = p.t;
     K.st(KS_TSTOP, tstop_in);
     double u0 = p.u0, u1 = p.u1, u2 = p.u2;
@@ -818,7 +838,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
         if (ph >= 2) {
             K.set(ph, 0, d0); K.set(ph, 1, d1); K.set(ph, 2, d2);
             double kx, ky;
-            prop(P, M, n1, n2, kx, ky);
+            PH_PROP(n1, n2, kx, ky);
             if (ph < 7) {
                 double a7 = T.a[7][ph];
                 if (PH_COEF_ON(a7, ph == 2)) { x7s = fma(a7, kx, x7s); y7s = fma(a7, ky, y7s); }
@@ -855,7 +875,8 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
                     }
                 }
                 n0 = fma(dt, i0, u0); n1 = fma(dt, i1, u1); n2 = fma(dt, i2, u2);
-                ts = (s >= 6) ? (t + dt) : fma(T.c[s - 1], dt, t);
+                /* c_6 = c_7 = 1 in both tableaus, and fma(1, dt, t) is t + dt: no select needed for the last two stages */
+                ts = fma(T.c[s - 1], dt, t);
                 if (autosw && s == 6) { K.st(KS_G60, n0); K.st(KS_G61, n1); K.st(KS_DT0, n2); } /* g6 of the monitor */
                 continue;
             }
@@ -995,7 +1016,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
         attempts++;
         {
             double kx, ky;
-            prop(P, M, u1, u2, kx, ky);
+            PH_PROP(u1, u2, kx, ky);
             x7s = T.a[7][1] * kx; y7s = T.a[7][1] * ky;
             xes = T.bt[1] * kx; yes = T.bt[1] * ky;
             if (autosw) { x6r = T.a[6][1] * kx; y6r = T.a[6][1] * ky; }
@@ -1013,6 +1034,7 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
     return switched;
 }
 #undef PH_COEF_ON
+#undef PH_PROP
 
 /* ---- ParticleInCell ------------------------------------------------------- */
 /* get_absolute_i_and_w(zp, i_node): floor offset and ceil-side weight */

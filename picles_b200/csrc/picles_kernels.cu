@@ -875,12 +875,14 @@ void launch_advance2(const DeviceArrays& A, const picles_params_t& P, double DT,
         COUNT_LAUNCH(2);
     } else {
         /* Tsit5 has its own instantiation (compile-time tableau without zero coefficients) */
-        const bool ts5 = (P.solver == PICLES_SOLVER_TSIT5);
+        /* (the specialised instantiations take propagation as given: a run without it — the reference's
+           propagation = false switch — is served by the generic one) */
+        const bool ts5 = (P.solver == PICLES_SOLVER_TSIT5) && P.propagation;
         if (pn && ts5) k_advance<true, false, true><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
         else if (pn) k_advance<true, false><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
         else if (ts5) k_advance<false, false, true><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
         /* ... and so has DP5 on a uniform kernel (the bench06 settings): -1.5 % */
-        else if (P.solver == PICLES_SOLVER_DP5) k_advance<false, false, 2><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
+        else if (P.solver == PICLES_SOLVER_DP5 && P.propagation) k_advance<false, false, 2><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
         else k_advance<false, false><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
         COUNT_LAUNCH(1);
     }

@@ -175,10 +175,10 @@ static void shim_advance_all(Shim* h, double DT, const double* u_t, const double
             double wu1 = u_t1[off + l], wv1 = v_t1[off + l];
             if (!s.ulag.empty() && !(p.flags & PICLES_PF_ON)) { wu1 = s.ulag[l]; wv1 = s.vlag[l]; }
             /* as launch_advance picks the kernel: Tsit5 has its own instantiation */
-            const bool pending = (ph_host_specialised && h->P.solver == PICLES_SOLVER_TSIT5)
+            const bool pending = (ph_host_specialised && h->P.solver == PICLES_SOLVER_TSIT5 && h->P.propagation)
                 ? advance_particle<false, true>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], wu1,
                                                 wv1, h->n_mid, um, vm, M, pc, r, c, K, attempts)
-                : (ph_host_specialised && h->P.solver == PICLES_SOLVER_DP5 && !h->perM)
+                : (ph_host_specialised && h->P.solver == PICLES_SOLVER_DP5 && !h->perM && h->P.propagation)
                 ? advance_particle<false, 2>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], wu1,
                                              wv1, h->n_mid, um, vm, M, pc, r, c, K, attempts)
                 : advance_particle<true>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], wu1,
@@ -421,7 +421,7 @@ int64_t shim_corner_target(int Nx, int Ny, int bx, int by, int64_t i, int64_t j)
 }
 void shim_rhs(const picles_params_t* P, const double* z, double u, double v, const double* M, double pc, double* dz) {
     Hoist H;
-    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false; H.std_terms = false;
+    H.y_rg = 0.0; H.y_eT = 0.0; H.us0 = 0.0; H.steady = false; H.steady_warp = false; H.std_terms = false;
     rhs3<OpsSafe, false>(*P, H, z[0], z[1], z[2], u, v, sqrt(u * u + v * v), pc, dz[0], dz[1], dz[2], (unsigned*)0);
     prop(*P, M, z[1], z[2], dz[3], dz[4]);
 }
