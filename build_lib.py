@@ -8,8 +8,8 @@ import sys
 ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, "picles_b200", "csrc")
 OUT = os.path.join(ROOT, "picles_b200", "libpicles_b200.so")
-SOURCES = ["picles_kernels.cu", "picles_capi.cu"]
-HEADERS = ["physics.h", "pmath.h", "pmath_body.h", "pmath_exptab.h", "pmath_trig.h", "wind_mesh.h", "stiff.h", "pmath_dual.h", "picles_device.h", os.path.join("..", "..", "include", "picles_b200.h")]
+SOURCES = ["picles_kernels.cu", "picles_capi.cu", "picles1d.cu"]
+HEADERS = ["physics.h", "physics1d.h", "pmath.h", "pmath_body.h", "pmath_exptab.h", "pmath_trig.h", "wind_mesh.h", "stiff.h", "pmath_dual.h", "picles_device.h", os.path.join("..", "..", "include", "picles_b200.h")]
 
 # --fmad=false: physics.h writes every fused multiply-add explicitly so device results are
 # bit-identical to the CPU oracle (see pmath.h).

@@ -421,6 +421,42 @@ int picles_measure_wind_sample(picles_t* h, double t, int reps, double* ms_per_l
 /* measured HBM copy bandwidth (read+write bytes / s) over a buffer of `mib` MiB */
 int picles_measure_hbm_copy(picles_t* h, int mib, double* gbs);
 
+/* ---- the ONE-DIMENSIONAL model (WaveGrowth1D) ---------------------------------
+ * The same seam, one dimension down: everything `init_particles!(::Abstract1DModel)` and
+ * `time_step!(::Abstract1DModel, dt)` do.
+ *   picles1d_seed  replaces  init_particles!                 src/Simulations/run.jl:268-302
+ *                            SeedParticle!                   src/Operators/core_1D.jl:270-330
+ *   picles1d_step  replaces  State .= 0                      src/Simulations/run.jl:72-80
+ *                            time_step!(::Abstract1DModel)   src/Operators/TimeSteppers.jl:51-92
+ *                              advance!                      src/Operators/mapping_1D.jl:84-190
+ *                              ParticleToNode! / push_to_grid! + merge!
+ *                                                            src/Operators/mapping_1D.jl:41-53, src/ParticleInCell.jl:562-590, 228-252
+ *                              remesh! / NodeToParticle!     src/Operators/mapping_1D.jl:197-283
+ *   picles1d_set_grid        OneDGrid / OneDGridNotes        src/ParticleMesh.jl:102-134
+ * The state vector of a particle is [lne, c̄_x, x] (particle_waves_v5.jl:584-650); State is (Nx, 3) column-major
+ * [e, m_x, 0].  picles_params_t is shared with the 2-D path: C_varphi, direction, defaults, on_persist and
+ * minimal_state as [E_min, m_x^2_min] — `periodic_boundary` is the model kwarg that wraps deposits and removes the
+ * two boundary particles.  Solver ids: Tsit5, DP5; AutoTsit5 runs as Tsit5 (the Rosenbrock23 branch is 2-D only).
+ * Winds: node values at t and t + dt_model; the particle reads them at its own position (linear in x between
+ * nodes, linear in time).  has_defaults must be 0 (wind-sea seeding).
+ */
+typedef struct picles1d_handle picles1d_t;
+int picles1d_create(picles1d_t** h, int device_id);
+int picles1d_destroy(picles1d_t* h);
+const char* picles1d_last_error(picles1d_t* h);
+/* x_nodes[Nx]: OneDGridNotes.x (the particles' coordinates); xmin, dx: OneDGrid.xmin, .dx (the frame of the
+   deposit weights, ParticleInCell.jl:165) */
+int picles1d_set_grid(picles1d_t* h, int Nx, double xmin, double dx, const double* x_nodes);
+int picles1d_set_params(picles1d_t* h, const picles_params_t* params);
+/* u0[Nx]: winds(x_i, 0) */
+int picles1d_seed(picles1d_t* h, const double* u0);
+/* u_t[Nx], u_t1[Nx]: winds(x_i, t), winds(x_i, t + dt_model) */
+int picles1d_step(picles1d_t* h, double t, double dt_model, const double* u_t, const double* u_t1);
+int picles1d_get_state(picles1d_t* h, double* S /* Nx*3 */);
+/* z[3*Nx] planes lne, c̄_x, x; t, dt, flags, status may be NULL */
+int picles1d_get_particles(picles1d_t* h, double* z, double* t, double* dt, uint8_t* flags, int32_t* status);
+int picles1d_get_counters(picles1d_t* h, picles_counters_t* out);
+
 #ifdef __cplusplus
 }
 #endif

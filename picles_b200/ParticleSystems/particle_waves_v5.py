@@ -85,15 +85,21 @@ class ParticleSystem:
     direction: bool = True
 
 
-def particle_equations(u_wind, v_wind, γ=0.88, q=-1 / 4.0, IDConstants_=None, propagation=True, input=True,
+_ONE_D = object()  # marker: particle_equations(u_wind; ...) with a single forcing field = the 1-D system
+
+
+def particle_equations(u_wind, v_wind=_ONE_D, γ=0.88, q=-1 / 4.0, IDConstants_=None, propagation=True, input=True,
                        dissipation=True, peak_shift=True, direction=True, debug_output=False, static=False):
-    """particle_waves_v5.jl:382-395.  `debug_output`/`static` select host-only variants
-    in the reference and are not part of the stepping path."""
+    """particle_waves_v5.jl:382-395 (two forcing fields: the 2-D system) and :584-650 (one forcing field: the 1-D
+    system [lne, c̄_x, x], no directional term).  `debug_output`/`static` select host-only variants in the
+    reference and are not part of the stepping path."""
     if debug_output or static:
         raise NotImplementedError("debug_output/static variants are outside the B200 path")
     idc = IDConstants_ if IDConstants_ is not None else IDConstants.make()
     p, q, n = magic_fractions(q)
     e_T = e_T_func(γ, p, q, n, c_β=idc.c_β, c_D=idc.c_D, c_e=idc.c_e, c_α=idc.c_alpha)
+    if v_wind is _ONE_D:
+        return ParticleSystem(u_wind, None, γ, q, p, n, e_T, propagation, input, dissipation, peak_shift, False)
     return ParticleSystem(u_wind, v_wind, γ, q, p, n, e_T, propagation, input, dissipation, peak_shift, direction)
 
 

@@ -167,6 +167,17 @@ SYMBOLS = {
     "picles_measure_fp64_peak": (C.c_int, [_vp, _dp]),
     "picles_measure_hbm_copy": (C.c_int, [_vp, C.c_int, _dp]),
     "picles_measure_wind_sample": (C.c_int, [_vp, C.c_double, C.c_int, _dp]),
+    # the one-dimensional model (WaveGrowth1D)
+    "picles1d_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "picles1d_destroy": (C.c_int, [_vp]),
+    "picles1d_last_error": (C.c_char_p, [_vp]),
+    "picles1d_set_grid": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _vp]),
+    "picles1d_set_params": (C.c_int, [_vp, C.POINTER(PiclesParams)]),
+    "picles1d_seed": (C.c_int, [_vp, _vp]),
+    "picles1d_step": (C.c_int, [_vp, C.c_double, C.c_double, _vp, _vp]),
+    "picles1d_get_state": (C.c_int, [_vp, _vp]),
+    "picles1d_get_particles": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "picles1d_get_counters": (C.c_int, [_vp, C.POINTER(PiclesCounters)]),
 }
 
 _lib = None

@@ -13,7 +13,7 @@ def make_params(ODEsets, ODEsys, minimal_state, defaults=None, periodic_boundary
     par = ODEsets.Parameters
     P.r_g = float(par["r_g"])
     P.C_alpha = float(par["C_α"])
-    P.C_varphi = float(par["C_φ"])
+    P.C_varphi = float(par.get("C_φ", 0.0))  # absent from the 1-D parameter set (r_g, C_α, C_e)
     P.C_e = float(par["C_e"])
     P.g = float(par.get("g", 9.81))
     P.p, P.q, P.n, P.e_T = float(ODEsys.p), float(ODEsys.q), float(ODEsys.n), float(ODEsys.e_T)

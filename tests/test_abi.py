@@ -16,7 +16,7 @@ HEADER = os.path.join(ROOT, "include", "picles_b200.h")
 def declared_symbols():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return set(re.findall(r"\b(picles_[a-z0-9_]+)\s*\(", src))
+    return set(re.findall(r"\b(picles(?:1d)?_[a-z0-9_]+)\s*\(", src))
 
 
 def test_library_exports_every_declared_symbol():
