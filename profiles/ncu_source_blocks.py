@@ -2,7 +2,7 @@
 """Dynamic view of a kernel from an ncu capture with source counters (--import-source on): executed warp
 instructions and stall samples per basic block and per opcode.  Read here, no GPU needed.
 
-    python profiles/ncu_source_blocks.py capture.ncu-rep [--top N] [--dump BLOCKSTART_HEX]
+    python profiles/ncu_source_blocks.py capture.ncu-rep [--kernel NAME] [--top N] [--dump BLOCKSTART_HEX]
 """
 import collections
 import csv
@@ -23,8 +23,13 @@ def main():
     top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 14
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     lines = txt.split("\n")
-    start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
-    rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:]))))
+    # one section per profiled launch ("Kernel Name" line, header line, rows): take the first whose name holds --kernel
+    want = sys.argv[sys.argv.index("--kernel") + 1] if "--kernel" in sys.argv else "k_advance"
+    heads = [i for i, l in enumerate(lines) if l.startswith('"Kernel Name"')]
+    sec = next(i for i in heads if want in lines[i])
+    end = next((j for j in heads if j > sec), len(lines))
+    start = next(i for i in range(sec, end) if lines[i].startswith('"Address"'))
+    rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:end]))))
     base = int(rows[0]["Address"], 16)
     ins = []
     for r in rows:
