@@ -368,7 +368,7 @@ def c5_grid(Nx=4320, Ny=3840, lat_min=-70.0, lat_max=89.0, R_earth=6.371e6):
     projection kernel [cos/dx sin/dy; -sin/dx cos/dy] (TripolarGridMOM6.jl:448-459), the great-circle coefficient
     (spherical_grid_corrections.jl:13), a masked southern cap and four round land masses; masks by the host mirror
     of make_boundaries (mask_utils.jl:38-55).  The same grid as profiles/bench_configs.py "C5" (tests build theirs
-    through the oracle's make_boundaries; tests/test_gpu_configs.py holds the two bit-equal)."""
+    through the oracle's make_boundaries; tests/test_bench_contract.py holds the two bit-equal)."""
     from picles_b200.Architectures import N_Periodic, N_TripolarNorth
     from picles_b200.Grids.mask_utils import make_boundaries
     lon = -280.0 + (np.arange(Nx) + 0.5) * 360.0 / Nx

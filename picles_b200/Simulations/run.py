@@ -51,9 +51,17 @@ class Simulation:
         self.store_itereation = 0
 
 
+def _is_1d(model):
+    return getattr(model, "dims", 2) == 1
+
+
 def init_particles(model, defaults=None, verbose=False):
     """init_particles!(model; defaults): SeedParticle for every node with the wind at t = 0
-    (run.jl:199-247) — one picles_seed call."""
+    (run.jl:199-247; the Abstract1DModel method: run.jl:268-302) — one picles_seed / picles1d_seed call."""
+    if _is_1d(model):
+        from ..Models.WaveGrowthModels1D import init_particles_1D
+        init_particles_1D(model, defaults=defaults, verbose=verbose)
+        return
     if model._gridded_winds is not None:
         model.engine.seed_wind_mesh(0.0)
     else:
@@ -69,7 +77,8 @@ def initialize_simulation(sim):
     if sim.model.clock.iteration != 0:
         sim.model.clock.iteration = 0
         sim.model.clock.time = 0.0
-    sim.model._wind_level_time = 0.0 if sim.model.clock.time == 0.0 else None
+    if not _is_1d(sim.model):
+        sim.model._wind_level_time = 0.0 if sim.model.clock.time == 0.0 else None
     sim.initialized = True
 
 
@@ -80,7 +89,8 @@ def reset_simulation(sim):
     sim.model.clock.iteration = 0
     sim.model.clock.time = 0.0
     init_particles(sim.model, defaults=sim.model.ODEdefaults, verbose=sim.verbose)
-    sim.model.engine.zero_state()
+    if not _is_1d(sim.model):
+        sim.model.engine.zero_state()
     sim.initialized = True
 
 
@@ -117,7 +127,11 @@ def run(sim, store=False, pickup=False, cash_store=False, debug=False):
         if snap:
             stage = eng.pinned_state_buffer()
     while sim.running:
-        time_step(sim.model, sim.Δt, debug=debug, zero_state_first=True)
+        if _is_1d(sim.model):
+            from ..Models.WaveGrowthModels1D import time_step_1D
+            time_step_1D(sim.model, sim.Δt, debug=debug)   # State .= 0 is part of picles1d_step
+        else:
+            time_step(sim.model, sim.Δt, debug=debug, zero_state_first=True)
         if debug and len(sim.model.FailedCollection) > 0:
             log.info("debug mode: found failed particles: %s; break", sim.model.FailedCollection)
             break

@@ -45,3 +45,18 @@ def test_product_arm_has_no_cpu_fallback():
     assert r.returncode != 0
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert "no CPU fallback" in r.stderr
+
+
+def test_bench_c5_grid_is_the_tests_grid():
+    """bench.py builds the tripolar + land grid of its strong_c5 leg without touching tests/ or oracle/ (host mirror of
+    make_boundaries); it must be the grid profiles/bench_configs.py and the GPU config tests build through the oracle"""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    import bench
+    from bench_configs import tripolar
+    for nx, ny in ((432, 384), (270, 240)):
+        a, b = bench.c5_grid(nx, ny), tripolar(nx, ny, True)
+        assert a["bx"] == b["bx"] and a["by"] == b["by"]
+        assert np.array_equal(a["mask"], b["mask"]) and a["mask"].dtype == np.uint8
+        assert np.array_equal(a["M"], b["M"]) and np.array_equal(a["pc"], b["pc"])

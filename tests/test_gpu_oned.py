@@ -72,3 +72,26 @@ def test_gpu_1d_host_api():
         assert np.array_equal(model.State, o.state().T), f"step {k + 1}"
     assert model.clock.iteration == 5 and model.State.shape == (40, 3)
     assert model.boundary == [1, 40]
+
+
+def test_gpu_1d_simulation_run_with_cash_store():
+    """Simulation(model, Δt, stop_time) / run!(sim, cash_store=true) on the 1-D model (tests/T03_PIC_propagation_1d.jl:
+    176-182): floor(stop/Δt) + 1 steps, one State copy per step plus the initial one"""
+    from picles_b200 import FetchRelations as FR
+    from picles_b200.Models.WaveGrowthModels1D import WaveGrowth1D
+    from picles_b200.ParticleMesh import OneDGrid
+    from picles_b200.ParticleSystems import particle_waves_v5 as PW
+    from picles_b200.Simulations.run import Simulation, run
+    DT = 600.0
+    pars, cid, _ = PW.ODEParameters(r_g=0.85)
+    u = lambda x, t: 12.0
+    system = PW.particle_equations(u, γ=cid.γ, q=cid.q)
+    sets = PW.ODESettings(Parameters=dict(r_g=0.85, C_α=pars["C_α"], C_e=pars["C_e"]), log_energy_minimum=FR.MinimalWindsea(10, 0, DT)["lne"],
+                          saving_step=DT, timestep=DT, total_time=86400.0, dt=1e-3, dtmin=1e-4, force_dtmin=True, solver="Tsit5")
+    model = WaveGrowth1D(grid=OneDGrid(0.0, 500e3, 51), winds=u, ODEsys=system, ODEsets=sets, periodic_boundary=True)
+    sim = Simulation(model, Δt=DT, stop_time=3600.0, verbose=False)
+    run(sim, cash_store=True)
+    assert model.clock.iteration == 7 and len(sim.store.store) == 8
+    assert all(s.shape == (51, 3) for s in sim.store.store)
+    assert np.array_equal(sim.store.store[-1], model.State) and np.all(np.isfinite(model.State))
+    assert model.counters()["n_integrated"] == 51 and model.counters()["n_failed"] == 0
