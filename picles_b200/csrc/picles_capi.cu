@@ -24,6 +24,7 @@ using namespace picles;
 #define PIPE_CHUNKS 8
 #define PIPE_MIN_NODES (1 << 20)
 static_assert(PIPE_CHUNKS + 2 <= ADV_SLOTS, "one work queue per advance launch of a step");
+static_assert(PIPE_CHUNKS == ADV_SLOT_BOUNDARY, "the boundary launch takes the queue behind the interior's chunks");
 #define PIPE_EVENTS (PIPE_CHUNKS + 6) /* chunk landed x8, boundary blocks x2, boundary advanced, halo exchanged, interior advanced, compute stream idle */
 
 struct picles_handle {
@@ -723,7 +724,7 @@ int picles_set_global_reach(picles_t* h, int reach) {
     int rc = need_ready(h, true);
     if (rc) return rc;
     if (reach < 0) return fail(h, PICLES_ERR_ARG, "negative reach");
-    h->reach_all_host = reach;
+    h->reach_all_host = reach + 1; /* 0 means "not set" to the gather */
     CK(cudaMemcpyAsync(&h->d_counters->reach_all, &h->reach_all_host, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return PICLES_OK;
@@ -1322,12 +1323,17 @@ int picles_halo_exchange(picles_t* h, int lo_rank, int hi_rank) {
     return exchange_on(h, lo_rank, hi_rank, h->stream);
 }
 
-/* the largest reach of any strip, for the gather's check that enough halo rows were exchanged: a 4-byte
-   ncclAllReduce(max) of the strips' own reach, enqueued behind the advance (every rank of the communicator takes
-   part in every step) */
-static int reach_allreduce(picles_t* h, cudaStream_t st) {
+/* the reach that decides whether enough halo rows were exchanged, the same number on every strip: a 4-byte
+   ncclAllReduce(max), every rank of the communicator taking part in every step.  Only particles within the supported
+   reach (PH_REACH_MAX_ABI rows) of a strip edge can land on a neighbour, so picles_step_strip advances exactly those
+   rows in its boundary launch and all-reduces THEIR reach (boundary_zones) while the interior still integrates: no
+   strip waits for another strip's interior.  The serial path all-reduces the whole strip's reach behind its advance. */
+__global__ void k_reach_word(const int32_t* src, int32_t* dst) { *dst = *src + 1; }
+static int reach_allreduce(picles_t* h, cudaStream_t st, bool boundary_zones) {
     if (!h->comm || h->comm_size < 2 || !h->reach_send) return PICLES_OK;
-    CK(cudaMemcpyAsync(h->reach_send, &h->d_counters->reach, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    /* 1 + reach: the gather reads 0 as "nobody all-reduced" */
+    k_reach_word<<<1, 1, 0, st>>>(boundary_zones ? &h->d_counters->reach_bnd : &h->d_counters->reach, h->reach_send);
+    CK(cudaGetLastError());
     NCK(g_nccl.all_reduce(h->reach_send, &h->d_counters->reach_all, 1, 2 /* ncclInt32 */, 2 /* ncclMax */, h->comm, st));
     return PICLES_OK;
 }
@@ -1345,30 +1351,34 @@ int picles_step_strip(picles_t* h, double t, double dt_model, const double* u_t,
     if (rc) return rc;
     (void)t;
     const DeviceArrays& A = h->A;
-    const bool overlap = A.hx > 0 && (lo_rank >= 0 || hi_rank >= 0) && A.ny > 2 * A.hx;
+    /* boundary zones: the hb rows next to each strip edge, hb = the widest exchange the strip supports.  A particle
+       further inside cannot reach a neighbour (PICLES_ERR_HALO otherwise), so the zones' reach is all the neighbours
+       need to know — and it is known early */
+    const int hb = A.halo;
+    const bool overlap = A.hx > 0 && (lo_rank >= 0 || hi_rank >= 0) && hb >= A.hx && A.ny > 2 * hb;
     if (!overlap) {
         rc = upload_and_advance(h, dt_model, u_t, v_t, u_t1, v_t1);
         if (rc) return rc;
         rc = exchange_on(h, lo_rank, hi_rank, h->stream);
         if (rc) return rc;
-        rc = reach_allreduce(h, h->stream);
+        rc = reach_allreduce(h, h->stream, false);
         if (rc) return rc;
     } else {
         rc = begin_advance(h, dt_model, u_t, v_t, u_t1, v_t1);
         if (rc) return rc;
-        /* the two boundary row blocks: ONE launch on the communication stream, submitted first so that its few blocks
+        /* the two boundary zones: ONE launch on the communication stream, submitted first so that its few blocks
            are resident before the interior launch (whose blocks stay until the work queue is empty) fills the SMs.
            Behind each other on the compute stream the two small launches cost their full latency (~0.15 ms each,
            one chunk per warp) with the GPU idle: the fixed cost that capped strong scaling. */
-        cudaEvent_t ready = h->pev[PIPE_CHUNKS + 2], exchanged = h->pev[PIPE_CHUNKS + 3], interior = h->pev[PIPE_CHUNKS + 4];
+        cudaEvent_t ready = h->pev[PIPE_CHUNKS + 2], exchanged = h->pev[PIPE_CHUNKS + 3];
         CK(cudaEventRecord(ready, h->stream));                     /* counters and per-row reach zeroed */
         CK(cudaStreamWaitEvent(h->comm_stream, ready, 0));
-        rc = upload_rows(h, u_t, v_t, u_t1, v_t1, 0, A.hx, h->pev[PIPE_CHUNKS], h->comm_stream);
+        rc = upload_rows(h, u_t, v_t, u_t1, v_t1, 0, hb, h->pev[PIPE_CHUNKS], h->comm_stream);
         if (rc) return rc;
-        rc = upload_rows(h, u_t, v_t, u_t1, v_t1, A.ny - A.hx, A.ny, h->pev[PIPE_CHUNKS + 1], h->comm_stream);
+        rc = upload_rows(h, u_t, v_t, u_t1, v_t1, A.ny - hb, A.ny, h->pev[PIPE_CHUNKS + 1], h->comm_stream);
         if (rc) return rc;
-        launch_advance2(A, h->P, dt_model, h->d_counters, h->sms, h->comm_stream, 0, (int64_t)A.hx * A.Nx,
-                        (int64_t)(A.ny - A.hx) * A.Nx, (int64_t)A.ny * A.Nx, PIPE_CHUNKS);
+        launch_advance2(A, h->P, dt_model, h->d_counters, h->sms, h->comm_stream, 0, (int64_t)hb * A.Nx,
+                        (int64_t)(A.ny - hb) * A.Nx, (int64_t)A.ny * A.Nx, ADV_SLOT_BOUNDARY);
         CK(cudaGetLastError());
         if (u_t || u_t1) { /* whole-plane readers on the compute stream (the lag-level copy, the remesh) see the boundary rows too */
             CK(cudaStreamWaitEvent(h->stream, h->pev[PIPE_CHUNKS], 0));
@@ -1376,19 +1386,17 @@ int picles_step_strip(picles_t* h, double t, double dt_model, const double* u_t,
         }
         /* the interior is enqueued before the exchange: the host side of the NCCL group (tens of microseconds) must not
            sit between the two advance launches */
-        rc = advance_range(h, dt_model, u_t, v_t, u_t1, v_t1, A.hx, A.ny - A.hx);
+        rc = advance_range(h, dt_model, u_t, v_t, u_t1, v_t1, hb, A.ny - hb);
         if (rc) return rc;
         rc = exchange_on(h, lo_rank, hi_rank, h->comm_stream);     /* boundary records written: pack, send/recv, unpack */
         if (rc) return rc;
+        rc = reach_allreduce(h, h->comm_stream, true);             /* ... and the zones' reach: nothing here waits for an interior */
+        if (rc) return rc;
+        CK(cudaEventRecord(exchanged, h->comm_stream));            /* halo rows in place, reach of every strip's zones known */
         CK(cudaEventRecord(h->ev[1], h->stream));
         CK(cudaGetLastError());
         rc = keep_lag_level(h);
         if (rc) return rc;
-        CK(cudaEventRecord(interior, h->stream));                  /* interior records written */
-        CK(cudaStreamWaitEvent(h->comm_stream, interior, 0));
-        rc = reach_allreduce(h, h->comm_stream);
-        if (rc) return rc;
-        CK(cudaEventRecord(exchanged, h->comm_stream));            /* halo rows in place, reach of every strip known */
         CK(cudaStreamWaitEvent(h->stream, exchanged, 0));
     }
     for (;;) {

@@ -18,6 +18,7 @@
 /* advance launches per step that may be in flight on one DeviceCounters: the pipelined row blocks of an upload
    (slots 0..7) and the two boundary blocks of a strip (8, 9) */
 #define ADV_SLOTS 12
+#define ADV_SLOT_BOUNDARY 8 /* work queue of the launch that advances a strip's two boundary zones (picles_step_strip) */
 #define ADV_HIST_BINS 48
 /* projection gather + remesh: one block per tile of PR_TX x TY target nodes; the record tile
    (targets + a halo) is staged in shared memory by TMA.  The TMA box is always PR_BW x PR_BH
@@ -84,9 +85,13 @@ struct DeviceCounters {
     int32_t reach_halo;   /* max reach of the records received into the halo rows */
     int32_t class1;       /* a deposit of the second class (a mask-3 particle of a periodic model) exists */
     int32_t n_pending;    /* AutoTsit5: particles parked by k_advance this step (entries of DeviceArrays::pending) */
-    int32_t reach_all;    /* strips: max reach over every strip (all-reduced before the gather; 0 when the host validates the reach itself) */
+    int32_t reach_all;    /* strips: 1 + the all-reduced reach that decides whether the hx rows exchanged suffice (the strips' boundary zones
+                             under picles_step_strip, whole strips when the host all-reduces picles_get_reach); 0: not set, the gather
+                             then judges by what this strip knows itself */
     int32_t halo_short;   /* strips: set by the gather when deposits reach further than the hx rows exchanged — it then changes nothing */
     int32_t n_seed_off;   /* written by k_seed: active particles seeded off (they need the lag wind level under B-1 as run) */
+    int32_t reach_bnd;    /* strips: max reach of the deposits of the two boundary zones (the rows within the supported reach of a
+                             strip edge: only their particles can land on a neighbour), known as soon as the boundary launch is done */
     /* work queue of the advance launches of one step: launch `slot` hands out its 32-particle chunks from next_chunk[slot] */
     unsigned long long next_chunk[ADV_SLOTS];
     /* particles that integrated this step by the number of Runge-Kutta attempts they took (last bin: >= ADV_HIST_BINS - 1) */

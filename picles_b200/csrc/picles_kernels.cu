@@ -57,7 +57,7 @@ __device__ __forceinline__ void tally_merge(Tally& a, const Tally& b) {
     a.reach = max(a.reach, b.reach); a.max_attempts = max(a.max_attempts, b.max_attempts);
     a.stiff_switches += b.stiff_switches; a.stiff_attempts += b.stiff_attempts;
 }
-__device__ void tally_flush(const Tally& c, DeviceCounters* dc) {
+__device__ void tally_flush(const Tally& c, DeviceCounters* dc, bool boundary_zone = false) {
     __shared__ int32_t s_sum[TALLY_NSUM];
     __shared__ int32_t s_max[2];
     if (threadIdx.x < TALLY_NSUM) s_sum[threadIdx.x] = 0;
@@ -81,6 +81,7 @@ __device__ void tally_flush(const Tally& c, DeviceCounters* dc) {
         atomicAdd(&dc->sums[threadIdx.x], (unsigned long long)s_sum[threadIdx.x]);
     if (threadIdx.x == 0) {
         if (s_max[0]) atomicMax(&dc->reach, s_max[0]);
+        if (s_max[0] && boundary_zone) atomicMax(&dc->reach_bnd, s_max[0]);
         if (s_max[1]) atomicMax(&dc->max_attempts, s_max[1]);
     }
 }
@@ -237,7 +238,7 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int6
             }
         }
     }
-    tally_flush(c, dc);
+    tally_flush(c, dc, slot == ADV_SLOT_BOUNDARY);
     if (threadIdx.x < ADV_HIST_BINS && s_hist[threadIdx.x])
         atomicAdd(&dc->attempt_hist[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
 }
@@ -300,7 +301,8 @@ k_advance_resume(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* d
             if (((uint32_t)r.cell >> 28) & 1u) dc->class1 = 1;
         }
     }
-    tally_flush(c, dc);
+    /* a parked particle may lie in a boundary zone: counted there too (an over-estimate can only widen an exchange) */
+    tally_flush(c, dc, true);
 }
 
 /* ---- projection gather + remesh ---------------------------------------------------- */
@@ -455,10 +457,13 @@ k_project_remesh(const __grid_constant__ ProjectMaps maps, const __grid_constant
        neighbours' rows received into the halo (reach_halo) */
     int R = min(max(dc->reach, dc->reach_halo), PH_REACH_MAX);
     if (A.ny != A.Ny) {
-        /* strips: a deposit of a neighbour's particle can land here from as far as the largest reach of any strip.
-           If that is more than the hx rows exchanged, records are missing: touch nothing, say so, and let the host
-           repeat exchange and gather with wider rows (picles_step_strip does; the advance is not repeated) */
-        const int need = max(max(dc->reach, dc->reach_halo), dc->reach_all);
+        /* strips: a deposit of a neighbour's particle can land here from as far as the largest reach of the particles
+           near a strip edge.  If that is more than the hx rows exchanged, records are missing: touch nothing, say so,
+           and let the host repeat exchange and gather with wider rows (picles_step_strip does; the advance is not repeated) */
+        /* reach_all - 1: the all-reduced reach, the same number on every strip (so every strip takes this branch together,
+           which the repeated exchange relies on); 0: nobody all-reduced, judge by what this strip knows */
+        const int ra = dc->reach_all;
+        const int need = ra > 0 ? ra - 1 : max(dc->reach, dc->reach_halo);
         if (need > A.hx) {
             if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) dc->halo_short = need;
             return;

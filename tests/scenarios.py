@@ -119,6 +119,24 @@ def sc_tripolar():
     return g, P, wind, 1200.0, 6
 
 
+def sc_tripolar_tall():
+    """the tripolar scenario on 72 rows: two strips of 36 rows are tall enough (> 2 x 15) for picles_step_strip's
+    overlapped path — boundary zones advanced and exchanged, their reach all-reduced, while the interior integrates"""
+    Nx, Ny = 48, 72
+    ocean = np.ones((Ny, Nx), np.uint8)
+    ocean[:2, :] = 0
+    ocean[20:30, 8:15] = 0
+    ocean[Ny - 3:, 20:27] = 0
+    g = tripolar_grid(Nx, Ny, ocean=ocean)
+    g["M"] = g["M"] * 60.0
+    P = default_params(DT=1200.0, periodic_boundary=True)
+
+    def wind(t):
+        return 15.0, -10.0 * np.cos(5 * t / (3600 * 2 * np.pi))
+
+    return g, P, wind, 1200.0, 5
+
+
 def sc_tripolar_propagation_only():
     """T03_PIC_tripolar_aqua.jl:149-155: source terms off, default particle, pure advection
     across the fold."""
@@ -224,6 +242,7 @@ SCENARIOS = {
     "growing_winds_persist": sc_growing_winds_persist,
     "pulse_winds": sc_pulse_winds,
     "tripolar": sc_tripolar,
+    "tripolar_tall": sc_tripolar_tall,
     "tripolar_propagation_only": sc_tripolar_propagation_only,
     "emax_clamp": sc_emax_clamp,
     "maxiters": sc_maxiters,

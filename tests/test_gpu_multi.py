@@ -24,7 +24,10 @@ def _ngpu():
     ("minimal", 2, 2, "torch-p2p"), ("tripolar", 3, 6, "nccl-lib"), ("land_block", 4, 2, "nccl-lib"),
     # one halo row, particles crossing 2-4 cells per step: the exchange widens itself (all-reduced reach, repeated
     # exchange + gather inside picles_step_strip; reach validated by the host for the torch transport)
-    ("fast_box", 2, 1, "nccl-lib"), ("fast_box", 2, 1, "torch-p2p"), ("pulse_winds", 2, 2, "nccl-lib")])
+    ("fast_box", 2, 1, "nccl-lib"), ("fast_box", 2, 1, "torch-p2p"), ("pulse_winds", 2, 2, "nccl-lib"),
+    # strips taller than twice the supported reach take the overlapped path of picles_step_strip (boundary zones first,
+    # their reach all-reduced while the interior integrates); fast_box above is one of them, with a widening exchange
+    ("tripolar_tall", 2, 6, "nccl-lib")])
 def test_strips_over_nccl_match_oracle(gpu_lib, tmp_path, name, world, halo, transport):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
