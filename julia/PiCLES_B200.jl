@@ -109,7 +109,7 @@ function flatten_params(model, arch::B200)
     par = S.Parameters
     mf = magic_fractions(arch.q)
     d = model.ODEdefaults
-    PiclesParams(par.r_g, par.C_α, par.C_φ, par.C_e, get(par, :g, 9.81),
+    PiclesParams(par.r_g, par.C_α, get(par, :C_φ, 0.0), par.C_e, get(par, :g, 9.81),   # the 1-D parameter set has no C_φ
         mf.p, mf.q, mf.n, e_T_func(arch.γ, mf.p, mf.q, mf.n),
         arch.propagation, arch.input, arch.dissipation, arch.peak_shift, arch.direction,
         solver_code(S.solver),
@@ -241,5 +241,61 @@ function b200_counters(ctx::B200Context)
 end
 
 b200_destroy!(ctx::B200Context) = (ccall((:picles_destroy, LIB), Cint, (Ptr{Cvoid},), ctx.handle); ctx.handle = C_NULL; nothing)
+
+# ---- the one-dimensional model (WaveGrowth1D): picles1d_* ---------------------------------------------------
+# init_particles!(model::Abstract1DModel) (run.jl:268-302) and State .= 0 ; time_step!(model::Abstract1DModel, Δt)
+# (TimeSteppers.jl:51-92).  The parameter struct is the 2-D one (flatten_params).
+mutable struct B200Context1D
+    handle::Ptr{Cvoid}
+    Nx::Int
+    x::Vector{Float64}      # OneDGridNotes.x: where the wind closure is evaluated
+end
+
+function check1d(h::Ptr{Cvoid}, rc::Integer)
+    rc == 0 && return nothing
+    error("picles_b200 (1-D) error $rc: " * unsafe_string(ccall((:picles1d_last_error, LIB), Cstring, (Ptr{Cvoid},), h)))
+end
+
+function b200_init_particles_1d!(model, arch::B200)
+    model.ODEdefaults === nothing || error("the B200 1-D path seeds from the wind sea (ODEinit_type = \"wind_sea\")")
+    href = Ref{Ptr{Cvoid}}(C_NULL)
+    check1d(C_NULL, ccall((:picles1d_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint), href, arch.device))
+    h = href[]
+    g = model.grid
+    x = collect(LinRange(0, g.dimx, g.Nx))                      # OneDGridNotes(grid).x, ParticleMesh.jl:131
+    check1d(h, ccall((:picles1d_set_grid, LIB), Cint, (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Ptr{Cdouble}), h, g.Nx, g.xmin, g.dx, x))
+    P = flatten_params(model, arch)                             # same struct; periodic_boundary = the model kwarg
+    check1d(h, ccall((:picles1d_set_params, LIB), Cint, (Ptr{Cvoid}, Ref{PiclesParams}), h, P))
+    u0 = Float64[model.winds(xi, 0.0) for xi in x]
+    check1d(h, ccall((:picles1d_seed, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), h, u0))
+    ctx = B200Context1D(h, g.Nx, x)
+    b200_fetch_state_1d!(model, ctx)
+    return ctx
+end
+
+function b200_time_step_1d!(model, ctx::B200Context1D, Δt::Float64)
+    t = model.clock.time
+    u_t = Float64[model.winds(xi, t) for xi in ctx.x]
+    u_t1 = Float64[model.winds(xi, t + Δt) for xi in ctx.x]
+    check1d(ctx.handle, ccall((:picles1d_step, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}),
+        ctx.handle, t, Δt, u_t, u_t1))
+    b200_fetch_state_1d!(model, ctx)
+    return nothing                                              # tick!(model.clock, Δt) stays with the caller
+end
+
+function b200_fetch_state_1d!(model, ctx::B200Context1D)
+    S = Matrix{Float64}(undef, ctx.Nx, 3)                       # (Nx, 3) column-major, as model.State
+    check1d(ctx.handle, ccall((:picles1d_get_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), ctx.handle, S))
+    model.State[:, :] .= S
+    return nothing
+end
+
+function b200_counters(ctx::B200Context1D)
+    c = Ref{PiclesCounters}()
+    check1d(ctx.handle, ccall((:picles1d_get_counters, LIB), Cint, (Ptr{Cvoid}, Ref{PiclesCounters}), ctx.handle, c))
+    return c[]
+end
+
+b200_destroy!(ctx::B200Context1D) = (ccall((:picles1d_destroy, LIB), Cint, (Ptr{Cvoid},), ctx.handle); ctx.handle = C_NULL; nothing)
 
 end # module

@@ -86,7 +86,7 @@ def test_julia_glue_ccalls_match_the_header():
     the header declares, with pointer/scalar kinds in the right places; the Julia mirrors of the two
     structs list the header's fields in order."""
     src = open(os.path.join(ROOT, "julia", "PiCLES_B200.jl"), encoding="utf-8").read()
-    calls = re.findall(r"ccall\(\(:(picles_\w+), LIB\),\s*(\w+),\s*\(([^)]*)\)", src, flags=re.S)
+    calls = re.findall(r"ccall\(\(:(picles(?:1d)?_\w+), LIB\),\s*(\w+),\s*\(([^)]*)\)", src, flags=re.S)
     assert len(calls) >= 12
     seen = set()
     for name, ret, argt in calls:
@@ -107,7 +107,8 @@ def test_julia_glue_ccalls_match_the_header():
         seen.add(name)
     for must in ("picles_create", "picles_set_grid", "picles_set_grid_metric", "picles_set_params", "picles_seed",
                  "picles_step", "picles_step_strip", "picles_get_state", "picles_get_counters", "picles_comm_init",
-                 "picles_set_wind_midlevels", "picles_set_wind_mesh", "picles_step_wind_mesh"):
+                 "picles_set_wind_midlevels", "picles_set_wind_mesh", "picles_step_wind_mesh",
+                 "picles1d_create", "picles1d_set_grid", "picles1d_set_params", "picles1d_seed", "picles1d_step", "picles1d_get_state"):
         assert must in seen, must
     # struct mirrors: same field names in the same order as the ctypes mirrors (checked against the header above)
     for jl_name, ct in (("PiclesParams", _abi.PiclesParams), ("PiclesCounters", _abi.PiclesCounters)):
