@@ -246,3 +246,31 @@ def test_golden_fixture_1d(name):
     assert np.array_equal(p["flags"], G[name + "/flags"]) and bits_equal(p["t"], G[name + "/t"])
     keys = ("n_integrated", "n_substeps", "n_rejects", "n_rhs", "n_remesh_A", "n_remesh_B", "n_remesh_D", "n_deposited")
     assert [c[k] for k in keys] == list(G[name + "/counters"])
+
+
+def test_integrator_1d_converges_to_an_independent_solver():
+    """One DT of the 1-D system under a steady wind, integrated by scipy's DOP853 (rtol 1e-12) on the oracle's right-hand
+    side: the oracle's Tsit5 at the reference's tolerances stays within 5e-3 of it and converges as they tighten.
+    Uniform periodic chain: every particle is the same, and node 1 keeps the floor-corner share of particle 1 (the
+    first charge to arrive there), so State[1, 1] = w_floor * exp(lne(DT))."""
+    from scipy.integrate import solve_ivp
+    g, P, wind, DT, _ = SCENARIOS_1D["steady_periodic"]()
+    U = 10.0
+
+    def first_node_energy(P):
+        o = make_oracle_1d(g, P)
+        o.seed(np.full(g["Nx"], U))
+        z0 = o.particles()["z"][:, 0].copy()
+        o.step(0.0, DT, np.full(g["Nx"], U), np.full(g["Nx"], U))
+        return z0, o.state()[0, 0]
+
+    z0, e_ref_tol = first_node_energy(P)
+    sol = solve_ivp(lambda t, z: oned.rhs(P, z, U), (0.0, DT), z0, method="DOP853", rtol=1e-12, atol=1e-14)
+    lne, _, x = sol.y[:, -1]
+    xn = (x - g["xmin"]) / g["dx"]
+    expect = (1.0 - (xn - math.floor(xn))) * math.exp(lne)
+    assert abs(e_ref_tol - expect) < 5e-3 * expect
+    P2 = params_1d(600.0, periodic=True)
+    P2.abstol, P2.reltol = 1e-11, 1e-10
+    _, e_tight = first_node_energy(P2)
+    assert abs(e_tight - expect) < 1e-7 * expect
