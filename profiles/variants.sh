@@ -11,16 +11,8 @@ set -e
 cd "$(dirname "$0")/.."
 declare -A V=(
   [base]=""
-  [stage_switch]="-DPH_STAGE_SWITCH"        # one straight-line stage sum per stage behind a switch (Tsit5 instantiation)
-  [share_rcp]="-DPH_SHARE_RCP"              # omega_p and alpha share the Newton reciprocal of 2*c_gp
-  [reg_sums]="-DPH_REG_SUMS"                # running sums of the propagation components in registers instead of scratch slots
-  [hoist_sdir]="-DPH_HOIST_SDIR"            # wind-only factors of S_dir hoisted in the steady copy
-  [dp5_ct]="-DPH_DP5_CT"                    # DP5 (bench06 settings) with a compile-time tableau: time with PROF=prof_step_dp5.py
-  [wind_row4]="-DPH_WIND_ROW4"              # wind sampler: four nodes per thread, y lookup shared along a row; time with profiles/prof_wind.py
-  [all4]="-DPH_STAGE_SWITCH -DPH_SHARE_RCP -DPH_REG_SUMS -DPH_HOIST_SDIR"
-  [no_std]="-DPH_NO_STD_TERMS"              # the switch-carrying right-hand side only (what the specialisation buys)
-  [no_steady_split]="-DPH_NO_STEADY_SPLIT"  # no separate copy for steady winds
-  [autosw_unrolled]="-DPH_AUTOSW_UNROLLED"  # AutoTsit5 instantiation with unrolled stage sums
+  [check_all]="-DPH_CHECK_ALL"              # every division of the right-hand side with its validity test (what the unchecked ones buy)
+  [vote_per_rhs]="-DPH_VOTE_PER_RHS"        # the steady-wind warp vote at the head of every right-hand side instead of once per particle
 )
 case "$1" in
 build)
@@ -35,7 +27,7 @@ PY
   done ;;
 time)
   shift
-  names=("$@"); [ ${#names[@]} -eq 0 ] && names=(base stage_switch share_rcp reg_sums hoist_sdir all4 base)
+  names=("$@"); [ ${#names[@]} -eq 0 ] && names=(base check_all vote_per_rhs base)
   mkdir -p gpurun_out
   for n in "${names[@]}"; do
     PICLES_B200_LIB=$PWD/_exp/lib_$n.so python profiles/${PROF:-prof_step.py} 4096 12 > gpurun_out/variant_$n.log 2>&1
