@@ -799,10 +799,11 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
     const Tableau& T = nz ? tableau(PICLES_SOLVER_TSIT5) : (dz ? tableau(PICLES_SOLVER_DP5) : tableau(P.solver));
 #define PH_COEF_ON(c, can_be_zero) (nz || (dz && !(can_be_zero)) || (c) != 0.0)
     /* prop() in the attempt loop: the Tsit5 / DP5 instantiations are launched with propagation on only
-       (launch_advance; the host build selects them the same way), so they carry no test per stage */
+       (launch_advance; the host build selects them the same way), so they carry no test per stage; the
+       monitor-carrying kernels have a second instantiation for it, TSIT5 == 3 */
 #define PH_PROP(cx_, cy_, ox_, oy_)                                                              \
     do {                                                                                         \
-        if (!AUTOSW && TSIT5 != 0) { ox_ = M[0] * (cx_) + M[1] * (cy_); oy_ = M[2] * (cx_) + M[3] * (cy_); } \
+        if ((!AUTOSW && TSIT5 != 0) || (AUTOSW && TSIT5 == 3)) { ox_ = M[0] * (cx_) + M[1] * (cy_); oy_ = M[2] * (cx_) + M[3] * (cy_); } \
         else prop(P, M, (cx_), (cy_), ox_, oy_);                                                 \
     } while (0)
     double t = p.t;

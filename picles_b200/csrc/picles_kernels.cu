@@ -870,11 +870,14 @@ void launch_advance2(const DeviceArrays& A, const picles_params_t& P, double DT,
     /* AutoTsit5 runs the instantiation that carries the stiffness monitor and the Rosenbrock23 branch */
     if (P.solver == PICLES_SOLVER_AUTOTSIT5) {
         const int gr = grid_for(count, ADV_THREADS, sms, 1);
+        /* (third template argument 3: propagation on, known at compile time, as in the Tsit5 / DP5 instantiations) */
         if (pn) {
-            k_advance<true, true><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
+            if (P.propagation) k_advance<true, true, 3><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
+            else k_advance<true, true><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
             k_advance_resume<true><<<gr, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end);
         } else {
-            k_advance<false, true><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
+            if (P.propagation) k_advance<false, true, 3><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
+            else k_advance<false, true><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
             k_advance_resume<false><<<gr, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end);
         }
         COUNT_LAUNCH(2);

@@ -181,6 +181,9 @@ static void shim_advance_all(Shim* h, double DT, const double* u_t, const double
                 : (ph_host_specialised && h->P.solver == PICLES_SOLVER_DP5 && !h->perM && h->P.propagation)
                 ? advance_particle<false, 2>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], wu1,
                                              wv1, h->n_mid, um, vm, M, pc, r, c, K, attempts)
+                : (ph_host_specialised && h->P.solver == PICLES_SOLVER_AUTOTSIT5 && h->P.propagation)
+                ? advance_particle<true, 3>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], wu1,
+                                            wv1, h->n_mid, um, vm, M, pc, r, c, K, attempts)
                 : advance_particle<true>(h->P, p, s.mask[l], DT, u_t[off + l], v_t[off + l], wu1,
                                          wv1, h->n_mid, um, vm, M, pc, r, c, K, attempts);
 
