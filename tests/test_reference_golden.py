@@ -115,3 +115,74 @@ def test_gpu_against_the_julia_reference(gpu_lib):
     errs = rel_errors(gold, res, active)
     print("CUDA path vs Julia reference, largest relative errors:", errs)
     assert errs["lne"] <= REL_TOL and errs["cg_bar"] <= REL_TOL, errs
+
+
+# ---- the one-dimensional model (julia/generate_golden_1d.jl) ---------------------------------------------------
+CASE_1D = os.path.join(HERE, "golden", "julia", "oned_steady")
+
+
+def load_julia_golden_1d(d):
+    with open(os.path.join(d, "manifest.json")) as f:
+        man = json.load(f)
+    Nx, n = man["Nx"], man["nsteps"] + 1
+    rd = lambda name, dt, shape: np.fromfile(os.path.join(d, name), dtype=dt).reshape(shape)
+    return dict(manifest=man, state=rd("state.f64", "<f8", (n, 3, Nx)), u=rd("particles_u.f64", "<f8", (n, 3, Nx)),
+                t=rd("particles_t.f64", "<f8", (n, Nx)), on=rd("particles_on.u8", "u1", (n, Nx)))
+
+
+def run_oned_steady(make_model):
+    """scenario steady_nonperiodic = the configuration julia/generate_golden_1d.jl runs (8 steps)"""
+    from scenarios_1d import SCENARIOS_1D
+    g, P, wind, DT, steps = SCENARIOS_1D["steady_nonperiodic"]()
+    m = make_model(g, P)
+    x = g["x"]
+    m.seed(wind(x, 0.0))
+    S, U, T, ON = [m.state()], [], [], []
+
+    def grab():
+        p = m.particles()
+        U.append(p["z"]); T.append(p["t"]); ON.append(p["flags"] & 1)
+    grab()
+    t = 0.0
+    for _ in range(steps):
+        m.step(t, DT, wind(x, t), wind(x, t + DT))
+        t += DT
+        S.append(m.state())
+        grab()
+    return dict(state=np.stack(S), u=np.stack(U), t=np.stack(T), on=np.stack(ON))
+
+
+def _oracle_1d(g, P):
+    from oracle import oned
+    return oned.Oracle1D(g["Nx"], g["xmin"], g["dx"], g["x"], P)
+
+
+def test_loader_reads_the_1d_generator_layout(tmp_path):
+    res = run_oned_steady(_oracle_1d)
+    d = tmp_path / "oned_steady"
+    d.mkdir()
+    res["state"].astype("<f8").tofile(d / "state.f64")
+    res["u"].astype("<f8").tofile(d / "particles_u.f64")
+    res["t"].astype("<f8").tofile(d / "particles_t.f64")
+    res["on"].astype("u1").tofile(d / "particles_on.u8")
+    (d / "manifest.json").write_text(json.dumps({"Nx": 51, "nsteps": 8, "DT": 600.0, "on_flag_persists": True}))
+    gold = load_julia_golden_1d(str(d))
+    assert gold["state"].shape == (9, 3, 51) and np.array_equal(gold["state"], res["state"])
+    assert np.array_equal(gold["u"], res["u"]) and np.array_equal(gold["on"], res["on"])
+
+
+@pytest.mark.skipif(not os.path.isdir(CASE_1D), reason="no reference-held 1-D vectors: run julia/generate_golden_1d.jl on a machine with Julia")
+def test_oracle_1d_against_the_julia_reference():
+    gold = load_julia_golden_1d(CASE_1D)
+    man = gold["manifest"]
+    assert (man["Nx"], man["nsteps"]) == (51, 8), man
+    if not man.get("on_flag_persists", True):
+        pytest.fail("`on` does not persist in the reference's 1-D ParticleCollection: DESIGN.md §4.6 reads the other way")
+    res = run_oned_steady(_oracle_1d)
+    interior = slice(1, 50)
+    assert np.array_equal(gold["on"][:, interior], res["on"][:, interior]), "on flags differ from the reference"
+    e_ref, e_got = gold["state"][:, 0, interior], res["state"][:, 0, interior]
+    rel = np.abs(e_got - e_ref) / np.maximum(np.abs(e_ref), 1e-300)
+    lne = np.abs(res["u"][:, 0, interior] - gold["u"][:, 0, interior]) / np.maximum(np.abs(gold["u"][:, 0, interior]), 1e-300)
+    print("1-D oracle vs Julia reference: largest relative error State e", float(rel.max()), "lne", float(lne.max()))
+    assert lne.max() <= REL_TOL and rel.max() <= 1e-5
