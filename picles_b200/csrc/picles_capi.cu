@@ -1328,11 +1328,10 @@ int picles_halo_exchange(picles_t* h, int lo_rank, int hi_rank) {
    reach (PH_REACH_MAX_ABI rows) of a strip edge can land on a neighbour, so picles_step_strip advances exactly those
    rows in its boundary launch and all-reduces THEIR reach (boundary_zones) while the interior still integrates: no
    strip waits for another strip's interior.  The serial path all-reduces the whole strip's reach behind its advance. */
-__global__ void k_reach_word(const int32_t* src, int32_t* dst) { *dst = *src + 1; }
 static int reach_allreduce(picles_t* h, cudaStream_t st, bool boundary_zones) {
     if (!h->comm || h->comm_size < 2 || !h->reach_send) return PICLES_OK;
     /* 1 + reach: the gather reads 0 as "nobody all-reduced" */
-    k_reach_word<<<1, 1, 0, st>>>(boundary_zones ? &h->d_counters->reach_bnd : &h->d_counters->reach, h->reach_send);
+    launch_reach_word(boundary_zones ? &h->d_counters->reach_bnd : &h->d_counters->reach, h->reach_send, st);
     CK(cudaGetLastError());
     NCK(g_nccl.all_reduce(h->reach_send, &h->d_counters->reach_all, 1, 2 /* ncclInt32 */, 2 /* ncclMax */, h->comm, st));
     return PICLES_OK;

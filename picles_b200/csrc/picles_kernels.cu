@@ -933,6 +933,12 @@ void launch_energy(const double* e, int64_t n, double* partial, int nblocks, cud
     COUNT_LAUNCH(1);
 }
 
+__global__ void k_reach_word(const int32_t* src, int32_t* dst) { *dst = *src + 1; }
+void launch_reach_word(const int32_t* src, int32_t* dst, cudaStream_t st) {
+    k_reach_word<<<1, 1, 0, st>>>(src, dst);
+    COUNT_LAUNCH(1);
+}
+
 void launch_halo_pack(const DeviceArrays& A, char* lo, char* hi, int sms, cudaStream_t st) {
     int64_t m = (int64_t)A.hx * A.rp;
     if (m > 0) { k_halo_pack<<<grid_for(m, 256, sms, 4), 256, 0, st>>>(A, lo, hi); COUNT_LAUNCH(1); }
