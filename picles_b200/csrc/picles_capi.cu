@@ -25,7 +25,6 @@ using namespace picles;
 #define PIPE_MIN_NODES (1 << 20)
 static_assert(PIPE_CHUNKS + 2 <= ADV_SLOTS, "one work queue per advance launch of a step");
 static_assert(PIPE_CHUNKS == ADV_SLOT_BOUNDARY, "the boundary launch takes the queue behind the interior's chunks");
-#define ADV_RESERVE_SMS 4 /* SMs the interior advance of a strip leaves to the exchange (2.7 % of a B200) */
 #define PIPE_EVENTS (PIPE_CHUNKS + 6) /* chunk landed x8, boundary blocks x2, boundary advanced, halo exchanged, interior advanced, compute stream idle */
 
 struct picles_handle {
@@ -226,12 +225,7 @@ static int create_resources(picles_t* h) {
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->snap_stream, cudaStreamNonBlocking));
-    {
-        /* the exchange runs beside the interior advance: its kernels go first whenever a slot opens */
-        int prio_lo = 0, prio_hi = 0;
-        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        CK(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, prio_hi));
-    }
+    CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
     for (int k = 0; k < PIPE_EVENTS; k++) CK(cudaEventCreateWithFlags(&h->pev[k], cudaEventDisableTiming));
     for (int k = 0; k < 5; k++) CK(cudaEventCreate(&h->ev[k]));
     for (int k = 0; k < 2; k++) CK(cudaEventCreate(&h->tev[k]));
@@ -333,7 +327,6 @@ static int set_grid_impl(picles_t* h, int Nx, int Ny, int bx, int by, int j0, in
     free_grid(h);
     DeviceArrays& A = h->A;
     A.Nx = Nx; A.Ny = Ny; A.bx = bx; A.by = by; A.j0 = j0; A.ny = ny_local; A.halo = halo; A.hx = halo_x;
-    A.adv_reserve = 0;
     A.rp = (Nx + REC_PITCH_ALIGN - 1) / REC_PITCH_ALIGN * REC_PITCH_ALIGN;
     int64_t n = (int64_t)Nx * ny_local;
     int64_t ne = (int64_t)A.rp * (ny_local + 2 * halo);
@@ -1392,12 +1385,7 @@ int picles_step_strip(picles_t* h, double t, double dt_model, const double* u_t,
         }
         /* the interior is enqueued before the exchange: the host side of the NCCL group (tens of microseconds) must not
            sit between the two advance launches */
-        /* ... and it leaves ADV_RESERVE_SMS SMs empty: the interior launch is persistent (its blocks stay until the work queue
-           is empty), so without them pack, the NCCL kernels and unpack would find no room before the interior is done —
-           measured: every strip's gather then started behind the SLOWEST strip's advance plus the exchange latency */
-        h->A.adv_reserve = ADV_RESERVE_SMS;
         rc = advance_range(h, dt_model, u_t, v_t, u_t1, v_t1, hb, A.ny - hb);
-        h->A.adv_reserve = 0;
         if (rc) return rc;
         rc = exchange_on(h, lo_rank, hi_rank, h->comm_stream);     /* boundary records written: pack, send/recv, unpack */
         if (rc) return rc;

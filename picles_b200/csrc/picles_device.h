@@ -56,9 +56,6 @@ struct DeviceArrays {
     int j0, ny, halo; /* strip: first global row (0-based), rows owned, halo rows the record planes hold on each side */
     int hx;           /* halo rows exchanged with the y-neighbours this step (<= halo; widened when the reach asks for it) */
     int rp;           /* row pitch (elements) of the record planes rec[] / cell */
-    int adv_reserve;  /* strips: SMs the advance kernel leaves empty (its blocks that land on SM ids below this exit at once) so
-                         that the exchange's kernels — pack, NCCL send/recv and all-reduce, unpack — find room while the persistent
-                         interior launch holds every other SM until its work queue is empty; 0: use every SM */
     double* z[5];     /* lne, c̄_x, c̄_y, x, y */
     double *t, *dt, *qold;
     int32_t* iter;

@@ -168,13 +168,6 @@ k_advance(DeviceArrays A, picles_params_t P, double DT, DeviceCounters* dc, int6
        (consecutive threads -> consecutive 8-byte words: conflict-free) */
     __shared__ double s_k[KS_SLOTS * ADV_THREADS];
     __shared__ int32_t s_hist[ADV_HIST_BINS];
-    if (A.adv_reserve > 0) {
-        /* strips: keep a few SMs free for the exchange.  Work is pulled from a queue, so a block that leaves loses
-           nothing: the blocks on the other SMs take its share.  (Uniform over the block: %smid is per SM.) */
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        if (smid < (unsigned)A.adv_reserve) return;
-    }
     KStrided K;
     K.base = &s_k[threadIdx.x];
     K.stride = ADV_THREADS;
