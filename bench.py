@@ -397,7 +397,9 @@ def strong_c5_leg(dist, rank, world, local_rank, steps, warmup, halo=6):
     partition" — ONE 4320x3840 tripolar + land grid cut in `world` y-strips (strong scaling), time-varying winds
     resident before each timed step, halo exchange over NCCL inside the library.  Land and the small cells near
     the pole make rows unequal, so the strips are cut by MEASURED cost: a calibration run on equal strips (per-strip
-    kernel times, per-row reach) first, then one refinement with the step times measured on the re-cut strips.  Rank 0 then times the same grid as one domain on its GPU, same steps."""
+    kernel times, per-row reach) first.  (A second pass that re-cut by the step times measured on the
+    re-cut strips bought nothing — 80.9 % on 8 GPUs either way, 96.5 -> 95.5 % on 2: a strip's step time is mostly the slowest
+    strip's advance, DESIGN.md §5 — and was dropped.)  Rank 0 then times the same grid as one domain on its GPU, same steps."""
     import torch
     from picles_b200.distributed import StripStepper, row_cost_measured, strip_bounds, strip_bounds_weighted
     from picles_b200.engine import B200Engine
@@ -445,15 +447,6 @@ def strong_c5_leg(dist, rank, world, local_rank, steps, warmup, halo=6):
     reach_rows = np.concatenate([np.asarray(c["row_reach"]) for c in allc])
     cost = row_cost_measured(active_rows, Nx, reach_rows, eq, [c["adv"] for c in allc], [c["prj"] for c in allc])
     bounds = strip_bounds_weighted(cost, world, min_rows=max(halo, 1))
-    # one refinement: what a strip really takes per step on the re-cut strips (kernels, exchange, fold rows, fixed
-    # costs) replaces the sum of its rows' modelled costs; each row keeps its share inside its strip
-    ref = run(bounds, warmup, 3)
-    allr = [None] * world
-    dist.all_gather_object(allr, ref)
-    cost2 = np.array(cost, np.float64)
-    for (j0, j1), r in zip(bounds, allr):
-        cost2[j0:j1] *= (r["ms"] / 3.0) / max(cost2[j0:j1].sum(), 1e-300)
-    bounds = strip_bounds_weighted(cost2, world, min_rows=max(halo, 1))
     mine = run(bounds, warmup, steps)
     parts = [None] * world if rank == 0 else None
     dist.gather_object(mine, parts, dst=0)
