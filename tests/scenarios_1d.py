@@ -93,3 +93,36 @@ def compare_models_1d(a, b, step):
         for k in ("n_integrated", "n_substeps", "n_rejects", "n_rhs", "n_reseed_advance", "n_fixups", "n_failed", "n_deposited",
                   "n_remesh_A", "n_remesh_B", "n_remesh_D", "max_attempts"):
             assert ca[k] == cb[k], f"counter {k}: {ca[k]} != {cb[k]} after step {step}"
+
+
+def _nan_at(i, U):
+    def u(x, t):
+        a = np.full(np.shape(x), float(U)) if np.ndim(x) else float(U)
+        if np.ndim(x):
+            a[i] = np.nan
+        return a
+    return u
+
+
+# edge cases, checked on the CPU only (host build of the device header against the oracle): not part of the GPU
+# parametrisation, whose scenarios were all run on a B200 before they were committed
+EDGE_1D = {
+    # five nodes, particles crossing several cells: the gather's window covers the whole chain (full scan) and wraps
+    "tiny_periodic_fast": lambda: (grid_1d(0.0, 2e3, 5), params_1d(1200.0, periodic=True), _steady(14.0), 1200.0, 4),
+    "two_nodes": lambda: (grid_1d(0.0, 50e3, 2), params_1d(600.0, periodic=True), _steady(11.0), 600.0, 4),
+    # no wind to speak of: every particle seeded off, nothing ever integrates, remesh keeps them off
+    "calm": lambda: (grid_1d(0.0, 300e3, 31), params_1d(600.0), _steady(0.5), 600.0, 3),
+    "zero_wind": lambda: (grid_1d(0.0, 300e3, 11), params_1d(600.0, periodic=True), _steady(0.0), 600.0, 2),
+    # a NaN in the wind field at one node: its particle is seeded off with a NaN state and stays off; its neighbours
+    # read a NaN wind when they come near it
+    "nan_wind_node": lambda: (grid_1d(0.0, 300e3, 21), params_1d(600.0), _nan_at(10, 13.0), 600.0, 4),
+    # maxiters: the integrators stop, as status codes
+    "maxiters": lambda: (grid_1d(0.0, 300e3, 15), _with(params_1d(600.0), maxiters=12), _steady(15.0), 600.0, 3),
+    "dtmin_no_force": lambda: (grid_1d(0.0, 300e3, 15), params_1d(600.0, dt=1e-3, dtmin=5.0, force_dtmin=False), _steady(15.0), 600.0, 3),
+}
+
+
+def _with(P, **kw):
+    for k, v in kw.items():
+        setattr(P, k, v)
+    return P

@@ -274,3 +274,22 @@ def test_integrator_1d_converges_to_an_independent_solver():
     P2.abstol, P2.reltol = 1e-11, 1e-10
     _, e_tight = first_node_energy(P2)
     assert abs(e_tight - expect) < 1e-7 * expect
+
+
+from scenarios_1d import EDGE_1D  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(EDGE_1D))
+def test_device_header_edge_cases_match_the_oracle(name):
+    g, P, wind, DT, steps = EDGE_1D[name]()
+    a, b = make_oracle_1d(g, P), Shim1D(g, P)
+    run_pair_1d(a, b, g, wind, DT, steps, compare_models_1d)
+    c = a.counters()
+    if name == "calm":
+        assert c["n_integrated"] == 0 and c["n_remesh_D"] == g["Nx"]
+    if name == "maxiters":
+        assert c["n_failed"] > 0 or (a.particles()["status"] & 1).any()
+    if name == "dtmin_no_force":
+        assert (a.particles()["status"] & 2).any()
+    if name == "tiny_periodic_fast":
+        assert b.counters()["reach"] * 2 + 1 >= g["Nx"]
