@@ -42,6 +42,8 @@ class Shim1D:
             L.shim1_get_state.argtypes = [vp, vp]
             L.shim1_get_particles.argtypes = [vp, vp, vp, vp, vp, vp]
             L.shim1_get_counters.argtypes = [vp, C.POINTER(PiclesCounters)]
+            L.shim1_merge.argtypes = [vp, vp]
+            L.shim1_rhs.argtypes = [C.POINTER(PiclesParams), vp, d, vp]
             cls._lib = L
         return cls._lib
 
@@ -293,3 +295,28 @@ def test_device_header_edge_cases_match_the_oracle(name):
         assert (a.particles()["status"] & 2).any()
     if name == "tiny_periodic_fast":
         assert b.counters()["reach"] * 2 + 1 >= g["Nx"]
+
+
+def test_device_header_merge_and_rhs_known_answers():
+    """the device header's merge rule and right-hand side by themselves against the oracle's, on the branch boundaries the
+    scenarios never hit exactly (cos theta == 0.5, dE == 0, an empty charge) and on random states"""
+    L = Shim1D.lib()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    cases = [([0, 0, 0], [2e-3, 1e-4, 0]), ([1.0, 1.0, 0], [0.5, 0.5, 0]), ([1.0, 1.0, 0], [0.5, 0.4999999999999999, 0]),
+             ([1.0, 2.0, 0], [1.0, 0.1, 0]), ([1.0, 1.0, 0], [0.5, 0.0, 0]), ([1.0, -1.0, 0], [0.5, -0.7, 0]),
+             ([1.0, -1.0, 0], [2.0, 0.7, 0]), ([0.0, 0.0, 0.0], [0.0, 0.0, 0.0]), ([1e-3, 1e-4, 0], [np.nan, 1e-4, 0])]
+    for g0, c0 in cases:
+        g = np.array(g0, np.float64)
+        c = np.array(c0, np.float64)
+        L.shim1_merge(p(g), p(c))
+        ref = oned.merge(g0, c0)
+        assert np.array_equal(g, ref, equal_nan=True), (g0, c0, g, ref)
+    assert np.array_equal(oned.merge([1.0, 1.0, 0], [0.5, 0.5, 0]), [1.5, 1.5, 0])   # cos theta == 0.5 exactly: added
+    P = params_1d()
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        z = np.array([rng.uniform(-14, 2), rng.choice([-1, 1]) * np.exp(rng.uniform(-5, 3)), rng.uniform(0, 1e6)])
+        u = rng.uniform(-30, 30)
+        dz = np.empty(3)
+        L.shim1_rhs(C.byref(P), p(z), float(u), p(dz))
+        assert np.array_equal(dz.view(np.uint64), oned.rhs(P, z, u).view(np.uint64))
