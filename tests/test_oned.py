@@ -320,3 +320,23 @@ def test_device_header_merge_and_rhs_known_answers():
         dz = np.empty(3)
         L.shim1_rhs(C.byref(P), p(z), float(u), p(dz))
         assert np.array_equal(dz.view(np.uint64), oned.rhs(P, z, u).view(np.uint64))
+
+
+def test_1d_system_is_the_2d_system_on_the_x_axis():
+    """Two separately transcribed right-hand sides: with the wind and the group velocity both along +x the 2-D system
+    (particle_waves_v5.jl:479-556; alpha_p, S_dir, great-circle term) reduces to the 1-D one (:597-646; alpha) — the same
+    tendencies of lne and c̄_x up to rounding, and dx/dt = c̄_x against M = identity."""
+    import oracle
+    from common import default_params
+    P1, P2 = params_1d(), default_params()
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        lne, cx, u = rng.uniform(-12, 1), np.exp(rng.uniform(-3, 2.5)), rng.uniform(0.5, 25)
+        if u / (2 * cx / P1.r_g) > 499.0:
+            continue
+        d1 = oned.rhs(P1, [lne, cx, 0.0], u)
+        d2 = oracle.rhs(P2, [lne, cx, 0.0, 0.0, 0.0], u, 0.0, M=(1.0, 0.0, 0.0, 1.0), pc=0.0)
+        scale = max(abs(d2[0]), abs(d2[1]), 1e-300)
+        assert abs(d1[0] - d2[0]) <= 1e-12 * max(abs(d2[0]), 1e-2 * scale) + 1e-13 * scale
+        assert abs(d1[1] - d2[1]) <= 1e-12 * scale
+        assert d2[2] == 0.0 and d1[2] == d2[3] == cx and d2[4] == 0.0
