@@ -169,6 +169,18 @@ def sc_dtmin_no_force():
     return g, default_params(force_dtmin=False, dt=1e-3, dtmin=10.0), _const(10.0, 10.0), 600.0, 3
 
 
+def sc_dp5_blowup():
+    """DP5 at the reference's tolerances with wind speeds across the 14 m/s band where its second substep (~85 s,
+    proposed by the PI controller after the tiny first one) overflows in the stages: EEst = NaN, the rejected
+    step leaves dt = NaN and the integrator ends (DtNaN, coded UNSTABLE) — for the columns inside the band only;
+    the others integrate normally beside them (tests/test_independent_integrator.py has the single-particle
+    view and the wind scan)."""
+    g = cartesian_grid(24, 10)
+    v = np.broadcast_to(np.linspace(13.6, 14.4, 24), (10, 24)).copy()
+    u = np.zeros((10, 24))
+    return g, default_params(solver="DP5"), (lambda t: (u, v)), 600.0, 3
+
+
 def sc_nan_wind():
     """a patch of NaN wind: integration goes NaN, advance! reseeds from the (NaN) wind, the NaN
     charge poisons the four nodes it is deposited on and spreads by one cell per step."""
@@ -247,6 +259,7 @@ SCENARIOS = {
     "emax_clamp": sc_emax_clamp,
     "maxiters": sc_maxiters,
     "dtmin_no_force": sc_dtmin_no_force,
+    "dp5_blowup": sc_dp5_blowup,
     "nan_wind": sc_nan_wind,
     "nan_defaults": sc_nan_defaults,
     "inf_defaults": sc_inf_defaults,
