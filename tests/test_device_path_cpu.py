@@ -33,7 +33,7 @@ def test_specialised_copies_bit_exact(name):
 @pytest.mark.parametrize("name,nstrips,halo", [
     ("minimal", 2, 2), ("minimal", 3, 1), ("periodic_grid", 2, 5), ("periodic_grid", 4, 5),
     ("land_block", 3, 2), ("tripolar", 2, 8), ("tripolar", 3, 6), ("growing_winds", 2, 2),
-    ("periodic_model_flag", 2, 2),
+    ("periodic_model_flag", 2, 2), ("dp5_blowup", 2, 2),
 ])
 def test_strips_bit_exact(name, nstrips, halo):
     """N y-strips with a halo of particle records give the same bits as one strip."""

@@ -111,7 +111,7 @@ def test_gpu_matches_oracle_bit_exact(gpu_lib, name):
 @pytest.mark.parametrize("name,nstrips,halo", [("minimal", 2, 2), ("periodic_grid", 2, 5), ("tripolar", 3, 6),
                                                ("land_block", 4, 2), ("fast_box", 3, 5), ("periodic_x_only", 2, 3),
                                                ("growing_winds_persist", 2, 2), ("growing_winds", 3, 2),
-                                               ("pulse_winds", 2, 2)])
+                                               ("pulse_winds", 2, 2), ("dp5_blowup", 2, 2)])
 def test_gpu_strips_match_oracle(gpu_lib, name, nstrips, halo):
     g, P, wind, DT, n = SCENARIOS[name]()
     run_pair(make_oracle(g, P), StripSet(g, P, nstrips, halo), wind, DT, n, compare_models)
@@ -393,7 +393,7 @@ def test_gpu_output_fields_and_async_snapshots(gpu_lib):
         assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
 
 
-@pytest.mark.parametrize("name", ["growing_winds_persist", "tripolar", "maxiters", "pulse_winds"])
+@pytest.mark.parametrize("name", ["growing_winds_persist", "tripolar", "maxiters", "pulse_winds", "dp5_blowup"])
 def test_gpu_checkpoint_resume_is_bit_identical(gpu_lib, name):
     """run k steps, checkpoint, continue; a fresh handle restored from the blob continues with the
     same bits (particle controller memory, pending dt resets, retcodes and wind level included)."""
