@@ -61,6 +61,11 @@ def make_boundaries_py(ocean, bx, by):
     return total
 
 
+class TrialStepOverflow(Exception):
+    """a trial step overflowed and ended the integrator (DtNaN): the two models part by design there — the oracle keeps
+    the last accepted state, the reference's in-place integrator the NaN trial"""
+
+
 class Particle:
     def __init__(self, ij, xy, u, on, boundary, dt):
         self.ij, self.xy, self.u, self.on, self.boundary = ij, xy, list(u), on, boundary
@@ -182,7 +187,8 @@ class RefModel:
             f = lambda t, z: list(oracle.rhs(P, np.asarray(z, np.float64), *self.wind(p, t), M=Mk, pc=pc))
             r = integrate_python(f, p.u, p.t, DT, p.dt, p.qold, self.solver, P.abstol, P.reltol, P.dtmin,
                                  P.dtmax if P.dtmax > 0 else math.inf, bool(P.force_dtmin), dt_reset=p.dt_reset)
-            assert r["retcode"] == "Success"
+            if r["retcode"] != "Success":
+                raise TrialStepOverflow(p.ij)
             p.u, p.t, p.dt, p.qold, p.dt_reset = list(r["u"]), r["t"], r["dt"], r["qold"], False
             self.tally["integrated"] += 1
         else:
@@ -261,7 +267,10 @@ def run_both(g, P, winds, DT, nsteps, solver="Tsit5", seed_timescale=None, defau
 
     def compare(what):
         So = orc.state()
-        scale = np.maximum(np.abs(ref.S), 1e-300)
+        # momentum components are compared on the scale of the node's momentum vector (a component can cancel to nothing
+        # between particles that arrive from different directions)
+        mnorm = np.hypot(ref.S[1], ref.S[2])
+        scale = np.maximum(np.stack([np.abs(ref.S[0]), mnorm, mnorm]), 1e-300)
         bad = np.abs(So - ref.S) > rtol * scale + 1e-300
         assert not bad.any(), (what, "State", np.argwhere(bad)[:4], So[bad][:4], ref.S[bad][:4])
         po = orc.particles()
@@ -377,3 +386,84 @@ def test_fast_box_reinit_of_integrating_particles():
     g = _grid("cartesian", 10, 9, dx=500.0, dy=500.0)
     ref, orc = run_both(g, default_params(), lambda x, y, t: (14.0, 9.0), 600.0, 4)
     assert ref.seen["B"] > 0 and ref.seen["A"] > 0 and orc.counters()["reach"] >= 2
+
+
+# ---- randomized differential runs ------------------------------------------------------------------------------
+def fuzz_case(seed):
+    """one random configuration (grid size and spacing, boundary types, land, model flag, solver, thresholds, a wind
+    that varies in space and time and is calm somewhere some of the time) through both models"""
+    rng = np.random.default_rng(seed)
+    Nx, Ny = int(rng.integers(5, 10)), int(rng.integers(5, 9))
+    kind = "tripolar" if rng.random() < 0.2 else "cartesian"
+    ocean = (rng.random((Ny, Nx)) > 0.12).astype(np.uint8) if rng.random() < 0.5 else None
+    kw = {}
+    if kind == "cartesian":
+        d = float(rng.choice([500.0, 1000.0, 2000.0]))
+        kw = dict(dx=d, dy=d, bx=int(rng.choice([BND_NONPERIODIC, BND_PERIODIC])), by=int(rng.choice([BND_NONPERIODIC, BND_PERIODIC])))
+    g = _grid(kind, Nx, Ny, ocean=ocean, **kw)
+    DT = float(rng.choice([600.0, 900.0, 1200.0]))
+    solver = str(rng.choice(["Tsit5", "Tsit5", "DP5"]))
+    P = default_params(DT=DT, solver=solver, periodic_boundary=bool(rng.random() < 0.5) or kind == "tripolar",
+                       wind_min_squared=float(rng.choice([2.0, 4.0])),
+                       log_energy_maximum=float(rng.choice([math.log(17), math.log(3e-3)])))
+    x0, x1 = float(g["x"].min()), float(g["x"].max())
+    y0, y1 = float(g["y"].min()), float(g["y"].max())
+    a, b, c = rng.uniform(-9, 9, 3)
+    d_, e, f = rng.uniform(-9, 9, 3)
+    om = 2 * math.pi / float(rng.choice([3600.0, 7200.0, 1e9]))
+    calm_x = rng.uniform(0.0, 0.6)
+
+    def winds(x, y, t):
+        """smooth in time (a jump of the wind inside a step makes the result depend on the step boundaries at the
+        size of the jump: 1e-8 between two roundings of the same algorithm), piecewise in space: a weak-wind band whose
+        strength swells across the on/off thresholds"""
+        sx, sy = (x - x0) / max(x1 - x0, 1.0), (y - y0) / max(y1 - y0, 1.0)
+        swell = 1.0 + 0.9 * math.sin(om * t + 2.0 * sy)
+        if sx < calm_x:
+            return 1.1 * swell, -0.6 * swell
+        return (a + b * sx) * (1.0 + 0.3 * math.sin(om * t)) + c * sy, d_ + e * sy + f * math.cos(om * t)
+
+    return g, P, winds, DT, solver
+
+
+def rounding_sensitivity(g, P, winds, DT, nsteps):
+    """how far two builds of the SAME oracle source drift apart when only the last bits of exp/log/pow differ (pmath.h
+    against the system libm): the yardstick for what agreement between two correct implementations can mean on a given
+    configuration.  Weak winds over a decaying sea under the reference's loose tolerances (abstol 1e-4, reltol 1e-3)
+    amplify such differences by two to three orders of magnitude per model step."""
+    sample = lambda t: tuple(np.array([[winds(g["x"][j, i], g["y"][j, i], t)[k] for i in range(g["Nx"])]
+                                       for j in range(g["Ny"])]) for k in (0, 1))
+    a, b = make_oracle(g, P), make_oracle(g, P, variant="libm")
+    for o in (a, b):
+        o.set_wind_closure(winds, g["x"], g["y"])
+        o.seed(*sample(0.0))
+    t, worst = 0.0, 0.0
+    for _ in range(nsteps):
+        for o in (a, b):
+            o.step(t, DT, *sample(t), *sample(t + DT))
+        t += DT
+        Sa, Sb = a.state(), b.state()
+        mn = np.hypot(Sa[1], Sa[2])
+        scale = np.maximum(np.stack([np.abs(Sa[0]), mn, mn]), 1e-300)
+        with np.errstate(invalid="ignore"):
+            d = np.abs(Sa - Sb) / scale
+        worst = max(worst, float(np.nanmax(d)))
+        za, zb = a.particles()["z"], b.particles()["z"]
+        with np.errstate(invalid="ignore"):
+            dz = np.abs(za - zb) / np.maximum(np.abs(za), 1e-6)
+        worst = max(worst, float(np.nanmax(np.where(np.isfinite(dz), dz, 0.0))))
+    return worst
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_configurations(seed):
+    """the tolerance is what the configuration allows: 5e-9, or 50 x the drift between the pmath and libm builds of the
+    oracle itself when that is larger (seeds 4, 21, 31 of this generator reach 1e-7 ... 1e-6 in three steps).  A
+    misread rule shows at 1e-3 and above — see the mutations in DESIGN.md §2 — or in the branch counts, which must
+    agree exactly."""
+    g, P, winds, DT, solver = fuzz_case(seed)
+    sens = rounding_sensitivity(g, P, winds, DT, 3)
+    try:
+        run_both(g, P, winds, DT, 3, solver=solver, rtol=max(5e-9, 50.0 * sens))
+    except TrialStepOverflow:
+        pytest.skip("a trial step overflowed (DtNaN): the two models part by design there, see the quirk table")
