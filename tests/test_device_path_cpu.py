@@ -85,3 +85,34 @@ def test_bare_time_step_accumulates_onto_state(name):
     o3.seed(u0, v0)
     o3.step(0.0, DT, *wind(0.0), *wind(DT))
     assert not np.array_equal(o2.state(), o3.state())
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_configurations_bit_exact(seed):
+    """the randomized configurations of tests/test_independent_model.py (grid, boundaries, land, model flag, solver,
+    thresholds, winds varying in space and time, staged here as the two levels of each step) through the host build
+    of the device header: one strip, the specialised copies, and two strips with a halo as deep as the reach — bit for
+    bit against the oracle.  (150 seeds x the three modes were run once: no difference.)"""
+    from common import shim_lib
+    from test_independent_model import fuzz_case
+    g, P, winds, DT, _ = fuzz_case(seed)
+
+    def wind(t):
+        return tuple(np.array([[winds(g["x"][j, i], g["y"][j, i], t)[k] for i in range(g["Nx"])] for j in range(g["Ny"])])
+                     for k in (0, 1))
+
+    ref = make_oracle(g, P)
+    run_pair(ref, HostShim(g, P), wind, DT, 4, compare_models)
+    reach = 1
+    probe = make_oracle(g, P)
+    probe.seed(*wind(0.0))
+    for k in range(4):
+        probe.step(k * DT, DT, *wind(k * DT), *wind((k + 1) * DT))
+        reach = max(reach, probe.counters()["reach"])
+    run_pair(make_oracle(g, P), HostShim(g, P, nstrips=2, halo=reach), wind, DT, 4, compare_models)
+    lib = shim_lib()
+    lib.shim_set_specialised(1)
+    try:
+        run_pair(make_oracle(g, P), HostShim(g, P), wind, DT, 4, compare_models)
+    finally:
+        lib.shim_set_specialised(0)
