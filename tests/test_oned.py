@@ -11,7 +11,7 @@ import pytest
 
 from oracle import oned
 from picles_b200._abi import PiclesCounters, PiclesParams
-from scenarios_1d import SCENARIOS_1D, compare_models_1d, params_1d, run_pair_1d
+from scenarios_1d import SCENARIOS_1D, compare_models_1d, grid_1d, params_1d, run_pair_1d
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -340,3 +340,37 @@ def test_1d_system_is_the_2d_system_on_the_x_axis():
         assert abs(d1[0] - d2[0]) <= 1e-12 * max(abs(d2[0]), 1e-2 * scale) + 1e-13 * scale
         assert abs(d1[1] - d2[1]) <= 1e-12 * scale
         assert d2[2] == 0.0 and d1[2] == d2[3] == cx and d2[4] == 0.0
+
+
+def fuzz_case_1d(seed):
+    """a random 1-D configuration: chain length and spacing, grid offset, periodicity, solver, thresholds, source
+    terms on or off, a wind that varies along the chain and in time with a weak stretch swelling across the on/off
+    thresholds"""
+    rng = np.random.default_rng(seed)
+    Nx = int(rng.integers(5, 60))
+    L = float(rng.choice([20e3, 100e3, 600e3, 1500e3]))
+    xmin = float(rng.choice([0.0, 1e3]))
+    periodic = bool(rng.random() < 0.5)
+    DT = float(rng.choice([600.0, 1200.0, 1800.0]))
+    solver = str(rng.choice(["Tsit5", "Tsit5", "DP5"]))
+    kw = dict(input=False, dissipation=False, peak_shift=False) if rng.random() < 0.2 else {}
+    P = params_1d(DT, solver=solver, periodic=periodic, wind_min_squared=float(rng.choice([2.0, 4.0])),
+                  log_energy_maximum=float(rng.choice([math.log(17), -6.0])), **kw)
+    g = grid_1d(xmin, xmin + L, Nx)
+    a, b, c = rng.uniform(-15, 15), rng.uniform(-10, 10), rng.uniform(0, 6)
+    om = 2 * math.pi / float(rng.choice([3600.0, 14400.0, 1e9]))
+    calm = rng.uniform(0, 0.5)
+
+    def wind(x, t):
+        s = (np.asarray(x, float) - xmin) / L
+        w = np.where(s < calm, 1.2 * (1 + 0.9 * np.sin(om * t)), a + b * s + c * np.sin(om * t + 3 * s))
+        return w if np.ndim(x) else float(w)
+    return g, P, wind, DT
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_configurations_1d(seed):
+    """the two transcriptions of the 1-D model (oracle/picles_oracle_1d.c and physics1d.h on the host) on random
+    configurations, bit for bit after every step (300 seeds were run once: no difference)"""
+    g, P, wind, DT = fuzz_case_1d(seed)
+    run_pair_1d(make_oracle_1d(g, P), Shim1D(g, P), g, wind, DT, 5, compare_models_1d)
