@@ -116,3 +116,22 @@ def test_random_configurations_bit_exact(seed):
         run_pair(make_oracle(g, P), HostShim(g, P), wind, DT, 4, compare_models)
     finally:
         lib.shim_set_specialised(0)
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("mode", ["AutoTsit5", "on_persist", "AutoTsit5+on_persist"])
+def test_random_configurations_default_solver_and_persisting_flags(seed, mode):
+    """the same generator under the reference's default solver (45 of 120 seeds reach the Rosenbrock23 branch) and
+    with `on` following the remesh (on_persist = 1): bit for bit (120 seeds x 3 modes were run once)"""
+    from common import default_params
+    from test_independent_model import fuzz_case
+    g, P, winds, DT, solver = fuzz_case(seed)
+    P2 = default_params(DT=DT, solver="AutoTsit5" if "AutoTsit5" in mode else solver, periodic_boundary=bool(P.periodic_boundary),
+                        wind_min_squared=P.wind_min_squared, log_energy_maximum=P.log_energy_maximum,
+                        on_persist="on_persist" in mode)
+
+    def wind(t):
+        return tuple(np.array([[winds(g["x"][j, i], g["y"][j, i], t)[k] for i in range(g["Nx"])] for j in range(g["Ny"])])
+                     for k in (0, 1))
+
+    run_pair(make_oracle(g, P2), HostShim(g, P2), wind, DT, 5, compare_models)
