@@ -401,7 +401,8 @@ def strong_c5_leg(dist, rank, world, local_rank, steps, warmup, halo=6):
     re-cut strips bought nothing — 80.9 % on 8 GPUs either way, 96.5 -> 95.5 % on 2: a strip's step time is mostly the slowest
     strip's advance, DESIGN.md §5 — and was dropped.)  Rank 0 then times the same grid as one domain on its GPU, same steps."""
     import torch
-    from picles_b200.distributed import StripStepper, row_cost_measured, strip_bounds, strip_bounds_weighted
+    from picles_b200.distributed import (StripStepper, overlapped_step_estimate, row_cost_measured, strip_bounds,
+                                         strip_bounds_overlapped, strip_bounds_weighted)
     from picles_b200.engine import B200Engine
     g = c5_grid()
     Nx, Ny = g["Nx"], g["Ny"]
@@ -445,8 +446,12 @@ def strong_c5_leg(dist, rank, world, local_rank, steps, warmup, halo=6):
     dist.all_gather_object(allc, cal)
     active_rows = ((g["mask"] == 1) | (g["mask"] == 3)).sum(axis=1)
     reach_rows = np.concatenate([np.asarray(c["row_reach"]) for c in allc])
-    cost = row_cost_measured(active_rows, Nx, reach_rows, eq, [c["adv"] for c in allc], [c["prj"] for c in allc])
-    bounds = strip_bounds_weighted(cost, world, min_rows=max(halo, 1))
+    adv_cost, gat_cost = row_cost_measured(active_rows, Nx, reach_rows, eq, [c["adv"] for c in allc], [c["prj"] for c in allc],
+                                           split=True)
+    # the overlapped step of a strip costs the SLOWEST strip's advance plus its own gather (measured on 2 and 8 GPUs,
+    # DESIGN.md §5), so the cut evens out the advance rather than the summed cost, unless that piles gather on one strip
+    bounds, lam, est = strip_bounds_overlapped(adv_cost, gat_cost, world, min_rows=max(halo, 1))
+    est_sum = overlapped_step_estimate(adv_cost, gat_cost, strip_bounds_weighted(adv_cost + gat_cost, world, min_rows=max(halo, 1)))
     mine = run(bounds, warmup, steps)
     parts = [None] * world if rank == 0 else None
     dist.gather_object(mine, parts, dst=0)
@@ -460,6 +465,8 @@ def strong_c5_leg(dist, rank, world, local_rank, steps, warmup, halo=6):
     return {"scaling": "strong", "workload": f"tripolar + land {Nx}x{Ny} (synthetic; BASELINE configs[4]) cut in {world} y-strips by measured cost, "
                                              f"DT=1200 s, u=15, v=-10 cos(5t/(3600 2pi)), periodic_boundary model, halo {halo} rows",
             "value": v, "unit": UNIT, "n_gpus": world, "steps": steps, "ms_per_step": ms_max / steps,
+            "partition": {"objective": "max_r(advance) + max_r(gather) from the calibration run's per-row costs", "blend": lam,
+                          "estimate_ms": est, "estimate_ms_if_summed_cost_were_balanced": est_sum},
             "rows_per_rank": [p["rows"] for p in parts], "ms_per_step_per_rank": [p["ms"] / steps for p in parts],
             "ms_advance_per_rank": [p["adv"] for p in parts], "ms_project_remesh_per_rank": [p["prj"] for p in parts],
             "halo_rows_exchanged": max(p["halo_rows"] for p in parts), "failed": sum(p["failed"] for p in parts),

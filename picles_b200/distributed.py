@@ -67,17 +67,45 @@ def row_cost_model(mask, periodic_boundary: bool, reach_rows=None, gather_weight
     return active.sum(axis=1).astype(np.float64) + gather_weight * m.shape[1] * (2.0 * R + 1.0) ** 2 / 9.0
 
 
-def row_cost_measured(active_rows, nodes_per_row, reach_rows, bounds, ms_advance, ms_gather):
+def row_cost_measured(active_rows, nodes_per_row, reach_rows, bounds, ms_advance, ms_gather, split=False):
     """cost of every global row from a calibration run on the strips `bounds`: each strip's measured advance
     time spread over its rows by their active particles (captures regional differences in substeps), its measured
     gather + remesh time spread over its rows by the window area (2R+1)^2 of the rows' measured reach.
-    active_rows, reach_rows: one value per global row; ms_advance, ms_gather: one value per strip."""
+    active_rows, reach_rows: one value per global row; ms_advance, ms_gather: one value per strip.
+    split=True returns the two parts (advance, gather) instead of their sum."""
     a = np.asarray(active_rows, np.float64)
     w = nodes_per_row * (2.0 * np.maximum(np.asarray(reach_rows, np.float64), 1.0) + 1.0) ** 2
-    cost = np.zeros_like(a)
+    adv, gat = np.zeros_like(a), np.zeros_like(a)
     for (j0, j1), ta, tg in zip(bounds, ms_advance, ms_gather):
-        cost[j0:j1] = ta * a[j0:j1] / max(a[j0:j1].sum(), 1.0) + tg * w[j0:j1] / max(w[j0:j1].sum(), 1.0)
-    return cost
+        adv[j0:j1] = ta * a[j0:j1] / max(a[j0:j1].sum(), 1.0)
+        gat[j0:j1] = tg * w[j0:j1] / max(w[j0:j1].sum(), 1.0)
+    return (adv, gat) if split else adv + gat
+
+
+def overlapped_step_estimate(adv_cost, gather_cost, bounds):
+    """what picles_step_strip's overlapped step costs on the slowest strip, up to a constant: every strip gathers only
+    after the all-reduce of the reach, which completes when the SLOWEST strip's advance does (the exchange's kernels
+    find no free SM beside a persistent interior launch), so a strip's step is max_r(advance_r) + its own gather —
+    measured on 2 and on 8 GPUs with a residual of 0.11-0.14 ms that is the same on every strip
+    (profiles/r02_bench_n2.json, r02_bench_n8.json)."""
+    A = max(float(np.sum(adv_cost[j0:j1])) for j0, j1 in bounds)
+    G = max(float(np.sum(gather_cost[j0:j1])) for j0, j1 in bounds)
+    return A + G
+
+
+def strip_bounds_overlapped(adv_cost, gather_cost, world: int, min_rows: int = 1, blends=(0.0, 0.25, 0.5, 0.75, 1.0)):
+    """strips for the overlapped step: the prefix-sum split of advance + λ·gather, λ in `blends`, that minimises
+    overlapped_step_estimate — in practice the split that evens out the ADVANCE (λ = 0) unless that piles too much
+    gather on one strip; λ = 1 is strip_bounds_weighted on the summed cost.  Returns (bounds, λ, estimate)."""
+    adv = np.maximum(np.asarray(adv_cost, np.float64), 0.0)
+    gat = np.maximum(np.asarray(gather_cost, np.float64), 0.0)
+    best = None
+    for lam in blends:
+        b = strip_bounds_weighted(adv + lam * gat, world, min_rows)
+        est = overlapped_step_estimate(adv, gat, b)
+        if best is None or est < best[2] - 1e-12:
+            best = (b, float(lam), est)
+    return best
 
 
 def neighbours(rank: int, world: int, periodic_y: bool):

@@ -79,3 +79,41 @@ def test_weighted_strip_bounds():
     m = row_cost_measured(active, 10, [1, 1, 1, 1, 2, 3], [(0, 3), (3, 6)], ms_advance=[1.0, 3.0], ms_gather=[0.3, 0.9])
     assert m[:3].sum() == pytest.approx(1.3) and m[3:].sum() == pytest.approx(3.9)
     assert m[0] == m[1] == pytest.approx(0.1) and m[2] == pytest.approx(1.1) and m[5] > m[4] > m[3]
+
+
+def test_overlapped_step_partition():
+    """picles_step_strip's overlapped step costs max_r(advance_r) + the strip's own gather, so the cut
+    evens out the advance unless that piles gather on one strip.  Checked on the numbers of profiles/r02_bench_n8.json:
+    the estimate reproduces every strip's measured step up to one constant."""
+    import json
+    import numpy as np
+    from picles_b200.distributed import overlapped_step_estimate, row_cost_measured, strip_bounds_overlapped
+    rng = np.random.default_rng(0)
+    Ny, world = 400, 8
+    adv = 1.0 + 0.3 * np.sin(np.arange(Ny) / 40.0) + 0.05 * rng.random(Ny)
+    adv[120:160] = 0.1                                     # a land belt
+    gat = np.full(Ny, 0.08)
+    gat[-30:] = 0.6                                        # fold rows near the pole: an expensive gather
+    b, lam, est = strip_bounds_overlapped(adv, gat, world, min_rows=6)
+    assert b[0][0] == 0 and b[-1][1] == Ny and all(x[1] == y[0] for x, y in zip(b, b[1:])) and all(c - a >= 6 for a, c in b)
+    b_sum = strip_bounds_weighted(adv + gat, world, min_rows=6)
+    assert est == pytest.approx(overlapped_step_estimate(adv, gat, b))
+    assert est < overlapped_step_estimate(adv, gat, b_sum)            # better than evening out the summed cost ...
+    A = [adv[a:c].sum() for a, c in b]
+    assert lam == 0.0 and max(A) - min(A) <= 2 * adv.max()            # ... by evening out the advance
+    # a gather so heavy that evening out the advance alone is not the best cut any more
+    gat2 = gat.copy()
+    gat2[-30:] = 6.0
+    assert strip_bounds_overlapped(adv, gat2, world, min_rows=6)[1] > 0.0
+    assert strip_bounds_overlapped(adv, gat, 1)[0] == [(0, Ny)]
+    # split=True returns the two parts of row_cost_measured
+    act, reach = np.full(12, 10.0), np.ones(12)
+    a2, g2 = row_cost_measured(act, 10, reach, [(0, 6), (6, 12)], [3.0, 6.0], [0.6, 1.2], split=True)
+    assert np.allclose(a2 + g2, row_cost_measured(act, 10, reach, [(0, 6), (6, 12)], [3.0, 6.0], [0.6, 1.2]))
+    assert a2[:6].sum() == pytest.approx(3.0) and g2[6:].sum() == pytest.approx(1.2)
+    # the model behind it, on the measured 8-GPU and 2-GPU runs: step_r - (max advance + own gather) is one constant
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f, lo, hi in (("r02_bench_n8.json", 0.12, 0.14), ("r02_bench_n2.json", 0.10, 0.13)):
+        d = json.load(open(os.path.join(root, "profiles", f)))["strong_c5"]
+        res = np.array(d["ms_per_step_per_rank"]) - (max(d["ms_advance_per_rank"]) + np.array(d["ms_project_remesh_per_rank"]))
+        assert lo < res.min() and res.max() < hi and res.max() - res.min() < 0.01
