@@ -40,6 +40,8 @@ def windsea_particle(u, v, T):
 
 def minimal_particle(u, v, T):
     """FetchRelations.MinimalParticle: the wind only gives the direction (unit speed), FetchRelations.jl:381-399"""
+    u = 1.0 if u == 0 else u            # MinimalWindsea: `U10 == 0 ? rand_sign() : U10` per component; rand_sign() = +1 (B-9)
+    v = 1.0 if v == 0 else v
     a = math.hypot(u, v)
     return windsea_particle(u / a, v / a, T)
 
@@ -234,12 +236,17 @@ class RefModel:
             self.tally["D"] += 1                    # PI.on = false on a copy: nothing persists
 
     # ---- run!: State .= 0; time_step! ----
-    def step(self, DT):
-        self.S[:] = 0.0
+    def step(self, DT, zero_first=True, zero_after=False):
+        """zero_first: run!'s `State .= 0` before time_step! (run.jl:75-79); a bare time_step! adds to what State
+        holds; movie_time_step! (TimeSteppers.jl:212-247) adds too and zeroes State after the remesh"""
+        if zero_first:
+            self.S[:] = 0.0
         for ij in self.ocean_points:
             self.advance(self.particles[ij], DT)
         for ij in self.ocean_points:
             self.remesh(self.particles[ij], DT)
+        if zero_after:
+            self.S[:] = 0.0
         self.time += DT
 
 
