@@ -34,6 +34,10 @@ cases = [
     (name="dp5_bench06", solver=DP5(), U=10.0, V=10.0, dt=10.0, dtmin=1.0, nDT=3, timescale=1800.0),
     (name="dp5_blowup_u0_v14", solver=DP5(), U=0.0, V=14.0, dt=1e-3, dtmin=1e-4, nDT=2, timescale=600.0),
     (name="dp5_blowup_um7_v12", solver=DP5(), U=-7.0, V=12.0, dt=1e-3, dtmin=1e-4, nDT=2, timescale=600.0),
+    # the ODESettings default solver on the parameter set of tests/T04_2D_reg_test.jl:56-58 (C_φ = c_β = 4e-2): stiff,
+    # the AutoSwitch hands the particle to Rosenbrock23 within its first model step (C_phi overrides ODEParameters')
+    (name="auto_stiff_um10_vm10", solver=AutoTsit5(Rosenbrock23()), U=-10.0, V=-10.0, dt=1e-3, dtmin=1e-4, nDT=3, timescale=600.0, C_phi=4e-2),
+    (name="auto_nonstiff_u10_v10", solver=AutoTsit5(Rosenbrock23()), U=10.0, V=10.0, dt=1e-3, dtmin=1e-4, nDT=3, timescale=600.0),
 ]
 
 DT = 600.0
@@ -45,6 +49,9 @@ for c in cases
     u(x, y, t) = c.U
     v(x, y, t) = c.V
     ODEpars, Const_ID, Const_Scg = PW.ODEParameters(r_g=0.85)
+    if haskey(c, :C_phi)
+        ODEpars = merge(ODEpars, (C_φ=c.C_phi,))
+    end
     particle_system = PW.particle_equations(u, v, γ=Const_ID.γ, q=Const_ID.q)
     sets = PW.ODESettings(Parameters=ODEpars, log_energy_minimum=FetchRelations.MinimalWindsea(10.0, 10.0, DT)["lne"],
         saving_step=DT, timestep=DT, total_time=6 * 86400.0, solver=c.solver, dt=c.dt, dtmin=c.dtmin, force_dtmin=true)
@@ -58,7 +65,8 @@ for c in cases
     for k in 1:c.nDT
         step!(integ, DT, true)
         st = hasproperty(integ, :stats) ? integ.stats : integ.destats   # renamed in SciMLBase 1.7x
-        push!(steps, "{\"u\": $(jvec(integ.u[1:5])), \"t\": $(jnum(integ.t)), \"dt\": $(jnum(integ.dt)), \"qold\": $(jnum(integ.qold)), " *
+        current = hasproperty(integ.cache, :current) ? integ.cache.current : 1      # CompositeCache: 1 = Tsit5, 2 = Rosenbrock23
+        push!(steps, "{\"u\": $(jvec(integ.u[1:5])), \"t\": $(jnum(integ.t)), \"dt\": $(jnum(integ.dt)), \"qold\": $(jnum(integ.qold)), \"current_alg\": $current, " *
                      "\"naccept\": $(st.naccept), \"nreject\": $(st.nreject), \"nf\": $(st.nf), \"iter\": $(integ.iter), " *
                      "\"retcode\": \"$(integ.sol.retcode)\"}")
     end

@@ -208,6 +208,9 @@ PROBE_CASES = [
     ("dp5_bench06", "DP5", (10.0, 10.0), 10.0, 1.0, 3, 1800.0),
     ("dp5_blowup_u0_v14", "DP5", (0.0, 14.0), 1e-3, 1e-4, 2, 600.0),
     ("dp5_blowup_um7_v12", "DP5", (-7.0, 12.0), 1e-3, 1e-4, 2, 600.0),
+    # the default solver on the stiff parameter set of tests/T04_2D_reg_test.jl (C_φ = c_β = 4e-2), and on the usual one
+    ("auto_stiff_um10_vm10", "AutoTsit5", (-10.0, -10.0), 1e-3, 1e-4, 3, 600.0, 4e-2),
+    ("auto_nonstiff_u10_v10", "AutoTsit5", (10.0, 10.0), 1e-3, 1e-4, 3, 600.0),
 ]
 
 
@@ -218,18 +221,18 @@ def _num(x):
 def run_probe_oracle():
     """the probe's cases on the oracle, in the layout julia/probe_integrator.jl writes (counters cumulative)"""
     out = []
-    for name, solver, wind, dt, dtmin, nDT, ts in PROBE_CASES:
-        P = default_params(solver=solver, dt=dt, dtmin=dtmin)
+    for name, solver, wind, dt, dtmin, nDT, ts, *rest in PROBE_CASES:
+        P = default_params(solver=solver, dt=dt, dtmin=dtmin, **({"C_phi": rest[0]} if rest else {}))
         z0, _, _ = oracle.windsea(wind[0], wind[1], ts)
-        r = dict(u=np.asarray(z0, np.float64), t=0.0, dt=dt, qold=1e-4, iter=0, status=0)
+        r = dict(u=np.asarray(z0, np.float64), t=0.0, dt=dt, qold=1e-4, iter=0, status=0, as_state=(0, 0))
         acc = rej = nf = 0
         steps = []
         for _ in range(nDT):
             r = oracle.integrate_one(P, r["u"], t=r["t"], dt=r["dt"], qold=r["qold"], it=r["iter"], wind0=wind, DT=600.0,
-                                     M=M, status=r["status"])
+                                     M=M, status=r["status"], as_state=r["as_state"])
             acc += r["counters"]["n_substeps"]; rej += r["counters"]["n_rejects"]; nf += r["counters"]["n_rhs"]
             steps.append(dict(u=[float(x) for x in r["u"]], t=r["t"], dt=r["dt"], qold=r["qold"], naccept=acc, nreject=rej,
-                              nf=nf, iter=r["iter"], retcode="Success" if r["status"] == 0 else "status %d" % r["status"]))
+                              nf=nf, iter=r["iter"], current_alg=2 if r["as_state"][1] else 1, retcode="Success" if r["status"] == 0 else "status %d" % r["status"]))
         out.append(dict(name=name, solver=solver, wind=list(wind), dt=dt, dtmin=dtmin, timescale=ts,
                         z0=[float(x) for x in z0], steps=steps))
     return out
@@ -296,6 +299,8 @@ def test_probe_layout_round_trips(tmp_path):
     rep = compare_probe(back["cases"], got)
     assert all(r["same_step_sequence"] and r["max_rel_u"] == 0.0 for r in rep.values())
     assert [n for n, r in rep.items() if r["got_retcodes"][-1] != "Success"] == ["dp5_blowup_u0_v14", "dp5_blowup_um7_v12"]
+    stiff = {c["name"]: [s["current_alg"] for s in c["steps"]] for c in got if c["name"].startswith("auto_")}
+    assert stiff["auto_stiff_um10_vm10"] == [2, 2, 2] and stiff["auto_nonstiff_u10_v10"][0] == 1
 
 
 @pytest.mark.skipif(not os.path.isfile(PROBE), reason="no integrator probe: run julia/probe_integrator.jl on a machine with Julia")
@@ -305,8 +310,10 @@ def test_oracle_against_the_julia_integrator_probe():
     rep = compare_probe(ref["cases"], run_probe_oracle())
     print("oracle vs OrdinaryDiffEq", ref.get("OrdinaryDiffEq"), json.dumps(rep, indent=1))
     for name, r in rep.items():
-        if name.startswith("dp5_blowup"):
-            continue    # reported, not asserted: the reference's behaviour here depends on its OrdinaryDiffEq version
+        if name.startswith("dp5_blowup") or name.startswith("auto_"):
+            # reported, not asserted: what the reference does on an overflowing trial step depends on its OrdinaryDiffEq
+            # version, and the oracle's AutoSwitch carries documented simplifications
+            continue
         assert r["same_step_sequence"], (name, r)
         assert r["max_rel_u"] <= 1e-6, (name, r)
 
