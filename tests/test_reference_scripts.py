@@ -161,7 +161,7 @@ def test_S02_2D_box_mesh_grid_single_steps():
     wave_model = WaveGrowth2D(grid=grid, winds=dict(u=u, v=v), ODEsys=particle_system, ODEsets=ODE_settings,
                               ODEinit_type=ParticleDefaults(math.log(5), 5.0, 5.0, 0.0, 0.0), periodic_boundary=False,
                               boundary_type="same", movie=True)
-    model, o, ref = three_ways(wave_model, u, v, 20 * minutes, 5, "bare")
+    model, o, ref = three_ways(wave_model, u, v, 20 * minutes, 5, "bare", third_steps=2)
     S = np.asarray(model.State)
     assert (grid.data.mask == 2).sum() > 0 and (grid.data.mask == 0).sum() > 0
     assert S[:, :, 0].max() > 5.0 * 2                      # accumulated over the steps: more than one particle's energy
