@@ -136,7 +136,12 @@ typedef struct {
     int32_t periodic_boundary;  /* the MODEL kwarg: selects ocean_points (WaveGrowthModels2D.jl:256-270) */
     /* quirk switches */
     int32_t on_persist;         /* 0: `on` frozen at seed (as the reference runs, B-1); 1: as intended */
-    int32_t reserved;
+    int32_t nan_eest_rejects;   /* a trial step whose stages overflow has EEst = NaN and is rejected; what the reject rule
+                                   dt /= min(1/qmin, EEst^beta1/gamma) makes of it depends on OrdinaryDiffEq's (unpinned)
+                                   version.  0: exact powers — NaN^beta1 = NaN, Julia's min propagates it, dt = NaN, the
+                                   integrator ends with DtNaN (status PICLES_PST_UNSTABLE).  1: `fastpow` / FastPower's
+                                   `fastpower` — they read the NaN bit pattern as a large finite number, so the step is
+                                   rejected by the full factor 1/qmin and the integration goes on */
 } picles_params_t;
 
 /* per-step device counters (summed over this handle's strip) */

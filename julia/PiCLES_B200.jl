@@ -40,6 +40,7 @@ Base.@kwdef struct B200 <: AbstractArchitecture
     peak_shift::Bool = true
     direction::Bool = true
     on_persist::Bool = false      # SURVEY B-1: false = `on` frozen at seed, as the reference runs
+    nan_eest_rejects::Bool = false  # a NaN error estimate: false = DtNaN (exact powers), true = rejected by 1/qmin (fastpow / fastpower)
     # multi-GPU: this process owns rows j0+1 : j0+ny_local of the global grid
     rank::Int = 0
     nranks::Int = 1
@@ -65,7 +66,7 @@ struct PiclesParams                # picles_params_t, 264 bytes
     minimal_state::NTuple{2,Cdouble}
     has_defaults::Int32
     defaults::NTuple{5,Cdouble}
-    periodic_boundary::Int32; on_persist::Int32; reserved::Int32
+    periodic_boundary::Int32; on_persist::Int32; nan_eest_rejects::Int32
 end
 
 struct PiclesCounters              # picles_counters_t
@@ -119,7 +120,7 @@ function flatten_params(model, arch::B200)
         (model.minimal_state[1], model.minimal_state[2]),
         d === nothing ? 0 : 1,
         d === nothing ? (0.0, 0.0, 0.0, 0.0, 0.0) : (d.lne, d.c̄_x, d.c̄_y, d.x, d.y),
-        model.periodic_boundary, arch.on_persist, 0)
+        model.periodic_boundary, arch.on_persist, arch.nan_eest_rejects)
 end
 
 # wind closures -> mesh arrays of this strip (north-star: evaluated on the host every step)

@@ -683,7 +683,11 @@ static void integrate(oracle_t* o, particle_t* p, const rhs_ctx_t* c, double DT,
             if (bad) { p->status |= PICLES_PST_UNSTABLE; C->n_failed++; break; } /* unstable_check */
         } else {
             /* step_reject_controller! */
-            dt = dt / pm_min(1.0 / qmin, q11 / gamma);
+            /* q11 = NaN (EEst = NaN: the stages of the trial step overflowed): Julia's min propagates it and the integrator
+               ends with DtNaN at the next check_error!, unless the powers are OrdinaryDiffEq's fastpow / fastpower, which
+               turn the NaN bit pattern into a large finite number: rejected by 1/qmin (picles_params_t::nan_eest_rejects) */
+            if (P->nan_eest_rejects && q11 != q11) dt = dt / (1.0 / qmin);
+            else dt = dt / pm_min(1.0 / qmin, q11 / gamma);
             C->n_rejects++;
         }
         /* AutoSwitch (AutoTsit5 defaults: maxstiffstep 10, maxnonstiffstep 3, nonstifftol = stifftol

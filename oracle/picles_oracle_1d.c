@@ -329,7 +329,8 @@ static void integrate1(oracle1d_t* o, p1_t* p, const ctx1_t* c, double DT) {
             C->n_substeps++;
             if ((u[0] != u[0]) | (u[1] != u[1]) | (u[2] != u[2])) { p->status |= PICLES_PST_UNSTABLE; C->n_failed++; break; }
         } else {
-            dt = dt / pm_min(1.0 / qmin, q11 / gamma);
+            if (P->nan_eest_rejects && q11 != q11) dt = dt / (1.0 / qmin); /* fastpow reading of a NaN error estimate: see picles_b200.h */
+            else dt = dt / pm_min(1.0 / qmin, q11 / gamma);
             C->n_rejects++;
         }
     }

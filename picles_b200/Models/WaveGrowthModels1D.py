@@ -30,7 +30,7 @@ class WaveGrowth1D:
 
     def __init__(self, *, grid, winds, ODEsys, ODEvars=None, layers=1, clock=None, ODEsets=None, ODEinit_type="wind_sea",
                  minimal_particle=None, minimal_state=None, currents=None, periodic_boundary=True, boundary_type="same",
-                 CBsets=None, architecture=None):
+                 CBsets=None, architecture=None, nan_eest_rejects=False):
         if not isinstance(grid, OneDGrid):
             raise TypeError("grid must be a OneDGrid")
         if layers != 1:
@@ -57,7 +57,8 @@ class WaveGrowth1D:
         self.minimal_state = FetchRelations.MinimalState(2, 0, ODEsets.timestep) if minimal_state is None else minimal_state
         self.FailedCollection = []
         self.gridnotes = OneDGridNotes(grid)
-        P = make_params(ODEsets, ODEsys, self.minimal_state, defaults=None, periodic_boundary=self.periodic_boundary)
+        P = make_params(ODEsets, ODEsys, self.minimal_state, defaults=None, periodic_boundary=self.periodic_boundary,
+                        nan_eest_rejects=nan_eest_rejects)
         from ..engine1d import B200Engine1D
         self.engine = B200Engine1D(grid.Nx, grid.xmin, grid.dx, self.gridnotes.x, P, device=arch.devices[0])
         self._seeded = False

@@ -59,7 +59,7 @@ class WaveGrowth2D:
     def __init__(self, *, grid, winds, ODEsys, ODEvars=None, layers=1, clock=None, ODEsets=None,
                  ODEinit_type="wind_sea", minimal_particle=None, minimal_state=None, currents=None,
                  periodic_boundary=True, boundary_type="same", CBsets=None, movie=False,
-                 architecture=B200(), on_persist=False, strip=None):
+                 architecture=B200(), on_persist=False, strip=None, nan_eest_rejects=False):
         if ODEsets is None:
             raise ValueError("ODEsets is required")
         if layers != 1:
@@ -108,7 +108,8 @@ class WaveGrowth2D:
         self.on_persist = bool(on_persist)
         self.params = make_params(ODEsets, ODEsys, self.minimal_state,
                                   defaults=None if self.ODEdefaults is None else self.ODEdefaults.as_list(),
-                                  periodic_boundary=self.periodic_boundary, on_persist=self.on_persist)
+                                  periodic_boundary=self.periodic_boundary, on_persist=self.on_persist,
+                                  nan_eest_rejects=nan_eest_rejects)
         self.Nx, self.Ny = grid.stats.Nx.N, grid.stats.Ny.N
         self._strip = strip  # (j0, ny_local, halo) when this model is one y-strip of a larger grid
         self._engine = None

@@ -63,7 +63,7 @@ class PiclesParams(C.Structure):
         ("defaults", C.c_double * 5),
         ("periodic_boundary", C.c_int32),
         ("on_persist", C.c_int32),
-        ("reserved", C.c_int32),
+        ("nan_eest_rejects", C.c_int32),
     ]
 
 

@@ -926,7 +926,13 @@ PM_HD bool integrate(const picles_params_t& P, const double wu0, const double wv
             } else {
                 /* step_reject_controller!: dt /= min(1/qmin, q11/gamma), q11 = EEst^beta1 */
                 double q11 = (EEst == 0.0) ? 1.0 : pm_exp(sc.t1);
-                dt_next = dt / pm_min(1.0 / qmin, q11 / gamma);
+#if defined(__CUDA_ARCH__)
+                /* the specialised copies (TSIT5 != 0) are launched only with the switch off (launch_advance2): their
+                   code is what it was before the switch existed */
+                dt_next = dt / pm_reject_factor(TSIT5 == 0 ? P.nan_eest_rejects : 0, q11, qmin, gamma);
+#else
+                dt_next = dt / pm_reject_factor(P.nan_eest_rejects, q11, qmin, gamma);
+#endif
             }
             bool is_stiff = false;
             if (autosw) {

@@ -340,7 +340,7 @@ P1_HD void p1_integrate(const picles_params_t& P, const WindCtx& w, double DT, P
             c.substeps++;
             if ((u[0] != u[0]) | (u[1] != u[1]) | (u[2] != u[2])) { p.status |= PICLES_PST_UNSTABLE; c.failed++; break; }
         } else {
-            dt = dt / pm_min(1.0 / qmin, q11 / gamma);
+            dt = dt / pm_reject_factor(P.nan_eest_rejects, q11, qmin, gamma);
             c.rejects++;
         }
     }

@@ -1139,7 +1139,7 @@ static uint64_t params_hash(const picles_params_t& P) {
     /* the two runs of fields around the padding word behind has_defaults (and the one at the tail) */
     const unsigned char* b = (const unsigned char*)&P;
     const size_t span[2][2] = {{0, offsetof(picles_params_t, has_defaults) + sizeof(int32_t)},
-                               {offsetof(picles_params_t, defaults), offsetof(picles_params_t, reserved)}};
+                               {offsetof(picles_params_t, defaults), offsetof(picles_params_t, nan_eest_rejects) + sizeof(int32_t)}};
     uint64_t hsh = 1469598103934665603ull;
     for (int r = 0; r < 2; r++)
         for (size_t k = span[r][0]; k < span[r][1]; k++) { hsh ^= b[k]; hsh *= 1099511628211ull; }

@@ -866,17 +866,20 @@ void launch_advance2(const DeviceArrays& A, const picles_params_t& P, double DT,
     if (count <= 0) return;
     int g = grid_for(count, ADV_THREADS, sms, ADV_MIN_BLOCKS);
     bool pn = (A.M[0] != nullptr);
+    /* picles_params_t::nan_eest_rejects (a NaN error estimate rejected by 1/qmin instead of ending the integrator) lives
+       in the generic instantiations only: the specialised ones keep the code they were measured with */
+    const bool spec = !P.nan_eest_rejects;
 #define ADV_ARGS A, P, DT, dc, l_begin, l_end, l2_begin, l2_end, slot
     /* AutoTsit5 runs the instantiation that carries the stiffness monitor and the Rosenbrock23 branch */
     if (P.solver == PICLES_SOLVER_AUTOTSIT5) {
         const int gr = grid_for(count, ADV_THREADS, sms, 1);
         /* (third template argument 3: propagation on, known at compile time, as in the Tsit5 / DP5 instantiations) */
         if (pn) {
-            if (P.propagation) k_advance<true, true, 3><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
+            if (P.propagation && spec) k_advance<true, true, 3><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
             else k_advance<true, true><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
             k_advance_resume<true><<<gr, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end);
         } else {
-            if (P.propagation) k_advance<false, true, 3><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
+            if (P.propagation && spec) k_advance<false, true, 3><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
             else k_advance<false, true><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
             k_advance_resume<false><<<gr, ADV_THREADS, 0, st>>>(A, P, DT, dc, l_begin, l_end);
         }
@@ -885,12 +888,12 @@ void launch_advance2(const DeviceArrays& A, const picles_params_t& P, double DT,
         /* Tsit5 has its own instantiation (compile-time tableau without zero coefficients) */
         /* (the specialised instantiations take propagation as given: a run without it — the reference's
            propagation = false switch — is served by the generic one) */
-        const bool ts5 = (P.solver == PICLES_SOLVER_TSIT5) && P.propagation;
+        const bool ts5 = (P.solver == PICLES_SOLVER_TSIT5) && P.propagation && spec;
         if (pn && ts5) k_advance<true, false, true><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
         else if (pn) k_advance<true, false><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
         else if (ts5) k_advance<false, false, true><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
         /* ... and so has DP5 on a uniform kernel (the bench06 settings): -1.5 % */
-        else if (P.solver == PICLES_SOLVER_DP5 && P.propagation) k_advance<false, false, 2><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
+        else if (P.solver == PICLES_SOLVER_DP5 && P.propagation && spec) k_advance<false, false, 2><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
         else k_advance<false, false><<<g, ADV_THREADS, 0, st>>>(ADV_ARGS);
         COUNT_LAUNCH(1);
     }

@@ -271,7 +271,7 @@ PM_HD_NOINLINE_DECL void stiff_integrate(const picles_params_t* Pp, const WindPo
             c.substeps++;
             if (bad) { p.status |= PICLES_PST_UNSTABLE; c.failed++; break; }
         } else {
-            dt = dt / pm_min(1.0 / qmin, q11 / gamma);
+            dt = dt / pm_reject_factor(P.nan_eest_rejects, q11, qmin, gamma);
             c.rejects++;
         }
         /* AutoSwitch with eigen_est = opnorm(J, Inf) */

@@ -5,7 +5,8 @@ from __future__ import annotations
 from ._abi import PiclesParams
 
 
-def make_params(ODEsets, ODEsys, minimal_state, defaults=None, periodic_boundary=True, on_persist=False):
+def make_params(ODEsets, ODEsys, minimal_state, defaults=None, periodic_boundary=True, on_persist=False,
+                nan_eest_rejects=False):
     """ODEsets: ParticleSystems.particle_waves_v5.ODESettings; ODEsys: ParticleSystem
     (result of particle_equations); minimal_state: [E_min, |m|²_min]; defaults: None
     ("wind_sea") or a 5-sequence (ParticleDefaults lne, c̄_x, c̄_y, x, y)."""
@@ -47,4 +48,7 @@ def make_params(ODEsets, ODEsys, minimal_state, defaults=None, periodic_boundary
             P.defaults[k] = float(defaults[k])
     P.periodic_boundary = int(bool(periodic_boundary))
     P.on_persist = int(bool(on_persist))
+    # a NaN error estimate (overflowing trial step): False = DtNaN, exact powers; True = rejected by 1/qmin, as
+    # OrdinaryDiffEq's fastpow / FastPower.fastpower make of it (include/picles_b200.h)
+    P.nan_eest_rejects = int(bool(nan_eest_rejects))
     return P

@@ -23,7 +23,7 @@ SHIM_SO = os.path.join(HERE, "_build", "libhost_shim.so")
 
 
 def default_params(DT=600.0, solver="Tsit5", dt=1e-3, dtmin=1e-4, force_dtmin=True, periodic_boundary=False,
-                   on_persist=False, wind_min_squared=4.0, log_energy_maximum=math.log(17), defaults=None,
+                   on_persist=False, wind_min_squared=4.0, log_energy_maximum=math.log(17), defaults=None, nan_eest_rejects=False,
                    timestep=None, minimal_state=None, C_phi=None, **switches):
     """example_00_minimal.jl:17-67 settings unless overridden."""
     pars, cid, _ = PW.ODEParameters(r_g=0.85)
@@ -35,7 +35,8 @@ def default_params(DT=600.0, solver="Tsit5", dt=1e-3, dtmin=1e-4, force_dtmin=Tr
                           timestep=ts, total_time=6 * 86400.0, dt=dt, dtmin=dtmin, force_dtmin=force_dtmin,
                           solver=solver, wind_min_squared=wind_min_squared, log_energy_maximum=log_energy_maximum)
     ms = FR.MinimalState(2, 2, ts) if minimal_state is None else minimal_state
-    return make_params(sets, ps, ms, defaults=defaults, periodic_boundary=periodic_boundary, on_persist=on_persist)
+    return make_params(sets, ps, ms, defaults=defaults, periodic_boundary=periodic_boundary, on_persist=on_persist,
+                       nan_eest_rejects=nan_eest_rejects)
 
 
 def cartesian_grid(Nx, Ny, dx=2000.0, dy=2000.0, bx=BND_NONPERIODIC, by=BND_NONPERIODIC, ocean=None):

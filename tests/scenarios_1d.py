@@ -11,14 +11,15 @@ from picles_b200.params import make_params
 
 
 def params_1d(DT=600.0, solver="Tsit5", periodic=False, dt=1e-3, dtmin=1e-4, force_dtmin=True, wind_min_squared=4.0,
-              log_energy_maximum=math.log(17), **switches):
+              log_energy_maximum=math.log(17), nan_eest_rejects=False, **switches):
     pars, cid, scg = PW.ODEParameters(r_g=0.85)
     ps = PW.particle_equations(None, γ=cid.γ, q=cid.q, **switches)   # one forcing field: the 1-D system
     pars1 = dict(r_g=pars["r_g"], C_α=pars["C_α"], C_e=pars["C_e"])  # default_ODE_parameters of the 1-D scripts
     sets = PW.ODESettings(Parameters=pars1, log_energy_minimum=FR.MinimalWindsea(10, 0, DT)["lne"], saving_step=DT, timestep=DT,
                           total_time=6 * 86400.0, dt=dt, dtmin=dtmin, force_dtmin=force_dtmin, solver=solver,
                           wind_min_squared=wind_min_squared, log_energy_maximum=log_energy_maximum)
-    return make_params(sets, ps, FR.MinimalState(2, 0, DT), defaults=None, periodic_boundary=periodic)
+    return make_params(sets, ps, FR.MinimalState(2, 0, DT), defaults=None, periodic_boundary=periodic,
+                       nan_eest_rejects=nan_eest_rejects)
 
 
 def grid_1d(xmin, xmax, Nx):

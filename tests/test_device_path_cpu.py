@@ -135,3 +135,59 @@ def test_random_configurations_default_solver_and_persisting_flags(seed, mode):
                      for k in (0, 1))
 
     run_pair(make_oracle(g, P2), HostShim(g, P2), wind, DT, 5, compare_models)
+
+
+def _blowup_case(nan_eest_rejects):
+    """scenario dp5_blowup (DP5 trial steps that overflow in a band of columns) with the reject switch"""
+    from common import cartesian_grid, default_params
+    g = cartesian_grid(24, 10)
+    v = np.broadcast_to(np.linspace(13.6, 14.4, 24), (10, 24)).copy()
+    u = np.zeros((10, 24))
+    return g, default_params(solver="DP5", nan_eest_rejects=nan_eest_rejects), (lambda t: (u, v)), 600.0, 3
+
+
+@pytest.mark.parametrize("mode", ["one strip", "specialised", "two strips"])
+def test_nan_error_estimate_rejected_instead_of_ending_the_integrator(mode):
+    """picles_params_t::nan_eest_rejects = 1 (the fastpow / fastpower reading, include/picles_b200.h): the particles that
+    scenario dp5_blowup loses integrate on — nobody fails — bit for bit between oracle and device code"""
+    from common import shim_lib
+    g, P, wind, DT, n = _blowup_case(True)
+    lib = shim_lib()
+    lib.shim_set_specialised(1 if mode == "specialised" else 0)
+    try:
+        ref = make_oracle(g, P)
+        kw = dict(nstrips=2, halo=2) if mode == "two strips" else {}
+        run_pair(ref, HostShim(g, P, **kw), wind, DT, n, compare_models)
+    finally:
+        lib.shim_set_specialised(0)
+    o = make_oracle(g, P)
+    o.seed(*wind(0.0))
+    failed = rejects = 0
+    for k in range(n):
+        o.step(k * DT, DT, *wind(k * DT), *wind((k + 1) * DT))
+        failed += o.counters()["n_failed"]
+        rejects += o.counters()["n_rejects"]
+    assert failed == 0 and rejects >= 176 and not (o.particles()["status"] & 4).any()
+    g0, P0, wind0, _, _ = _blowup_case(False)
+    o0 = make_oracle(g0, P0)
+    o0.seed(*wind0(0.0))
+    o0.step(0.0, DT, *wind0(0.0), *wind0(DT))
+    assert o0.counters()["n_failed"] == 32
+
+
+@pytest.mark.parametrize("seed", [2, 5, 9, 13, 17, 23])
+def test_random_configurations_with_the_reject_switch(seed):
+    """random configurations (several of these seeds lose particles to overflowing trial steps with the switch off) with
+    nan_eest_rejects = 1, under the configuration's solver: device code = oracle bit for bit, nobody ends with DtNaN"""
+    from common import default_params
+    from test_independent_model import fuzz_case
+    g, P, winds, DT, solver = fuzz_case(seed)
+    P2 = default_params(DT=DT, solver=solver, periodic_boundary=bool(P.periodic_boundary), wind_min_squared=P.wind_min_squared,
+                        log_energy_maximum=P.log_energy_maximum, nan_eest_rejects=True)
+
+    def wind(t):
+        return tuple(np.array([[winds(g["x"][j, i], g["y"][j, i], t)[k] for i in range(g["Nx"])] for j in range(g["Ny"])])
+                     for k in (0, 1))
+
+    ref = make_oracle(g, P2)
+    run_pair(ref, HostShim(g, P2), wind, DT, 4, compare_models)

@@ -28,3 +28,16 @@ def test_gpu_random_configurations_bit_exact(gpu_lib, seed):
                      for k in (0, 1))
 
     run_pair(make_oracle(g, P), engine_for(g, P), wind, DT, 4, compare_models)
+
+
+@pytest.mark.parametrize("mode", ["one strip", "two strips"])
+def test_gpu_nan_error_estimate_rejected(gpu_lib, mode):
+    """picles_params_t::nan_eest_rejects = 1 on scenario dp5_blowup (the generic instantiation of the advance kernel
+    carries the switch; the specialised ones are launched only with it off): nobody fails, bit for bit"""
+    from test_device_path_cpu import _blowup_case
+    from test_gpu_parity import StripSet, engine_for
+    g, P, wind, DT, n = _blowup_case(True)
+    dut = StripSet(g, P, 2, 2) if mode == "two strips" else engine_for(g, P)
+    ref = make_oracle(g, P)
+    run_pair(ref, dut, wind, DT, n, compare_models)
+    assert ref.counters()["n_failed"] == 0

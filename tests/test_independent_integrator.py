@@ -80,7 +80,7 @@ def _initdt(f, u0, t, abstol, reltol, dtmin, dtmax, order=5):
 
 
 def integrate_python(f, u, t, DT, dt, qold, solver, abstol, reltol, dtmin, dtmax, force_dtmin, dt_reset=False,
-                     gamma=0.9, qmin=0.2, qmax=10.0, qoldinit=1e-4):
+                     gamma=0.9, qmin=0.2, qmax=10.0, qoldinit=1e-4, nan_eest_rejects=False):
     """`step!(integ, DT, true)`: adaptive steps until the added tstop t + DT is reached."""
     c, a, bt, beta1, beta2 = _tableau(solver)
     tstop = t + DT
@@ -124,7 +124,12 @@ def integrate_python(f, u, t, DT, dt, qold, solver, abstol, reltol, dtmin, dtmax
             dt = dt / q
         else:
             n_rej += 1
-            dt = dt / jmin(1.0 / qmin, q11 / gamma)
+            if nan_eest_rejects and q11 != q11:
+                # OrdinaryDiffEq's fastpow / FastPower.fastpower: Float32(NaN) read as bits is 2^(β1·128.56), a large finite
+                # q11, so min(1/qmin, q11/γ) = 1/qmin — the step is rejected by the full factor and the run goes on
+                dt = dt / (1.0 / qmin)
+            else:
+                dt = dt / jmin(1.0 / qmin, q11 / gamma)
             u_trial = unew            # an in-place integrator's `u` holds the rejected trial until the next attempt
     return dict(u=np.array(u), t=t, dt=dt, qold=qold, n_acc=n_acc, n_rej=n_rej, n_rhs=n_rhs, retcode=retcode,
                 u_trial=u_trial)
@@ -341,3 +346,35 @@ def test_wind_scan_where_trial_steps_overflow():
         return bad
     assert scan("Tsit5") == set() and scan("AutoTsit5") == set()
     assert scan("DP5") == {(14.0, 0, 4), (24.08, 1, 4), (24.41, 1, 4)}
+
+
+@pytest.mark.parametrize("wind", [(0.0, 14.0), (-7.0, 12.0), (20.0, 14.0)])
+def test_nan_error_estimate_rejected_as_fastpow_does(wind):
+    """picles_params_t::nan_eest_rejects = 1: the reading of OrdinaryDiffEq versions whose PI controller forms its powers
+    with `fastpow` (DiffEqBase) or `fastpower` (FastPower.jl) — a NaN error estimate comes out of them as a large finite
+    number, the overflowing trial step is rejected by 1/qmin and the integration goes on.  Oracle against the independent
+    restatement on the winds where DP5 otherwise ends with DtNaN: same accepted / rejected counts, state to rounding level,
+    the tstop reached."""
+    P = default_params(solver="DP5", nan_eest_rejects=True)
+    assert P.nan_eest_rejects == 1
+    z0, _, _ = oracle.windsea(wind[0], wind[1], 600)
+    f = lambda t, z: list(oracle.rhs(P, np.asarray(z, np.float64), wind[0], wind[1], M=M))
+    ro = dict(u=np.asarray(z0, np.float64), t=0.0, dt=1e-3, qold=1e-4, iter=0)
+    rp = dict(u=np.asarray(z0, np.float64), t=0.0, dt=1e-3, qold=1e-4)
+    nan_rejects = 0
+    for k in range(3):
+        ro = oracle.integrate_one(P, ro["u"], t=ro["t"], dt=ro["dt"], qold=ro["qold"], it=ro["iter"], wind0=wind, DT=600.0, M=M)
+        rp = integrate_python(f, rp["u"], rp["t"], 600.0, rp["dt"], rp["qold"], "DP5", P.abstol, P.reltol, P.dtmin, math.inf,
+                              True, nan_eest_rejects=True)
+        assert ro["status"] == 0 and rp["retcode"] == "Success" and ro["t"] == rp["t"] == 600.0 * (k + 1)
+        assert (ro["counters"]["n_substeps"], ro["counters"]["n_rejects"]) == (rp["n_acc"], rp["n_rej"])
+        assert np.max(np.abs(ro["u"] - rp["u"]) / np.maximum(np.abs(rp["u"]), 1e-6)) < 1e-9
+        nan_rejects += rp["n_rej"]
+    assert nan_rejects >= 1
+    # and with the switch off the same winds end the integrator (the default: exact powers)
+    P0 = default_params(solver="DP5")
+    r = dict(u=np.asarray(z0, np.float64), t=0.0, dt=1e-3, qold=1e-4, iter=0, status=0)
+    for k in range(3):
+        r = oracle.integrate_one(P0, r["u"], t=r["t"], dt=r["dt"], qold=r["qold"], it=r["iter"], wind0=wind, DT=600.0, M=M,
+                                 status=r["status"])
+    assert r["status"] != 0

@@ -374,3 +374,16 @@ def test_random_configurations_1d(seed):
     configurations, bit for bit after every step (300 seeds were run once: no difference)"""
     g, P, wind, DT = fuzz_case_1d(seed)
     run_pair_1d(make_oracle_1d(g, P), Shim1D(g, P), g, wind, DT, 5, compare_models_1d)
+
+
+@pytest.mark.parametrize("flag", [False, True])
+def test_nan_error_estimate_switch_1d(flag):
+    """picles_params_t::nan_eest_rejects on the 1-D path: DP5 under winds across the 14 m/s band loses a particle to an
+    overflowing trial step with the switch off (DtNaN) and none with it on; oracle = device header either way"""
+    g = grid_1d(0.0, 200e3, 21)
+    P = params_1d(600.0, solver="DP5", nan_eest_rejects=flag)
+    wind = lambda x, t: np.linspace(13.6, 14.4, 21) if np.ndim(x) else 14.0
+    a, b = make_oracle_1d(g, P), Shim1D(g, P)
+    run_pair_1d(a, b, g, wind, 600.0, 3, compare_models_1d)
+    dead = int(((a.particles()["status"] & 4) != 0).sum())
+    assert dead == (0 if flag else 1)
