@@ -36,6 +36,10 @@ class B200(AbstractArchitecture):
     #: steady winds; 5: within 1e-9 of the closure for the time-varying winds of the reference's
     #: scripts, tests/test_wind_levels.py).
     wind_levels: int = 2
+    #: a trial step whose stages overflow (EEst = NaN): False = the integrator ends with DtNaN (exact powers in the PI
+    #: controller, the default); True = rejected by 1/qmin, as OrdinaryDiffEq's fastpow / FastPower.fastpower make of it
+    #: (include/picles_b200.h: picles_params_t::nan_eest_rejects)
+    nan_eest_rejects: bool = False
 
     def __post_init__(self):
         if not 2 <= int(self.wind_levels) <= 5:

@@ -58,7 +58,7 @@ class WaveGrowth1D:
         self.FailedCollection = []
         self.gridnotes = OneDGridNotes(grid)
         P = make_params(ODEsets, ODEsys, self.minimal_state, defaults=None, periodic_boundary=self.periodic_boundary,
-                        nan_eest_rejects=nan_eest_rejects)
+                        nan_eest_rejects=nan_eest_rejects or getattr(architecture, "nan_eest_rejects", False))
         from ..engine1d import B200Engine1D
         self.engine = B200Engine1D(grid.Nx, grid.xmin, grid.dx, self.gridnotes.x, P, device=arch.devices[0])
         self._seeded = False

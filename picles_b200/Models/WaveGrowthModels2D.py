@@ -109,7 +109,7 @@ class WaveGrowth2D:
         self.params = make_params(ODEsets, ODEsys, self.minimal_state,
                                   defaults=None if self.ODEdefaults is None else self.ODEdefaults.as_list(),
                                   periodic_boundary=self.periodic_boundary, on_persist=self.on_persist,
-                                  nan_eest_rejects=nan_eest_rejects)
+                                  nan_eest_rejects=nan_eest_rejects or getattr(architecture, "nan_eest_rejects", False))
         self.Nx, self.Ny = grid.stats.Nx.N, grid.stats.Ny.N
         self._strip = strip  # (j0, ny_local, halo) when this model is one y-strip of a larger grid
         self._engine = None

@@ -287,3 +287,13 @@ def test_spherical_grid_mesh_through_the_model():
         t += DT
     compare_models(o, model.engine)
     assert np.nanmax(model.State[:, :, 0]) > 0
+
+
+def test_nan_eest_rejects_reaches_the_parameter_struct():
+    """B200(nan_eest_rejects=True) (or the model keyword) sets picles_params_t::nan_eest_rejects; the default is 0"""
+    model, _ = example_00_minimal()
+    assert model.params.nan_eest_rejects == 0
+    model, _ = example_00_minimal(architecture=B200(nan_eest_rejects=True))
+    assert model.params.nan_eest_rejects == 1
+    model, _ = example_00_minimal(nan_eest_rejects=True)
+    assert model.params.nan_eest_rejects == 1
