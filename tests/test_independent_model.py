@@ -188,7 +188,8 @@ class RefModel:
             Mk, pc = self.M_pc(p.ij)
             f = lambda t, z: list(oracle.rhs(P, np.asarray(z, np.float64), *self.wind(p, t), M=Mk, pc=pc))
             r = integrate_python(f, p.u, p.t, DT, p.dt, p.qold, self.solver, P.abstol, P.reltol, P.dtmin,
-                                 P.dtmax if P.dtmax > 0 else math.inf, bool(P.force_dtmin), dt_reset=p.dt_reset)
+                                 P.dtmax if P.dtmax > 0 else math.inf, bool(P.force_dtmin), dt_reset=p.dt_reset,
+                                 nan_eest_rejects=bool(P.nan_eest_rejects))
             if r["retcode"] != "Success":
                 raise TrialStepOverflow(p.ij)
             p.u, p.t, p.dt, p.qold, p.dt_reset = list(r["u"]), r["t"], r["dt"], r["qold"], False
@@ -474,3 +475,14 @@ def test_random_configurations(seed):
         run_both(g, P, winds, DT, 3, solver=solver, rtol=max(5e-9, 50.0 * sens))
     except TrialStepOverflow:
         pytest.skip("a trial step overflowed (DtNaN): the two models part by design there, see the quirk table")
+
+
+@pytest.mark.parametrize("seed", [2, 5, 9, 13])
+def test_random_configurations_with_the_reject_switch(seed):
+    """the seeds of this generator that stop at an overflowing trial step, with picles_params_t::nan_eest_rejects = 1 (the
+    fastpow / fastpower reading): nothing ends, and the third reading follows the oracle through the rejected NaN steps"""
+    g, P, winds, DT, solver = fuzz_case(seed)
+    P.nan_eest_rejects = 1
+    sens = rounding_sensitivity(g, P, winds, DT, 3)
+    ref, orc = run_both(g, P, winds, DT, 3, solver=solver, rtol=max(5e-9, 50.0 * sens))
+    assert orc.counters()["n_failed"] == 0
