@@ -297,3 +297,90 @@ def test_nan_eest_rejects_reaches_the_parameter_struct():
     assert model.params.nan_eest_rejects == 1
     model, _ = example_00_minimal(nan_eest_rejects=True)
     assert model.params.nan_eest_rejects == 1
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_scripts_through_the_mirror_api(seed):
+    """a random user script — grid size and spacing, periodic axes, land, the model's periodic flag, solver (the default
+    AutoTsit5 included), thresholds, B200(wind_levels = 2, 3 or 5), wind closures varying in space and time — driven through
+    a mix of run!-style steps, bare time_step!, movie_time_step! with a CHANGING Δt, then reset_simulation! and run!(...,
+    cash_store=true): at every point the fields equal the oracle driven by hand with the winds staged the way the library
+    documents, bit for bit (60 seeds were run once)."""
+    rng = np.random.default_rng(seed)
+    Nx, Ny = int(rng.integers(5, 12)), int(rng.integers(5, 10))
+    d = float(rng.choice([500.0, 1000.0, 2000.0]))
+    per = (bool(rng.random() < 0.5), bool(rng.random() < 0.5))
+    mask = (rng.random((Nx, Ny)) > 0.12) if rng.random() < 0.5 else None
+    grid = TwoDCartesianGridMesh(d * (Nx - 1), Nx, d * (Ny - 1), Ny, periodic_boundary=per, mask=mask)
+    DT = float(rng.choice([600.0, 900.0, 1200.0]))
+    a, b, c = rng.uniform(-9, 9, 3)
+    d_, e, f = rng.uniform(-9, 9, 3)
+    om = 2 * math.pi / float(rng.choice([3600.0, 7200.0, 1e9]))
+    calm = rng.uniform(0, 0.6)
+    x1, y1 = max(d * (Nx - 1), 1.0), max(d * (Ny - 1), 1.0)
+
+    def w(x, y, t):
+        sx, sy = x / x1, y / y1
+        sw = 1.0 + 0.9 * math.sin(om * t + 2.0 * sy)
+        if sx < calm:
+            return 1.1 * sw, -0.6 * sw
+        return (a + b * sx) * (1.0 + 0.3 * math.sin(om * t)) + c * sy, d_ + e * sy + f * math.cos(om * t)
+
+    u = lambda x, y, t: w(x, y, t)[0]
+    v = lambda x, y, t: w(x, y, t)[1]
+    ODEpars, CID, _ = PW.ODEParameters(r_g=0.85)
+    solver = str(rng.choice(["Tsit5", "DP5", "AutoTsit5"]))
+    S = PW.ODESettings(Parameters=ODEpars, log_energy_minimum=FetchRelations.MinimalWindsea(10, 10, DT)["lne"],
+                       log_energy_maximum=float(rng.choice([math.log(17), math.log(3e-3)])),
+                       wind_min_squared=float(rng.choice([2.0, 4.0])), saving_step=DT, timestep=DT, total_time=6 * days,
+                       dt=1e-3, dtmin=1e-4, force_dtmin=True, solver=solver)
+    levels = int(rng.choice([2, 2, 3, 5]))
+    m = WaveGrowth2D(grid=grid, winds=dict(u=u, v=v), ODEsys=PW.particle_equations(u, v, γ=CID.γ, q=CID.q), ODEsets=S,
+                     periodic_boundary=bool(rng.random() < 0.5), architecture=B200(wind_levels=levels), movie=True)
+    attach_shim(m)
+    g = grid_dict_from_mesh(m.grid)
+    wa = lambda t: tuple(np.array([[w(g["x"][j, i], g["y"][j, i], t)[k] for i in range(g["Nx"])] for j in range(g["Ny"])])
+                         for k in (0, 1))
+    clock = [0.0]
+
+    def ostep(o, accumulate, dt):
+        t = clock[0]
+        o.set_accumulate(accumulate)
+        nm = levels - 2
+        if nm:
+            lv = [wa(t + dt * float(k) / float(nm + 1)) for k in range(1, nm + 1)]
+            o.set_wind_midlevels([x for x, _ in lv], [y for _, y in lv])
+        o.step(t, dt, *wa(t), *wa(t + dt))
+        clock[0] = t + dt
+
+    o = make_oracle(g, m.params)
+    o.seed(*wa(0.0))
+    sim = Simulation(m, Δt=DT, stop_time=3 * DT)
+    initialize_simulation(sim)
+    assert bits_equal(np.asarray(m.State).transpose(2, 1, 0), o.state())
+    for kind, dt in [("run", DT), ("bare", DT), ("movie", DT / 2), ("run", DT), ("bare", DT / 2)]:
+        if kind == "run":
+            time_step(m, dt, zero_state_first=True)
+            ostep(o, 0, dt)
+            shown = m.State
+        elif kind == "bare":
+            time_step(m, dt)
+            ostep(o, 1, dt)
+            shown = m.State
+        else:
+            movie_time_step(m, dt)
+            ostep(o, 1, dt)
+            shown = m.MovieState
+        assert bits_equal(np.asarray(shown).transpose(2, 1, 0), o.state()), (kind, dt)
+        if kind == "movie":
+            o.set_state(np.zeros((3, g["Ny"], g["Nx"])))
+    compare_models(o, m.engine)
+    reset_simulation(sim)
+    o = make_oracle(g, m.params)
+    o.seed(*wa(0.0))
+    clock[0] = 0.0
+    sim.stop_time = 2 * DT
+    run(sim, cash_store=True)
+    for _ in range(3):
+        ostep(o, 0, DT)
+    assert len(sim.store.store) == 4 and bits_equal(np.asarray(sim.store.store[-1]).transpose(2, 1, 0), o.state())
