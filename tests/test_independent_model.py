@@ -397,11 +397,11 @@ def test_fast_box_reinit_of_integrating_particles():
 
 
 # ---- randomized differential runs ------------------------------------------------------------------------------
-def fuzz_case(seed):
+def fuzz_case(seed, ny_scale=1):
     """one random configuration (grid size and spacing, boundary types, land, model flag, solver, thresholds, a wind
     that varies in space and time and is calm somewhere some of the time) through both models"""
     rng = np.random.default_rng(seed)
-    Nx, Ny = int(rng.integers(5, 10)), int(rng.integers(5, 9))
+    Nx, Ny = int(rng.integers(5, 10)), int(rng.integers(5, 9)) * ny_scale      # ny_scale > 1: tall grids for strips
     kind = "tripolar" if rng.random() < 0.2 else "cartesian"
     ocean = (rng.random((Ny, Nx)) > 0.12).astype(np.uint8) if rng.random() < 0.5 else None
     kw = {}
