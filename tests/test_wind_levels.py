@@ -277,3 +277,34 @@ def test_off_particles_test_the_wind_at_their_own_clock(shape):
             m.step(t, DT, *arrays(t), *arrays(t + DT))
         t += DT
     compare_models(a, b)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_wind_mesh_sampler_on_random_meshes(seed):
+    """random knot vectors (uniform or not, 2 to 19 knots per axis), random fields, query points inside, on the knots and
+    up to three periods outside, times inside and outside: device header = oracle bit for bit, and the oracle within 1e-11
+    of scipy's RegularGridInterpolator inside the mesh (300 + 200 seeds were run once)"""
+    from scipy.interpolate import RegularGridInterpolator
+    rng = np.random.default_rng(1000 + seed)
+    nx, ny, nt = int(rng.integers(2, 20)), int(rng.integers(2, 15)), int(rng.integers(2, 8))
+
+    def knots(n):
+        if rng.random() < 0.5:
+            return np.linspace(rng.uniform(-1e5, 1e5), rng.uniform(2e5, 9e5), n)
+        return np.cumsum(rng.uniform(0.1, 3.0, n)) * rng.uniform(10, 1e4) + rng.uniform(-1e5, 1e5)
+
+    xw, yw, tw = knots(nx), knots(ny), knots(nt)
+    U, V = rng.normal(5, 6, (nt, ny, nx)), rng.normal(-2, 5, (nt, ny, nx))
+    n = int(rng.integers(1, 700))
+    Lx, Ly, Lt = xw[-1] - xw[0], yw[-1] - yw[0], tw[-1] - tw[0]
+    x = np.concatenate([rng.uniform(xw[0] - 3 * Lx, xw[-1] + 3 * Lx, n), xw, [xw[0], xw[-1]]])
+    y = np.concatenate([rng.uniform(yw[0] - 2 * Ly, yw[-1] + 2 * Ly, n), np.resize(yw, xw.size), [yw[-1], yw[0]]])
+    for t in list(rng.uniform(tw[0] - 2 * Lt, tw[-1] + 2 * Lt, 4)) + [tw[0], tw[-1], tw[len(tw) // 2]]:
+        uo, vo = oracle.wind_mesh_sample(xw, yw, tw, U, V, x, y, float(t))
+        us, vs = shim_sample(xw, yw, tw, U, V, x, y, float(t))
+        assert bits_equal(uo, us) and bits_equal(vo, vs)
+    xi, yi = rng.uniform(xw[0], xw[-1], 300), rng.uniform(yw[0], yw[-1], 300)
+    for t in rng.uniform(tw[0], tw[-1], 3):
+        ref = RegularGridInterpolator((tw, yw, xw), U)(np.stack([np.full_like(xi, t), yi, xi], axis=1))
+        got, _ = oracle.wind_mesh_sample(xw, yw, tw, U, V, xi, yi, float(t))
+        assert np.max(np.abs(got - ref)) < 1e-11
