@@ -185,3 +185,36 @@ def test_particle_node_maps_against_exact_arithmetic():
         assert abs(F(float(back[0])) - mp.log(F(float(ch[0])))) <= REL * max(abs(lne), 1)
         assert close(back[1], F(float(ch[1])) * F(float(ch[0])) / (2 * m2), scale=abs(F(cx)) + abs(F(cy)))
         assert abs(back[1] - cx) <= 1e-12 * (abs(cx) + abs(cy)) and abs(back[2] - cy) <= 1e-12 * (abs(cx) + abs(cy))
+
+
+def test_grid_metric_against_exact_arithmetic():
+    """TripolarGridMOM6.jl:448-459 (`cos.(angle_dx * pi / 180)` — a product rounded to float64 BEFORE the cosine, not cosd)
+    and spherical_grid_corrections.jl:13 (`sign(φ)·min(sign(φ)·tand(φ), 60)/R`), from the Julia text in 50 digits, against
+    oracle.grid_metric (whose sin/cos/tand are this repository's own pmath_trig.h, shared with k_grid_metric): random
+    spacings, rotation angles over ±180°, latitudes over ±90° including the clamp near the poles, the equator and ±45°."""
+    rng = np.random.default_rng(11)
+    n = 4000
+    dx = rng.uniform(500.0, 2e5, n)
+    dy = rng.uniform(500.0, 2e5, n)
+    ang = np.concatenate([rng.uniform(-180.0, 180.0, n - 8), [0.0, 90.0, -90.0, 180.0, 45.0, 1e-9, -1e-9, 30.0]])
+    lat = np.concatenate([rng.uniform(-90.0, 90.0, n - 8), [0.0, 45.0, -45.0, 89.0, -89.0, 89.99, -89.99, 60.0]])
+    Mo, pco = oracle.grid_metric(dx, dy, ang, lat)
+    R = F("6.3710e6")
+    worst_M = worst_pc = 0.0
+    for k in range(n):
+        arg = F(float(ang[k]) * math.pi / 180)            # the float64 product the reference hands to cos / sin
+        ca, sa = mp.cos(arg), mp.sin(arg)
+        ref = [ca / F(float(dx[k])), sa / F(float(dy[k])), -sa / F(float(dx[k])), ca / F(float(dy[k]))]
+        for j in range(4):
+            # on the scale of the row's larger entry: cos(90°·π/180) is 6e-17, not 0, in both
+            scale = max(abs(ref[j]), 1 / F(float(max(dx[k], dy[k]))) * F("1e-3"))
+            worst_M = max(worst_M, float(abs(F(float(Mo[j][k])) - ref[j]) / scale))
+        ph = F(float(lat[k]))
+        sg = mp.sign(ph)
+        td = mp.tan(ph * mp.pi / 180)                      # tand: exact degrees
+        refpc = sg * min(sg * td, F(60)) / R
+        if refpc == 0:
+            assert pco[k] == 0.0
+        else:
+            worst_pc = max(worst_pc, float(abs(F(float(pco[k])) - refpc) / abs(refpc)))
+    assert worst_M < 5e-16 * 4 and worst_pc < 5e-16 * 4, (worst_M, worst_pc)
