@@ -117,3 +117,19 @@ def test_overlapped_step_partition():
         d = json.load(open(os.path.join(root, "profiles", f)))["strong_c5"]
         res = np.array(d["ms_per_step_per_rank"]) - (max(d["ms_advance_per_rank"]) + np.array(d["ms_project_remesh_per_rank"]))
         assert lo < res.min() and res.max() < hi and res.max() - res.min() < 0.01
+
+
+@pytest.mark.parametrize("seed,world,halo", [(0, 2, 5), (3, 3, 5), (6, 2, 6)])
+def test_random_configurations_over_gloo(tmp_path, seed, world, halo):
+    """random configurations (tall grids) in 2 and 3 strips over gloo through StripStepper's torch transport — bit for bit
+    against the single-domain oracle after every step.  (The halo covers the reach: the host build behind ShimStripEngine
+    has no halo_widen; the library's widening is tested on the GPU, tests/test_gpu_multi.py.)"""
+    import torch.multiprocessing as mp
+
+    import dist_worker
+    out = tmp_path / "result"
+    mp.spawn(dist_worker.run, args=(world, _free_port(), f"fuzz:{seed}", halo, str(out)), nprocs=world, join=True)
+    res = out.read_text()
+    if res == "skip":
+        pytest.skip("deposits reach further than the halo or a strip is shorter than its halo")
+    assert res == "ok"
